@@ -1,0 +1,164 @@
+"""ctypes binding of libavocado_b200.so (the C ABI in include/avocado_b200.h).
+
+There is no fallback: if the shared library is missing the import fails loudly with the command
+that builds it, and every compute entry point needs a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libavocado_b200.so")
+
+AVO_OK = 0
+AVO_E_INVALID = -1
+AVO_E_CUDA = -2
+AVO_E_CAPACITY = -3
+AVO_E_EMPTY_SITES = -4
+AVO_E_UNSORTED = -5
+AVO_E_UNSUPPORTED = -6
+AVO_E_NOMEM = -7
+MEM_HOST, MEM_DEVICE = 0, 1
+MAX_PLOIDY = 7
+
+OP_MATCH, OP_MISMATCH, OP_INS, OP_DEL, OP_SOFTCLIP, OP_HARDCLIP = range(6)
+READ_NEGATIVE_STRAND, READ_SKIP_CALL = 1, 2
+
+STATUS_NAMES = {0: "AVO_OK", -1: "AVO_E_INVALID", -2: "AVO_E_CUDA", -3: "AVO_E_CAPACITY",
+                -4: "AVO_E_EMPTY_SITES", -5: "AVO_E_UNSORTED", -6: "AVO_E_UNSUPPORTED",
+                -7: "AVO_E_NOMEM"}
+
+P = C.c_void_p
+
+
+class ReadBatchStruct(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_bases", C.c_int64), ("n_ops", C.c_int64),
+                ("n_refb", C.c_int64), ("contig_id", C.c_int32), ("mem", C.c_int32),
+                ("start", P), ("end", P), ("mapq", P), ("flags", P), ("seq_off", P), ("bases4", P),
+                ("quals", P), ("op_off", P), ("ops", P), ("refb_off", P), ("refb4", P)]
+
+
+class SitesStruct(C.Structure):
+    _fields_ = [("n", C.c_int64), ("n_allele_nibbles", C.c_int64), ("mem", C.c_int32),
+                ("reserved", C.c_int32), ("contig", P), ("start", P), ("ref_len", P), ("alt_len", P),
+                ("allele_off", P), ("alleles4", P)]
+
+
+class CnvStruct(C.Structure):
+    _fields_ = [("n", C.c_int64), ("contig", P), ("start", P), ("end", P), ("copy_number", P)]
+
+
+class ParamsStruct(C.Structure):
+    _fields_ = [("ploidy", C.c_int32), ("score_all_sites", C.c_int32), ("max_quality", C.c_int32),
+                ("max_mapq", C.c_int32), ("min_phred_discover", C.c_int32),
+                ("min_obs_discover", C.c_int32)]
+
+
+class SitesOutStruct(C.Structure):
+    _fields_ = [("capacity", C.c_int64), ("allele_capacity", C.c_int64), ("n", C.c_int64),
+                ("n_allele_nibbles", C.c_int64), ("mem", C.c_int32), ("reserved", C.c_int32),
+                ("start", P), ("ref_len", P), ("alt_len", P), ("allele_off", P), ("alleles4", P),
+                ("count", P)]
+
+
+RESULT_COLUMNS = [
+    # name, dtype, per-site width ("ns" = n_states)
+    ("emitted", "uint8", 1), ("allele_fwd", "int32", 1), ("other_fwd", "int32", 1),
+    ("allele_cov", "int32", 1), ("other_cov", "int32", 1), ("total_cov", "int32", 1),
+    ("square_mapq", "float64", 1), ("ref_ll", "float64", "ns"), ("allele_ll", "float64", "ns"),
+    ("other_ll", "float64", "ns"), ("nonref_ll", "float64", "ns"), ("first_is_ref", "uint8", 1),
+    ("copy_number", "int32", 1), ("n_alt", "int32", 1), ("n_ref", "int32", 1), ("n_other", "int32", 1),
+    ("qual", "float64", 1), ("gq", "int32", 1), ("sb", "int32", 4), ("fisher", "float32", 1),
+    ("rms_mapq", "float32", 1), ("gl", "float64", "ns"), ("nonref_gl", "float64", "ns"),
+]
+
+
+class SiteResultsStruct(C.Structure):
+    _fields_ = [("n_sites", C.c_int64), ("n_states", C.c_int32), ("mem", C.c_int32)] + \
+               [(name, P) for name, _, _ in RESULT_COLUMNS]
+
+
+class TimingStruct(C.Structure):
+    _fields_ = [("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_discover", C.c_float),
+                ("ms_observe", C.c_float), ("ms_d2h", C.c_float), ("ms_discover_tiles", C.c_float),
+                ("ms_call_tiles", C.c_float), ("n_launches", C.c_int32),
+                ("n_tile_launches", C.c_int32), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64)]
+
+
+class TextReadsStruct(C.Structure):
+    _fields_ = [("n", C.c_int64), ("start", P), ("end", P), ("mapq", P), ("rec_flags", P),
+                ("cigar", P), ("cigar_off", P), ("md", P), ("md_off", P), ("seq", P), ("seq_off", P),
+                ("qual", P), ("qual_off", P), ("keep", P)]
+
+
+class PackedOutStruct(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_bases", C.c_int64), ("n_ops", C.c_int64),
+                ("n_refb", C.c_int64), ("start", P), ("end", P), ("mapq", P), ("flags", P),
+                ("seq_off", P), ("bases4", P), ("quals", P), ("op_off", P), ("ops", P),
+                ("refb_off", P), ("refb4", P), ("source_index", P)]
+
+
+class SynthParamsStruct(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("contig_len", C.c_int32), ("first_pos", C.c_int32),
+                ("n_reads_total", C.c_int64), ("read_len", C.c_int32), ("max_indel", C.c_int32),
+                ("snp_rate", C.c_double), ("indel_rate", C.c_double), ("triallelic_frac", C.c_double),
+                ("softclip_frac", C.c_double)]
+
+
+# every symbol declared in include/avocado_b200.h and include/avocado_b200_synth.h
+EXPORTED_SYMBOLS = [
+    "avo_ctx_create", "avo_ctx_destroy", "avo_last_error", "avo_version", "avo_ctx_set_stream",
+    "avo_get_timing", "avo_discover", "avo_call", "avo_discover_and_call",
+    "avo_pack_bounds", "avo_pack_reads", "avo_synth_default_params", "avo_synth_host",
+    "avo_synth_device",
+]
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "avocado_b200: %s is missing; there is no CPU fallback. Build it with "
+            "`make -C avocado_b200/csrc -j` or `python -c 'import __graft_entry__ as g; g.build()'`."
+            % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.avo_version.restype = C.c_char_p
+    lib.avo_last_error.restype = C.c_char_p
+    lib.avo_last_error.argtypes = [P]
+    lib.avo_ctx_create.argtypes = [C.c_int, C.POINTER(P)]
+    lib.avo_ctx_destroy.argtypes = [P]
+    lib.avo_ctx_destroy.restype = None
+    lib.avo_ctx_set_stream.argtypes = [P, P]
+    lib.avo_get_timing.argtypes = [P, C.POINTER(TimingStruct)]
+    lib.avo_discover.argtypes = [P, C.POINTER(ReadBatchStruct), C.POINTER(ParamsStruct),
+                                 C.POINTER(SitesOutStruct)]
+    lib.avo_call.argtypes = [P, C.POINTER(ReadBatchStruct), C.POINTER(SitesStruct),
+                             C.POINTER(CnvStruct), C.POINTER(ParamsStruct),
+                             C.POINTER(SiteResultsStruct)]
+    lib.avo_discover_and_call.argtypes = [P, C.POINTER(ReadBatchStruct), C.POINTER(CnvStruct),
+                                          C.POINTER(ParamsStruct), C.POINTER(SitesOutStruct),
+                                          C.POINTER(SiteResultsStruct)]
+    lib.avo_pack_bounds.argtypes = [C.POINTER(TextReadsStruct)] + [C.POINTER(C.c_int64)] * 4
+    lib.avo_pack_reads.argtypes = [C.POINTER(TextReadsStruct), C.POINTER(PackedOutStruct)]
+    lib.avo_synth_default_params.argtypes = [C.POINTER(SynthParamsStruct)]
+    lib.avo_synth_host.argtypes = [C.POINTER(SynthParamsStruct), C.c_int64, C.c_int64,
+                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                   C.POINTER(PackedOutStruct)]
+    lib.avo_synth_device.argtypes = [C.POINTER(SynthParamsStruct), C.c_int64, C.c_int64, P, P,
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                     C.POINTER(PackedOutStruct), P]
+    _lib = lib
+    return lib
+
+
+class AvocadoError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("%s: %s" % (STATUS_NAMES.get(status, status), message))
+        self.status = status

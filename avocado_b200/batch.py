@@ -1,0 +1,390 @@
+"""Columnar read batches and site tables (the data that crosses the C ABI), the host packer
+wrapper, and the synthetic generator wrappers.
+
+A :class:`ReadBatch` / :class:`SiteTable` holds either numpy arrays (host) or torch CUDA tensors
+(device); ``as_struct`` produces the ctypes struct the library consumes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from .records import AlignmentRecord, Variant
+
+NIB = "=ACMGRSVTWYHKDBN"
+_NIB_OF = {c: i for i, c in enumerate(NIB)}
+
+READ_COLUMNS = [("start", np.int32), ("end", np.int32), ("mapq", np.uint8), ("flags", np.uint8),
+                ("seq_off", np.uint32), ("bases4", np.uint8), ("quals", np.uint8),
+                ("op_off", np.uint32), ("ops", np.uint32), ("refb_off", np.uint32),
+                ("refb4", np.uint8)]
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return a.data_ptr()  # torch tensor
+
+
+def _is_device(a):
+    return not isinstance(a, np.ndarray)
+
+
+@dataclass
+class ReadBatch:
+    """Reads of one contig, sorted by start (include/avocado_b200.h: avo_read_batch)."""
+    n_reads: int
+    n_bases: int
+    n_ops: int
+    n_refb: int
+    contig_id: int = 0
+    start: object = None
+    end: object = None
+    mapq: object = None
+    flags: object = None
+    seq_off: object = None
+    bases4: object = None
+    quals: object = None
+    op_off: object = None
+    ops: object = None
+    refb_off: object = None
+    refb4: object = None
+    source_index: Optional[np.ndarray] = None
+
+    @property
+    def on_device(self):
+        return _is_device(self.start)
+
+    def as_struct(self):
+        s = L.ReadBatchStruct()
+        s.n_reads, s.n_bases, s.n_ops, s.n_refb = self.n_reads, self.n_bases, self.n_ops, self.n_refb
+        s.contig_id = self.contig_id
+        s.mem = L.MEM_DEVICE if self.on_device else L.MEM_HOST
+        for name, _ in READ_COLUMNS:
+            setattr(s, name, _ptr(getattr(self, name)))
+        return s
+
+    def nbytes(self):
+        """Bytes of the packed batch = the algorithmic bytes of one full scan."""
+        tot = 0
+        for name, _ in READ_COLUMNS:
+            a = getattr(self, name)
+            tot += a.nbytes if isinstance(a, np.ndarray) else a.numel() * a.element_size()
+        return tot
+
+    def to_device(self, device="cuda:0", pinned=False):
+        import torch
+        kw = {}
+        out = ReadBatch(self.n_reads, self.n_bases, self.n_ops, self.n_refb, self.contig_id)
+        for name, _ in READ_COLUMNS:
+            a = getattr(self, name)
+            t = torch.from_numpy(_torch_view(a))
+            setattr(out, name, t.to(device, **kw))
+        return out
+
+    def to_host(self):
+        if not self.on_device:
+            return self
+        out = ReadBatch(self.n_reads, self.n_bases, self.n_ops, self.n_refb, self.contig_id)
+        for name, dt in READ_COLUMNS:
+            setattr(out, name, _from_torch(getattr(self, name), dt))
+        return out
+
+    def slice(self, lo, hi):
+        """Host-side sub-batch of reads [lo, hi) (offsets rebased)."""
+        assert not self.on_device
+        b0, b1 = int(self.seq_off[lo]), int(self.seq_off[hi])
+        o0, o1 = int(self.op_off[lo]), int(self.op_off[hi])
+        f0, f1 = int(self.refb_off[lo]), int(self.refb_off[hi])
+        assert b0 % 2 == 0 and f0 % 2 == 0, "slices must start on byte-aligned nibble offsets"
+        out = ReadBatch(hi - lo, b1 - b0, o1 - o0, f1 - f0, self.contig_id)
+        out.start = np.ascontiguousarray(self.start[lo:hi])
+        out.end = np.ascontiguousarray(self.end[lo:hi])
+        out.mapq = np.ascontiguousarray(self.mapq[lo:hi])
+        out.flags = np.ascontiguousarray(self.flags[lo:hi])
+        out.seq_off = np.ascontiguousarray(self.seq_off[lo:hi + 1] - np.uint32(b0))
+        out.bases4 = np.ascontiguousarray(self.bases4[b0 // 2:(b1 + 1) // 2])
+        out.quals = np.ascontiguousarray(self.quals[b0:b1])
+        out.op_off = np.ascontiguousarray(self.op_off[lo:hi + 1] - np.uint32(o0))
+        out.ops = np.ascontiguousarray(self.ops[o0:o1])
+        out.refb_off = np.ascontiguousarray(self.refb_off[lo:hi + 1] - np.uint32(f0))
+        out.refb4 = np.ascontiguousarray(self.refb4[f0 // 2:(f1 + 1) // 2])
+        return out
+
+
+_TORCH_VIEW = {np.dtype(np.uint32): np.int32, np.dtype(np.uint16): np.int16}
+
+
+def _torch_view(a: np.ndarray) -> np.ndarray:
+    """torch has no uint32: reinterpret as int32 (bit pattern preserved)."""
+    v = _TORCH_VIEW.get(a.dtype)
+    return a.view(v) if v is not None else a
+
+
+def _from_torch(t, dtype) -> np.ndarray:
+    a = t.detach().cpu().numpy()
+    return a.view(dtype) if a.dtype != np.dtype(dtype) else a
+
+
+def _device_empty(n, dtype, device):
+    import torch
+    tdt = {np.int32: torch.int32, np.uint32: torch.int32, np.uint8: torch.uint8,
+           np.float64: torch.float64, np.float32: torch.float32, np.int64: torch.int64}[dtype]
+    return torch.empty(max(int(n), 1), dtype=tdt, device=device)
+
+
+# ---------------------------------------------------------------------------------------------
+# Site tables
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class SiteTable:
+    """Variant sites sorted by (contig, start, start+ref_len) (avo_sites)."""
+    n: int
+    n_allele_nibbles: int
+    start: object
+    ref_len: object
+    alt_len: object
+    allele_off: object
+    alleles4: object
+    contig: object = None
+    count: object = None
+
+    @property
+    def on_device(self):
+        return _is_device(self.start)
+
+    def as_struct(self):
+        s = L.SitesStruct()
+        s.n, s.n_allele_nibbles = self.n, self.n_allele_nibbles
+        s.mem = L.MEM_DEVICE if self.on_device else L.MEM_HOST
+        for name in ("contig", "start", "ref_len", "alt_len", "allele_off", "alleles4"):
+            setattr(s, name, _ptr(getattr(self, name)))
+        return s
+
+    def to_host(self):
+        if not self.on_device:
+            return self
+        f = _from_torch
+        return SiteTable(self.n, self.n_allele_nibbles, f(self.start, np.int32), f(self.ref_len, np.int32),
+                         f(self.alt_len, np.int32), f(self.allele_off, np.uint32), f(self.alleles4, np.uint8),
+                         None if self.contig is None else f(self.contig, np.int32),
+                         None if self.count is None else f(self.count, np.int32))
+
+    def alleles(self, i):
+        """(ref, alt) strings of site i (host tables only)."""
+        off = int(self.allele_off[i])
+        rl, al = int(self.ref_len[i]), int(self.alt_len[i])
+        s = [NIB[(self.alleles4[(off + k) >> 1] >> (0 if (off + k) & 1 else 4)) & 15] for k in range(rl + al)]
+        return "".join(s[:rl]), "".join(s[rl:])
+
+    def to_variants(self, contig_names: Sequence[str] = ("0",), contig_id=0) -> List[Variant]:
+        t = self.to_host()
+        out = []
+        for i in range(t.n):
+            ref, alt = t.alleles(i)
+            c = contig_names[int(t.contig[i])] if t.contig is not None else contig_names[contig_id]
+            out.append(Variant(c, int(t.start[i]), int(t.start[i]) + len(ref), ref, alt))
+        return out
+
+
+def sites_from_variants(variants: Sequence[Variant], contig_rank=None) -> SiteTable:
+    """Builds a host :class:`SiteTable` sorted the way ``Forest.apply`` sorts its keys
+    (TreeRegionJoin.scala:43-50: by contig, start, end).  ``contig_rank`` maps contig name -> rank
+    (default: ranks by name order, the ReferenceRegion ordering)."""
+    if contig_rank is None:
+        names = sorted({v.contigName for v in variants})
+        contig_rank = {c: i for i, c in enumerate(names)}
+    for v in variants:
+        if v.end != v.start + len(v.referenceAllele):
+            raise ValueError("variant end must equal start + len(referenceAllele): %r" % (v,))
+        if v.alternateAllele is None:
+            raise ValueError("variants to call need an alternate allele")
+    order = sorted(range(len(variants)), key=lambda i: (contig_rank[variants[i].contigName],
+                                                         variants[i].start, variants[i].end))
+    n = len(order)
+    start = np.zeros(n, np.int32)
+    ref_len = np.zeros(n, np.int32)
+    alt_len = np.zeros(n, np.int32)
+    contig = np.zeros(n, np.int32)
+    allele_off = np.zeros(n + 1, np.uint32)
+    nibs: List[int] = []
+    for k, i in enumerate(order):
+        v = variants[i]
+        start[k], ref_len[k], alt_len[k] = v.start, len(v.referenceAllele), len(v.alternateAllele)
+        contig[k] = contig_rank[v.contigName]
+        allele_off[k] = len(nibs)
+        nibs.extend(_NIB_OF.get(c, 15) for c in (v.referenceAllele + v.alternateAllele).upper())
+        if len(nibs) & 1:
+            nibs.append(0)
+    allele_off[n] = len(nibs)
+    packed = np.zeros(max(len(nibs) // 2, 1), np.uint8)
+    if nibs:
+        a = np.array(nibs, np.uint8)
+        packed[:len(nibs) // 2] = (a[0::2] << 4) | a[1::2]
+    t = SiteTable(n, len(nibs), start, ref_len, alt_len, allele_off, packed, contig)
+    t.order = order  # input index of each sorted row
+    return t
+
+
+# ---------------------------------------------------------------------------------------------
+# Packer (host): AlignmentRecords -> ReadBatch through avo_pack_reads
+# ---------------------------------------------------------------------------------------------
+def _blob(strings):
+    offs = np.zeros(len(strings) + 1, np.int64)
+    enc = [s.encode() if s is not None else b"" for s in strings]
+    np.cumsum([len(e) for e in enc], out=offs[1:])
+    return b"".join(enc), offs
+
+
+def text_columns(records: Sequence[AlignmentRecord]):
+    """The text columns avo_pack_reads consumes (also what the oracle's make_reads takes)."""
+    n = len(records)
+    start = np.array([-1 if r.start is None else r.start for r in records], np.int64).reshape(n)
+    end = np.array([-1 if r.end is None else r.end for r in records], np.int64).reshape(n)
+    mapq = np.array([-1 if r.mapq is None else r.mapq for r in records], np.int32).reshape(n)
+    flags = np.array([(1 if r.readMapped else 0) | (2 if r.readNegativeStrand else 0) |
+                      (4 if r.cigar is not None else 0) | (8 if r.mismatchingPositions is not None else 0) |
+                      (16 if r.mapq is not None else 0) for r in records], np.uint8).reshape(n)
+    cigar, cigar_off = _blob([r.cigar for r in records])
+    md, md_off = _blob([r.mismatchingPositions for r in records])
+    seq, seq_off = _blob([r.sequence for r in records])
+    qual, qual_off = _blob([r.qual for r in records])
+    return dict(start=start, end=end, mapq=mapq, flags=flags, cigar=cigar, cigar_off=cigar_off, md=md,
+                md_off=md_off, seq=seq, seq_off=seq_off, qual=qual, qual_off=qual_off)
+
+
+def pack_reads(records: Sequence[AlignmentRecord], contig_id=0, keep=None, sort=True) -> ReadBatch:
+    """Packs mapped reads of ONE contig, (stably) sorted by start, into a host ReadBatch.
+    ``keep`` optionally selects reads (the PrefilterReads predicate lives in prefilter.py)."""
+    lib = L.load()
+    idx = [i for i, r in enumerate(records) if r.readMapped and r.start is not None and
+           (keep is None or keep[i])]
+    if sort:
+        idx.sort(key=lambda i: records[i].start)   # Python's sort is stable
+    recs = [records[i] for i in idx]
+    cols = text_columns(recs)
+    t = L.TextReadsStruct()
+    t.n = len(recs)
+    keepalive = []
+    for name in ("start", "end", "mapq"):
+        setattr(t, name, cols[name].ctypes.data)
+    t.rec_flags = cols["flags"].ctypes.data
+    for name in ("cigar", "md", "seq", "qual"):
+        buf = C.create_string_buffer(cols[name], len(cols[name]) + 1)
+        keepalive.append(buf)
+        setattr(t, name, C.cast(buf, C.c_void_p).value)
+        setattr(t, name + "_off", cols[name + "_off"].ctypes.data)
+    t.keep = None
+    nr, nb, no, nf = (C.c_int64() for _ in range(4))
+    rc = lib.avo_pack_bounds(C.byref(t), C.byref(nr), C.byref(nb), C.byref(no), C.byref(nf))
+    if rc != 0:
+        raise L.AvocadoError(rc, "avo_pack_bounds failed")
+    out = L.PackedOutStruct()
+    arrs = dict(start=np.zeros(nr.value, np.int32), end=np.zeros(nr.value, np.int32),
+                mapq=np.zeros(nr.value, np.uint8), flags=np.zeros(nr.value, np.uint8),
+                seq_off=np.zeros(nr.value + 1, np.uint32), bases4=np.zeros(nb.value // 2 + 1, np.uint8),
+                quals=np.zeros(max(nb.value, 1), np.uint8), op_off=np.zeros(nr.value + 1, np.uint32),
+                ops=np.zeros(max(no.value, 1), np.uint32), refb_off=np.zeros(nr.value + 1, np.uint32),
+                refb4=np.zeros(nf.value // 2 + 1, np.uint8), source_index=np.zeros(max(nr.value, 1), np.int64))
+    out.n_reads, out.n_bases, out.n_ops, out.n_refb = nr.value, nb.value, no.value, nf.value
+    for k, a in arrs.items():
+        setattr(out, k, a.ctypes.data)
+    rc = lib.avo_pack_reads(C.byref(t), C.byref(out))
+    if rc != 0:
+        raise L.AvocadoError(rc, "avo_pack_reads failed")
+    b = ReadBatch(out.n_reads, out.n_bases, out.n_ops, out.n_refb, contig_id)
+    b.start, b.end, b.mapq, b.flags = arrs["start"], arrs["end"], arrs["mapq"], arrs["flags"]
+    b.seq_off, b.op_off, b.refb_off = arrs["seq_off"], arrs["op_off"], arrs["refb_off"]
+    b.bases4 = arrs["bases4"][:(out.n_bases + 1) // 2 or 1]
+    b.quals = arrs["quals"][:max(out.n_bases, 1)]
+    b.ops = arrs["ops"][:max(out.n_ops, 1)]
+    b.refb4 = arrs["refb4"][:(out.n_refb + 1) // 2 or 1]
+    b.source_index = np.array([idx[j] for j in arrs["source_index"][:out.n_reads]], np.int64)
+    return b
+
+
+# ---------------------------------------------------------------------------------------------
+# Synthetic generator wrappers (bench / test infrastructure)
+# ---------------------------------------------------------------------------------------------
+def synth_params(**kw) -> "L.SynthParamsStruct":
+    lib = L.load()
+    p = L.SynthParamsStruct()
+    lib.avo_synth_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError("unknown synth parameter %r" % k)
+        setattr(p, k, v)
+    return p
+
+
+def _packed_out(arrs, n, nb, no, nf):
+    out = L.PackedOutStruct()
+    out.n_reads, out.n_bases, out.n_ops, out.n_refb = n, nb, no, nf
+    for k, a in arrs.items():
+        setattr(out, k, _ptr(a))
+    out.source_index = None
+    return out
+
+
+def synth_host(p, first=0, n=None, contig_id=0) -> ReadBatch:
+    lib = L.load()
+    n = p.n_reads_total - first if n is None else n
+    no, nf = C.c_int64(), C.c_int64()
+    rc = lib.avo_synth_host(C.byref(p), first, n, C.byref(no), C.byref(nf), None)
+    if rc != 0:
+        raise L.AvocadoError(rc, "avo_synth_host(count) failed")
+    lpad = (p.read_len + 1) & ~1
+    nb = n * lpad
+    arrs = dict(start=np.zeros(n, np.int32), end=np.zeros(n, np.int32), mapq=np.zeros(n, np.uint8),
+                flags=np.zeros(n, np.uint8), seq_off=np.zeros(n + 1, np.uint32),
+                bases4=np.zeros(nb // 2 + 1, np.uint8), quals=np.zeros(max(nb, 1), np.uint8),
+                op_off=np.zeros(n + 1, np.uint32), ops=np.zeros(max(no.value, 1), np.uint32),
+                refb_off=np.zeros(n + 1, np.uint32), refb4=np.zeros(nf.value // 2 + 1, np.uint8))
+    out = _packed_out(arrs, n, nb, no.value, nf.value)
+    rc = lib.avo_synth_host(C.byref(p), first, n, None, None, C.byref(out))
+    if rc != 0:
+        raise L.AvocadoError(rc, "avo_synth_host failed")
+    b = ReadBatch(n, nb, no.value, nf.value, contig_id)
+    for k, a in arrs.items():
+        setattr(b, k, a)
+    return b
+
+
+def synth_device(p, first=0, n=None, contig_id=0, device="cuda:0") -> ReadBatch:
+    import torch
+    lib = L.load()
+    n = p.n_reads_total - first if n is None else n
+    with torch.cuda.device(device):
+        op_off = _device_empty(n + 1, np.uint32, device)
+        refb_off = _device_empty(n + 1, np.uint32, device)
+        no, nf = C.c_int64(), C.c_int64()
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = lib.avo_synth_device(C.byref(p), first, n, op_off.data_ptr(), refb_off.data_ptr(),
+                                  C.byref(no), C.byref(nf), None, stream)
+        if rc != 0:
+            raise L.AvocadoError(rc, "avo_synth_device(count) failed")
+        lpad = (p.read_len + 1) & ~1
+        nb = n * lpad
+        arrs = dict(start=_device_empty(n, np.int32, device), end=_device_empty(n, np.int32, device),
+                    mapq=_device_empty(n, np.uint8, device), flags=_device_empty(n, np.uint8, device),
+                    seq_off=_device_empty(n + 1, np.uint32, device),
+                    bases4=_device_empty(nb // 2 + 1, np.uint8, device),
+                    quals=_device_empty(nb, np.uint8, device), op_off=op_off,
+                    ops=_device_empty(no.value, np.uint32, device), refb_off=refb_off,
+                    refb4=_device_empty(nf.value // 2 + 1, np.uint8, device))
+        out = _packed_out(arrs, n, nb, no.value, nf.value)
+        rc = lib.avo_synth_device(C.byref(p), first, n, op_off.data_ptr(), refb_off.data_ptr(), None,
+                                  None, C.byref(out), stream)
+        if rc != 0:
+            raise L.AvocadoError(rc, "avo_synth_device failed")
+    b = ReadBatch(n, nb, no.value, nf.value, contig_id)
+    for k, a in arrs.items():
+        setattr(b, k, a)
+    return b

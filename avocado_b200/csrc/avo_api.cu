@@ -1,0 +1,720 @@
+// avo_api.cu -- the C ABI of include/avocado_b200.h: context, device memory, host<->device
+// staging, the score table, and the orchestration of the kernels in avo_setup.cu,
+// avo_discover.cu and avo_call.cu.  No CPU fallback exists anywhere in this file: every entry
+// point needs a CUDA device and reports AVO_E_CUDA when the runtime fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "avo_internal.h"
+
+using namespace avo;
+
+namespace {
+
+constexpr int32_t LNK_N = 1 << 16;
+
+enum Slot {
+  SL_START, SL_END, SL_MAPQ, SL_FLAGS, SL_SEQOFF, SL_BASES, SL_QUALS, SL_OPOFF, SL_OPS, SL_REFBOFF,
+  SL_REFB,
+  SL_S_CONTIG, SL_S_START, SL_S_REFLEN, SL_S_ALTLEN, SL_S_AOFF, SL_S_ALLELES, SL_S_END, SL_S_PME,
+  SL_S_COUNT,
+  SL_CNV, SL_STATS, SL_SMALL, SL_RIDX, SL_SIDX, SL_TEMP, SL_LUT,
+  SL_RES,                      // one block holding every result column
+  SL_U_START, SL_U_REFLEN, SL_U_ALTLEN, SL_U_COUNT, SL_U_SRC,
+  SL_L_POS, SL_L_LENS, SL_L_NIBS, SL_L_SRC, SL_L_HASH,
+  SL_TABLE, SL_TCOUNT, SL_KEYS_A, SL_KEYS_B, SL_VALS_A, SL_VALS_B, SL_FOOT, SL_AOFF,
+  SL_COUNT_
+};
+
+struct Buf { void* p = nullptr; size_t cap = 0; };
+
+}  // namespace
+
+struct avo_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  Buf bufs[SL_COUNT_];
+  double* d_lnk = nullptr;
+  double* d_lnfact = nullptr;
+  // score table cache key
+  int lut_minp = -1, lut_maxp = -1, lut_maxq = -1, lut_maxmq = -1;
+  avo_timing timing{};
+  cudaEvent_t ev[8] = {};
+  BatchStats* h_stats = nullptr;   // pinned
+  int32_t* h_small = nullptr;      // pinned scratch (16 ints)
+};
+
+namespace {
+
+int fail(avo_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(ctx, AVO_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define CKS(call)                                   \
+  do {                                              \
+    int s__ = (call);                               \
+    if (s__ != AVO_OK) return s__;                  \
+  } while (0)
+
+int get_buf(avo_ctx* ctx, int slot, size_t bytes, void** out) {
+  Buf& b = ctx->bufs[slot];
+  if (bytes == 0) bytes = 16;
+  if (b.cap < bytes) {
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, AVO_E_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+  }
+  *out = b.p;
+  return AVO_OK;
+}
+
+template <typename T>
+int stage_in(avo_ctx* ctx, int slot, const T* src, size_t count, int mem, const T** out) {
+  if (mem == AVO_MEM_DEVICE) { *out = src; return AVO_OK; }
+  void* d;
+  CKS(get_buf(ctx, slot, count * sizeof(T), &d));
+  if (count) {
+    CK(cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->timing.h2d_bytes += (int64_t)(count * sizeof(T));
+  }
+  *out = static_cast<const T*>(d);
+  return AVO_OK;
+}
+
+int validate_reads(avo_ctx* ctx, const avo_read_batch* r) {
+  if (!r) return fail(ctx, AVO_E_INVALID, "reads is NULL");
+  if (r->n_reads < 0 || r->n_reads >= (int64_t)INT32_MAX)
+    return fail(ctx, AVO_E_INVALID, "n_reads out of range (must be < 2^31 per batch)");
+  if (r->n_bases < 0 || r->n_bases > (int64_t)UINT32_MAX || r->n_ops < 0 ||
+      r->n_ops > (int64_t)UINT32_MAX || r->n_refb < 0 || r->n_refb > (int64_t)UINT32_MAX)
+    return fail(ctx, AVO_E_INVALID, "batch totals must fit 32-bit offsets; split the batch");
+  if (r->n_reads > 0 && (!r->start || !r->end || !r->mapq || !r->flags || !r->seq_off || !r->op_off ||
+                         !r->refb_off))
+    return fail(ctx, AVO_E_INVALID, "read batch has NULL columns");
+  if (r->mem != AVO_MEM_HOST && r->mem != AVO_MEM_DEVICE) return fail(ctx, AVO_E_INVALID, "bad reads->mem");
+  return AVO_OK;
+}
+
+int upload_reads(avo_ctx* ctx, const avo_read_batch* r, DReads* R) {
+  const size_t n = (size_t)r->n_reads;
+  R->n = r->n_reads;
+  R->contig = r->contig_id;
+  CKS(stage_in(ctx, SL_START, r->start, n, r->mem, &R->start));
+  CKS(stage_in(ctx, SL_END, r->end, n, r->mem, &R->end));
+  CKS(stage_in(ctx, SL_MAPQ, r->mapq, n, r->mem, &R->mapq));
+  CKS(stage_in(ctx, SL_FLAGS, r->flags, n, r->mem, &R->flags));
+  CKS(stage_in(ctx, SL_SEQOFF, r->seq_off, n + 1, r->mem, &R->seq_off));
+  CKS(stage_in(ctx, SL_BASES, r->bases4, (size_t)(r->n_bases + 1) / 2, r->mem, &R->bases4));
+  CKS(stage_in(ctx, SL_QUALS, r->quals, (size_t)r->n_bases, r->mem, &R->quals));
+  CKS(stage_in(ctx, SL_OPOFF, r->op_off, n + 1, r->mem, &R->op_off));
+  CKS(stage_in(ctx, SL_OPS, r->ops, (size_t)r->n_ops, r->mem, &R->ops));
+  CKS(stage_in(ctx, SL_REFBOFF, r->refb_off, n + 1, r->mem, &R->refb_off));
+  CKS(stage_in(ctx, SL_REFB, r->refb4, (size_t)(r->n_refb + 1) / 2, r->mem, &R->refb4));
+  return AVO_OK;
+}
+
+int begin_call(avo_ctx* ctx) {
+  if (!ctx) return AVO_E_INVALID;
+  ctx->err.clear();
+  CK(cudaSetDevice(ctx->device));
+  memset(&ctx->timing, 0, sizeof ctx->timing);
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  return AVO_OK;
+}
+
+float ev_ms(avo_ctx* ctx, int a, int b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+  return ms;
+}
+
+// batch statistics + sortedness (one small D2H + sync)
+int batch_stats(avo_ctx* ctx, const DReads& R, BatchStats* h) {
+  void* d;
+  CKS(get_buf(ctx, SL_STATS, sizeof(BatchStats), &d));
+  CK(launch_batch_stats(R, (BatchStats*)d, ctx->stream));
+  ctx->timing.n_launches += (R.n > 0) ? 2 : 1;
+  CK(cudaMemcpyAsync(ctx->h_stats, d, sizeof(BatchStats), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *h = *ctx->h_stats;
+  if (R.n == 0) { h->min_start = 0; h->max_end = 0; h->max_span = 0; }
+  if (h->unsorted) return fail(ctx, AVO_E_UNSORTED, "reads are not sorted by start");
+  return AVO_OK;
+}
+
+// The score table of ScoredObservation.createScores (ScoredObservation.scala:101-165) reduced to
+// what the join can reach: L[g] = ln((m-g) eps + g (1-eps)), eps = 1 - s_map s_base
+// (Observer.scala:151-185), for m in minPloidy..maxPloidy, q in 0..maxQ, mq in 0..maxMapQ.  Built
+// with the host libm so that table values do not depend on the device's log/pow.
+int ensure_lut(avo_ctx* ctx, int minp, int maxp, int maxq, int maxmq, const double** out) {
+  const int ns = maxp + 1;
+  const size_t count = (size_t)(maxp - minp + 1) * (maxq + 1) * (maxmq + 1) * ns;
+  void* d;
+  if (ctx->lut_minp == minp && ctx->lut_maxp == maxp && ctx->lut_maxq == maxq &&
+      ctx->lut_maxmq == maxmq && ctx->bufs[SL_LUT].p) {
+    *out = (const double*)ctx->bufs[SL_LUT].p;
+    return AVO_OK;
+  }
+  CKS(get_buf(ctx, SL_LUT, count * sizeof(double), &d));
+  std::vector<double> lut(count);
+  for (int m = minp; m <= maxp; ++m)
+    for (int q = 0; q <= maxq; ++q)
+      for (int mq = 0; mq <= maxmq; ++mq) {
+        const double s_map = 1.0 - std::pow(10.0, -(double)mq / 10.0);   // PhredUtils (ADAM)
+        const double s_base = 1.0 - std::pow(10.0, -(double)q / 10.0);
+        const double ome = s_map * s_base;
+        const double eps = 1.0 - ome;
+        double* row = &lut[((((size_t)(m - minp) * (maxq + 1) + q) * (maxmq + 1)) + mq) * ns];
+        for (int g = 0; g < ns; ++g)
+          row[g] = (g <= m && m > 0) ? std::log((m - g) * eps + g * ome) : 0.0;
+      }
+  CK(cudaMemcpyAsync(d, lut.data(), count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));   // `lut` goes out of scope
+  ctx->lut_minp = minp; ctx->lut_maxp = maxp; ctx->lut_maxq = maxq; ctx->lut_maxmq = maxmq;
+  *out = (const double*)d;
+  return AVO_OK;
+}
+
+// ---- device-resident site table ------------------------------------------------------------------
+struct DevSites {
+  int32_t n = 0;
+  uint32_t n_nibbles = 0;
+  const int32_t* contig = nullptr;
+  const int32_t* start = nullptr;
+  const int32_t* ref_len = nullptr;
+  const int32_t* alt_len = nullptr;
+  const uint32_t* allele_off = nullptr;
+  const uint8_t* alleles4 = nullptr;
+  const int32_t* count = nullptr;
+};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct ResLayout {
+  size_t off[24];
+  size_t total;
+};
+
+// one allocation holding all result columns (order = avo_site_results fields)
+ResLayout res_layout(int64_t n, int ns) {
+  const size_t sz[24] = {
+      (size_t)n,                                   // emitted u8
+      (size_t)n * 4, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4,  // 5 x i32
+      (size_t)n * 8,                               // square_mapq
+      (size_t)n * ns * 8, (size_t)n * ns * 8, (size_t)n * ns * 8, (size_t)n * ns * 8,  // 4 x ll
+      (size_t)n,                                   // first_is_ref
+      (size_t)n * 4,                               // copy_number
+      (size_t)n * 4, (size_t)n * 4, (size_t)n * 4, // n_alt n_ref n_other
+      (size_t)n * 8,                               // qual
+      (size_t)n * 4,                               // gq
+      (size_t)n * 16,                              // sb
+      (size_t)n * 4, (size_t)n * 4,                // fisher rms
+      (size_t)n * ns * 8, (size_t)n * ns * 8,      // gl nonref_gl
+      0};
+  ResLayout L;
+  size_t o = 0;
+  for (int i = 0; i < 23; ++i) { L.off[i] = o; o += align_up(sz[i], 256); }
+  L.off[23] = o;
+  L.total = o;
+  return L;
+}
+
+void res_pointers(void* base, const ResLayout& L, int ns, DResults* D) {
+  char* b = (char*)base;
+  D->ns = ns;
+  D->emitted = (uint8_t*)(b + L.off[0]);
+  D->allele_fwd = (int32_t*)(b + L.off[1]); D->other_fwd = (int32_t*)(b + L.off[2]);
+  D->allele_cov = (int32_t*)(b + L.off[3]); D->other_cov = (int32_t*)(b + L.off[4]);
+  D->total_cov = (int32_t*)(b + L.off[5]);
+  D->square_mapq = (double*)(b + L.off[6]);
+  D->ref_ll = (double*)(b + L.off[7]); D->allele_ll = (double*)(b + L.off[8]);
+  D->other_ll = (double*)(b + L.off[9]); D->nonref_ll = (double*)(b + L.off[10]);
+  D->first_is_ref = (uint8_t*)(b + L.off[11]);
+  D->copy_number = (int32_t*)(b + L.off[12]);
+  D->n_alt = (int32_t*)(b + L.off[13]); D->n_ref = (int32_t*)(b + L.off[14]);
+  D->n_other = (int32_t*)(b + L.off[15]);
+  D->qual = (double*)(b + L.off[16]);
+  D->gq = (int32_t*)(b + L.off[17]);
+  D->sb = (int32_t*)(b + L.off[18]);
+  D->fisher = (float*)(b + L.off[19]); D->rms_mapq = (float*)(b + L.off[20]);
+  D->gl = (double*)(b + L.off[21]); D->nonref_gl = (double*)(b + L.off[22]);
+}
+
+int check_results(avo_ctx* ctx, const avo_site_results* o) {
+  if (!o) return fail(ctx, AVO_E_INVALID, "results is NULL");
+  if (!o->emitted || !o->allele_fwd || !o->other_fwd || !o->allele_cov || !o->other_cov ||
+      !o->total_cov || !o->square_mapq || !o->ref_ll || !o->allele_ll || !o->other_ll ||
+      !o->nonref_ll || !o->first_is_ref || !o->copy_number || !o->n_alt || !o->n_ref ||
+      !o->n_other || !o->qual || !o->gq || !o->sb || !o->fisher || !o->rms_mapq || !o->gl ||
+      !o->nonref_gl)
+    return fail(ctx, AVO_E_INVALID, "results has NULL columns");
+  return AVO_OK;
+}
+
+// copy the device result block into the caller's arrays (host or device)
+int export_results(avo_ctx* ctx, const DResults& D, int64_t n, int ns, avo_site_results* o) {
+  const cudaMemcpyKind kind = (o->mem == AVO_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  struct { void* dst; const void* src; size_t bytes; } c[] = {
+      {o->emitted, D.emitted, (size_t)n}, {o->allele_fwd, D.allele_fwd, (size_t)n * 4},
+      {o->other_fwd, D.other_fwd, (size_t)n * 4}, {o->allele_cov, D.allele_cov, (size_t)n * 4},
+      {o->other_cov, D.other_cov, (size_t)n * 4}, {o->total_cov, D.total_cov, (size_t)n * 4},
+      {o->square_mapq, D.square_mapq, (size_t)n * 8}, {o->ref_ll, D.ref_ll, (size_t)n * ns * 8},
+      {o->allele_ll, D.allele_ll, (size_t)n * ns * 8}, {o->other_ll, D.other_ll, (size_t)n * ns * 8},
+      {o->nonref_ll, D.nonref_ll, (size_t)n * ns * 8}, {o->first_is_ref, D.first_is_ref, (size_t)n},
+      {o->copy_number, D.copy_number, (size_t)n * 4}, {o->n_alt, D.n_alt, (size_t)n * 4},
+      {o->n_ref, D.n_ref, (size_t)n * 4}, {o->n_other, D.n_other, (size_t)n * 4},
+      {o->qual, D.qual, (size_t)n * 8}, {o->gq, D.gq, (size_t)n * 4}, {o->sb, D.sb, (size_t)n * 16},
+      {o->fisher, D.fisher, (size_t)n * 4}, {o->rms_mapq, D.rms_mapq, (size_t)n * 4},
+      {o->gl, D.gl, (size_t)n * ns * 8}, {o->nonref_gl, D.nonref_gl, (size_t)n * ns * 8}};
+  for (auto& x : c) {
+    if (x.bytes == 0) continue;
+    CK(cudaMemcpyAsync(x.dst, x.src, x.bytes, kind, ctx->stream));
+    if (kind == cudaMemcpyDeviceToHost) ctx->timing.d2h_bytes += (int64_t)x.bytes;
+  }
+  return AVO_OK;
+}
+
+int check_params(avo_ctx* ctx, const avo_params* p) {
+  if (!p) return fail(ctx, AVO_E_INVALID, "params is NULL");
+  if (p->ploidy < 1 || p->ploidy > AVO_MAX_PLOIDY)
+    return fail(ctx, AVO_E_UNSUPPORTED, "ploidy %d outside 1..%d", p->ploidy, AVO_MAX_PLOIDY);
+  if (p->max_quality < 1 || p->max_quality > 127 || p->max_mapq < 1 || p->max_mapq > 127)
+    return fail(ctx, AVO_E_UNSUPPORTED, "max_quality / max_mapq must be in 1..127");
+  if (p->score_all_sites)
+    return fail(ctx, AVO_E_UNSUPPORTED, "score_all_sites (gVCF mode) is not built yet");
+  return AVO_OK;
+}
+
+// BiallelicGenotyper.call against a device-resident site table.
+int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const DevSites& T,
+                  const avo_cnv* cnv, const avo_params* p, avo_site_results* out) {
+  if (T.n == 0)
+    return fail(ctx, AVO_E_EMPTY_SITES,
+                "empty variant set: the reference throws here (TreeRegionJoin.scala:77)");
+  // copy-number map: ploidy range over ALL CNVs (CopyNumberMap.min/maxPloidy), list of this contig
+  int minp = p->ploidy, maxp = p->ploidy;
+  std::vector<int32_t> cs, ce, cc;
+  if (cnv && cnv->n > 0) {
+    if (!cnv->contig || !cnv->start || !cnv->end || !cnv->copy_number)
+      return fail(ctx, AVO_E_INVALID, "cnv has NULL columns");
+    for (int64_t i = 0; i < cnv->n; ++i) {
+      minp = std::min(minp, cnv->copy_number[i]);
+      maxp = std::max(maxp, cnv->copy_number[i]);
+      if (cnv->contig[i] == R.contig) {
+        cs.push_back(cnv->start[i]); ce.push_back(cnv->end[i]); cc.push_back(cnv->copy_number[i]);
+      }
+    }
+  }
+  if (minp < 1 || maxp > AVO_MAX_PLOIDY)
+    return fail(ctx, AVO_E_UNSUPPORTED, "copy numbers must stay within 1..%d", AVO_MAX_PLOIDY);
+  const int ns = maxp + 1;
+  if (out->n_states != ns)
+    return fail(ctx, AVO_E_INVALID, "results->n_states must be max ploidy + 1 = %d", ns);
+  if (out->n_sites != T.n) return fail(ctx, AVO_E_INVALID, "results->n_sites != number of sites");
+
+  DCnv C{};
+  C.n = (int32_t)cs.size();
+  if (C.n) {
+    void* d;
+    CKS(get_buf(ctx, SL_CNV, (size_t)C.n * 12, &d));
+    int32_t* b = (int32_t*)d;
+    CK(cudaMemcpyAsync(b, cs.data(), (size_t)C.n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(b + C.n, ce.data(), (size_t)C.n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(b + 2 * C.n, cc.data(), (size_t)C.n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    C.start = b; C.end = b + C.n; C.cn = b + 2 * C.n;
+  }
+
+  DCallParams P{};
+  P.base_ploidy = p->ploidy; P.min_ploidy = minp; P.max_ploidy = maxp; P.ns = ns;
+  P.max_quality = p->max_quality; P.max_mapq = p->max_mapq;
+  CKS(ensure_lut(ctx, minp, maxp, p->max_quality, p->max_mapq, &P.lut));
+  P.lnk = ctx->d_lnk; P.lnfact = ctx->d_lnfact; P.lnk_n = LNK_N;
+  P.ten_div_log10 = 10.0 / std::log(10.0);
+  P.log10 = std::log(10.0);
+
+  // derived site columns + sortedness + contig range
+  DSites S{};
+  S.n = T.n;
+  S.contig = T.contig; S.start = T.start; S.ref_len = T.ref_len; S.alt_len = T.alt_len;
+  S.allele_off = T.allele_off; S.alleles4 = T.alleles4;
+  void *d_end, *d_pme, *d_small, *d_temp;
+  CKS(get_buf(ctx, SL_S_END, (size_t)T.n * 4, &d_end));
+  CKS(get_buf(ctx, SL_S_PME, (size_t)T.n * 4, &d_pme));
+  CKS(get_buf(ctx, SL_SMALL, 64, &d_small));
+  const size_t tb = site_setup_temp_bytes(T.n);
+  CKS(get_buf(ctx, SL_TEMP, tb, &d_temp));
+  int32_t* small = (int32_t*)d_small;   // [0] unsorted, [1..2] contig range, [4..5] s_range
+  CK(launch_site_setup(T.n, T.contig, T.start, T.ref_len, (int32_t*)d_end, (int32_t*)d_pme, small,
+                       d_temp, tb, ctx->stream));
+  CK(launch_contig_range(T.n, T.contig, R.contig, small + 1, ctx->stream));
+  ctx->timing.n_launches += 3;
+  CK(cudaMemcpyAsync(ctx->h_small, small, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_small[0]) return fail(ctx, AVO_E_UNSORTED, "sites are not sorted by (contig, start, end)");
+  S.c_lo = ctx->h_small[1]; S.c_hi = ctx->h_small[2];
+  S.end = (const int32_t*)d_end; S.pme = (const int32_t*)d_pme;
+  int mp = 1;                                                  // TreeRegionJoin.scala:66-72
+  while (!(2 * (int64_t)mp >= (int64_t)S.n)) mp *= 2;
+  S.midpoint = mp;
+
+  // coarse index
+  const int32_t nb = index_bins(hs);
+  void *d_ridx, *d_sidx;
+  CKS(get_buf(ctx, SL_RIDX, (size_t)(nb + 1) * 4, &d_ridx));
+  CKS(get_buf(ctx, SL_SIDX, (size_t)(nb + 1) * 4, &d_sidx));
+  CK(launch_build_index(R, S, hs, (int32_t*)d_ridx, (int32_t*)d_sidx, small + 4, ctx->stream));
+  ctx->timing.n_launches += 1;
+  DIndex X{hs.min_start, nb, (const int32_t*)d_ridx, (const int32_t*)d_sidx, small + 4};
+
+  // results block (zeroed: untouched sites are "not emitted")
+  const ResLayout L = res_layout(T.n, ns);
+  void* d_res;
+  CKS(get_buf(ctx, SL_RES, L.total, &d_res));
+  CK(cudaMemsetAsync(d_res, 0, L.total, ctx->stream));
+  DResults D;
+  res_pointers(d_res, L, ns, &D);
+
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  int nl = 0;
+  CK(launch_call_tiles(R, S, C, P, D, X, hs, small + 8, ctx->num_sms, ctx->stream, &nl));
+  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  ctx->timing.n_launches += nl;
+  ctx->timing.n_tile_launches += nl;
+  CKS(export_results(ctx, D, T.n, ns, out));
+  return AVO_OK;
+}
+
+// DiscoverVariants on a device batch; leaves the sorted site table in ctx buffers.
+int discover_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const avo_params* p,
+                      DevSites* T) {
+  void *d_small, *d_ridx;
+  CKS(get_buf(ctx, SL_SMALL, 64, &d_small));
+  int32_t* small = (int32_t*)d_small;   // [8] tile counter, [10] out.n, [11] indel n
+  const int32_t nb = index_bins(hs);
+  CKS(get_buf(ctx, SL_RIDX, (size_t)(nb + 1) * 4, &d_ridx));
+  DSites none{};
+  CK(launch_build_index(R, none, hs, (int32_t*)d_ridx, nullptr, nullptr, ctx->stream));
+  ctx->timing.n_launches += 1;
+  DIndex X{hs.min_start, nb, (const int32_t*)d_ridx, nullptr, nullptr};
+
+  int64_t ucap = std::max<int64_t>(1 << 16, R.n / 8);
+  int64_t lcap = std::max<int64_t>(1 << 16, R.n / 8);
+  DDiscoverOut U{};
+  DIndelList Lst{};
+  int32_t n_out = 0, n_indel = 0;
+  for (int attempt = 0;; ++attempt) {
+    if (attempt > 3) return fail(ctx, AVO_E_NOMEM, "discovery buffers kept overflowing");
+    void* q;
+    U.capacity = (int32_t)std::min<int64_t>(ucap, INT32_MAX);
+    CKS(get_buf(ctx, SL_U_START, (size_t)ucap * 4, &q)); U.start = (int32_t*)q;
+    CKS(get_buf(ctx, SL_U_REFLEN, (size_t)ucap * 4, &q)); U.ref_len = (int32_t*)q;
+    CKS(get_buf(ctx, SL_U_ALTLEN, (size_t)ucap * 4, &q)); U.alt_len = (int32_t*)q;
+    CKS(get_buf(ctx, SL_U_COUNT, (size_t)ucap * 4, &q)); U.count = (int32_t*)q;
+    CKS(get_buf(ctx, SL_U_SRC, (size_t)ucap * 8, &q)); U.src = (uint64_t*)q;
+    U.n = small + 10;
+    Lst.capacity = (int32_t)std::min<int64_t>(lcap, INT32_MAX);
+    CKS(get_buf(ctx, SL_L_POS, (size_t)lcap * 4, &q)); Lst.pos = (int32_t*)q;
+    CKS(get_buf(ctx, SL_L_LENS, (size_t)lcap * 4, &q)); Lst.lens = (uint32_t*)q;
+    CKS(get_buf(ctx, SL_L_NIBS, (size_t)lcap * 4, &q)); Lst.nibs = (uint32_t*)q;
+    CKS(get_buf(ctx, SL_L_SRC, (size_t)lcap * 4, &q)); Lst.src = (uint32_t*)q;
+    CKS(get_buf(ctx, SL_L_HASH, (size_t)lcap * 4, &q)); Lst.hash = (uint32_t*)q;
+    Lst.n = small + 11;
+    CK(cudaMemsetAsync(small + 8, 0, 4 * sizeof(int32_t), ctx->stream));
+
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    int nl = 0;
+    CK(launch_discover_tiles(R, p->min_phred_discover, p->min_obs_discover, X, hs, U, Lst, small + 8,
+                             ctx->num_sms, ctx->stream, &nl));
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->timing.n_launches += nl;
+    ctx->timing.n_tile_launches += nl;
+    CK(cudaMemcpyAsync(ctx->h_small, small + 10, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    n_out = ctx->h_small[0];
+    n_indel = ctx->h_small[1];
+    // the indel pass can add at most n_indel survivors
+    const int64_t need_u = (int64_t)n_out + (int64_t)n_indel;
+    if (need_u > ucap || n_indel > lcap) {
+      ucap = std::max(ucap, need_u + need_u / 8 + 1024);
+      lcap = std::max<int64_t>(lcap, (int64_t)n_indel + n_indel / 8 + 1024);
+      continue;
+    }
+    break;
+  }
+
+  if (n_indel > 0) {
+    uint32_t tsize = 1024;
+    while (tsize < 2u * (uint32_t)n_indel) tsize <<= 1;
+    void *d_table, *d_tcount;
+    CKS(get_buf(ctx, SL_TABLE, (size_t)tsize * 8, &d_table));
+    CKS(get_buf(ctx, SL_TCOUNT, (size_t)tsize * 4, &d_tcount));
+    int nl = 0;
+    CK(launch_indel_group(R, Lst, n_indel, (unsigned long long*)d_table, (int32_t*)d_tcount, tsize,
+                          p->min_obs_discover, U, ctx->stream, &nl));
+    ctx->timing.n_launches += nl;
+    CK(cudaMemcpyAsync(ctx->h_small, small + 10, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    n_out = ctx->h_small[0];
+  }
+
+  // sort + materialise
+  T->n = n_out;
+  T->n_nibbles = 0;
+  T->contig = nullptr;
+  if (n_out == 0) return AVO_OK;
+  void *ka, *kb, *va, *vb, *foot, *aoff, *temp;
+  CKS(get_buf(ctx, SL_KEYS_A, (size_t)n_out * 8, &ka));
+  CKS(get_buf(ctx, SL_KEYS_B, (size_t)n_out * 8, &kb));
+  CKS(get_buf(ctx, SL_VALS_A, (size_t)n_out * 4, &va));
+  CKS(get_buf(ctx, SL_VALS_B, (size_t)n_out * 4, &vb));
+  CKS(get_buf(ctx, SL_FOOT, (size_t)n_out * 4, &foot));
+  CKS(get_buf(ctx, SL_AOFF, (size_t)n_out * 4, &aoff));
+  const size_t tb = assemble_temp_bytes(n_out);
+  CKS(get_buf(ctx, SL_TEMP, tb, &temp));
+  int nl = 0;
+  CK(launch_assemble_sites(R, Lst, U, n_out, (unsigned long long*)ka, (unsigned long long*)kb,
+                           (int32_t*)va, (int32_t*)vb, (uint32_t*)foot, (uint32_t*)aoff, temp, tb,
+                           ctx->stream, &nl));
+  // total nibbles = aoff[n-1] + foot[n-1]
+  uint32_t* h2 = (uint32_t*)ctx->h_small;
+  CK(cudaMemcpyAsync(h2, (uint32_t*)aoff + (n_out - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h2 + 1, (uint32_t*)foot + (n_out - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const uint32_t total = h2[0] + h2[1];
+  void *o_start, *o_ref, *o_alt, *o_aoff, *o_all, *o_cnt;
+  CKS(get_buf(ctx, SL_S_START, (size_t)n_out * 4, &o_start));
+  CKS(get_buf(ctx, SL_S_REFLEN, (size_t)n_out * 4, &o_ref));
+  CKS(get_buf(ctx, SL_S_ALTLEN, (size_t)n_out * 4, &o_alt));
+  CKS(get_buf(ctx, SL_S_AOFF, (size_t)(n_out + 1) * 4, &o_aoff));
+  CKS(get_buf(ctx, SL_S_ALLELES, (size_t)total / 2 + 16, &o_all));
+  CKS(get_buf(ctx, SL_S_COUNT, (size_t)n_out * 4, &o_cnt));
+  CK(launch_fill_sites(R, Lst, U, n_out, (const int32_t*)vb, (const uint32_t*)aoff, (int32_t*)o_start,
+                       (int32_t*)o_ref, (int32_t*)o_alt, (uint32_t*)o_aoff, (uint8_t*)o_all,
+                       (int32_t*)o_cnt, total, ctx->stream, &nl));
+  ctx->timing.n_launches += nl;
+  T->n_nibbles = total;
+  T->start = (const int32_t*)o_start; T->ref_len = (const int32_t*)o_ref;
+  T->alt_len = (const int32_t*)o_alt; T->allele_off = (const uint32_t*)o_aoff;
+  T->alleles4 = (const uint8_t*)o_all; T->count = (const int32_t*)o_cnt;
+  return AVO_OK;
+}
+
+int export_sites(avo_ctx* ctx, const DevSites& T, avo_sites_out* o) {
+  if (!o) return fail(ctx, AVO_E_INVALID, "sites_out is NULL");
+  const bool fits = (int64_t)T.n <= o->capacity && (int64_t)T.n_nibbles <= o->allele_capacity;
+  o->n = T.n;
+  o->n_allele_nibbles = T.n_nibbles;
+  if (!fits)
+    return fail(ctx, AVO_E_CAPACITY, "sites_out too small: need %d entries, %u allele nibbles", T.n,
+                T.n_nibbles);
+  if (T.n == 0) return AVO_OK;
+  if (!o->start || !o->ref_len || !o->alt_len || !o->allele_off || !o->alleles4)
+    return fail(ctx, AVO_E_INVALID, "sites_out has NULL columns");
+  const cudaMemcpyKind kind = (o->mem == AVO_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  const size_t n = (size_t)T.n;
+  CK(cudaMemcpyAsync(o->start, T.start, n * 4, kind, ctx->stream));
+  CK(cudaMemcpyAsync(o->ref_len, T.ref_len, n * 4, kind, ctx->stream));
+  CK(cudaMemcpyAsync(o->alt_len, T.alt_len, n * 4, kind, ctx->stream));
+  CK(cudaMemcpyAsync(o->allele_off, T.allele_off, (n + 1) * 4, kind, ctx->stream));
+  CK(cudaMemcpyAsync(o->alleles4, T.alleles4, ((size_t)T.n_nibbles + 1) / 2, kind, ctx->stream));
+  if (o->count) CK(cudaMemcpyAsync(o->count, T.count, n * 4, kind, ctx->stream));
+  if (kind == cudaMemcpyDeviceToHost)
+    ctx->timing.d2h_bytes += (int64_t)(n * 16 + 4 + ((size_t)T.n_nibbles + 1) / 2 + (o->count ? n * 4 : 0));
+  return AVO_OK;
+}
+
+int finish_call(avo_ctx* ctx, bool did_discover, bool did_call) {
+  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  avo_timing& t = ctx->timing;
+  t.ms_total = ev_ms(ctx, 0, 7);
+  t.ms_h2d = ev_ms(ctx, 0, 1);
+  if (did_discover) t.ms_discover = ev_ms(ctx, 1, 6);
+  if (did_call) t.ms_observe = did_discover ? ev_ms(ctx, 6, 5) : ev_ms(ctx, 1, 5);
+  if (did_discover) t.ms_discover_tiles = ev_ms(ctx, 2, 3);
+  if (did_call) t.ms_call_tiles = ev_ms(ctx, 4, 5);
+  t.ms_d2h = did_call ? ev_ms(ctx, 5, 7) : ev_ms(ctx, 6, 7);
+  return AVO_OK;
+}
+
+}  // namespace
+
+// ---- public entry points -------------------------------------------------------------------------
+extern "C" {
+
+const char* avo_version(void) { return "avocado_b200 0.1 (sm_100a)"; }
+
+int avo_ctx_create(int device, avo_ctx** out) {
+  if (!out) return AVO_E_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || device < 0 || device >= count) { cudaGetLastError(); return AVO_E_CUDA; }
+  avo_ctx* ctx = new (std::nothrow) avo_ctx();
+  if (!ctx) return AVO_E_NOMEM;
+  ctx->device = device;
+  auto bail = [&](int code) { avo_ctx_destroy(ctx); return code; };
+  if (cudaSetDevice(device) != cudaSuccess) return bail(AVO_E_CUDA);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(AVO_E_CUDA);
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(AVO_E_CUDA);
+  ctx->stream = ctx->own_stream;
+  for (auto& ev : ctx->ev)
+    if (cudaEventCreate(&ev) != cudaSuccess) return bail(AVO_E_CUDA);
+  if (cudaMallocHost(&ctx->h_stats, sizeof(BatchStats)) != cudaSuccess) return bail(AVO_E_CUDA);
+  if (cudaMallocHost(&ctx->h_small, 16 * sizeof(int32_t)) != cudaSuccess) return bail(AVO_E_CUDA);
+  // ln table (host libm) and logFactorial table (device, reference summation order)
+  std::vector<double> lnk(LNK_N);
+  lnk[0] = 0.0;
+  for (int k = 1; k < LNK_N; ++k) lnk[k] = std::log((double)k);
+  if (cudaMalloc(&ctx->d_lnk, LNK_N * sizeof(double)) != cudaSuccess) return bail(AVO_E_NOMEM);
+  if (cudaMalloc(&ctx->d_lnfact, LNK_N * sizeof(double)) != cudaSuccess) return bail(AVO_E_NOMEM);
+  if (cudaMemcpy(ctx->d_lnk, lnk.data(), LNK_N * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+    return bail(AVO_E_CUDA);
+  if (launch_lnfact_table(ctx->d_lnk, ctx->d_lnfact, LNK_N, ctx->stream) != cudaSuccess) return bail(AVO_E_CUDA);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return bail(AVO_E_CUDA);
+  *out = ctx;
+  return AVO_OK;
+}
+
+void avo_ctx_destroy(avo_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto& b : ctx->bufs) if (b.p) cudaFree(b.p);
+  if (ctx->d_lnk) cudaFree(ctx->d_lnk);
+  if (ctx->d_lnfact) cudaFree(ctx->d_lnfact);
+  if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
+  if (ctx->h_small) cudaFreeHost(ctx->h_small);
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  cudaGetLastError();
+  delete ctx;
+}
+
+const char* avo_last_error(const avo_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int avo_ctx_set_stream(avo_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return AVO_E_INVALID;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return AVO_OK;
+}
+
+int avo_get_timing(const avo_ctx* ctx, avo_timing* out) {
+  if (!ctx || !out) return AVO_E_INVALID;
+  *out = ctx->timing;
+  return AVO_OK;
+}
+
+int avo_discover(avo_ctx* ctx, const avo_read_batch* reads, const avo_params* params,
+                 avo_sites_out* out) {
+  CKS(begin_call(ctx));
+  CKS(validate_reads(ctx, reads));
+  if (!params) return fail(ctx, AVO_E_INVALID, "params is NULL");
+  DReads R;
+  CKS(upload_reads(ctx, reads, &R));
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  BatchStats hs;
+  CKS(batch_stats(ctx, R, &hs));
+  DevSites T;
+  CKS(discover_internal(ctx, R, hs, params, &T));
+  CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  const int rc = export_sites(ctx, T, out);
+  CKS(finish_call(ctx, true, false));
+  return rc;
+}
+
+int avo_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_sites* sites, const avo_cnv* cnv,
+             const avo_params* params, avo_site_results* out) {
+  CKS(begin_call(ctx));
+  CKS(validate_reads(ctx, reads));
+  CKS(check_params(ctx, params));
+  CKS(check_results(ctx, out));
+  if (!sites) return fail(ctx, AVO_E_INVALID, "sites is NULL");
+  if (sites->n < 0 || sites->n >= INT32_MAX) return fail(ctx, AVO_E_INVALID, "sites->n out of range");
+  if (sites->n == 0)
+    return fail(ctx, AVO_E_EMPTY_SITES,
+                "empty variant set: the reference throws here (TreeRegionJoin.scala:77)");
+  if (!sites->start || !sites->ref_len || !sites->alt_len || !sites->allele_off || !sites->alleles4)
+    return fail(ctx, AVO_E_INVALID, "sites has NULL columns");
+  DReads R;
+  CKS(upload_reads(ctx, reads, &R));
+  DevSites T;
+  T.n = (int32_t)sites->n;
+  T.n_nibbles = (uint32_t)sites->n_allele_nibbles;
+  const size_t n = (size_t)sites->n;
+  if (sites->contig) CKS(stage_in(ctx, SL_S_CONTIG, sites->contig, n, sites->mem, &T.contig));
+  CKS(stage_in(ctx, SL_S_START, sites->start, n, sites->mem, &T.start));
+  CKS(stage_in(ctx, SL_S_REFLEN, sites->ref_len, n, sites->mem, &T.ref_len));
+  CKS(stage_in(ctx, SL_S_ALTLEN, sites->alt_len, n, sites->mem, &T.alt_len));
+  CKS(stage_in(ctx, SL_S_AOFF, sites->allele_off, n + 1, sites->mem, &T.allele_off));
+  CKS(stage_in(ctx, SL_S_ALLELES, sites->alleles4, (size_t)(sites->n_allele_nibbles + 1) / 2,
+               sites->mem, &T.alleles4));
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  BatchStats hs;
+  CKS(batch_stats(ctx, R, &hs));
+  CKS(call_internal(ctx, R, hs, T, cnv, params, out));
+  CKS(finish_call(ctx, false, true));
+  return AVO_OK;
+}
+
+int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_cnv* cnv,
+                          const avo_params* params, avo_sites_out* sites_out,
+                          avo_site_results* results) {
+  CKS(begin_call(ctx));
+  CKS(validate_reads(ctx, reads));
+  CKS(check_params(ctx, params));
+  CKS(check_results(ctx, results));
+  DReads R;
+  CKS(upload_reads(ctx, reads, &R));
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  BatchStats hs;
+  CKS(batch_stats(ctx, R, &hs));
+  DevSites T;
+  CKS(discover_internal(ctx, R, hs, params, &T));
+  CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  const int64_t cap = results->n_sites;
+  results->n_sites = T.n;
+  int rc = export_sites(ctx, T, sites_out);
+  if (rc == AVO_OK && cap < T.n)
+    rc = fail(ctx, AVO_E_CAPACITY, "results too small: need %d rows", T.n);
+  if (rc != AVO_OK) { finish_call(ctx, true, false); return rc; }
+  if (T.n == 0) {
+    finish_call(ctx, true, false);
+    return fail(ctx, AVO_E_EMPTY_SITES,
+                "no variants discovered: the reference throws here (TreeRegionJoin.scala:77)");
+  }
+  CKS(call_internal(ctx, R, hs, T, cnv, params, results));
+  CKS(finish_call(ctx, true, true));
+  return AVO_OK;
+}
+
+}  // extern "C"

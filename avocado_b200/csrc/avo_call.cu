@@ -1,0 +1,507 @@
+// avo_call.cu -- BiallelicGenotyper.call on the GPU: read<->site join, per-read observation and
+// site classification, score lookup, per-site reduction and genotype emission in ONE kernel.
+//
+// Reference semantics (file:line under avocado-core/src/main/scala/org/bdgenomics/avocado/):
+//   join            util/TreeRegionJoin.scala:74-119, 175-203        -> forest_get (avo_device.cuh)
+//   observations    genotyping/Observer.scala:48-140                 -> classify()
+//   classification  genotyping/BiallelicGenotyper.scala:195-393      -> classify(), process_read()
+//   scoring         genotyping/ScoredObservation.scala:45-90, BG:444-472  -> LUT built by the host
+//   reduction       BG:475-500                                        -> phase B below
+//   genotype        BG:579-797, util/LogPhred.scala:38-40             -> finalize_site()
+//
+// Layout of the work (DESIGN.md "call kernel"): the genome is cut into windows of CALL_W bases; a
+// CTA that takes window w OWNS the sites whose start lies in it, and walks every read that can
+// overlap one of them (reads are sorted by start, so that is one contiguous index range, found by
+// binary search, including a look-back of max read span).  Because each site is reduced by exactly
+// one CTA, in read order, the fp64 likelihood sums are produced in the batch's read order --
+// the same order the oracle uses -- and no atomics or cross-CTA combine are needed.
+#include <cub/block/block_scan.cuh>
+
+#include "avo_device.cuh"
+
+namespace avo {
+
+constexpr int CALL_THREADS = 256;
+constexpr int CALL_WARPS = CALL_THREADS / 32;
+constexpr int CALL_W = 4096;        // window width in bases
+constexpr int SCHUNK = 16;          // owned sites reduced at a time
+constexpr int REC_CAP = 2048;       // records staged in shared memory per round
+constexpr int MAX_LOCAL_SITES = 32; // per-read category cache
+constexpr int NSMAX = AVO_MAX_PLOIDY + 1;
+
+// categories (reachable flag combinations of SummarizedObservation)
+enum : uint32_t { CAT_REF = 0, CAT_ALT = 1, CAT_OTHER = 2, CAT_NONREF = 3, CAT_NONE = 4, CAT_EXC = 5 };
+
+struct ReadCtx {
+  int32_t start, end;
+  uint32_t sb;  // first base (global base index)
+  uint32_t ob;  // first op
+  uint32_t no;  // number of ops
+  uint32_t mapq;
+  bool fwd;
+};
+
+// (category, optional quality) of one read at one site; q = -1 means None
+struct Cls { uint32_t cat; int32_t q; };
+
+// mean quality of an insertion (Observer.scala:101-103): integer division
+__device__ __forceinline__ int32_t ins_quality(const uint8_t* __restrict__ quals, uint32_t b, int len) {
+  int sum = 0;
+  for (int i = 0; i < len; ++i) sum += __ldg(quals + b + i);
+  return sum / len;
+}
+
+// S4 + S5 of SURVEY.md for one (read, site): walk the read's operators, summarise the observations
+// that overlap [vs, vs + ref_len) in read order, then apply BG:297-355.
+__device__ Cls classify(const DReads& R, const ReadCtx& rc, int32_t vs, int32_t ref_len,
+                        int32_t alt_len, uint32_t aoff, const uint8_t* __restrict__ alleles4) {
+  const int32_t ve = vs + ref_len;
+  const bool insVar = (ref_len == 1 && alt_len > 1);                    // BG:409-412
+  const uint32_t altoff = aoff + (uint32_t)ref_len;
+  int32_t pos = rc.start;
+  uint32_t ridx = 0;
+  int n_obs = 0, n_nonempty = 0, n_del = 0, first_del_w = 0;
+  bool head_isref = false, head_eq_alt = false;
+  int32_t head_q = -1;
+  int n_ins_eq = 0;
+  int32_t inseq_q = -1;
+  bool inseq_isref = false;
+  int lead_kind = 0;  // 0 none, 1 non-empty allele, 2 empty allele (deletion)
+  uint32_t lead_first = 0;
+  bool all_isref = true;
+
+  for (uint32_t k = 0; k < rc.no; ++k) {
+    const uint32_t op = __ldg(R.ops + rc.ob + k);
+    const int len = (int)(op >> 4);
+    const uint32_t code = op & 15u;
+    if (code == AVO_OP_SOFTCLIP) { ridx += len; continue; }             // Observer.scala:66-71
+    if (code == AVO_OP_HARDCLIP) continue;
+    if (code == AVO_OP_MATCH || code == AVO_OP_MISMATCH) {              // Observer.scala:72-92
+      const int32_t lo = max(pos, vs), hi = min(pos + len, ve);
+      if (lo < hi) {
+        const bool isref = (code == AVO_OP_MATCH);
+        for (int32_t p = lo; p < hi; ++p) {
+          const uint32_t bi = rc.sb + ridx + (uint32_t)(p - pos);
+          const bool first = (n_obs == 0);
+          ++n_obs; ++n_nonempty;
+          all_isref = all_isref && isref;
+          if (first || insVar) {
+            const uint32_t b = nib_at(R.bases4, bi);
+            if (first) {
+              head_isref = isref;
+              head_q = __ldg(R.quals + bi);
+              head_eq_alt = (alt_len == 1 && b == nib_at(alleles4, altoff));
+            }
+            if (insVar) {
+              const bool eq = (alt_len == 2 && b == nib_at(alleles4, altoff + 1));
+              if (eq) {
+                if (n_ins_eq == 0) { inseq_q = __ldg(R.quals + bi); inseq_isref = isref; }
+                ++n_ins_eq;
+              } else if (lead_kind == 0) { lead_kind = 1; lead_first = b; }
+            }
+          }
+        }
+      }
+      pos += len; ridx += len;
+    } else if (code == AVO_OP_INS) {                                    // Observer.scala:93-118
+      if (pos - 1 < ve && pos > vs) {
+        const bool first = (n_obs == 0);
+        ++n_obs; ++n_nonempty;
+        all_isref = false;
+        if (first) {
+          head_isref = false;
+          head_q = ins_quality(R.quals, rc.sb + ridx, len);
+          bool eq = (len == alt_len);
+          for (int i = 0; eq && i < len; ++i)
+            eq = nib_at(R.bases4, rc.sb + ridx + i) == nib_at(alleles4, altoff + i);
+          head_eq_alt = eq;
+        }
+        if (insVar) {
+          bool eq = (len == alt_len - 1);
+          for (int i = 0; eq && i < len; ++i)
+            eq = nib_at(R.bases4, rc.sb + ridx + i) == nib_at(alleles4, altoff + 1 + i);
+          if (eq) {
+            if (n_ins_eq == 0) { inseq_q = ins_quality(R.quals, rc.sb + ridx, len); inseq_isref = false; }
+            ++n_ins_eq;
+          } else if (lead_kind == 0) { lead_kind = 1; lead_first = nib_at(R.bases4, rc.sb + ridx); }
+        }
+      }
+      ridx += len;
+    } else if (code == AVO_OP_DEL) {                                    // Observer.scala:119-138
+      if (pos < ve && pos + len > vs) {
+        const bool first = (n_obs == 0);
+        ++n_obs;
+        all_isref = false;
+        if (n_del == 0) first_del_w = len;
+        ++n_del;
+        if (first) { head_isref = false; head_q = -1; head_eq_alt = (alt_len == 0); }
+        if (insVar && lead_kind == 0) lead_kind = 2;
+      }
+      pos += len;
+    }
+    if (pos > ve) break;  // nothing later in the read can overlap the site
+  }
+
+  Cls out;
+  out.q = head_q;
+  if (n_obs == 0) { out.cat = CAT_NONE; return out; }                   // BG:297-298
+  if (insVar) {                                                         // BG:307-326
+    if (n_obs == 2 && n_ins_eq == 1) {
+      if (lead_kind == 2) { out.cat = CAT_EXC; return out; }            // leadBaseObserved(0) on ""
+      out.q = inseq_q;
+      if (lead_first == nib_at(alleles4, altoff)) out.cat = inseq_isref ? CAT_REF : CAT_ALT;
+      else out.cat = CAT_NONREF;
+    } else if (all_isref) {
+      out.cat = CAT_REF;
+    } else {
+      out.cat = CAT_NONREF;
+    }
+  } else {                                                              // BG:327-355
+    if (n_nonempty == 1 && head_eq_alt) {
+      if (ref_len > 1 && alt_len == 1) {                                // isDeletion
+        out.cat = (n_del == 1 && n_obs == 2 && first_del_w == ref_len - alt_len) ? CAT_ALT : CAT_NONREF;
+      } else {
+        out.cat = head_isref ? CAT_REF : CAT_ALT;
+      }
+    } else if (!head_isref || n_obs != ref_len) {
+      out.cat = CAT_NONREF;
+    } else {
+      out.cat = CAT_REF;
+    }
+  }
+  return out;
+}
+
+__device__ __forceinline__ Cls classify_site(const DReads& R, const ReadCtx& rc, const DSites& S,
+                                             int32_t j) {
+  return classify(R, rc, __ldg(S.start + j), __ldg(S.ref_len + j), __ldg(S.alt_len + j),
+                  __ldg(S.allele_off + j), S.alleles4);
+}
+
+// BG:376-383 with CopyNumberMap.overlappingVariants (CopyNumberMap.scala:103-111): the CNVs seen by
+// a read are the first contiguous run of list entries overlapping it; the site takes the first of
+// those that overlaps it, else the base ploidy.
+__device__ int32_t copy_number_for(const DCnv& C, int32_t base, int32_t rs, int32_t re, int32_t vs,
+                                   int32_t ve) {
+  if (C.n == 0) return base;
+  int32_t i = 0;
+  while (i < C.n && !(__ldg(C.end + i) > rs && __ldg(C.start + i) < re)) ++i;
+  while (i < C.n && (__ldg(C.end + i) > rs && __ldg(C.start + i) < re)) {
+    if (vs < __ldg(C.end + i) && ve > __ldg(C.start + i)) return __ldg(C.cn + i);
+    ++i;
+  }
+  return base;
+}
+
+// record word: [3:0] site slot in chunk, [5:4] category, [6] forward strand, [13:7] q', [20:14] mq',
+//              [24:21] copy number - min ploidy
+__device__ __forceinline__ uint32_t make_record(int slot, uint32_t cat, bool fwd, int q, int mq, int cni) {
+  return (uint32_t)slot | (cat << 4) | ((uint32_t)fwd << 6) | ((uint32_t)q << 7) |
+         ((uint32_t)mq << 14) | ((uint32_t)cni << 21);
+}
+
+// Everything one read contributes to the owned site chunk [cLo, cHi): returns the number of
+// records written to recs[] (at most SCHUNK).
+__device__ int process_read(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
+                            int64_t r, int32_t cLo, int32_t cHi, int32_t hLo, int32_t hHi,
+                            uint32_t* recs) {
+  const uint32_t flags = __ldg(R.flags + r);
+  if (flags & AVO_READ_SKIP_CALL) return 0;
+  ReadCtx rc;
+  rc.start = __ldg(R.start + r);
+  rc.end = __ldg(R.end + r);
+  int32_t a, b;
+  forest_get(S, R.contig, rc.start, rc.end, hLo, hHi, a, b);
+  if (a >= b) return 0;                                   // no overlapping variant: read dropped
+  if (b <= cLo || a >= cHi) return 0;                     // nothing of this chunk
+  rc.ob = __ldg(R.op_off + r);
+  rc.no = __ldg(R.op_off + r + 1) - rc.ob;
+  if (rc.no == 0) return 0;
+  rc.sb = __ldg(R.seq_off + r);
+  rc.mapq = __ldg(R.mapq + r);
+  rc.fwd = !(flags & AVO_READ_NEGATIVE_STRAND);
+
+  const int ns = b - a;
+  uint32_t cats[MAX_LOCAL_SITES];
+  int32_t qs[MAX_LOCAL_SITES];
+  const bool cached = ns <= MAX_LOCAL_SITES;
+  if (cached) {
+    for (int j = 0; j < ns; ++j) {
+      Cls c = classify_site(R, rc, S, a + j);
+      if (c.cat == CAT_EXC) return 0;                     // BG:385-391: the whole read is skipped
+      cats[j] = c.cat;
+      qs[j] = c.q;
+    }
+  } else {
+    for (int j = 0; j < ns; ++j)
+      if (classify_site(R, rc, S, a + j).cat == CAT_EXC) return 0;
+  }
+
+  const int mq = min(P.max_mapq, (int)rc.mapq);           // BG:452
+  int nrec = 0;
+  const int jLo = max(a, cLo), jHi = min(b, cHi);
+  for (int32_t j = jLo; j < jHi; ++j) {
+    Cls c;
+    if (cached) { c.cat = cats[j - a]; c.q = qs[j - a]; } else c = classify_site(R, rc, S, j);
+    if (c.cat == CAT_NONE) continue;
+    const int32_t js = __ldg(S.start + j), je = __ldg(S.end + j);
+    if (c.cat == CAT_NONREF) {                            // BG:359-373 other-alt pass
+      for (int32_t k = a; k < b; ++k) {
+        if (!(__ldg(S.start + k) < je && __ldg(S.end + k) > js)) continue;
+        const uint32_t kc = cached ? cats[k - a] : classify_site(R, rc, S, k).cat;
+        if (kc == CAT_ALT) { c.cat = CAT_OTHER; break; }
+      }
+    }
+    const int q = (c.q < 0) ? P.max_quality : min(P.max_quality, c.q);  // BG:451 least() skips null
+    if (q < 1 || mq < 1) continue;                        // no such row in the score table: dropped
+    const int cn = copy_number_for(C, P.base_ploidy, rc.start, rc.end, js, js + __ldg(S.ref_len + j));
+    recs[nrec++] = make_record(j - cLo, c.cat, rc.fwd, q, mq, cn - P.min_ploidy);
+  }
+  return nrec;
+}
+
+// ---- per-site accumulators in shared memory ---------------------------------------------------
+struct SiteAcc {
+  double ll[4][NSMAX];        // [category][state]
+  unsigned long long sq;      // sum of mapQ^2 (exact integer)
+  int32_t allele_fwd, other_fwd, allele_cov, other_cov, total_cov;
+  int32_t first_is_ref, copy_number, seen;
+};
+
+// BG:755-762 logFactorial: table built by k_lnfact in the reference's accumulation order; beyond
+// the table the same descending recurrence is run directly
+__device__ double log_factorial(const DCallParams& P, int n) {
+  if (n < P.lnk_n) return n > 1 ? __ldg(P.lnfact + n) : 0.0;
+  double f = 0.0;
+  while (n > 1) {
+    const double l = (n < P.lnk_n) ? __ldg(P.lnk + n) : log((double)n);
+    f = l + f;
+    --n;
+  }
+  return f;
+}
+
+// BG:622-668
+__device__ void state_and_quality(const double* ll, int n, double k, int& state, double& qual) {
+  int mi; double mx, sec;
+  if (ll[0] >= ll[1]) { mi = 0; mx = ll[0]; sec = ll[1]; } else { mi = 1; mx = ll[1]; sec = ll[0]; }
+  for (int i = 2; i < n; ++i) {
+    const double c = ll[i];
+    if (c > mx) { sec = mx; mx = c; mi = i; } else if (c > sec) { sec = c; }
+  }
+  state = mi;
+  qual = k * (mx - sec);
+}
+
+__device__ __forceinline__ int32_t double_to_int(double d) {   // Scala Double.toInt
+  if (d != d) return 0;
+  if (d >= 2147483647.0) return 2147483647;
+  if (d <= -2147483648.0) return (int32_t)0x80000000;
+  return (int32_t)d;
+}
+
+// BG:579-616, 677-748 for one reduced site; writes the result row.
+__device__ void finalize_site(const DCallParams& P, const DResults& O, int32_t site, const SiteAcc& A) {
+  const int ns = P.ns;
+  if (!A.seen) { O.emitted[site] = 0; return; }
+  O.emitted[site] = 1;
+  O.allele_fwd[site] = A.allele_fwd; O.other_fwd[site] = A.other_fwd;
+  O.allele_cov[site] = A.allele_cov; O.other_cov[site] = A.other_cov; O.total_cov[site] = A.total_cov;
+  const double sq = (double)A.sq;
+  O.square_mapq[site] = sq;
+  O.first_is_ref[site] = (uint8_t)A.first_is_ref;
+  O.copy_number[site] = A.copy_number;
+  for (int g = 0; g < ns; ++g) {
+    O.ref_ll[(int64_t)site * ns + g] = A.ll[CAT_REF][g];
+    O.allele_ll[(int64_t)site * ns + g] = A.ll[CAT_ALT][g];
+    O.other_ll[(int64_t)site * ns + g] = A.ll[CAT_OTHER][g];
+    O.nonref_ll[(int64_t)site * ns + g] = A.ll[CAT_NONREF][g];
+  }
+  const int n = A.copy_number + 1;
+  double sc[NSMAX];
+  int s_ar, s_ao, s_or; double q_ar, q_ao, q_or;
+  for (int i = 0; i < n; ++i) sc[i] = A.ll[CAT_ALT][i] + A.ll[CAT_REF][n - 1 - i];
+  state_and_quality(sc, n, P.ten_div_log10, s_ar, q_ar);
+  for (int i = 0; i < n; ++i) {
+    O.gl[(int64_t)site * ns + i] = sc[i];                                       // BG:728
+    O.nonref_gl[(int64_t)site * ns + i] = A.ll[CAT_NONREF][i] + A.ll[CAT_REF][n - 1 - i];  // BG:729
+  }
+  for (int i = n; i < ns; ++i) { O.gl[(int64_t)site * ns + i] = 0.0; O.nonref_gl[(int64_t)site * ns + i] = 0.0; }
+  for (int i = 0; i < n; ++i) sc[i] = A.ll[CAT_ALT][i] + A.ll[CAT_OTHER][n - 1 - i];
+  state_and_quality(sc, n, P.ten_div_log10, s_ao, q_ao);
+  for (int i = 0; i < n; ++i) sc[i] = A.ll[CAT_OTHER][i] + A.ll[CAT_REF][n - 1 - i];
+  state_and_quality(sc, n, P.ten_div_log10, s_or, q_or);
+  int alt, ref, other; double qual;
+  if (q_ar >= q_ao && q_ar >= q_or) { alt = s_ar; ref = n - s_ar - 1; other = 0; qual = q_ar; }
+  else if (q_ao >= q_or) { alt = s_ao; ref = 0; other = n - s_ao - 1; qual = q_ao; }
+  else { alt = 0; ref = n - s_or - 1; other = s_or; qual = q_or; }
+  O.n_alt[site] = alt; O.n_ref[site] = ref; O.n_other[site] = other;
+  O.qual[site] = qual;
+  O.gq[site] = double_to_int(qual);
+  const int ofw = A.other_fwd, orv = A.other_cov - A.other_fwd, afw = A.allele_fwd,
+            arv = A.allele_cov - A.allele_fwd;
+  O.sb[(int64_t)site * 4 + 0] = ofw; O.sb[(int64_t)site * 4 + 1] = orv;
+  O.sb[(int64_t)site * 4 + 2] = afw; O.sb[(int64_t)site * 4 + 3] = arv;
+  const double num = log_factorial(P, ofw + orv) + log_factorial(P, ofw + afw) +
+                     log_factorial(P, afw + arv) + log_factorial(P, orv + arv);
+  const double den = log_factorial(P, ofw) + log_factorial(P, orv) + log_factorial(P, afw) +
+                     log_factorial(P, arv) + log_factorial(P, ofw + orv + afw + arv);
+  O.fisher[site] = (float)(-10.0 * (num - den) / P.log10);                      // LogPhred.scala:38-40
+  O.rms_mapq[site] = (float)sqrt(sq / (double)(A.allele_cov + A.other_cov));    // BG:709
+}
+
+struct __align__(16) CallSmem {
+  SiteAcc acc[SCHUNK];
+  uint32_t rec[REC_CAP];
+  typename cub::BlockScan<int, CALL_THREADS>::TempStorage scan;
+  int32_t tile;
+};
+
+__global__ void __launch_bounds__(CALL_THREADS)
+k_call_tiles(DReads R, DSites S, DCnv C, DCallParams P, DResults O, DIndex X, int32_t n_tiles,
+             int32_t max_span, int32_t* __restrict__ tile_counter) {
+  __shared__ CallSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (;;) {
+    if (tid == 0) sm.tile = atomicAdd(tile_counter, 1);
+    __syncthreads();
+    const int32_t tile = sm.tile;
+    __syncthreads();
+    if (tile >= n_tiles) break;
+
+    // owned sites: start in [win0 + tile*CALL_W, win0 + (tile+1)*CALL_W).  The first tile also owns
+    // the sites that start before the first read but reach into the batch (s_begin), the last tile
+    // everything up to the end of the last read (s_end).  Sites outside [s_begin, s_end) cannot
+    // overlap any read; their (pre-zeroed) rows stay "not emitted".
+    constexpr int BPT = CALL_W / IDX_G;
+    const int32_t sLo = (tile == 0) ? __ldg(X.s_range) : __ldg(X.sidx + min(tile * BPT, X.nb));
+    const int32_t sHi = (tile == n_tiles - 1) ? __ldg(X.s_range + 1)
+                                              : __ldg(X.sidx + min((tile + 1) * BPT, X.nb));
+
+    for (int32_t cLo = sLo; cLo < sHi; cLo += SCHUNK) {
+      const int32_t cHi = min(cLo + SCHUNK, sHi);
+      // zero the accumulators
+      for (int i = tid; i < (int)(sizeof(SiteAcc) * SCHUNK / 4); i += CALL_THREADS)
+        reinterpret_cast<uint32_t*>(sm.acc)[i] = 0u;
+      // reads that can overlap a site of the chunk: start < max site end, start >= first site start - max_span
+      int32_t maxEnd = INT32_MIN;
+      for (int32_t j = cLo; j < cHi; ++j) maxEnd = max(maxEnd, __ldg(S.end + j));
+      const int64_t loKey = (int64_t)__ldg(S.start + cLo) - max_span;
+      // over-approximate (by < one index bin each side) read range and site search range
+      const int64_t rLo = __ldg(X.ridx + idx_bin_floor(X, loKey));
+      const int64_t rHi = __ldg(X.ridx + idx_bin_ceil(X, maxEnd));
+      const int32_t hLo = (loKey <= X.win0) ? S.c_lo : __ldg(X.sidx + idx_bin_floor(X, loKey));
+      // reads of the range start before maxEnd + IDX_G and end within max_span of their start
+      const int32_t hb = idx_bin_ceil(X, (int64_t)maxEnd + max_span) + 1;
+      const int32_t hHi = (hb >= X.nb) ? S.c_hi : __ldg(X.sidx + hb);
+      __syncthreads();
+
+      for (int64_t seg = rLo; seg < rHi; seg += CALL_THREADS) {
+        const int64_t r = seg + tid;
+        uint32_t recs[SCHUNK];
+        int nrec = 0;
+        if (r < rHi) nrec = process_read(R, S, C, P, r, cLo, cHi, hLo, hHi, recs);
+        int off, total;
+        cub::BlockScan<int, CALL_THREADS>(sm.scan).ExclusiveSum(nrec, off, total);
+        __syncthreads();
+        // rounds of at most REC_CAP records, in read order
+        for (int base = 0; base < total; base += REC_CAP) {
+          const int cnt = min(REC_CAP, total - base);
+          for (int i = 0; i < nrec; ++i) {
+            const int o = off + i - base;
+            if (o >= 0 && o < REC_CAP) sm.rec[o] = recs[i];
+          }
+          __syncthreads();
+          // phase B: one warp per site slot; records are scanned in order
+          for (int slot = warp; slot < cHi - cLo; slot += CALL_WARPS) {
+            SiteAcc& A = sm.acc[slot];
+            int c_afw = 0, c_ofw = 0, c_acov = 0, c_ocov = 0, c_tot = 0;
+            unsigned long long sq = 0;
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            const bool ll_lane = lane < P.ns;
+            if (ll_lane) { a0 = A.ll[0][lane]; a1 = A.ll[1][lane]; a2 = A.ll[2][lane]; a3 = A.ll[3][lane]; }
+            int seen = A.seen, first_is_ref = A.first_is_ref, first_cn = A.copy_number;
+            for (int i0 = 0; i0 < cnt; i0 += 32) {
+              const int i = i0 + lane;
+              const uint32_t w = (i < cnt) ? sm.rec[i] : 0xFFFFFFFFu;
+              const bool mine = (i < cnt) && ((w & 15u) == (uint32_t)slot);
+              const unsigned m = __ballot_sync(0xFFFFFFFFu, mine);
+              if (m == 0) continue;
+              const uint32_t cat = (w >> 4) & 3u;
+              const bool fwd = (w >> 6) & 1u;
+              const unsigned isRef = __ballot_sync(0xFFFFFFFFu, mine && cat == CAT_REF);
+              const unsigned isAl = __ballot_sync(0xFFFFFFFFu, mine && (cat == CAT_ALT || cat == CAT_NONREF));
+              const unsigned fw = __ballot_sync(0xFFFFFFFFu, mine && fwd);
+              c_tot += __popc(m);                                        // ScoredObservation.scala:88
+              c_ocov += __popc(isRef);                                   // :87
+              c_acov += __popc(isAl);                                    // :86
+              c_ofw += __popc(isRef & fw);                               // :80
+              c_afw += __popc(isAl & fw);                                // :79
+              if (mine) { const unsigned long long q = (w >> 14) & 127u; sq += q * q; }  // :81
+              if (!seen) {                                               // first("isRef"), first("copyNumber")
+                const int f = __ffs(m) - 1;
+                const uint32_t wf = __shfl_sync(0xFFFFFFFFu, w, f);
+                first_is_ref = (((wf >> 4) & 3u) == CAT_REF);
+                first_cn = (int)((wf >> 21) & 15u) + P.min_ploidy;
+                seen = 1;
+              }
+              // ordered fp64 accumulation: lane g owns state g of the four arrays
+              unsigned mm = m;
+              while (mm) {
+                const int src = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const uint32_t ws = __shfl_sync(0xFFFFFFFFu, w, src);
+                if (ll_lane) {
+                  const uint32_t c = (ws >> 4) & 3u;
+                  const int q = (ws >> 7) & 127u, mq = (ws >> 14) & 127u, cni = (ws >> 21) & 15u;
+                  const double v = __ldg(P.lut + ((((int64_t)cni * (P.max_quality + 1) + q) *
+                                                   (P.max_mapq + 1) + mq) * P.ns + lane));
+                  // Spark sums every column for every row; the non-selected arrays add 0.0
+                  a0 += (c == 0) ? v : 0.0;
+                  a1 += (c == 1) ? v : 0.0;
+                  a2 += (c == 2) ? v : 0.0;
+                  a3 += (c == 3) ? v : 0.0;
+                }
+              }
+            }
+            // fold this round into the shared accumulators
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
+            if (ll_lane) { A.ll[0][lane] = a0; A.ll[1][lane] = a1; A.ll[2][lane] = a2; A.ll[3][lane] = a3; }
+            if (lane == 0) {
+              A.sq += sq;
+              A.allele_fwd += c_afw; A.other_fwd += c_ofw; A.allele_cov += c_acov;
+              A.other_cov += c_ocov; A.total_cov += c_tot;
+              A.seen = seen; A.first_is_ref = first_is_ref; A.copy_number = first_cn;
+            }
+          }
+          __syncthreads();
+        }
+      }
+      // emit the chunk's rows
+      __syncthreads();
+      if (tid < cHi - cLo) finalize_site(P, O, cLo + tid, sm.acc[tid]);
+      __syncthreads();
+    }
+  }
+}
+
+cudaError_t launch_call_tiles(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
+                              const DResults& out, const DIndex& X, const BatchStats& hstats,
+                              int32_t* d_tile_counter, int num_sms, cudaStream_t s, int* n_launches) {
+  cudaError_t e = cudaMemsetAsync(d_tile_counter, 0, sizeof(int32_t), s);
+  if (e != cudaSuccess) return e;
+  if (R.n == 0 || S.c_hi <= S.c_lo) return cudaSuccess;
+  const int64_t span = (int64_t)hstats.max_end - (int64_t)hstats.min_start;
+  const int32_t n_tiles = (int32_t)max((int64_t)1, (span + CALL_W - 1) / CALL_W);
+  int blocks_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_call_tiles, CALL_THREADS, 0);
+  if (e != cudaSuccess) return e;
+  const int grid = (int)min((int64_t)n_tiles, (int64_t)num_sms * max(1, blocks_per_sm));
+  k_call_tiles<<<grid, CALL_THREADS, 0, s>>>(R, S, C, P, out, X, n_tiles, hstats.max_span,
+                                             d_tile_counter);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace avo

@@ -1,0 +1,106 @@
+// avo_device.cuh -- small device helpers shared by the kernels.
+#pragma once
+
+#include "avo_internal.h"
+
+namespace avo {
+
+__device__ __forceinline__ uint32_t nib_at(const uint8_t* __restrict__ p, uint32_t i) {
+  uint32_t b = __ldg(p + (i >> 1));
+  return (i & 1u) ? (b & 15u) : (b >> 4);
+}
+
+__device__ __forceinline__ int32_t site_contig(const DSites& S, int32_t k) {
+  return S.contig ? __ldg(S.contig + k) : 0;
+}
+
+// first index in [lo, hi) with a[i] >= v   (a non-decreasing)
+__device__ __forceinline__ int32_t lower_bound_i32(const int32_t* __restrict__ a, int32_t lo,
+                                                   int32_t hi, int32_t v) {
+  while (lo < hi) {
+    int32_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// bin of position x in the coarse index, clamped to [0, nb]
+__device__ __forceinline__ int32_t idx_bin_floor(const DIndex& X, int64_t x) {
+  const int64_t d = x - (int64_t)X.win0;
+  if (d <= 0) return 0;
+  const int64_t k = d / IDX_G;
+  return (int32_t)(k > X.nb ? X.nb : k);
+}
+__device__ __forceinline__ int32_t idx_bin_ceil(const DIndex& X, int64_t x) {
+  const int64_t d = x - (int64_t)X.win0;
+  if (d <= 0) return 0;
+  const int64_t k = (d + IDX_G - 1) / IDX_G;
+  return (int32_t)(k > X.nb ? X.nb : k);
+}
+
+__device__ __forceinline__ int64_t lower_bound_i64n(const int32_t* __restrict__ a, int64_t lo,
+                                                    int64_t hi, int32_t v) {
+  while (lo < hi) {
+    int64_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forest.get (CORE/util/TreeRegionJoin.scala:74-119) for the read region [rs, re) on contig c.
+// Returns the contiguous index range [a, b) of the sorted site table the reference would return.
+//
+// Fast path: when no site that starts before rs reaches past rs (prefix-max-end test), the
+// overlapping set is exactly the sites with start in [rs, re), which is contiguous, and the
+// reference's probe sequence is guaranteed to hit it ("join").  Otherwise the
+// reference's result depends on which element its power-of-two descent probes first, so the
+// descent is replayed literally.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool site_overlaps(const DSites& S, int32_t k, int32_t c, int32_t rs,
+                                              int32_t re) {
+  return site_contig(S, k) == c && re > __ldg(S.start + k) && rs < __ldg(S.end + k);
+}
+
+// [hLo, hHi) is a caller-supplied index range known to contain every site with start in [rs, re]
+// (from the coarse index); it only narrows the two lower-bound searches.
+__device__ inline void forest_get(const DSites& S, int32_t c, int32_t rs, int32_t re, int32_t hLo,
+                                  int32_t hHi, int32_t& a, int32_t& b) {
+  int32_t i0 = lower_bound_i32(S.start, hLo, hHi, rs);
+  if (!(i0 > S.c_lo && __ldg(S.pme + i0 - 1) > rs)) {
+    a = i0;
+    b = lower_bound_i32(S.start, i0, hHi, re);
+    return;
+  }
+  // literal replay of binarySearch (:74-92)
+  int32_t idx = 0, step = S.midpoint;
+  int32_t hit = -1;
+  for (;;) {
+    if (site_overlaps(S, idx, c, rs, re)) { hit = idx; break; }
+    if (step == 0) break;
+    int32_t s = idx + step;
+    bool stay;
+    if (s >= S.n) {
+      stay = true;
+    } else if (site_overlaps(S, s, c, rs, re)) {
+      stay = false;
+    } else {
+      // rr.compareTo(array(s)) < 0 on (contig, start, end)
+      int32_t kc = site_contig(S, s), ks = __ldg(S.start + s), ke = __ldg(S.end + s);
+      bool lt = (c != kc) ? (c < kc) : (rs != ks) ? (rs < ks) : (re < ke);
+      stay = lt;
+    }
+    if (!stay) idx = s;
+    step >>= 1;
+  }
+  if (hit < 0) { a = 0; b = 0; return; }
+  // expand (:94-105): left from hit, right from hit+1, while overlapping
+  int32_t l = hit;
+  while (l - 1 >= 0 && site_overlaps(S, l - 1, c, rs, re)) --l;
+  int32_t r = hit + 1;
+  while (r < S.n && site_overlaps(S, r, c, rs, re)) ++r;
+  a = l;
+  b = r;
+}
+
+}  // namespace avo

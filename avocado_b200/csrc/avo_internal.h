@@ -1,0 +1,161 @@
+// avo_internal.h -- device-side views and launcher prototypes shared by the .cu files.
+// Not part of the public ABI (that is include/avocado_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/avocado_b200.h"
+
+namespace avo {
+
+// ---- device views (all pointers are device pointers) ----------------------------------------
+struct DReads {
+  int64_t n;
+  int32_t contig;
+  const int32_t* start;
+  const int32_t* end;
+  const uint8_t* mapq;
+  const uint8_t* flags;
+  const uint32_t* seq_off;
+  const uint8_t* bases4;
+  const uint8_t* quals;
+  const uint32_t* op_off;
+  const uint32_t* ops;
+  const uint32_t* refb_off;
+  const uint8_t* refb4;
+};
+
+struct DSites {
+  int32_t n;          // total entries in the table (all contigs)
+  int32_t c_lo, c_hi; // index range of the batch's contig
+  int32_t midpoint;   // Forest.midpoint (TreeRegionJoin.scala:66-72) over the whole table
+  const int32_t* contig; // may be null (all zero)
+  const int32_t* start;
+  const int32_t* end;    // start + ref_len (built by k_site_setup)
+  const int32_t* ref_len;
+  const int32_t* alt_len;
+  const uint32_t* allele_off;
+  const uint8_t* alleles4;
+  const int32_t* pme;    // prefix max of `end` within the contig (inclusive)
+};
+
+// Coarse position index over one batch (bins of IDX_G bases from win0): built by k_build_index.
+//   ridx[k] = first read with start >= win0 + k*IDX_G      (k = 0..nb, ridx[nb] = n_reads)
+//   sidx[k] = first site of the batch contig with start >= win0 + k*IDX_G
+//   s_begin = first site of the contig whose prefix-max end reaches past the first read's start
+//   s_end   = first site of the contig with start >= max read end
+constexpr int IDX_G = 256;
+struct DIndex {
+  int32_t win0;
+  int32_t nb;
+  const int32_t* ridx;
+  const int32_t* sidx;
+  const int32_t* s_range;  // [2] = {s_begin, s_end}
+};
+
+struct DCnv {   // CNVs of the batch's contig only, sorted by (start, end)
+  int32_t n;
+  const int32_t* start;
+  const int32_t* end;
+  const int32_t* cn;
+};
+
+struct DResults {
+  int32_t ns; // n_states (row stride)
+  uint8_t* emitted;
+  int32_t *allele_fwd, *other_fwd, *allele_cov, *other_cov, *total_cov;
+  double* square_mapq;
+  double *ref_ll, *allele_ll, *other_ll, *nonref_ll;
+  uint8_t* first_is_ref;
+  int32_t* copy_number;
+  int32_t *n_alt, *n_ref, *n_other;
+  double* qual;
+  int32_t* gq;
+  int32_t* sb;
+  float *fisher, *rms_mapq;
+  double *gl, *nonref_gl;
+};
+
+struct DCallParams {
+  int32_t base_ploidy, min_ploidy, max_ploidy, ns;
+  int32_t max_quality, max_mapq;
+  // lut[((cn - min_ploidy) * (max_quality+1) + q) * (max_mapq+1) + mq) * ns + g]  (S6 of SURVEY.md)
+  const double* lut;
+  const double* lnk;     // lnk[k] = log(k), k < lnk_n (host libm)
+  const double* lnfact;  // lnfact[n] = logFactorial(n) (BG:755-762), n < lnk_n, same summation order
+  int32_t lnk_n;
+  double ten_div_log10;   // 10 / ln 10   (BG:572)
+  double log10;           // ln 10        (LogPhred.scala)
+};
+
+// batch statistics produced by k_batch_stats
+struct BatchStats {
+  int32_t min_start;
+  int32_t max_end;
+  int32_t max_span;   // max(end - start)
+  int32_t unsorted;   // != 0 if start[] is not non-decreasing
+};
+
+// ---- launchers (each returns the cudaError_t of its launches) --------------------------------
+cudaError_t launch_batch_stats(const DReads& R, BatchStats* d_stats, cudaStream_t s);
+cudaError_t launch_site_setup(int32_t n, const int32_t* contig, const int32_t* start,
+                              const int32_t* ref_len, int32_t* end, int32_t* pme, int32_t* d_unsorted,
+                              void* d_temp, size_t temp_bytes, cudaStream_t s);
+size_t site_setup_temp_bytes(int32_t n);
+
+cudaError_t launch_lnfact_table(const double* lnk, double* lnfact, int32_t n, cudaStream_t s);
+// index over reads (and, when S.n > 0, sites); ridx/sidx need nb+1 entries, nb = index_bins(stats)
+int32_t index_bins(const BatchStats& hstats);
+cudaError_t launch_build_index(const DReads& R, const DSites& S, const BatchStats& hstats,
+                               int32_t* ridx, int32_t* sidx, int32_t* s_range, cudaStream_t s);
+
+cudaError_t launch_call_tiles(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
+                              const DResults& out, const DIndex& X, const BatchStats& hstats,
+                              int32_t* d_tile_counter, int num_sms, cudaStream_t s, int* n_launches);
+
+// discovery
+struct DDiscoverOut {
+  // unsorted candidate survivors appended by the kernels
+  int32_t capacity;
+  int32_t* n;           // device counter (may exceed capacity: overflow)
+  int32_t* start;
+  int32_t* ref_len;
+  int32_t* alt_len;
+  int32_t* count;
+  uint64_t* src;        // where the allele content lives: see avo_discover.cu
+};
+
+struct DIndelList {
+  int32_t capacity;
+  int32_t* n;           // device counter
+  int32_t* pos;
+  uint32_t* lens;       // (ref_len << 16) | alt_len
+  uint32_t* nibs;       // (lastRef nibble << 4) | anchor (alt[0] / read base) nibble
+  uint32_t* src;        // INS: global base index of the first inserted base; DEL: global refb nibble index
+  uint32_t* hash;
+};
+
+cudaError_t launch_discover_tiles(const DReads& R, int32_t thr, int32_t min_obs /* <0: distinct */,
+                                  const DIndex& X, const BatchStats& hstats, const DDiscoverOut& out,
+                                  const DIndelList& indels, int32_t* d_tile_counter, int num_sms,
+                                  cudaStream_t s, int* n_launches);
+
+cudaError_t launch_indel_group(const DReads& R, const DIndelList& L, int32_t n_indel,
+                               unsigned long long* table, int32_t* tcount, uint32_t tsize,
+                               int32_t min_obs, const DDiscoverOut& out, cudaStream_t s,
+                               int* n_launches);
+size_t assemble_temp_bytes(int32_t n);
+cudaError_t launch_assemble_sites(const DReads& R, const DIndelList& L, const DDiscoverOut& U,
+                                  int32_t n, unsigned long long* keys_a, unsigned long long* keys_b,
+                                  int32_t* vals_a, int32_t* vals_b, uint32_t* foot, uint32_t* aoff,
+                                  void* d_temp, size_t temp_bytes, cudaStream_t s, int* n_launches);
+cudaError_t launch_fill_sites(const DReads& R, const DIndelList& L, const DDiscoverOut& U, int32_t n,
+                              const int32_t* vals, const uint32_t* aoff, int32_t* o_start,
+                              int32_t* o_ref_len, int32_t* o_alt_len, uint32_t* o_aoff,
+                              uint8_t* o_alleles, int32_t* o_count, uint32_t total_nibbles,
+                              cudaStream_t s, int* n_launches);
+cudaError_t launch_contig_range(int32_t n, const int32_t* contig, int32_t c, int32_t* d_range,
+                                cudaStream_t s);
+
+}  // namespace avo

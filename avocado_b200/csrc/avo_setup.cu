@@ -1,0 +1,159 @@
+// avo_setup.cu -- small set-up kernels around the two tile kernels: batch statistics, the site
+// table's derived columns (end, prefix-max end = the Forest fast-path test), the coarse position
+// index that replaces per-tile binary searches, and the logFactorial table.
+#include <cub/device/device_scan.cuh>
+
+#include "avo_device.cuh"
+
+namespace avo {
+
+// ---- batch statistics -------------------------------------------------------------------------
+__global__ void k_batch_stats(DReads R, BatchStats* __restrict__ st) {
+  int32_t mn = INT32_MAX, mxe = INT32_MIN, mxs = 0, uns = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < R.n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t s = __ldg(R.start + i), e = __ldg(R.end + i);
+    mn = min(mn, s);
+    mxe = max(mxe, e);
+    mxs = max(mxs, e - s);
+    if (i > 0 && __ldg(R.start + i - 1) > s) uns = 1;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+    mxe = max(mxe, __shfl_xor_sync(0xFFFFFFFFu, mxe, o));
+    mxs = max(mxs, __shfl_xor_sync(0xFFFFFFFFu, mxs, o));
+    uns |= __shfl_xor_sync(0xFFFFFFFFu, uns, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&st->min_start, mn);
+    atomicMax(&st->max_end, mxe);
+    atomicMax(&st->max_span, mxs);
+    if (uns) atomicOr(&st->unsorted, 1);
+  }
+}
+
+__global__ void k_init_stats(BatchStats* st) {
+  st->min_start = INT32_MAX; st->max_end = INT32_MIN; st->max_span = 0; st->unsorted = 0;
+}
+
+cudaError_t launch_batch_stats(const DReads& R, BatchStats* d_stats, cudaStream_t s) {
+  k_init_stats<<<1, 1, 0, s>>>(d_stats);
+  if (R.n > 0) {
+    const int grid = (int)min((int64_t)2048, (R.n + 255) / 256);
+    k_batch_stats<<<grid, 256, 0, s>>>(R, d_stats);
+  }
+  return cudaGetLastError();
+}
+
+// ---- site table -------------------------------------------------------------------------------
+__global__ void k_site_end(int32_t n, const int32_t* __restrict__ contig,
+                           const int32_t* __restrict__ start, const int32_t* __restrict__ ref_len,
+                           int32_t* __restrict__ end, int32_t* __restrict__ unsorted) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t e = start[i] + ref_len[i];
+  end[i] = e;
+  if (i > 0) {  // ReferenceRegion ordering: (contig, start, end)
+    const int32_t c0 = contig ? contig[i - 1] : 0, c1 = contig ? contig[i] : 0;
+    const int32_t s0 = start[i - 1], e0 = s0 + ref_len[i - 1];
+    const bool le = (c0 != c1) ? (c0 < c1) : (s0 != start[i]) ? (s0 < start[i]) : (e0 <= e);
+    if (!le) atomicOr(unsorted, 1);
+  }
+}
+
+struct MaxOp {
+  __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; }
+};
+
+size_t site_setup_temp_bytes(int32_t n) {
+  size_t a = 0, b = 0;
+  cub::DeviceScan::InclusiveScan((void*)nullptr, a, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                 MaxOp(), n);
+  cub::DeviceScan::InclusiveScanByKey((void*)nullptr, b, (const int32_t*)nullptr,
+                                      (const int32_t*)nullptr, (int32_t*)nullptr, MaxOp(), n);
+  return (a > b ? a : b) + 256;
+}
+
+cudaError_t launch_site_setup(int32_t n, const int32_t* contig, const int32_t* start,
+                              const int32_t* ref_len, int32_t* end, int32_t* pme, int32_t* d_unsorted,
+                              void* d_temp, size_t temp_bytes, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(d_unsorted, 0, sizeof(int32_t), s);
+  if (e != cudaSuccess || n == 0) return e;
+  k_site_end<<<(n + 255) / 256, 256, 0, s>>>(n, contig, start, ref_len, end, d_unsorted);
+  if (contig)
+    e = cub::DeviceScan::InclusiveScanByKey(d_temp, temp_bytes, contig, (const int32_t*)end, pme,
+                                            MaxOp(), n, cub::Equality(), s);
+  else
+    e = cub::DeviceScan::InclusiveScan(d_temp, temp_bytes, (const int32_t*)end, pme, MaxOp(), n, s);
+  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+
+// index range [lo, hi) of contig c in a table sorted by contig
+__global__ void k_contig_range(int32_t n, const int32_t* __restrict__ contig, int32_t c,
+                               int32_t* __restrict__ range) {
+  if (!contig) { range[0] = (c == 0) ? 0 : n; range[1] = (c == 0) ? n : n; return; }
+  range[0] = lower_bound_i32(contig, 0, n, c);
+  range[1] = lower_bound_i32(contig, range[0], n, c + 1);
+}
+
+cudaError_t launch_contig_range(int32_t n, const int32_t* contig, int32_t c, int32_t* d_range,
+                                cudaStream_t s) {
+  k_contig_range<<<1, 1, 0, s>>>(n, contig, c, d_range);
+  return cudaGetLastError();
+}
+
+// ---- logFactorial table (BG:755-762): lnfact[n] = ln n + (ln(n-1) + ( ... + ln 2)) accumulated
+// from n downwards exactly as the reference's tail recursion does, from the host-built ln table.
+__global__ void k_lnfact(const double* __restrict__ lnk, double* __restrict__ lnfact, int32_t n) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double f = 0.0;
+  for (int32_t k = i; k > 1; --k) f = lnk[k] + f;
+  lnfact[i] = f;
+}
+
+cudaError_t launch_lnfact_table(const double* lnk, double* lnfact, int32_t n, cudaStream_t s) {
+  k_lnfact<<<(n + 127) / 128, 128, 0, s>>>(lnk, lnfact, n);
+  return cudaGetLastError();
+}
+
+// ---- coarse position index --------------------------------------------------------------------
+int32_t index_bins(const BatchStats& h) {
+  if (h.max_end <= h.min_start) return 1;
+  const int64_t span = (int64_t)h.max_end - (int64_t)h.min_start;
+  return (int32_t)((span + IDX_G - 1) / IDX_G) + 1;
+}
+
+__global__ void k_build_index(DReads R, DSites S, int32_t win0, int32_t nb, int32_t max_end,
+                              int32_t* __restrict__ ridx, int32_t* __restrict__ sidx,
+                              int32_t* __restrict__ s_range) {
+  const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k <= nb) {
+    const int64_t key64 = (int64_t)win0 + (int64_t)k * IDX_G;
+    const int32_t key = (int32_t)min(key64, (int64_t)INT32_MAX);
+    ridx[k] = (k == nb) ? (int32_t)R.n : (int32_t)lower_bound_i64n(R.start, 0, R.n, key);
+    if (S.n > 0) sidx[k] = lower_bound_i32(S.start, S.c_lo, S.c_hi, key);
+  }
+  if (k == 0 && S.n > 0) {
+    // first site whose prefix-max end reaches past win0 (= first read start): earlier sites
+    // cannot overlap any read of the batch
+    int32_t lo = S.c_lo, hi = S.c_hi;
+    while (lo < hi) {
+      const int32_t mid = lo + ((hi - lo) >> 1);
+      if (__ldg(S.pme + mid) <= win0) lo = mid + 1; else hi = mid;
+    }
+    s_range[0] = lo;
+    s_range[1] = lower_bound_i32(S.start, S.c_lo, S.c_hi, max_end);
+  }
+}
+
+cudaError_t launch_build_index(const DReads& R, const DSites& S, const BatchStats& h, int32_t* ridx,
+                               int32_t* sidx, int32_t* s_range, cudaStream_t s) {
+  const int32_t nb = index_bins(h);
+  k_build_index<<<(nb + 1 + 255) / 256, 256, 0, s>>>(R, S, h.min_start, nb, h.max_end, ridx, sidx,
+                                                      s_range);
+  return cudaGetLastError();
+}
+
+}  // namespace avo

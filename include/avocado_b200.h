@@ -1,0 +1,252 @@
+/* avocado_b200.h -- C ABI of the B200-native replacement for avocado's genotyping hot path.
+ *
+ * The reference (bigdatagenomics/avocado, Scala on Spark) has no FFI; the seam this library
+ * sits behind is the pair of Scala entry points
+ *
+ *   DiscoverVariants.apply(reads, optPhredThreshold, optMinObservations): VariantRDD
+ *       avocado-core/src/main/scala/org/bdgenomics/avocado/genotyping/DiscoverVariants.scala:51-61
+ *   BiallelicGenotyper.call(reads, variants, copyNumber, scoreAllSites, ..., maxQuality, maxMapQ): GenotypeRDD
+ *       .../genotyping/BiallelicGenotyper.scala:88-135      (discoverAndCall: :156-184)
+ *   JointAnnotatorCaller.apply(genotypes): VariantContextRDD
+ *       .../genotyping/JointAnnotatorCaller.scala:52-64
+ *
+ * A JVM shim keeps those signatures and, per partition / region bin, packs reads into the
+ * columnar batch below, calls one of the avo_* functions through JNI, and fills Avro builders
+ * from the SoA results without arithmetic (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *  - Every buffer is caller-owned; the library keeps no pointer after a call returns.
+ *  - `mem` says where a struct's buffers live: AVO_MEM_HOST (pinned preferred) or
+ *    AVO_MEM_DEVICE (pointers valid on the context's GPU).
+ *  - All functions return 0 (AVO_OK) or a negative avo_status; nothing throws or aborts.
+ *    A malformed read is skipped, never an error (BiallelicGenotyper.scala:385-391).
+ *  - A context is bound to one GPU and is NOT thread-safe; use one per thread.
+ *  - Coordinates are 0-based half-open (ADAM); bases are 4-bit BAM codes (=ACMGRSVTWYHKDBN),
+ *    two per byte, even index in the HIGH nibble; qualities are raw phred (no +33).
+ *  - There is no CPU fallback: without a usable CUDA device avo_ctx_create fails.
+ */
+#ifndef AVOCADO_B200_H
+#define AVOCADO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct avo_ctx avo_ctx;
+
+typedef enum {
+  AVO_OK = 0,
+  AVO_E_INVALID = -1,      /* bad argument / inconsistent struct */
+  AVO_E_CUDA = -2,         /* CUDA runtime error, see avo_last_error */
+  AVO_E_CAPACITY = -3,     /* an output buffer is too small; required sizes are written back */
+  AVO_E_EMPTY_SITES = -4,  /* call() with no variants: the reference throws (TreeRegionJoin.scala:77) */
+  AVO_E_UNSORTED = -5,     /* reads not sorted by start / sites not sorted by (contig,start,end) */
+  AVO_E_UNSUPPORTED = -6,  /* parameter outside the supported domain (e.g. ploidy > AVO_MAX_PLOIDY) */
+  AVO_E_NOMEM = -7
+} avo_status;
+
+enum { AVO_MEM_HOST = 0, AVO_MEM_DEVICE = 1 };
+enum { AVO_MAX_PLOIDY = 7 };
+
+/* alignment operators after merging CIGAR with MD (ObservationOperator.scala:42-171):
+ * op word = (length << 4) | code */
+enum {
+  AVO_OP_MATCH = 0,     /* Match(n)           sequence match   '=' */
+  AVO_OP_MISMATCH = 1,  /* Match(n, Some(ref)) sequence mismatch 'X'; n ref nibbles in refb4 */
+  AVO_OP_INS = 2,       /* Insertion(n) */
+  AVO_OP_DEL = 3,       /* Deletion(ref); n ref nibbles in refb4 */
+  AVO_OP_SOFTCLIP = 4,  /* Clipped(n, soft = true) */
+  AVO_OP_HARDCLIP = 5   /* Clipped(n, soft = false) */
+};
+
+/* flags[] bits */
+enum {
+  AVO_READ_NEGATIVE_STRAND = 1, /* AlignmentRecord.readNegativeStrand */
+  AVO_READ_SKIP_CALL = 2        /* the reference's observeRead would throw for this read (null mapq,
+                                   sequence/qual shorter than the CIGAR): skipped by call(), still
+                                   walked by discover() */
+};
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+int avo_ctx_create(int device, avo_ctx** out);
+void avo_ctx_destroy(avo_ctx* ctx);
+const char* avo_last_error(const avo_ctx* ctx); /* owned by ctx; valid until the next call */
+const char* avo_version(void);
+/* Run on this CUDA stream (a cudaStream_t) instead of the context's own; NULL restores it. */
+int avo_ctx_set_stream(avo_ctx* ctx, void* cuda_stream);
+
+/* ---- inputs ------------------------------------------------------------------------------- */
+/* One batch = reads of ONE contig, sorted by start (ties in any order; the order of the batch is
+ * the canonical summation order).  Replaces the AlignmentRecord fields listed in SURVEY.md 8b. */
+typedef struct {
+  int64_t n_reads;
+  int64_t n_bases; /* seq_off[n_reads] */
+  int64_t n_ops;   /* op_off[n_reads] */
+  int64_t n_refb;  /* refb_off[n_reads] (nibbles) */
+  int32_t contig_id; /* rank of this contig in the site table's contig order */
+  int32_t mem;
+  const int32_t* start;     /* [n] AlignmentRecord.start */
+  const int32_t* end;       /* [n] AlignmentRecord.end */
+  const uint8_t* mapq;      /* [n] */
+  const uint8_t* flags;     /* [n] */
+  const uint32_t* seq_off;  /* [n+1] base index of the read's first base */
+  const uint8_t* bases4;    /* [(n_bases+1)/2] */
+  const uint8_t* quals;     /* [n_bases] */
+  const uint32_t* op_off;   /* [n+1] */
+  const uint32_t* ops;      /* [n_ops] */
+  const uint32_t* refb_off; /* [n+1] nibble index */
+  const uint8_t* refb4;     /* [(n_refb+1)/2] reference bases of MISMATCH and DEL ops, in op order */
+} avo_read_batch;
+
+/* Variant sites, sorted by (contig, start, start + ref_len); unique.  Replaces the Variant
+ * fields read by DiscoveredVariant.apply (DiscoveredVariant.scala:32-37); end == start + ref_len. */
+typedef struct {
+  int64_t n;
+  int64_t n_allele_nibbles; /* allele_off[n] */
+  int32_t mem;
+  int32_t reserved;
+  const int32_t* contig;      /* [n] contig rank, or NULL = all 0 */
+  const int32_t* start;       /* [n] */
+  const int32_t* ref_len;     /* [n] >= 1 */
+  const int32_t* alt_len;     /* [n] >= 0 */
+  const uint32_t* allele_off; /* [n+1] nibble index (always even); ref nibbles then alt nibbles */
+  const uint8_t* alleles4;
+} avo_sites;
+
+/* CopyNumberMap (CopyNumberMap.scala:75-111): base ploidy + per-contig sorted CNV list.  Host memory. */
+typedef struct {
+  int64_t n;
+  const int32_t* contig; /* [n] contig rank; entries sorted by (contig, start, end) */
+  const int32_t* start;
+  const int32_t* end;
+  const int32_t* copy_number;
+} avo_cnv;
+
+typedef struct {
+  int32_t ploidy;             /* CopyNumberMap.basePloidy */
+  int32_t score_all_sites;    /* scoreAllSites (gVCF mode) */
+  int32_t max_quality;        /* call(maxQuality = 93) */
+  int32_t max_mapq;           /* call(maxMapQ = 93) */
+  int32_t min_phred_discover; /* optPhredThreshold.getOrElse(0) */
+  int32_t min_obs_discover;   /* optMinObservations; < 0 = None (distinct); keep count > this */
+} avo_params;
+
+/* ---- outputs ------------------------------------------------------------------------------ */
+/* Discovered variants, sorted (start, ref_len, alt_len, alleles).  Two-phase: on AVO_E_CAPACITY
+ * n and n_allele_nibbles hold the required capacities. */
+typedef struct {
+  int64_t capacity;        /* in: entries available */
+  int64_t allele_capacity; /* in: nibbles available in alleles4 */
+  int64_t n;               /* out */
+  int64_t n_allele_nibbles;/* out */
+  int32_t mem;
+  int32_t reserved;
+  int32_t* start;
+  int32_t* ref_len;
+  int32_t* alt_len;
+  uint32_t* allele_off; /* [capacity+1] */
+  uint8_t* alleles4;
+  int32_t* count;       /* supporting observations per variant (may be NULL) */
+} avo_sites_out;
+
+/* Per-site aggregate (Observation.scala:72-83, summed as BiallelicGenotyper.scala:475-500) and the
+ * genotype fields of BiallelicGenotyper.scala:677-748, one row per input site, same order.
+ * n_states = maxPloidy + 1 is the row stride of the likelihood arrays. */
+typedef struct {
+  int64_t n_sites;  /* in: == sites->n */
+  int32_t n_states; /* in */
+  int32_t mem;
+  uint8_t* emitted;      /* 1 iff >= 1 observation survived the score join (the reference emits
+                            only such sites); all other fields are zero when 0 */
+  int32_t* allele_fwd;   /* alleleForwardStrand */
+  int32_t* other_fwd;    /* otherForwardStrand */
+  int32_t* allele_cov;   /* alleleCoverage  -> alternateReadDepth */
+  int32_t* other_cov;    /* otherCoverage   -> referenceReadDepth */
+  int32_t* total_cov;    /* totalCoverage   -> readDepth */
+  double* square_mapq;
+  double* ref_ll;        /* [n * n_states] referenceLogLikelihoods */
+  double* allele_ll;     /* alleleLogLikelihoods */
+  double* other_ll;      /* otherLogLikelihoods */
+  double* nonref_ll;     /* nonRefLogLikelihoods */
+  uint8_t* first_is_ref; /* first("isRef") */
+  int32_t* copy_number;  /* first("copyNumber") */
+  int32_t* n_alt;        /* alleles = ALT x n_alt ++ REF x n_ref ++ OTHER_ALT x n_other */
+  int32_t* n_ref;
+  int32_t* n_other;
+  double* qual;          /* 10/ln10 * (max - second) */
+  int32_t* gq;           /* qual.toInt */
+  int32_t* sb;           /* [n * 4] strandBiasComponents */
+  float* fisher;         /* fisherStrandBiasPValue */
+  float* rms_mapq;
+  double* gl;            /* [n * n_states] genotypeLikelihoods (entries 0..copy_number) */
+  double* nonref_gl;     /* nonReferenceLikelihoods */
+} avo_site_results;
+
+/* Device-side time of the last call, measured with CUDA events on the context's stream. */
+typedef struct {
+  float ms_total;
+  float ms_h2d;       /* host -> device copies of inputs */
+  float ms_discover;  /* all discovery kernels */
+  float ms_observe;   /* observe/classify/reduce/genotype kernel (+ its set-up kernels) */
+  float ms_d2h;
+  float ms_discover_tiles; /* k_discover_tiles alone */
+  float ms_call_tiles;     /* k_call_tiles alone */
+  int32_t n_launches;      /* kernels launched by the call */
+  int32_t n_tile_launches; /* of which tile kernels (1 per stage unless a buffer overflowed) */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+} avo_timing;
+int avo_get_timing(const avo_ctx* ctx, avo_timing* out);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+/* DiscoverVariants.apply on one batch. */
+int avo_discover(avo_ctx* ctx, const avo_read_batch* reads, const avo_params* params,
+                 avo_sites_out* out);
+
+/* BiallelicGenotyper.call on one batch against a site table (variant-only mode). */
+int avo_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_sites* sites, const avo_cnv* cnv,
+             const avo_params* params, avo_site_results* out);
+
+/* BiallelicGenotyper.discoverAndCall: discovery, then call against the discovered sites, which
+ * stay on the device in between.  `results` rows correspond to `sites_out` rows; results->n_sites
+ * is an in/out capacity like sites_out->capacity. */
+int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_cnv* cnv,
+                          const avo_params* params, avo_sites_out* sites_out,
+                          avo_site_results* results);
+
+/* ---- host-side packer (PrefilterReads + ObservationOperator.extractAlignmentOperators) ------ */
+/* Text columns of AlignmentRecords (blobs + [n+1] offsets; has_* bits in rec_flags:
+ * bit0 readMapped, bit1 readNegativeStrand, bit2 cigar present, bit3 MD present, bit4 mapq present).
+ * Packs the reads for which keep[i] != 0 (NULL = all mapped reads), in input order.  Output
+ * arrays must be sized for the upper bounds returned by avo_pack_bounds. */
+typedef struct {
+  int64_t n;
+  const int64_t* start;
+  const int64_t* end;
+  const int32_t* mapq;
+  const uint8_t* rec_flags;
+  const char* cigar; const int64_t* cigar_off;
+  const char* md;    const int64_t* md_off;
+  const char* seq;   const int64_t* seq_off;
+  const char* qual;  const int64_t* qual_off;
+  const uint8_t* keep;
+} avo_text_reads;
+
+typedef struct {
+  int64_t n_reads, n_bases, n_ops, n_refb; /* in: capacities; out: used */
+  int32_t* start; int32_t* end; uint8_t* mapq; uint8_t* flags;
+  uint32_t* seq_off; uint8_t* bases4; uint8_t* quals;
+  uint32_t* op_off; uint32_t* ops; uint32_t* refb_off; uint8_t* refb4;
+  int64_t* source_index; /* [n_reads] index of each packed read in the input (may be NULL) */
+} avo_packed_out;
+
+int avo_pack_bounds(const avo_text_reads* in, int64_t* n_reads, int64_t* n_bases, int64_t* n_ops,
+                    int64_t* n_refb);
+int avo_pack_reads(const avo_text_reads* in, avo_packed_out* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVOCADO_B200_H */

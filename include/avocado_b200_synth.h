@@ -1,0 +1,46 @@
+/* avocado_b200_synth.h -- seeded synthetic read generator exported by libavocado_b200.so.
+ *
+ * Bench / test infrastructure, NOT part of the reference's interface: it produces the packed
+ * batches of avocado_b200.h directly (SURVEY.md 8(d) shapes) so that full-size benchmark inputs
+ * are born in HBM.  The same stateless generator runs on the host for the small cases that are
+ * handed to the CPU oracle; both produce identical bytes.
+ */
+#ifndef AVOCADO_B200_SYNTH_H
+#define AVOCADO_B200_SYNTH_H
+
+#include <stdint.h>
+
+#include "avocado_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  uint64_t seed;
+  int32_t contig_len;     /* reads start in [first_pos, first_pos + contig_len - read_len - slack) */
+  int32_t first_pos;
+  int64_t n_reads_total;  /* reads of the whole contig; read i starts near i/n_reads_total of it */
+  int32_t read_len;
+  int32_t max_indel;      /* <= 20 */
+  double snp_rate;        /* per reference base */
+  double indel_rate;
+  double triallelic_frac; /* fraction of SNV sites carrying two different alts */
+  double softclip_frac;   /* fraction of reads soft-clipped 1..20 bases at one end */
+} avo_synth_params;
+
+int avo_synth_default_params(avo_synth_params* p);
+
+/* Host generation of reads [first, first+n).  out == NULL: only count (n_ops / n_refb totals). */
+int avo_synth_host(const avo_synth_params* p, int64_t first, int64_t n, int64_t* n_ops,
+                   int64_t* n_refb, avo_packed_out* out);
+
+/* Device generation, two phases (see avo_synth.cu).  All array pointers are device pointers. */
+int avo_synth_device(const avo_synth_params* p, int64_t first, int64_t n, uint32_t* op_off_dev,
+                     uint32_t* refb_off_dev, int64_t* n_ops, int64_t* n_refb, avo_packed_out* out,
+                     void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1255,6 +1255,59 @@ static std::shared_ptr<ReadSet> makeReads(
   return rs;
 }
 
+
+// Packed columnar batch (include/avocado_b200.h) -> text AlignmentRecords, so that synthetic
+// batches (which are born packed) can be handed to the oracle.  CIGAR uses =/X/I/D/S/H, the MD
+// tag is rebuilt from the =/X/D runs.  skip-call reads get a null mapq (what the flag stands for).
+static std::shared_ptr<ReadSet> readsFromPacked(
+    const std::string& contigName,
+    py::array_t<int32_t, py::array::c_style | py::array::forcecast> start,
+    py::array_t<int32_t, py::array::c_style | py::array::forcecast> end,
+    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> mapq,
+    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> flags,
+    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> seqOff,
+    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> bases4,
+    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> quals,
+    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> opOff,
+    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> ops,
+    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> refbOff,
+    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> refb4) {
+  static const char* NIBS = "=ACMGRSVTWYHKDBN";
+  auto rs = std::make_shared<ReadSet>();
+  const size_t n = (size_t)start.size();
+  auto st = start.unchecked<1>(); auto en = end.unchecked<1>(); auto mq = mapq.unchecked<1>();
+  auto fl = flags.unchecked<1>(); auto so = seqOff.unchecked<1>(); auto b4 = bases4.unchecked<1>();
+  auto ql = quals.unchecked<1>(); auto oo = opOff.unchecked<1>(); auto op = ops.unchecked<1>();
+  auto fo = refbOff.unchecked<1>(); auto f4 = refb4.unchecked<1>();
+  auto nib = [](const auto& a, uint64_t i) -> int { int b = a(i >> 1); return (i & 1) ? (b & 15) : (b >> 4); };
+  rs->reads.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    Read& r = rs->reads[i];
+    r.mapped = true; r.contigName = contigName; r.hasStart = true;
+    r.start = st(i); r.end = en(i);
+    r.negativeStrand = fl(i) & 1;
+    r.hasMapq = !(fl(i) & 2); r.mapq = mq(i);
+    const uint64_t b0 = so(i), b1 = so(i + 1);
+    for (uint64_t b = b0; b < b1; ++b) { r.seq.push_back(NIBS[nib(b4, b)]); r.qual.push_back((char)(ql(b) + 33)); }
+    uint64_t f = fo(i);
+    long run = 0;
+    std::string md;
+    bool any = false;
+    for (uint32_t k = oo(i); k < oo(i + 1); ++k) {
+      const uint32_t w = op(k), len = w >> 4, code = w & 15;
+      any = true;
+      r.cigar += std::to_string(len) + "=XIDSH"[code];
+      if (code == 0) run += len;
+      else if (code == 1) { for (uint32_t j = 0; j < len; ++j) { md += std::to_string(run); md.push_back(NIBS[nib(f4, f++)]); run = 0; } }
+      else if (code == 3) { md += std::to_string(run) + "^"; for (uint32_t j = 0; j < len; ++j) md.push_back(NIBS[nib(f4, f++)]); run = 0; }
+    }
+    md += std::to_string(run);
+    r.hasCigar = any; r.hasMd = any;
+    r.md = md;
+  }
+  return rs;
+}
+
 static Read readFromDict(const py::dict& d) {
   Read r;
   auto has = [&](const char* k) { return d.contains(k) && !d[k].is_none(); };
@@ -1328,6 +1381,18 @@ PYBIND11_MODULE(avocado_oracle, m) {
       .def("__len__", [](const ReadSet& r) { return r.reads.size(); });
   m.def("make_reads", &makeReads);
   m.def("reads_from_dicts", &readsFromDicts);
+  m.def("reads_from_packed", &readsFromPacked);
+  m.def("read_as_dict", [](std::shared_ptr<ReadSet> rs, size_t i) {
+    const Read& r = rs->reads.at(i);
+    py::dict d;
+    d["readMapped"] = r.mapped; d["contigName"] = r.contigName; d["start"] = r.start; d["end"] = r.end;
+    d["cigar"] = r.hasCigar ? py::object(py::str(r.cigar)) : py::object(py::none());
+    d["mismatchingPositions"] = r.hasMd ? py::object(py::str(r.md)) : py::object(py::none());
+    d["sequence"] = r.seq; d["qual"] = r.qual;
+    d["mapq"] = r.hasMapq ? py::object(py::int_(r.mapq)) : py::object(py::none());
+    d["readNegativeStrand"] = r.negativeStrand;
+    return d;
+  });
 
   m.def("extract_alignment_operators", [](const py::dict& d) {
     return opsToString(extractAlignmentOperators(readFromDict(d)));

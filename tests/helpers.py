@@ -58,3 +58,74 @@ def rows(res):
         d["alleles"] = alleles_of(res, i)
         out.append(d)
     return out
+
+
+# ---- GPU parity glue ----------------------------------------------------------------------------
+def oracle_reads_from_batch(oracle, batch, contig="ctg"):
+    b = batch.to_host()
+    return oracle.reads_from_packed(contig, b.start, b.end, b.mapq, b.flags, b.seq_off, b.bases4,
+                                    b.quals, b.op_off, b.ops, b.refb_off, b.refb4)
+
+
+ORACLE_OF = {  # product column -> oracle column
+    "allele_fwd": "alleleForwardStrand", "other_fwd": "otherForwardStrand", "allele_cov": "alleleCoverage",
+    "other_cov": "otherCoverage", "total_cov": "totalCoverage", "square_mapq": "squareMapQ",
+    "ref_ll": "referenceLogLikelihoods", "allele_ll": "alleleLogLikelihoods",
+    "other_ll": "otherLogLikelihoods", "nonref_ll": "nonRefLogLikelihoods", "first_is_ref": "isRef",
+    "copy_number": "copyNumber", "n_alt": "nAlt", "n_ref": "nRef", "n_other": "nOther", "qual": "qual",
+    "gq": "genotypeQuality", "sb": "strandBiasComponents", "fisher": "fisherStrandBiasPValue",
+    "rms_mapq": "rmsMapQ", "gl": "genotypeLikelihoods", "nonref_gl": "nonReferenceLikelihoods"}
+INT_COLS = ["allele_fwd", "other_fwd", "allele_cov", "other_cov", "total_cov", "first_is_ref",
+            "copy_number", "n_alt", "n_ref", "n_other", "gq", "sb"]
+FP_COLS = ["square_mapq", "ref_ll", "allele_ll", "other_ll", "nonref_ll", "qual", "fisher", "rms_mapq",
+           "gl", "nonref_gl"]
+REL_TOL = 1e-6   # north_star: floating-point likelihoods and qualities within 1e-6 relative
+
+
+def compare_call(site_keys, cols, want, exact_fp=True):
+    """site_keys[i] = (contig, start, ref, alt) of product row i.  Checks that the product emits
+    exactly the oracle's sites and that every column agrees: integers / alleles / genotypes
+    bit-exact, floating point within REL_TOL (and, when exact_fp, bit-identical: the product sums
+    in the oracle's read order from the same libm-built table)."""
+    import numpy as np
+    okey = {(c, int(s), r, a): j for j, (c, s, r, a) in enumerate(
+        zip(want["contigName"], want["start"], want["referenceAllele"], want["alternateAllele"]))}
+    emitted = [i for i in range(len(site_keys)) if cols["emitted"][i]]
+    got_keys = {site_keys[i] for i in emitted}
+    assert got_keys == set(okey), "emitted sites differ: only GPU %s / only oracle %s" % (
+        sorted(got_keys - set(okey))[:5], sorted(set(okey) - got_keys)[:5])
+    idx_g = np.array(emitted, dtype=np.int64)
+    idx_o = np.array([okey[site_keys[i]] for i in emitted], dtype=np.int64)
+    stats = {"sites": len(emitted), "max_rel": 0.0, "fp_bit_identical": True}
+    if len(emitted) == 0:
+        return stats
+    for c in INT_COLS:
+        g, o = np.asarray(cols[c])[idx_g], np.asarray(want[ORACLE_OF[c]])[idx_o]
+        assert np.array_equal(g.astype(np.int64), o.astype(np.int64)), "column %s differs" % c
+    for c in FP_COLS:
+        g = np.asarray(cols[c])[idx_g].astype(np.float64)
+        o = np.asarray(want[ORACLE_OF[c]])[idx_o].astype(np.float64)
+        if g.ndim == 2:
+            # entries beyond a site's copy number are unspecified in the reference; compare 0..cn
+            cn = np.asarray(cols["copy_number"])[idx_g]
+            mask = np.arange(g.shape[1])[None, :] <= cn[:, None]
+            if c in ("ref_ll", "allele_ll", "other_ll", "nonref_ll"):
+                mask = np.ones_like(mask)
+            g, o = g[mask], o[mask]
+        same_nan = np.isnan(g) == np.isnan(o)
+        assert same_nan.all(), "NaN pattern differs in " + c
+        fin = ~np.isnan(g)
+        inf = np.isinf(g) | np.isinf(o)
+        assert np.array_equal(g[inf], o[inf]), "inf pattern differs in " + c
+        fin &= ~inf
+        denom = np.maximum(np.abs(o[fin]), 1e-300)
+        rel = np.abs(g[fin] - o[fin]) / denom
+        rel[(g[fin] == o[fin])] = 0.0
+        if rel.size:
+            stats["max_rel"] = max(stats["max_rel"], float(rel.max()))
+        assert (rel <= REL_TOL).all(), "column %s exceeds %g relative (max %g)" % (c, REL_TOL, rel.max())
+        if not np.array_equal(g[fin], o[fin]):
+            stats["fp_bit_identical"] = False
+    if exact_fp:
+        assert stats["fp_bit_identical"], "floating-point columns are within tolerance but not bit-identical"
+    return stats

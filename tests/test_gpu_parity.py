@@ -1,0 +1,170 @@
+"""GPU parity tests: the CUDA path, through the C ABI, against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): bit-exact observation counts, allele assignments and called
+genotypes; floating-point likelihoods and qualities within 1e-6 relative (helpers.REL_TOL).  The
+product additionally sums in the oracle's canonical read order, so the tests also require the
+floating-point columns to be bit-identical.
+"""
+import numpy as np
+import pytest
+
+from helpers import (compare_call, load_fixture, oracle_call, oracle_discover, oracle_reads_from_batch)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from avocado_b200.genotyping import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def mapq_gt(recs, thr):
+    return [r for r in recs if r.mapq is not None and r.mapq > thr]
+
+
+E2E = [  # fixture, mapq filter, phred, min_obs   (TEST/genotyping/BiallelicGenotyperSuite.scala:383-911)
+    ("NA12878_snp_A2G_chr20_225058", 0, None, None),
+    ("NA12878.chr1.832736", 0, None, None),
+    ("NA12878.chr1.839395", 0, None, None),
+    ("NA12878.chr1.567239", 0, None, None),
+    ("NA12878.chr1.875159", 0, None, None),
+    ("NA12878.1_1777263", 0, None, 3),
+    ("NA12878.1_1067596", None, None, None),
+    ("NA12878.chr1.877715", 0, None, None),
+    ("NA12878.chr1.886049", 0, None, None),
+    ("NA12878.chr1.889159", 0, 30, None),
+    ("NA12878.chr1.866511", 0, 30, None),
+    ("NA12878.chr1.905130", 0, 30, None),
+    ("NA12878.chr1.905130", 0, 30, 4),
+    ("NA12878.chr1.907170", 0, 30, None),
+    ("NA12878.chr1.240898", 10, 25, None),
+    ("NA12878.1_4120185", None, 18, 3),
+    ("NA12878.1_5274547", None, 18, 3),
+    ("NA12878.chr1.104160", 0, None, None),
+    ("NA12878.chr1.875635", 0, 25, 5),
+]
+
+
+@pytest.mark.parametrize("name,mq,phred,min_obs", E2E)
+def test_fixture_discover_and_call_matches_oracle(oracle, ctx, name, mq, phred, min_obs):
+    from avocado_b200.genotyping import BiallelicGenotyper, DiscoverVariants
+    recs = load_fixture(name)[0]
+    if mq is not None:
+        recs = mapq_gt(recs, mq)
+    want_v = oracle_discover(oracle, recs, phred, min_obs)
+    got_v = DiscoverVariants(recs, phred, min_obs, ctx=ctx)
+    assert sorted(v.as_tuple() for v in got_v) == sorted(want_v)
+    if not want_v:
+        return
+    want = oracle_call(oracle, recs, want_v)
+    gts = BiallelicGenotyper.discoverAndCall(recs, optPhredThreshold=phred, optMinObservations=min_obs,
+                                             samples=["s"], ctx=ctx)
+    # rebuild columns from the record-level API to compare with the oracle
+    keys = [(g.contigName, g.start, g.variant.referenceAllele, g.variant.alternateAllele) for g in gts]
+    okeys = list(zip(want["contigName"], [int(s) for s in want["start"]], want["referenceAllele"],
+                     want["alternateAllele"]))
+    assert sorted(keys) == sorted(okeys)
+    oi = {k: j for j, k in enumerate(okeys)}
+    for g in gts:
+        j = oi[(g.contigName, g.start, g.variant.referenceAllele, g.variant.alternateAllele)]
+        assert g.alleles == ["ALT"] * int(want["nAlt"][j]) + ["REF"] * int(want["nRef"][j]) + \
+            ["OTHER_ALT"] * int(want["nOther"][j])
+        assert g.genotypeQuality == want["genotypeQuality"][j]
+        assert g.readDepth == want["totalCoverage"][j]
+        assert g.referenceReadDepth == want["otherCoverage"][j]
+        assert g.alternateReadDepth == want["alleleCoverage"][j]
+        assert g.strandBiasComponents == list(want["strandBiasComponents"][j])
+        cn = int(want["copyNumber"][j])
+        assert g.genotypeLikelihoods == list(want["genotypeLikelihoods"][j][:cn + 1])
+        assert g.nonReferenceLikelihoods == list(want["nonReferenceLikelihoods"][j][:cn + 1])
+        assert np.float32(g.rmsMapQ) == want["rmsMapQ"][j] or (np.isnan(g.rmsMapQ) and np.isnan(want["rmsMapQ"][j]))
+        assert np.float32(g.fisherStrandBiasPValue) == want["fisherStrandBiasPValue"][j]
+
+
+def test_reference_e2e_expectations_on_gpu(ctx):
+    """A few of the reference's own assertions evaluated directly on the GPU output
+    (BiallelicGenotyperSuite.scala:383-410, 600-619, 828-863, 890-911)."""
+    from avocado_b200.genotyping import BiallelicGenotyper
+    from avocado_b200.records import AlignmentRecord
+    recs = mapq_gt(load_fixture("NA12878_snp_A2G_chr20_225058")[0], 0)
+    gts = [g for g in BiallelicGenotyper.discoverAndCall(recs, samples=["s"], ctx=ctx)
+           if g.readDepth > 10 and not all(a == "REF" for a in g.alleles) and g.genotypeQuality > 30]
+    assert len(gts) == 1
+    g = gts[0]
+    assert (g.start, g.end, g.variant.referenceAllele, g.variant.alternateAllele) == (225057, 225058, "A", "G")
+    assert sorted(g.alleles) == ["ALT", "REF"]
+
+    recs = mapq_gt(load_fixture("NA12878.1_1777263")[0], 0)
+    gts = BiallelicGenotyper.discoverAndCall(recs, optMinObservations=3, samples=["s"], ctx=ctx)
+    assert len(gts) == 1 and gts[0].start == 1777262 and gts[0].alleles == ["ALT", "ALT"]
+    assert gts[0].variant.referenceAllele == "TACACACACACACACACACACACACACACAC"
+
+    def make_read(allele):
+        return AlignmentRecord(contigName="ctg", start=10, end=15, sequence="AC%sTG" % allele, cigar="5M",
+                               mismatchingPositions="2T2", qual="8383838383", mapq=50, readMapped=True)
+    gts = BiallelicGenotyper.discoverAndCall([make_read("A")] * 4 + [make_read("C")] * 4, samples=["s"], ctx=ctx)
+    assert len(gts) == 2 and {g.variant.alternateAllele for g in gts} == {"A", "C"}
+    assert all(sorted(g.alleles) == ["ALT", "OTHER_ALT"] and g.genotypeQuality == 67 for g in gts)
+
+    recs = load_fixture("NA12878.1_5274547")[0]
+    gts = BiallelicGenotyper.discoverAndCall(recs, optPhredThreshold=18, optMinObservations=3,
+                                             samples=["s"], ctx=ctx)
+    assert len(gts) == 2 and all(g.start == 5274546 and g.variant.alternateAllele == "T" for g in gts)
+    assert sorted(g.variant.referenceAllele for g in gts) == ["TTA", "TTATA"]
+    assert all(sorted(g.alleles) == ["ALT", "OTHER_ALT"] for g in gts)
+
+
+@pytest.mark.parametrize("seed,n_reads,contig_len,phred,min_obs", [
+    (1, 6000, 30000, 25, 5), (2, 20000, 100000, 25, 5), (3, 3000, 10000, 0, None),
+    (4, 12000, 40000, 30, 2), (5, 40000, 100000, 25, 5)])
+def test_synthetic_batch_matches_oracle(oracle, ctx, seed, n_reads, contig_len, phred, min_obs):
+    from avocado_b200 import batch as B
+    p = B.synth_params(seed=seed, n_reads_total=n_reads, contig_len=contig_len, first_pos=1000 * seed)
+    host = B.synth_host(p)
+    dev = B.synth_device(p)
+    dh = dev.to_host()
+    for name, _ in B.READ_COLUMNS:      # host and device generators agree byte for byte
+        a = getattr(host, name)
+        assert np.array_equal(a, getattr(dh, name)[:len(a)]), name
+    rs = oracle_reads_from_batch(oracle, host)
+    want_v = oracle.discover(rs, phred, min_obs)
+    # discovery: host-resident input and device-resident input give the same table
+    sites = ctx.discover_packed(host, phred=phred, min_obs=min_obs)
+    sites_d = ctx.discover_packed(dev, phred=phred, min_obs=min_obs)
+    got = [(v.start, v.end, v.referenceAllele, v.alternateAllele) for v in sites.to_variants(["ctg"])]
+    assert got == [(v.start, v.end, v.referenceAllele, v.alternateAllele) for v in sites_d.to_variants(["ctg"])]
+    assert sorted(got) == sorted((s, e, r, a) for _, s, e, r, a, _ in want_v)
+    assert sorted(zip(got, sites.count.tolist())) == sorted(((s, e, r, a), n) for _, s, e, r, a, n in want_v)
+    # call against those sites
+    want = oracle.call(rs, [(c, s, e, r, a) for c, s, e, r, a, _ in want_v], 2, [], False, 93, 93, 1)
+    cols = ctx.call_packed(dev, sites)
+    keys = [("ctg", s, r, a) for (s, e, r, a) in got]
+    st = compare_call(keys, cols, want)
+    assert st["sites"] > 0
+    # fused entry point gives the same rows
+    sites2, cols2 = ctx.discover_and_call_packed(host, phred=phred, min_obs=min_obs)
+    assert np.array_equal(sites2.start, sites.start)
+    for k in cols:
+        assert np.array_equal(np.asarray(cols[k]), np.asarray(cols2[k]), equal_nan=True), k
+
+
+def test_empty_sites_and_unsorted_reads_are_errors(ctx):
+    from avocado_b200 import _lib as L, batch as B
+    from avocado_b200.genotyping import BiallelicGenotyper
+    from avocado_b200.records import AlignmentRecord
+    r = AlignmentRecord(readMapped=True, contigName="1", start=10, end=18, sequence="ACACATGA",
+                        qual="!!!!!!!!", cigar="8M", mismatchingPositions="8", mapq=30)
+    with pytest.raises(L.AvocadoError) as e:       # TreeRegionJoin.scala:77 throws on an empty forest
+        BiallelicGenotyper.call([r], [], samples=["s"], ctx=ctx)
+    assert e.value.status == L.AVO_E_EMPTY_SITES
+    p = B.synth_params(n_reads_total=1000, contig_len=5000)
+    b = B.synth_host(p)
+    b.start = np.ascontiguousarray(b.start[::-1])
+    with pytest.raises(L.AvocadoError) as e:
+        ctx.discover_packed(b)
+    assert e.value.status == L.AVO_E_UNSORTED
+    with pytest.raises(ValueError):                 # BG:102-105 exactly one sample
+        BiallelicGenotyper.call([r], [], samples=["a", "b"], ctx=ctx)

@@ -54,6 +54,9 @@ def test_fixture_discover_and_call_matches_oracle(oracle, ctx, name, mq, phred, 
     recs = load_fixture(name)[0]
     if mq is not None:
         recs = mapq_gt(recs, mq)
+    # the product's canonical summation order is the batch order = reads stably sorted by start;
+    # hand the oracle the same order (the reference's own order is Spark's partition order)
+    recs = sorted([r for r in recs if r.readMapped], key=lambda r: (r.contigName, r.start))
     want_v = oracle_discover(oracle, recs, phred, min_obs)
     got_v = DiscoverVariants(recs, phred, min_obs, ctx=ctx)
     assert sorted(v.as_tuple() for v in got_v) == sorted(want_v)
@@ -126,9 +129,11 @@ def test_synthetic_batch_matches_oracle(oracle, ctx, seed, n_reads, contig_len, 
     host = B.synth_host(p)
     dev = B.synth_device(p)
     dh = dev.to_host()
+    used = {"bases4": (host.n_bases + 1) // 2, "quals": host.n_bases, "ops": host.n_ops,
+            "refb4": (host.n_refb + 1) // 2}
     for name, _ in B.READ_COLUMNS:      # host and device generators agree byte for byte
-        a = getattr(host, name)
-        assert np.array_equal(a, getattr(dh, name)[:len(a)]), name
+        n = used.get(name, len(getattr(host, name)))
+        assert np.array_equal(getattr(host, name)[:n], getattr(dh, name)[:n]), name
     rs = oracle_reads_from_batch(oracle, host)
     want_v = oracle.discover(rs, phred, min_obs)
     # discovery: host-resident input and device-resident input give the same table

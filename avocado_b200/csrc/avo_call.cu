@@ -15,8 +15,6 @@
 // binary search, including a look-back of max read span).  Because each site is reduced by exactly
 // one CTA, in read order, the fp64 likelihood sums are produced in the batch's read order --
 // the same order the oracle uses -- and no atomics or cross-CTA combine are needed.
-#include <cub/block/block_scan.cuh>
-
 #include "avo_device.cuh"
 
 namespace avo {
@@ -25,7 +23,6 @@ constexpr int CALL_THREADS = 256;
 constexpr int CALL_WARPS = CALL_THREADS / 32;
 constexpr int CALL_W = 4096;        // window width in bases
 constexpr int SCHUNK = 16;          // owned sites reduced at a time
-constexpr int REC_CAP = 2048;       // records staged in shared memory per round
 constexpr int MAX_LOCAL_SITES = 32; // per-read category cache
 constexpr int NSMAX = AVO_MAX_PLOIDY + 1;
 
@@ -200,23 +197,28 @@ __device__ __forceinline__ uint32_t make_record(int slot, uint32_t cat, bool fwd
          ((uint32_t)mq << 14) | ((uint32_t)cni << 21);
 }
 
-// Everything one read contributes to the owned site chunk [cLo, cHi): returns the number of
+// Join part (TreeRegionJoin): the read's Forest.get range [a, b); false when the read yields
+// nothing for the owned site chunk [cLo, cHi).
+__device__ __forceinline__ bool join_read(const DReads& R, const DSites& S, int32_t r, int32_t cLo,
+                                          int32_t cHi, int32_t hLo, int32_t hHi, int32_t& a, int32_t& b) {
+  if (__ldg(R.flags + r) & AVO_READ_SKIP_CALL) return false;
+  forest_get(S, R.contig, __ldg(R.start + r), __ldg(R.end + r), hLo, hHi, a, b);
+  if (a >= b) return false;                               // no overlapping variant: read dropped
+  if (b <= cLo || a >= cHi) return false;                 // nothing of this chunk
+  return __ldg(R.op_off + r + 1) != __ldg(R.op_off + r);  // no operators -> no observations
+}
+
+// Everything one joined read contributes to the owned site chunk [cLo, cHi): returns the number of
 // records written to recs[] (at most SCHUNK).
-__device__ int process_read(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
-                            int64_t r, int32_t cLo, int32_t cHi, int32_t hLo, int32_t hHi,
-                            uint32_t* recs) {
+__device__ int classify_read(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
+                             int32_t r, int32_t a, int32_t b, int32_t cLo, int32_t cHi,
+                             uint32_t* recs) {
   const uint32_t flags = __ldg(R.flags + r);
-  if (flags & AVO_READ_SKIP_CALL) return 0;
   ReadCtx rc;
   rc.start = __ldg(R.start + r);
   rc.end = __ldg(R.end + r);
-  int32_t a, b;
-  forest_get(S, R.contig, rc.start, rc.end, hLo, hHi, a, b);
-  if (a >= b) return 0;                                   // no overlapping variant: read dropped
-  if (b <= cLo || a >= cHi) return 0;                     // nothing of this chunk
   rc.ob = __ldg(R.op_off + r);
   rc.no = __ldg(R.op_off + r + 1) - rc.ob;
-  if (rc.no == 0) return 0;
   rc.sb = __ldg(R.seq_off + r);
   rc.mapq = __ldg(R.mapq + r);
   rc.fwd = !(flags & AVO_READ_NEGATIVE_STRAND);
@@ -350,12 +352,144 @@ __device__ void finalize_site(const DCallParams& P, const DResults& O, int32_t s
   O.rms_mapq[site] = (float)sqrt(sq / (double)(A.allele_cov + A.other_cov));    // BG:709
 }
 
+constexpr int WREC_CAP = 512;              // records per warp region; >= 32 * SCHUNK guarantees progress
+constexpr int MIN_SEG = CALL_WARPS * 32;   // smallest super-segment: one read per lane
+constexpr int QCAP = 64;
+
 struct __align__(16) CallSmem {
   SiteAcc acc[SCHUNK];
-  uint32_t rec[REC_CAP];
-  typename cub::BlockScan<int, CALL_THREADS>::TempStorage scan;
+  uint32_t rec[CALL_WARPS][WREC_CAP];  // warp-private record regions; region order == read order
+  int32_t wcount[CALL_WARPS];
+  int32_t q_read[CALL_WARPS][QCAP];    // per-warp queue of joined reads awaiting classification
+  int32_t q_a[CALL_WARPS][QCAP];
+  int32_t q_b[CALL_WARPS][QCAP];
   int32_t tile;
+  int32_t overflow;
 };
+
+// Phase A for one warp: reads [bLo, bHi) in order.  Lanes first run the join for 32 reads at a
+// time and compact the joined ones into the warp's queue; whenever 32 are pending (or the block is
+// exhausted) each lane classifies one of them, so that the expensive part runs at full SIMD width.
+// Records land in the warp's private region in read order.
+__device__ __forceinline__ void phase_a_warp(const DReads& R, const DSites& S, const DCnv& C,
+                                             const DCallParams& P, CallSmem& sm, int warp, int lane,
+                                             int32_t bLo, int32_t bHi, int32_t cLo, int32_t cHi,
+                                             int32_t hLo, int32_t hHi) {
+  int wc = 0, qn = 0;
+  int32_t base = bLo;
+  const unsigned lt = (1u << lane) - 1u;
+  while (base < bHi || qn > 0) {
+    if (base < bHi) {
+      const int32_t r = base + lane;
+      int32_t a = 0, b = 0;
+      const bool joined = (r < bHi) && join_read(R, S, r, cLo, cHi, hLo, hHi, a, b);
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, joined);
+      if (joined) {
+        const int slot = qn + __popc(m & lt);
+        sm.q_read[warp][slot] = r; sm.q_a[warp][slot] = a; sm.q_b[warp][slot] = b;
+      }
+      qn += __popc(m);
+      base += 32;
+      __syncwarp();
+    }
+    if (qn >= 32 || (base >= bHi && qn > 0)) {
+      const int take = min(qn, 32);
+      uint32_t recs[SCHUNK];
+      int nrec = 0;
+      if (lane < take)
+        nrec = classify_read(R, S, C, P, sm.q_read[warp][lane], sm.q_a[warp][lane], sm.q_b[warp][lane],
+                             cLo, cHi, recs);
+      int incl = nrec;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      const int off = wc + incl - nrec;
+      if (wc + total <= WREC_CAP) {
+        for (int i = 0; i < nrec; ++i) sm.rec[warp][off + i] = recs[i];
+      } else if (lane == 0) {
+        sm.overflow = 1;
+      }
+      wc += total;
+      // pop the classified entries
+      const int rest = qn - take;
+      int32_t tr = 0, ta = 0, tb = 0;
+      if (lane < rest) { tr = sm.q_read[warp][take + lane]; ta = sm.q_a[warp][take + lane]; tb = sm.q_b[warp][take + lane]; }
+      __syncwarp();
+      if (lane < rest) { sm.q_read[warp][lane] = tr; sm.q_a[warp][lane] = ta; sm.q_b[warp][lane] = tb; }
+      qn = rest;
+      __syncwarp();
+    }
+  }
+  if (lane == 0) sm.wcount[warp] = min(wc, WREC_CAP);
+}
+
+// Phase B for one site slot: scan every warp region in order, accumulate in read order.
+__device__ __forceinline__ void phase_b_slot(const DCallParams& P, CallSmem& sm, int slot, int lane) {
+  SiteAcc& A = sm.acc[slot];
+  int c_afw = 0, c_ofw = 0, c_acov = 0, c_ocov = 0, c_tot = 0;
+  unsigned long long sq = 0;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  const bool ll_lane = lane < P.ns;
+  if (ll_lane) { a0 = A.ll[0][lane]; a1 = A.ll[1][lane]; a2 = A.ll[2][lane]; a3 = A.ll[3][lane]; }
+  int seen = A.seen, first_is_ref = A.first_is_ref, first_cn = A.copy_number;
+  for (int wreg = 0; wreg < CALL_WARPS; ++wreg) {
+    const int cnt = sm.wcount[wreg];
+    const uint32_t* rec = sm.rec[wreg];
+    for (int i0 = 0; i0 < cnt; i0 += 32) {
+      const int i = i0 + lane;
+      const uint32_t w = (i < cnt) ? rec[i] : 0xFFFFFFFFu;
+      const bool mine = (i < cnt) && ((w & 15u) == (uint32_t)slot);
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, mine);
+      if (m == 0) continue;
+      const uint32_t cat = (w >> 4) & 3u;
+      const bool fwd = (w >> 6) & 1u;
+      const unsigned isRef = __ballot_sync(0xFFFFFFFFu, mine && cat == CAT_REF);
+      const unsigned isAl = __ballot_sync(0xFFFFFFFFu, mine && (cat == CAT_ALT || cat == CAT_NONREF));
+      const unsigned fw = __ballot_sync(0xFFFFFFFFu, mine && fwd);
+      c_tot += __popc(m);                                        // ScoredObservation.scala:88
+      c_ocov += __popc(isRef);                                   // :87
+      c_acov += __popc(isAl);                                    // :86
+      c_ofw += __popc(isRef & fw);                               // :80
+      c_afw += __popc(isAl & fw);                                // :79
+      if (mine) { const unsigned long long q = (w >> 14) & 127u; sq += q * q; }  // :81
+      if (!seen) {                                               // first("isRef"), first("copyNumber")
+        const int f = __ffs(m) - 1;
+        const uint32_t wf = __shfl_sync(0xFFFFFFFFu, w, f);
+        first_is_ref = (((wf >> 4) & 3u) == CAT_REF);
+        first_cn = (int)((wf >> 21) & 15u) + P.min_ploidy;
+        seen = 1;
+      }
+      // ordered fp64 accumulation: lane g owns state g of the four arrays
+      unsigned mm = m;
+      while (mm) {
+        const int src = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const uint32_t ws = __shfl_sync(0xFFFFFFFFu, w, src);
+        if (ll_lane) {
+          const uint32_t c = (ws >> 4) & 3u;
+          const int q = (ws >> 7) & 127u, mq = (ws >> 14) & 127u, cni = (ws >> 21) & 15u;
+          const double v = __ldg(P.lut + ((((int64_t)cni * (P.max_quality + 1) + q) *
+                                           (P.max_mapq + 1) + mq) * P.ns + lane));
+          // Spark sums every column for every row; the non-selected arrays add 0.0
+          a0 += (c == 0) ? v : 0.0;
+          a1 += (c == 1) ? v : 0.0;
+          a2 += (c == 2) ? v : 0.0;
+          a3 += (c == 3) ? v : 0.0;
+        }
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
+  if (ll_lane) { A.ll[0][lane] = a0; A.ll[1][lane] = a1; A.ll[2][lane] = a2; A.ll[3][lane] = a3; }
+  if (lane == 0) {
+    A.sq += sq;
+    A.allele_fwd += c_afw; A.other_fwd += c_ofw; A.allele_cov += c_acov;
+    A.other_cov += c_ocov; A.total_cov += c_tot;
+    A.seen = seen; A.first_is_ref = first_is_ref; A.copy_number = first_cn;
+  }
+}
 
 __global__ void __launch_bounds__(CALL_THREADS)
 k_call_tiles(DReads R, DSites S, DCnv C, DCallParams P, DResults O, DIndex X, int32_t n_tiles,
@@ -381,105 +515,44 @@ k_call_tiles(DReads R, DSites S, DCnv C, DCallParams P, DResults O, DIndex X, in
 
     for (int32_t cLo = sLo; cLo < sHi; cLo += SCHUNK) {
       const int32_t cHi = min(cLo + SCHUNK, sHi);
-      // zero the accumulators
       for (int i = tid; i < (int)(sizeof(SiteAcc) * SCHUNK / 4); i += CALL_THREADS)
         reinterpret_cast<uint32_t*>(sm.acc)[i] = 0u;
+      if (tid == 0) sm.overflow = 0;
       // reads that can overlap a site of the chunk: start < max site end, start >= first site start - max_span
       int32_t maxEnd = INT32_MIN;
       for (int32_t j = cLo; j < cHi; ++j) maxEnd = max(maxEnd, __ldg(S.end + j));
       const int64_t loKey = (int64_t)__ldg(S.start + cLo) - max_span;
       // over-approximate (by < one index bin each side) read range and site search range
-      const int64_t rLo = __ldg(X.ridx + idx_bin_floor(X, loKey));
-      const int64_t rHi = __ldg(X.ridx + idx_bin_ceil(X, maxEnd));
+      const int32_t rLo = __ldg(X.ridx + idx_bin_floor(X, loKey));
+      const int32_t rHi = __ldg(X.ridx + idx_bin_ceil(X, maxEnd));
       const int32_t hLo = (loKey <= X.win0) ? S.c_lo : __ldg(X.sidx + idx_bin_floor(X, loKey));
       // reads of the range start before maxEnd + IDX_G and end within max_span of their start
       const int32_t hb = idx_bin_ceil(X, (int64_t)maxEnd + max_span) + 1;
       const int32_t hHi = (hb >= X.nb) ? S.c_hi : __ldg(X.sidx + hb);
       __syncthreads();
 
-      for (int64_t seg = rLo; seg < rHi; seg += CALL_THREADS) {
-        const int64_t r = seg + tid;
-        uint32_t recs[SCHUNK];
-        int nrec = 0;
-        if (r < rHi) nrec = process_read(R, S, C, P, r, cLo, cHi, hLo, hHi, recs);
-        int off, total;
-        cub::BlockScan<int, CALL_THREADS>(sm.scan).ExclusiveSum(nrec, off, total);
+      // super-segments of reads: phase A (barrier-free, per warp) then phase B.  If a warp's record
+      // region overflows the segment is halved and redone; at MIN_SEG it cannot overflow.
+      int32_t seg = max(rHi - rLo, MIN_SEG);
+      int32_t pos = rLo;
+      while (pos < rHi) {
+        const int32_t n = min(seg, rHi - pos);
+        const int32_t per = (n + CALL_WARPS - 1) / CALL_WARPS;
+        const int32_t bLo = min(pos + warp * per, pos + n), bHi = min(bLo + per, pos + n);
+        phase_a_warp(R, S, C, P, sm, warp, lane, bLo, bHi, cLo, cHi, hLo, hHi);
         __syncthreads();
-        // rounds of at most REC_CAP records, in read order
-        for (int base = 0; base < total; base += REC_CAP) {
-          const int cnt = min(REC_CAP, total - base);
-          for (int i = 0; i < nrec; ++i) {
-            const int o = off + i - base;
-            if (o >= 0 && o < REC_CAP) sm.rec[o] = recs[i];
-          }
+        if (sm.overflow) {
           __syncthreads();
-          // phase B: one warp per site slot; records are scanned in order
-          for (int slot = warp; slot < cHi - cLo; slot += CALL_WARPS) {
-            SiteAcc& A = sm.acc[slot];
-            int c_afw = 0, c_ofw = 0, c_acov = 0, c_ocov = 0, c_tot = 0;
-            unsigned long long sq = 0;
-            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-            const bool ll_lane = lane < P.ns;
-            if (ll_lane) { a0 = A.ll[0][lane]; a1 = A.ll[1][lane]; a2 = A.ll[2][lane]; a3 = A.ll[3][lane]; }
-            int seen = A.seen, first_is_ref = A.first_is_ref, first_cn = A.copy_number;
-            for (int i0 = 0; i0 < cnt; i0 += 32) {
-              const int i = i0 + lane;
-              const uint32_t w = (i < cnt) ? sm.rec[i] : 0xFFFFFFFFu;
-              const bool mine = (i < cnt) && ((w & 15u) == (uint32_t)slot);
-              const unsigned m = __ballot_sync(0xFFFFFFFFu, mine);
-              if (m == 0) continue;
-              const uint32_t cat = (w >> 4) & 3u;
-              const bool fwd = (w >> 6) & 1u;
-              const unsigned isRef = __ballot_sync(0xFFFFFFFFu, mine && cat == CAT_REF);
-              const unsigned isAl = __ballot_sync(0xFFFFFFFFu, mine && (cat == CAT_ALT || cat == CAT_NONREF));
-              const unsigned fw = __ballot_sync(0xFFFFFFFFu, mine && fwd);
-              c_tot += __popc(m);                                        // ScoredObservation.scala:88
-              c_ocov += __popc(isRef);                                   // :87
-              c_acov += __popc(isAl);                                    // :86
-              c_ofw += __popc(isRef & fw);                               // :80
-              c_afw += __popc(isAl & fw);                                // :79
-              if (mine) { const unsigned long long q = (w >> 14) & 127u; sq += q * q; }  // :81
-              if (!seen) {                                               // first("isRef"), first("copyNumber")
-                const int f = __ffs(m) - 1;
-                const uint32_t wf = __shfl_sync(0xFFFFFFFFu, w, f);
-                first_is_ref = (((wf >> 4) & 3u) == CAT_REF);
-                first_cn = (int)((wf >> 21) & 15u) + P.min_ploidy;
-                seen = 1;
-              }
-              // ordered fp64 accumulation: lane g owns state g of the four arrays
-              unsigned mm = m;
-              while (mm) {
-                const int src = __ffs(mm) - 1;
-                mm &= mm - 1;
-                const uint32_t ws = __shfl_sync(0xFFFFFFFFu, w, src);
-                if (ll_lane) {
-                  const uint32_t c = (ws >> 4) & 3u;
-                  const int q = (ws >> 7) & 127u, mq = (ws >> 14) & 127u, cni = (ws >> 21) & 15u;
-                  const double v = __ldg(P.lut + ((((int64_t)cni * (P.max_quality + 1) + q) *
-                                                   (P.max_mapq + 1) + mq) * P.ns + lane));
-                  // Spark sums every column for every row; the non-selected arrays add 0.0
-                  a0 += (c == 0) ? v : 0.0;
-                  a1 += (c == 1) ? v : 0.0;
-                  a2 += (c == 2) ? v : 0.0;
-                  a3 += (c == 3) ? v : 0.0;
-                }
-              }
-            }
-            // fold this round into the shared accumulators
-            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
-            if (ll_lane) { A.ll[0][lane] = a0; A.ll[1][lane] = a1; A.ll[2][lane] = a2; A.ll[3][lane] = a3; }
-            if (lane == 0) {
-              A.sq += sq;
-              A.allele_fwd += c_afw; A.other_fwd += c_ofw; A.allele_cov += c_acov;
-              A.other_cov += c_ocov; A.total_cov += c_tot;
-              A.seen = seen; A.first_is_ref = first_is_ref; A.copy_number = first_cn;
-            }
-          }
+          if (tid == 0) sm.overflow = 0;
+          seg = max(MIN_SEG, seg / 2);
           __syncthreads();
+          continue;
         }
+        for (int slot = warp; slot < cHi - cLo; slot += CALL_WARPS) phase_b_slot(P, sm, slot, lane);
+        __syncthreads();
+        pos += n;
       }
       // emit the chunk's rows
-      __syncthreads();
       if (tid < cHi - cLo) finalize_site(P, O, cLo + tid, sm.acc[tid]);
       __syncthreads();
     }

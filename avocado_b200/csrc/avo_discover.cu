@@ -19,8 +19,9 @@
 namespace avo {
 
 constexpr int DISC_THREADS = 256;
-constexpr int DISC_W = 4096;
-constexpr int DISC_HB = 16;      // hot positions histogrammed per pass-2 batch
+constexpr int DISC_W = 2048;      // reference positions owned by one tile
+constexpr int DISC_HB = 8;        // hot positions histogrammed per pass-2 batch
+constexpr int DISC_LIST = 3072;   // SNV candidates of one tile kept in shared memory
 constexpr uint32_t NOT_HOT = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t mix32(uint32_t h, uint32_t v) {
@@ -91,10 +92,34 @@ __device__ __forceinline__ void walk_discover(const DReads& R, int64_t r, int32_
 struct __align__(16) DiscSmem {
   uint32_t cnt[DISC_W];                 // pass 1: candidates per position; then hot index or NOT_HOT
   uint32_t hist[DISC_HB][256];          // pass 2: exact (ref<<4|alt) counts of the batch's hot positions
+  uint32_t list[DISC_LIST];             // SNV candidates of the tile: (pos_off << 8) | (ref << 4) | alt
   typename cub::BlockScan<int, DISC_THREADS>::TempStorage scan;
   int32_t tile;
-  int32_t n_hot;
+  int32_t n_list;
 };
+
+__device__ __forceinline__ void disc_indel_append(const DReads& R, const DIndelList& L, int32_t pos,
+                                                  int32_t ref_len, int32_t alt_len, uint32_t lastRef,
+                                                  uint32_t anchor, uint32_t src, bool is_del) {
+  const int32_t slot = atomicAdd(L.n, 1);
+  if (slot >= L.capacity) return;   // counted; the host grows the list and reruns
+  uint32_t h = mix32(0x811C9DC5u, (uint32_t)pos);
+  h = mix32(h, ((uint32_t)ref_len << 16) | (uint32_t)alt_len);
+  h = mix32(h, (lastRef << 4) | anchor);
+  const int n = is_del ? ref_len - 1 : alt_len - 1;
+  const uint8_t* buf = is_del ? R.refb4 : R.bases4;
+  uint32_t acc = 0;
+  for (int i = 0; i < n; ++i) {
+    acc = (acc << 4) | nib_at(buf, src + i);
+    if ((i & 7) == 7) { h = mix32(h, acc); acc = 0; }
+  }
+  h = mix32(h, acc);
+  L.pos[slot] = pos;
+  L.lens[slot] = ((uint32_t)ref_len << 16) | (uint32_t)alt_len;
+  L.nibs[slot] = (lastRef << 4) | anchor;
+  L.src[slot] = src;
+  L.hash[slot] = h;
+}
 
 __global__ void __launch_bounds__(DISC_THREADS)
 k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep count > min_count */,
@@ -106,53 +131,42 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
   constexpr int PER_T = DISC_W / DISC_THREADS;
 
   for (;;) {
-    if (tid == 0) sm.tile = atomicAdd(tile_counter, 1);
+    __syncthreads();
+    if (tid == 0) { sm.tile = atomicAdd(tile_counter, 1); sm.n_list = 0; }
     __syncthreads();
     const int32_t tile = sm.tile;
-    __syncthreads();
     if (tile >= n_tiles) break;
     const int64_t wlo = (int64_t)X.win0 + (int64_t)tile * DISC_W;
     const int64_t whi = wlo + DISC_W;
     // candidates of a read lie in [start, end): reads with start < whi and start > wlo - max_span
-    const int64_t rLo = __ldg(X.ridx + idx_bin_floor(X, wlo - max_span));
-    const int64_t rHi = __ldg(X.ridx + min((tile + 1) * BPT, X.nb));
+    const int32_t rLo = __ldg(X.ridx + idx_bin_floor(X, wlo - max_span));
+    const int32_t rHi = __ldg(X.ridx + min((tile + 1) * BPT, X.nb));
     if (rLo >= rHi) continue;
 
     for (int i = tid; i < DISC_W; i += DISC_THREADS) sm.cnt[i] = 0;
     __syncthreads();
 
-    // ---- pass 1: per-position SNV candidate counts; indel candidates to the global list --------
-    for (int64_t r = rLo + tid; r < rHi; r += DISC_THREADS) {
+    // ---- pass 1 (the only walk over the reads): per-position SNV candidate counts, the tile's SNV
+    // candidate list in shared memory, indel candidates to the global list ----------------------
+    for (int32_t r = rLo + tid; r < rHi; r += DISC_THREADS) {
       walk_discover(
           R, r, thr,
-          [&](int32_t pos, uint32_t, uint32_t) {
+          [&](int32_t pos, uint32_t refn, uint32_t altn) {
             const int64_t o = (int64_t)pos - wlo;
-            if (o >= 0 && o < DISC_W) atomicAdd(&sm.cnt[o], 1u);
+            if (o < 0 || o >= DISC_W) return;
+            atomicAdd(&sm.cnt[o], 1u);
+            const int slot = atomicAdd(&sm.n_list, 1);
+            if (slot < DISC_LIST) sm.list[slot] = ((uint32_t)o << 8) | (refn << 4) | altn;
           },
           [&](int32_t pos, int32_t ref_len, int32_t alt_len, uint32_t lastRef, uint32_t anchor,
               uint32_t src, bool is_del) {
             if ((int64_t)pos < wlo || (int64_t)pos >= whi) return;
-            const int32_t slot = atomicAdd(L.n, 1);
-            if (slot >= L.capacity) return;   // counted; the host grows the list and reruns
-            uint32_t h = mix32(0x811C9DC5u, (uint32_t)pos);
-            h = mix32(h, ((uint32_t)ref_len << 16) | (uint32_t)alt_len);
-            h = mix32(h, (lastRef << 4) | anchor);
-            const int n = is_del ? ref_len - 1 : alt_len - 1;
-            const uint8_t* buf = is_del ? R.refb4 : R.bases4;
-            uint32_t acc = 0;
-            for (int i = 0; i < n; ++i) {
-              acc = (acc << 4) | nib_at(buf, src + i);
-              if ((i & 7) == 7) { h = mix32(h, acc); acc = 0; }
-            }
-            h = mix32(h, acc);
-            L.pos[slot] = pos;
-            L.lens[slot] = ((uint32_t)ref_len << 16) | (uint32_t)alt_len;
-            L.nibs[slot] = (lastRef << 4) | anchor;
-            L.src[slot] = src;
-            L.hash[slot] = h;
+            disc_indel_append(R, L, pos, ref_len, alt_len, lastRef, anchor, src, is_del);
           });
     }
     __syncthreads();
+    const int n_list = sm.n_list;
+    const bool list_ok = n_list <= DISC_LIST;   // else: fall back to re-walking the reads in pass 2
 
     // ---- hot positions: ordered compaction; cnt[] becomes the hot index ------------------------
     int nh = 0;
@@ -170,26 +184,34 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
       hoff += hot;
     }
     __syncthreads();
-    if (htotal == 0) continue;
 
     // ---- pass 2: exact (ref, alt) counts at the hot positions, DISC_HB positions at a time ------
     for (int hb = 0; hb < htotal; hb += DISC_HB) {
       for (int i = tid; i < DISC_HB * 256; i += DISC_THREADS) (&sm.hist[0][0])[i] = 0;
       __syncthreads();
-      for (int64_t r = rLo + tid; r < rHi; r += DISC_THREADS) {
-        walk_discover(
-            R, r, thr,
-            [&](int32_t pos, uint32_t refn, uint32_t altn) {
-              const int64_t o = (int64_t)pos - wlo;
-              if (o < 0 || o >= DISC_W) return;
-              const uint32_t h = sm.cnt[o];
-              if (h == NOT_HOT || (int)h < hb || (int)h >= hb + DISC_HB) return;
-              atomicAdd(&sm.hist[h - hb][(refn << 4) | altn], 1u);
-            },
-            [&](int32_t, int32_t, int32_t, uint32_t, uint32_t, uint32_t, bool) {});
+      if (list_ok) {
+        for (int i = tid; i < n_list; i += DISC_THREADS) {
+          const uint32_t e = sm.list[i];
+          const uint32_t h = sm.cnt[e >> 8];
+          if (h == NOT_HOT || (int)h < hb || (int)h >= hb + DISC_HB) continue;
+          atomicAdd(&sm.hist[h - hb][e & 255u], 1u);
+        }
+      } else {
+        for (int32_t r = rLo + tid; r < rHi; r += DISC_THREADS) {
+          walk_discover(
+              R, r, thr,
+              [&](int32_t pos, uint32_t refn, uint32_t altn) {
+                const int64_t o = (int64_t)pos - wlo;
+                if (o < 0 || o >= DISC_W) return;
+                const uint32_t h = sm.cnt[o];
+                if (h == NOT_HOT || (int)h < hb || (int)h >= hb + DISC_HB) return;
+                atomicAdd(&sm.hist[h - hb][(refn << 4) | altn], 1u);
+              },
+              [&](int32_t, int32_t, int32_t, uint32_t, uint32_t, uint32_t, bool) {});
+        }
       }
       __syncthreads();
-      // emit: thread i scans window positions for hot ones of this batch
+      // emit: hot positions of this batch, all 256 (ref, alt) bins
       for (int i = tid; i < DISC_W; i += DISC_THREADS) {
         const uint32_t h = sm.cnt[i];
         if (h == NOT_HOT || (int)h < hb || (int)h >= hb + DISC_HB) continue;

@@ -199,14 +199,16 @@ class Context:
         for _ in range(3):
             # output buffers are cached across calls (a shim would reuse its direct buffers too)
             key = (cap, acap, ns, bool(device_out))
-            cache = getattr(self, "_dc_cache", None)
-            if cache is None or cache[0] != key:
+            caches = self.__dict__.setdefault("_dc_cache", {})
+            if key not in caches:
                 sarr = dict(start=mk(cap, np.int32), ref_len=mk(cap, np.int32), alt_len=mk(cap, np.int32),
                             allele_off=mk(cap + 1, np.uint32), alleles4=mk(acap // 2 + 1, np.uint8),
                             count=mk(cap, np.int32))
                 res, arrs = self._alloc_results(cap, ns, dev)
-                self._dc_cache = cache = (key, sarr, res, arrs)
-            _, sarr, res, arrs = cache
+                for k in [k for k in caches if k[3] == key[3]]:
+                    del caches[k]          # keep one host and one device set
+                caches[key] = (sarr, res, arrs)
+            sarr, res, arrs = caches[key]
             out = L.SitesOutStruct()
             out.capacity, out.allele_capacity = cap, acap
             out.mem = L.MEM_DEVICE if device_out else L.MEM_HOST

@@ -175,7 +175,9 @@ int batch_stats(avo_ctx* ctx, const DReads& R, BatchStats* h) {
 // with the host libm so that table values do not depend on the device's log/pow.
 int ensure_lut(avo_ctx* ctx, int minp, int maxp, int maxq, int maxmq, const double** out) {
   const int ns = maxp + 1;
-  const size_t count = (size_t)(maxp - minp + 1) * (maxq + 1) * (maxmq + 1) * ns;
+  // layout [copy number - minp][mq' : 128][q' : 128][ns]: the kernel indexes it with the bit
+  // field (cn index << 14 | mq' << 7 | q') taken straight from its record word
+  const size_t count = (size_t)(maxp - minp + 1) * 128 * 128 * ns;
   void* d;
   if (ctx->lut_minp == minp && ctx->lut_maxp == maxp && ctx->lut_maxq == maxq &&
       ctx->lut_maxmq == maxmq && ctx->bufs[SL_LUT].p) {
@@ -191,7 +193,7 @@ int ensure_lut(avo_ctx* ctx, int minp, int maxp, int maxq, int maxmq, const doub
         const double s_base = 1.0 - std::pow(10.0, -(double)q / 10.0);
         const double ome = s_map * s_base;
         const double eps = 1.0 - ome;
-        double* row = &lut[((((size_t)(m - minp) * (maxq + 1) + q) * (maxmq + 1)) + mq) * ns];
+        double* row = &lut[((((size_t)(m - minp) * 128 + mq) * 128) + q) * ns];
         for (int g = 0; g < ns; ++g)
           row[g] = (g <= m && m > 0) ? std::log((m - g) * eps + g * ome) : 0.0;
       }
@@ -586,6 +588,10 @@ int avo_ctx_create(int device, avo_ctx** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(AVO_E_CUDA);
   ctx->num_sms = prop.multiProcessorCount;
+  // the kernels gather single 32-byte sectors (one quality / base sector per mismatch or site):
+  // ask L2 to fetch 32 B on a miss instead of the default 64 B (a hint; ignored if unsupported)
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+  cudaGetLastError();
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(AVO_E_CUDA);
   ctx->stream = ctx->own_stream;
   for (auto& ev : ctx->ev)

@@ -21,8 +21,8 @@ namespace avo {
 
 constexpr int CALL_THREADS = 256;
 constexpr int CALL_WARPS = CALL_THREADS / 32;
-constexpr int CALL_W = 4096;        // window width in bases
-constexpr int SCHUNK = 16;          // owned sites reduced at a time
+constexpr int CALL_W = 1024;        // window width in bases (one warp per window)
+constexpr int SCHUNK = 8;           // owned sites reduced at a time
 constexpr int MAX_LOCAL_SITES = 32; // per-read category cache
 constexpr int NSMAX = AVO_MAX_PLOIDY + 1;
 
@@ -352,30 +352,29 @@ __device__ void finalize_site(const DCallParams& P, const DResults& O, int32_t s
   O.rms_mapq[site] = (float)sqrt(sq / (double)(A.allele_cov + A.other_cov));    // BG:709
 }
 
-constexpr int WREC_CAP = 512;              // records per warp region; >= 32 * SCHUNK guarantees progress
-constexpr int MIN_SEG = CALL_WARPS * 32;   // smallest super-segment: one read per lane
+constexpr int WREC_CAP = 512;   // records per warp region; >= 32 * SCHUNK guarantees progress
 constexpr int QCAP = 64;
 
-struct __align__(16) CallSmem {
+// Everything a warp needs in shared memory: the kernel has NO block-level barrier; every warp is
+// an independent worker that pulls window tiles from a global counter.
+struct __align__(16) WarpSmem {
   SiteAcc acc[SCHUNK];
-  uint32_t rec[CALL_WARPS][WREC_CAP];  // warp-private record regions; region order == read order
-  int32_t wcount[CALL_WARPS];
-  int32_t q_read[CALL_WARPS][QCAP];    // per-warp queue of joined reads awaiting classification
-  int32_t q_a[CALL_WARPS][QCAP];
-  int32_t q_b[CALL_WARPS][QCAP];
-  int32_t tile;
-  int32_t overflow;
+  uint32_t rec[WREC_CAP];       // records of the current read segment, in read order
+  int32_t q_read[QCAP];         // joined reads awaiting classification
+  int32_t q_a[QCAP];
+  int32_t q_b[QCAP];
 };
 
-// Phase A for one warp: reads [bLo, bHi) in order.  Lanes first run the join for 32 reads at a
-// time and compact the joined ones into the warp's queue; whenever 32 are pending (or the block is
-// exhausted) each lane classifies one of them, so that the expensive part runs at full SIMD width.
-// Records land in the warp's private region in read order.
-__device__ __forceinline__ void phase_a_warp(const DReads& R, const DSites& S, const DCnv& C,
-                                             const DCallParams& P, CallSmem& sm, int warp, int lane,
-                                             int32_t bLo, int32_t bHi, int32_t cLo, int32_t cHi,
-                                             int32_t hLo, int32_t hHi) {
+// Phase A: reads [bLo, bHi) in order.  Lanes first run the join for 32 reads at a time and compact
+// the joined ones into the warp's queue; whenever 32 are pending (or the range is exhausted) each
+// lane classifies one of them, so that the expensive part runs at full SIMD width.  Records land
+// in ws.rec in read order.  Returns the record count, or -1 if the region overflowed.
+__device__ __forceinline__ int phase_a_warp(const DReads& R, const DSites& S, const DCnv& C,
+                                            const DCallParams& P, WarpSmem& ws, int lane, int32_t bLo,
+                                            int32_t bHi, int32_t cLo, int32_t cHi, int32_t hLo,
+                                            int32_t hHi) {
   int wc = 0, qn = 0;
+  bool ovf = false;
   int32_t base = bLo;
   const unsigned lt = (1u << lane) - 1u;
   while (base < bHi || qn > 0) {
@@ -386,7 +385,7 @@ __device__ __forceinline__ void phase_a_warp(const DReads& R, const DSites& S, c
       const unsigned m = __ballot_sync(0xFFFFFFFFu, joined);
       if (joined) {
         const int slot = qn + __popc(m & lt);
-        sm.q_read[warp][slot] = r; sm.q_a[warp][slot] = a; sm.q_b[warp][slot] = b;
+        ws.q_read[slot] = r; ws.q_a[slot] = a; ws.q_b[slot] = b;
       }
       qn += __popc(m);
       base += 32;
@@ -397,8 +396,7 @@ __device__ __forceinline__ void phase_a_warp(const DReads& R, const DSites& S, c
       uint32_t recs[SCHUNK];
       int nrec = 0;
       if (lane < take)
-        nrec = classify_read(R, S, C, P, sm.q_read[warp][lane], sm.q_a[warp][lane], sm.q_b[warp][lane],
-                             cLo, cHi, recs);
+        nrec = classify_read(R, S, C, P, ws.q_read[lane], ws.q_a[lane], ws.q_b[lane], cLo, cHi, recs);
       int incl = nrec;
       for (int o = 1; o < 32; o <<= 1) {
         const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -407,101 +405,96 @@ __device__ __forceinline__ void phase_a_warp(const DReads& R, const DSites& S, c
       const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
       const int off = wc + incl - nrec;
       if (wc + total <= WREC_CAP) {
-        for (int i = 0; i < nrec; ++i) sm.rec[warp][off + i] = recs[i];
-      } else if (lane == 0) {
-        sm.overflow = 1;
+        for (int i = 0; i < nrec; ++i) ws.rec[off + i] = recs[i];
+      } else {
+        ovf = true;
       }
       wc += total;
       // pop the classified entries
       const int rest = qn - take;
       int32_t tr = 0, ta = 0, tb = 0;
-      if (lane < rest) { tr = sm.q_read[warp][take + lane]; ta = sm.q_a[warp][take + lane]; tb = sm.q_b[warp][take + lane]; }
+      if (lane < rest) { tr = ws.q_read[take + lane]; ta = ws.q_a[take + lane]; tb = ws.q_b[take + lane]; }
       __syncwarp();
-      if (lane < rest) { sm.q_read[warp][lane] = tr; sm.q_a[warp][lane] = ta; sm.q_b[warp][lane] = tb; }
+      if (lane < rest) { ws.q_read[lane] = tr; ws.q_a[lane] = ta; ws.q_b[lane] = tb; }
       qn = rest;
       __syncwarp();
     }
   }
-  if (lane == 0) sm.wcount[warp] = min(wc, WREC_CAP);
+  return ovf ? -1 : wc;
 }
 
-// Phase B for one site slot: scan every warp region in order, accumulate in read order.
-__device__ __forceinline__ void phase_b_slot(const DCallParams& P, CallSmem& sm, int slot, int lane) {
-  SiteAcc& A = sm.acc[slot];
+// Phase B for one site slot: scan the records in order, accumulate in read order.  Lane
+// (cat * ns + g) owns state g of category cat's likelihood array.
+__device__ __forceinline__ void phase_b_slot(const DCallParams& P, WarpSmem& ws, int cnt, int slot,
+                                             int lane) {
+  SiteAcc& A = ws.acc[slot];
   int c_afw = 0, c_ofw = 0, c_acov = 0, c_ocov = 0, c_tot = 0;
   unsigned long long sq = 0;
-  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-  const bool ll_lane = lane < P.ns;
-  if (ll_lane) { a0 = A.ll[0][lane]; a1 = A.ll[1][lane]; a2 = A.ll[2][lane]; a3 = A.ll[3][lane]; }
+  const int ns = P.ns;
+  const bool ll_lane = lane < 4 * ns;
+  const uint32_t mycat = (uint32_t)(lane / ns);
+  const int myg = lane - (int)mycat * ns;
+  double acc = ll_lane ? A.ll[mycat][myg] : 0.0;
   int seen = A.seen, first_is_ref = A.first_is_ref, first_cn = A.copy_number;
-  for (int wreg = 0; wreg < CALL_WARPS; ++wreg) {
-    const int cnt = sm.wcount[wreg];
-    const uint32_t* rec = sm.rec[wreg];
-    for (int i0 = 0; i0 < cnt; i0 += 32) {
-      const int i = i0 + lane;
-      const uint32_t w = (i < cnt) ? rec[i] : 0xFFFFFFFFu;
-      const bool mine = (i < cnt) && ((w & 15u) == (uint32_t)slot);
-      const unsigned m = __ballot_sync(0xFFFFFFFFu, mine);
-      if (m == 0) continue;
-      const uint32_t cat = (w >> 4) & 3u;
-      const bool fwd = (w >> 6) & 1u;
-      const unsigned isRef = __ballot_sync(0xFFFFFFFFu, mine && cat == CAT_REF);
-      const unsigned isAl = __ballot_sync(0xFFFFFFFFu, mine && (cat == CAT_ALT || cat == CAT_NONREF));
-      const unsigned fw = __ballot_sync(0xFFFFFFFFu, mine && fwd);
-      c_tot += __popc(m);                                        // ScoredObservation.scala:88
-      c_ocov += __popc(isRef);                                   // :87
-      c_acov += __popc(isAl);                                    // :86
-      c_ofw += __popc(isRef & fw);                               // :80
-      c_afw += __popc(isAl & fw);                                // :79
-      if (mine) { const unsigned long long q = (w >> 14) & 127u; sq += q * q; }  // :81
-      if (!seen) {                                               // first("isRef"), first("copyNumber")
-        const int f = __ffs(m) - 1;
-        const uint32_t wf = __shfl_sync(0xFFFFFFFFu, w, f);
-        first_is_ref = (((wf >> 4) & 3u) == CAT_REF);
-        first_cn = (int)((wf >> 21) & 15u) + P.min_ploidy;
-        seen = 1;
-      }
-      // ordered fp64 accumulation: lane g owns state g of the four arrays
-      unsigned mm = m;
-      while (mm) {
-        const int src = __ffs(mm) - 1;
-        mm &= mm - 1;
-        const uint32_t ws = __shfl_sync(0xFFFFFFFFu, w, src);
-        if (ll_lane) {
-          const uint32_t c = (ws >> 4) & 3u;
-          const int q = (ws >> 7) & 127u, mq = (ws >> 14) & 127u, cni = (ws >> 21) & 15u;
-          const double v = __ldg(P.lut + ((((int64_t)cni * (P.max_quality + 1) + q) *
-                                           (P.max_mapq + 1) + mq) * P.ns + lane));
-          // Spark sums every column for every row; the non-selected arrays add 0.0
-          a0 += (c == 0) ? v : 0.0;
-          a1 += (c == 1) ? v : 0.0;
-          a2 += (c == 2) ? v : 0.0;
-          a3 += (c == 3) ? v : 0.0;
-        }
-      }
+  for (int i0 = 0; i0 < cnt; i0 += 32) {
+    const int i = i0 + lane;
+    const uint32_t w = (i < cnt) ? ws.rec[i] : 0xFFFFFFFFu;
+    const bool mine = (i < cnt) && ((w & 15u) == (uint32_t)slot);
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, mine);
+    if (m == 0) continue;
+    const uint32_t cat = (w >> 4) & 3u;
+    const bool fwd = (w >> 6) & 1u;
+    const unsigned isRef = __ballot_sync(0xFFFFFFFFu, mine && cat == CAT_REF);
+    const unsigned isAl = __ballot_sync(0xFFFFFFFFu, mine && (cat == CAT_ALT || cat == CAT_NONREF));
+    const unsigned fw = __ballot_sync(0xFFFFFFFFu, mine && fwd);
+    c_tot += __popc(m);                                        // ScoredObservation.scala:88
+    c_ocov += __popc(isRef);                                   // :87
+    c_acov += __popc(isAl);                                    // :86
+    c_ofw += __popc(isRef & fw);                               // :80
+    c_afw += __popc(isAl & fw);                                // :79
+    if (mine) { const unsigned long long q = (w >> 14) & 127u; sq += q * q; }  // :81
+    if (!seen) {                                               // first("isRef"), first("copyNumber")
+      const int f = __ffs(m) - 1;
+      const uint32_t wf = __shfl_sync(0xFFFFFFFFu, w, f);
+      first_is_ref = (((wf >> 4) & 3u) == CAT_REF);
+      first_cn = (int)((wf >> 21) & 15u) + P.min_ploidy;
+      seen = 1;
+    }
+    // ordered fp64 accumulation.  Spark sums every column for every row; the arrays a record
+    // does not select receive + 0.0, which leaves them bit-identical.
+    unsigned mm = m;
+    while (mm) {
+      const int src = __ffs(mm) - 1;
+      mm &= mm - 1;
+      const uint32_t x = __shfl_sync(0xFFFFFFFFu, w, src);
+      const bool sel = ll_lane && ((x >> 4) & 3u) == mycat;
+      // row = (copy-number index, mq', q') packed exactly as bits [24:7] of the record word
+      const double v = sel ? __ldg(P.lut + ((x >> 7) & 0x3FFFFu) * (uint32_t)ns + (uint32_t)myg) : 0.0;
+      acc += v;
     }
   }
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
-  if (ll_lane) { A.ll[0][lane] = a0; A.ll[1][lane] = a1; A.ll[2][lane] = a2; A.ll[3][lane] = a3; }
+  if (ll_lane) A.ll[mycat][myg] = acc;
   if (lane == 0) {
     A.sq += sq;
     A.allele_fwd += c_afw; A.other_fwd += c_ofw; A.allele_cov += c_acov;
     A.other_cov += c_ocov; A.total_cov += c_tot;
     A.seen = seen; A.first_is_ref = first_is_ref; A.copy_number = first_cn;
   }
+  __syncwarp();
 }
 
-__global__ void __launch_bounds__(CALL_THREADS)
+__global__ void __launch_bounds__(CALL_THREADS, 4)
 k_call_tiles(DReads R, DSites S, DCnv C, DCallParams P, DResults O, DIndex X, int32_t n_tiles,
              int32_t max_span, int32_t* __restrict__ tile_counter) {
-  __shared__ CallSmem sm;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ WarpSmem smem[CALL_WARPS];
+  const int lane = threadIdx.x & 31;
+  WarpSmem& ws = smem[threadIdx.x >> 5];
 
   for (;;) {
-    if (tid == 0) sm.tile = atomicAdd(tile_counter, 1);
-    __syncthreads();
-    const int32_t tile = sm.tile;
-    __syncthreads();
+    int32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(tile_counter, 1);
+    tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
     if (tile >= n_tiles) break;
 
     // owned sites: start in [win0 + tile*CALL_W, win0 + (tile+1)*CALL_W).  The first tile also owns
@@ -515,9 +508,8 @@ k_call_tiles(DReads R, DSites S, DCnv C, DCallParams P, DResults O, DIndex X, in
 
     for (int32_t cLo = sLo; cLo < sHi; cLo += SCHUNK) {
       const int32_t cHi = min(cLo + SCHUNK, sHi);
-      for (int i = tid; i < (int)(sizeof(SiteAcc) * SCHUNK / 4); i += CALL_THREADS)
-        reinterpret_cast<uint32_t*>(sm.acc)[i] = 0u;
-      if (tid == 0) sm.overflow = 0;
+      for (int i = lane; i < (int)(sizeof(SiteAcc) * SCHUNK / 4); i += 32)
+        reinterpret_cast<uint32_t*>(ws.acc)[i] = 0u;
       // reads that can overlap a site of the chunk: start < max site end, start >= first site start - max_span
       int32_t maxEnd = INT32_MIN;
       for (int32_t j = cLo; j < cHi; ++j) maxEnd = max(maxEnd, __ldg(S.end + j));
@@ -529,32 +521,25 @@ k_call_tiles(DReads R, DSites S, DCnv C, DCallParams P, DResults O, DIndex X, in
       // reads of the range start before maxEnd + IDX_G and end within max_span of their start
       const int32_t hb = idx_bin_ceil(X, (int64_t)maxEnd + max_span) + 1;
       const int32_t hHi = (hb >= X.nb) ? S.c_hi : __ldg(X.sidx + hb);
-      __syncthreads();
+      __syncwarp();
 
-      // super-segments of reads: phase A (barrier-free, per warp) then phase B.  If a warp's record
-      // region overflows the segment is halved and redone; at MIN_SEG it cannot overflow.
-      int32_t seg = max(rHi - rLo, MIN_SEG);
+      // segments of reads: phase A then phase B.  If the record region overflows the segment is
+      // halved and redone; a 32-read segment cannot overflow (32 * SCHUNK <= WREC_CAP).
+      int32_t seg = max(rHi - rLo, 32);
       int32_t pos = rLo;
       while (pos < rHi) {
         const int32_t n = min(seg, rHi - pos);
-        const int32_t per = (n + CALL_WARPS - 1) / CALL_WARPS;
-        const int32_t bLo = min(pos + warp * per, pos + n), bHi = min(bLo + per, pos + n);
-        phase_a_warp(R, S, C, P, sm, warp, lane, bLo, bHi, cLo, cHi, hLo, hHi);
-        __syncthreads();
-        if (sm.overflow) {
-          __syncthreads();
-          if (tid == 0) sm.overflow = 0;
-          seg = max(MIN_SEG, seg / 2);
-          __syncthreads();
-          continue;
-        }
-        for (int slot = warp; slot < cHi - cLo; slot += CALL_WARPS) phase_b_slot(P, sm, slot, lane);
-        __syncthreads();
+        const int cnt = phase_a_warp(R, S, C, P, ws, lane, pos, pos + n, cLo, cHi, hLo, hHi);
+        if (cnt < 0) { seg = max(32, seg / 2); continue; }
+        __syncwarp();
+        if (cnt > 0)
+          for (int slot = 0; slot < cHi - cLo; ++slot) phase_b_slot(P, ws, cnt, slot, lane);
         pos += n;
       }
       // emit the chunk's rows
-      if (tid < cHi - cLo) finalize_site(P, O, cLo + tid, sm.acc[tid]);
-      __syncthreads();
+      __syncwarp();
+      if (lane < cHi - cLo) finalize_site(P, O, cLo + lane, ws.acc[lane]);
+      __syncwarp();
     }
   }
 }
@@ -570,7 +555,9 @@ cudaError_t launch_call_tiles(const DReads& R, const DSites& S, const DCnv& C, c
   int blocks_per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_call_tiles, CALL_THREADS, 0);
   if (e != cudaSuccess) return e;
-  const int grid = (int)min((int64_t)n_tiles, (int64_t)num_sms * max(1, blocks_per_sm));
+  // persistent grid; every warp pulls tiles, so a grid needs at most n_tiles / CALL_WARPS blocks
+  const int grid = (int)min((int64_t)(n_tiles + CALL_WARPS - 1) / CALL_WARPS,
+                            (int64_t)num_sms * max(1, blocks_per_sm));
   k_call_tiles<<<grid, CALL_THREADS, 0, s>>>(R, S, C, P, out, X, n_tiles, hstats.max_span,
                                              d_tile_counter);
   if (n_launches) *n_launches += 1;

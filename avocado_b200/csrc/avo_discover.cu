@@ -59,8 +59,15 @@ __device__ __forceinline__ void walk_discover(const DReads& R, int64_t r, int32_
   auto last_ref = [&]() -> uint32_t {
     return last_is_refb ? nib_at(R.refb4, last_loc) : nib_at(R.bases4, last_loc);
   };
+  // the next four operators are fetched together (independent loads, one memory round trip)
+  uint32_t pre[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pre[j] = (k + j < no) ? __ldg(R.ops + ob + k + j) : 0u;
+  const uint32_t k0 = k;
   for (; k < no; ++k) {
-    const uint32_t op = __ldg(R.ops + ob + k);
+    const uint32_t dk = k - k0;
+    const uint32_t op = dk == 0 ? pre[0] : dk == 1 ? pre[1] : dk == 2 ? pre[2] : dk == 3 ? pre[3]
+                                                                       : __ldg(R.ops + ob + k);
     const uint32_t len = op >> 4, code = op & 15u;
     if (code == AVO_OP_MATCH) {                                           // :194-197
       last_is_refb = false; last_loc = sb + idx + len - 1;

@@ -80,7 +80,7 @@ struct DResults {
 struct DCallParams {
   int32_t base_ploidy, min_ploidy, max_ploidy, ns;
   int32_t max_quality, max_mapq;
-  // lut[((cn - min_ploidy) * (max_quality+1) + q) * (max_mapq+1) + mq) * ns + g]  (S6 of SURVEY.md)
+  // lut[(((cn - min_ploidy) * 128 + mq') * 128 + q') * ns + g]   (S6 of SURVEY.md)
   const double* lut;
   const double* lnk;     // lnk[k] = log(k), k < lnk_n (host libm)
   const double* lnfact;  // lnfact[n] = logFactorial(n) (BG:755-762), n < lnk_n, same summation order

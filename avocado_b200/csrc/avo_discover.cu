@@ -59,15 +59,8 @@ __device__ __forceinline__ void walk_discover(const DReads& R, int64_t r, int32_
   auto last_ref = [&]() -> uint32_t {
     return last_is_refb ? nib_at(R.refb4, last_loc) : nib_at(R.bases4, last_loc);
   };
-  // the next four operators are fetched together (independent loads, one memory round trip)
-  uint32_t pre[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) pre[j] = (k + j < no) ? __ldg(R.ops + ob + k + j) : 0u;
-  const uint32_t k0 = k;
   for (; k < no; ++k) {
-    const uint32_t dk = k - k0;
-    const uint32_t op = dk == 0 ? pre[0] : dk == 1 ? pre[1] : dk == 2 ? pre[2] : dk == 3 ? pre[3]
-                                                                       : __ldg(R.ops + ob + k);
+    const uint32_t op = __ldg(R.ops + ob + k);
     const uint32_t len = op >> 4, code = op & 15u;
     if (code == AVO_OP_MATCH) {                                           // :194-197
       last_is_refb = false; last_loc = sb + idx + len - 1;
@@ -96,13 +89,30 @@ __device__ __forceinline__ void walk_discover(const DReads& R, int64_t r, int32_
   }
 }
 
+// One X / I / D operator of one read, queued by the warp that walked the read and handled later by
+// whichever lane picks it up (so that the loads and atomics of candidate emission run converged).
+struct DiscEvent {
+  int32_t pos;       // X: reference position of the first mismatching base; I, D: pos - 1 (the anchor)
+  uint32_t bidx;     // X: global index of the first mismatching read base; I: first inserted base; D: anchor base
+  uint32_t rb;       // X, D: global refb nibble index of the operator's reference bases
+  uint32_t sb;       // first base of the read (the reference indexes qual(i) from the read start for X)
+  uint32_t lenkind;  // (len << 3) | (lastRef lives in refb4 ? 4 : 0) | kind   kind: 0 X, 1 I, 2 D
+  uint32_t last;     // location of lastRef (bases4 or refb4 nibble index)
+};
+
+constexpr int DISC_WARPS = DISC_THREADS / 32;
+constexpr int DISC_Q = 64;
+
 struct __align__(16) DiscSmem {
   uint32_t cnt[DISC_W];                 // pass 1: candidates per position; then hot index or NOT_HOT
   uint32_t hist[DISC_HB][256];          // pass 2: exact (ref<<4|alt) counts of the batch's hot positions
   uint32_t list[DISC_LIST];             // SNV candidates of the tile: (pos_off << 8) | (ref << 4) | alt
+  DiscEvent q[DISC_WARPS][DISC_Q];
   typename cub::BlockScan<int, DISC_THREADS>::TempStorage scan;
   int32_t tile;
   int32_t n_list;
+  int32_t next;                         // next unclaimed read of the tile (warps claim 32 at a time)
+  int32_t hotpos[DISC_HB];              // window offsets of the current batch's hot positions
 };
 
 __device__ __forceinline__ void disc_indel_append(const DReads& R, const DIndelList& L, int32_t pos,
@@ -128,12 +138,124 @@ __device__ __forceinline__ void disc_indel_append(const DReads& R, const DIndelL
   L.hash[slot] = h;
 }
 
-__global__ void __launch_bounds__(DISC_THREADS)
+// candidate emission for one queued event (DiscoverVariants.scala:198-242)
+__device__ __forceinline__ void disc_handle_event(const DReads& R, const DIndelList& L, DiscSmem& sm,
+                                                  const DiscEvent& e, int32_t thr, int64_t wlo) {
+  const uint32_t kind = e.lenkind & 3u, len = e.lenkind >> 3;
+  if (kind == 0) {                                                          // :198-210
+    for (uint32_t i = 0; i < len; ++i) {
+      if ((int32_t)__ldg(R.quals + e.sb + i) < thr) continue;               // qual(i), not qual(idx+i)
+      const int64_t o = (int64_t)e.pos + i - wlo;
+      if (o < 0 || o >= DISC_W) continue;
+      const uint32_t refn = nib_at(R.refb4, e.rb + i), altn = nib_at(R.bases4, e.bidx + i);
+      atomicAdd(&sm.cnt[o], 1u);
+      const int slot = atomicAdd(&sm.n_list, 1);
+      if (slot < DISC_LIST) sm.list[slot] = ((uint32_t)o << 8) | (refn << 4) | altn;
+    }
+    return;
+  }
+  const int64_t o = (int64_t)e.pos - wlo;
+  if (o < 0 || o >= DISC_W) return;
+  const bool last_refb = e.lenkind & 4u;
+  if (kind == 1) {                                                          // :215-228
+    int sum = 0;
+    for (uint32_t j = 0; j <= len; ++j) sum += __ldg(R.quals + e.bidx - 1 + j);
+    if (sum / (int)len < thr) return;
+    const uint32_t lastRef = last_refb ? nib_at(R.refb4, e.last) : nib_at(R.bases4, e.last);
+    disc_indel_append(R, L, e.pos, 1, (int32_t)len + 1, lastRef, nib_at(R.bases4, e.bidx - 1), e.bidx, false);
+  } else {                                                                  // :229-242
+    if ((int32_t)__ldg(R.quals + e.bidx) < thr) return;
+    const uint32_t lastRef = last_refb ? nib_at(R.refb4, e.last) : nib_at(R.bases4, e.last);
+    disc_indel_append(R, L, e.pos, (int32_t)len + 1, 1, lastRef, nib_at(R.bases4, e.bidx), e.rb, true);
+  }
+}
+
+// Pass 1 for one warp: claims 32 reads at a time, walks their operators in lock step (the walk is
+// pure integer bookkeeping), queues every X / I / D operator, and drains the queue 32 events at a time.
+__device__ __forceinline__ void disc_walk_warp(const DReads& R, const DIndelList& L, DiscSmem& sm,
+                                               int warp, int lane, int32_t rHi, int32_t thr, int64_t wlo) {
+  DiscEvent* q = sm.q[warp];
+  const unsigned lt = (1u << lane) - 1u;
+  int qn = 0;
+  auto drain = [&](int take) {
+    if (lane < take) disc_handle_event(R, L, sm, q[lane], thr, wlo);
+    const int rest = qn - take;
+    DiscEvent t;
+    if (lane < rest) t = q[take + lane];
+    __syncwarp();
+    if (lane < rest) q[lane] = t;
+    qn = rest;
+    __syncwarp();
+  };
+  for (;;) {
+    int32_t base = 0;
+    if (lane == 0) base = atomicAdd(&sm.next, 32);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= rHi) break;
+    const int32_t r = base + lane;
+    const bool active = r < rHi;
+    uint32_t ob = 0, no = 0, sb = 0, rb = 0;
+    int32_t pos = 0;
+    if (active) {
+      ob = __ldg(R.op_off + r);
+      no = __ldg(R.op_off + r + 1) - ob;
+      sb = __ldg(R.seq_off + r);
+      rb = __ldg(R.refb_off + r);
+      pos = __ldg(R.start + r);
+    }
+    uint32_t idx = 0, last = 0;
+    bool ff = true, last_refb = false;
+    const uint32_t maxno = __reduce_max_sync(0xFFFFFFFFu, no);
+    for (uint32_t k = 0; k < maxno; ++k) {
+      DiscEvent e;
+      bool ev = false;
+      if (k < no) {
+        const uint32_t op = __ldg(R.ops + ob + k);
+        const uint32_t len = op >> 4, code = op & 15u;
+        if (ff && (code == AVO_OP_MATCH || code == AVO_OP_MISMATCH)) ff = false;
+        if (ff) {                                                           // fastForward (:139-172)
+          if (code == AVO_OP_SOFTCLIP || code == AVO_OP_INS) idx += len;
+          else if (code == AVO_OP_DEL) { pos += (int32_t)len; rb += len; }
+        } else if (code == AVO_OP_MATCH) {                                  // :194-197
+          last = sb + idx + len - 1; last_refb = false;
+          pos += (int32_t)len; idx += len;
+        } else if (code == AVO_OP_MISMATCH) {
+          ev = true;
+          e.pos = pos; e.bidx = sb + idx; e.rb = rb; e.sb = sb; e.lenkind = (len << 3) | 0u; e.last = 0;
+          last = rb + len - 1; last_refb = true;
+          rb += len; pos += (int32_t)len; idx += len;
+        } else if (code == AVO_OP_INS) {
+          ev = true;
+          e.pos = pos - 1; e.bidx = sb + idx; e.rb = rb; e.sb = sb;
+          e.lenkind = (len << 3) | (last_refb ? 4u : 0u) | 1u; e.last = last;
+          idx += len;
+        } else if (code == AVO_OP_DEL) {
+          ev = true;
+          e.pos = pos - 1; e.bidx = sb + idx - 1; e.rb = rb; e.sb = sb;
+          e.lenkind = (len << 3) | (last_refb ? 4u : 0u) | 2u; e.last = last;
+          pos += (int32_t)len;
+          last = rb + len - 1; last_refb = true;
+          rb += len;
+        }                                                                   // Clipped: no-op (:191-193)
+      }
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, ev);
+      if (m) {
+        if (ev) q[qn + __popc(m & lt)] = e;
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) drain(32);
+      }
+    }
+  }
+  if (qn > 0) drain(qn);
+}
+
+__global__ void __launch_bounds__(DISC_THREADS, 5)
 k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep count > min_count */,
                  int32_t n_tiles, int32_t max_span, DDiscoverOut out, DIndelList L,
                  int32_t* __restrict__ tile_counter) {
   __shared__ DiscSmem sm;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int BPT = DISC_W / IDX_G;
   constexpr int PER_T = DISC_W / DISC_THREADS;
 
@@ -144,33 +266,18 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
     const int32_t tile = sm.tile;
     if (tile >= n_tiles) break;
     const int64_t wlo = (int64_t)X.win0 + (int64_t)tile * DISC_W;
-    const int64_t whi = wlo + DISC_W;
     // candidates of a read lie in [start, end): reads with start < whi and start > wlo - max_span
     const int32_t rLo = __ldg(X.ridx + idx_bin_floor(X, wlo - max_span));
     const int32_t rHi = __ldg(X.ridx + min((tile + 1) * BPT, X.nb));
     if (rLo >= rHi) continue;
 
     for (int i = tid; i < DISC_W; i += DISC_THREADS) sm.cnt[i] = 0;
+    if (tid == 0) sm.next = rLo;
     __syncthreads();
 
     // ---- pass 1 (the only walk over the reads): per-position SNV candidate counts, the tile's SNV
     // candidate list in shared memory, indel candidates to the global list ----------------------
-    for (int32_t r = rLo + tid; r < rHi; r += DISC_THREADS) {
-      walk_discover(
-          R, r, thr,
-          [&](int32_t pos, uint32_t refn, uint32_t altn) {
-            const int64_t o = (int64_t)pos - wlo;
-            if (o < 0 || o >= DISC_W) return;
-            atomicAdd(&sm.cnt[o], 1u);
-            const int slot = atomicAdd(&sm.n_list, 1);
-            if (slot < DISC_LIST) sm.list[slot] = ((uint32_t)o << 8) | (refn << 4) | altn;
-          },
-          [&](int32_t pos, int32_t ref_len, int32_t alt_len, uint32_t lastRef, uint32_t anchor,
-              uint32_t src, bool is_del) {
-            if ((int64_t)pos < wlo || (int64_t)pos >= whi) return;
-            disc_indel_append(R, L, pos, ref_len, alt_len, lastRef, anchor, src, is_del);
-          });
-    }
+    disc_walk_warp(R, L, sm, warp, lane, rHi, thr, wlo);
     __syncthreads();
     const int n_list = sm.n_list;
     const bool list_ok = n_list <= DISC_LIST;   // else: fall back to re-walking the reads in pass 2
@@ -218,11 +325,16 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
         }
       }
       __syncthreads();
-      // emit: hot positions of this batch, all 256 (ref, alt) bins
+      // emit: a warp scans the 256 (ref, alt) bins of one hot position of this batch
       for (int i = tid; i < DISC_W; i += DISC_THREADS) {
         const uint32_t h = sm.cnt[i];
-        if (h == NOT_HOT || (int)h < hb || (int)h >= hb + DISC_HB) continue;
-        for (int k = 0; k < 256; ++k) {
+        if (h != NOT_HOT && (int)h >= hb && (int)h < hb + DISC_HB) sm.hotpos[h - hb] = i;
+      }
+      __syncthreads();
+      for (int s = warp; s < min(DISC_HB, htotal - hb); s += DISC_WARPS) {
+        const int i = sm.hotpos[s];
+        const uint32_t h = (uint32_t)(hb + s);
+        for (int k = lane; k < 256; k += 32) {
           const int32_t c = (int32_t)sm.hist[h - hb][k];
           if (c > min_count) {
             const int32_t slot = atomicAdd(out.n, 1);

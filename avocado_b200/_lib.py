@@ -35,8 +35,7 @@ P = C.c_void_p
 class ReadBatchStruct(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("n_bases", C.c_int64), ("n_ops", C.c_int64),
                 ("n_refb", C.c_int64), ("contig_id", C.c_int32), ("mem", C.c_int32),
-                ("start", P), ("end", P), ("mapq", P), ("flags", P), ("seq_off", P), ("bases4", P),
-                ("quals", P), ("op_off", P), ("ops", P), ("refb_off", P), ("refb4", P)]
+                ("meta", P), ("bases4", P), ("quals", P), ("ops", P), ("refb", P)]
 
 
 class SitesStruct(C.Structure):
@@ -95,9 +94,8 @@ class TextReadsStruct(C.Structure):
 
 class PackedOutStruct(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("n_bases", C.c_int64), ("n_ops", C.c_int64),
-                ("n_refb", C.c_int64), ("start", P), ("end", P), ("mapq", P), ("flags", P),
-                ("seq_off", P), ("bases4", P), ("quals", P), ("op_off", P), ("ops", P),
-                ("refb_off", P), ("refb4", P), ("source_index", P)]
+                ("n_refb", C.c_int64), ("meta", P), ("bases4", P), ("quals", P), ("ops", P),
+                ("refb", P), ("source_index", P)]
 
 
 class SynthParamsStruct(C.Structure):

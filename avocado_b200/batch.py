@@ -18,10 +18,14 @@ from .records import AlignmentRecord, Variant
 NIB = "=ACMGRSVTWYHKDBN"
 _NIB_OF = {c: i for i, c in enumerate(NIB)}
 
-READ_COLUMNS = [("start", np.int32), ("end", np.int32), ("mapq", np.uint8), ("flags", np.uint8),
-                ("seq_off", np.uint32), ("bases4", np.uint8), ("quals", np.uint8),
-                ("op_off", np.uint32), ("ops", np.uint32), ("refb_off", np.uint32),
-                ("refb4", np.uint8)]
+# avo_read_meta (include/avocado_b200.h): one 32-byte record per read
+META_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("seq_off", "<u4"), ("op_off", "<u4"),
+                       ("refb_off", "<u4"), ("n_ops", "<u2"), ("mapq", "u1"), ("flags", "u1"),
+                       ("qhead", "<u4"), ("l_seq", "<u4")])
+assert META_DTYPE.itemsize == 32
+
+READ_COLUMNS = [("meta", META_DTYPE), ("bases4", np.uint8), ("quals", np.uint8), ("ops", np.uint32),
+                ("refb", np.uint8)]
 
 
 def _ptr(a):
@@ -45,22 +49,24 @@ class ReadBatch:
     n_ops: int
     n_refb: int
     contig_id: int = 0
-    start: object = None
-    end: object = None
-    mapq: object = None
-    flags: object = None
-    seq_off: object = None
+    meta: object = None      # host: structured array of META_DTYPE; device: uint8 tensor [n * 32]
     bases4: object = None
     quals: object = None
-    op_off: object = None
     ops: object = None
-    refb_off: object = None
-    refb4: object = None
+    refb: object = None
     source_index: Optional[np.ndarray] = None
 
     @property
     def on_device(self):
-        return _is_device(self.start)
+        return _is_device(self.meta)
+
+    def __getattr__(self, name):
+        # per-read scalar columns (host batches): batch.start, batch.end, batch.mapq, ...
+        if name in META_DTYPE.names:
+            meta = self.__dict__.get("meta")
+            if isinstance(meta, np.ndarray):
+                return meta[name]
+        raise AttributeError(name)
 
     def as_struct(self):
         s = L.ReadBatchStruct()
@@ -86,7 +92,9 @@ class ReadBatch:
         for name, _ in READ_COLUMNS:
             a = getattr(self, name)
             t = torch.from_numpy(_torch_view(a))
-            setattr(out, name, t.to(device, **kw))
+            if pinned:
+                t = t.pin_memory()
+            setattr(out, name, t.to(device, non_blocking=pinned, **kw))
         return out
 
     def to_host(self):
@@ -100,22 +108,23 @@ class ReadBatch:
     def slice(self, lo, hi):
         """Host-side sub-batch of reads [lo, hi) (offsets rebased)."""
         assert not self.on_device
-        b0, b1 = int(self.seq_off[lo]), int(self.seq_off[hi])
-        o0, o1 = int(self.op_off[lo]), int(self.op_off[hi])
-        f0, f1 = int(self.refb_off[lo]), int(self.refb_off[hi])
-        assert b0 % 2 == 0 and f0 % 2 == 0, "slices must start on byte-aligned nibble offsets"
+        m = self.meta[lo:hi].copy()
+        if hi > lo:
+            last = self.meta[hi - 1]
+            b0 = int(m["seq_off"][0]); b1 = int(last["seq_off"]) + ((int(last["l_seq"]) + 1) & ~1)
+            o0 = int(m["op_off"][0]); o1 = int(last["op_off"]) + int(last["n_ops"])
+            f0 = int(m["refb_off"][0])
+            f1 = int(self.meta[hi]["refb_off"]) if hi < self.n_reads else self.n_refb
+        else:
+            b0 = b1 = o0 = o1 = f0 = f1 = 0
+        assert b0 % 2 == 0
+        m["seq_off"] -= np.uint32(b0); m["op_off"] -= np.uint32(o0); m["refb_off"] -= np.uint32(f0)
         out = ReadBatch(hi - lo, b1 - b0, o1 - o0, f1 - f0, self.contig_id)
-        out.start = np.ascontiguousarray(self.start[lo:hi])
-        out.end = np.ascontiguousarray(self.end[lo:hi])
-        out.mapq = np.ascontiguousarray(self.mapq[lo:hi])
-        out.flags = np.ascontiguousarray(self.flags[lo:hi])
-        out.seq_off = np.ascontiguousarray(self.seq_off[lo:hi + 1] - np.uint32(b0))
+        out.meta = m
         out.bases4 = np.ascontiguousarray(self.bases4[b0 // 2:(b1 + 1) // 2])
         out.quals = np.ascontiguousarray(self.quals[b0:b1])
-        out.op_off = np.ascontiguousarray(self.op_off[lo:hi + 1] - np.uint32(o0))
         out.ops = np.ascontiguousarray(self.ops[o0:o1])
-        out.refb_off = np.ascontiguousarray(self.refb_off[lo:hi + 1] - np.uint32(f0))
-        out.refb4 = np.ascontiguousarray(self.refb4[f0 // 2:(f1 + 1) // 2])
+        out.refb = np.ascontiguousarray(self.refb[f0:f1])
         return out
 
 
@@ -123,13 +132,17 @@ _TORCH_VIEW = {np.dtype(np.uint32): np.int32, np.dtype(np.uint16): np.int16}
 
 
 def _torch_view(a: np.ndarray) -> np.ndarray:
-    """torch has no uint32: reinterpret as int32 (bit pattern preserved)."""
+    """torch has no uint32: reinterpret as int32 (bit pattern preserved); records as bytes."""
+    if a.dtype == META_DTYPE:
+        return a.view(np.uint8)
     v = _TORCH_VIEW.get(a.dtype)
     return a.view(v) if v is not None else a
 
 
 def _from_torch(t, dtype) -> np.ndarray:
     a = t.detach().cpu().numpy()
+    if np.dtype(dtype) == META_DTYPE:
+        return a.view(np.uint8)[:(a.nbytes // 32) * 32].view(META_DTYPE)
     return a.view(dtype) if a.dtype != np.dtype(dtype) else a
 
 
@@ -287,12 +300,9 @@ def pack_reads(records: Sequence[AlignmentRecord], contig_id=0, keep=None, sort=
     if rc != 0:
         raise L.AvocadoError(rc, "avo_pack_bounds failed")
     out = L.PackedOutStruct()
-    arrs = dict(start=np.zeros(nr.value, np.int32), end=np.zeros(nr.value, np.int32),
-                mapq=np.zeros(nr.value, np.uint8), flags=np.zeros(nr.value, np.uint8),
-                seq_off=np.zeros(nr.value + 1, np.uint32), bases4=np.zeros(nb.value // 2 + 1, np.uint8),
-                quals=np.zeros(max(nb.value, 1), np.uint8), op_off=np.zeros(nr.value + 1, np.uint32),
-                ops=np.zeros(max(no.value, 1), np.uint32), refb_off=np.zeros(nr.value + 1, np.uint32),
-                refb4=np.zeros(nf.value // 2 + 1, np.uint8), source_index=np.zeros(max(nr.value, 1), np.int64))
+    arrs = dict(meta=np.zeros(max(nr.value, 1), META_DTYPE), bases4=np.zeros(nb.value // 2 + 1, np.uint8),
+                quals=np.zeros(max(nb.value, 1), np.uint8), ops=np.zeros(max(no.value, 1), np.uint32),
+                refb=np.zeros(max(nf.value, 1), np.uint8), source_index=np.zeros(max(nr.value, 1), np.int64))
     out.n_reads, out.n_bases, out.n_ops, out.n_refb = nr.value, nb.value, no.value, nf.value
     for k, a in arrs.items():
         setattr(out, k, a.ctypes.data)
@@ -300,12 +310,11 @@ def pack_reads(records: Sequence[AlignmentRecord], contig_id=0, keep=None, sort=
     if rc != 0:
         raise L.AvocadoError(rc, "avo_pack_reads failed")
     b = ReadBatch(out.n_reads, out.n_bases, out.n_ops, out.n_refb, contig_id)
-    b.start, b.end, b.mapq, b.flags = arrs["start"], arrs["end"], arrs["mapq"], arrs["flags"]
-    b.seq_off, b.op_off, b.refb_off = arrs["seq_off"], arrs["op_off"], arrs["refb_off"]
+    b.meta = arrs["meta"][:out.n_reads]
     b.bases4 = arrs["bases4"][:(out.n_bases + 1) // 2 or 1]
     b.quals = arrs["quals"][:max(out.n_bases, 1)]
     b.ops = arrs["ops"][:max(out.n_ops, 1)]
-    b.refb4 = arrs["refb4"][:(out.n_refb + 1) // 2 or 1]
+    b.refb = arrs["refb"][:max(out.n_refb, 1)]
     b.source_index = np.array([idx[j] for j in arrs["source_index"][:out.n_reads]], np.int64)
     return b
 
@@ -342,11 +351,9 @@ def synth_host(p, first=0, n=None, contig_id=0) -> ReadBatch:
         raise L.AvocadoError(rc, "avo_synth_host(count) failed")
     lpad = (p.read_len + 1) & ~1
     nb = n * lpad
-    arrs = dict(start=np.zeros(n, np.int32), end=np.zeros(n, np.int32), mapq=np.zeros(n, np.uint8),
-                flags=np.zeros(n, np.uint8), seq_off=np.zeros(n + 1, np.uint32),
-                bases4=np.zeros(nb // 2 + 1, np.uint8), quals=np.zeros(max(nb, 1), np.uint8),
-                op_off=np.zeros(n + 1, np.uint32), ops=np.zeros(max(no.value, 1), np.uint32),
-                refb_off=np.zeros(n + 1, np.uint32), refb4=np.zeros(nf.value // 2 + 1, np.uint8))
+    arrs = dict(meta=np.zeros(n, META_DTYPE), bases4=np.zeros(nb // 2 + 1, np.uint8),
+                quals=np.zeros(max(nb, 1), np.uint8), ops=np.zeros(max(no.value, 1), np.uint32),
+                refb=np.zeros(max(nf.value, 1), np.uint8))
     out = _packed_out(arrs, n, nb, no.value, nf.value)
     rc = lib.avo_synth_host(C.byref(p), first, n, None, None, C.byref(out))
     if rc != 0:
@@ -372,13 +379,11 @@ def synth_device(p, first=0, n=None, contig_id=0, device="cuda:0") -> ReadBatch:
             raise L.AvocadoError(rc, "avo_synth_device(count) failed")
         lpad = (p.read_len + 1) & ~1
         nb = n * lpad
-        arrs = dict(start=_device_empty(n, np.int32, device), end=_device_empty(n, np.int32, device),
-                    mapq=_device_empty(n, np.uint8, device), flags=_device_empty(n, np.uint8, device),
-                    seq_off=_device_empty(n + 1, np.uint32, device),
+        arrs = dict(meta=_device_empty(n * 32, np.uint8, device),
                     bases4=_device_empty(nb // 2 + 1, np.uint8, device),
-                    quals=_device_empty(nb, np.uint8, device), op_off=op_off,
-                    ops=_device_empty(no.value, np.uint32, device), refb_off=refb_off,
-                    refb4=_device_empty(nf.value // 2 + 1, np.uint8, device))
+                    quals=_device_empty(nb, np.uint8, device),
+                    ops=_device_empty(no.value, np.uint32, device),
+                    refb=_device_empty(nf.value, np.uint8, device))
         out = _packed_out(arrs, n, nb, no.value, nf.value)
         rc = lib.avo_synth_device(C.byref(p), first, n, op_off.data_ptr(), refb_off.data_ptr(), None,
                                   None, C.byref(out), stream)

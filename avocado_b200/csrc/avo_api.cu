@@ -19,8 +19,7 @@ namespace {
 constexpr int32_t LNK_N = 1 << 16;
 
 enum Slot {
-  SL_START, SL_END, SL_MAPQ, SL_FLAGS, SL_SEQOFF, SL_BASES, SL_QUALS, SL_OPOFF, SL_OPS, SL_REFBOFF,
-  SL_REFB,
+  SL_META, SL_BASES, SL_QUALS, SL_OPS, SL_REFB,
   SL_S_CONTIG, SL_S_START, SL_S_REFLEN, SL_S_ALTLEN, SL_S_AOFF, SL_S_ALLELES, SL_S_END, SL_S_PME,
   SL_S_COUNT,
   SL_CNV, SL_STATS, SL_SMALL, SL_RIDX, SL_SIDX, SL_TEMP, SL_LUT,
@@ -113,10 +112,11 @@ int validate_reads(avo_ctx* ctx, const avo_read_batch* r) {
   if (r->n_reads < 0 || r->n_reads >= (int64_t)INT32_MAX)
     return fail(ctx, AVO_E_INVALID, "n_reads out of range (must be < 2^31 per batch)");
   if (r->n_bases < 0 || r->n_bases > (int64_t)UINT32_MAX || r->n_ops < 0 ||
-      r->n_ops > (int64_t)UINT32_MAX || r->n_refb < 0 || r->n_refb > (int64_t)UINT32_MAX)
+      r->n_ops > (int64_t)UINT32_MAX || r->n_refb < 0 || r->n_refb > (int64_t)INT32_MAX)
     return fail(ctx, AVO_E_INVALID, "batch totals must fit 32-bit offsets; split the batch");
-  if (r->n_reads > 0 && (!r->start || !r->end || !r->mapq || !r->flags || !r->seq_off || !r->op_off ||
-                         !r->refb_off))
+  if (r->n_reads > 0 && !r->meta) return fail(ctx, AVO_E_INVALID, "read batch has no meta column");
+  if ((r->n_bases > 0 && (!r->bases4 || !r->quals)) || (r->n_ops > 0 && !r->ops) ||
+      (r->n_refb > 0 && !r->refb))
     return fail(ctx, AVO_E_INVALID, "read batch has NULL columns");
   if (r->mem != AVO_MEM_HOST && r->mem != AVO_MEM_DEVICE) return fail(ctx, AVO_E_INVALID, "bad reads->mem");
   return AVO_OK;
@@ -126,17 +126,11 @@ int upload_reads(avo_ctx* ctx, const avo_read_batch* r, DReads* R) {
   const size_t n = (size_t)r->n_reads;
   R->n = r->n_reads;
   R->contig = r->contig_id;
-  CKS(stage_in(ctx, SL_START, r->start, n, r->mem, &R->start));
-  CKS(stage_in(ctx, SL_END, r->end, n, r->mem, &R->end));
-  CKS(stage_in(ctx, SL_MAPQ, r->mapq, n, r->mem, &R->mapq));
-  CKS(stage_in(ctx, SL_FLAGS, r->flags, n, r->mem, &R->flags));
-  CKS(stage_in(ctx, SL_SEQOFF, r->seq_off, n + 1, r->mem, &R->seq_off));
+  CKS(stage_in(ctx, SL_META, r->meta, n, r->mem, &R->meta));
+  CKS(stage_in(ctx, SL_OPS, r->ops, (size_t)r->n_ops, r->mem, &R->ops));
+  CKS(stage_in(ctx, SL_REFB, r->refb, (size_t)r->n_refb, r->mem, &R->refb));
   CKS(stage_in(ctx, SL_BASES, r->bases4, (size_t)(r->n_bases + 1) / 2, r->mem, &R->bases4));
   CKS(stage_in(ctx, SL_QUALS, r->quals, (size_t)r->n_bases, r->mem, &R->quals));
-  CKS(stage_in(ctx, SL_OPOFF, r->op_off, n + 1, r->mem, &R->op_off));
-  CKS(stage_in(ctx, SL_OPS, r->ops, (size_t)r->n_ops, r->mem, &R->ops));
-  CKS(stage_in(ctx, SL_REFBOFF, r->refb_off, n + 1, r->mem, &R->refb_off));
-  CKS(stage_in(ctx, SL_REFB, r->refb4, (size_t)(r->n_refb + 1) / 2, r->mem, &R->refb4));
   return AVO_OK;
 }
 

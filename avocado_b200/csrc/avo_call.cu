@@ -201,11 +201,10 @@ __device__ __forceinline__ uint32_t make_record(int slot, uint32_t cat, bool fwd
 // nothing for the owned site chunk [cLo, cHi).
 __device__ __forceinline__ bool join_read(const DReads& R, const DSites& S, int32_t r, int32_t cLo,
                                           int32_t cHi, int32_t hLo, int32_t hHi, int32_t& a, int32_t& b) {
-  if (__ldg(R.flags + r) & AVO_READ_SKIP_CALL) return false;
-  forest_get(S, R.contig, __ldg(R.start + r), __ldg(R.end + r), hLo, hHi, a, b);
+  const int2 se = __ldg(reinterpret_cast<const int2*>(R.meta + r));   // start, end
+  forest_get(S, R.contig, se.x, se.y, hLo, hHi, a, b);
   if (a >= b) return false;                               // no overlapping variant: read dropped
-  if (b <= cLo || a >= cHi) return false;                 // nothing of this chunk
-  return __ldg(R.op_off + r + 1) != __ldg(R.op_off + r);  // no operators -> no observations
+  return !(b <= cLo || a >= cHi);                         // nothing of this chunk
 }
 
 // Everything one joined read contributes to the owned site chunk [cLo, cHi): returns the number of
@@ -213,15 +212,18 @@ __device__ __forceinline__ bool join_read(const DReads& R, const DSites& S, int3
 __device__ int classify_read(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
                              int32_t r, int32_t a, int32_t b, int32_t cLo, int32_t cHi,
                              uint32_t* recs) {
-  const uint32_t flags = __ldg(R.flags + r);
+  const MetaA ma = load_meta_a(R.meta, r);
+  const MetaB mb = load_meta_b(R.meta, r);
+  // observeRead throws for such reads (BG:385-391: skipped); no operators -> no observations
+  if ((mb.flags & AVO_READ_SKIP_CALL) || mb.n_ops == 0) return 0;
   ReadCtx rc;
-  rc.start = __ldg(R.start + r);
-  rc.end = __ldg(R.end + r);
-  rc.ob = __ldg(R.op_off + r);
-  rc.no = __ldg(R.op_off + r + 1) - rc.ob;
-  rc.sb = __ldg(R.seq_off + r);
-  rc.mapq = __ldg(R.mapq + r);
-  rc.fwd = !(flags & AVO_READ_NEGATIVE_STRAND);
+  rc.start = ma.start;
+  rc.end = ma.end;
+  rc.ob = ma.op_off;
+  rc.no = mb.n_ops;
+  rc.sb = ma.seq_off;
+  rc.mapq = mb.mapq;
+  rc.fwd = !(mb.flags & AVO_READ_NEGATIVE_STRAND);
 
   const int ns = b - a;
   uint32_t cats[MAX_LOCAL_SITES];

@@ -10,6 +10,26 @@ __device__ __forceinline__ uint32_t nib_at(const uint8_t* __restrict__ p, uint32
   return (i & 1u) ? (b & 15u) : (b >> 4);
 }
 
+// The 32-byte read record is fetched as two 16-byte halves.
+struct MetaA { int32_t start, end; uint32_t seq_off, op_off; };
+struct MetaB { uint32_t refb_off, n_ops, mapq, flags, qhead, l_seq; };
+
+__device__ __forceinline__ MetaA load_meta_a(const avo_read_meta* __restrict__ m, int64_t r) {
+  const int4 v = __ldg(reinterpret_cast<const int4*>(m + r));
+  MetaA a; a.start = v.x; a.end = v.y; a.seq_off = (uint32_t)v.z; a.op_off = (uint32_t)v.w;
+  return a;
+}
+__device__ __forceinline__ MetaB load_meta_b(const avo_read_meta* __restrict__ m, int64_t r) {
+  const int4 v = __ldg(reinterpret_cast<const int4*>(m + r) + 1);
+  MetaB b; b.refb_off = (uint32_t)v.x;
+  b.n_ops = (uint32_t)v.y & 0xFFFFu; b.mapq = ((uint32_t)v.y >> 16) & 0xFFu; b.flags = (uint32_t)v.y >> 24;
+  b.qhead = (uint32_t)v.z; b.l_seq = (uint32_t)v.w;
+  return b;
+}
+__device__ __forceinline__ int32_t meta_start(const avo_read_meta* __restrict__ m, int64_t r) {
+  return __ldg(&m[r].start);
+}
+
 __device__ __forceinline__ int32_t site_contig(const DSites& S, int32_t k) {
   return S.contig ? __ldg(S.contig + k) : 0;
 }
@@ -38,11 +58,12 @@ __device__ __forceinline__ int32_t idx_bin_ceil(const DIndex& X, int64_t x) {
   return (int32_t)(k > X.nb ? X.nb : k);
 }
 
-__device__ __forceinline__ int64_t lower_bound_i64n(const int32_t* __restrict__ a, int64_t lo,
-                                                    int64_t hi, int32_t v) {
+// first read in [lo, hi) with start >= v   (reads sorted by start)
+__device__ __forceinline__ int64_t lower_bound_reads(const avo_read_meta* __restrict__ m, int64_t lo,
+                                                     int64_t hi, int32_t v) {
   while (lo < hi) {
     int64_t mid = lo + ((hi - lo) >> 1);
-    if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid;
+    if (meta_start(m, mid) < v) lo = mid + 1; else hi = mid;
   }
   return lo;
 }

@@ -31,87 +31,77 @@ __device__ __forceinline__ uint32_t mix32(uint32_t h, uint32_t v) {
   return h;
 }
 
-// DiscoverVariants.scala:112-252 for one read.  snp(pos, refNib, altNib) and
-// indel(pos, ref_len, alt_len, lastRefNib, anchorNib, src) are called for every candidate that
-// passes the phred threshold.
+// One I / D operator of one read, queued by the thread that walked the read and handled after the
+// walk by whichever thread picks it up (indels are rare; handling them inline would stall the
+// other 31 reads of the warp on their scattered quality / base loads).
+struct IndelEvent {
+  int32_t pos;       // pos - 1 (the anchor position)
+  uint32_t bidx;     // I: global index of the first inserted base; D: of the anchor base
+  uint32_t rb;       // D: refb nibble index of the deleted bases
+  uint32_t lenkind;  // (len << 3) | (lastRef lives in refb ? 4 : 0) | kind   kind: 1 I, 2 D
+  uint32_t last;     // location of lastRef (bases4 index or refb nibble index)
+};
+
+// DiscoverVariants.scala:112-252 for one read.  snp(pos, (ref << 4) | alt) is called for every
+// mismatching base that passes the phred threshold, indel(IndelEvent) for every I / D operator
+// after the first aligned base (its quality test runs in disc_handle_indel).
 template <typename SnpF, typename IndelF>
-__device__ __forceinline__ void walk_discover(const DReads& R, int64_t r, int32_t thr, SnpF&& snp,
-                                              IndelF&& indel) {
-  const uint32_t ob = __ldg(R.op_off + r);
-  const uint32_t no = __ldg(R.op_off + r + 1) - ob;
-  if (no == 0) return;
-  const uint32_t sb = __ldg(R.seq_off + r);
-  uint32_t rb = __ldg(R.refb_off + r);
-  int32_t pos = __ldg(R.start + r);
-  uint32_t idx = 0;
-  uint32_t k = 0;
-  // fastForward (:139-172)
-  for (; k < no; ++k) {
-    const uint32_t op = __ldg(R.ops + ob + k);
+__device__ __forceinline__ void walk_discover(const DReads& R, const MetaA& a, const MetaB& m, int32_t thr,
+                                              SnpF&& snp, IndelF&& indel) {
+  const uint32_t no = m.n_ops;
+  const uint32_t sb = a.seq_off;
+  uint32_t rb = m.refb_off;          // byte index into refb
+  int32_t pos = a.start;
+  uint32_t idx = 0, last = 0;
+  bool ff = true, last_refb = false;
+  for (uint32_t k = 0; k < no; ++k) {
+    const uint32_t op = __ldg(R.ops + a.op_off + k);
     const uint32_t len = op >> 4, code = op & 15u;
-    if (code == AVO_OP_MATCH || code == AVO_OP_MISMATCH) break;
-    if (code == AVO_OP_SOFTCLIP || code == AVO_OP_INS) idx += len;
-    else if (code == AVO_OP_DEL) { pos += (int32_t)len; rb += len; }
-  }
-  // emitVariants (:177-249).  lastRef is tracked lazily as a location.
-  bool last_is_refb = false;
-  uint32_t last_loc = 0;
-  auto last_ref = [&]() -> uint32_t {
-    return last_is_refb ? nib_at(R.refb4, last_loc) : nib_at(R.bases4, last_loc);
-  };
-  for (; k < no; ++k) {
-    const uint32_t op = __ldg(R.ops + ob + k);
-    const uint32_t len = op >> 4, code = op & 15u;
-    if (code == AVO_OP_MATCH) {                                           // :194-197
-      last_is_refb = false; last_loc = sb + idx + len - 1;
+    if (ff && (code == AVO_OP_MATCH || code == AVO_OP_MISMATCH)) ff = false;
+    if (ff) {                                                             // fastForward (:139-172)
+      if (code == AVO_OP_SOFTCLIP || code == AVO_OP_INS) idx += len;
+      else if (code == AVO_OP_DEL) { pos += (int32_t)len; rb += (len + 1) >> 1; }
+    } else if (code == AVO_OP_MATCH) {                                    // :194-197
+      last = sb + idx + len - 1; last_refb = false;
       pos += (int32_t)len; idx += len;
     } else if (code == AVO_OP_MISMATCH) {                                 // :198-210
       for (uint32_t i = 0; i < len; ++i) {
-        if ((int32_t)__ldg(R.quals + sb + i) >= thr)                      // qual(i), not qual(idx+i)
-          snp(pos + (int32_t)i, nib_at(R.refb4, rb + i), nib_at(R.bases4, sb + idx + i));
+        // qual(i), not qual(idx + i): the first four qualities of the read travel in the record
+        const int32_t q = (i < 4) ? (int32_t)((m.qhead >> (8 * i)) & 255u) : (int32_t)__ldg(R.quals + sb + i);
+        if (q >= thr) snp(pos + (int32_t)i, (uint32_t)__ldg(R.refb + rb + i));
       }
-      last_is_refb = true; last_loc = rb + len - 1;
+      last = 2 * (rb + len - 1); last_refb = true;
       rb += len; pos += (int32_t)len; idx += len;
     } else if (code == AVO_OP_INS) {                                      // :215-228
-      int sum = 0;
-      for (uint32_t j = idx - 1; j < idx + len; ++j) sum += __ldg(R.quals + sb + j);
-      if (sum / (int)len >= thr)
-        indel(pos - 1, 1, (int32_t)len + 1, last_ref(), nib_at(R.bases4, sb + idx - 1), sb + idx, false);
+      IndelEvent e;
+      e.pos = pos - 1; e.bidx = sb + idx; e.rb = 0;
+      e.lenkind = (len << 3) | (last_refb ? 4u : 0u) | 1u; e.last = last;
+      indel(e);
       idx += len;
     } else if (code == AVO_OP_DEL) {                                      // :229-242
-      if ((int32_t)__ldg(R.quals + sb + idx - 1) >= thr)
-        indel(pos - 1, (int32_t)len + 1, 1, last_ref(), nib_at(R.bases4, sb + idx - 1), rb, true);
+      IndelEvent e;
+      e.pos = pos - 1; e.bidx = sb + idx - 1; e.rb = 2 * rb;
+      e.lenkind = (len << 3) | (last_refb ? 4u : 0u) | 2u; e.last = last;
+      indel(e);
       pos += (int32_t)len;
-      last_is_refb = true; last_loc = rb + len - 1;
-      rb += len;
-    }
-    // Clipped: no-op (:191-193)
+      last = 2 * rb + len - 1; last_refb = true;
+      rb += (len + 1) >> 1;
+    }                                                                     // Clipped: no-op (:191-193)
   }
 }
 
-// One X / I / D operator of one read, queued by the warp that walked the read and handled later by
-// whichever lane picks it up (so that the loads and atomics of candidate emission run converged).
-struct DiscEvent {
-  int32_t pos;       // X: reference position of the first mismatching base; I, D: pos - 1 (the anchor)
-  uint32_t bidx;     // X: global index of the first mismatching read base; I: first inserted base; D: anchor base
-  uint32_t rb;       // X, D: global refb nibble index of the operator's reference bases
-  uint32_t sb;       // first base of the read (the reference indexes qual(i) from the read start for X)
-  uint32_t lenkind;  // (len << 3) | (lastRef lives in refb4 ? 4 : 0) | kind   kind: 0 X, 1 I, 2 D
-  uint32_t last;     // location of lastRef (bases4 or refb4 nibble index)
-};
-
 constexpr int DISC_WARPS = DISC_THREADS / 32;
-constexpr int DISC_Q = 64;
+constexpr int DISC_Q = 256;             // indel events of one tile kept in shared memory
 
 struct __align__(16) DiscSmem {
   uint32_t cnt[DISC_W];                 // pass 1: candidates per position; then hot index or NOT_HOT
   uint32_t hist[DISC_HB][256];          // pass 2: exact (ref<<4|alt) counts of the batch's hot positions
   uint32_t list[DISC_LIST];             // SNV candidates of the tile: (pos_off << 8) | (ref << 4) | alt
-  DiscEvent q[DISC_WARPS][DISC_Q];
+  IndelEvent q[DISC_Q];
   typename cub::BlockScan<int, DISC_THREADS>::TempStorage scan;
   int32_t tile;
   int32_t n_list;
-  int32_t next;                         // next unclaimed read of the tile (warps claim 32 at a time)
+  int32_t n_q;
   int32_t hotpos[DISC_HB];              // window offsets of the current batch's hot positions
 };
 
@@ -124,7 +114,7 @@ __device__ __forceinline__ void disc_indel_append(const DReads& R, const DIndelL
   h = mix32(h, ((uint32_t)ref_len << 16) | (uint32_t)alt_len);
   h = mix32(h, (lastRef << 4) | anchor);
   const int n = is_del ? ref_len - 1 : alt_len - 1;
-  const uint8_t* buf = is_del ? R.refb4 : R.bases4;
+  const uint8_t* buf = is_del ? R.refb : R.bases4;
   uint32_t acc = 0;
   for (int i = 0; i < n; ++i) {
     acc = (acc << 4) | nib_at(buf, src + i);
@@ -138,130 +128,37 @@ __device__ __forceinline__ void disc_indel_append(const DReads& R, const DIndelL
   L.hash[slot] = h;
 }
 
-// candidate emission for one queued event (DiscoverVariants.scala:198-242)
-__device__ __forceinline__ void disc_handle_event(const DReads& R, const DIndelList& L, DiscSmem& sm,
-                                                  const DiscEvent& e, int32_t thr, int64_t wlo) {
+// candidate emission for one I / D operator (DiscoverVariants.scala:215-242)
+__device__ __forceinline__ void disc_handle_indel(const DReads& R, const DIndelList& L, const IndelEvent& e,
+                                                  int32_t thr) {
   const uint32_t kind = e.lenkind & 3u, len = e.lenkind >> 3;
-  if (kind == 0) {                                                          // :198-210
-    for (uint32_t i = 0; i < len; ++i) {
-      if ((int32_t)__ldg(R.quals + e.sb + i) < thr) continue;               // qual(i), not qual(idx+i)
-      const int64_t o = (int64_t)e.pos + i - wlo;
-      if (o < 0 || o >= DISC_W) continue;
-      const uint32_t refn = nib_at(R.refb4, e.rb + i), altn = nib_at(R.bases4, e.bidx + i);
-      atomicAdd(&sm.cnt[o], 1u);
-      const int slot = atomicAdd(&sm.n_list, 1);
-      if (slot < DISC_LIST) sm.list[slot] = ((uint32_t)o << 8) | (refn << 4) | altn;
-    }
-    return;
-  }
-  const int64_t o = (int64_t)e.pos - wlo;
-  if (o < 0 || o >= DISC_W) return;
   const bool last_refb = e.lenkind & 4u;
   if (kind == 1) {                                                          // :215-228
     int sum = 0;
     for (uint32_t j = 0; j <= len; ++j) sum += __ldg(R.quals + e.bidx - 1 + j);
     if (sum / (int)len < thr) return;
-    const uint32_t lastRef = last_refb ? nib_at(R.refb4, e.last) : nib_at(R.bases4, e.last);
+    const uint32_t lastRef = last_refb ? nib_at(R.refb, e.last) : nib_at(R.bases4, e.last);
     disc_indel_append(R, L, e.pos, 1, (int32_t)len + 1, lastRef, nib_at(R.bases4, e.bidx - 1), e.bidx, false);
   } else {                                                                  // :229-242
     if ((int32_t)__ldg(R.quals + e.bidx) < thr) return;
-    const uint32_t lastRef = last_refb ? nib_at(R.refb4, e.last) : nib_at(R.bases4, e.last);
+    const uint32_t lastRef = last_refb ? nib_at(R.refb, e.last) : nib_at(R.bases4, e.last);
     disc_indel_append(R, L, e.pos, (int32_t)len + 1, 1, lastRef, nib_at(R.bases4, e.bidx), e.rb, true);
   }
 }
 
-// Pass 1 for one warp: claims 32 reads at a time, walks their operators in lock step (the walk is
-// pure integer bookkeeping), queues every X / I / D operator, and drains the queue 32 events at a time.
-__device__ __forceinline__ void disc_walk_warp(const DReads& R, const DIndelList& L, DiscSmem& sm,
-                                               int warp, int lane, int32_t rHi, int32_t thr, int64_t wlo) {
-  DiscEvent* q = sm.q[warp];
-  const unsigned lt = (1u << lane) - 1u;
-  int qn = 0;
-  auto drain = [&](int take) {
-    if (lane < take) disc_handle_event(R, L, sm, q[lane], thr, wlo);
-    const int rest = qn - take;
-    DiscEvent t;
-    if (lane < rest) t = q[take + lane];
-    __syncwarp();
-    if (lane < rest) q[lane] = t;
-    qn = rest;
-    __syncwarp();
-  };
-  for (;;) {
-    int32_t base = 0;
-    if (lane == 0) base = atomicAdd(&sm.next, 32);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base >= rHi) break;
-    const int32_t r = base + lane;
-    const bool active = r < rHi;
-    uint32_t ob = 0, no = 0, sb = 0, rb = 0;
-    int32_t pos = 0;
-    if (active) {
-      ob = __ldg(R.op_off + r);
-      no = __ldg(R.op_off + r + 1) - ob;
-      sb = __ldg(R.seq_off + r);
-      rb = __ldg(R.refb_off + r);
-      pos = __ldg(R.start + r);
-    }
-    uint32_t idx = 0, last = 0;
-    bool ff = true, last_refb = false;
-    const uint32_t maxno = __reduce_max_sync(0xFFFFFFFFu, no);
-    for (uint32_t k = 0; k < maxno; ++k) {
-      DiscEvent e;
-      bool ev = false;
-      if (k < no) {
-        const uint32_t op = __ldg(R.ops + ob + k);
-        const uint32_t len = op >> 4, code = op & 15u;
-        if (ff && (code == AVO_OP_MATCH || code == AVO_OP_MISMATCH)) ff = false;
-        if (ff) {                                                           // fastForward (:139-172)
-          if (code == AVO_OP_SOFTCLIP || code == AVO_OP_INS) idx += len;
-          else if (code == AVO_OP_DEL) { pos += (int32_t)len; rb += len; }
-        } else if (code == AVO_OP_MATCH) {                                  // :194-197
-          last = sb + idx + len - 1; last_refb = false;
-          pos += (int32_t)len; idx += len;
-        } else if (code == AVO_OP_MISMATCH) {
-          ev = true;
-          e.pos = pos; e.bidx = sb + idx; e.rb = rb; e.sb = sb; e.lenkind = (len << 3) | 0u; e.last = 0;
-          last = rb + len - 1; last_refb = true;
-          rb += len; pos += (int32_t)len; idx += len;
-        } else if (code == AVO_OP_INS) {
-          ev = true;
-          e.pos = pos - 1; e.bidx = sb + idx; e.rb = rb; e.sb = sb;
-          e.lenkind = (len << 3) | (last_refb ? 4u : 0u) | 1u; e.last = last;
-          idx += len;
-        } else if (code == AVO_OP_DEL) {
-          ev = true;
-          e.pos = pos - 1; e.bidx = sb + idx - 1; e.rb = rb; e.sb = sb;
-          e.lenkind = (len << 3) | (last_refb ? 4u : 0u) | 2u; e.last = last;
-          pos += (int32_t)len;
-          last = rb + len - 1; last_refb = true;
-          rb += len;
-        }                                                                   // Clipped: no-op (:191-193)
-      }
-      const unsigned m = __ballot_sync(0xFFFFFFFFu, ev);
-      if (m) {
-        if (ev) q[qn + __popc(m & lt)] = e;
-        qn += __popc(m);
-        __syncwarp();
-        if (qn >= 32) drain(32);
-      }
-    }
-  }
-  if (qn > 0) drain(qn);
-}
-
-__global__ void __launch_bounds__(DISC_THREADS, 5)
+__global__ void __launch_bounds__(DISC_THREADS, 4)
 k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep count > min_count */,
                  int32_t n_tiles, int32_t max_span, DDiscoverOut out, DIndelList L,
                  int32_t* __restrict__ tile_counter) {
   __shared__ DiscSmem sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt = (1u << lane) - 1u;
   constexpr int BPT = DISC_W / IDX_G;
   constexpr int PER_T = DISC_W / DISC_THREADS;
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) { sm.tile = atomicAdd(tile_counter, 1); sm.n_list = 0; }
+    if (tid == 0) { sm.tile = atomicAdd(tile_counter, 1); sm.n_list = 0; sm.n_q = 0; }
     __syncthreads();
     const int32_t tile = sm.tile;
     if (tile >= n_tiles) break;
@@ -272,13 +169,39 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
     if (rLo >= rHi) continue;
 
     for (int i = tid; i < DISC_W; i += DISC_THREADS) sm.cnt[i] = 0;
-    if (tid == 0) sm.next = rLo;
     __syncthreads();
 
-    // ---- pass 1 (the only walk over the reads): per-position SNV candidate counts, the tile's SNV
-    // candidate list in shared memory, indel candidates to the global list ----------------------
-    disc_walk_warp(R, L, sm, warp, lane, rHi, thr, wlo);
+    // ---- pass 1 (the only walk over the reads): one read per thread.  Per-position SNV candidate
+    // counts and the tile's SNV candidate list in shared memory; I / D operators to the event queue
+    for (int32_t r = rLo + tid; r < rHi; r += DISC_THREADS) {
+      const MetaA a = load_meta_a(R.meta, r);
+      if ((int64_t)a.end <= wlo) continue;             // ends before the window
+      const MetaB m = load_meta_b(R.meta, r);
+      walk_discover(
+          R, a, m, thr,
+          [&](int32_t pos, uint32_t pair) {
+            const int64_t o = (int64_t)pos - wlo;
+            if (o < 0 || o >= DISC_W) return;
+            atomicAdd(&sm.cnt[o], 1u);
+            const unsigned am = __activemask();
+            const int leader = __ffs(am) - 1;
+            int slot = 0;
+            if (lane == leader) slot = atomicAdd(&sm.n_list, __popc(am));
+            slot = __shfl_sync(am, slot, leader) + __popc(am & lt);
+            if (slot < DISC_LIST) sm.list[slot] = ((uint32_t)o << 8) | (pair & 255u);
+          },
+          [&](const IndelEvent& e) {
+            const int64_t o = (int64_t)e.pos - wlo;
+            if (o < 0 || o >= DISC_W) return;
+            const int slot = atomicAdd(&sm.n_q, 1);
+            if (slot < DISC_Q) sm.q[slot] = e; else disc_handle_indel(R, L, e, thr);
+          });
+    }
     __syncthreads();
+    {
+      const int nq = min(sm.n_q, DISC_Q);
+      for (int i = tid; i < nq; i += DISC_THREADS) disc_handle_indel(R, L, sm.q[i], thr);
+    }
     const int n_list = sm.n_list;
     const bool list_ok = n_list <= DISC_LIST;   // else: fall back to re-walking the reads in pass 2
 
@@ -312,16 +235,18 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
         }
       } else {
         for (int32_t r = rLo + tid; r < rHi; r += DISC_THREADS) {
+          const MetaA a = load_meta_a(R.meta, r);
+          const MetaB m = load_meta_b(R.meta, r);
           walk_discover(
-              R, r, thr,
-              [&](int32_t pos, uint32_t refn, uint32_t altn) {
+              R, a, m, thr,
+              [&](int32_t pos, uint32_t pair) {
                 const int64_t o = (int64_t)pos - wlo;
                 if (o < 0 || o >= DISC_W) return;
                 const uint32_t h = sm.cnt[o];
                 if (h == NOT_HOT || (int)h < hb || (int)h >= hb + DISC_HB) return;
-                atomicAdd(&sm.hist[h - hb][(refn << 4) | altn], 1u);
+                atomicAdd(&sm.hist[h - hb][pair & 255u], 1u);
               },
-              [&](int32_t, int32_t, int32_t, uint32_t, uint32_t, uint32_t, bool) {});
+              [&](const IndelEvent&) {});
         }
       }
       __syncthreads();
@@ -381,7 +306,7 @@ __device__ __forceinline__ bool indel_equal(const DReads& R, const DIndelList& L
   const int ref_len = (int)(lens >> 16), alt_len = (int)(lens & 0xFFFFu);
   const bool is_del = ref_len > 1;
   const int n = is_del ? ref_len - 1 : alt_len - 1;
-  const uint8_t* buf = is_del ? R.refb4 : R.bases4;
+  const uint8_t* buf = is_del ? R.refb : R.bases4;
   const uint32_t sa = L.src[a], sb = L.src[b];
   for (int i = 0; i < n; ++i)
     if (nib_at(buf, sa + i) != nib_at(buf, sb + i)) return false;
@@ -459,7 +384,7 @@ __device__ __forceinline__ uint32_t survivor_nib(const DReads& R, const DIndelLi
   const uint32_t nibs = L.nibs[rec];
   if (ref_len > 1) {                   // deletion: lastRef + deleted ref bases | anchor
     if (t == 0) return nibs >> 4;
-    if (t < ref_len) return nib_at(R.refb4, L.src[rec] + (uint32_t)(t - 1));
+    if (t < ref_len) return nib_at(R.refb, L.src[rec] + (uint32_t)(t - 1));
     return nibs & 15u;
   }
   if (t == 0) return nibs >> 4;        // insertion: lastRef | anchor + inserted bases

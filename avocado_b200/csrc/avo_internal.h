@@ -13,18 +13,13 @@ namespace avo {
 struct DReads {
   int64_t n;
   int32_t contig;
-  const int32_t* start;
-  const int32_t* end;
-  const uint8_t* mapq;
-  const uint8_t* flags;
-  const uint32_t* seq_off;
+  const avo_read_meta* meta;   // 32-byte record per read (include/avocado_b200.h)
   const uint8_t* bases4;
   const uint8_t* quals;
-  const uint32_t* op_off;
   const uint32_t* ops;
-  const uint32_t* refb_off;
-  const uint8_t* refb4;
+  const uint8_t* refb;
 };
+static_assert(sizeof(avo_read_meta) == 32, "avo_read_meta must be one 32-byte sector");
 
 struct DSites {
   int32_t n;          // total entries in the table (all contigs)
@@ -132,7 +127,7 @@ struct DIndelList {
   int32_t* pos;
   uint32_t* lens;       // (ref_len << 16) | alt_len
   uint32_t* nibs;       // (lastRef nibble << 4) | anchor (alt[0] / read base) nibble
-  uint32_t* src;        // INS: global base index of the first inserted base; DEL: global refb nibble index
+  uint32_t* src;        // INS: global base index of the first inserted base; DEL: nibble index (2 * byte) into refb
   uint32_t* hash;
 };
 

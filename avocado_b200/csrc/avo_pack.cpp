@@ -98,16 +98,23 @@ struct Scratch {
 inline char lookup(const std::vector<char>& m, size_t i) { return i < m.size() ? m[i] : 0; }
 
 // returns false when the reference's extractAlignmentOperators would throw or return empty
+// refb bytes: MISMATCH -> one (reference base << 4) | read base byte per position, DEL -> the deleted
+// reference bases as nibbles, high first, padded to whole bytes.
+// `seq`/`lseq` give the read bases for the pairs (0 = N when the sequence is too short; such reads
+// are dropped by the caller anyway).
 bool extract_ops(const char* cig, size_t ncig, bool has_cigar, const char* md, size_t nmd, bool has_md,
-                 Scratch& sc, uint32_t* read_len_needed) {
+                 const char* seq, int64_t lseq, Scratch& sc, uint32_t* read_len_needed) {
   sc.ops.clear(); sc.refb.clear();
   *read_len_needed = 0;
   if (!has_cigar || (ncig == 1 && cig[0] == '*') || !has_md) return false;
   if (!parse_cigar(cig, ncig, sc.cigar)) return false;
   if (!parse_md(md, nmd, sc.mism, sc.del)) return false;
   size_t idx = 0;
-  uint32_t need = 0;
+  uint32_t need = 0;   // read bases consumed so far == index of the next read base
   auto push = [&](uint32_t len, uint32_t code) { sc.ops.push_back((len << 4) | code); };
+  auto read_nib = [&](uint32_t ri) -> uint8_t {
+    return (int64_t)ri < lseq ? NIB.t[(unsigned char)seq[ri]] : (uint8_t)15;
+  };
   for (const Elem& e : sc.cigar) {
     if (e.len == 0 && e.op != 'S' && e.op != 'H') return false;  // 0-length M asserts; 0I divides by zero
     switch (e.op) {
@@ -120,7 +127,7 @@ bool extract_ops(const char* cig, size_t ncig, bool has_cigar, const char* md, s
           if (k > 0 && mis != in_mis) { push(run, in_mis ? AVO_OP_MISMATCH : AVO_OP_MATCH); run = 0; }
           in_mis = mis;
           ++run;
-          if (mis) sc.refb.push_back(NIB.t[(unsigned char)b]);
+          if (mis) sc.refb.push_back((uint8_t)((NIB.t[(unsigned char)b] << 4) | read_nib(need + k)));
         }
         push(run, in_mis ? AVO_OP_MISMATCH : AVO_OP_MATCH);
         idx += e.len; need += e.len;
@@ -134,7 +141,7 @@ bool extract_ops(const char* cig, size_t ncig, bool has_cigar, const char* md, s
         for (uint32_t k = 0; k < e.len; ++k) {
           const char b = lookup(sc.mism, idx + k);
           if (!b) return false;
-          sc.refb.push_back(NIB.t[(unsigned char)b]);
+          sc.refb.push_back((uint8_t)((NIB.t[(unsigned char)b] << 4) | read_nib(need + k)));
         }
         push(e.len, AVO_OP_MISMATCH);
         idx += e.len; need += e.len;
@@ -147,7 +154,8 @@ bool extract_ops(const char* cig, size_t ncig, bool has_cigar, const char* md, s
         for (uint32_t k = 0; k < e.len; ++k) {
           const char b = lookup(sc.del, idx + k);
           if (!b) return false;
-          sc.refb.push_back(NIB.t[(unsigned char)b]);
+          const uint8_t nb = NIB.t[(unsigned char)b];
+          if (k & 1) sc.refb.back() |= nb; else sc.refb.push_back((uint8_t)(nb << 4));
         }
         push(e.len, AVO_OP_DEL);
         idx += e.len;
@@ -184,12 +192,12 @@ int avo_pack_bounds(const avo_text_reads* in, int64_t* n_reads, int64_t* n_bases
   for (int64_t i = 0; i < in->n; ++i) {
     if (!kept(in, i)) continue;
     ++r;
-    b += in->seq_off[i + 1] - in->seq_off[i];
+    b += ((in->seq_off[i + 1] - in->seq_off[i]) + 1) & ~(int64_t)1;   // reads start on even indices
     // every op needs at least one CIGAR character pair or one MD character
     const int64_t c = in->cigar_off[i + 1] - in->cigar_off[i];
     const int64_t m = in->md_off[i + 1] - in->md_off[i];
     o += c / 2 + 1 + 2 * m;
-    f += m;
+    f += m + 1;
   }
   *n_reads = r; *n_bases = b; *n_ops = o; *n_refb = f;
   return AVO_OK;
@@ -211,7 +219,7 @@ int avo_pack_reads(const avo_text_reads* in, avo_packed_out* out) {
     uint32_t need = 0;
     bool ok = extract_ops(in->cigar + in->cigar_off[i], (size_t)(in->cigar_off[i + 1] - in->cigar_off[i]),
                           rf & 4, in->md + in->md_off[i], (size_t)(in->md_off[i + 1] - in->md_off[i]),
-                          rf & 8, sc, &need);
+                          rf & 8, seq, lseq, sc, &need);
     uint8_t flags = (rf & 2) ? AVO_READ_NEGATIVE_STRAND : 0;
     const bool has_mapq = (rf & 16) && in->mapq[i] >= 0;
     // observeRead indexes sequence and qualities up to the CIGAR's read length
@@ -219,38 +227,39 @@ int avo_pack_reads(const avo_text_reads* in, avo_packed_out* out) {
     // discovery additionally indexes qual(i) from 0 and sequence up to the same length: a read
     // whose strings are too short would crash the reference job; it is dropped here instead
     if (ok && ((int64_t)need > lseq || (int64_t)need > lqual)) ok = false;
-    if (!ok) { sc.ops.clear(); sc.refb.clear(); }
-    if ((int64_t)(nb + (uint64_t)lseq) > out->n_bases || (int64_t)(no + sc.ops.size()) > out->n_ops ||
+    if (!ok || sc.ops.size() > 0xFFFFu) { sc.ops.clear(); sc.refb.clear(); }
+    const uint64_t lpad = ((uint64_t)lseq + 1) & ~1ull;       // reads start on even base indices
+    if ((int64_t)(nb + lpad) > out->n_bases || (int64_t)(no + sc.ops.size()) > out->n_ops ||
         (int64_t)(nf + sc.refb.size()) > out->n_refb)
       return AVO_E_CAPACITY;
-    if (nb + (uint64_t)lseq > 0xFFFFFFFFull) return AVO_E_INVALID;   // split the batch
-    out->start[r] = (int32_t)in->start[i];
-    out->end[r] = (int32_t)in->end[i];
-    int mq = has_mapq ? in->mapq[i] : 0;
-    out->mapq[r] = (uint8_t)(mq > 255 ? 255 : mq);
-    out->flags[r] = flags;
-    out->seq_off[r] = (uint32_t)nb;
-    out->op_off[r] = (uint32_t)no;
-    out->refb_off[r] = (uint32_t)nf;
+    if (nb + lpad > 0xFFFFFFFFull) return AVO_E_INVALID;   // split the batch
+    avo_read_meta& m = out->meta[r];
+    m.start = (int32_t)in->start[i];
+    m.end = (int32_t)in->end[i];
+    const int mq = has_mapq ? in->mapq[i] : 0;
+    m.mapq = (uint8_t)(mq > 255 ? 255 : mq);
+    m.flags = flags;
+    m.seq_off = (uint32_t)nb;
+    m.op_off = (uint32_t)no;
+    m.refb_off = (uint32_t)nf;
+    m.n_ops = (uint16_t)sc.ops.size();
+    m.l_seq = (uint32_t)lseq;
+    m.qhead = 0;
     if (out->source_index) out->source_index[r] = i;
-    for (int64_t k = 0; k < lseq; ++k) {
+    for (int64_t k = 0; k < (int64_t)lpad; ++k) {
       const uint64_t bi = nb + (uint64_t)k;
-      const uint8_t nibv = NIB.t[(unsigned char)seq[k]];
+      const uint8_t nibv = k < lseq ? NIB.t[(unsigned char)seq[k]] : (uint8_t)0;
       if (bi & 1) out->bases4[bi >> 1] |= nibv; else out->bases4[bi >> 1] = (uint8_t)(nibv << 4);
-      int q = (k < lqual) ? (int)(unsigned char)qual[k] - 33 : 0;
-      out->quals[bi] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+      int q = (k < lqual && k < lseq) ? (int)(unsigned char)qual[k] - 33 : 0;
+      q = q < 0 ? 0 : (q > 255 ? 255 : q);
+      out->quals[bi] = (uint8_t)q;
+      if (k < 4) m.qhead |= (uint32_t)q << (8 * k);
     }
     for (size_t k = 0; k < sc.ops.size(); ++k) out->ops[no + k] = sc.ops[k];
-    for (size_t k = 0; k < sc.refb.size(); ++k) {
-      const uint64_t fi = nf + k;
-      if (fi & 1) out->refb4[fi >> 1] |= sc.refb[k]; else out->refb4[fi >> 1] = (uint8_t)(sc.refb[k] << 4);
-    }
-    nb += (uint64_t)lseq; no += sc.ops.size(); nf += sc.refb.size();
+    for (size_t k = 0; k < sc.refb.size(); ++k) out->refb[nf + k] = sc.refb[k];
+    nb += lpad; no += sc.ops.size(); nf += sc.refb.size();
     ++r;
   }
-  out->seq_off[r] = (uint32_t)nb;
-  out->op_off[r] = (uint32_t)no;
-  out->refb_off[r] = (uint32_t)nf;
   out->n_reads = r; out->n_bases = (int64_t)nb; out->n_ops = (int64_t)no; out->n_refb = (int64_t)nf;
   return AVO_OK;
 }

@@ -12,11 +12,12 @@ __global__ void k_batch_stats(DReads R, BatchStats* __restrict__ st) {
   int32_t mn = INT32_MAX, mxe = INT32_MIN, mxs = 0, uns = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < R.n;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int32_t s = __ldg(R.start + i), e = __ldg(R.end + i);
+    const MetaA a = load_meta_a(R.meta, i);
+    const int32_t s = a.start, e = a.end;
     mn = min(mn, s);
     mxe = max(mxe, e);
     mxs = max(mxs, e - s);
-    if (i > 0 && __ldg(R.start + i - 1) > s) uns = 1;
+    if (i > 0 && meta_start(R.meta, i - 1) > s) uns = 1;
   }
   for (int o = 16; o > 0; o >>= 1) {
     mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
@@ -132,7 +133,7 @@ __global__ void k_build_index(DReads R, DSites S, int32_t win0, int32_t nb, int3
   if (k <= nb) {
     const int64_t key64 = (int64_t)win0 + (int64_t)k * IDX_G;
     const int32_t key = (int32_t)min(key64, (int64_t)INT32_MAX);
-    ridx[k] = (k == nb) ? (int32_t)R.n : (int32_t)lower_bound_i64n(R.start, 0, R.n, key);
+    ridx[k] = (k == nb) ? (int32_t)R.n : (int32_t)lower_bound_reads(R.meta, 0, R.n, key);
     if (S.n > 0) sidx[k] = lower_bound_i32(S.start, S.c_lo, S.c_hi, key);
   }
   if (k == 0 && S.n > 0) {

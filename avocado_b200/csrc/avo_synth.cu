@@ -116,7 +116,9 @@ HD int64_t read_start(const avo_synth_params& P, int64_t i) {
   return s + P.first_pos;
 }
 
-// Sink concept: base(nibble, qual), op(len, code), refb(nibble).  One read, fully determined by i.
+// Sink concept: base(nibble, qual), op(len, code), pair(ref, read) for a mismatching base,
+// delbase(nibble)... delend() for a deletion (include/avocado_b200.h: avo_read_batch.refb).
+// One read, fully determined by i.
 template <typename Sink>
 HD void synth_read(const avo_synth_params& P, int64_t i, Sink& out, int32_t* o_start, int32_t* o_end,
                    uint8_t* o_mapq, uint8_t* o_flags) {
@@ -160,7 +162,7 @@ HD void synth_read(const avo_synth_params& P, int64_t i, Sink& out, int32_t* o_s
     if (run_len && code != run_code) flush();
     run_code = code;
     ++run_len;
-    if (code == AVO_OP_MISMATCH) out.refb(code_of(r2));
+    if (code == AVO_OP_MISMATCH) out.pair(code_of(r2), code_of(b2));
     ++p;
     if (emitted >= body) break;
     if (v.kind == 2 && v.on[hap]) {                 // insertion after the anchor base
@@ -172,7 +174,8 @@ HD void synth_read(const avo_synth_params& P, int64_t i, Sink& out, int32_t* o_s
       out.op((uint32_t)n, (emitted >= body) ? AVO_OP_SOFTCLIP : AVO_OP_INS);
     } else if (v.kind == 3 && v.on[hap]) {          // deletion of p .. p+len-1 (anchor was p-1)
       flush();
-      for (int k = 0; k < v.len; ++k) out.refb(code_of(ref_base(P, p + k)));
+      for (int k = 0; k < v.len; ++k) out.delbase(code_of(ref_base(P, p + k)));
+      out.delend();
       out.op((uint32_t)v.len, AVO_OP_DEL);
       p += v.len;
     }
@@ -190,31 +193,40 @@ HD void synth_read(const avo_synth_params& P, int64_t i, Sink& out, int32_t* o_s
 }
 
 struct CountSink {
-  uint32_t n_ops = 0, n_refb = 0;
+  uint32_t n_ops = 0, n_refb = 0, pend = 0;   // n_refb in bytes
   HD void base(uint32_t, uint32_t) {}
   HD void op(uint32_t, uint32_t) { ++n_ops; }
-  HD void refb(uint32_t) { ++n_refb; }
+  HD void pair(uint32_t, uint32_t) { ++n_refb; }
+  HD void delbase(uint32_t) { ++pend; }
+  HD void delend() { n_refb += (pend + 1) >> 1; pend = 0; }
 };
 
 struct WriteSink {
-  uint8_t* bases4; uint8_t* quals; uint32_t* ops; uint8_t* refb4;
+  uint8_t* bases4; uint8_t* quals; uint32_t* ops; uint8_t* refb;
   uint64_t bi;   // global base index (even at read start)
   uint64_t oi;   // global op index
-  uint64_t fi;   // global refb nibble index (even at read start)
-  uint32_t pend_b = 0, pend_f = 0;
+  uint64_t fi;   // global refb byte index
+  uint32_t pend_b = 0, pend_f = 0, n_pend = 0;
+  uint32_t nb = 0, qhead = 0;   // bases written so far; phred of the first four
   HD void base(uint32_t nib, uint32_t q) {
+    if (nb < 4) qhead |= q << (8 * nb);
+    ++nb;
     quals[bi] = (uint8_t)q;
     if (bi & 1) bases4[bi >> 1] = (uint8_t)((pend_b << 4) | nib); else pend_b = nib;
     ++bi;
   }
   HD void op(uint32_t len, uint32_t code) { ops[oi++] = (len << 4) | code; }
-  HD void refb(uint32_t nib) {
-    if (fi & 1) refb4[fi >> 1] = (uint8_t)((pend_f << 4) | nib); else pend_f = nib;
-    ++fi;
+  HD void pair(uint32_t refn, uint32_t readn) { refb[fi++] = (uint8_t)((refn << 4) | readn); }
+  HD void delbase(uint32_t nib) {
+    if (n_pend & 1) refb[fi++] = (uint8_t)((pend_f << 4) | nib); else pend_f = nib;
+    ++n_pend;
+  }
+  HD void delend() {
+    if (n_pend & 1) refb[fi++] = (uint8_t)(pend_f << 4);
+    n_pend = 0;
   }
   HD void finish() {
     if (bi & 1) bases4[bi >> 1] = (uint8_t)(pend_b << 4);
-    if (fi & 1) refb4[fi >> 1] = (uint8_t)(pend_f << 4);
   }
 };
 
@@ -228,25 +240,31 @@ __global__ void k_synth_count(avo_synth_params P, int64_t first, int64_t n, uint
   int32_t s, e; uint8_t mq, fl;
   synth_read(P, first + j, c, &s, &e, &mq, &fl);
   n_ops[j] = c.n_ops;
-  n_refb[j] = even_up(c.n_refb);
+  n_refb[j] = c.n_refb;
 }
 
-__global__ void k_synth_write(avo_synth_params P, int64_t first, int64_t n, int32_t* __restrict__ start,
-                              int32_t* __restrict__ end, uint8_t* __restrict__ mapq,
-                              uint8_t* __restrict__ flags, uint32_t* __restrict__ seq_off,
+HD void fill_meta(avo_read_meta& m, int32_t start, int32_t end, uint8_t mapq, uint8_t flags,
+                  uint32_t seq_off, uint32_t op_off, uint32_t refb_off, uint32_t n_ops, uint32_t qhead,
+                  uint32_t l_seq) {
+  m.start = start; m.end = end; m.seq_off = seq_off; m.op_off = op_off; m.refb_off = refb_off;
+  m.n_ops = (uint16_t)n_ops; m.mapq = mapq; m.flags = flags; m.qhead = qhead; m.l_seq = l_seq;
+}
+
+__global__ void k_synth_write(avo_synth_params P, int64_t first, int64_t n, avo_read_meta* __restrict__ meta,
                               uint8_t* __restrict__ bases4, uint8_t* __restrict__ quals,
                               const uint32_t* __restrict__ op_off, uint32_t* __restrict__ ops,
-                              const uint32_t* __restrict__ refb_off, uint8_t* __restrict__ refb4) {
+                              const uint32_t* __restrict__ refb_off, uint8_t* __restrict__ refb) {
   const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (j > n) return;
+  if (j >= n) return;
   const uint32_t lpad = even_up((uint32_t)P.read_len);
-  seq_off[j] = (uint32_t)(j * lpad);
-  if (j == n) return;
   WriteSink w;
-  w.bases4 = bases4; w.quals = quals; w.ops = ops; w.refb4 = refb4;
+  w.bases4 = bases4; w.quals = quals; w.ops = ops; w.refb = refb;
   w.bi = (uint64_t)j * lpad; w.oi = op_off[j]; w.fi = refb_off[j];
-  synth_read(P, first + j, w, &start[j], &end[j], &mapq[j], &flags[j]);
+  int32_t s, e; uint8_t mq, fl;
+  synth_read(P, first + j, w, &s, &e, &mq, &fl);
   w.finish();
+  fill_meta(meta[j], s, e, mq, fl, (uint32_t)(j * lpad), op_off[j], refb_off[j], op_off[j + 1] - op_off[j],
+            w.qhead, (uint32_t)P.read_len);
 }
 
 }  // namespace avo
@@ -292,7 +310,7 @@ int avo_synth_host(const avo_synth_params* p, int64_t first, int64_t n, int64_t*
       CountSink c;
       int32_t s, e; uint8_t mq, fl;
       synth_read(*p, first + j, c, &s, &e, &mq, &fl);
-      to += c.n_ops; tf += even_up(c.n_refb);
+      to += c.n_ops; tf += c.n_refb;
     }
     if (n_ops) *n_ops = (int64_t)to;
     if (n_refb) *n_refb = (int64_t)tf;
@@ -302,22 +320,18 @@ int avo_synth_host(const avo_synth_params* p, int64_t first, int64_t n, int64_t*
     CountSink c;
     int32_t s, e; uint8_t mq, fl;
     synth_read(*p, first + j, c, &s, &e, &mq, &fl);
-    if ((int64_t)(to + c.n_ops) > out->n_ops || (int64_t)(tf + even_up(c.n_refb)) > out->n_refb ||
+    if ((int64_t)(to + c.n_ops) > out->n_ops || (int64_t)(tf + c.n_refb) > out->n_refb ||
         j >= out->n_reads)
       return AVO_E_CAPACITY;
-    out->seq_off[j] = (uint32_t)(j * lpad);
-    out->op_off[j] = (uint32_t)to;
-    out->refb_off[j] = (uint32_t)tf;
     WriteSink w;
-    w.bases4 = out->bases4; w.quals = out->quals; w.ops = out->ops; w.refb4 = out->refb4;
+    w.bases4 = out->bases4; w.quals = out->quals; w.ops = out->ops; w.refb = out->refb;
     w.bi = (uint64_t)j * lpad; w.oi = to; w.fi = tf;
-    synth_read(*p, first + j, w, &out->start[j], &out->end[j], &out->mapq[j], &out->flags[j]);
+    synth_read(*p, first + j, w, &s, &e, &mq, &fl);
     w.finish();
-    to += c.n_ops; tf += even_up(c.n_refb);
+    fill_meta(out->meta[j], s, e, mq, fl, (uint32_t)(j * lpad), (uint32_t)to, (uint32_t)tf, c.n_ops,
+              w.qhead, (uint32_t)p->read_len);
+    to += c.n_ops; tf += c.n_refb;
   }
-  out->seq_off[n] = (uint32_t)(n * lpad);
-  out->op_off[n] = (uint32_t)to;
-  out->refb_off[n] = (uint32_t)tf;
   out->n_reads = n; out->n_bases = (int64_t)n * lpad; out->n_ops = (int64_t)to; out->n_refb = (int64_t)tf;
   if (n_ops) *n_ops = (int64_t)to;
   if (n_refb) *n_refb = (int64_t)tf;
@@ -358,9 +372,9 @@ int avo_synth_device(const avo_synth_params* p, int64_t first, int64_t n, uint32
     *n_ops = tot[0]; *n_refb = tot[1];
     return AVO_OK;
   }
-  k_synth_write<<<grid, 128, 0, s>>>(*p, first, n, out->start, out->end, out->mapq, out->flags,
-                                     out->seq_off, out->bases4, out->quals, op_off_dev, out->ops,
-                                     refb_off_dev, out->refb4);
+  if (n > 0)
+    k_synth_write<<<grid, 128, 0, s>>>(*p, first, n, out->meta, out->bases4, out->quals, op_off_dev,
+                                       out->ops, refb_off_dev, out->refb);
   cudaError_t e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) { cudaGetLastError(); return AVO_E_CUDA; }
   return AVO_OK;

@@ -138,8 +138,10 @@ def oracle_sample(B, p, first, n, contig_id=0):
     dev = B.synth_device(p, first=first, n=n)
     h = dev.to_host()
     del dev
-    rs = oracle.reads_from_packed("chr20", h.start, h.end, h.mapq, h.flags, h.seq_off, h.bases4, h.quals,
-                                  h.op_off, h.ops, h.refb_off, h.refb4)
+    m = h.meta
+    rs = oracle.reads_from_packed("chr20", m["start"], m["end"], m["mapq"], m["flags"], m["seq_off"],
+                                  m["l_seq"], h.bases4, h.quals, m["op_off"], m["n_ops"], h.ops,
+                                  m["refb_off"], h.refb)
     return oracle, rs
 
 

@@ -54,9 +54,9 @@ enum { AVO_MAX_PLOIDY = 7 };
  * op word = (length << 4) | code */
 enum {
   AVO_OP_MATCH = 0,     /* Match(n)           sequence match   '=' */
-  AVO_OP_MISMATCH = 1,  /* Match(n, Some(ref)) sequence mismatch 'X'; n ref nibbles in refb4 */
+  AVO_OP_MISMATCH = 1,  /* Match(n, Some(ref)) sequence mismatch 'X'; n (ref, read) bytes in refb */
   AVO_OP_INS = 2,       /* Insertion(n) */
-  AVO_OP_DEL = 3,       /* Deletion(ref); n ref nibbles in refb4 */
+  AVO_OP_DEL = 3,       /* Deletion(ref); n ref nibbles ((n+1)/2 bytes) in refb */
   AVO_OP_SOFTCLIP = 4,  /* Clipped(n, soft = true) */
   AVO_OP_HARDCLIP = 5   /* Clipped(n, soft = false) */
 };
@@ -78,26 +78,38 @@ const char* avo_version(void);
 int avo_ctx_set_stream(avo_ctx* ctx, void* cuda_stream);
 
 /* ---- inputs ------------------------------------------------------------------------------- */
+/* Per-read scalars, one 32-byte record per read (one DRAM sector: a read that joins a site costs
+ * one sector for all of them).  Replaces the AlignmentRecord fields listed in SURVEY.md 8b. */
+typedef struct {
+  int32_t start;     /* AlignmentRecord.start */
+  int32_t end;       /* AlignmentRecord.end */
+  uint32_t seq_off;  /* index of the read's first base in bases4 / quals (even) */
+  uint32_t op_off;   /* index of the read's first operator in ops */
+  uint32_t refb_off; /* byte index of the read's first entry in refb */
+  uint16_t n_ops;    /* number of operators (0: the reference could not extract any) */
+  uint8_t mapq;
+  uint8_t flags;     /* AVO_READ_* */
+  uint32_t qhead;    /* phred of the read's first four bases, byte i = qual(i): DiscoverVariants
+                        tests qual(i), i = offset inside the mismatch run (DiscoverVariants.scala:199) */
+  uint32_t l_seq;    /* number of bases */
+} avo_read_meta;
+
 /* One batch = reads of ONE contig, sorted by start (ties in any order; the order of the batch is
- * the canonical summation order).  Replaces the AlignmentRecord fields listed in SURVEY.md 8b. */
+ * the canonical summation order). */
 typedef struct {
   int64_t n_reads;
-  int64_t n_bases; /* seq_off[n_reads] */
-  int64_t n_ops;   /* op_off[n_reads] */
-  int64_t n_refb;  /* refb_off[n_reads] (nibbles) */
+  int64_t n_bases; /* bases4 / quals entries (reads start on even indices) */
+  int64_t n_ops;
+  int64_t n_refb;  /* refb bytes (< 2^31) */
   int32_t contig_id; /* rank of this contig in the site table's contig order */
   int32_t mem;
-  const int32_t* start;     /* [n] AlignmentRecord.start */
-  const int32_t* end;       /* [n] AlignmentRecord.end */
-  const uint8_t* mapq;      /* [n] */
-  const uint8_t* flags;     /* [n] */
-  const uint32_t* seq_off;  /* [n+1] base index of the read's first base */
-  const uint8_t* bases4;    /* [(n_bases+1)/2] */
-  const uint8_t* quals;     /* [n_bases] */
-  const uint32_t* op_off;   /* [n+1] */
-  const uint32_t* ops;      /* [n_ops] */
-  const uint32_t* refb_off; /* [n+1] nibble index */
-  const uint8_t* refb4;     /* [(n_refb+1)/2] reference bases of MISMATCH and DEL ops, in op order */
+  const avo_read_meta* meta; /* [n_reads] */
+  const uint8_t* bases4;     /* [(n_bases+1)/2] */
+  const uint8_t* quals;      /* [n_bases] */
+  const uint32_t* ops;       /* [n_ops] */
+  const uint8_t* refb;       /* [n_refb] in operator order: a MISMATCH op of length n holds n bytes
+                                (reference base << 4) | read base, a DEL op its n deleted reference
+                                bases as nibbles (high first) padded to (n+1)/2 bytes */
 } avo_read_batch;
 
 /* Variant sites, sorted by (contig, start, start + ref_len); unique.  Replaces the Variant
@@ -236,9 +248,8 @@ typedef struct {
 
 typedef struct {
   int64_t n_reads, n_bases, n_ops, n_refb; /* in: capacities; out: used */
-  int32_t* start; int32_t* end; uint8_t* mapq; uint8_t* flags;
-  uint32_t* seq_off; uint8_t* bases4; uint8_t* quals;
-  uint32_t* op_off; uint32_t* ops; uint32_t* refb_off; uint8_t* refb4;
+  avo_read_meta* meta;
+  uint8_t* bases4; uint8_t* quals; uint32_t* ops; uint8_t* refb;
   int64_t* source_index; /* [n_reads] index of each packed read in the input (may be NULL) */
 } avo_packed_out;
 

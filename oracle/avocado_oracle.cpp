@@ -1266,19 +1266,22 @@ static std::shared_ptr<ReadSet> readsFromPacked(
     py::array_t<uint8_t, py::array::c_style | py::array::forcecast> mapq,
     py::array_t<uint8_t, py::array::c_style | py::array::forcecast> flags,
     py::array_t<uint32_t, py::array::c_style | py::array::forcecast> seqOff,
+    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> lSeq,
     py::array_t<uint8_t, py::array::c_style | py::array::forcecast> bases4,
     py::array_t<uint8_t, py::array::c_style | py::array::forcecast> quals,
     py::array_t<uint32_t, py::array::c_style | py::array::forcecast> opOff,
+    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> nOps,
     py::array_t<uint32_t, py::array::c_style | py::array::forcecast> ops,
     py::array_t<uint32_t, py::array::c_style | py::array::forcecast> refbOff,
-    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> refb4) {
+    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> refb) {
   static const char* NIBS = "=ACMGRSVTWYHKDBN";
   auto rs = std::make_shared<ReadSet>();
   const size_t n = (size_t)start.size();
   auto st = start.unchecked<1>(); auto en = end.unchecked<1>(); auto mq = mapq.unchecked<1>();
-  auto fl = flags.unchecked<1>(); auto so = seqOff.unchecked<1>(); auto b4 = bases4.unchecked<1>();
-  auto ql = quals.unchecked<1>(); auto oo = opOff.unchecked<1>(); auto op = ops.unchecked<1>();
-  auto fo = refbOff.unchecked<1>(); auto f4 = refb4.unchecked<1>();
+  auto fl = flags.unchecked<1>(); auto so = seqOff.unchecked<1>(); auto ls = lSeq.unchecked<1>();
+  auto b4 = bases4.unchecked<1>(); auto ql = quals.unchecked<1>(); auto oo = opOff.unchecked<1>();
+  auto no = nOps.unchecked<1>(); auto op = ops.unchecked<1>(); auto fo = refbOff.unchecked<1>();
+  auto fb = refb.unchecked<1>();
   auto nib = [](const auto& a, uint64_t i) -> int { int b = a(i >> 1); return (i & 1) ? (b & 15) : (b >> 4); };
   rs->reads.resize(n);
   for (size_t i = 0; i < n; ++i) {
@@ -1287,19 +1290,33 @@ static std::shared_ptr<ReadSet> readsFromPacked(
     r.start = st(i); r.end = en(i);
     r.negativeStrand = fl(i) & 1;
     r.hasMapq = !(fl(i) & 2); r.mapq = mq(i);
-    const uint64_t b0 = so(i), b1 = so(i + 1);
+    const uint64_t b0 = so(i), b1 = b0 + ls(i);
     for (uint64_t b = b0; b < b1; ++b) { r.seq.push_back(NIBS[nib(b4, b)]); r.qual.push_back((char)(ql(b) + 33)); }
-    uint64_t f = fo(i);
+    uint64_t f = fo(i);   // byte index into refb
+    uint64_t ridx = 0;    // read bases consumed
     long run = 0;
     std::string md;
     bool any = false;
-    for (uint32_t k = oo(i); k < oo(i + 1); ++k) {
+    for (uint32_t k = oo(i); k < oo(i) + no(i); ++k) {
       const uint32_t w = op(k), len = w >> 4, code = w & 15;
       any = true;
       r.cigar += std::to_string(len) + "=XIDSH"[code];
-      if (code == 0) run += len;
-      else if (code == 1) { for (uint32_t j = 0; j < len; ++j) { md += std::to_string(run); md.push_back(NIBS[nib(f4, f++)]); run = 0; } }
-      else if (code == 3) { md += std::to_string(run) + "^"; for (uint32_t j = 0; j < len; ++j) md.push_back(NIBS[nib(f4, f++)]); run = 0; }
+      if (code == 0) { run += len; ridx += len; }
+      else if (code == 1) {
+        for (uint32_t j = 0; j < len; ++j) {
+          const int pr = fb(f++);
+          // the low nibble repeats the read base: a packer / generator consistency check
+          if ((pr & 15) != nib(b4, b0 + ridx + j))
+            throw std::runtime_error("packed batch: mismatch pair does not repeat the read base");
+          md += std::to_string(run); md.push_back(NIBS[pr >> 4]); run = 0;
+        }
+        ridx += len;
+      } else if (code == 3) {
+        md += std::to_string(run) + "^";
+        for (uint32_t j = 0; j < len; ++j) md.push_back(NIBS[nib(fb, 2 * f + j)]);
+        f += (len + 1) / 2;
+        run = 0;
+      } else if (code == 2 || code == 4) ridx += len;
     }
     md += std::to_string(run);
     r.hasCigar = any; r.hasMd = any;

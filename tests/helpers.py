@@ -63,8 +63,10 @@ def rows(res):
 # ---- GPU parity glue ----------------------------------------------------------------------------
 def oracle_reads_from_batch(oracle, batch, contig="ctg"):
     b = batch.to_host()
-    return oracle.reads_from_packed(contig, b.start, b.end, b.mapq, b.flags, b.seq_off, b.bases4,
-                                    b.quals, b.op_off, b.ops, b.refb_off, b.refb4)
+    m = b.meta
+    return oracle.reads_from_packed(contig, m["start"], m["end"], m["mapq"], m["flags"], m["seq_off"],
+                                    m["l_seq"], b.bases4, b.quals, m["op_off"], m["n_ops"], b.ops,
+                                    m["refb_off"], b.refb)
 
 
 ORACLE_OF = {  # product column -> oracle column

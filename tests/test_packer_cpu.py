@@ -1,0 +1,82 @@
+"""CPU tests of the host packer and of the C-ABI library surface (no GPU, no compute calls).
+
+The packer is where ObservationOperator.extractAlignmentOperators (ObservationOperator.scala:42-171)
+happens in this build; the oracle's own restatement of that function is the checker.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import load_fixture, oracle_reads_from_batch
+
+FIXTURES = ["NA12878_snp_A2G_chr20_225058", "NA12878.chr1.832736", "NA12878.chr1.567239",
+            "NA12878.1_1777263", "NA12878.chr1.905130", "NA12878.1_5274547", "NA12878.chr1.104160"]
+
+
+def test_library_exports_every_declared_symbol():
+    from avocado_b200 import _lib as L
+    lib = L.load()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    declared = set()
+    for h in ("avocado_b200.h", "avocado_b200_synth.h"):
+        src = open(os.path.join(root, "include", h)).read()
+        declared |= set(re.findall(r"^\s*(?:int|void|const char\*)\s+(avo_\w+)\s*\(", src, re.M))
+    assert declared, "no declarations found"
+    assert declared == set(L.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+    assert C.sizeof(L.ReadBatchStruct) == 4 * 8 + 2 * 4 + 5 * 8
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_packed_reads_round_trip_through_the_oracle(oracle, name):
+    """pack -> unpack gives reads whose operators, sequence, qualities, strand and mapq are the
+    ones the oracle extracts from the original text."""
+    from avocado_b200 import batch as B
+    recs = [r for r in load_fixture(name)[0] if r.readMapped]
+    b = B.pack_reads(recs, sort=False)
+    assert b.n_reads == len(recs)
+    rs = oracle_reads_from_batch(oracle, b, contig="c")
+    for i, r in enumerate(recs):
+        d = oracle.read_as_dict(rs, i)
+        want_ops = oracle.extract_alignment_operators(r.as_dict())
+        m = b.meta[i]
+        if not want_ops:
+            assert m["n_ops"] == 0
+            continue
+        got_ops = oracle.extract_alignment_operators(d)
+        assert got_ops == want_ops, (i, r.cigar, r.mismatchingPositions)
+        assert d["sequence"] == r.sequence.upper() and d["qual"] == r.qual
+        assert (d["start"], d["end"]) == (r.start, r.end)
+        assert d["readNegativeStrand"] == bool(r.readNegativeStrand)
+        assert d["mapq"] == r.mapq
+        q = [ord(c) - 33 for c in r.qual[:4]] + [0] * 4
+        assert int(m["qhead"]) == q[0] | q[1] << 8 | q[2] << 16 | q[3] << 24
+        assert int(m["seq_off"]) % 2 == 0 and int(m["l_seq"]) == len(r.sequence)
+
+
+def test_synthetic_host_batch_is_consistent(oracle):
+    """The generator's packed batch decodes (the oracle checks every mismatch pair against the
+    read's bases), is sorted by start, and its records index disjoint, in-range slices."""
+    from avocado_b200 import batch as B
+    p = B.synth_params(seed=11, n_reads_total=5000, contig_len=40000)
+    b = B.synth_host(p)
+    m = b.meta
+    assert np.all(np.diff(m["start"]) >= 0)
+    assert np.all(m["end"] > m["start"])
+    assert np.array_equal(m["op_off"][1:], (m["op_off"] + m["n_ops"])[:-1])
+    assert int(m["op_off"][-1]) + int(m["n_ops"][-1]) == b.n_ops
+    assert np.all(np.diff(m["refb_off"].astype(np.int64)) >= 0) and int(m["refb_off"][-1]) <= b.n_refb
+    rs = oracle_reads_from_batch(oracle, b)
+    # the reference span of the operators equals end - start for every read
+    for i in range(0, b.n_reads, 97):
+        d = oracle.read_as_dict(rs, i)
+        span = sum(int(n) for n, c in re.findall(r"(\d+)([=XD])", d["cigar"]))
+        assert span == d["end"] - d["start"]
+    s = b.slice(100, 300)
+    rs2 = oracle_reads_from_batch(oracle, s)
+    for j in (0, 57, 199):
+        assert oracle.read_as_dict(rs2, j) == oracle.read_as_dict(rs, 100 + j)

@@ -21,7 +21,6 @@ namespace avo {
 constexpr int DISC_THREADS = 256;
 constexpr int DISC_W = 2048;      // reference positions owned by one tile
 constexpr int DISC_HB = 8;        // hot positions histogrammed per pass-2 batch
-constexpr int DISC_LIST = 3072;   // SNV candidates of one tile kept in shared memory
 constexpr uint32_t NOT_HOT = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t mix32(uint32_t h, uint32_t v) {
@@ -31,77 +30,81 @@ __device__ __forceinline__ uint32_t mix32(uint32_t h, uint32_t v) {
   return h;
 }
 
-// One I / D operator of one read, queued by the thread that walked the read and handled after the
-// walk by whichever thread picks it up (indels are rare; handling them inline would stall the
-// other 31 reads of the warp on their scattered quality / base loads).
-struct IndelEvent {
-  int32_t pos;       // pos - 1 (the anchor position)
-  uint32_t bidx;     // I: global index of the first inserted base; D: of the anchor base
-  uint32_t rb;       // D: refb nibble index of the deleted bases
-  uint32_t lenkind;  // (len << 3) | (lastRef lives in refb ? 4 : 0) | kind   kind: 1 I, 2 D
-  uint32_t last;     // location of lastRef (bases4 index or refb nibble index)
+// DiscoverVariants.scala:112-252, one operator at a time.  The hot loop carries only what SNV
+// candidates need (reference position, refb cursor, the fastForward flag) and is written without
+// branches on the operator kind (lanes of a warp hold different kinds); only candidate emission
+// diverges: snp(pos, (ref << 4) | alt) for every mismatching base that passes the phred threshold,
+// and indel(k, anchor) for every I / D operator after the first aligned base.  Indel candidates are
+// rare; their read index, lastRef and quality window are recomputed by disc_handle_indel.
+struct WalkState {
+  int32_t pos;       // reference position of the next aligned base
+  uint32_t rb;       // byte index into refb
+  bool ff;           // still in fastForward (:139-172): no aligned operator seen yet
 };
 
-// DiscoverVariants.scala:112-252 for one read.  snp(pos, (ref << 4) | alt) is called for every
-// mismatching base that passes the phred threshold, indel(IndelEvent) for every I / D operator
-// after the first aligned base (its quality test runs in disc_handle_indel).
-template <typename SnpF, typename IndelF>
-__device__ __forceinline__ void walk_discover(const DReads& R, const MetaA& a, const MetaB& m, int32_t thr,
-                                              SnpF&& snp, IndelF&& indel) {
-  const uint32_t no = m.n_ops;
-  const uint32_t sb = a.seq_off;
-  uint32_t rb = m.refb_off;          // byte index into refb
-  int32_t pos = a.start;
-  uint32_t idx = 0, last = 0;
-  bool ff = true, last_refb = false;
-  for (uint32_t k = 0; k < no; ++k) {
-    const uint32_t op = __ldg(R.ops + a.op_off + k);
-    const uint32_t len = op >> 4, code = op & 15u;
-    if (ff && (code == AVO_OP_MATCH || code == AVO_OP_MISMATCH)) ff = false;
-    if (ff) {                                                             // fastForward (:139-172)
-      if (code == AVO_OP_SOFTCLIP || code == AVO_OP_INS) idx += len;
-      else if (code == AVO_OP_DEL) { pos += (int32_t)len; rb += (len + 1) >> 1; }
-    } else if (code == AVO_OP_MATCH) {                                    // :194-197
-      last = sb + idx + len - 1; last_refb = false;
-      pos += (int32_t)len; idx += len;
-    } else if (code == AVO_OP_MISMATCH) {                                 // :198-210
-      for (uint32_t i = 0; i < len; ++i) {
-        // qual(i), not qual(idx + i): the first four qualities of the read travel in the record
-        const int32_t q = (i < 4) ? (int32_t)((m.qhead >> (8 * i)) & 255u) : (int32_t)__ldg(R.quals + sb + i);
-        if (q >= thr) snp(pos + (int32_t)i, (uint32_t)__ldg(R.refb + rb + i));
-      }
-      last = 2 * (rb + len - 1); last_refb = true;
-      rb += len; pos += (int32_t)len; idx += len;
-    } else if (code == AVO_OP_INS) {                                      // :215-228
-      IndelEvent e;
-      e.pos = pos - 1; e.bidx = sb + idx; e.rb = 0;
-      e.lenkind = (len << 3) | (last_refb ? 4u : 0u) | 1u; e.last = last;
-      indel(e);
-      idx += len;
-    } else if (code == AVO_OP_DEL) {                                      // :229-242
-      IndelEvent e;
-      e.pos = pos - 1; e.bidx = sb + idx - 1; e.rb = 2 * rb;
-      e.lenkind = (len << 3) | (last_refb ? 4u : 0u) | 2u; e.last = last;
-      indel(e);
-      pos += (int32_t)len;
-      last = 2 * rb + len - 1; last_refb = true;
-      rb += (len + 1) >> 1;
-    }                                                                     // Clipped: no-op (:191-193)
+__device__ __forceinline__ WalkState walk_begin(const MetaA& a, const MetaB& m) {
+  WalkState st;
+  st.pos = a.start; st.rb = m.refb_off; st.ff = true;
+  return st;
+}
+
+// SNV candidates of one mismatch run (:198-210)
+template <typename SnpF>
+__device__ __forceinline__ void walk_mismatch(const DReads& R, uint32_t len, int32_t pos, uint32_t rb,
+                                              uint32_t sb, uint32_t qhead, int32_t thr, SnpF&& snp) {
+  // qual(i), not qual(idx + i): the first four qualities of the read travel in the record
+  if ((int32_t)(qhead & 255u) >= thr) snp(pos, (uint32_t)__ldg(R.refb + rb));
+  for (uint32_t i = 1; i < len; ++i) {
+    const int32_t q = (i < 4) ? (int32_t)((qhead >> (8 * i)) & 255u) : (int32_t)__ldg(R.quals + sb + i);
+    if (q >= thr) snp(pos + (int32_t)i, (uint32_t)__ldg(R.refb + rb + i));
   }
 }
 
+template <typename SnpF, typename IndelF>
+__device__ __forceinline__ void walk_step(const DReads& R, uint32_t op, uint32_t k, uint32_t sb,
+                                          uint32_t qhead, int32_t thr, WalkState& st, SnpF&& snp,
+                                          IndelF&& indel) {
+  const uint32_t len = op >> 4, code = op & 15u;
+  const bool isX = code == AVO_OP_MISMATCH, isD = code == AVO_OP_DEL;
+  const bool aligned = code <= AVO_OP_MISMATCH;                           // MATCH or MISMATCH
+  if (isX) walk_mismatch(R, len, st.pos, st.rb, sb, qhead, thr, snp);
+  if ((code == AVO_OP_INS || isD) && !st.ff) indel(k, st.pos - 1);        // :215-242
+  st.pos += (aligned || isD) ? (int32_t)len : 0;
+  st.rb += isX ? len : isD ? ((len + 1) >> 1) : 0u;
+  st.ff = st.ff && !aligned;
+}
+
+// the whole read (long reads and the overflow paths)
+template <typename SnpF, typename IndelF>
+__device__ __forceinline__ void walk_discover(const DReads& R, const MetaA& a, const MetaB& m, int32_t thr,
+                                              SnpF&& snp, IndelF&& indel) {
+  WalkState st = walk_begin(a, m);
+  for (uint32_t k = 0; k < m.n_ops; ++k)
+    walk_step(R, __ldg(R.ops + a.op_off + k), k, a.seq_off, m.qhead, thr, st, snp, indel);
+}
+
+// An I / D operator awaiting its quality test: (read, operator index)
+struct IndelEvent { int32_t r; uint32_t k; };
+
 constexpr int DISC_WARPS = DISC_THREADS / 32;
 constexpr int DISC_Q = 256;             // indel events of one tile kept in shared memory
+constexpr int DISC_SHORT = 3;           // reads with at most this many operators are walked at once
+constexpr int DISC_LONGQ = 1024;        // reads with more operators: walked afterwards, lanes full
 
 struct __align__(16) DiscSmem {
-  uint32_t cnt[DISC_W];                 // pass 1: candidates per position; then hot index or NOT_HOT
-  uint32_t hist[DISC_HB][256];          // pass 2: exact (ref<<4|alt) counts of the batch's hot positions
-  uint32_t list[DISC_LIST];             // SNV candidates of the tile: (pos_off << 8) | (ref << 4) | alt
+  // fast path: SNV candidate counts per position and alternate base, two 16-bit fields per word
+  // (cnt[0]: A | C << 16, cnt[1]: G | T << 16), and the OR of the candidates' reference nibbles,
+  // 4 bits per position.  slow path: cnt[0] = candidates per position, then hot index or NOT_HOT.
+  uint32_t cnt[2][DISC_W];
+  uint32_t refm[DISC_W / 8];
+  uint32_t hist[DISC_HB][256];          // slow path: exact (ref<<4|alt) counts of the hot positions
   IndelEvent q[DISC_Q];
+  int32_t longq[DISC_LONGQ];
   typename cub::BlockScan<int, DISC_THREADS>::TempStorage scan;
   int32_t tile;
-  int32_t n_list;
   int32_t n_q;
+  int32_t n_long;
+  int32_t exotic;                       // a candidate with a non-ACGT base was seen: use the slow path
   int32_t hotpos[DISC_HB];              // window offsets of the current batch's hot positions
 };
 
@@ -128,21 +131,59 @@ __device__ __forceinline__ void disc_indel_append(const DReads& R, const DIndelL
   L.hash[slot] = h;
 }
 
-// candidate emission for one I / D operator (DiscoverVariants.scala:215-242)
-__device__ __forceinline__ void disc_handle_indel(const DReads& R, const DIndelList& L, const IndelEvent& e,
-                                                  int32_t thr) {
-  const uint32_t kind = e.lenkind & 3u, len = e.lenkind >> 3;
-  const bool last_refb = e.lenkind & 4u;
-  if (kind == 1) {                                                          // :215-228
+// candidate emission for operator k (an I or D) of read r: DiscoverVariants.scala:177-242 replayed
+// up to that operator to recover the read index, the refb cursor and lastRef (:186)
+__device__ void disc_handle_indel(const DReads& R, const DIndelList& L, int32_t r, uint32_t k, int32_t thr) {
+  const MetaA a = load_meta_a(R.meta, r);
+  const MetaB m = load_meta_b(R.meta, r);
+  const uint32_t sb = a.seq_off;
+  int32_t pos = a.start;
+  uint32_t idx = 0, rb = m.refb_off, last = 0;
+  bool ff = true, last_refb = false;
+  for (uint32_t j = 0; j < k; ++j) {
+    const uint32_t op = __ldg(R.ops + a.op_off + j);
+    const uint32_t len = op >> 4, code = op & 15u;
+    if (ff && code <= AVO_OP_MISMATCH) ff = false;
+    if (ff) {                                                             // fastForward (:139-172)
+      if (code == AVO_OP_SOFTCLIP || code == AVO_OP_INS) idx += len;
+      else if (code == AVO_OP_DEL) { pos += (int32_t)len; rb += (len + 1) >> 1; }
+    } else if (code == AVO_OP_MATCH) {                                    // :194-197
+      last = sb + idx + len - 1; last_refb = false;
+      pos += (int32_t)len; idx += len;
+    } else if (code == AVO_OP_MISMATCH) {                                 // :198-210
+      last = 2 * (rb + len - 1); last_refb = true;
+      rb += len; pos += (int32_t)len; idx += len;
+    } else if (code == AVO_OP_INS) {
+      idx += len;
+    } else if (code == AVO_OP_DEL) {
+      pos += (int32_t)len;
+      last = 2 * rb + len - 1; last_refb = true;
+      rb += (len + 1) >> 1;
+    }                                                                     // Clipped: no-op (:191-193)
+  }
+  const uint32_t op = __ldg(R.ops + a.op_off + k);
+  const uint32_t len = op >> 4;
+  const uint32_t lastRef = last_refb ? nib_at(R.refb, last) : nib_at(R.bases4, last);
+  const uint32_t anchor = nib_at(R.bases4, sb + idx - 1);
+  if ((op & 15u) == AVO_OP_INS) {                                         // :215-228
     int sum = 0;
-    for (uint32_t j = 0; j <= len; ++j) sum += __ldg(R.quals + e.bidx - 1 + j);
+    for (uint32_t j = 0; j <= len; ++j) sum += __ldg(R.quals + sb + idx - 1 + j);
     if (sum / (int)len < thr) return;
-    const uint32_t lastRef = last_refb ? nib_at(R.refb, e.last) : nib_at(R.bases4, e.last);
-    disc_indel_append(R, L, e.pos, 1, (int32_t)len + 1, lastRef, nib_at(R.bases4, e.bidx - 1), e.bidx, false);
-  } else {                                                                  // :229-242
-    if ((int32_t)__ldg(R.quals + e.bidx) < thr) return;
-    const uint32_t lastRef = last_refb ? nib_at(R.refb, e.last) : nib_at(R.bases4, e.last);
-    disc_indel_append(R, L, e.pos, (int32_t)len + 1, 1, lastRef, nib_at(R.bases4, e.bidx), e.rb, true);
+    disc_indel_append(R, L, pos - 1, 1, (int32_t)len + 1, lastRef, anchor, sb + idx, false);
+  } else {                                                                // :229-242
+    if ((int32_t)__ldg(R.quals + sb + idx - 1) < thr) return;
+    disc_indel_append(R, L, pos - 1, (int32_t)len + 1, 1, lastRef, anchor, 2 * rb, true);
+  }
+}
+
+__device__ __forceinline__ void disc_emit_snv(const DDiscoverOut& out, int32_t pos, uint32_t pair, int32_t c) {
+  const int32_t slot = atomicAdd(out.n, 1);
+  if (slot < out.capacity) {
+    out.start[slot] = pos;
+    out.ref_len[slot] = 1;
+    out.alt_len[slot] = 1;
+    out.count[slot] = c;
+    out.src[slot] = (1ull << 63) | (uint64_t)pair;
   }
 }
 
@@ -152,13 +193,14 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
                  int32_t* __restrict__ tile_counter) {
   __shared__ DiscSmem sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned lt = (1u << lane) - 1u;
   constexpr int BPT = DISC_W / IDX_G;
   constexpr int PER_T = DISC_W / DISC_THREADS;
 
+  for (int i = tid; i < 2 * DISC_W; i += DISC_THREADS) (&sm.cnt[0][0])[i] = 0;
+  for (int i = tid; i < DISC_W / 8; i += DISC_THREADS) sm.refm[i] = 0;
   for (;;) {
     __syncthreads();
-    if (tid == 0) { sm.tile = atomicAdd(tile_counter, 1); sm.n_list = 0; sm.n_q = 0; }
+    if (tid == 0) { sm.tile = atomicAdd(tile_counter, 1); sm.n_q = 0; sm.n_long = 0; sm.exotic = 0; }
     __syncthreads();
     const int32_t tile = sm.tile;
     if (tile >= n_tiles) break;
@@ -168,48 +210,135 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
     const int32_t rHi = __ldg(X.ridx + min((tile + 1) * BPT, X.nb));
     if (rLo >= rHi) continue;
 
-    for (int i = tid; i < DISC_W; i += DISC_THREADS) sm.cnt[i] = 0;
-    __syncthreads();
-
-    // ---- pass 1 (the only walk over the reads): one read per thread.  Per-position SNV candidate
-    // counts and the tile's SNV candidate list in shared memory; I / D operators to the event queue
+    // ---- the walk over the reads: one read per thread.  SNV candidates are counted per position
+    // and alternate base in shared memory; I / D operators go to the event queue.  Most reads are
+    // one match, or one mismatch run after the leading match, and are handled on the spot; the
+    // others are queued and walked afterwards so that no lane idles while a neighbour works
+    // through a long operator list.
+    auto snp = [&](int32_t pos, uint32_t pair) {
+      const int64_t o = (int64_t)pos - wlo;
+      if (o < 0 || o >= DISC_W) return;
+      const uint32_t refn = (pair >> 4) & 15u, altn = pair & 15u;
+      if (__popc(refn) != 1 || __popc(altn) != 1) { sm.exotic = 1; return; }
+      const int ai = __ffs(altn) - 1;                                 // A C G T -> 0 1 2 3
+      atomicAdd(&sm.cnt[ai >> 1][o], 1u << ((ai & 1) * 16));
+      atomicOr(&sm.refm[o >> 3], refn << ((o & 7) * 4));
+    };
     for (int32_t r = rLo + tid; r < rHi; r += DISC_THREADS) {
       const MetaA a = load_meta_a(R.meta, r);
-      if ((int64_t)a.end <= wlo) continue;             // ends before the window
       const MetaB m = load_meta_b(R.meta, r);
-      walk_discover(
-          R, a, m, thr,
-          [&](int32_t pos, uint32_t pair) {
-            const int64_t o = (int64_t)pos - wlo;
-            if (o < 0 || o >= DISC_W) return;
-            atomicAdd(&sm.cnt[o], 1u);
-            const unsigned am = __activemask();
-            const int leader = __ffs(am) - 1;
-            int slot = 0;
-            if (lane == leader) slot = atomicAdd(&sm.n_list, __popc(am));
-            slot = __shfl_sync(am, slot, leader) + __popc(am & lt);
-            if (slot < DISC_LIST) sm.list[slot] = ((uint32_t)o << 8) | (pair & 255u);
-          },
-          [&](const IndelEvent& e) {
-            const int64_t o = (int64_t)e.pos - wlo;
-            if (o < 0 || o >= DISC_W) return;
-            const int slot = atomicAdd(&sm.n_q, 1);
-            if (slot < DISC_Q) sm.q[slot] = e; else disc_handle_indel(R, L, e, thr);
-          });
+      if ((int64_t)a.end <= wlo || m.n_ops == 0) continue;   // ends before the window / no operators
+      const uint32_t w0 = __ldg(R.ops + a.op_off);
+      const uint32_t w1 = (m.n_ops > 1) ? __ldg(R.ops + a.op_off + 1) : 0u;
+      // the common shapes "=", "= X", "= X =" and "= X S"
+      const bool simple = m.n_ops <= DISC_SHORT && (w0 & 15u) == AVO_OP_MATCH &&
+                          (m.n_ops == 1 || (w1 & 15u) == AVO_OP_MISMATCH);
+      if (simple) {
+        if (m.n_ops > 1 && (m.n_ops == 2 || ((__ldg(R.ops + a.op_off + 2) & 15u) | 4u) == 4u))
+          walk_mismatch(R, w1 >> 4, a.start + (int32_t)(w0 >> 4), m.refb_off, a.seq_off, m.qhead, thr, snp);
+        else if (m.n_ops > 1) goto general;
+        continue;
+      }
+    general:
+      {
+        const int slot = atomicAdd(&sm.n_long, 1);
+        if (slot < DISC_LONGQ) { sm.longq[slot] = r; continue; }
+      }
+      walk_discover(R, a, m, thr, snp, [&](uint32_t k, int32_t anchor) {
+        if ((int64_t)anchor >= wlo && (int64_t)anchor < wlo + DISC_W) disc_handle_indel(R, L, r, k, thr);
+      });
+    }
+    __syncthreads();
+    {
+      const int nl = min(sm.n_long, DISC_LONGQ);
+      for (int i = tid; i < nl; i += DISC_THREADS) {
+        const int32_t r = sm.longq[i];
+        walk_discover(R, load_meta_a(R.meta, r), load_meta_b(R.meta, r), thr, snp,
+                      [&](uint32_t k, int32_t anchor) {
+                        if ((int64_t)anchor < wlo || (int64_t)anchor >= wlo + DISC_W) return;
+                        const int slot = atomicAdd(&sm.n_q, 1);
+                        if (slot < DISC_Q) { sm.q[slot].r = r; sm.q[slot].k = k; }
+                        else disc_handle_indel(R, L, r, k, thr);
+                      });
+      }
     }
     __syncthreads();
     {
       const int nq = min(sm.n_q, DISC_Q);
-      for (int i = tid; i < nq; i += DISC_THREADS) disc_handle_indel(R, L, sm.q[i], thr);
+      for (int i = tid; i < nq; i += DISC_THREADS) disc_handle_indel(R, L, sm.q[i].r, sm.q[i].k, thr);
     }
-    const int n_list = sm.n_list;
-    const bool list_ok = n_list <= DISC_LIST;   // else: fall back to re-walking the reads in pass 2
 
-    // ---- hot positions: ordered compaction; cnt[] becomes the hot index ------------------------
+    // ---- emission.  Fast path: every candidate had ACGT bases and each position saw one reference
+    // base, so the per-alt counters ARE the (ref, alt) counts.  The counters are cleared as they
+    // are read.  (16-bit fields cannot overflow: fewer than 65536 reads reach the tile.)
+    // A position is hot when one of its 16-bit counters exceeds min_count (tested four positions
+    // at a time; fields stay below 32768: fewer than 32768 reads reach the tile).
+    bool slow = sm.exotic != 0 || (rHi - rLo) >= 32768 || min_count >= 32767;
+    const uint32_t bias = (uint32_t)(0x7FFF - min_count) * 0x00010001u;
+    uint32_t hot = 0;                      // bit (4 j + e): position 4 (tid + j * DISC_THREADS) + e is hot
+    if (!slow) {
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < PER_T / 4; ++j) {
+        const int o4 = tid + j * DISC_THREADS;        // 16 contiguous bytes per lane: no bank conflicts
+        const uint4 vAC = reinterpret_cast<const uint4*>(sm.cnt[0])[o4];
+        const uint4 vGT = reinterpret_cast<const uint4*>(sm.cnt[1])[o4];
+        const uint32_t wa[4] = {vAC.x, vAC.y, vAC.z, vAC.w};
+        const uint32_t wg[4] = {vGT.x, vGT.y, vGT.z, vGT.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (((wa[e] + bias) | (wg[e] + bias)) & 0x80008000u) hot |= 1u << (4 * j + e);
+      }
+      for (uint32_t h = hot; h; h &= h - 1) {
+        const int b = __ffs(h) - 1;
+        const int o = 4 * (tid + (b >> 2) * DISC_THREADS) + (b & 3);
+        bad = bad || __popc((sm.refm[o >> 3] >> ((o & 7) * 4)) & 15u) != 1;
+      }
+      slow = __syncthreads_or(bad);
+    }
+    if (!slow) {
+      for (uint32_t h = hot; h; h &= h - 1) {
+        const int b = __ffs(h) - 1;
+        const int o = 4 * (tid + (b >> 2) * DISC_THREADS) + (b & 3);
+        const uint32_t wAC = sm.cnt[0][o], wGT = sm.cnt[1][o];
+        const uint32_t refn = (sm.refm[o >> 3] >> ((o & 7) * 4)) & 15u;
+        const int32_t c[4] = {(int32_t)(wAC & 0xFFFFu), (int32_t)(wAC >> 16), (int32_t)(wGT & 0xFFFFu),
+                              (int32_t)(wGT >> 16)};
+        for (int ai = 0; ai < 4; ++ai)
+          if (c[ai] > min_count) disc_emit_snv(out, (int32_t)(wlo + o), (refn << 4) | (1u << ai), c[ai]);
+      }
+      __syncthreads();
+      const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int j = 0; j < PER_T / 4; ++j) {
+        reinterpret_cast<uint4*>(sm.cnt[0])[tid + j * DISC_THREADS] = z;
+        reinterpret_cast<uint4*>(sm.cnt[1])[tid + j * DISC_THREADS] = z;
+      }
+      for (int i = tid; i < DISC_W / 8; i += DISC_THREADS) sm.refm[i] = 0;
+      continue;
+    }
+
+    // ---- slow path (non-ACGT candidate bases, inconsistent reference bases, or extreme depth):
+    // exact.  Re-walk for per-position candidate totals, then (ref, alt) histograms of the positions
+    // whose total exceeds the threshold, DISC_HB positions at a time.
+    __syncthreads();
+    for (int i = tid; i < 2 * DISC_W; i += DISC_THREADS) (&sm.cnt[0][0])[i] = 0;
+    for (int i = tid; i < DISC_W / 8; i += DISC_THREADS) sm.refm[i] = 0;
+    __syncthreads();
+    for (int32_t r = rLo + tid; r < rHi; r += DISC_THREADS) {
+      walk_discover(
+          R, load_meta_a(R.meta, r), load_meta_b(R.meta, r), thr,
+          [&](int32_t pos, uint32_t) {
+            const int64_t o = (int64_t)pos - wlo;
+            if (o >= 0 && o < DISC_W) atomicAdd(&sm.cnt[0][o], 1u);
+          },
+          [&](uint32_t, int32_t) {});
+    }
+    __syncthreads();
     int nh = 0;
     uint32_t hot_mask = 0;
     for (int i = 0; i < PER_T; ++i) {
-      const bool hot = (int32_t)sm.cnt[tid * PER_T + i] > min_count;
+      const bool hot = (int32_t)sm.cnt[0][tid * PER_T + i] > min_count;
       hot_mask |= (uint32_t)hot << i;
       nh += hot;
     }
@@ -217,64 +346,42 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
     cub::BlockScan<int, DISC_THREADS>(sm.scan).ExclusiveSum(nh, hoff, htotal);
     for (int i = 0; i < PER_T; ++i) {
       const bool hot = (hot_mask >> i) & 1u;
-      sm.cnt[tid * PER_T + i] = hot ? (uint32_t)hoff : NOT_HOT;
+      sm.cnt[0][tid * PER_T + i] = hot ? (uint32_t)hoff : NOT_HOT;
       hoff += hot;
     }
     __syncthreads();
-
-    // ---- pass 2: exact (ref, alt) counts at the hot positions, DISC_HB positions at a time ------
     for (int hb = 0; hb < htotal; hb += DISC_HB) {
       for (int i = tid; i < DISC_HB * 256; i += DISC_THREADS) (&sm.hist[0][0])[i] = 0;
       __syncthreads();
-      if (list_ok) {
-        for (int i = tid; i < n_list; i += DISC_THREADS) {
-          const uint32_t e = sm.list[i];
-          const uint32_t h = sm.cnt[e >> 8];
-          if (h == NOT_HOT || (int)h < hb || (int)h >= hb + DISC_HB) continue;
-          atomicAdd(&sm.hist[h - hb][e & 255u], 1u);
-        }
-      } else {
-        for (int32_t r = rLo + tid; r < rHi; r += DISC_THREADS) {
-          const MetaA a = load_meta_a(R.meta, r);
-          const MetaB m = load_meta_b(R.meta, r);
-          walk_discover(
-              R, a, m, thr,
-              [&](int32_t pos, uint32_t pair) {
-                const int64_t o = (int64_t)pos - wlo;
-                if (o < 0 || o >= DISC_W) return;
-                const uint32_t h = sm.cnt[o];
-                if (h == NOT_HOT || (int)h < hb || (int)h >= hb + DISC_HB) return;
-                atomicAdd(&sm.hist[h - hb][pair & 255u], 1u);
-              },
-              [&](const IndelEvent&) {});
-        }
+      for (int32_t r = rLo + tid; r < rHi; r += DISC_THREADS) {
+        walk_discover(
+            R, load_meta_a(R.meta, r), load_meta_b(R.meta, r), thr,
+            [&](int32_t pos, uint32_t pair) {
+              const int64_t o = (int64_t)pos - wlo;
+              if (o < 0 || o >= DISC_W) return;
+              const uint32_t h = sm.cnt[0][o];
+              if (h == NOT_HOT || (int)h < hb || (int)h >= hb + DISC_HB) return;
+              atomicAdd(&sm.hist[h - hb][pair & 255u], 1u);
+            },
+            [&](uint32_t, int32_t) {});
       }
       __syncthreads();
-      // emit: a warp scans the 256 (ref, alt) bins of one hot position of this batch
       for (int i = tid; i < DISC_W; i += DISC_THREADS) {
-        const uint32_t h = sm.cnt[i];
+        const uint32_t h = sm.cnt[0][i];
         if (h != NOT_HOT && (int)h >= hb && (int)h < hb + DISC_HB) sm.hotpos[h - hb] = i;
       }
       __syncthreads();
+      // a warp scans the 256 (ref, alt) bins of one hot position of this batch
       for (int s = warp; s < min(DISC_HB, htotal - hb); s += DISC_WARPS) {
         const int i = sm.hotpos[s];
-        const uint32_t h = (uint32_t)(hb + s);
         for (int k = lane; k < 256; k += 32) {
-          const int32_t c = (int32_t)sm.hist[h - hb][k];
-          if (c > min_count) {
-            const int32_t slot = atomicAdd(out.n, 1);
-            if (slot < out.capacity) {
-              out.start[slot] = (int32_t)(wlo + i);
-              out.ref_len[slot] = 1;
-              out.alt_len[slot] = 1;
-              out.count[slot] = c;
-              out.src[slot] = (1ull << 63) | (uint64_t)k;
-            }
-          }
+          const int32_t c = (int32_t)sm.hist[s][k];
+          if (c > min_count) disc_emit_snv(out, (int32_t)(wlo + i), (uint32_t)k, c);
         }
       }
       __syncthreads();
     }
+    for (int i = tid; i < DISC_W; i += DISC_THREADS) sm.cnt[0][i] = 0;
   }
 }
 

@@ -173,3 +173,30 @@ def test_empty_sites_and_unsorted_reads_are_errors(ctx):
     assert e.value.status == L.AVO_E_UNSORTED
     with pytest.raises(ValueError):                 # BG:102-105 exactly one sample
         BiallelicGenotyper.call([r], [], samples=["a", "b"], ctx=ctx)
+
+
+def test_discovery_exact_path_for_exotic_bases(oracle, ctx):
+    """Candidates with non-ACGT bases, or reads that disagree about the reference base of a
+    position, take the exact (ref, alt) histogram path of k_discover_tiles; the result must still
+    be the reference's groupBy(contig, start, ref, alt).count (DiscoverVariants.scala:87-97)."""
+    from avocado_b200.genotyping import DiscoverVariants
+    from avocado_b200.records import AlignmentRecord
+
+    def read(start, seq, md, name):
+        return AlignmentRecord(readMapped=True, contigName="1", start=start, end=start + len(seq),
+                               sequence=seq, qual="I" * len(seq), cigar="%dM" % len(seq),
+                               mismatchingPositions=md, mapq=40, readName=name)
+    recs = []
+    for i in range(6):      # alt N over ref A at 1004; alt C over ref A at 1008
+        recs.append(read(1000, "ACGTNACGCACGT", "4A3T4", "n%d" % i))
+    for i in range(5):      # the same positions, but these reads claim other reference bases
+        recs.append(read(1000, "ACGTNACGCACGT", "4C3G4", "m%d" % i))
+    for i in range(7):      # plain ACGT candidates in the same tile
+        recs.append(read(1002, "GTTACGTACG", "2A7", "p%d" % i))
+    for i in range(4):      # reference base N
+        recs.append(read(1003, "TTACGTAC", "3N4", "q%d" % i))
+    for phred, min_obs in ((None, None), (0, 3), (10, 5)):
+        want = oracle_discover(oracle, recs, phred, min_obs)
+        got = DiscoverVariants(recs, phred, min_obs, ctx=ctx)
+        assert sorted(v.as_tuple() for v in got) == sorted(want), (phred, min_obs)
+    assert len(oracle_discover(oracle, recs, 0, 3)) >= 4

@@ -35,6 +35,8 @@ P = C.c_void_p
 class ReadBatchStruct(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("n_bases", C.c_int64), ("n_ops", C.c_int64),
                 ("n_refb", C.c_int64), ("contig_id", C.c_int32), ("mem", C.c_int32),
+                ("stats_min_start", C.c_int32), ("stats_max_end", C.c_int32),
+                ("stats_max_span", C.c_int32), ("stats_valid", C.c_int32),
                 ("meta", P), ("bases4", P), ("quals", P), ("ops", P), ("refb", P)]
 
 

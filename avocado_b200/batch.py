@@ -55,6 +55,21 @@ class ReadBatch:
     ops: object = None
     refb: object = None
     source_index: Optional[np.ndarray] = None
+    stats: Optional[tuple] = None   # (min_start, max_end, max_span): avo_batch_stats, optional
+
+    def with_stats(self):
+        """Fills `stats` (what a packer knows for free) so that the library can skip its own
+        statistics pass; the discovery kernel still verifies the bounds and the sort order."""
+        if self.n_reads == 0:
+            self.stats = None
+        elif self.on_device:
+            m = self.meta[:self.n_reads * 32].view(__import__("torch").int32).view(-1, 8)
+            st, en = m[:, 0], m[:, 1]
+            self.stats = (int(st.min()), int(en.max()), int((en - st).max()))
+        else:
+            st, en = self.meta["start"].astype(np.int64), self.meta["end"].astype(np.int64)
+            self.stats = (int(st.min()), int(en.max()), int((en - st).max()))
+        return self
 
     @property
     def on_device(self):
@@ -73,6 +88,9 @@ class ReadBatch:
         s.n_reads, s.n_bases, s.n_ops, s.n_refb = self.n_reads, self.n_bases, self.n_ops, self.n_refb
         s.contig_id = self.contig_id
         s.mem = L.MEM_DEVICE if self.on_device else L.MEM_HOST
+        if self.stats is not None:
+            s.stats_min_start, s.stats_max_end, s.stats_max_span = self.stats
+            s.stats_valid = 1
         for name, _ in READ_COLUMNS:
             setattr(s, name, _ptr(getattr(self, name)))
         return s
@@ -95,6 +113,7 @@ class ReadBatch:
             if pinned:
                 t = t.pin_memory()
             setattr(out, name, t.to(device, non_blocking=pinned, **kw))
+        out.stats = self.stats
         return out
 
     def to_host(self):
@@ -103,6 +122,7 @@ class ReadBatch:
         out = ReadBatch(self.n_reads, self.n_bases, self.n_ops, self.n_refb, self.contig_id)
         for name, dt in READ_COLUMNS:
             setattr(out, name, _from_torch(getattr(self, name), dt))
+        out.stats = self.stats
         return out
 
     def slice(self, lo, hi):
@@ -125,7 +145,7 @@ class ReadBatch:
         out.quals = np.ascontiguousarray(self.quals[b0:b1])
         out.ops = np.ascontiguousarray(self.ops[o0:o1])
         out.refb = np.ascontiguousarray(self.refb[f0:f1])
-        return out
+        return out.with_stats() if self.stats is not None else out
 
 
 _TORCH_VIEW = {np.dtype(np.uint32): np.int32, np.dtype(np.uint16): np.int16}
@@ -316,7 +336,7 @@ def pack_reads(records: Sequence[AlignmentRecord], contig_id=0, keep=None, sort=
     b.ops = arrs["ops"][:max(out.n_ops, 1)]
     b.refb = arrs["refb"][:max(out.n_refb, 1)]
     b.source_index = np.array([idx[j] for j in arrs["source_index"][:out.n_reads]], np.int64)
-    return b
+    return b.with_stats()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -361,7 +381,7 @@ def synth_host(p, first=0, n=None, contig_id=0) -> ReadBatch:
     b = ReadBatch(n, nb, no.value, nf.value, contig_id)
     for k, a in arrs.items():
         setattr(b, k, a)
-    return b
+    return b.with_stats()
 
 
 def synth_device(p, first=0, n=None, contig_id=0, device="cuda:0") -> ReadBatch:
@@ -392,4 +412,4 @@ def synth_device(p, first=0, n=None, contig_id=0, device="cuda:0") -> ReadBatch:
     b = ReadBatch(n, nb, no.value, nf.value, contig_id)
     for k, a in arrs.items():
         setattr(b, k, a)
-    return b
+    return b.with_stats()

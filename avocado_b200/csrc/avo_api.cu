@@ -47,6 +47,7 @@ struct avo_ctx {
   int lut_minp = -1, lut_maxp = -1, lut_maxq = -1, lut_maxmq = -1;
   avo_timing timing{};
   cudaEvent_t ev[8] = {};
+  int64_t indel_guess = 0;         // indel candidates seen by the previous discovery (sizes the table)
   BatchStats* h_stats = nullptr;   // pinned
   int32_t* h_small = nullptr;      // pinned scratch (16 ints)
 };
@@ -147,6 +148,15 @@ float ev_ms(avo_ctx* ctx, int a, int b) {
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.f; }
   return ms;
+}
+
+// The caller's bounds (avo_batch_stats), to be verified on the device by the discovery kernel.
+bool stats_from_hints(const avo_read_batch* r, BatchStats* h) {
+  if (!r->stats.valid || r->n_reads == 0) return false;
+  if (r->stats.max_end < r->stats.min_start || r->stats.max_span < 0) return false;
+  h->min_start = r->stats.min_start; h->max_end = r->stats.max_end; h->max_span = r->stats.max_span;
+  h->unsorted = 0;
+  return true;
 }
 
 // batch statistics + sortedness (one small D2H + sync)
@@ -308,9 +318,11 @@ int check_params(avo_ctx* ctx, const avo_params* p) {
   return AVO_OK;
 }
 
-// BiallelicGenotyper.call against a device-resident site table.
+// BiallelicGenotyper.call against a device-resident site table.  `fresh` = the table was just
+// produced by discover_internal on the same batch: it is sorted and single-contig by construction
+// and the read index in SL_RIDX is current.
 int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const DevSites& T,
-                  const avo_cnv* cnv, const avo_params* p, avo_site_results* out) {
+                  const avo_cnv* cnv, const avo_params* p, bool fresh, avo_site_results* out) {
   if (T.n == 0)
     return fail(ctx, AVO_E_EMPTY_SITES,
                 "empty variant set: the reference throws here (TreeRegionJoin.scala:77)");
@@ -370,12 +382,17 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
   int32_t* small = (int32_t*)d_small;   // [0] unsorted, [1..2] contig range, [4..5] s_range
   CK(launch_site_setup(T.n, T.contig, T.start, T.ref_len, (int32_t*)d_end, (int32_t*)d_pme, small,
                        d_temp, tb, ctx->stream));
-  CK(launch_contig_range(T.n, T.contig, R.contig, small + 1, ctx->stream));
-  ctx->timing.n_launches += 3;
-  CK(cudaMemcpyAsync(ctx->h_small, small, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (ctx->h_small[0]) return fail(ctx, AVO_E_UNSORTED, "sites are not sorted by (contig, start, end)");
-  S.c_lo = ctx->h_small[1]; S.c_hi = ctx->h_small[2];
+  ctx->timing.n_launches += 2;
+  if (fresh) {
+    S.c_lo = 0; S.c_hi = T.n;
+  } else {
+    CK(launch_contig_range(T.n, T.contig, R.contig, small + 1, ctx->stream));
+    ctx->timing.n_launches += 1;
+    CK(cudaMemcpyAsync(ctx->h_small, small, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_small[0]) return fail(ctx, AVO_E_UNSORTED, "sites are not sorted by (contig, start, end)");
+    S.c_lo = ctx->h_small[1]; S.c_hi = ctx->h_small[2];
+  }
   S.end = (const int32_t*)d_end; S.pme = (const int32_t*)d_pme;
   int mp = 1;                                                  // TreeRegionJoin.scala:66-72
   while (!(2 * (int64_t)mp >= (int64_t)S.n)) mp *= 2;
@@ -386,7 +403,10 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
   void *d_ridx, *d_sidx;
   CKS(get_buf(ctx, SL_RIDX, (size_t)(nb + 1) * 4, &d_ridx));
   CKS(get_buf(ctx, SL_SIDX, (size_t)(nb + 1) * 4, &d_sidx));
-  CK(launch_build_index(R, S, hs, (int32_t*)d_ridx, (int32_t*)d_sidx, small + 4, ctx->stream));
+  if (fresh)
+    CK(launch_build_site_index(S, hs, (int32_t*)d_sidx, small + 4, ctx->stream));
+  else
+    CK(launch_build_index(R, S, hs, (int32_t*)d_ridx, (int32_t*)d_sidx, small + 4, ctx->stream));
   ctx->timing.n_launches += 1;
   DIndex X{hs.min_start, nb, (const int32_t*)d_ridx, (const int32_t*)d_sidx, small + 4};
 
@@ -408,12 +428,15 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
   return AVO_OK;
 }
 
-// DiscoverVariants on a device batch; leaves the sorted site table in ctx buffers.
-int discover_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const avo_params* p,
-                      DevSites* T) {
+// DiscoverVariants on a device batch; leaves the sorted site table in ctx buffers.  One host
+// round trip: the tile kernel and the indel grouping run back to back on device-side counts, then
+// the counters come back together.  verify: hs holds the caller's bounds, checked by the kernel.
+int discover_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, bool verify,
+                      const avo_params* p, DevSites* T) {
   void *d_small, *d_ridx;
   CKS(get_buf(ctx, SL_SMALL, 64, &d_small));
-  int32_t* small = (int32_t*)d_small;   // [8] tile counter, [10] out.n, [11] indel n
+  // [8] tile counter, [9] flags, [10] out.n, [11] indel n, [12] indel survivors' nibbles, [13] indel survivors
+  int32_t* small = (int32_t*)d_small;
   const int32_t nb = index_bins(hs);
   CKS(get_buf(ctx, SL_RIDX, (size_t)(nb + 1) * 4, &d_ridx));
   DSites none{};
@@ -423,11 +446,12 @@ int discover_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const
 
   int64_t ucap = std::max<int64_t>(1 << 16, R.n / 8);
   int64_t lcap = std::max<int64_t>(1 << 16, R.n / 8);
+  int64_t tguess = std::max<int64_t>(1 << 15, ctx->indel_guess + ctx->indel_guess / 4);
   DDiscoverOut U{};
   DIndelList Lst{};
-  int32_t n_out = 0, n_indel = 0;
+  int32_t n_out = 0, n_indel = 0, nib_indel = 0, n_surv = 0;
   for (int attempt = 0;; ++attempt) {
-    if (attempt > 3) return fail(ctx, AVO_E_NOMEM, "discovery buffers kept overflowing");
+    if (attempt > 4) return fail(ctx, AVO_E_NOMEM, "discovery buffers kept overflowing");
     void* q;
     U.capacity = (int32_t)std::min<int64_t>(ucap, INT32_MAX);
     CKS(get_buf(ctx, SL_U_START, (size_t)ucap * 4, &q)); U.start = (int32_t*)q;
@@ -443,42 +467,40 @@ int discover_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const
     CKS(get_buf(ctx, SL_L_SRC, (size_t)lcap * 4, &q)); Lst.src = (uint32_t*)q;
     CKS(get_buf(ctx, SL_L_HASH, (size_t)lcap * 4, &q)); Lst.hash = (uint32_t*)q;
     Lst.n = small + 11;
-    CK(cudaMemsetAsync(small + 8, 0, 4 * sizeof(int32_t), ctx->stream));
-
-    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    int nl = 0;
-    CK(launch_discover_tiles(R, p->min_phred_discover, p->min_obs_discover, X, hs, U, Lst, small + 8,
-                             ctx->num_sms, ctx->stream, &nl));
-    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-    ctx->timing.n_launches += nl;
-    ctx->timing.n_tile_launches += nl;
-    CK(cudaMemcpyAsync(ctx->h_small, small + 10, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    n_out = ctx->h_small[0];
-    n_indel = ctx->h_small[1];
-    // the indel pass can add at most n_indel survivors
-    const int64_t need_u = (int64_t)n_out + (int64_t)n_indel;
-    if (need_u > ucap || n_indel > lcap) {
-      ucap = std::max(ucap, need_u + need_u / 8 + 1024);
-      lcap = std::max<int64_t>(lcap, (int64_t)n_indel + n_indel / 8 + 1024);
-      continue;
-    }
-    break;
-  }
-
-  if (n_indel > 0) {
     uint32_t tsize = 1024;
-    while (tsize < 2u * (uint32_t)n_indel) tsize <<= 1;
+    while ((int64_t)tsize < 2 * tguess) tsize <<= 1;
     void *d_table, *d_tcount;
     CKS(get_buf(ctx, SL_TABLE, (size_t)tsize * 8, &d_table));
     CKS(get_buf(ctx, SL_TCOUNT, (size_t)tsize * 4, &d_tcount));
+    CK(cudaMemsetAsync(small + 8, 0, 6 * sizeof(int32_t), ctx->stream));
+
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     int nl = 0;
-    CK(launch_indel_group(R, Lst, n_indel, (unsigned long long*)d_table, (int32_t*)d_tcount, tsize,
-                          p->min_obs_discover, U, ctx->stream, &nl));
+    CK(launch_discover_tiles(R, p->min_phred_discover, p->min_obs_discover, X, hs, verify ? 1 : 0, U, Lst,
+                             small + 8, small + 9, ctx->num_sms, ctx->stream, &nl));
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     ctx->timing.n_launches += nl;
-    CK(cudaMemcpyAsync(ctx->h_small, small + 10, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->timing.n_tile_launches += nl;
+    nl = 0;
+    CK(launch_indel_group(R, Lst, (unsigned long long*)d_table, (int32_t*)d_tcount, tsize,
+                          p->min_obs_discover, U, small + 12, small + 13, small + 9, ctx->num_sms,
+                          ctx->stream, &nl));
+    ctx->timing.n_launches += nl;
+    CK(cudaMemcpyAsync(ctx->h_small, small + 9, 5 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    n_out = ctx->h_small[0];
+    const int32_t flags = ctx->h_small[0];
+    n_out = ctx->h_small[1]; n_indel = ctx->h_small[2]; nib_indel = ctx->h_small[3]; n_surv = ctx->h_small[4];
+    if (flags & DISC_FLAG_UNSORTED) return fail(ctx, AVO_E_UNSORTED, "reads are not sorted by start");
+    if (flags & DISC_FLAG_BAD_STATS)
+      return fail(ctx, AVO_E_INVALID, "reads->stats does not bound the batch (max_end / max_span too small)");
+    ctx->indel_guess = n_indel;
+    bool again = false;
+    if (n_indel > lcap) { lcap = (int64_t)n_indel + n_indel / 8 + 1024; again = true; }
+    if (flags & DISC_FLAG_TABLE_FULL) { tguess = std::max<int64_t>(2 * tguess, n_indel); again = true; }
+    // without the table the survivors of the indel pass are unknown: at most n_indel
+    const int64_t need_u = (int64_t)n_out + ((flags & DISC_FLAG_TABLE_FULL) ? (int64_t)n_indel : 0);
+    if (need_u > ucap) { ucap = need_u + need_u / 8 + 1024; again = true; }
+    if (!again) break;
   }
 
   // sort + materialise
@@ -486,6 +508,7 @@ int discover_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const
   T->n_nibbles = 0;
   T->contig = nullptr;
   if (n_out == 0) return AVO_OK;
+  const uint32_t total = 2u * (uint32_t)(n_out - n_surv) + (uint32_t)nib_indel;   // SNVs: 2 nibbles each
   void *ka, *kb, *va, *vb, *foot, *aoff, *temp;
   CKS(get_buf(ctx, SL_KEYS_A, (size_t)n_out * 8, &ka));
   CKS(get_buf(ctx, SL_KEYS_B, (size_t)n_out * 8, &kb));
@@ -496,15 +519,9 @@ int discover_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const
   const size_t tb = assemble_temp_bytes(n_out);
   CKS(get_buf(ctx, SL_TEMP, tb, &temp));
   int nl = 0;
-  CK(launch_assemble_sites(R, Lst, U, n_out, (unsigned long long*)ka, (unsigned long long*)kb,
-                           (int32_t*)va, (int32_t*)vb, (uint32_t*)foot, (uint32_t*)aoff, temp, tb,
-                           ctx->stream, &nl));
-  // total nibbles = aoff[n-1] + foot[n-1]
-  uint32_t* h2 = (uint32_t*)ctx->h_small;
-  CK(cudaMemcpyAsync(h2, (uint32_t*)aoff + (n_out - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(h2 + 1, (uint32_t*)foot + (n_out - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  const uint32_t total = h2[0] + h2[1];
+  CK(launch_assemble_sites(R, Lst, U, n_out, hs.min_start, hs.max_end, (unsigned long long*)ka,
+                           (unsigned long long*)kb, (int32_t*)va, (int32_t*)vb, (uint32_t*)foot,
+                           (uint32_t*)aoff, temp, tb, ctx->stream, &nl));
   void *o_start, *o_ref, *o_alt, *o_aoff, *o_all, *o_cnt;
   CKS(get_buf(ctx, SL_S_START, (size_t)n_out * 4, &o_start));
   CKS(get_buf(ctx, SL_S_REFLEN, (size_t)n_out * 4, &o_ref));
@@ -643,9 +660,10 @@ int avo_discover(avo_ctx* ctx, const avo_read_batch* reads, const avo_params* pa
   CKS(upload_reads(ctx, reads, &R));
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   BatchStats hs;
-  CKS(batch_stats(ctx, R, &hs));
+  const bool hinted = stats_from_hints(reads, &hs);
+  if (!hinted) CKS(batch_stats(ctx, R, &hs));
   DevSites T;
-  CKS(discover_internal(ctx, R, hs, params, &T));
+  CKS(discover_internal(ctx, R, hs, hinted, params, &T));
   CK(cudaEventRecord(ctx->ev[6], ctx->stream));
   const int rc = export_sites(ctx, T, out);
   CKS(finish_call(ctx, true, false));
@@ -681,7 +699,7 @@ int avo_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_sites* sites, 
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   BatchStats hs;
   CKS(batch_stats(ctx, R, &hs));
-  CKS(call_internal(ctx, R, hs, T, cnv, params, out));
+  CKS(call_internal(ctx, R, hs, T, cnv, params, false, out));
   CKS(finish_call(ctx, false, true));
   return AVO_OK;
 }
@@ -697,9 +715,10 @@ int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_c
   CKS(upload_reads(ctx, reads, &R));
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   BatchStats hs;
-  CKS(batch_stats(ctx, R, &hs));
+  const bool hinted = stats_from_hints(reads, &hs);
+  if (!hinted) CKS(batch_stats(ctx, R, &hs));
   DevSites T;
-  CKS(discover_internal(ctx, R, hs, params, &T));
+  CKS(discover_internal(ctx, R, hs, hinted, params, &T));
   CK(cudaEventRecord(ctx->ev[6], ctx->stream));
   const int64_t cap = results->n_sites;
   results->n_sites = T.n;
@@ -712,7 +731,7 @@ int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_c
     return fail(ctx, AVO_E_EMPTY_SITES,
                 "no variants discovered: the reference throws here (TreeRegionJoin.scala:77)");
   }
-  CKS(call_internal(ctx, R, hs, T, cnv, params, results));
+  CKS(call_internal(ctx, R, hs, T, cnv, params, true, results));
   CKS(finish_call(ctx, true, true));
   return AVO_OK;
 }

@@ -189,8 +189,8 @@ __device__ __forceinline__ void disc_emit_snv(const DDiscoverOut& out, int32_t p
 
 __global__ void __launch_bounds__(DISC_THREADS, 4)
 k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep count > min_count */,
-                 int32_t n_tiles, int32_t max_span, DDiscoverOut out, DIndelList L,
-                 int32_t* __restrict__ tile_counter) {
+                 int32_t n_tiles, int32_t max_span, int32_t max_end, int32_t verify, DDiscoverOut out,
+                 DIndelList L, int32_t* __restrict__ tile_counter, int32_t* __restrict__ flags) {
   __shared__ DiscSmem sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int BPT = DISC_W / IDX_G;
@@ -208,6 +208,13 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
     // candidates of a read lie in [start, end): reads with start < whi and start > wlo - max_span
     const int32_t rLo = __ldg(X.ridx + idx_bin_floor(X, wlo - max_span));
     const int32_t rHi = __ldg(X.ridx + min((tile + 1) * BPT, X.nb));
+    // the records whose start lies in this window: every record is owned by exactly one tile as
+    // long as the index is monotone (checked here), so the checks below see every record once
+    const int32_t rOwn = verify ? __ldg(X.ridx + min(tile * BPT, X.nb)) : rHi;
+    if (verify && tid == 0) {
+      if (rOwn > rHi || (tile == 0 && rOwn != 0) || (tile == 0 && R.n > 0 && meta_start(R.meta, 0) < X.win0))
+        atomicOr(flags, DISC_FLAG_UNSORTED);
+    }
     if (rLo >= rHi) continue;
 
     // ---- the walk over the reads: one read per thread.  SNV candidates are counted per position
@@ -227,6 +234,10 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
     for (int32_t r = rLo + tid; r < rHi; r += DISC_THREADS) {
       const MetaA a = load_meta_a(R.meta, r);
       const MetaB m = load_meta_b(R.meta, r);
+      if (r >= rOwn) {    // verify: sort order and the caller's bounds (avo_batch_stats)
+        if (r > 0 && meta_start(R.meta, r - 1) > a.start) atomicOr(flags, DISC_FLAG_UNSORTED);
+        if (a.end > max_end || (int64_t)a.end - a.start > max_span) atomicOr(flags, DISC_FLAG_BAD_STATS);
+      }
       if ((int64_t)a.end <= wlo || m.n_ops == 0) continue;   // ends before the window / no operators
       const uint32_t w0 = __ldg(R.ops + a.op_off);
       const uint32_t w1 = (m.n_ops > 1) ? __ldg(R.ops + a.op_off + 1) : 0u;
@@ -386,9 +397,9 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
 }
 
 cudaError_t launch_discover_tiles(const DReads& R, int32_t thr, int32_t min_obs, const DIndex& X,
-                                  const BatchStats& hstats, const DDiscoverOut& out,
-                                  const DIndelList& indels, int32_t* d_tile_counter, int num_sms,
-                                  cudaStream_t s, int* n_launches) {
+                                  const BatchStats& hstats, int verify, const DDiscoverOut& out,
+                                  const DIndelList& indels, int32_t* d_tile_counter, int32_t* d_flags,
+                                  int num_sms, cudaStream_t s, int* n_launches) {
   cudaError_t e = cudaMemsetAsync(d_tile_counter, 0, sizeof(int32_t), s);
   if (e != cudaSuccess) return e;
   if (R.n == 0) return cudaSuccess;
@@ -399,8 +410,9 @@ cudaError_t launch_discover_tiles(const DReads& R, int32_t thr, int32_t min_obs,
   if (e != cudaSuccess) return e;
   const int grid = (int)min((int64_t)n_tiles, (int64_t)num_sms * max(1, blocks_per_sm));
   const int32_t min_count = min_obs < 0 ? 0 : min_obs;  // distinct == count > 0
-  k_discover_tiles<<<grid, DISC_THREADS, 0, s>>>(R, X, thr, min_count, n_tiles, hstats.max_span, out,
-                                                 indels, d_tile_counter);
+  k_discover_tiles<<<grid, DISC_THREADS, 0, s>>>(R, X, thr, min_count, n_tiles, hstats.max_span,
+                                                 hstats.max_end, verify, out, indels, d_tile_counter,
+                                                 d_flags);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }
@@ -420,30 +432,35 @@ __device__ __forceinline__ bool indel_equal(const DReads& R, const DIndelList& L
   return true;
 }
 
-__global__ void k_indel_count(DReads R, DIndelList L, int32_t n, unsigned long long* __restrict__ table,
-                              int32_t* __restrict__ tcount, uint32_t mask) {
-  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t h = L.hash[i];
-  uint32_t slot = (h * 0x85EBCA6Bu) & mask;
-  const unsigned long long mine = ((unsigned long long)h << 32) | (unsigned long long)(i + 1);
-  for (;;) {
-    unsigned long long w = table[slot];
-    if (w == 0ull) {
-      w = atomicCAS(&table[slot], 0ull, mine);
-      if (w == 0ull) { atomicAdd(&tcount[slot], 1); return; }
+__global__ void k_indel_count(DReads R, DIndelList L, unsigned long long* __restrict__ table,
+                              int32_t* __restrict__ tcount, uint32_t mask, int32_t* __restrict__ flags) {
+  const int32_t n = min(*L.n, L.capacity);
+  if ((uint32_t)n > (mask + 1) / 2) {          // the probe loops need free slots
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(flags, DISC_FLAG_TABLE_FULL);
+    return;
+  }
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t h = L.hash[i];
+    uint32_t slot = (h * 0x85EBCA6Bu) & mask;
+    const unsigned long long mine = ((unsigned long long)h << 32) | (unsigned long long)(i + 1);
+    for (;;) {
+      unsigned long long w = table[slot];
+      if (w == 0ull) {
+        w = atomicCAS(&table[slot], 0ull, mine);
+        if (w == 0ull) { atomicAdd(&tcount[slot], 1); break; }
+      }
+      if ((uint32_t)(w >> 32) == h && indel_equal(R, L, i, (int32_t)(w & 0xFFFFFFFFull) - 1)) {
+        atomicAdd(&tcount[slot], 1);
+        break;
+      }
+      slot = (slot + 1) & mask;
     }
-    if ((uint32_t)(w >> 32) == h && indel_equal(R, L, i, (int32_t)(w & 0xFFFFFFFFull) - 1)) {
-      atomicAdd(&tcount[slot], 1);
-      return;
-    }
-    slot = (slot + 1) & mask;
   }
 }
 
 __global__ void k_indel_emit(DIndelList L, const unsigned long long* __restrict__ table,
                              const int32_t* __restrict__ tcount, uint32_t tsize, int32_t min_count,
-                             DDiscoverOut out) {
+                             DDiscoverOut out, int32_t* __restrict__ nib, int32_t* __restrict__ nsurv) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= tsize) return;
   const unsigned long long w = table[i];
@@ -451,9 +468,11 @@ __global__ void k_indel_emit(DIndelList L, const unsigned long long* __restrict_
   const int32_t c = tcount[i];
   if (c <= min_count) return;
   const int32_t rec = (int32_t)(w & 0xFFFFFFFFull) - 1;
+  const uint32_t lens = L.lens[rec];
+  atomicAdd(nib, (int32_t)(((lens >> 16) + (lens & 0xFFFFu) + 1u) & ~1u));
+  atomicAdd(nsurv, 1);
   const int32_t slot = atomicAdd(out.n, 1);
   if (slot >= out.capacity) return;
-  const uint32_t lens = L.lens[rec];
   out.start[slot] = L.pos[rec];
   out.ref_len[slot] = (int32_t)(lens >> 16);
   out.alt_len[slot] = (int32_t)(lens & 0xFFFFu);
@@ -461,18 +480,17 @@ __global__ void k_indel_emit(DIndelList L, const unsigned long long* __restrict_
   out.src[slot] = (uint64_t)rec;
 }
 
-cudaError_t launch_indel_group(const DReads& R, const DIndelList& L, int32_t n_indel,
-                               unsigned long long* table, int32_t* tcount, uint32_t tsize,
-                               int32_t min_obs, const DDiscoverOut& out, cudaStream_t s,
-                               int* n_launches) {
-  if (n_indel == 0) return cudaSuccess;
+cudaError_t launch_indel_group(const DReads& R, const DIndelList& L, unsigned long long* table,
+                               int32_t* tcount, uint32_t tsize, int32_t min_obs,
+                               const DDiscoverOut& out, int32_t* d_nib, int32_t* d_nsurv,
+                               int32_t* d_flags, int num_sms, cudaStream_t s, int* n_launches) {
   cudaError_t e = cudaMemsetAsync(table, 0, sizeof(unsigned long long) * tsize, s);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(tcount, 0, sizeof(int32_t) * tsize, s);
   if (e != cudaSuccess) return e;
   const int32_t min_count = min_obs < 0 ? 0 : min_obs;
-  k_indel_count<<<(n_indel + 255) / 256, 256, 0, s>>>(R, L, n_indel, table, tcount, tsize - 1);
-  k_indel_emit<<<(tsize + 255) / 256, 256, 0, s>>>(L, table, tcount, tsize, min_count, out);
+  k_indel_count<<<num_sms * 4, 256, 0, s>>>(R, L, table, tcount, tsize - 1, d_flags);
+  k_indel_emit<<<(tsize + 255) / 256, 256, 0, s>>>(L, table, tcount, tsize, min_count, out, d_nib, d_nsurv);
   if (n_launches) *n_launches += 2;
   return cudaGetLastError();
 }
@@ -499,49 +517,52 @@ __device__ __forceinline__ uint32_t survivor_nib(const DReads& R, const DIndelLi
   return nib_at(R.bases4, L.src[rec] + (uint32_t)(t - 2));
 }
 
-__global__ void k_survivor_keys(DDiscoverOut U, int32_t n, unsigned long long* __restrict__ keys,
-                                int32_t* __restrict__ vals) {
+__global__ void k_survivor_keys(DDiscoverOut U, int32_t n, int32_t min_start,
+                                unsigned long long* __restrict__ keys, int32_t* __restrict__ vals) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  // (start, ref_len, alt_len); start is biased so that negative positions sort first
-  keys[i] = ((unsigned long long)((uint32_t)U.start[i] ^ 0x80000000u) << 32) |
-            ((unsigned long long)(uint32_t)min(U.ref_len[i], 0xFFFF) << 16) |
-            (unsigned long long)(uint32_t)min(U.alt_len[i], 0xFFFF);
+  keys[i] = (unsigned long long)(uint32_t)(U.start[i] - min_start);   // candidates lie at or after min_start
   vals[i] = i;
 }
 
-// order ties of (start, ref_len, alt_len) by allele content so that the output is deterministic;
-// also emits the nibble footprint (even-aligned) of every sorted site
+// (ref_len, alt_len, allele content) order of two survivors that share a start
+__device__ int survivor_cmp(const DReads& R, const DIndelList& L, const DDiscoverOut& U, int32_t x, int32_t y) {
+  const int rx = U.ref_len[x], ry = U.ref_len[y];
+  if (rx != ry) return rx < ry ? -1 : 1;
+  const int ax = U.alt_len[x], ay = U.alt_len[y];
+  if (ax != ay) return ax < ay ? -1 : 1;
+  for (int t = 0; t < rx + ax; ++t) {
+    const uint32_t p = survivor_nib(R, L, U, x, t), q = survivor_nib(R, L, U, y, t);
+    if (p != q) return p < q ? -1 : 1;
+  }
+  return 0;
+}
+
+// The radix sort orders by start only; the (tiny) runs of survivors that share a start are put in
+// (ref_len, alt_len, allele content) order here, so that the table is sorted the way Forest sorts
+// its keys and is deterministic.  Also emits the nibble footprint (even-aligned) of every sorted site.
 __global__ void k_survivor_ties(DReads R, DIndelList L, DDiscoverOut U, int32_t n,
                                 const unsigned long long* __restrict__ keys,
                                 int32_t* __restrict__ vals, uint32_t* __restrict__ foot) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  {
-    const int32_t e = vals[i];
-    foot[i] = (uint32_t)((U.ref_len[e] + U.alt_len[e] + 1) & ~1);
-  }
   if (i > 0 && keys[i - 1] == keys[i]) return;   // not a run head
   int32_t j = i + 1;
   while (j < n && keys[j] == keys[i]) ++j;
-  if (j - i < 2) return;
-  // insertion sort of vals[i..j) by content (runs are tiny: alleles sharing position and lengths)
-  for (int32_t a = i + 1; a < j; ++a) {
+  for (int32_t a = i + 1; a < j; ++a) {          // insertion sort of vals[i..j)
     const int32_t va = vals[a];
     int32_t b = a - 1;
     while (b >= i) {
       const int32_t vb = vals[b];
-      const int len = U.ref_len[va] + U.alt_len[va];
-      int cmp = 0;
-      for (int t = 0; t < len && cmp == 0; ++t) {
-        const uint32_t x = survivor_nib(R, L, U, vb, t), y = survivor_nib(R, L, U, va, t);
-        cmp = (x > y) - (x < y);
-      }
-      if (cmp <= 0) break;
+      if (survivor_cmp(R, L, U, vb, va) <= 0) break;
       vals[b + 1] = vb;
       --b;
     }
     vals[b + 1] = va;
+  }
+  for (int32_t a = i; a < j; ++a) {
+    const int32_t e = vals[a];
+    foot[a] = (uint32_t)((U.ref_len[e] + U.alt_len[e] + 1) & ~1);
   }
 }
 
@@ -582,14 +603,17 @@ size_t assemble_temp_bytes(int32_t n) {
 // Sorts the n survivors and writes the site table.  keys_a/keys_b, vals_a/vals_b, foot, aoff are
 // scratch arrays of n (aoff: n) entries.  *d_total receives the nibble total (device scalar).
 cudaError_t launch_assemble_sites(const DReads& R, const DIndelList& L, const DDiscoverOut& U,
-                                  int32_t n, unsigned long long* keys_a, unsigned long long* keys_b,
+                                  int32_t n, int32_t min_start, int32_t max_end,
+                                  unsigned long long* keys_a, unsigned long long* keys_b,
                                   int32_t* vals_a, int32_t* vals_b, uint32_t* foot, uint32_t* aoff,
                                   void* d_temp, size_t temp_bytes, cudaStream_t s, int* n_launches) {
   if (n == 0) return cudaSuccess;
   const int g = (n + 255) / 256;
-  k_survivor_keys<<<g, 256, 0, s>>>(U, n, keys_a, vals_a);
+  k_survivor_keys<<<g, 256, 0, s>>>(U, n, min_start, keys_a, vals_a);
+  int bits = 1;
+  while (bits < 32 && (((int64_t)max_end - (int64_t)min_start) >> bits) != 0) ++bits;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, keys_a, keys_b, vals_a, vals_b,
-                                                  n, 0, 64, s);
+                                                  n, 0, bits, s);
   if (e != cudaSuccess) return e;
   k_survivor_ties<<<g, 256, 0, s>>>(R, L, U, n, keys_b, vals_b, foot);
   e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, foot, aoff, n, s);

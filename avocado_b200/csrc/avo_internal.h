@@ -104,6 +104,9 @@ cudaError_t launch_lnfact_table(const double* lnk, double* lnfact, int32_t n, cu
 int32_t index_bins(const BatchStats& hstats);
 cudaError_t launch_build_index(const DReads& R, const DSites& S, const BatchStats& hstats,
                                int32_t* ridx, int32_t* sidx, int32_t* s_range, cudaStream_t s);
+// sites only (the read index of the same batch already exists)
+cudaError_t launch_build_site_index(const DSites& S, const BatchStats& hstats, int32_t* sidx,
+                                    int32_t* s_range, cudaStream_t s);
 
 cudaError_t launch_call_tiles(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
                               const DResults& out, const DIndex& X, const BatchStats& hstats,
@@ -131,18 +134,26 @@ struct DIndelList {
   uint32_t* hash;
 };
 
+// d_flags: DISC_FLAG_* bits set by the kernels
+enum : int32_t { DISC_FLAG_UNSORTED = 1, DISC_FLAG_BAD_STATS = 2, DISC_FLAG_TABLE_FULL = 4 };
+// verify != 0: every record is checked against hstats and the sort order while it is walked
 cudaError_t launch_discover_tiles(const DReads& R, int32_t thr, int32_t min_obs /* <0: distinct */,
-                                  const DIndex& X, const BatchStats& hstats, const DDiscoverOut& out,
-                                  const DIndelList& indels, int32_t* d_tile_counter, int num_sms,
+                                  const DIndex& X, const BatchStats& hstats, int verify,
+                                  const DDiscoverOut& out, const DIndelList& indels,
+                                  int32_t* d_tile_counter, int32_t* d_flags, int num_sms,
                                   cudaStream_t s, int* n_launches);
 
-cudaError_t launch_indel_group(const DReads& R, const DIndelList& L, int32_t n_indel,
-                               unsigned long long* table, int32_t* tcount, uint32_t tsize,
-                               int32_t min_obs, const DDiscoverOut& out, cudaStream_t s,
-                               int* n_launches);
+// groups the *L.n (device counter) indel candidates; survivors are appended to `out`, their
+// allele-nibble footprints added to *d_nib, their number to *d_nsurv.  Sets DISC_FLAG_TABLE_FULL
+// (and does nothing) when the table is too small for *L.n.
+cudaError_t launch_indel_group(const DReads& R, const DIndelList& L, unsigned long long* table,
+                               int32_t* tcount, uint32_t tsize, int32_t min_obs,
+                               const DDiscoverOut& out, int32_t* d_nib, int32_t* d_nsurv,
+                               int32_t* d_flags, int num_sms, cudaStream_t s, int* n_launches);
 size_t assemble_temp_bytes(int32_t n);
 cudaError_t launch_assemble_sites(const DReads& R, const DIndelList& L, const DDiscoverOut& U,
-                                  int32_t n, unsigned long long* keys_a, unsigned long long* keys_b,
+                                  int32_t n, int32_t min_start, int32_t max_end,
+                                  unsigned long long* keys_a, unsigned long long* keys_b,
                                   int32_t* vals_a, int32_t* vals_b, uint32_t* foot, uint32_t* aoff,
                                   void* d_temp, size_t temp_bytes, cudaStream_t s, int* n_launches);
 cudaError_t launch_fill_sites(const DReads& R, const DIndelList& L, const DDiscoverOut& U, int32_t n,

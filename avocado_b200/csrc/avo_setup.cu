@@ -133,7 +133,7 @@ __global__ void k_build_index(DReads R, DSites S, int32_t win0, int32_t nb, int3
   if (k <= nb) {
     const int64_t key64 = (int64_t)win0 + (int64_t)k * IDX_G;
     const int32_t key = (int32_t)min(key64, (int64_t)INT32_MAX);
-    ridx[k] = (k == nb) ? (int32_t)R.n : (int32_t)lower_bound_reads(R.meta, 0, R.n, key);
+    if (ridx) ridx[k] = (k == nb) ? (int32_t)R.n : (int32_t)lower_bound_reads(R.meta, 0, R.n, key);
     if (S.n > 0) sidx[k] = lower_bound_i32(S.start, S.c_lo, S.c_hi, key);
   }
   if (k == 0 && S.n > 0) {
@@ -153,6 +153,15 @@ cudaError_t launch_build_index(const DReads& R, const DSites& S, const BatchStat
                                int32_t* sidx, int32_t* s_range, cudaStream_t s) {
   const int32_t nb = index_bins(h);
   k_build_index<<<(nb + 1 + 255) / 256, 256, 0, s>>>(R, S, h.min_start, nb, h.max_end, ridx, sidx,
+                                                      s_range);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_build_site_index(const DSites& S, const BatchStats& h, int32_t* sidx,
+                                    int32_t* s_range, cudaStream_t s) {
+  const int32_t nb = index_bins(h);
+  DReads none{};
+  k_build_index<<<(nb + 1 + 255) / 256, 256, 0, s>>>(none, S, h.min_start, nb, h.max_end, nullptr, sidx,
                                                       s_range);
   return cudaGetLastError();
 }

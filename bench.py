@@ -360,6 +360,7 @@ class ReadBatchPinned:
             a = h.numpy()
             setattr(b, name, a.view(dt) if a.dtype != dt else a)
         torch.cuda.synchronize()
+        b.stats = dev.stats
         self.batch = b
 
 

@@ -94,6 +94,17 @@ typedef struct {
   uint32_t l_seq;    /* number of bases */
 } avo_read_meta;
 
+/* Bounds a packer knows for free.  Optional (valid = 0: the library computes them with one extra
+ * pass over the records).  When given they are only bounds, and avo_discover /
+ * avo_discover_and_call check them, together with the sort order, against every record on the
+ * device while discovering (AVO_E_INVALID / AVO_E_UNSORTED if wrong); avo_call always recomputes. */
+typedef struct {
+  int32_t min_start; /* <= every start */
+  int32_t max_end;   /* >= every end */
+  int32_t max_span;  /* >= every end - start */
+  int32_t valid;
+} avo_batch_stats;
+
 /* One batch = reads of ONE contig, sorted by start (ties in any order; the order of the batch is
  * the canonical summation order). */
 typedef struct {
@@ -103,6 +114,7 @@ typedef struct {
   int64_t n_refb;  /* refb bytes (< 2^31) */
   int32_t contig_id; /* rank of this contig in the site table's contig order */
   int32_t mem;
+  avo_batch_stats stats;
   const avo_read_meta* meta; /* [n_reads] */
   const uint8_t* bases4;     /* [(n_bases+1)/2] */
   const uint8_t* quals;      /* [n_bases] */

@@ -149,7 +149,8 @@ def test_synthetic_batch_matches_oracle(oracle, ctx, seed, n_reads, contig_len, 
     keys = [("ctg", s, r, a) for (s, e, r, a) in got]
     st = compare_call(keys, cols, want)
     assert st["sites"] > 0
-    # fused entry point gives the same rows
+    # fused entry point gives the same rows (with and without the packer's bounds)
+    host.stats = None if seed % 2 else host.stats
     sites2, cols2 = ctx.discover_and_call_packed(host, phred=phred, min_obs=min_obs)
     assert np.array_equal(sites2.start, sites.start)
     for k in cols:
@@ -167,7 +168,29 @@ def test_empty_sites_and_unsorted_reads_are_errors(ctx):
     assert e.value.status == L.AVO_E_EMPTY_SITES
     p = B.synth_params(n_reads_total=1000, contig_len=5000)
     b = B.synth_host(p)
+    good = b.stats
+    b.stats = (good[0], good[1] - 1, good[2])       # the caller's bounds are checked on the device
+    with pytest.raises(L.AvocadoError) as e:
+        ctx.discover_packed(b)
+    assert e.value.status == L.AVO_E_INVALID
+    b.stats = (good[0], good[1], good[2] - 1)
+    with pytest.raises(L.AvocadoError) as e:
+        ctx.discover_packed(b)
+    assert e.value.status == L.AVO_E_INVALID
+    b.stats = (good[0] - 100, good[1] + 100, good[2] + 100)   # loose bounds are fine
+    want = ctx.discover_packed(b)
+    b.stats = None                                   # no bounds: the library computes them
+    got = ctx.discover_packed(b)
+    assert np.array_equal(want.start, got.start) and np.array_equal(want.count, got.count)
     b.meta["start"] = np.ascontiguousarray(b.meta["start"][::-1])
+    for stats in (None, good):
+        b.stats = stats
+        with pytest.raises(L.AvocadoError) as e:
+            ctx.discover_packed(b)
+        assert e.value.status == L.AVO_E_UNSORTED
+    b.meta["start"] = np.ascontiguousarray(b.meta["start"][::-1])
+    b.meta["start"][500], b.meta["start"][501] = b.meta["start"][501] + 1, b.meta["start"][500]
+    b.stats = good                                   # one swapped pair in the middle
     with pytest.raises(L.AvocadoError) as e:
         ctx.discover_packed(b)
     assert e.value.status == L.AVO_E_UNSORTED

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(L.EXPORTED_SYMBOLS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert C.sizeof(L.ReadBatchStruct) == 4 * 8 + 2 * 4 + 5 * 8
+    assert C.sizeof(L.ReadBatchStruct) == 4 * 8 + 2 * 4 + 4 * 4 + 5 * 8
 
 
 @pytest.mark.parametrize("name", FIXTURES)

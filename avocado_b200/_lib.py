@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libavocado_b200.so")
+# AVO_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("AVO_LIB") or os.path.join(_HERE, "libavocado_b200.so")
 
 AVO_OK = 0
 AVO_E_INVALID = -1

@@ -299,10 +299,20 @@ int export_results(avo_ctx* ctx, const DResults& D, int64_t n, int ns, avo_site_
       {o->qual, D.qual, (size_t)n * 8}, {o->gq, D.gq, (size_t)n * 4}, {o->sb, D.sb, (size_t)n * 16},
       {o->fisher, D.fisher, (size_t)n * 4}, {o->rms_mapq, D.rms_mapq, (size_t)n * 4},
       {o->gl, D.gl, (size_t)n * ns * 8}, {o->nonref_gl, D.nonref_gl, (size_t)n * ns * 8}};
+  if (kind == cudaMemcpyDeviceToDevice) {
+    ColumnCopies cc{};
+    for (auto& x : c) {
+      if (x.bytes == 0) continue;
+      cc.dst[cc.n] = x.dst; cc.src[cc.n] = x.src; cc.bytes[cc.n] = x.bytes; ++cc.n;
+    }
+    CK(launch_copy_columns(cc, ctx->stream));
+    ctx->timing.n_launches += 1;
+    return AVO_OK;
+  }
   for (auto& x : c) {
     if (x.bytes == 0) continue;
     CK(cudaMemcpyAsync(x.dst, x.src, x.bytes, kind, ctx->stream));
-    if (kind == cudaMemcpyDeviceToHost) ctx->timing.d2h_bytes += (int64_t)x.bytes;
+    ctx->timing.d2h_bytes += (int64_t)x.bytes;
   }
   return AVO_OK;
 }
@@ -553,6 +563,16 @@ int export_sites(avo_ctx* ctx, const DevSites& T, avo_sites_out* o) {
     return fail(ctx, AVO_E_INVALID, "sites_out has NULL columns");
   const cudaMemcpyKind kind = (o->mem == AVO_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   const size_t n = (size_t)T.n;
+  if (kind == cudaMemcpyDeviceToDevice) {
+    ColumnCopies cc{};
+    auto add = [&](void* d, const void* s_, size_t b) { cc.dst[cc.n] = d; cc.src[cc.n] = s_; cc.bytes[cc.n] = b; ++cc.n; };
+    add(o->start, T.start, n * 4); add(o->ref_len, T.ref_len, n * 4); add(o->alt_len, T.alt_len, n * 4);
+    add(o->allele_off, T.allele_off, (n + 1) * 4); add(o->alleles4, T.alleles4, ((size_t)T.n_nibbles + 1) / 2);
+    if (o->count) add(o->count, T.count, n * 4);
+    CK(launch_copy_columns(cc, ctx->stream));
+    ctx->timing.n_launches += 1;
+    return AVO_OK;
+  }
   CK(cudaMemcpyAsync(o->start, T.start, n * 4, kind, ctx->stream));
   CK(cudaMemcpyAsync(o->ref_len, T.ref_len, n * 4, kind, ctx->stream));
   CK(cudaMemcpyAsync(o->alt_len, T.alt_len, n * 4, kind, ctx->stream));

@@ -21,7 +21,13 @@ namespace avo {
 
 constexpr int CALL_THREADS = 256;
 constexpr int CALL_WARPS = CALL_THREADS / 32;
-constexpr int CALL_W = 1024;        // window width in bases (one warp per window)
+#ifndef AVO_CALL_W
+#define AVO_CALL_W 1024
+#endif
+#ifndef AVO_CALL_MINB
+#define AVO_CALL_MINB 4
+#endif
+constexpr int CALL_W = AVO_CALL_W;  // window width in bases (one warp per window)
 constexpr int SCHUNK = 8;           // owned sites reduced at a time
 constexpr int MAX_LOCAL_SITES = 32; // per-read category cache
 constexpr int NSMAX = AVO_MAX_PLOIDY + 1;
@@ -486,7 +492,7 @@ __device__ __forceinline__ void phase_b_slot(const DCallParams& P, WarpSmem& ws,
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(CALL_THREADS, 4)
+__global__ void __launch_bounds__(CALL_THREADS, AVO_CALL_MINB)
 k_call_tiles(DReads R, DSites S, DCnv C, DCallParams P, DResults O, DIndex X, int32_t n_tiles,
              int32_t max_span, int32_t* __restrict__ tile_counter) {
   __shared__ WarpSmem smem[CALL_WARPS];

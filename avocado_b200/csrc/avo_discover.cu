@@ -19,8 +19,17 @@
 namespace avo {
 
 constexpr int DISC_THREADS = 256;
-constexpr int DISC_W = 2048;      // reference positions owned by one tile
-constexpr int DISC_HB = 8;        // hot positions histogrammed per pass-2 batch
+#ifndef AVO_DISC_W
+#define AVO_DISC_W 2048
+#endif
+#ifndef AVO_DISC_MINB
+#define AVO_DISC_MINB 6
+#endif
+constexpr int DISC_W = AVO_DISC_W;  // reference positions owned by one tile
+#ifndef AVO_DISC_HB
+#define AVO_DISC_HB 8
+#endif
+constexpr int DISC_HB = AVO_DISC_HB;        // hot positions histogrammed per pass-2 batch
 constexpr uint32_t NOT_HOT = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t mix32(uint32_t h, uint32_t v) {
@@ -187,7 +196,7 @@ __device__ __forceinline__ void disc_emit_snv(const DDiscoverOut& out, int32_t p
   }
 }
 
-__global__ void __launch_bounds__(DISC_THREADS, 4)
+__global__ void __launch_bounds__(DISC_THREADS, AVO_DISC_MINB)
 k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep count > min_count */,
                  int32_t n_tiles, int32_t max_span, int32_t max_end, int32_t verify, DDiscoverOut out,
                  DIndelList L, int32_t* __restrict__ tile_counter, int32_t* __restrict__ flags) {

@@ -92,6 +92,15 @@ struct BatchStats {
   int32_t unsorted;   // != 0 if start[] is not non-decreasing
 };
 
+// device -> device column copies done by one launch
+struct ColumnCopies {
+  int n;
+  void* dst[32];
+  const void* src[32];
+  size_t bytes[32];
+};
+cudaError_t launch_copy_columns(const ColumnCopies& cc, cudaStream_t s);
+
 // ---- launchers (each returns the cudaError_t of its launches) --------------------------------
 cudaError_t launch_batch_stats(const DReads& R, BatchStats* d_stats, cudaStream_t s);
 cudaError_t launch_site_setup(int32_t n, const int32_t* contig, const int32_t* start,

@@ -3,6 +3,8 @@
 // index that replaces per-tile binary searches, and the logFactorial table.
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
+
 #include "avo_device.cuh"
 
 namespace avo {
@@ -154,6 +156,34 @@ cudaError_t launch_build_index(const DReads& R, const DSites& S, const BatchStat
   const int32_t nb = index_bins(h);
   k_build_index<<<(nb + 1 + 255) / 256, 256, 0, s>>>(R, S, h.min_start, nb, h.max_end, ridx, sidx,
                                                       s_range);
+  return cudaGetLastError();
+}
+
+// ---- device -> device export of result columns: one launch instead of one copy per column ------
+__global__ void k_copy_columns(ColumnCopies cc) {
+  for (int c = blockIdx.y; c < cc.n; c += gridDim.y) {
+    const size_t bytes = cc.bytes[c];
+    const char* src = (const char*)cc.src[c];
+    char* dst = (char*)cc.dst[c];
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) {
+      const size_t n16 = bytes / 16;
+      for (size_t k = i; k < n16; k += stride)
+        reinterpret_cast<uint4*>(dst)[k] = reinterpret_cast<const uint4*>(src)[k];
+      for (size_t k = n16 * 16 + i; k < bytes; k += stride) dst[k] = src[k];
+    } else {
+      for (size_t k = i; k < bytes; k += stride) dst[k] = src[k];
+    }
+  }
+}
+
+cudaError_t launch_copy_columns(const ColumnCopies& cc, cudaStream_t s) {
+  if (cc.n == 0) return cudaSuccess;
+  size_t mx = 0;
+  for (int c = 0; c < cc.n; ++c) mx = cc.bytes[c] > mx ? cc.bytes[c] : mx;
+  const int gx = (int)std::min<size_t>(64, (mx / 16 + 255) / 256 + 1);
+  k_copy_columns<<<dim3(gx, cc.n), 256, 0, s>>>(cc);
   return cudaGetLastError();
 }
 

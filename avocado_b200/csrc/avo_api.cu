@@ -108,6 +108,16 @@ int stage_in(avo_ctx* ctx, int slot, const T* src, size_t count, int mem, const 
   return AVO_OK;
 }
 
+// Page-locked host memory is mapped into the device address space (UVA): returns the pointer the
+// kernels can dereference, or null when `p` is pageable / unknown to the runtime.
+template <typename T>
+const T* mapped_alias(const T* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+  return static_cast<const T*>(a.devicePointer);
+}
+
 int validate_reads(avo_ctx* ctx, const avo_read_batch* r) {
   if (!r) return fail(ctx, AVO_E_INVALID, "reads is NULL");
   if (r->n_reads < 0 || r->n_reads >= (int64_t)INT32_MAX)
@@ -123,13 +133,24 @@ int validate_reads(avo_ctx* ctx, const avo_read_batch* r) {
   return AVO_OK;
 }
 
-int upload_reads(avo_ctx* ctx, const avo_read_batch* r, DReads* R) {
+// sparse: the mode reads bases4 / quals only at variant sites and indels, so a page-locked host
+// batch keeps them where they are and the kernels fetch single sectors over PCIe
+int upload_reads(avo_ctx* ctx, const avo_read_batch* r, bool sparse, DReads* R) {
   const size_t n = (size_t)r->n_reads;
   R->n = r->n_reads;
   R->contig = r->contig_id;
   CKS(stage_in(ctx, SL_META, r->meta, n, r->mem, &R->meta));
   CKS(stage_in(ctx, SL_OPS, r->ops, (size_t)r->n_ops, r->mem, &R->ops));
   CKS(stage_in(ctx, SL_REFB, r->refb, (size_t)r->n_refb, r->mem, &R->refb));
+  if (sparse && r->mem == AVO_MEM_HOST && r->n_bases > 0) {
+    const uint8_t* b = mapped_alias(r->bases4);
+    const uint8_t* q = mapped_alias(r->quals);
+    if (b && q) {
+      R->bases4 = b; R->quals = q;
+      ctx->timing.payload_in_place = 1;
+      return AVO_OK;
+    }
+  }
   CKS(stage_in(ctx, SL_BASES, r->bases4, (size_t)(r->n_bases + 1) / 2, r->mem, &R->bases4));
   CKS(stage_in(ctx, SL_QUALS, r->quals, (size_t)r->n_bases, r->mem, &R->quals));
   return AVO_OK;
@@ -677,7 +698,7 @@ int avo_discover(avo_ctx* ctx, const avo_read_batch* reads, const avo_params* pa
   CKS(validate_reads(ctx, reads));
   if (!params) return fail(ctx, AVO_E_INVALID, "params is NULL");
   DReads R;
-  CKS(upload_reads(ctx, reads, &R));
+  CKS(upload_reads(ctx, reads, params->host_payload == 0, &R));
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   BatchStats hs;
   const bool hinted = stats_from_hints(reads, &hs);
@@ -704,7 +725,7 @@ int avo_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_sites* sites, 
   if (!sites->start || !sites->ref_len || !sites->alt_len || !sites->allele_off || !sites->alleles4)
     return fail(ctx, AVO_E_INVALID, "sites has NULL columns");
   DReads R;
-  CKS(upload_reads(ctx, reads, &R));
+  CKS(upload_reads(ctx, reads, params->host_payload == 0 && !params->score_all_sites, &R));
   DevSites T;
   T.n = (int32_t)sites->n;
   T.n_nibbles = (uint32_t)sites->n_allele_nibbles;
@@ -732,7 +753,7 @@ int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_c
   CKS(check_params(ctx, params));
   CKS(check_results(ctx, results));
   DReads R;
-  CKS(upload_reads(ctx, reads, &R));
+  CKS(upload_reads(ctx, reads, params->host_payload == 0 && !params->score_all_sites, &R));
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   BatchStats hs;
   const bool hinted = stats_from_hints(reads, &hs);

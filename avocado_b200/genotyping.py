@@ -91,9 +91,11 @@ class Context:
         return {k: getattr(t, k) for k, _ in L.TimingStruct._fields_}
 
     # ---- raw entry points over packed data ------------------------------------------------------
-    @staticmethod
-    def _params(ploidy=2, max_quality=93, max_mapq=93, phred=0, min_obs=None, score_all=False):
+    host_payload = 0    # avo_params.host_payload: 0 = pinned host payload read in place, 1 = copy
+
+    def _params(self, ploidy=2, max_quality=93, max_mapq=93, phred=0, min_obs=None, score_all=False):
         p = L.ParamsStruct()
+        p.host_payload = self.host_payload
         p.ploidy, p.score_all_sites = ploidy, int(bool(score_all))
         p.max_quality, p.max_mapq = max_quality, max_mapq
         p.min_phred_discover = phred

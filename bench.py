@@ -306,7 +306,14 @@ def main():
                "h2d_bytes_per_step": int(statistics.mean(t["h2d_bytes"] for t in t_h)) * world,
                "d2h_bytes_per_step": int(statistics.mean(t["d2h_bytes"] for t in t_h)) * world,
                "ms_per_step": float(t_dev.item()) / args.steps,
-               "ms_h2d": statistics.mean(t["ms_h2d"] for t in t_h)}
+               "ms_h2d": statistics.mean(t["ms_h2d"] for t in t_h),
+               "ms_discover": statistics.mean(t["ms_discover"] for t in t_h),
+               "ms_call": statistics.mean(t["ms_observe"] for t in t_h),
+               "ms_d2h": statistics.mean(t["ms_d2h"] for t in t_h),
+               "payload_in_place": bool(t_h[-1]["payload_in_place"]),
+               "note": "pinned host batch through the C ABI: records / operators / mismatch bytes are copied "
+                       "(h2d_bytes_per_step), bases and qualities stay in host memory and the kernels read "
+                       "only the sectors they need over PCIe"}
         assert s2.n == n_sites_dev
         del host
     clocks = sampler.stop() if rank == 0 else None

@@ -16,8 +16,11 @@
  *
  * Conventions
  *  - Every buffer is caller-owned; the library keeps no pointer after a call returns.
- *  - `mem` says where a struct's buffers live: AVO_MEM_HOST (pinned preferred) or
- *    AVO_MEM_DEVICE (pointers valid on the context's GPU).
+ *  - `mem` says where a struct's buffers live: AVO_MEM_HOST or AVO_MEM_DEVICE (pointers valid on
+ *    the context's GPU).  Host batches should be page-locked (cudaHostAlloc / cudaHostRegister,
+ *    e.g. the shim's direct ByteBuffers registered once): the per-read records, operators and
+ *    mismatch bytes are then copied at full PCIe rate and the two large columns (bases4, quals)
+ *    are read in place, only the 32-byte sectors the kernels touch (avo_params.host_payload).
  *  - All functions return 0 (AVO_OK) or a negative avo_status; nothing throws or aborts.
  *    A malformed read is skipped, never an error (BiallelicGenotyper.scala:385-391).
  *  - A context is bound to one GPU and is NOT thread-safe; use one per thread.
@@ -155,6 +158,10 @@ typedef struct {
   int32_t max_mapq;           /* call(maxMapQ = 93) */
   int32_t min_phred_discover; /* optPhredThreshold.getOrElse(0) */
   int32_t min_obs_discover;   /* optMinObservations; < 0 = None (distinct); keep count > this */
+  int32_t host_payload;       /* AVO_MEM_HOST batches: 0 = read bases4 / quals in place over PCIe when
+                                 they are page-locked and the mode touches them sparsely (variant-only
+                                 calling, discovery), 1 = always copy them to the device */
+  int32_t reserved;
 } avo_params;
 
 /* ---- outputs ------------------------------------------------------------------------------ */
@@ -221,6 +228,8 @@ typedef struct {
   int32_t n_tile_launches; /* of which tile kernels (1 per stage unless a buffer overflowed) */
   int64_t h2d_bytes;
   int64_t d2h_bytes;
+  int32_t payload_in_place; /* 1: bases4 / quals were read from pinned host memory, not copied */
+  int32_t reserved;
 } avo_timing;
 int avo_get_timing(const avo_ctx* ctx, avo_timing* out);
 

@@ -223,3 +223,34 @@ def test_discovery_exact_path_for_exotic_bases(oracle, ctx):
         got = DiscoverVariants(recs, phred, min_obs, ctx=ctx)
         assert sorted(v.as_tuple() for v in got) == sorted(want), (phred, min_obs)
     assert len(oracle_discover(oracle, recs, 0, 3)) >= 4
+
+
+def test_pinned_host_batch_is_read_in_place(ctx):
+    """A page-locked host batch keeps bases4 / quals on the host (the kernels gather single
+    sectors over PCIe); results are identical to the copied path and to device-resident input."""
+    import torch
+    from avocado_b200 import batch as B
+    p = B.synth_params(seed=9, n_reads_total=30000, contig_len=80000)
+    host = B.synth_host(p)
+    pinned = B.ReadBatch(host.n_reads, host.n_bases, host.n_ops, host.n_refb, host.contig_id, stats=host.stats)
+    keep = []
+    for name, dt in B.READ_COLUMNS:
+        a = getattr(host, name)
+        t = torch.from_numpy(a.view(np.uint8) if a.dtype == B.META_DTYPE else B._torch_view(a)).pin_memory()
+        keep.append(t)
+        v = t.numpy()
+        setattr(pinned, name, v.view(dt) if v.dtype != np.dtype(dt) else v)
+    outs = []
+    for batch, payload, in_place in ((pinned, 0, 1), (pinned, 1, 0), (host, 0, 0)):
+        ctx.host_payload = payload
+        try:
+            sites, cols = ctx.discover_and_call_packed(batch, phred=25, min_obs=5)
+        finally:
+            ctx.host_payload = 0
+        assert ctx.timing()["payload_in_place"] == in_place
+        outs.append((sites, cols))
+    for sites, cols in outs[1:]:
+        assert np.array_equal(sites.start, outs[0][0].start)
+        for k in cols:
+            assert np.array_equal(np.asarray(cols[k]), np.asarray(outs[0][1][k]), equal_nan=True), k
+    assert outs[0][0].n > 10

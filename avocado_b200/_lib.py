@@ -101,6 +101,24 @@ class PackedOutStruct(C.Structure):
                 ("refb", P), ("source_index", P)]
 
 
+class JointInStruct(C.Structure):
+    _fields_ = [("n_sites", C.c_int64), ("n_samples", C.c_int32), ("n_states", C.c_int32),
+                ("mem", C.c_int32), ("reserved", C.c_int32), ("present", P), ("n_alt", P), ("n_ref", P),
+                ("n_other", P), ("n_nocall", P), ("gl", P), ("alt_alleles", P), ("called_alleles", P)]
+
+
+JOINT_OUT_COLUMNS = [  # name, dtype, shape kind: "N" per site, "SN" per (sample, site), "SNG" x n_states
+    ("site_emitted", "uint8", "N"), ("maf", "float64", "N"), ("quality", "float64", "N"),
+    ("post0_sum", "float64", "N"), ("flags", "uint8", "SN"), ("posteriors", "float32", "SNG"),
+    ("priors", "float32", "SNG"), ("n_alt", "int32", "SN"), ("n_ref", "int32", "SN"), ("gq", "int32", "SN")]
+JOINT_POSTERIORS, JOINT_PRIORS, JOINT_RECALLED = 1, 2, 4
+
+
+class JointOutStruct(C.Structure):
+    _fields_ = [("n_sites", C.c_int64), ("n_samples", C.c_int32), ("n_states", C.c_int32),
+                ("mem", C.c_int32), ("reserved", C.c_int32)] + [(n, P) for n, _, _ in JOINT_OUT_COLUMNS]
+
+
 class SynthParamsStruct(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("contig_len", C.c_int32), ("first_pos", C.c_int32),
                 ("n_reads_total", C.c_int64), ("read_len", C.c_int32), ("max_indel", C.c_int32),
@@ -112,6 +130,7 @@ class SynthParamsStruct(C.Structure):
 EXPORTED_SYMBOLS = [
     "avo_ctx_create", "avo_ctx_destroy", "avo_last_error", "avo_version", "avo_ctx_set_stream",
     "avo_get_timing", "avo_discover", "avo_call", "avo_discover_and_call",
+    "avo_joint_counts", "avo_joint",
     "avo_pack_bounds", "avo_pack_reads", "avo_synth_default_params", "avo_synth_host",
     "avo_synth_device",
 ]
@@ -146,6 +165,8 @@ def load():
     lib.avo_discover_and_call.argtypes = [P, C.POINTER(ReadBatchStruct), C.POINTER(CnvStruct),
                                           C.POINTER(ParamsStruct), C.POINTER(SitesOutStruct),
                                           C.POINTER(SiteResultsStruct)]
+    lib.avo_joint_counts.argtypes = [P, C.POINTER(JointInStruct), P, P]
+    lib.avo_joint.argtypes = [P, C.POINTER(JointInStruct), C.POINTER(JointOutStruct)]
     lib.avo_pack_bounds.argtypes = [C.POINTER(TextReadsStruct)] + [C.POINTER(C.c_int64)] * 4
     lib.avo_pack_reads.argtypes = [C.POINTER(TextReadsStruct), C.POINTER(PackedOutStruct)]
     lib.avo_synth_default_params.argtypes = [C.POINTER(SynthParamsStruct)]

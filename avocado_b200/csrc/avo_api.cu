@@ -26,6 +26,7 @@ enum Slot {
   SL_RES,                      // one block holding every result column
   SL_U_START, SL_U_REFLEN, SL_U_ALTLEN, SL_U_COUNT, SL_U_SRC,
   SL_L_POS, SL_L_LENS, SL_L_NIBS, SL_L_SRC, SL_L_HASH,
+  SL_J_PRESENT, SL_J_NALT, SL_J_NREF, SL_J_NOTHER, SL_J_NOCALL, SL_J_GL, SL_J_ALT, SL_J_CALLED, SL_J_OUT,
   SL_TABLE, SL_TCOUNT, SL_KEYS_A, SL_KEYS_B, SL_VALS_A, SL_VALS_B, SL_FOOT, SL_AOFF,
   SL_COUNT_
 };
@@ -43,6 +44,7 @@ struct avo_ctx {
   Buf bufs[SL_COUNT_];
   double* d_lnk = nullptr;
   double* d_lnfact = nullptr;
+  double* d_lgam = nullptr;        // lgamma(k), k = 0..AVO_MAX_PLOIDY + 2 (host libm)
   // score table cache key
   int lut_minp = -1, lut_maxp = -1, lut_maxq = -1, lut_maxmq = -1;
   avo_timing timing{};
@@ -659,6 +661,12 @@ int avo_ctx_create(int device, avo_ctx** out) {
   if (cudaMemcpy(ctx->d_lnk, lnk.data(), LNK_N * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
     return bail(AVO_E_CUDA);
   if (launch_lnfact_table(ctx->d_lnk, ctx->d_lnfact, LNK_N, ctx->stream) != cudaSuccess) return bail(AVO_E_CUDA);
+  {
+    double lg[AVO_MAX_PLOIDY + 3];
+    for (int k = 0; k < AVO_MAX_PLOIDY + 3; ++k) lg[k] = k == 0 ? 0.0 : std::lgamma((double)k);
+    if (cudaMalloc(&ctx->d_lgam, sizeof lg) != cudaSuccess) return bail(AVO_E_NOMEM);
+    if (cudaMemcpy(ctx->d_lgam, lg, sizeof lg, cudaMemcpyHostToDevice) != cudaSuccess) return bail(AVO_E_CUDA);
+  }
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return bail(AVO_E_CUDA);
   *out = ctx;
   return AVO_OK;
@@ -670,6 +678,7 @@ void avo_ctx_destroy(avo_ctx* ctx) {
   for (auto& b : ctx->bufs) if (b.p) cudaFree(b.p);
   if (ctx->d_lnk) cudaFree(ctx->d_lnk);
   if (ctx->d_lnfact) cudaFree(ctx->d_lnfact);
+  if (ctx->d_lgam) cudaFree(ctx->d_lgam);
   if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -774,6 +783,118 @@ int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_c
   }
   CKS(call_internal(ctx, R, hs, T, cnv, params, true, results));
   CKS(finish_call(ctx, true, true));
+  return AVO_OK;
+}
+
+// ---- joint calling ---------------------------------------------------------------------------------
+static int joint_inputs(avo_ctx* ctx, const avo_joint_in* in, DJointIn* J) {
+  if (!in) return fail(ctx, AVO_E_INVALID, "joint input is NULL");
+  if (in->n_sites < 0 || in->n_samples < 1 || in->n_states < 2 || in->n_states > AVO_MAX_PLOIDY + 1)
+    return fail(ctx, AVO_E_INVALID, "joint input: bad n_sites / n_samples / n_states");
+  if (in->mem != AVO_MEM_HOST && in->mem != AVO_MEM_DEVICE) return fail(ctx, AVO_E_INVALID, "bad mem");
+  if (in->n_sites > 0 && (!in->n_alt || !in->n_ref || !in->n_other || !in->gl))
+    return fail(ctx, AVO_E_INVALID, "joint input has NULL columns");
+  const size_t sn = (size_t)in->n_samples * (size_t)in->n_sites;
+  J->n_sites = in->n_sites; J->n_samples = in->n_samples; J->n_states = in->n_states;
+  J->present = nullptr; J->n_nocall = nullptr;
+  if (in->present) CKS(stage_in(ctx, SL_J_PRESENT, in->present, sn, in->mem, &J->present));
+  CKS(stage_in(ctx, SL_J_NALT, in->n_alt, sn, in->mem, &J->n_alt));
+  CKS(stage_in(ctx, SL_J_NREF, in->n_ref, sn, in->mem, &J->n_ref));
+  CKS(stage_in(ctx, SL_J_NOTHER, in->n_other, sn, in->mem, &J->n_other));
+  if (in->n_nocall) CKS(stage_in(ctx, SL_J_NOCALL, in->n_nocall, sn, in->mem, &J->n_nocall));
+  CKS(stage_in(ctx, SL_J_GL, in->gl, sn * (size_t)in->n_states, in->mem, &J->gl));
+  return AVO_OK;
+}
+
+int avo_joint_counts(avo_ctx* ctx, const avo_joint_in* in, int32_t* alt_alleles, int32_t* called_alleles) {
+  CKS(begin_call(ctx));
+  DJointIn J;
+  CKS(joint_inputs(ctx, in, &J));
+  if (!alt_alleles || !called_alleles) return fail(ctx, AVO_E_INVALID, "count outputs are NULL");
+  const size_t n = (size_t)in->n_sites;
+  int32_t *d_alt = alt_alleles, *d_called = called_alleles;
+  if (in->mem == AVO_MEM_HOST) {
+    void* q;
+    CKS(get_buf(ctx, SL_J_ALT, n * 4, &q)); d_alt = (int32_t*)q;
+    CKS(get_buf(ctx, SL_J_CALLED, n * 4, &q)); d_called = (int32_t*)q;
+  }
+  CK(launch_joint_counts(J, d_alt, d_called, ctx->stream));
+  ctx->timing.n_launches += 1;
+  if (in->mem == AVO_MEM_HOST && n) {
+    CK(cudaMemcpyAsync(alt_alleles, d_alt, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(called_alleles, d_called, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->timing.d2h_bytes += (int64_t)n * 8;
+  }
+  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.ms_total = ev_ms(ctx, 0, 7);
+  return AVO_OK;
+}
+
+int avo_joint(avo_ctx* ctx, const avo_joint_in* in, avo_joint_out* out) {
+  CKS(begin_call(ctx));
+  DJointIn J;
+  CKS(joint_inputs(ctx, in, &J));
+  if (!out) return fail(ctx, AVO_E_INVALID, "joint output is NULL");
+  if (out->n_sites != in->n_sites || out->n_samples != in->n_samples || out->n_states != in->n_states)
+    return fail(ctx, AVO_E_INVALID, "joint output shape differs from the input");
+  if (out->mem != AVO_MEM_HOST && out->mem != AVO_MEM_DEVICE) return fail(ctx, AVO_E_INVALID, "bad mem");
+  if (in->n_sites > 0 && (!out->site_emitted || !out->maf || !out->quality || !out->post0_sum ||
+                          !out->flags || !out->posteriors || !out->priors || !out->n_alt ||
+                          !out->n_ref || !out->gq))
+    return fail(ctx, AVO_E_INVALID, "joint output has NULL columns");
+  if ((in->alt_alleles == nullptr) != (in->called_alleles == nullptr))
+    return fail(ctx, AVO_E_INVALID, "alt_alleles and called_alleles go together");
+  const size_t n = (size_t)in->n_sites, sn = n * (size_t)in->n_samples, ns = (size_t)in->n_states;
+  // site totals: given (sharded cohort) or counted here
+  const int32_t *d_alt, *d_called;
+  if (in->alt_alleles) {
+    CKS(stage_in(ctx, SL_J_ALT, in->alt_alleles, n, in->mem, &d_alt));
+    CKS(stage_in(ctx, SL_J_CALLED, in->called_alleles, n, in->mem, &d_called));
+  } else {
+    void* q;
+    CKS(get_buf(ctx, SL_J_ALT, n * 4, &q)); d_alt = (int32_t*)q;
+    CKS(get_buf(ctx, SL_J_CALLED, n * 4, &q)); d_called = (int32_t*)q;
+    CK(launch_joint_counts(J, (int32_t*)d_alt, (int32_t*)d_called, ctx->stream));
+    ctx->timing.n_launches += 1;
+  }
+  // outputs: straight into the caller's arrays when they are on the device, else one staging block
+  DJointOut O;
+  const size_t sz[10] = {n, n * 8, n * 8, n * 8, sn, sn * ns * 4, sn * ns * 4, sn * 4, sn * 4, sn * 4};
+  void* dst[10] = {out->site_emitted, out->maf, out->quality, out->post0_sum, out->flags,
+                   out->posteriors, out->priors, out->n_alt, out->n_ref, out->gq};
+  void* dev[10];
+  if (out->mem == AVO_MEM_DEVICE) {
+    for (int k = 0; k < 10; ++k) dev[k] = dst[k];
+  } else {
+    size_t off[11]; off[0] = 0;
+    for (int k = 0; k < 10; ++k) off[k + 1] = off[k] + align_up(sz[k], 256);
+    void* blk;
+    CKS(get_buf(ctx, SL_J_OUT, off[10], &blk));
+    for (int k = 0; k < 10; ++k) dev[k] = (char*)blk + off[k];
+  }
+  O.site_emitted = (uint8_t*)dev[0]; O.maf = (double*)dev[1]; O.quality = (double*)dev[2];
+  O.post0_sum = (double*)dev[3]; O.flags = (uint8_t*)dev[4]; O.posteriors = (float*)dev[5];
+  O.priors = (float*)dev[6]; O.n_alt = (int32_t*)dev[7]; O.n_ref = (int32_t*)dev[8]; O.gq = (int32_t*)dev[9];
+  if (sn) {
+    CK(cudaMemsetAsync(O.posteriors, 0, sz[5], ctx->stream));
+    CK(cudaMemsetAsync(O.priors, 0, sz[6], ctx->stream));
+  }
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  CK(launch_joint_recall(J, d_alt, d_called, O, ctx->d_lgam, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  ctx->timing.n_launches += 1;
+  if (out->mem == AVO_MEM_HOST) {
+    for (int k = 0; k < 10; ++k) {
+      if (!sz[k]) continue;
+      CK(cudaMemcpyAsync(dst[k], dev[k], sz[k], cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->timing.d2h_bytes += (int64_t)sz[k];
+    }
+  }
+  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.ms_total = ev_ms(ctx, 0, 7);
+  ctx->timing.ms_observe = ev_ms(ctx, 4, 5);
   return AVO_OK;
 }
 

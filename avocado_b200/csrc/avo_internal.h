@@ -84,6 +84,26 @@ struct DCallParams {
   double log10;           // ln 10        (LogPhred.scala)
 };
 
+// ---- joint calling (avo_joint.cu): S samples x N sites, sample-major -------------------------
+struct DJointIn {
+  int64_t n_sites;
+  int32_t n_samples, n_states;
+  const uint8_t* present;   // may be null (all present)
+  const int32_t *n_alt, *n_ref, *n_other;
+  const int32_t* n_nocall;  // may be null
+  const double* gl;
+};
+struct DJointOut {
+  uint8_t* site_emitted;
+  double *maf, *quality, *post0_sum;
+  uint8_t* flags;
+  float *posteriors, *priors;
+  int32_t *n_alt, *n_ref, *gq;
+};
+cudaError_t launch_joint_counts(const DJointIn& J, int32_t* alt, int32_t* called, cudaStream_t s);
+cudaError_t launch_joint_recall(const DJointIn& J, const int32_t* alt, const int32_t* called,
+                                const DJointOut& O, const double* lgam, cudaStream_t s);
+
 // batch statistics produced by k_batch_stats
 struct BatchStats {
   int32_t min_start;

@@ -1,0 +1,172 @@
+"""Host-side mirror of JointAnnotatorCaller (CORE/genotyping/JointAnnotatorCaller.scala) over the
+C ABI (avo_joint_counts / avo_joint), plus the sample-sharded multi-process form.
+
+    JointAnnotatorCaller.apply(genotypes)   -> JointAnnotatorCaller.scala:52-64
+    annotateSite                            -> :74-106
+
+The reference groups a GenotypeRDD into VariantContexts (one per variant, the genotypes of all
+samples); here the grouping is the (samples x sites) matrix the library consumes, sample-major.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from .batch import _device_empty, _ptr
+from .records import ALT, NO_CALL, OTHER_ALT, REF, Genotype, Variant
+
+
+def _is_dev(a):
+    return a is not None and not isinstance(a, np.ndarray)
+
+
+def _joint_in(n_sites, n_samples, n_states, n_alt, n_ref, n_other, gl, present=None, n_nocall=None,
+              totals=None):
+    s = L.JointInStruct()
+    s.n_sites, s.n_samples, s.n_states = n_sites, n_samples, n_states
+    s.mem = L.MEM_DEVICE if _is_dev(n_alt) else L.MEM_HOST
+    s.present, s.n_alt, s.n_ref, s.n_other = _ptr(present), _ptr(n_alt), _ptr(n_ref), _ptr(n_other)
+    s.n_nocall, s.gl = _ptr(n_nocall), _ptr(gl)
+    if totals is not None:
+        s.alt_alleles, s.called_alleles = _ptr(totals[0]), _ptr(totals[1])
+    return s
+
+
+def joint_counts(ctx, n_sites, n_samples, n_states, n_alt, n_ref, n_other, gl, present=None,
+                 n_nocall=None):
+    """avo_joint_counts: (alt alleles, called alleles) per site over these samples."""
+    dev = _is_dev(n_alt)
+    mk = (lambda: _device_empty(n_sites, np.int32, "cuda:%d" % ctx.device)) if dev else \
+         (lambda: np.zeros(max(n_sites, 1), np.int32))
+    alt, called = mk(), mk()
+    s = _joint_in(n_sites, n_samples, n_states, n_alt, n_ref, n_other, gl, present, n_nocall)
+    ctx._check(ctx.lib.avo_joint_counts(ctx.h, C.byref(s), _ptr(alt), _ptr(called)))
+    return alt[:n_sites], called[:n_sites]
+
+
+def joint_call(ctx, n_sites, n_samples, n_states, n_alt, n_ref, n_other, gl, present=None,
+               n_nocall=None, totals=None) -> Dict[str, object]:
+    """avo_joint on (samples x sites) columns (numpy or torch CUDA tensors, sample-major).
+    `totals` = (alt_alleles, called_alleles) of the whole cohort when these samples are a shard."""
+    dev = _is_dev(n_alt)
+    s = _joint_in(n_sites, n_samples, n_states, n_alt, n_ref, n_other, gl, present, n_nocall, totals)
+    o = L.JointOutStruct()
+    o.n_sites, o.n_samples, o.n_states = n_sites, n_samples, n_states
+    o.mem = s.mem
+    out = {}
+    for name, dt, kind in L.JOINT_OUT_COLUMNS:
+        n = {"N": n_sites, "SN": n_sites * n_samples, "SNG": n_sites * n_samples * n_states}[kind]
+        a = _device_empty(n, np.dtype(dt).type, "cuda:%d" % ctx.device) if dev else np.zeros(max(n, 1), dt)
+        out[name] = a
+        setattr(o, name, _ptr(a))
+    ctx._check(ctx.lib.avo_joint(ctx.h, C.byref(s), C.byref(o)))
+    shaped = {}
+    for name, dt, kind in L.JOINT_OUT_COLUMNS:
+        a = out[name]
+        if kind == "N":
+            shaped[name] = a[:n_sites]
+        elif kind == "SN":
+            shaped[name] = a[:n_sites * n_samples].reshape(n_samples, n_sites)
+        else:
+            shaped[name] = a[:n_sites * n_samples * n_states].reshape(n_samples, n_sites, n_states)
+    return shaped
+
+
+MINUS_TEN_DIV_LOG10 = -10.0 / np.log(10.0)
+
+
+def joint_call_sharded(ctx, cols, group=None) -> Dict[str, object]:
+    """Cohort sharded by sample over the ranks of `group`: local allele counts,
+    all-reduce(sum) of the two int32 vectors, local re-call against the cohort totals, all-reduce
+    (sum) of the per-site posterior(0) sums, quality = -10/ln10 * sum.  `cols` holds this rank's
+    samples: n_sites, n_samples, n_states, n_alt, n_ref, n_other, gl [, present, n_nocall] as CUDA
+    tensors (NCCL) or numpy arrays (gloo); every rank must hold the same sites in the same order."""
+    import torch
+    import torch.distributed as dist
+    alt, called = joint_counts(ctx, **cols)
+    dev = _is_dev(alt)
+    t_alt = alt if dev else torch.from_numpy(np.ascontiguousarray(alt))
+    t_called = called if dev else torch.from_numpy(np.ascontiguousarray(called))
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(t_alt, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(t_called, op=dist.ReduceOp.SUM, group=group)
+    totals = (t_alt, t_called) if dev else (t_alt.numpy(), t_called.numpy())
+    out = joint_call(ctx, totals=totals, **cols)
+    p0 = out["post0_sum"] if dev else torch.from_numpy(out["post0_sum"])
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(p0, op=dist.ReduceOp.SUM, group=group)
+    out["quality"] = p0 * MINUS_TEN_DIV_LOG10 if dev else p0.numpy() * MINUS_TEN_DIV_LOG10
+    out["alt_alleles"], out["called_alleles"] = totals
+    return out
+
+
+@dataclass
+class VariantContext:
+    """One squared-off site: the variant (with its joint quality) and the genotypes of all samples."""
+    variant: Variant
+    quality: float
+    genotypes: List[Genotype]
+    minorAlleleFrequency: float
+
+
+class JointAnnotatorCaller:
+    """CORE/genotyping/JointAnnotatorCaller.scala (the rolled-up VariantAnnotation of :141-147 is
+    formatting downstream of the hot path and is not produced here)."""
+
+    @staticmethod
+    def apply(genotypes: Sequence[Genotype], ctx=None) -> List[VariantContext]:
+        from .genotyping import default_context
+        ctx = ctx or default_context()
+        samples = sorted({g.sampleId for g in genotypes}, key=lambda x: (x is None, x))
+        s_of = {s: i for i, s in enumerate(samples)}
+        keys: Dict[tuple, int] = {}
+        for g in genotypes:                       # toVariantContexts: group by variant
+            keys.setdefault(g.variant.as_tuple(), len(keys))
+        n, S = len(keys), len(samples)
+        if n == 0:
+            return []
+        ns = max(max(len(g.genotypeLikelihoods) for g in genotypes), 2)
+        if ns > L.MAX_PLOIDY + 1:
+            raise L.AvocadoError(L.AVO_E_UNSUPPORTED, "more than %d genotype states" % (L.MAX_PLOIDY + 1))
+        present = np.zeros((S, n), np.uint8)
+        cnt = {a: np.zeros((S, n), np.int32) for a in (ALT, REF, OTHER_ALT, NO_CALL)}
+        gl = np.zeros((S, n, ns), np.float64)
+        where: Dict[tuple, Genotype] = {}
+        for g in genotypes:
+            s, i = s_of[g.sampleId], keys[g.variant.as_tuple()]
+            if present[s, i]:
+                raise ValueError("two genotypes of sample %r at %r" % (g.sampleId, g.variant))
+            present[s, i] = 1
+            for a in g.alleles:
+                cnt[a][s, i] += 1
+            gl[s, i, :len(g.genotypeLikelihoods)] = g.genotypeLikelihoods
+            where[(s, i)] = g
+        out = joint_call(ctx, n, S, ns, cnt[ALT].ravel(), cnt[REF].ravel(), cnt[OTHER_ALT].ravel(),
+                         gl.ravel(), present.ravel(), cnt[NO_CALL].ravel())
+        sites: List[VariantContext] = []
+        for key, i in keys.items():
+            if not out["site_emitted"][i]:
+                continue                                                    # :81-83
+            gts = []
+            for s in range(S):
+                g = where.get((s, i))
+                if g is None:
+                    continue
+                fl = int(out["flags"][s, i])
+                k = len(g.genotypeLikelihoods)
+                new = dataclasses.replace(g, nonReferenceLikelihoods=[])         # :231, :247, :259
+                if fl & L.JOINT_POSTERIORS:
+                    new.genotypePosteriors = [float(x) for x in out["posteriors"][s, i, :k]]
+                if fl & L.JOINT_PRIORS:
+                    new.genotypePriors = [float(x) for x in out["priors"][s, i, :k]]
+                if fl & L.JOINT_RECALLED:
+                    new.alleles = [ALT] * int(out["n_alt"][s, i]) + [REF] * int(out["n_ref"][s, i])
+                    new.genotypeQuality = int(out["gq"][s, i])
+                gts.append(new)
+            sites.append(VariantContext(Variant(*key), float(out["quality"][i]), gts, float(out["maf"][i])))
+        return sites

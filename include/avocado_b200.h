@@ -249,6 +249,56 @@ int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_c
                           const avo_params* params, avo_sites_out* sites_out,
                           avo_site_results* results);
 
+/* ---- joint calling: JointAnnotatorCaller.apply (JointAnnotatorCaller.scala:52-64, 74-281) ------ */
+/* Genotypes of S samples at the same N (squared-off) sites, sample-major: entry [s * n_sites + i].
+ * The per-sample columns are the ones avo_call produces (n_alt, n_ref, n_other, gl). */
+typedef struct {
+  int64_t n_sites;
+  int32_t n_samples;
+  int32_t n_states;        /* row stride of gl */
+  int32_t mem;
+  int32_t reserved;
+  const uint8_t* present;  /* [S*N] 1 iff the sample has a genotype at the site; NULL = all */
+  const int32_t* n_alt;    /* [S*N] alleles: ALT x n_alt, REF x n_ref, OTHER_ALT x n_other, NO_CALL x n_nocall */
+  const int32_t* n_ref;
+  const int32_t* n_other;
+  const int32_t* n_nocall; /* NULL = none */
+  const double* gl;        /* [S*N*n_states] genotypeLikelihoods, entries 0..copies */
+  /* site totals over ALL samples of the cohort, when the samples of this call are only a shard
+   * (the caller all-reduced the outputs of avo_joint_counts); NULL = count these samples */
+  const int32_t* alt_alleles;    /* [N] */
+  const int32_t* called_alleles; /* [N] */
+} avo_joint_in;
+
+enum {
+  AVO_JOINT_POSTERIORS = 1, /* genotypePosteriors set */
+  AVO_JOINT_PRIORS = 2,     /* genotypePriors set */
+  AVO_JOINT_RECALLED = 4    /* alleles and genotypeQuality rewritten (n_alt, n_ref, gq) */
+};
+
+typedef struct {
+  int64_t n_sites;
+  int32_t n_samples;
+  int32_t n_states;
+  int32_t mem;
+  int32_t reserved;
+  uint8_t* site_emitted; /* [N] minorAlleleFrequency > 0 (sites with 0 are discarded, :81-83) */
+  double* maf;           /* [N] */
+  double* quality;       /* [N] -10/ln10 * post0_sum (final only when all samples are in this call) */
+  double* post0_sum;     /* [N] sum over this call's samples of posterior(0), in sample order */
+  uint8_t* flags;        /* [S*N] AVO_JOINT_* */
+  float* posteriors;     /* [S*N*n_states] */
+  float* priors;         /* [S*N*n_states] */
+  int32_t* n_alt;        /* [S*N] re-called alleles: ALT x n_alt ++ REF x n_ref (unchanged when not re-called) */
+  int32_t* n_ref;
+  int32_t* gq;           /* [S*N] valid when AVO_JOINT_RECALLED */
+} avo_joint_out;
+
+/* Local allele counts per site (calculateMinorAlleleFrequency's two sums, :117-128). */
+int avo_joint_counts(avo_ctx* ctx, const avo_joint_in* in, int32_t* alt_alleles, int32_t* called_alleles);
+/* annotateSite for every site. */
+int avo_joint(avo_ctx* ctx, const avo_joint_in* in, avo_joint_out* out);
+
 /* ---- host-side packer (PrefilterReads + ObservationOperator.extractAlignmentOperators) ------ */
 /* Text columns of AlignmentRecords (blobs + [n+1] offsets; has_* bits in rec_flags:
  * bit0 readMapped, bit1 readNegativeStrand, bit2 cigar present, bit3 MD present, bit4 mapq present).

@@ -1,0 +1,172 @@
+"""Multi-GPU form of the hot path: one process per GPU, work sharded by genomic region
+(SURVEY.md 8e).  Nothing on the data path is exchanged between ranks except
+
+  * the discovered site tables (all-gather, so that every rank joins its reads against the
+    GLOBAL sorted table, which the Forest look-up of TreeRegionJoin.scala:74-119 depends on), and
+  * the per-site result rows of the sites each rank owns (all-gather to every rank).
+
+Rank g owns the sites that START in [lo_g, hi_g) and is handed every read that can overlap one of
+them or contribute a discovery candidate to one of them (read-overlap halo), so its candidate
+counts and per-site sums are complete and no cross-rank reduction exists.  The reads of a rank
+are a contiguous slice of the sorted batch, so per-site sums keep the batch's read order.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .batch import ReadBatch, SiteTable
+
+
+@dataclass
+class RegionShard:
+    rank: int
+    lo: int          # owned sites start in [lo, hi)
+    hi: int
+    read_lo: int     # reads [read_lo, read_hi) of the sorted batch
+    read_hi: int
+    max_site_len: int = 1 << 12
+
+
+def plan_region_shards(start: np.ndarray, end: np.ndarray, world: int, max_site_len: int = 1 << 12
+                       ) -> List[RegionShard]:
+    """Cuts a sorted batch into `world` shards of (nearly) equal read count; boundaries are read
+    starts.  Rank g owns the sites starting in [lo_g, hi_g) and gets the reads with
+    lo_g - max_span <= start < hi_g + max_site_len: everything that can overlap an owned site or
+    put a discovery candidate on an owned position.  `max_site_len` bounds the reference length of
+    a site (checked against the discovered table by discover_and_call_sharded)."""
+    n = len(start)
+    start = np.asarray(start, np.int64)
+    span = int((np.asarray(end, np.int64) - start).max()) if n else 0
+    NEG, POS = -(1 << 40), 1 << 40
+    cuts = [NEG] + [int(start[(g * n) // world]) if n else 0 for g in range(1, world)] + [POS]
+    for g in range(2, world):
+        cuts[g] = max(cuts[g], cuts[g - 1])
+    shards = []
+    for g in range(world):
+        lo, hi = cuts[g], cuts[g + 1]
+        r_lo = 0 if g == 0 else int(np.searchsorted(start, lo - span, side="left"))
+        r_hi = n if g + 1 == world else int(np.searchsorted(start, hi + max_site_len, side="left"))
+        shards.append(RegionShard(g, lo, hi, r_lo, max(r_hi, r_lo), max_site_len))
+    return shards
+
+
+def _cat_sites(tables: Sequence[SiteTable]) -> Tuple[SiteTable, List[int]]:
+    """Concatenates per-rank (already position-ordered, disjoint) site tables; returns the merged
+    table and the row offset of every part."""
+    offs, rows, nibs = [], 0, 0
+    st, rl, al, ao, a4, ct = [], [], [], [], [], []
+    for t in tables:
+        offs.append(rows)
+        st.append(np.asarray(t.start[:t.n], np.int32)); rl.append(np.asarray(t.ref_len[:t.n], np.int32))
+        al.append(np.asarray(t.alt_len[:t.n], np.int32))
+        ao.append(np.asarray(t.allele_off[:t.n], np.uint32) + np.uint32(nibs))
+        assert t.n_allele_nibbles % 2 == 0
+        a4.append(np.asarray(t.alleles4[:t.n_allele_nibbles // 2], np.uint8))
+        ct.append(np.asarray(t.count[:t.n], np.int32) if t.count is not None else np.zeros(t.n, np.int32))
+        rows += t.n
+        nibs += t.n_allele_nibbles
+    ao.append(np.array([nibs], np.uint32))
+    cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs)) if xs else np.zeros(0, dt)
+    alle = cat(a4, np.uint8)
+    if alle.size == 0:
+        alle = np.zeros(1, np.uint8)
+    merged = SiteTable(rows, nibs, cat(st, np.int32), cat(rl, np.int32), cat(al, np.int32),
+                       cat(ao, np.uint32), alle, None, cat(ct, np.int32))
+    return merged, offs
+
+
+def _take_sites(t: SiteTable, keep: np.ndarray) -> SiteTable:
+    """Rows `keep` (a boolean mask) of a host site table, alleles repacked."""
+    idx = np.nonzero(keep)[0]
+    nibs: List[int] = []
+    ao = np.zeros(len(idx) + 1, np.uint32)
+    for k, i in enumerate(idx):
+        off, ln = int(t.allele_off[i]), int(t.ref_len[i]) + int(t.alt_len[i])
+        ao[k] = len(nibs)
+        for j in range(ln):
+            b = int(t.alleles4[(off + j) >> 1])
+            nibs.append((b & 15) if (off + j) & 1 else (b >> 4))
+        if len(nibs) & 1:
+            nibs.append(0)
+    ao[len(idx)] = len(nibs)
+    a = np.array(nibs, np.uint8) if nibs else np.zeros(0, np.uint8)
+    packed = ((a[0::2] << 4) | a[1::2]).astype(np.uint8) if len(a) else np.zeros(1, np.uint8)
+    return SiteTable(len(idx), len(nibs), np.ascontiguousarray(t.start[idx]), np.ascontiguousarray(t.ref_len[idx]),
+                     np.ascontiguousarray(t.alt_len[idx]), ao, packed, None,
+                     None if t.count is None else np.ascontiguousarray(t.count[idx]))
+
+
+def _all_gather_objects(obj, group=None):
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return [obj]
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, obj, group=group)
+    return out
+
+
+def _all_gather_rows(x, device=None, group=None):
+    """All-gather of a per-rank array with a different number of rows on every rank (padded to the
+    maximum, one collective per column; NCCL when `device` is a CUDA device, else the group's CPU
+    backend).  Returns the list of per-rank numpy arrays."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return [np.asarray(x)]
+    world = dist.get_world_size(group)
+    x = np.ascontiguousarray(x)
+    view = x.view(np.int32) if x.dtype == np.uint32 else x
+    t = torch.from_numpy(view)
+    if device is not None:
+        t = t.to(device)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(max(sizes), 1)
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    parts = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return [p[:s].cpu().numpy().view(x.dtype) for p, s in zip(parts, sizes)]
+
+
+class GpuEngine:
+    """The product engine: avo_discover / avo_call on this rank's GPU."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def discover(self, batch: ReadBatch, phred: int, min_obs: Optional[int]) -> SiteTable:
+        return self.ctx.discover_packed(batch, phred=phred, min_obs=min_obs)
+
+    def call(self, batch: ReadBatch, sites: SiteTable, ploidy: int) -> Dict[str, np.ndarray]:
+        return self.ctx.call_packed(batch, sites, ploidy=ploidy)
+
+
+def discover_and_call_sharded(engine, batch: ReadBatch, shard: RegionShard, phred: int = 0,
+                              min_obs: Optional[int] = None, ploidy: int = 2, group=None,
+                              collective_device=None):
+    """BiallelicGenotyper.discoverAndCall (BG:156-184) over region shards.  `batch` holds THIS
+    rank's reads (shard.read_lo .. shard.read_hi of the sorted whole).  Returns, on every rank,
+    (global SiteTable, dict of result columns for all its rows)."""
+    local = engine.discover(batch, phred, min_obs).to_host()
+    st = np.asarray(local.start[:local.n], np.int64)
+    owned = _take_sites(local, (st >= shard.lo) & (st < shard.hi))
+    parts = _all_gather_objects(owned, group)                    # replicate the global sorted table
+    table, offs = _cat_sites(parts)
+    if table.n == 0:
+        return table, {}
+    if int(np.max(table.ref_len[:table.n])) > shard.max_site_len:
+        raise ValueError("a discovered site is longer than the shard plan's max_site_len=%d: "
+                         "re-plan with a larger halo" % shard.max_site_len)
+    cols = engine.call(batch, table, ploidy)
+    my = slice(offs[shard.rank], offs[shard.rank] + parts[shard.rank].n)
+    merged = {}
+    for k, v in cols.items():                                    # gather the rows each rank owns
+        rows = _all_gather_rows(np.asarray(v)[my], collective_device, group)
+        merged[k] = np.concatenate(rows) if len(rows) > 1 else rows[0]
+    return table, merged

@@ -254,3 +254,20 @@ def test_pinned_host_batch_is_read_in_place(ctx):
         for k in cols:
             assert np.array_equal(np.asarray(cols[k]), np.asarray(outs[0][1][k]), equal_nan=True), k
     assert outs[0][0].n > 10
+
+
+def test_two_gpu_region_and_sample_sharding():
+    """Region-sharded calling and sample-sharded joint calling over NCCL (tests/multi_gpu_check.py);
+    needs two GPUs on the box."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        os.path.join(root, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "multi_gpu_check ok" in r.stdout

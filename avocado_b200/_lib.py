@@ -81,6 +81,10 @@ class SiteResultsStruct(C.Structure):
                [(name, P) for name, _, _ in RESULT_COLUMNS]
 
 
+class RefModelOutStruct(C.Structure):
+    _fields_ = [("capacity", C.c_int64), ("n", C.c_int64), ("start", P), ("rows", SiteResultsStruct)]
+
+
 class TimingStruct(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_discover", C.c_float),
                 ("ms_observe", C.c_float), ("ms_d2h", C.c_float), ("ms_discover_tiles", C.c_float),
@@ -130,7 +134,7 @@ class SynthParamsStruct(C.Structure):
 EXPORTED_SYMBOLS = [
     "avo_ctx_create", "avo_ctx_destroy", "avo_last_error", "avo_version", "avo_ctx_set_stream",
     "avo_get_timing", "avo_discover", "avo_call", "avo_discover_and_call",
-    "avo_joint_counts", "avo_joint",
+    "avo_call_all_sites", "avo_joint_counts", "avo_joint",
     "avo_pack_bounds", "avo_pack_reads", "avo_synth_default_params", "avo_synth_host",
     "avo_synth_device",
 ]
@@ -165,6 +169,9 @@ def load():
     lib.avo_discover_and_call.argtypes = [P, C.POINTER(ReadBatchStruct), C.POINTER(CnvStruct),
                                           C.POINTER(ParamsStruct), C.POINTER(SitesOutStruct),
                                           C.POINTER(SiteResultsStruct)]
+    lib.avo_call_all_sites.argtypes = [P, C.POINTER(ReadBatchStruct), C.POINTER(SitesStruct),
+                                       C.POINTER(CnvStruct), C.POINTER(ParamsStruct),
+                                       C.POINTER(SiteResultsStruct), C.POINTER(RefModelOutStruct)]
     lib.avo_joint_counts.argtypes = [P, C.POINTER(JointInStruct), P, P]
     lib.avo_joint.argtypes = [P, C.POINTER(JointInStruct), C.POINTER(JointOutStruct)]
     lib.avo_pack_bounds.argtypes = [C.POINTER(TextReadsStruct)] + [C.POINTER(C.c_int64)] * 4

@@ -26,6 +26,8 @@ enum Slot {
   SL_RES,                      // one block holding every result column
   SL_U_START, SL_U_REFLEN, SL_U_ALTLEN, SL_U_COUNT, SL_U_SRC,
   SL_L_POS, SL_L_LENS, SL_L_NIBS, SL_L_SRC, SL_L_HASH,
+  SL_AS_FLAG, SL_AS_JPOS, SL_AS_JR, SL_AS_JIDX, SL_AS_COVER, SL_AS_SCOVER, SL_AS_WCOUNT, SL_AS_WBASE,
+  SL_AS_RES, SL_AS_START,
   SL_J_PRESENT, SL_J_NALT, SL_J_NREF, SL_J_NOTHER, SL_J_NOCALL, SL_J_GL, SL_J_ALT, SL_J_CALLED, SL_J_OUT,
   SL_TABLE, SL_TCOUNT, SL_KEYS_A, SL_KEYS_B, SL_VALS_A, SL_VALS_B, SL_FOOT, SL_AOFF,
   SL_COUNT_
@@ -346,16 +348,18 @@ int check_params(avo_ctx* ctx, const avo_params* p) {
     return fail(ctx, AVO_E_UNSUPPORTED, "ploidy %d outside 1..%d", p->ploidy, AVO_MAX_PLOIDY);
   if (p->max_quality < 1 || p->max_quality > 127 || p->max_mapq < 1 || p->max_mapq > 127)
     return fail(ctx, AVO_E_UNSUPPORTED, "max_quality / max_mapq must be in 1..127");
-  if (p->score_all_sites)
-    return fail(ctx, AVO_E_UNSUPPORTED, "score_all_sites (gVCF mode) is not built yet");
   return AVO_OK;
 }
 
 // BiallelicGenotyper.call against a device-resident site table.  `fresh` = the table was just
 // produced by discover_internal on the same batch: it is sorted and single-contig by construction
 // and the read index in SL_RIDX is current.
+int allsites_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const DSites& S, const DCnv& C,
+                      const DCallParams& P, const DIndex& X, avo_ref_model_out* ro);
+
 int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const DevSites& T,
-                  const avo_cnv* cnv, const avo_params* p, bool fresh, avo_site_results* out) {
+                  const avo_cnv* cnv, const avo_params* p, bool fresh, avo_site_results* out,
+                  avo_ref_model_out* ref_out = nullptr) {
   if (T.n == 0)
     return fail(ctx, AVO_E_EMPTY_SITES,
                 "empty variant set: the reference throws here (TreeRegionJoin.scala:77)");
@@ -458,6 +462,68 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
   ctx->timing.n_launches += nl;
   ctx->timing.n_tile_launches += nl;
   CKS(export_results(ctx, D, T.n, ns, out));
+  if (ref_out) CKS(allsites_internal(ctx, R, hs, S, C, P, X, ref_out));
+  return AVO_OK;
+}
+
+// The reference-model rows of scoreAllSites (avo_allsites.cu) for the batch and site table of a
+// call_internal in progress.
+int allsites_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const DSites& S, const DCnv& C,
+                      const DCallParams& P, const DIndex& X, avo_ref_model_out* ro) {
+  avo_site_results* rows = &ro->rows;
+  if (rows->mem != AVO_MEM_HOST && rows->mem != AVO_MEM_DEVICE) return fail(ctx, AVO_E_INVALID, "bad ref_model->rows.mem");
+  if (rows->n_states != P.ns) return fail(ctx, AVO_E_INVALID, "ref_model->rows.n_states must be %d", P.ns);
+  ro->n = 0;
+  if (R.n == 0) return AVO_OK;
+  AllSitesPlan A{};
+  A.p0 = (int64_t)hs.min_start - 1;
+  A.nbits = ((int64_t)hs.max_end - A.p0 + 255) / 256 * 256;
+  if (A.nbits <= 0) return AVO_OK;
+  A.n_win = (int32_t)(A.nbits / 256);
+  void* q;
+  CKS(get_buf(ctx, SL_AS_FLAG, (size_t)(R.n + 1) * 4, &q)); A.flag = (int32_t*)q;
+  CKS(get_buf(ctx, SL_AS_JPOS, (size_t)(R.n + 1) * 4, &q)); A.jpos = (int32_t*)q;
+  CKS(get_buf(ctx, SL_AS_JR, (size_t)R.n * 12, &q)); A.jr = q;
+  CKS(get_buf(ctx, SL_AS_JIDX, (size_t)(X.nb + 1) * 4, &q)); A.jidx = (int32_t*)q;
+  CKS(get_buf(ctx, SL_AS_COVER, (size_t)A.nbits / 8, &q)); A.cover = (uint32_t*)q;
+  CKS(get_buf(ctx, SL_AS_SCOVER, (size_t)A.nbits / 8, &q)); A.site_cover = (uint32_t*)q;
+  CKS(get_buf(ctx, SL_AS_WCOUNT, (size_t)(A.n_win + 1) * 4, &q)); A.win_count = (int32_t*)q;
+  CKS(get_buf(ctx, SL_AS_WBASE, (size_t)(A.n_win + 1) * 4, &q)); A.win_base = (int32_t*)q;
+  const size_t tb = allsites_scan_temp_bytes(std::max<int64_t>(R.n + 1, A.n_win + 1));
+  void* temp;
+  CKS(get_buf(ctx, SL_TEMP, tb, &temp));
+  int nl = 0;
+  CK(launch_allsites_plan(R, S, X, A, temp, tb, ctx->stream, &nl));
+  CK(cudaMemcpyAsync(ctx->h_small, A.jpos + R.n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_small + 1, A.win_base + A.n_win, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const int32_t n_joined = ctx->h_small[0];
+  const int64_t total = ctx->h_small[1];
+  ro->n = total;
+  ctx->timing.n_launches += nl;
+  if (total > ro->capacity)
+    return fail(ctx, AVO_E_CAPACITY, "ref_model too small: need %lld rows", (long long)total);
+  if (total == 0) return AVO_OK;
+  if (!ro->start) return fail(ctx, AVO_E_INVALID, "ref_model->start is NULL");
+  rows->n_sites = total;
+  CKS(check_results(ctx, rows));
+  const ResLayout L = res_layout(total, P.ns);
+  void *d_res, *d_start;
+  CKS(get_buf(ctx, SL_AS_RES, L.total, &d_res));
+  CKS(get_buf(ctx, SL_AS_START, (size_t)total * 4, &d_start));
+  CK(cudaMemsetAsync(d_res, 0, L.total, ctx->stream));
+  DResults D;
+  res_pointers(d_res, L, P.ns, &D);
+  nl = 0;
+  CK(launch_allsites_tiles(R, S, C, P, D, (int32_t*)d_start, X, A, n_joined, hs.max_span, ctx->stream, &nl));
+  ctx->timing.n_launches += nl;
+  CKS(export_results(ctx, D, total, P.ns, rows));
+  if (rows->mem == AVO_MEM_DEVICE) {
+    CK(cudaMemcpyAsync(ro->start, d_start, (size_t)total * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    CK(cudaMemcpyAsync(ro->start, d_start, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->timing.d2h_bytes += total * 4;
+  }
   return AVO_OK;
 }
 
@@ -720,8 +786,8 @@ int avo_discover(avo_ctx* ctx, const avo_read_batch* reads, const avo_params* pa
   return rc;
 }
 
-int avo_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_sites* sites, const avo_cnv* cnv,
-             const avo_params* params, avo_site_results* out) {
+static int call_entry(avo_ctx* ctx, const avo_read_batch* reads, const avo_sites* sites, const avo_cnv* cnv,
+                      const avo_params* params, avo_site_results* out, avo_ref_model_out* ref_model) {
   CKS(begin_call(ctx));
   CKS(validate_reads(ctx, reads));
   CKS(check_params(ctx, params));
@@ -734,7 +800,7 @@ int avo_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_sites* sites, 
   if (!sites->start || !sites->ref_len || !sites->alt_len || !sites->allele_off || !sites->alleles4)
     return fail(ctx, AVO_E_INVALID, "sites has NULL columns");
   DReads R;
-  CKS(upload_reads(ctx, reads, params->host_payload == 0 && !params->score_all_sites, &R));
+  CKS(upload_reads(ctx, reads, params->host_payload == 0 && !ref_model, &R));
   DevSites T;
   T.n = (int32_t)sites->n;
   T.n_nibbles = (uint32_t)sites->n_allele_nibbles;
@@ -749,9 +815,23 @@ int avo_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_sites* sites, 
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   BatchStats hs;
   CKS(batch_stats(ctx, R, &hs));
-  CKS(call_internal(ctx, R, hs, T, cnv, params, false, out));
+  CKS(call_internal(ctx, R, hs, T, cnv, params, false, out, ref_model));
   CKS(finish_call(ctx, false, true));
   return AVO_OK;
+}
+
+int avo_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_sites* sites, const avo_cnv* cnv,
+             const avo_params* params, avo_site_results* out) {
+  if (params && params->score_all_sites)
+    return fail(ctx, AVO_E_INVALID, "score_all_sites needs the reference-model output: call avo_call_all_sites");
+  return call_entry(ctx, reads, sites, cnv, params, out, nullptr);
+}
+
+int avo_call_all_sites(avo_ctx* ctx, const avo_read_batch* reads, const avo_sites* sites,
+                       const avo_cnv* cnv, const avo_params* params, avo_site_results* out,
+                       avo_ref_model_out* ref_model) {
+  if (!ref_model) return fail(ctx, AVO_E_INVALID, "ref_model is NULL");
+  return call_entry(ctx, reads, sites, cnv, params, out, ref_model);
 }
 
 int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_cnv* cnv,
@@ -760,6 +840,8 @@ int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_c
   CKS(begin_call(ctx));
   CKS(validate_reads(ctx, reads));
   CKS(check_params(ctx, params));
+  if (params->score_all_sites)
+    return fail(ctx, AVO_E_INVALID, "score_all_sites: discover with avo_discover, then avo_call_all_sites");
   CKS(check_results(ctx, results));
   DReads R;
   CKS(upload_reads(ctx, reads, params->host_payload == 0 && !params->score_all_sites, &R));

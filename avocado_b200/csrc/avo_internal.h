@@ -141,6 +141,28 @@ cudaError_t launch_call_tiles(const DReads& R, const DSites& S, const DCnv& C, c
                               const DResults& out, const DIndex& X, const BatchStats& hstats,
                               int32_t* d_tile_counter, int num_sms, cudaStream_t s, int* n_launches);
 
+// scoreAllSites reference-model rows (avo_allsites.cu).  All pointers are device scratch.
+struct AllSitesPlan {
+  int64_t p0;          // reference position of bit 0 (min read start - 1)
+  int64_t nbits;       // positions covered by the bitmaps (multiple of 256)
+  int32_t n_win;       // nbits / 256
+  int32_t* flag;       // [n_reads + 1] joined flag per read
+  int32_t* jpos;       // [n_reads + 1] exclusive scan of flag
+  void* jr;            // [n_joined] (read, a, b)
+  int32_t* jidx;       // [nb + 1] coarse index into jr
+  uint32_t* cover;     // positions that may receive a row
+  uint32_t* site_cover;// positions covered by a variant site
+  int32_t* win_count;  // [n_win + 1]
+  int32_t* win_base;   // [n_win + 1] exclusive scan: first row of every 256-position window
+};
+size_t allsites_scan_temp_bytes(int64_t n);
+cudaError_t launch_allsites_plan(const DReads& R, const DSites& S, const DIndex& X, const AllSitesPlan& A,
+                                 void* d_temp, size_t temp_bytes, cudaStream_t s, int* n_launches);
+cudaError_t launch_allsites_tiles(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
+                                  const DResults& O, int32_t* o_start, const DIndex& X,
+                                  const AllSitesPlan& A, int32_t n_joined, int32_t max_span,
+                                  cudaStream_t s, int* n_launches);
+
 // discovery
 struct DDiscoverOut {
   // unsorted candidate survivors appended by the kernels

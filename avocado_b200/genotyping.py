@@ -183,6 +183,36 @@ class Context:
         self._check(rc)
         return self._shape_results(arrs, sites.n, ns) if not device_out else arrs
 
+    def call_all_sites_packed(self, batch: ReadBatch, sites: SiteTable, ploidy=2, cnvs=None,
+                              contig_rank=None, max_quality=93, max_mapq=93, capacity=None,
+                              device_out=False):
+        """avo_call_all_sites (scoreAllSites / gVCF mode) -> (variant columns, ref-model start
+        positions, ref-model columns)."""
+        p = self._params(ploidy=ploidy, max_quality=max_quality, max_mapq=max_mapq, score_all=True)
+        cn = CopyNumberMap(ploidy, list(cnvs or []))
+        ns = cn.maxPloidy + 1
+        cnv_s, keep = self._cnv(cn.cnvs, contig_rank or {})
+        dev = "cuda:%d" % self.device if device_out else None
+        res, arrs = self._alloc_results(sites.n, ns, dev)
+        bs, ss = batch.as_struct(), sites.as_struct()
+        cap = capacity or max(1024, 160 * max(batch.n_reads, 1) // 4)
+        for _ in range(3):
+            rres, rarrs = self._alloc_results(cap, ns, dev)
+            start = _device_empty(cap, np.int32, dev) if device_out else np.zeros(max(cap, 1), np.int32)
+            ro = L.RefModelOutStruct()
+            ro.capacity, ro.start, ro.rows = cap, _ptr(start), rres
+            rc = self.lib.avo_call_all_sites(self.h, C.byref(bs), C.byref(ss), C.byref(cnv_s) if cnv_s else None,
+                                             C.byref(p), C.byref(res), C.byref(ro))
+            if rc == L.AVO_E_CAPACITY:
+                cap = ro.n + 16
+                continue
+            self._check(rc)
+            n = ro.n
+            cols = self._shape_results(arrs, sites.n, ns) if not device_out else arrs
+            rcols = self._shape_results(rarrs, n, ns) if not device_out else rarrs
+            return cols, start[:n], rcols
+        raise L.AvocadoError(L.AVO_E_CAPACITY, "ref-model output kept growing")
+
     def discover_and_call_packed(self, batch: ReadBatch, ploidy=2, phred=0, min_obs=None, cnvs=None,
                                  contig_rank=None, max_quality=93, max_mapq=93, capacity=None,
                                  device_out=False, copy=True):
@@ -325,8 +355,6 @@ class BiallelicGenotyper:
         ctx = ctx or default_context()
         copyNumber = copyNumber or CopyNumberMap.empty(2)
         sample = _one_sample(reads, samples)
-        if scoreAllSites:
-            raise L.AvocadoError(L.AVO_E_UNSUPPORTED, "scoreAllSites (gVCF mode) is not built yet")
         if len(variants) == 0:
             raise L.AvocadoError(L.AVO_E_EMPTY_SITES, "empty variant set: the reference throws "
                                  "ArrayIndexOutOfBounds at TreeRegionJoin.scala:77")
@@ -336,10 +364,19 @@ class BiallelicGenotyper:
         sorted_variants = [variants[i] for i in table.order]
         out: List[Genotype] = []
         merged = None
+        ref_model: List[Genotype] = []
         for contig in sorted(groups):
             batch = pack_reads(groups[contig], contig_id=ranks[contig])
-            cols = ctx.call_packed(batch, table, ploidy=copyNumber.basePloidy, cnvs=copyNumber.cnvs,
-                                   contig_rank=ranks, max_quality=maxQuality, max_mapq=maxMapQ)
+            if scoreAllSites:                                                       # BG:223-275
+                cols, rstart, rcols = ctx.call_all_sites_packed(
+                    batch, table, ploidy=copyNumber.basePloidy, cnvs=copyNumber.cnvs, contig_rank=ranks,
+                    max_quality=maxQuality, max_mapq=maxMapQ)
+                rv = [Variant(contig, int(s), int(s) + 1, "N", None) for s in rstart]
+                rt = SiteTable(len(rv), 0, rstart, None, None, None, None)
+                ref_model.extend(_genotypes_from_columns(rt, rcols, rv, sample))
+            else:
+                cols = ctx.call_packed(batch, table, ploidy=copyNumber.basePloidy, cnvs=copyNumber.cnvs,
+                                       contig_rank=ranks, max_quality=maxQuality, max_mapq=maxMapQ)
             # a site belongs to one contig, so per-contig results never overlap
             if merged is None:
                 merged = {k: v.copy() for k, v in cols.items()}
@@ -349,7 +386,7 @@ class BiallelicGenotyper:
                     merged[k][m] = cols[k][m]
         if merged is None:
             return []
-        return _genotypes_from_columns(table, merged, sorted_variants, sample)
+        return ref_model + _genotypes_from_columns(table, merged, sorted_variants, sample)
 
     @staticmethod
     def discoverAndCall(reads: Sequence[AlignmentRecord], copyNumber: Optional[CopyNumberMap] = None,
@@ -362,10 +399,8 @@ class BiallelicGenotyper:
         ctx = ctx or default_context()
         copyNumber = copyNumber or CopyNumberMap.empty(2)
         sample = _one_sample(reads, samples)
-        if scoreAllSites:
-            raise L.AvocadoError(L.AVO_E_UNSUPPORTED, "scoreAllSites (gVCF mode) is not built yet")
         groups = _by_contig(reads)
-        if len(groups) == 1:
+        if len(groups) == 1 and not scoreAllSites:
             (contig, recs), = groups.items()
             ranks = {contig: 0}
             batch = pack_reads(recs, contig_id=0)

@@ -238,7 +238,8 @@ int avo_get_timing(const avo_ctx* ctx, avo_timing* out);
 int avo_discover(avo_ctx* ctx, const avo_read_batch* reads, const avo_params* params,
                  avo_sites_out* out);
 
-/* BiallelicGenotyper.call on one batch against a site table (variant-only mode). */
+/* BiallelicGenotyper.call on one batch against a site table (variant-only mode; use
+ * avo_call_all_sites for scoreAllSites). */
 int avo_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_sites* sites, const avo_cnv* cnv,
              const avo_params* params, avo_site_results* out);
 
@@ -248,6 +249,26 @@ int avo_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_sites* sites, 
 int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_cnv* cnv,
                           const avo_params* params, avo_sites_out* sites_out,
                           avo_site_results* results);
+
+/* ---- scoreAllSites (gVCF mode) ---------------------------------------------------------------- */
+/* Reference-model rows of BiallelicGenotyper.call(scoreAllSites = true) (BG:223-275, 299-306): one
+ * row per reference position that an observation of a joined read reaches without overlapping
+ * one of that read's variants: DiscoveredVariant(rr) = (contig, start, "N", no alternate),
+ * end = start + 1 (DiscoveredVariant.scala:59-61).  Rows are in ascending position order; like
+ * variant rows, a row with emitted == 0 is not a site (every observation there fell out of the
+ * score join).  Two-phase: on AVO_E_CAPACITY `n` holds the capacity that is needed. */
+typedef struct {
+  int64_t capacity;      /* in: rows available in start[] and rows.* (rows.n_sites is ignored) */
+  int64_t n;             /* out */
+  int32_t* start;        /* [capacity] */
+  avo_site_results rows; /* rows.mem: where start[] and the columns live; rows.n_states as for variants */
+} avo_ref_model_out;
+
+/* BiallelicGenotyper.call(..., scoreAllSites = true): `out` receives the variant rows exactly as
+ * avo_call produces them, `ref_model` the reference-model rows.  params->score_all_sites is implied. */
+int avo_call_all_sites(avo_ctx* ctx, const avo_read_batch* reads, const avo_sites* sites,
+                       const avo_cnv* cnv, const avo_params* params, avo_site_results* out,
+                       avo_ref_model_out* ref_model);
 
 /* ---- joint calling: JointAnnotatorCaller.apply (JointAnnotatorCaller.scala:52-64, 74-281) ------ */
 /* Genotypes of S samples at the same N (squared-off) sites, sample-major: entry [s * n_sites + i].

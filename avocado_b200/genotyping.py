@@ -195,7 +195,7 @@ class Context:
         dev = "cuda:%d" % self.device if device_out else None
         res, arrs = self._alloc_results(sites.n, ns, dev)
         bs, ss = batch.as_struct(), sites.as_struct()
-        cap = capacity or max(1024, 160 * max(batch.n_reads, 1) // 4)
+        cap = capacity or 1 << 16      # two-phase: a too small guess costs one planning pass
         for _ in range(3):
             rres, rarrs = self._alloc_results(cap, ns, dev)
             start = _device_empty(cap, np.int32, dev) if device_out else np.zeros(max(cap, 1), np.int32)

@@ -1,0 +1,174 @@
+"""GPU edge cases and full-size properties of the hot path.
+
+Edge cases the reference's tests touch (copy-number variants over site boundaries
+BiallelicGenotyperSuite.scala:145-213, reads the reference skips, empty inputs) and, at the
+BASELINE.json configs[1] size, properties that do not need the oracle: determinism, invariance to
+region sharding, and internal consistency of every emitted row (recomputed with torch in fp64)."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import compare_call, oracle_reads_from_batch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from avocado_b200.genotyping import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("ploidy,cnvs", [
+    (2, [("ctg", 3000, 9000, 3), ("ctg", 15000, 15500, 1)]),       # DUP and DEL inside the batch
+    (2, [("ctg", 0, 100000, 3)]),                                     # everything duplicated
+    (1, []), (3, []), (4, [("ctg", 10000, 20000, 2)]),
+    (2, [("other", 0, 100000, 5), ("ctg", 7000, 7200, 1)])])          # a CNV on another contig widens the ploidy range
+def test_copy_number_and_ploidy(oracle, ctx, ploidy, cnvs):
+    from avocado_b200 import batch as B
+    p = B.synth_params(seed=31, n_reads_total=8000, contig_len=30000, first_pos=1000)
+    host = B.synth_host(p)
+    rs = oracle_reads_from_batch(oracle, host)
+    want_v = oracle.discover(rs, 25, 5)
+    sites = ctx.discover_packed(host, phred=25, min_obs=5)
+    want = oracle.call(rs, [(c, s, e, r, a) for c, s, e, r, a, _ in want_v], ploidy, list(cnvs), False, 93, 93, 1)
+    cols = ctx.call_packed(host, sites, ploidy=ploidy, cnvs=cnvs, contig_rank={"ctg": 0, "other": 1})
+    keys = [("ctg", v.start, v.referenceAllele, v.alternateAllele) for v in sites.to_variants(["ctg"])]
+    st = compare_call(keys, cols, want)
+    assert st["sites"] > 10
+    if len(cnvs) == 2 and cnvs[0][0] == "ctg":
+        assert len(set(np.asarray(cols["copy_number"])[np.asarray(cols["emitted"]).astype(bool)].tolist())) > 1
+    # gVCF rows carry the copy number of their position too
+    want_all = oracle.call(rs, [(c, s, e, r, a) for c, s, e, r, a, _ in want_v], ploidy, list(cnvs), True, 93, 93, 1)
+    c2, rstart, rcols = ctx.call_all_sites_packed(host, sites, ploidy=ploidy, cnvs=cnvs,
+                                                  contig_rank={"ctg": 0, "other": 1})
+    keys2 = keys + [("ctg", int(s), "N", None) for s in rstart]
+    merged = {k: np.concatenate([np.asarray(c2[k]), np.asarray(rcols[k])]) for k in c2}
+    compare_call(keys2, merged, want_all)
+
+
+def test_quality_and_mapq_caps(oracle, ctx):
+    """call(maxQuality, maxMapQ) (BG:95-96, 451-452): clamping through least()."""
+    from avocado_b200 import batch as B
+    p = B.synth_params(seed=5, n_reads_total=5000, contig_len=20000)
+    host = B.synth_host(p)
+    rs = oracle_reads_from_batch(oracle, host)
+    want_v = oracle.discover(rs, 25, 5)
+    sites = ctx.discover_packed(host, phred=25, min_obs=5)
+    keys = [("ctg", v.start, v.referenceAllele, v.alternateAllele) for v in sites.to_variants(["ctg"])]
+    for mq, mm in ((30, 50), (93, 20), (10, 10)):
+        want = oracle.call(rs, [(c, s, e, r, a) for c, s, e, r, a, _ in want_v], 2, [], False, mq, mm, 1)
+        compare_call(keys, ctx.call_packed(host, sites, max_quality=mq, max_mapq=mm), want)
+
+
+def test_reads_the_reference_skips_and_empty_inputs(oracle, ctx):
+    from avocado_b200 import _lib as L, batch as B
+    from avocado_b200.genotyping import BiallelicGenotyper, DiscoverVariants
+    from avocado_b200.records import AlignmentRecord, Variant
+
+    def read(start, seq, cigar, md, **kw):
+        d = dict(readMapped=True, contigName="1", start=start, end=start + len(seq), sequence=seq,
+                 qual="I" * len(seq), cigar=cigar, mismatchingPositions=md, mapq=40)
+        d.update(kw)
+        return AlignmentRecord(**d)
+    good = [read(100, "ACGTACGTAC", "10M", "4A5") for _ in range(3)]
+    odd = [read(100, "ACGTACGTAC", "10M", None),                     # no MD: no operators
+           read(100, "ACGTACGTAC", "*", "10"),                       # no CIGAR
+           read(100, "ACGTACGTAC", "4M2N4M", "8"),                   # unsupported CIGAR operator
+           read(100, "ACGTACGTAC", "10M", "4A5", mapq=None),         # observeRead throws: skipped by call
+           read(100, "ACGTA", "10M", "4A5"),                         # sequence shorter than the CIGAR
+           AlignmentRecord(readMapped=False, sequence="ACGT", qual="IIII")]
+    recs = good + odd
+    # (a sequence shorter than its CIGAR crashes the reference's discovery job; the packer drops
+    # such a read instead, so the oracle is not asked about it there)
+    no_short = [r for r in recs if r.sequence != "ACGTA"]
+    want_v = oracle.discover(oracle.reads_from_dicts([r.as_dict() for r in no_short]), 0, None)
+    got_v = DiscoverVariants(recs, ctx=ctx)
+    assert sorted(v.as_tuple() for v in got_v) == sorted((c, s, e, r, a) for c, s, e, r, a, _ in want_v)
+    assert got_v == DiscoverVariants(no_short, ctx=ctx)
+    gts = BiallelicGenotyper.call(recs, [Variant("1", 104, 105, "A", "A")], samples=["s"], ctx=ctx)
+    want = oracle.call(oracle.reads_from_dicts([r.as_dict() for r in recs]), [("1", 104, 105, "A", "A")],
+                       2, [], False, 93, 93, 1)
+    assert len(gts) == len(want["start"]) == 1 and gts[0].readDepth == want["totalCoverage"][0]
+    # no mapped read at all / an empty packed batch
+    assert DiscoverVariants([odd[-1]], ctx=ctx) == []
+    empty = B.pack_reads([])
+    assert empty.n_reads == 0 and ctx.discover_packed(empty).n == 0
+    table = B.sites_from_variants([Variant("1", 104, 105, "A", "C")], {"1": 0})
+    cols = ctx.call_packed(empty, table)
+    assert not cols["emitted"].any()
+    # parameters outside the supported domain are errors, not crashes
+    for kw in (dict(ploidy=0), dict(ploidy=L.MAX_PLOIDY + 1), dict(max_quality=0), dict(max_mapq=200)):
+        with pytest.raises(L.AvocadoError):
+            ctx.call_packed(B.pack_reads(good), table, **kw)
+    unsorted = B.sites_from_variants([Variant("1", 104, 105, "A", "C"), Variant("1", 102, 103, "G", "C")], {"1": 0})
+    unsorted.start = np.ascontiguousarray(unsorted.start[::-1])
+    with pytest.raises(L.AvocadoError) as e:
+        ctx.call_packed(B.pack_reads(good), unsorted)
+    assert e.value.status == L.AVO_E_UNSORTED
+
+
+def test_full_size_properties(ctx):
+    """BASELINE.json configs[1] (25.6 M reads, 64 Mb): the oracle cannot run at this size, so the
+    check is through properties: bit-identical repeat, invariance of a region's rows to computing
+    only that region (the sharding property of SURVEY.md 8e), and every row recomputed from its
+    own aggregates in torch fp64 (blend / arg-max / quality, strand components, RMS mapQ)."""
+    import torch
+    from avocado_b200 import batch as B
+    n, clen = 25_600_000, 64_000_000
+    p = B.synth_params(seed=0xA70CAD0 + 1, contig_len=clen, n_reads_total=n)
+    dev = B.synth_device(p)
+    s1, c1 = ctx.discover_and_call_packed(dev, phred=25, min_obs=5, capacity=1 << 18, device_out=True, copy=False)
+    n_sites = s1.n
+    assert 50_000 < n_sites < 100_000
+    snap = {k: v.clone() for k, v in c1.items()}
+    start1 = s1.start[:n_sites].clone()
+    s2, c2 = ctx.discover_and_call_packed(dev, phred=25, min_obs=5, capacity=1 << 18, device_out=True, copy=False)
+    assert s2.n == n_sites and torch.equal(s2.start[:n_sites], start1)
+    bits = lambda t: t.contiguous().view(-1).view(torch.uint8)
+    for k, v in c2.items():
+        assert torch.equal(bits(snap[k]), bits(v)), k                        # bit-identical repeat
+    em = snap["emitted"].bool()
+    assert int(em.sum()) == n_sites                                      # every discovered site is observed
+    ns = 3
+    al, rf, ot = (snap[k].view(n_sites, ns) for k in ("allele_ll", "ref_ll", "other_ll"))
+    gl = al + rf.flip(1)
+    assert torch.equal(gl, snap["gl"].view(n_sites, ns))                 # BG:728, bit-exact
+    k10 = 10.0 / math.log(10.0)
+
+    def qual_state(x):
+        top2 = torch.topk(x, 2, dim=1).values
+        return k10 * (top2[:, 0] - top2[:, 1]), torch.argmax(x, dim=1)
+    q_ar, s_ar = qual_state(gl)
+    q_ao, _ = qual_state(al + ot.flip(1))
+    q_or, _ = qual_state(ot + rf.flip(1))
+    qual = torch.maximum(torch.maximum(q_ar, q_ao), q_or)
+    assert torch.equal(qual, snap["qual"])                               # BG:598-615, 665
+    assert torch.equal(qual.to(torch.int32), snap["gq"])                 # toInt truncation
+    pick = (q_ar >= q_ao) & (q_ar >= q_or)
+    assert torch.equal(snap["n_alt"][pick], s_ar[pick].to(torch.int32))
+    assert torch.equal(snap["n_alt"] + snap["n_ref"] + snap["n_other"], snap["copy_number"])
+    sb = snap["sb"].view(n_sites, 4)
+    assert torch.equal(sb[:, 0] + sb[:, 1], snap["other_cov"]) and torch.equal(sb[:, 2] + sb[:, 3], snap["allele_cov"])
+    assert bool((snap["allele_cov"] + snap["other_cov"] <= snap["total_cov"]).all())
+    rms = torch.sqrt(snap["square_mapq"] / (snap["allele_cov"] + snap["other_cov"]).double()).float()
+    assert torch.equal(rms, snap["rms_mapq"])
+    assert 55 < float(snap["total_cov"].double().mean()) < 62           # 60x coverage, minus mapQ-0 / Q0 drops
+
+    # a region computed on its own (reads overlapping it, with halo) gives the same rows
+    host_meta = dev.meta.view(torch.int32).view(-1, 8)
+    st = host_meta[:, 0].contiguous()
+    lo_pos, hi_pos = 20_000_000, 21_000_000
+    r_lo = int(torch.searchsorted(st, torch.tensor(lo_pos - 400, device=st.device, dtype=st.dtype)))
+    r_hi = int(torch.searchsorted(st, torch.tensor(hi_pos + 400, device=st.device, dtype=st.dtype)))
+    sub = B.synth_device(p, first=r_lo, n=r_hi - r_lo)                   # the same reads, generated as their own batch
+    s3, c3 = ctx.discover_and_call_packed(sub, phred=25, min_obs=5, capacity=1 << 18, device_out=True, copy=False)
+    m1 = (start1 >= lo_pos) & (start1 < hi_pos)
+    m3 = (s3.start[:s3.n] >= lo_pos) & (s3.start[:s3.n] < hi_pos)
+    assert int(m1.sum()) == int(m3.sum()) > 500
+    assert torch.equal(start1[m1], s3.start[:s3.n][m3])
+    for k in ("total_cov", "allele_cov", "gq", "qual", "allele_ll", "ref_ll", "fisher"):
+        assert torch.equal(bits(snap[k][m1]), bits(c3[k][m3])), k

@@ -26,6 +26,7 @@ enum Slot {
   SL_RES,                      // one block holding every result column
   SL_U_START, SL_U_REFLEN, SL_U_ALTLEN, SL_U_COUNT, SL_U_SRC,
   SL_L_POS, SL_L_LENS, SL_L_NIBS, SL_L_SRC, SL_L_HASH,
+  SL_C_RBASE, SL_C_BLEN, SL_C_BOFF, SL_C_BUCKETS,
   SL_AS_FLAG, SL_AS_JPOS, SL_AS_JR, SL_AS_JIDX, SL_AS_COVER, SL_AS_SCOVER, SL_AS_WCOUNT, SL_AS_WBASE,
   SL_AS_RES, SL_AS_START,
   SL_J_PRESENT, SL_J_NALT, SL_J_NREF, SL_J_NOTHER, SL_J_NOCALL, SL_J_GL, SL_J_ALT, SL_J_CALLED, SL_J_OUT,
@@ -455,9 +456,27 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
   DResults D;
   res_pointers(d_res, L, ns, &D);
 
+  // per-site buckets: one 32-bit slot per read that can overlap the site
+  void *d_rbase, *d_blen, *d_boff, *d_buckets;
+  CKS(get_buf(ctx, SL_C_RBASE, (size_t)(T.n + 1) * 4, &d_rbase));
+  CKS(get_buf(ctx, SL_C_BLEN, (size_t)(T.n + 1) * 4, &d_blen));
+  CKS(get_buf(ctx, SL_C_BOFF, (size_t)(T.n + 1) * 4, &d_boff));
+  const size_t tb2 = call_scan_temp_bytes(T.n);
+  CKS(get_buf(ctx, SL_TEMP, tb2, &d_temp));
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   int nl = 0;
-  CK(launch_call_tiles(R, S, C, P, D, X, hs, small + 8, ctx->num_sms, ctx->stream, &nl));
+  size_t n_slots = 0;
+  if (R.n > 0 && S.c_hi > S.c_lo) {
+    CK(launch_call_buckets(R, S, hs, (int32_t*)d_rbase, (uint32_t*)d_blen, (uint32_t*)d_boff, d_temp, tb2,
+                           ctx->stream, &nl));
+    CK(cudaMemcpyAsync(ctx->h_small, (uint32_t*)d_boff + S.c_hi, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    n_slots = (size_t)(uint32_t)ctx->h_small[0];
+  }
+  CKS(get_buf(ctx, SL_C_BUCKETS, n_slots * 4, &d_buckets));
+  CK(launch_call_tiles(R, S, C, P, D, X, (const int32_t*)d_rbase, (const uint32_t*)d_blen,
+                       (const uint32_t*)d_boff, (uint32_t*)d_buckets, n_slots, small + 8, ctx->num_sms,
+                       ctx->stream, &nl));
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
   ctx->timing.n_launches += nl;
   ctx->timing.n_tile_launches += nl;

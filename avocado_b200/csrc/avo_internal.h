@@ -137,9 +137,16 @@ cudaError_t launch_build_index(const DReads& R, const DSites& S, const BatchStat
 cudaError_t launch_build_site_index(const DSites& S, const BatchStats& hstats, int32_t* sidx,
                                     int32_t* s_range, cudaStream_t s);
 
+// call: per-site buckets (one slot per read that can overlap the site), observe, reduce
+size_t call_scan_temp_bytes(int32_t n);
+cudaError_t launch_call_buckets(const DReads& R, const DSites& S, const BatchStats& hstats, int32_t* rbase,
+                                uint32_t* blen, uint32_t* boff, void* d_temp, size_t temp_bytes,
+                                cudaStream_t s, int* n_launches);
 cudaError_t launch_call_tiles(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
-                              const DResults& out, const DIndex& X, const BatchStats& hstats,
-                              int32_t* d_tile_counter, int num_sms, cudaStream_t s, int* n_launches);
+                              const DResults& out, const DIndex& X, const int32_t* rbase,
+                              const uint32_t* blen, const uint32_t* boff, uint32_t* buckets,
+                              size_t n_slots, int32_t* d_block_counter, int num_sms, cudaStream_t s,
+                              int* n_launches);
 
 // scoreAllSites reference-model rows (avo_allsites.cu).  All pointers are device scratch.
 struct AllSitesPlan {

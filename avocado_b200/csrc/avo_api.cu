@@ -474,9 +474,11 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
     n_slots = (size_t)(uint32_t)ctx->h_small[0];
   }
   CKS(get_buf(ctx, SL_C_BUCKETS, n_slots * 4, &d_buckets));
+  void* d_jlist;
+  CKS(get_buf(ctx, SL_AS_JR, (size_t)R.n * 12, &d_jlist));
   CK(launch_call_tiles(R, S, C, P, D, X, (const int32_t*)d_rbase, (const uint32_t*)d_blen,
-                       (const uint32_t*)d_boff, (uint32_t*)d_buckets, n_slots, small + 8, ctx->num_sms,
-                       ctx->stream, &nl));
+                       (const uint32_t*)d_boff, (uint32_t*)d_buckets, n_slots, d_jlist, small + 8,
+                       ctx->num_sms, ctx->stream, &nl));
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
   ctx->timing.n_launches += nl;
   ctx->timing.n_tile_launches += nl;

@@ -10,7 +10,8 @@
 //   genotype        BG:579-797, util/LogPhred.scala:38-40             -> finalize_site()
 //
 // Two kernels (DESIGN.md "call"):
-//  k_call_observe  walks the reads.  Reads are sorted by start, so the reads that can overlap site j
+//  k_call_join     one thread per read: index test + Forest.get; joined reads go to a list.
+//  k_call_observe  one thread per joined read.  Reads are sorted by start, so the reads that can overlap site j
 //                  are one contiguous index range [rbase_j, rend_j) (k_site_buckets); site j owns a
 //                  bucket of that many 32-bit slots and read r writes its record for site j into
 //                  slot r - rbase_j.  Every record therefore has a fixed place that does not depend
@@ -26,9 +27,6 @@
 namespace avo {
 
 constexpr int OBS_THREADS = 256;
-constexpr int OBS_WARPS = OBS_THREADS / 32;
-constexpr int OBS_QCAP = 64;         // joined reads queued per warp
-constexpr int OBS_CLAIM = 16;        // blocks of 32 reads claimed per atomic
 constexpr int MAX_LOCAL_SITES = 32;  // per-read category cache
 #ifndef AVO_CALL_MINB
 #define AVO_CALL_MINB 4
@@ -111,73 +109,57 @@ __device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, co
   }
 }
 
-struct __align__(16) ObsWarpSmem {
-  int32_t q_read[OBS_QCAP];        // joined reads awaiting classification
-  int32_t q_a[OBS_QCAP];
-  int32_t q_b[OBS_QCAP];
-};
+struct JoinedRead { int32_t r, a, b; };
 
-// Warps pull blocks of 32 reads.  Lanes run the join for their read (a cheap index test first:
-// most reads have no site in reach) and compact the joined reads (~15 %) into the warp's queue;
-// whenever 32 are pending each lane classifies one of them, so that the expensive part runs at
-// full SIMD width.  No block barrier, no ordering between warps.
-__global__ void __launch_bounds__(OBS_THREADS, AVO_CALL_MINB)
-k_call_observe(DReads R, DSites S, DCnv C, DCallParams P, DIndex X, const int32_t* __restrict__ rbase,
-               const uint32_t* __restrict__ boff, uint32_t* __restrict__ buckets, int32_t n_blocks,
-               int32_t* __restrict__ block_counter) {
-  __shared__ ObsWarpSmem smem[OBS_WARPS];
+// Join (TreeRegionJoin.scala:175-203): one thread per read.  A cheap index test first (most reads
+// have no site in reach), then Forest.get; the joined reads (~15 %) are appended to a global list.
+// The list order is irrelevant (every record has its own slot), so the append is one shared-memory
+// atomic per warp and one global atomic per block.
+constexpr int JOIN_THREADS = 512;
+__global__ void __launch_bounds__(JOIN_THREADS)
+k_call_join(DReads R, DSites S, DIndex X, JoinedRead* __restrict__ list, int32_t* __restrict__ n_list) {
+  __shared__ int32_t s_count, s_base;
   const int lane = threadIdx.x & 31;
-  ObsWarpSmem& ws = smem[threadIdx.x >> 5];
-  const unsigned lt = (1u << lane) - 1u;
-  int qn = 0;
-  int32_t claim = 0;
-  auto drain = [&](int take) {
-    if (lane < take)
-      observe_read(R, S, C, P, ws.q_read[lane], ws.q_a[lane], ws.q_b[lane], rbase, boff, buckets);
-    const int rest = qn - take;
-    int32_t tr = 0, ta = 0, tb = 0;
-    if (lane < rest) { tr = ws.q_read[take + lane]; ta = ws.q_a[take + lane]; tb = ws.q_b[take + lane]; }
-    __syncwarp();
-    if (lane < rest) { ws.q_read[lane] = tr; ws.q_a[lane] = ta; ws.q_b[lane] = tb; }
-    qn = rest;
-    __syncwarp();
-  };
-  for (int32_t it = 0;; ++it) {
-    // blocks are claimed OBS_CLAIM at a time: one atomic per 32 reads would serialise on the counter
-    int32_t blk0 = 0;
-    if ((it % OBS_CLAIM) == 0) {
-      if (lane == 0) blk0 = atomicAdd(block_counter, OBS_CLAIM);
-      claim = __shfl_sync(0xFFFFFFFFu, blk0, 0);
-    }
-    const int32_t blk = claim + (it % OBS_CLAIM);
-    if (blk >= n_blocks) { if (claim >= n_blocks) break; else continue; }
-    const int64_t r = (int64_t)blk * 32 + lane;
-    int32_t a = 0, b = 0;
-    bool joined = false;
-    if (r < R.n) {
-      const int2 se = __ldg(reinterpret_cast<const int2*>(R.meta + r));   // start, end
-      // sites that start in the bins the read touches, or an earlier site reaching past its start
-      const int32_t hLo = (se.x <= X.win0) ? S.c_lo : __ldg(X.sidx + idx_bin_floor(X, se.x));
-      const int64_t d = (int64_t)se.y - X.win0;
-      const int64_t k = d < 0 ? 0 : d / IDX_G + 1;
-      const int32_t hHi = (k >= X.nb) ? S.c_hi : __ldg(X.sidx + (int32_t)k);
-      if (hLo < hHi || (hLo > S.c_lo && __ldg(S.pme + hLo - 1) > se.x)) {
-        forest_get(S, R.contig, se.x, se.y, hLo, hHi, a, b);
-        joined = a < b;                                   // no overlapping variant: read dropped
-      }
-    }
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, joined);
-    if (m) {
-      if (joined) {
-        const int slot = qn + __popc(m & lt);
-        ws.q_read[slot] = (int32_t)r; ws.q_a[slot] = a; ws.q_b[slot] = b;
-      }
-      qn += __popc(m);
-      __syncwarp();
-      if (qn >= 32) drain(32);
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  const int64_t r = (int64_t)blockIdx.x * JOIN_THREADS + threadIdx.x;
+  int32_t a = 0, b = 0;
+  bool joined = false;
+  if (r < R.n) {
+    const int2 se = __ldg(reinterpret_cast<const int2*>(R.meta + r));   // start, end
+    // sites that start in the index bins the read touches, or an earlier site reaching past its start
+    const int32_t hLo = (se.x <= X.win0) ? S.c_lo : __ldg(X.sidx + idx_bin_floor(X, se.x));
+    const int64_t d = (int64_t)se.y - X.win0;
+    const int64_t k = d < 0 ? 0 : d / IDX_G + 1;
+    const int32_t hHi = (k >= X.nb) ? S.c_hi : __ldg(X.sidx + (int32_t)k);
+    if (hLo < hHi || (hLo > S.c_lo && __ldg(S.pme + hLo - 1) > se.x)) {
+      forest_get(S, R.contig, se.x, se.y, hLo, hHi, a, b);
+      joined = a < b;                                     // no overlapping variant: read dropped
     }
   }
-  if (qn > 0) drain(qn);
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, joined);
+  int32_t wbase = 0;
+  if (m && lane == 0) wbase = atomicAdd(&s_count, __popc(m));
+  wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_count > 0) s_base = atomicAdd(n_list, s_count);
+  __syncthreads();
+  if (joined) {
+    JoinedRead j; j.r = (int32_t)r; j.a = a; j.b = b;
+    list[s_base + wbase + __popc(m & ((1u << lane) - 1u))] = j;
+  }
+}
+
+// Observation + classification: one thread per joined read.
+__global__ void __launch_bounds__(OBS_THREADS, AVO_CALL_MINB)
+k_call_observe(DReads R, DSites S, DCnv C, DCallParams P, const JoinedRead* __restrict__ list,
+               const int32_t* __restrict__ n_list, const int32_t* __restrict__ rbase,
+               const uint32_t* __restrict__ boff, uint32_t* __restrict__ buckets) {
+  const int32_t n = *n_list;
+  for (int32_t i = blockIdx.x * OBS_THREADS + threadIdx.x; i < n; i += gridDim.x * OBS_THREADS) {
+    const JoinedRead j = list[i];
+    observe_read(R, S, C, P, j.r, j.a, j.b, rbase, boff, buckets);
+  }
 }
 
 // ---- per-site ordered reduction + genotype ---------------------------------------------------------
@@ -267,28 +249,28 @@ cudaError_t launch_call_buckets(const DReads& R, const DSites& S, const BatchSta
 cudaError_t launch_call_tiles(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
                               const DResults& out, const DIndex& X, const int32_t* rbase,
                               const uint32_t* blen, const uint32_t* boff, uint32_t* buckets,
-                              size_t n_slots, int32_t* d_block_counter, int num_sms, cudaStream_t s,
-                              int* n_launches) {
-  cudaError_t e = cudaMemsetAsync(d_block_counter, 0, sizeof(int32_t), s);
+                              size_t n_slots, void* joined_list, int32_t* d_counter, int num_sms,
+                              cudaStream_t s, int* n_launches) {
+  cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int32_t), s);
   if (e != cudaSuccess) return e;
   if (R.n == 0 || S.c_hi <= S.c_lo) return cudaSuccess;
   if (n_slots) {
     e = cudaMemsetAsync(buckets, 0, n_slots * sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
   }
-  const int32_t n_blocks = (int32_t)((R.n + 31) / 32);
+  k_call_join<<<(unsigned)((R.n + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, s>>>(
+      R, S, X, (JoinedRead*)joined_list, d_counter);
   int blocks_per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_call_observe, OBS_THREADS, 0);
   if (e != cudaSuccess) return e;
-  const int grid = (int)min((int64_t)(n_blocks + OBS_WARPS - 1) / OBS_WARPS,
-                            (int64_t)num_sms * max(1, blocks_per_sm));
-  k_call_observe<<<grid, OBS_THREADS, 0, s>>>(R, S, C, P, X, rbase, boff, buckets, n_blocks, d_block_counter);
+  k_call_observe<<<num_sms * max(1, blocks_per_sm), OBS_THREADS, 0, s>>>(
+      R, S, C, P, (const JoinedRead*)joined_list, d_counter, rbase, boff, buckets);
   const int32_t n = S.c_hi - S.c_lo;
   if (P.ns <= 3)
     k_call_reduce<3><<<(n + 127) / 128, 128, 0, s>>>(S, P, out, boff, blen, buckets);
   else
     k_call_reduce<NSMAX><<<(n + 127) / 128, 128, 0, s>>>(S, P, out, boff, blen, buckets);
-  if (n_launches) *n_launches += 2;
+  if (n_launches) *n_launches += 3;
   return cudaGetLastError();
 }
 

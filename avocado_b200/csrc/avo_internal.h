@@ -145,8 +145,8 @@ cudaError_t launch_call_buckets(const DReads& R, const DSites& S, const BatchSta
 cudaError_t launch_call_tiles(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
                               const DResults& out, const DIndex& X, const int32_t* rbase,
                               const uint32_t* blen, const uint32_t* boff, uint32_t* buckets,
-                              size_t n_slots, int32_t* d_block_counter, int num_sms, cudaStream_t s,
-                              int* n_launches);
+                              size_t n_slots, void* joined_list /* 12 B x n_reads */, int32_t* d_counter,
+                              int num_sms, cudaStream_t s, int* n_launches);
 
 // scoreAllSites reference-model rows (avo_allsites.cu).  All pointers are device scratch.
 struct AllSitesPlan {

@@ -19,7 +19,7 @@ namespace {
 constexpr int32_t LNK_N = 1 << 16;
 
 enum Slot {
-  SL_META, SL_BASES, SL_QUALS, SL_OPS, SL_REFB,
+  SL_META, SL_COORDS, SL_BASES, SL_QUALS, SL_OPS, SL_REFB,
   SL_S_CONTIG, SL_S_START, SL_S_REFLEN, SL_S_ALTLEN, SL_S_AOFF, SL_S_ALLELES, SL_S_END, SL_S_PME,
   SL_S_COUNT,
   SL_CNV, SL_STATS, SL_SMALL, SL_RIDX, SL_SIDX, SL_TEMP, SL_LUT,
@@ -144,6 +144,11 @@ int upload_reads(avo_ctx* ctx, const avo_read_batch* r, bool sparse, DReads* R) 
   const size_t n = (size_t)r->n_reads;
   R->n = r->n_reads;
   R->contig = r->contig_id;
+  {
+    void* c;
+    CKS(get_buf(ctx, SL_COORDS, n * sizeof(int2), &c));
+    R->coords = (int2*)c;
+  }
   CKS(stage_in(ctx, SL_META, r->meta, n, r->mem, &R->meta));
   CKS(stage_in(ctx, SL_OPS, r->ops, (size_t)r->n_ops, r->mem, &R->ops));
   CKS(stage_in(ctx, SL_REFB, r->refb, (size_t)r->n_refb, r->mem, &R->refb));
@@ -467,7 +472,7 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
   int nl = 0;
   size_t n_slots = 0;
   if (R.n > 0 && S.c_hi > S.c_lo) {
-    CK(launch_call_buckets(R, S, hs, (int32_t*)d_rbase, (uint32_t*)d_blen, (uint32_t*)d_boff, d_temp, tb2,
+    CK(launch_call_buckets(R, S, X, hs, (int32_t*)d_rbase, (uint32_t*)d_blen, (uint32_t*)d_boff, d_temp, tb2,
                            ctx->stream, &nl));
     CK(cudaMemcpyAsync(ctx->h_small, (uint32_t*)d_boff + S.c_hi, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

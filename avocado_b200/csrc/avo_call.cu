@@ -42,15 +42,26 @@ __device__ __forceinline__ uint32_t make_record(uint32_t cat, bool fwd, int q, i
 // ---- buckets ------------------------------------------------------------------------------------
 // rbase[j] = first read that can overlap site j (start > site.start - max_span),
 // len[j]   = reads from there up to the first read starting at or after the site's end.
-__global__ void k_site_buckets(DReads R, DSites S, int32_t max_span, int32_t* __restrict__ rbase,
+// first read with start >= key, searched inside the key's bin of the coarse index
+__device__ __forceinline__ int32_t first_read_at(const DReads& R, const DIndex& X, int64_t key) {
+  if (key <= X.win0) return 0;
+  const int32_t bin = idx_bin_floor(X, key);
+  int32_t lo = __ldg(X.ridx + bin), hi = __ldg(X.ridx + min(bin + 1, X.nb));
+  const int32_t k32 = (int32_t)min(key, (int64_t)INT32_MAX);
+  while (lo < hi) {
+    const int32_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(&R.coords[mid].x) < k32) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void k_site_buckets(DReads R, DSites S, DIndex X, int32_t max_span, int32_t* __restrict__ rbase,
                                uint32_t* __restrict__ len) {
   const int32_t j = S.c_lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= S.c_hi) return;
-  const int64_t lo_key = (int64_t)__ldg(S.start + j) - max_span + 1;
-  const int32_t key = (int32_t)max(lo_key, (int64_t)INT32_MIN);
-  const int64_t a = lower_bound_reads(R.meta, 0, R.n, key);
-  const int64_t b = lower_bound_reads(R.meta, a, R.n, __ldg(S.end + j));
-  rbase[j] = (int32_t)a;
+  const int32_t a = first_read_at(R, X, (int64_t)__ldg(S.start + j) - max_span + 1);
+  const int32_t b = max(a, first_read_at(R, X, (int64_t)__ldg(S.end + j)));
+  rbase[j] = a;
   len[j] = (uint32_t)(b - a);
 }
 
@@ -111,43 +122,71 @@ __device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, co
 
 struct JoinedRead { int32_t r, a, b; };
 
-// Join (TreeRegionJoin.scala:175-203): one thread per read.  A cheap index test first (most reads
-// have no site in reach), then Forest.get; the joined reads (~15 %) are appended to a global list.
-// The list order is irrelevant (every record has its own slot), so the append is one shared-memory
-// atomic per warp and one global atomic per block.
-constexpr int JOIN_THREADS = 512;
+// Join (TreeRegionJoin.scala:175-203): persistent warps stride over blocks of 32 reads.  A cheap
+// index test first (most reads have no site in reach), then Forest.get; the joined reads (~15 %) are
+// staged in a per-warp shared-memory buffer and appended to a global list JOIN_FLUSH at a time
+// (one global atomic per flush; the list order is irrelevant: every record has its own slot).
+// No block barrier: a CTA-wide append would put two barriers and a global atomic on the critical
+// path of every 512 reads.
+constexpr int JOIN_THREADS = 256;
+constexpr int JOIN_WARPS = JOIN_THREADS / 32;
+constexpr int JOIN_UNROLL = 2;
+constexpr int JOIN_FLUSH = 96;
+constexpr int JOIN_CAP = JOIN_FLUSH + 32 * JOIN_UNROLL;
+
 __global__ void __launch_bounds__(JOIN_THREADS)
 k_call_join(DReads R, DSites S, DIndex X, JoinedRead* __restrict__ list, int32_t* __restrict__ n_list) {
-  __shared__ int32_t s_count, s_base;
+  __shared__ JoinedRead stage[JOIN_WARPS][JOIN_CAP];
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) s_count = 0;
-  __syncthreads();
-  const int64_t r = (int64_t)blockIdx.x * JOIN_THREADS + threadIdx.x;
-  int32_t a = 0, b = 0;
-  bool joined = false;
-  if (r < R.n) {
-    const int2 se = __ldg(reinterpret_cast<const int2*>(R.meta + r));   // start, end
-    // sites that start in the index bins the read touches, or an earlier site reaching past its start
-    const int32_t hLo = (se.x <= X.win0) ? S.c_lo : __ldg(X.sidx + idx_bin_floor(X, se.x));
-    const int64_t d = (int64_t)se.y - X.win0;
-    const int64_t k = d < 0 ? 0 : d / IDX_G + 1;
-    const int32_t hHi = (k >= X.nb) ? S.c_hi : __ldg(X.sidx + (int32_t)k);
-    if (hLo < hHi || (hLo > S.c_lo && __ldg(S.pme + hLo - 1) > se.x)) {
-      forest_get(S, R.contig, se.x, se.y, hLo, hHi, a, b);
-      joined = a < b;                                     // no overlapping variant: read dropped
+  JoinedRead* st = stage[threadIdx.x >> 5];
+  const unsigned lt = (1u << lane) - 1u;
+  int cnt = 0;
+  auto flush = [&]() {
+    int32_t base = 0;
+    if (lane == 0) base = atomicAdd(n_list, cnt);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    for (int i = lane; i < cnt; i += 32) list[base + i] = st[i];
+    cnt = 0;
+    __syncwarp();
+  };
+  const int64_t n_blocks = (R.n + 31) / 32;
+  const int64_t stride = (int64_t)gridDim.x * JOIN_WARPS * JOIN_UNROLL;
+  for (int64_t blk = ((int64_t)blockIdx.x * JOIN_WARPS + (threadIdx.x >> 5)) * JOIN_UNROLL; blk < n_blocks;
+       blk += stride) {
+    int2 se[JOIN_UNROLL];
+    bool in[JOIN_UNROLL];
+#pragma unroll
+    for (int u = 0; u < JOIN_UNROLL; ++u) {
+      const int64_t r = (blk + u) * 32 + lane;
+      in[u] = r < R.n;
+      se[u] = in[u] ? __ldg(R.coords + r) : make_int2(0, 0);          // start, end
     }
+#pragma unroll
+    for (int u = 0; u < JOIN_UNROLL; ++u) {
+      int32_t a = 0, b = 0;
+      bool joined = false;
+      if (in[u]) {
+        // sites that start in the index bins the read touches, or an earlier site reaching past its start
+        const int32_t hLo = (se[u].x <= X.win0) ? S.c_lo : __ldg(X.sidx + idx_bin_floor(X, se[u].x));
+        const int64_t d = (int64_t)se[u].y - X.win0;
+        const int64_t k = d < 0 ? 0 : d / IDX_G + 1;
+        const int32_t hHi = (k >= X.nb) ? S.c_hi : __ldg(X.sidx + (int32_t)k);
+        if (hLo < hHi || (hLo > S.c_lo && __ldg(S.pme + hLo - 1) > se[u].x)) {
+          forest_get(S, R.contig, se[u].x, se[u].y, hLo, hHi, a, b);
+          joined = a < b;                                   // no overlapping variant: read dropped
+        }
+      }
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, joined);
+      if (joined) {
+        JoinedRead j; j.r = (int32_t)((blk + u) * 32 + lane); j.a = a; j.b = b;
+        st[cnt + __popc(m & lt)] = j;
+      }
+      cnt += __popc(m);
+    }
+    __syncwarp();
+    if (cnt >= JOIN_FLUSH) flush();
   }
-  const unsigned m = __ballot_sync(0xFFFFFFFFu, joined);
-  int32_t wbase = 0;
-  if (m && lane == 0) wbase = atomicAdd(&s_count, __popc(m));
-  wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-  __syncthreads();
-  if (threadIdx.x == 0 && s_count > 0) s_base = atomicAdd(n_list, s_count);
-  __syncthreads();
-  if (joined) {
-    JoinedRead j; j.r = (int32_t)r; j.a = a; j.b = b;
-    list[s_base + wbase + __popc(m & ((1u << lane) - 1u))] = j;
-  }
+  if (cnt > 0) flush();
 }
 
 // Observation + classification: one thread per joined read.
@@ -232,14 +271,14 @@ size_t call_scan_temp_bytes(int32_t n) {
 }
 
 // rbase / blen / boff: [S.n + 1] scratch.  boff[c_hi] (device) = total number of slots.
-cudaError_t launch_call_buckets(const DReads& R, const DSites& S, const BatchStats& hstats, int32_t* rbase,
+cudaError_t launch_call_buckets(const DReads& R, const DSites& S, const DIndex& X, const BatchStats& hstats, int32_t* rbase,
                                 uint32_t* blen, uint32_t* boff, void* d_temp, size_t temp_bytes,
                                 cudaStream_t s, int* n_launches) {
   const int32_t n = S.c_hi - S.c_lo;
   if (n <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(blen + S.c_hi, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
-  k_site_buckets<<<(n + 127) / 128, 128, 0, s>>>(R, S, hstats.max_span, rbase, blen);
+  k_site_buckets<<<(n + 127) / 128, 128, 0, s>>>(R, S, X, hstats.max_span, rbase, blen);
   e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, blen + S.c_lo, boff + S.c_lo, n + 1, s);
   if (e != cudaSuccess) return e;
   if (n_launches) *n_launches += 2;
@@ -258,8 +297,14 @@ cudaError_t launch_call_tiles(const DReads& R, const DSites& S, const DCnv& C, c
     e = cudaMemsetAsync(buckets, 0, n_slots * sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
   }
-  k_call_join<<<(unsigned)((R.n + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, s>>>(
-      R, S, X, (JoinedRead*)joined_list, d_counter);
+  {
+    int bps = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_call_join, JOIN_THREADS, 0);
+    if (e != cudaSuccess) return e;
+    const int64_t want = ((R.n + 31) / 32 + JOIN_WARPS * JOIN_UNROLL - 1) / (JOIN_WARPS * JOIN_UNROLL);
+    const int grid = (int)min(want, (int64_t)num_sms * max(1, bps));
+    k_call_join<<<grid, JOIN_THREADS, 0, s>>>(R, S, X, (JoinedRead*)joined_list, d_counter);
+  }
   int blocks_per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_call_observe, OBS_THREADS, 0);
   if (e != cudaSuccess) return e;

@@ -219,7 +219,7 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
     const int32_t rHi = __ldg(X.ridx + min((tile + 1) * BPT, X.nb));
     // the records whose start lies in this window: every record is owned by exactly one tile as
     // long as the index is monotone (checked here), so the checks below see every record once
-    const int32_t rOwn = verify ? __ldg(X.ridx + min(tile * BPT, X.nb)) : rHi;
+    const int32_t rOwn = __ldg(X.ridx + min(tile * BPT, X.nb));
     if (verify && tid == 0) {
       if (rOwn > rHi || (tile == 0 && rOwn != 0) || (tile == 0 && R.n > 0 && meta_start(R.meta, 0) < X.win0))
         atomicOr(flags, DISC_FLAG_UNSORTED);
@@ -243,9 +243,12 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
     for (int32_t r = rLo + tid; r < rHi; r += DISC_THREADS) {
       const MetaA a = load_meta_a(R.meta, r);
       const MetaB m = load_meta_b(R.meta, r);
-      if (r >= rOwn) {    // verify: sort order and the caller's bounds (avo_batch_stats)
-        if (r > 0 && meta_start(R.meta, r - 1) > a.start) atomicOr(flags, DISC_FLAG_UNSORTED);
-        if (a.end > max_end || (int64_t)a.end - a.start > max_span) atomicOr(flags, DISC_FLAG_BAD_STATS);
+      if (r >= rOwn) {
+        if (R.coords) R.coords[r] = make_int2(a.start, a.end);   // dense (start, end) copy for the join
+        if (verify) {     // sort order and the caller's bounds (avo_batch_stats)
+          if (r > 0 && meta_start(R.meta, r - 1) > a.start) atomicOr(flags, DISC_FLAG_UNSORTED);
+          if (a.end > max_end || (int64_t)a.end - a.start > max_span) atomicOr(flags, DISC_FLAG_BAD_STATS);
+        }
       }
       if ((int64_t)a.end <= wlo || m.n_ops == 0) continue;   // ends before the window / no operators
       const uint32_t w0 = __ldg(R.ops + a.op_off);

@@ -14,6 +14,8 @@ struct DReads {
   int64_t n;
   int32_t contig;
   const avo_read_meta* meta;   // 32-byte record per read (include/avocado_b200.h)
+  int2* coords;                // (start, end) per read: dense copy written by the first kernel that
+                               // streams the records (k_batch_stats / k_discover_tiles), read by the join
   const uint8_t* bases4;
   const uint8_t* quals;
   const uint32_t* ops;
@@ -139,7 +141,7 @@ cudaError_t launch_build_site_index(const DSites& S, const BatchStats& hstats, i
 
 // call: per-site buckets (one slot per read that can overlap the site), observe, reduce
 size_t call_scan_temp_bytes(int32_t n);
-cudaError_t launch_call_buckets(const DReads& R, const DSites& S, const BatchStats& hstats, int32_t* rbase,
+cudaError_t launch_call_buckets(const DReads& R, const DSites& S, const DIndex& X, const BatchStats& hstats, int32_t* rbase,
                                 uint32_t* blen, uint32_t* boff, void* d_temp, size_t temp_bytes,
                                 cudaStream_t s, int* n_launches);
 cudaError_t launch_call_tiles(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,

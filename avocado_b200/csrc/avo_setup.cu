@@ -20,6 +20,7 @@ __global__ void k_batch_stats(DReads R, BatchStats* __restrict__ st) {
     mxe = max(mxe, e);
     mxs = max(mxs, e - s);
     if (i > 0 && meta_start(R.meta, i - 1) > s) uns = 1;
+    if (R.coords) R.coords[i] = make_int2(s, e);
   }
   for (int o = 16; o > 0; o >>= 1) {
     mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));

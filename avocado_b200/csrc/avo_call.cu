@@ -29,7 +29,7 @@ namespace avo {
 constexpr int OBS_THREADS = 256;
 constexpr int MAX_LOCAL_SITES = 32;  // per-read category cache
 #ifndef AVO_CALL_MINB
-#define AVO_CALL_MINB 4
+#define AVO_CALL_MINB 6
 #endif
 
 // record word: [0] valid, [2:1] category, [3] forward strand, [10:4] q', [17:11] mq',

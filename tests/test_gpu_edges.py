@@ -172,3 +172,88 @@ def test_full_size_properties(ctx):
     assert torch.equal(start1[m1], s3.start[:s3.n][m3])
     for k in ("total_cov", "allele_cov", "gq", "qual", "allele_ll", "ref_ll", "fisher"):
         assert torch.equal(bits(snap[k][m1]), bits(c3[k][m3])), k
+
+
+def test_forest_quirk_and_multi_contig_table(oracle, ctx):
+    """Forest.get returns only the contiguous run of overlapping entries around the first probe hit
+    (TreeRegionJoin.scala:74-119), over the GLOBAL sorted table of all contigs.  Long deletions that
+    reach across shorter non-overlapping variants make the result depend on the probe order; the
+    oracle replays it literally, and so must the kernels (fast path + replay)."""
+    from avocado_b200.genotyping import BiallelicGenotyper
+    from avocado_b200.records import AlignmentRecord, Variant
+    rng = np.random.default_rng(17)
+    bases = "ACGT"
+    ref = {c: "".join(bases[i] for i in rng.integers(0, 4, 1400)) for c in ("chrA", "chrB", "chrC")}
+
+    def read(contig, start, length, name, edits=()):
+        seq = list(ref[contig][start:start + length])
+        md, run = "", 0
+        for k in range(length):
+            if k in edits:
+                b = bases[(bases.index(seq[k]) + 1) % 4]
+                md += "%d%s" % (run, seq[k]); run = 0
+                seq[k] = b
+            else:
+                run += 1
+        md += str(run)
+        return AlignmentRecord(readMapped=True, contigName=contig, start=start, end=start + length,
+                               sequence="".join(seq), qual="".join(chr(33 + int(q)) for q in rng.integers(20, 41, length)),
+                               cigar="%dM" % length, mismatchingPositions=md, mapq=int(rng.integers(20, 61)),
+                               readName=name, readNegativeStrand=bool(rng.integers(0, 2)))
+    recs = []
+    for c in ref:
+        for i in range(400):
+            s = int(rng.integers(0, 1300))
+            ln = int(rng.integers(40, 100))
+            ed = set(int(x) for x in rng.integers(0, ln, 2)) if i % 3 == 0 else ()
+            recs.append(read(c, s, min(ln, 1400 - s), "%s_%d" % (c, i), ed))
+    variants = []
+    for c in ref:
+        pos = sorted(set(int(x) for x in rng.integers(5, 1350, 60)))
+        for k, p in enumerate(pos):
+            r = ref[c]
+            if k % 7 == 0:          # long deletion reaching across the next few short variants
+                ln = int(rng.integers(15, 45))
+                variants.append(Variant(c, p, p + ln + 1, r[p:p + ln + 1], r[p]))
+            elif k % 5 == 0:        # insertion
+                variants.append(Variant(c, p, p + 1, r[p], r[p] + "GT"))
+            else:                   # SNV
+                variants.append(Variant(c, p, p + 1, r[p], bases[(bases.index(r[p]) + 1) % 4]))
+    variants = list({v.as_tuple(): v for v in variants}.values())
+    recs.sort(key=lambda r: (r.contigName, r.start))
+    want = oracle.call(oracle.reads_from_dicts([r.as_dict() for r in recs]), [v.as_tuple() for v in variants],
+                       2, [], False, 93, 93, 1)
+    gts = BiallelicGenotyper.call(recs, variants, samples=["s"], ctx=ctx)
+    okey = {(c, int(s), r, a): j for j, (c, s, r, a) in enumerate(
+        zip(want["contigName"], want["start"], want["referenceAllele"], want["alternateAllele"]))}
+    assert {(g.contigName, g.start, g.variant.referenceAllele, g.variant.alternateAllele) for g in gts} == set(okey)
+    assert len(gts) > 100
+    for g in gts:
+        j = okey[(g.contigName, g.start, g.variant.referenceAllele, g.variant.alternateAllele)]
+        assert (g.readDepth, g.referenceReadDepth, g.alternateReadDepth) == \
+            (want["totalCoverage"][j], want["otherCoverage"][j], want["alleleCoverage"][j]), g.variant
+        assert g.genotypeQuality == want["genotypeQuality"][j]
+        assert g.alleles == ["ALT"] * int(want["nAlt"][j]) + ["REF"] * int(want["nRef"][j]) + \
+            ["OTHER_ALT"] * int(want["nOther"][j])
+        cn = int(want["copyNumber"][j])
+        assert g.genotypeLikelihoods == list(want["genotypeLikelihoods"][j][:cn + 1])
+    # the quirk is really exercised: for some reads Forest.get misses variants they overlap
+    regions = sorted((v.contigName, v.start, v.end) for v in variants)
+    quirky = 0
+    for r in recs:
+        got = set(oracle.forest_get(regions, (r.contigName, r.start, r.end)))
+        full = {i for i, (c, s, e) in enumerate(regions) if c == r.contigName and s < r.end and e > r.start}
+        quirky += got != full
+    assert quirky > 20
+    # gVCF rows over the same multi-contig table
+    want_all = oracle.call(oracle.reads_from_dicts([r.as_dict() for r in recs]), [v.as_tuple() for v in variants],
+                           2, [], True, 93, 93, 1)
+    gts_all = BiallelicGenotyper.call(recs, variants, scoreAllSites=True, samples=["s"], ctx=ctx)
+    okey = {(c, int(s), r, a): j for j, (c, s, r, a) in enumerate(
+        zip(want_all["contigName"], want_all["start"], want_all["referenceAllele"], want_all["alternateAllele"]))}
+    assert {(g.contigName, g.start, g.variant.referenceAllele, g.variant.alternateAllele) for g in gts_all} == set(okey)
+    for g in gts_all:
+        j = okey[(g.contigName, g.start, g.variant.referenceAllele, g.variant.alternateAllele)]
+        assert g.readDepth == want_all["totalCoverage"][j] and g.genotypeQuality == want_all["genotypeQuality"][j]
+        cn = int(want_all["copyNumber"][j])
+        assert g.genotypeLikelihoods == list(want_all["genotypeLikelihoods"][j][:cn + 1])

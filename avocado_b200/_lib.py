@@ -34,11 +34,11 @@ P = C.c_void_p
 
 
 class ReadBatchStruct(C.Structure):
-    _fields_ = [("n_reads", C.c_int64), ("n_bases", C.c_int64), ("n_ops", C.c_int64),
+    _fields_ = [("n_reads", C.c_int64), ("n_blocks", C.c_int64), ("n_ops", C.c_int64),
                 ("n_refb", C.c_int64), ("contig_id", C.c_int32), ("mem", C.c_int32),
                 ("stats_min_start", C.c_int32), ("stats_max_end", C.c_int32),
                 ("stats_max_span", C.c_int32), ("stats_valid", C.c_int32),
-                ("meta", P), ("bases4", P), ("quals", P), ("ops", P), ("refb", P)]
+                ("meta", P), ("payload", P), ("ops", P), ("refb", P)]
 
 
 class SitesStruct(C.Structure):
@@ -100,8 +100,8 @@ class TextReadsStruct(C.Structure):
 
 
 class PackedOutStruct(C.Structure):
-    _fields_ = [("n_reads", C.c_int64), ("n_bases", C.c_int64), ("n_ops", C.c_int64),
-                ("n_refb", C.c_int64), ("meta", P), ("bases4", P), ("quals", P), ("ops", P),
+    _fields_ = [("n_reads", C.c_int64), ("n_blocks", C.c_int64), ("n_ops", C.c_int64),
+                ("n_refb", C.c_int64), ("meta", P), ("payload", P), ("ops", P),
                 ("refb", P), ("source_index", P)]
 
 

@@ -24,8 +24,12 @@ META_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("seq_off", "<u4"), ("o
                        ("qhead", "<u4"), ("l_seq", "<u4")])
 assert META_DTYPE.itemsize == 32
 
-READ_COLUMNS = [("meta", META_DTYPE), ("bases4", np.uint8), ("quals", np.uint8), ("ops", np.uint32),
-                ("refb", np.uint8)]
+READ_COLUMNS = [("meta", META_DTYPE), ("payload", np.uint8), ("ops", np.uint32), ("refb", np.uint8)]
+BLOCK_BASES, BLOCK_BYTES = 20, 32     # payload: 20 bases (4 bit) + their 20 qualities per 32-byte block
+
+
+def blocks_of(l_seq):
+    return (l_seq + BLOCK_BASES - 1) // BLOCK_BASES
 
 
 def _ptr(a):
@@ -45,13 +49,12 @@ def _is_device(a):
 class ReadBatch:
     """Reads of one contig, sorted by start (include/avocado_b200.h: avo_read_batch)."""
     n_reads: int
-    n_bases: int
+    n_blocks: int
     n_ops: int
     n_refb: int
     contig_id: int = 0
     meta: object = None      # host: structured array of META_DTYPE; device: uint8 tensor [n * 32]
-    bases4: object = None
-    quals: object = None
+    payload: object = None   # [n_blocks * 32] bytes
     ops: object = None
     refb: object = None
     source_index: Optional[np.ndarray] = None
@@ -85,7 +88,7 @@ class ReadBatch:
 
     def as_struct(self):
         s = L.ReadBatchStruct()
-        s.n_reads, s.n_bases, s.n_ops, s.n_refb = self.n_reads, self.n_bases, self.n_ops, self.n_refb
+        s.n_reads, s.n_blocks, s.n_ops, s.n_refb = self.n_reads, self.n_blocks, self.n_ops, self.n_refb
         s.contig_id = self.contig_id
         s.mem = L.MEM_DEVICE if self.on_device else L.MEM_HOST
         if self.stats is not None:
@@ -106,7 +109,7 @@ class ReadBatch:
     def to_device(self, device="cuda:0", pinned=False):
         import torch
         kw = {}
-        out = ReadBatch(self.n_reads, self.n_bases, self.n_ops, self.n_refb, self.contig_id)
+        out = ReadBatch(self.n_reads, self.n_blocks, self.n_ops, self.n_refb, self.contig_id)
         for name, _ in READ_COLUMNS:
             a = getattr(self, name)
             t = torch.from_numpy(_torch_view(a))
@@ -119,7 +122,7 @@ class ReadBatch:
     def to_host(self):
         if not self.on_device:
             return self
-        out = ReadBatch(self.n_reads, self.n_bases, self.n_ops, self.n_refb, self.contig_id)
+        out = ReadBatch(self.n_reads, self.n_blocks, self.n_ops, self.n_refb, self.contig_id)
         for name, dt in READ_COLUMNS:
             setattr(out, name, _from_torch(getattr(self, name), dt))
         out.stats = self.stats
@@ -131,18 +134,16 @@ class ReadBatch:
         m = self.meta[lo:hi].copy()
         if hi > lo:
             last = self.meta[hi - 1]
-            b0 = int(m["seq_off"][0]); b1 = int(last["seq_off"]) + ((int(last["l_seq"]) + 1) & ~1)
+            b0 = int(m["seq_off"][0]); b1 = int(last["seq_off"]) + blocks_of(int(last["l_seq"]))
             o0 = int(m["op_off"][0]); o1 = int(last["op_off"]) + int(last["n_ops"])
             f0 = int(m["refb_off"][0])
             f1 = int(self.meta[hi]["refb_off"]) if hi < self.n_reads else self.n_refb
         else:
             b0 = b1 = o0 = o1 = f0 = f1 = 0
-        assert b0 % 2 == 0
         m["seq_off"] -= np.uint32(b0); m["op_off"] -= np.uint32(o0); m["refb_off"] -= np.uint32(f0)
         out = ReadBatch(hi - lo, b1 - b0, o1 - o0, f1 - f0, self.contig_id)
         out.meta = m
-        out.bases4 = np.ascontiguousarray(self.bases4[b0 // 2:(b1 + 1) // 2])
-        out.quals = np.ascontiguousarray(self.quals[b0:b1])
+        out.payload = np.ascontiguousarray(self.payload[b0 * BLOCK_BYTES:b1 * BLOCK_BYTES])
         out.ops = np.ascontiguousarray(self.ops[o0:o1])
         out.refb = np.ascontiguousarray(self.refb[f0:f1])
         return out.with_stats() if self.stats is not None else out
@@ -320,19 +321,18 @@ def pack_reads(records: Sequence[AlignmentRecord], contig_id=0, keep=None, sort=
     if rc != 0:
         raise L.AvocadoError(rc, "avo_pack_bounds failed")
     out = L.PackedOutStruct()
-    arrs = dict(meta=np.zeros(max(nr.value, 1), META_DTYPE), bases4=np.zeros(nb.value // 2 + 1, np.uint8),
-                quals=np.zeros(max(nb.value, 1), np.uint8), ops=np.zeros(max(no.value, 1), np.uint32),
+    arrs = dict(meta=np.zeros(max(nr.value, 1), META_DTYPE), payload=np.zeros(max(nb.value, 1) * BLOCK_BYTES, np.uint8),
+                ops=np.zeros(max(no.value, 1), np.uint32),
                 refb=np.zeros(max(nf.value, 1), np.uint8), source_index=np.zeros(max(nr.value, 1), np.int64))
-    out.n_reads, out.n_bases, out.n_ops, out.n_refb = nr.value, nb.value, no.value, nf.value
+    out.n_reads, out.n_blocks, out.n_ops, out.n_refb = nr.value, nb.value, no.value, nf.value
     for k, a in arrs.items():
         setattr(out, k, a.ctypes.data)
     rc = lib.avo_pack_reads(C.byref(t), C.byref(out))
     if rc != 0:
         raise L.AvocadoError(rc, "avo_pack_reads failed")
-    b = ReadBatch(out.n_reads, out.n_bases, out.n_ops, out.n_refb, contig_id)
+    b = ReadBatch(out.n_reads, out.n_blocks, out.n_ops, out.n_refb, contig_id)
     b.meta = arrs["meta"][:out.n_reads]
-    b.bases4 = arrs["bases4"][:(out.n_bases + 1) // 2 or 1]
-    b.quals = arrs["quals"][:max(out.n_bases, 1)]
+    b.payload = arrs["payload"][:max(out.n_blocks, 1) * BLOCK_BYTES]
     b.ops = arrs["ops"][:max(out.n_ops, 1)]
     b.refb = arrs["refb"][:max(out.n_refb, 1)]
     b.source_index = np.array([idx[j] for j in arrs["source_index"][:out.n_reads]], np.int64)
@@ -355,7 +355,7 @@ def synth_params(**kw) -> "L.SynthParamsStruct":
 
 def _packed_out(arrs, n, nb, no, nf):
     out = L.PackedOutStruct()
-    out.n_reads, out.n_bases, out.n_ops, out.n_refb = n, nb, no, nf
+    out.n_reads, out.n_blocks, out.n_ops, out.n_refb = n, nb, no, nf
     for k, a in arrs.items():
         setattr(out, k, _ptr(a))
     out.source_index = None
@@ -369,10 +369,9 @@ def synth_host(p, first=0, n=None, contig_id=0) -> ReadBatch:
     rc = lib.avo_synth_host(C.byref(p), first, n, C.byref(no), C.byref(nf), None)
     if rc != 0:
         raise L.AvocadoError(rc, "avo_synth_host(count) failed")
-    lpad = (p.read_len + 1) & ~1
-    nb = n * lpad
-    arrs = dict(meta=np.zeros(n, META_DTYPE), bases4=np.zeros(nb // 2 + 1, np.uint8),
-                quals=np.zeros(max(nb, 1), np.uint8), ops=np.zeros(max(no.value, 1), np.uint32),
+    nb = n * blocks_of(p.read_len)
+    arrs = dict(meta=np.zeros(n, META_DTYPE), payload=np.zeros(max(nb, 1) * BLOCK_BYTES, np.uint8),
+                ops=np.zeros(max(no.value, 1), np.uint32),
                 refb=np.zeros(max(nf.value, 1), np.uint8))
     out = _packed_out(arrs, n, nb, no.value, nf.value)
     rc = lib.avo_synth_host(C.byref(p), first, n, None, None, C.byref(out))
@@ -397,11 +396,9 @@ def synth_device(p, first=0, n=None, contig_id=0, device="cuda:0") -> ReadBatch:
                                   C.byref(no), C.byref(nf), None, stream)
         if rc != 0:
             raise L.AvocadoError(rc, "avo_synth_device(count) failed")
-        lpad = (p.read_len + 1) & ~1
-        nb = n * lpad
+        nb = n * blocks_of(p.read_len)
         arrs = dict(meta=_device_empty(n * 32, np.uint8, device),
-                    bases4=_device_empty(nb // 2 + 1, np.uint8, device),
-                    quals=_device_empty(nb, np.uint8, device),
+                    payload=_device_empty(nb * BLOCK_BYTES, np.uint8, device),
                     ops=_device_empty(no.value, np.uint32, device),
                     refb=_device_empty(nf.value, np.uint8, device))
         out = _packed_out(arrs, n, nb, no.value, nf.value)

@@ -186,15 +186,14 @@ k_as_tiles(DReads R, DSites S, DCnv C, DCallParams P, DResults O, int32_t* __res
       if (code == AVO_OP_HARDCLIP) continue;
       if (code == AVO_OP_MATCH || code == AVO_OP_MISMATCH) {
         if (p >= pos && p < pos + len) {
-          const uint32_t bi = ma.seq_off + ridx + (uint32_t)(p - pos);
           observe(ma.start, ma.end, J.a, J.b, 1, (scov >> lane) & 1u, code == AVO_OP_MATCH,
-                  (int32_t)__ldg(R.quals + bi), mb.mapq, fwd);
+                  (int32_t)pl_qual(R.payload, ma.seq_off, ridx + (uint32_t)(p - pos)), mb.mapq, fwd);
         }
         pos += len; ridx += len;
       } else if (code == AVO_OP_INS) {
         if (p == pos - 1)
           observe(ma.start, ma.end, J.a, J.b, 1, (scov >> lane) & 1u, false,
-                  ins_quality(R.quals, ma.seq_off + ridx, len), mb.mapq, fwd);
+                  ins_quality(R.payload, ma.seq_off, ridx, len), mb.mapq, fwd);
         ridx += len;
       } else if (code == AVO_OP_DEL) {
         if (p == pos) observe(ma.start, ma.end, J.a, J.b, len, true, false, -1, mb.mapq, fwd);

@@ -19,13 +19,13 @@ namespace {
 constexpr int32_t LNK_N = 1 << 16;
 
 enum Slot {
-  SL_META, SL_COORDS, SL_BASES, SL_QUALS, SL_OPS, SL_REFB,
+  SL_META, SL_COORDS, SL_PAYLOAD, SL_OPS, SL_REFB,
   SL_S_CONTIG, SL_S_START, SL_S_REFLEN, SL_S_ALTLEN, SL_S_AOFF, SL_S_ALLELES, SL_S_END, SL_S_PME,
   SL_S_COUNT,
   SL_CNV, SL_STATS, SL_SMALL, SL_RIDX, SL_SIDX, SL_TEMP, SL_LUT,
   SL_RES,                      // one block holding every result column
   SL_U_START, SL_U_REFLEN, SL_U_ALTLEN, SL_U_COUNT, SL_U_SRC,
-  SL_L_POS, SL_L_LENS, SL_L_NIBS, SL_L_SRC, SL_L_HASH,
+  SL_L_POS, SL_L_LENS, SL_L_NIBS, SL_L_SRC, SL_L_BLK, SL_L_HASH,
   SL_C_RBASE, SL_C_BLEN, SL_C_BOFF, SL_C_BUCKETS,
   SL_AS_FLAG, SL_AS_JPOS, SL_AS_JR, SL_AS_JIDX, SL_AS_COVER, SL_AS_SCOVER, SL_AS_WCOUNT, SL_AS_WBASE,
   SL_AS_RES, SL_AS_START,
@@ -127,19 +127,19 @@ int validate_reads(avo_ctx* ctx, const avo_read_batch* r) {
   if (!r) return fail(ctx, AVO_E_INVALID, "reads is NULL");
   if (r->n_reads < 0 || r->n_reads >= (int64_t)INT32_MAX)
     return fail(ctx, AVO_E_INVALID, "n_reads out of range (must be < 2^31 per batch)");
-  if (r->n_bases < 0 || r->n_bases > (int64_t)UINT32_MAX || r->n_ops < 0 ||
+  if (r->n_blocks < 0 || r->n_blocks > (int64_t)UINT32_MAX || r->n_ops < 0 ||
       r->n_ops > (int64_t)UINT32_MAX || r->n_refb < 0 || r->n_refb > (int64_t)INT32_MAX)
     return fail(ctx, AVO_E_INVALID, "batch totals must fit 32-bit offsets; split the batch");
   if (r->n_reads > 0 && !r->meta) return fail(ctx, AVO_E_INVALID, "read batch has no meta column");
-  if ((r->n_bases > 0 && (!r->bases4 || !r->quals)) || (r->n_ops > 0 && !r->ops) ||
+  if ((r->n_blocks > 0 && !r->payload) || (r->n_ops > 0 && !r->ops) ||
       (r->n_refb > 0 && !r->refb))
     return fail(ctx, AVO_E_INVALID, "read batch has NULL columns");
   if (r->mem != AVO_MEM_HOST && r->mem != AVO_MEM_DEVICE) return fail(ctx, AVO_E_INVALID, "bad reads->mem");
   return AVO_OK;
 }
 
-// sparse: the mode reads bases4 / quals only at variant sites and indels, so a page-locked host
-// batch keeps them where they are and the kernels fetch single sectors over PCIe
+// sparse: the mode reads the payload only at variant sites and indels, so a page-locked host
+// batch keeps it where it is and the kernels fetch single sectors over PCIe
 int upload_reads(avo_ctx* ctx, const avo_read_batch* r, bool sparse, DReads* R) {
   const size_t n = (size_t)r->n_reads;
   R->n = r->n_reads;
@@ -152,17 +152,15 @@ int upload_reads(avo_ctx* ctx, const avo_read_batch* r, bool sparse, DReads* R) 
   CKS(stage_in(ctx, SL_META, r->meta, n, r->mem, &R->meta));
   CKS(stage_in(ctx, SL_OPS, r->ops, (size_t)r->n_ops, r->mem, &R->ops));
   CKS(stage_in(ctx, SL_REFB, r->refb, (size_t)r->n_refb, r->mem, &R->refb));
-  if (sparse && r->mem == AVO_MEM_HOST && r->n_bases > 0) {
-    const uint8_t* b = mapped_alias(r->bases4);
-    const uint8_t* q = mapped_alias(r->quals);
-    if (b && q) {
-      R->bases4 = b; R->quals = q;
+  if (sparse && r->mem == AVO_MEM_HOST && r->n_blocks > 0) {
+    const uint8_t* b = mapped_alias(r->payload);
+    if (b) {
+      R->payload = b;
       ctx->timing.payload_in_place = 1;
       return AVO_OK;
     }
   }
-  CKS(stage_in(ctx, SL_BASES, r->bases4, (size_t)(r->n_bases + 1) / 2, r->mem, &R->bases4));
-  CKS(stage_in(ctx, SL_QUALS, r->quals, (size_t)r->n_bases, r->mem, &R->quals));
+  CKS(stage_in(ctx, SL_PAYLOAD, r->payload, (size_t)r->n_blocks * AVO_BLOCK_BYTES, r->mem, &R->payload));
   return AVO_OK;
 }
 
@@ -590,6 +588,7 @@ int discover_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, bool 
     CKS(get_buf(ctx, SL_L_LENS, (size_t)lcap * 4, &q)); Lst.lens = (uint32_t*)q;
     CKS(get_buf(ctx, SL_L_NIBS, (size_t)lcap * 4, &q)); Lst.nibs = (uint32_t*)q;
     CKS(get_buf(ctx, SL_L_SRC, (size_t)lcap * 4, &q)); Lst.src = (uint32_t*)q;
+    CKS(get_buf(ctx, SL_L_BLK, (size_t)lcap * 4, &q)); Lst.blk = (uint32_t*)q;
     CKS(get_buf(ctx, SL_L_HASH, (size_t)lcap * 4, &q)); Lst.hash = (uint32_t*)q;
     Lst.n = small + 11;
     uint32_t tsize = 1024;

@@ -10,6 +10,25 @@ __device__ __forceinline__ uint32_t nib_at(const uint8_t* __restrict__ p, uint32
   return (i & 1u) ? (b & 15u) : (b >> 4);
 }
 
+// Payload accessors: base / quality i of the read whose first block is blk0 (one sector for both)
+__device__ __forceinline__ const uint8_t* pl_block(const uint8_t* __restrict__ pl, uint32_t blk0, uint32_t i,
+                                                    uint32_t& w) {
+  const uint32_t c = i / (uint32_t)AVO_BLOCK_BASES;
+  w = i - c * (uint32_t)AVO_BLOCK_BASES;
+  return pl + ((size_t)(blk0 + c) << 5);
+}
+__device__ __forceinline__ uint32_t pl_base(const uint8_t* __restrict__ pl, uint32_t blk0, uint32_t i) {
+  uint32_t w;
+  const uint8_t* b = pl_block(pl, blk0, i, w);
+  const uint32_t v = __ldg(b + (w >> 1));
+  return (w & 1u) ? (v & 15u) : (v >> 4);
+}
+__device__ __forceinline__ uint32_t pl_qual(const uint8_t* __restrict__ pl, uint32_t blk0, uint32_t i) {
+  uint32_t w;
+  const uint8_t* b = pl_block(pl, blk0, i, w);
+  return __ldg(b + 10 + w);
+}
+
 // The 32-byte read record is fetched as two 16-byte halves.
 struct MetaA { int32_t start, end; uint32_t seq_off, op_off; };
 struct MetaB { uint32_t refb_off, n_ops, mapq, flags, qhead, l_seq; };

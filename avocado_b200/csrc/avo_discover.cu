@@ -64,7 +64,7 @@ __device__ __forceinline__ void walk_mismatch(const DReads& R, uint32_t len, int
   // qual(i), not qual(idx + i): the first four qualities of the read travel in the record
   if ((int32_t)(qhead & 255u) >= thr) snp(pos, (uint32_t)__ldg(R.refb + rb));
   for (uint32_t i = 1; i < len; ++i) {
-    const int32_t q = (i < 4) ? (int32_t)((qhead >> (8 * i)) & 255u) : (int32_t)__ldg(R.quals + sb + i);
+    const int32_t q = (i < 4) ? (int32_t)((qhead >> (8 * i)) & 255u) : (int32_t)pl_qual(R.payload, sb, i);
     if (q >= thr) snp(pos + (int32_t)i, (uint32_t)__ldg(R.refb + rb + i));
   }
 }
@@ -119,17 +119,16 @@ struct __align__(16) DiscSmem {
 
 __device__ __forceinline__ void disc_indel_append(const DReads& R, const DIndelList& L, int32_t pos,
                                                   int32_t ref_len, int32_t alt_len, uint32_t lastRef,
-                                                  uint32_t anchor, uint32_t src, bool is_del) {
+                                                  uint32_t anchor, uint32_t src, uint32_t blk, bool is_del) {
   const int32_t slot = atomicAdd(L.n, 1);
   if (slot >= L.capacity) return;   // counted; the host grows the list and reruns
   uint32_t h = mix32(0x811C9DC5u, (uint32_t)pos);
   h = mix32(h, ((uint32_t)ref_len << 16) | (uint32_t)alt_len);
   h = mix32(h, (lastRef << 4) | anchor);
   const int n = is_del ? ref_len - 1 : alt_len - 1;
-  const uint8_t* buf = is_del ? R.refb : R.bases4;
   uint32_t acc = 0;
   for (int i = 0; i < n; ++i) {
-    acc = (acc << 4) | nib_at(buf, src + i);
+    acc = (acc << 4) | (is_del ? nib_at(R.refb, src + i) : pl_base(R.payload, blk, src + i));
     if ((i & 7) == 7) { h = mix32(h, acc); acc = 0; }
   }
   h = mix32(h, acc);
@@ -137,6 +136,7 @@ __device__ __forceinline__ void disc_indel_append(const DReads& R, const DIndelL
   L.lens[slot] = ((uint32_t)ref_len << 16) | (uint32_t)alt_len;
   L.nibs[slot] = (lastRef << 4) | anchor;
   L.src[slot] = src;
+  L.blk[slot] = blk;
   L.hash[slot] = h;
 }
 
@@ -157,7 +157,7 @@ __device__ void disc_handle_indel(const DReads& R, const DIndelList& L, int32_t 
       if (code == AVO_OP_SOFTCLIP || code == AVO_OP_INS) idx += len;
       else if (code == AVO_OP_DEL) { pos += (int32_t)len; rb += (len + 1) >> 1; }
     } else if (code == AVO_OP_MATCH) {                                    // :194-197
-      last = sb + idx + len - 1; last_refb = false;
+      last = idx + len - 1; last_refb = false;     // index within the read
       pos += (int32_t)len; idx += len;
     } else if (code == AVO_OP_MISMATCH) {                                 // :198-210
       last = 2 * (rb + len - 1); last_refb = true;
@@ -172,16 +172,16 @@ __device__ void disc_handle_indel(const DReads& R, const DIndelList& L, int32_t 
   }
   const uint32_t op = __ldg(R.ops + a.op_off + k);
   const uint32_t len = op >> 4;
-  const uint32_t lastRef = last_refb ? nib_at(R.refb, last) : nib_at(R.bases4, last);
-  const uint32_t anchor = nib_at(R.bases4, sb + idx - 1);
+  const uint32_t lastRef = last_refb ? nib_at(R.refb, last) : pl_base(R.payload, sb, last);
+  const uint32_t anchor = pl_base(R.payload, sb, idx - 1);
   if ((op & 15u) == AVO_OP_INS) {                                         // :215-228
     int sum = 0;
-    for (uint32_t j = 0; j <= len; ++j) sum += __ldg(R.quals + sb + idx - 1 + j);
+    for (uint32_t j = 0; j <= len; ++j) sum += (int)pl_qual(R.payload, sb, idx - 1 + j);
     if (sum / (int)len < thr) return;
-    disc_indel_append(R, L, pos - 1, 1, (int32_t)len + 1, lastRef, anchor, sb + idx, false);
+    disc_indel_append(R, L, pos - 1, 1, (int32_t)len + 1, lastRef, anchor, idx, sb, false);
   } else {                                                                // :229-242
-    if ((int32_t)__ldg(R.quals + sb + idx - 1) < thr) return;
-    disc_indel_append(R, L, pos - 1, (int32_t)len + 1, 1, lastRef, anchor, 2 * rb, true);
+    if ((int32_t)pl_qual(R.payload, sb, idx - 1) < thr) return;
+    disc_indel_append(R, L, pos - 1, (int32_t)len + 1, 1, lastRef, anchor, 2 * rb, 0u, true);
   }
 }
 
@@ -437,10 +437,15 @@ __device__ __forceinline__ bool indel_equal(const DReads& R, const DIndelList& L
   const int ref_len = (int)(lens >> 16), alt_len = (int)(lens & 0xFFFFu);
   const bool is_del = ref_len > 1;
   const int n = is_del ? ref_len - 1 : alt_len - 1;
-  const uint8_t* buf = is_del ? R.refb : R.bases4;
   const uint32_t sa = L.src[a], sb = L.src[b];
-  for (int i = 0; i < n; ++i)
-    if (nib_at(buf, sa + i) != nib_at(buf, sb + i)) return false;
+  if (is_del) {
+    for (int i = 0; i < n; ++i)
+      if (nib_at(R.refb, sa + i) != nib_at(R.refb, sb + i)) return false;
+  } else {
+    const uint32_t ba = L.blk[a], bb = L.blk[b];
+    for (int i = 0; i < n; ++i)
+      if (pl_base(R.payload, ba, sa + i) != pl_base(R.payload, bb, sb + i)) return false;
+  }
   return true;
 }
 
@@ -526,7 +531,7 @@ __device__ __forceinline__ uint32_t survivor_nib(const DReads& R, const DIndelLi
   }
   if (t == 0) return nibs >> 4;        // insertion: lastRef | anchor + inserted bases
   if (t == 1) return nibs & 15u;
-  return nib_at(R.bases4, L.src[rec] + (uint32_t)(t - 2));
+  return pl_base(R.payload, L.blk[rec], L.src[rec] + (uint32_t)(t - 2));
 }
 
 __global__ void k_survivor_keys(DDiscoverOut U, int32_t n, int32_t min_start,

@@ -16,8 +16,7 @@ struct DReads {
   const avo_read_meta* meta;   // 32-byte record per read (include/avocado_b200.h)
   int2* coords;                // (start, end) per read: dense copy written by the first kernel that
                                // streams the records (k_batch_stats / k_discover_tiles), read by the join
-  const uint8_t* bases4;
-  const uint8_t* quals;
+  const uint8_t* payload;      // 32-byte blocks: 20 bases (4 bit) + their 20 qualities
   const uint32_t* ops;
   const uint8_t* refb;
 };
@@ -190,7 +189,8 @@ struct DIndelList {
   int32_t* pos;
   uint32_t* lens;       // (ref_len << 16) | alt_len
   uint32_t* nibs;       // (lastRef nibble << 4) | anchor (alt[0] / read base) nibble
-  uint32_t* src;        // INS: global base index of the first inserted base; DEL: nibble index (2 * byte) into refb
+  uint32_t* src;        // INS: index (within the read) of the first inserted base; DEL: nibble index (2 * byte) into refb
+  uint32_t* blk;        // INS: the read's first payload block
   uint32_t* hash;
 };
 

@@ -14,7 +14,7 @@ enum : uint32_t { CAT_REF = 0, CAT_ALT = 1, CAT_OTHER = 2, CAT_NONREF = 3, CAT_N
 
 struct ReadCtx {
   int32_t start, end;
-  uint32_t sb;  // first base (global base index)
+  uint32_t sb;  // first payload block of the read
   uint32_t ob;  // first op
   uint32_t no;  // number of ops
   uint32_t mapq;
@@ -25,9 +25,9 @@ struct ReadCtx {
 struct Cls { uint32_t cat; int32_t q; };
 
 // mean quality of an insertion (Observer.scala:101-103): integer division
-__device__ __forceinline__ int32_t ins_quality(const uint8_t* __restrict__ quals, uint32_t b, int len) {
+__device__ __forceinline__ int32_t ins_quality(const uint8_t* __restrict__ pl, uint32_t blk0, uint32_t b, int len) {
   int sum = 0;
-  for (int i = 0; i < len; ++i) sum += __ldg(quals + b + i);
+  for (int i = 0; i < len; ++i) sum += (int)pl_qual(pl, blk0, b + (uint32_t)i);
   return sum / len;
 }
 
@@ -61,21 +61,21 @@ __device__ inline Cls classify(const DReads& R, const ReadCtx& rc, int32_t vs, i
       if (lo < hi) {
         const bool isref = (code == AVO_OP_MATCH);
         for (int32_t p = lo; p < hi; ++p) {
-          const uint32_t bi = rc.sb + ridx + (uint32_t)(p - pos);
+          const uint32_t bi = ridx + (uint32_t)(p - pos);   // index within the read
           const bool first = (n_obs == 0);
           ++n_obs; ++n_nonempty;
           all_isref = all_isref && isref;
           if (first || insVar) {
-            const uint32_t b = nib_at(R.bases4, bi);
+            const uint32_t b = pl_base(R.payload, rc.sb, bi);
             if (first) {
               head_isref = isref;
-              head_q = __ldg(R.quals + bi);
+              head_q = (int32_t)pl_qual(R.payload, rc.sb, bi);
               head_eq_alt = (alt_len == 1 && b == nib_at(alleles4, altoff));
             }
             if (insVar) {
               const bool eq = (alt_len == 2 && b == nib_at(alleles4, altoff + 1));
               if (eq) {
-                if (n_ins_eq == 0) { inseq_q = __ldg(R.quals + bi); inseq_isref = isref; }
+                if (n_ins_eq == 0) { inseq_q = (int32_t)pl_qual(R.payload, rc.sb, bi); inseq_isref = isref; }
                 ++n_ins_eq;
               } else if (lead_kind == 0) { lead_kind = 1; lead_first = b; }
             }
@@ -90,20 +90,20 @@ __device__ inline Cls classify(const DReads& R, const ReadCtx& rc, int32_t vs, i
         all_isref = false;
         if (first) {
           head_isref = false;
-          head_q = ins_quality(R.quals, rc.sb + ridx, len);
+          head_q = ins_quality(R.payload, rc.sb, ridx, len);
           bool eq = (len == alt_len);
           for (int i = 0; eq && i < len; ++i)
-            eq = nib_at(R.bases4, rc.sb + ridx + i) == nib_at(alleles4, altoff + i);
+            eq = pl_base(R.payload, rc.sb, ridx + i) == nib_at(alleles4, altoff + i);
           head_eq_alt = eq;
         }
         if (insVar) {
           bool eq = (len == alt_len - 1);
           for (int i = 0; eq && i < len; ++i)
-            eq = nib_at(R.bases4, rc.sb + ridx + i) == nib_at(alleles4, altoff + 1 + i);
+            eq = pl_base(R.payload, rc.sb, ridx + i) == nib_at(alleles4, altoff + 1 + i);
           if (eq) {
-            if (n_ins_eq == 0) { inseq_q = ins_quality(R.quals, rc.sb + ridx, len); inseq_isref = false; }
+            if (n_ins_eq == 0) { inseq_q = ins_quality(R.payload, rc.sb, ridx, len); inseq_isref = false; }
             ++n_ins_eq;
-          } else if (lead_kind == 0) { lead_kind = 1; lead_first = nib_at(R.bases4, rc.sb + ridx); }
+          } else if (lead_kind == 0) { lead_kind = 1; lead_first = pl_base(R.payload, rc.sb, ridx); }
         }
       }
       ridx += len;

@@ -185,21 +185,21 @@ bool kept(const avo_text_reads* in, int64_t i) {
 
 extern "C" {
 
-int avo_pack_bounds(const avo_text_reads* in, int64_t* n_reads, int64_t* n_bases, int64_t* n_ops,
+int avo_pack_bounds(const avo_text_reads* in, int64_t* n_reads, int64_t* n_blocks, int64_t* n_ops,
                     int64_t* n_refb) {
-  if (!in || !n_reads || !n_bases || !n_ops || !n_refb) return AVO_E_INVALID;
+  if (!in || !n_reads || !n_blocks || !n_ops || !n_refb) return AVO_E_INVALID;
   int64_t r = 0, b = 0, o = 0, f = 0;
   for (int64_t i = 0; i < in->n; ++i) {
     if (!kept(in, i)) continue;
     ++r;
-    b += ((in->seq_off[i + 1] - in->seq_off[i]) + 1) & ~(int64_t)1;   // reads start on even indices
+    b += ((in->seq_off[i + 1] - in->seq_off[i]) + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES;   // payload blocks
     // every op needs at least one CIGAR character pair or one MD character
     const int64_t c = in->cigar_off[i + 1] - in->cigar_off[i];
     const int64_t m = in->md_off[i + 1] - in->md_off[i];
     o += c / 2 + 1 + 2 * m;
     f += m + 1;
   }
-  *n_reads = r; *n_bases = b; *n_ops = o; *n_refb = f;
+  *n_reads = r; *n_blocks = b; *n_ops = o; *n_refb = f;
   return AVO_OK;
 }
 
@@ -228,8 +228,8 @@ int avo_pack_reads(const avo_text_reads* in, avo_packed_out* out) {
     // whose strings are too short would crash the reference job; it is dropped here instead
     if (ok && ((int64_t)need > lseq || (int64_t)need > lqual)) ok = false;
     if (!ok || sc.ops.size() > 0xFFFFu) { sc.ops.clear(); sc.refb.clear(); }
-    const uint64_t lpad = ((uint64_t)lseq + 1) & ~1ull;       // reads start on even base indices
-    if ((int64_t)(nb + lpad) > out->n_bases || (int64_t)(no + sc.ops.size()) > out->n_ops ||
+    const uint64_t lpad = ((uint64_t)lseq + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES;   // payload blocks of the read
+    if ((int64_t)(nb + lpad) > out->n_blocks || (int64_t)(no + sc.ops.size()) > out->n_ops ||
         (int64_t)(nf + sc.refb.size()) > out->n_refb)
       return AVO_E_CAPACITY;
     if (nb + lpad > 0xFFFFFFFFull) return AVO_E_INVALID;   // split the batch
@@ -246,13 +246,15 @@ int avo_pack_reads(const avo_text_reads* in, avo_packed_out* out) {
     m.l_seq = (uint32_t)lseq;
     m.qhead = 0;
     if (out->source_index) out->source_index[r] = i;
-    for (int64_t k = 0; k < (int64_t)lpad; ++k) {
-      const uint64_t bi = nb + (uint64_t)k;
-      const uint8_t nibv = k < lseq ? NIB.t[(unsigned char)seq[k]] : (uint8_t)0;
-      if (bi & 1) out->bases4[bi >> 1] |= nibv; else out->bases4[bi >> 1] = (uint8_t)(nibv << 4);
-      int q = (k < lqual && k < lseq) ? (int)(unsigned char)qual[k] - 33 : 0;
+    memset(out->payload + (nb << 5), 0, (size_t)lpad << 5);
+    for (int64_t k = 0; k < lseq; ++k) {
+      const uint64_t c = (uint64_t)k / AVO_BLOCK_BASES, w = (uint64_t)k - c * AVO_BLOCK_BASES;
+      uint8_t* blk = out->payload + ((nb + c) << 5);
+      const uint8_t nibv = NIB.t[(unsigned char)seq[k]];
+      blk[w >> 1] |= (w & 1) ? nibv : (uint8_t)(nibv << 4);
+      int q = (k < lqual) ? (int)(unsigned char)qual[k] - 33 : 0;
       q = q < 0 ? 0 : (q > 255 ? 255 : q);
-      out->quals[bi] = (uint8_t)q;
+      blk[10 + w] = (uint8_t)q;
       if (k < 4) m.qhead |= (uint32_t)q << (8 * k);
     }
     for (size_t k = 0; k < sc.ops.size(); ++k) out->ops[no + k] = sc.ops[k];
@@ -260,7 +262,7 @@ int avo_pack_reads(const avo_text_reads* in, avo_packed_out* out) {
     nb += lpad; no += sc.ops.size(); nf += sc.refb.size();
     ++r;
   }
-  out->n_reads = r; out->n_bases = (int64_t)nb; out->n_ops = (int64_t)no; out->n_refb = (int64_t)nf;
+  out->n_reads = r; out->n_blocks = (int64_t)nb; out->n_ops = (int64_t)no; out->n_refb = (int64_t)nf;
   return AVO_OK;
 }
 

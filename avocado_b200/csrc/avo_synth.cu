@@ -202,18 +202,19 @@ struct CountSink {
 };
 
 struct WriteSink {
-  uint8_t* bases4; uint8_t* quals; uint32_t* ops; uint8_t* refb;
-  uint64_t bi;   // global base index (even at read start)
+  uint8_t* payload; uint32_t* ops; uint8_t* refb;
+  uint64_t blk0; // the read's first payload block
   uint64_t oi;   // global op index
   uint64_t fi;   // global refb byte index
   uint32_t pend_b = 0, pend_f = 0, n_pend = 0;
   uint32_t nb = 0, qhead = 0;   // bases written so far; phred of the first four
   HD void base(uint32_t nib, uint32_t q) {
     if (nb < 4) qhead |= q << (8 * nb);
+    const uint32_t c = nb / AVO_BLOCK_BASES, w = nb - c * AVO_BLOCK_BASES;
+    uint8_t* b = payload + ((blk0 + c) << 5);
+    b[10 + w] = (uint8_t)q;
+    if (w & 1) b[w >> 1] = (uint8_t)((pend_b << 4) | nib); else { pend_b = nib; b[w >> 1] = (uint8_t)(nib << 4); }
     ++nb;
-    quals[bi] = (uint8_t)q;
-    if (bi & 1) bases4[bi >> 1] = (uint8_t)((pend_b << 4) | nib); else pend_b = nib;
-    ++bi;
   }
   HD void op(uint32_t len, uint32_t code) { ops[oi++] = (len << 4) | code; }
   HD void pair(uint32_t refn, uint32_t readn) { refb[fi++] = (uint8_t)((refn << 4) | readn); }
@@ -225,12 +226,14 @@ struct WriteSink {
     if (n_pend & 1) refb[fi++] = (uint8_t)(pend_f << 4);
     n_pend = 0;
   }
-  HD void finish() {
-    if (bi & 1) bases4[bi >> 1] = (uint8_t)(pend_b << 4);
+  HD void begin(uint32_t n_blocks) {     // unused slots and the two pad bytes of every block are zero
+    uint4* z = reinterpret_cast<uint4*>(payload + (blk0 << 5));
+    for (uint32_t k = 0; k < 2 * n_blocks; ++k) z[k] = make_uint4(0, 0, 0, 0);
   }
+  HD void finish() {}
 };
 
-HD uint32_t even_up(uint32_t x) { return (x + 1u) & ~1u; }
+HD uint32_t blocks_of(uint32_t l_seq) { return (l_seq + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES; }
 
 __global__ void k_synth_count(avo_synth_params P, int64_t first, int64_t n, uint32_t* __restrict__ n_ops,
                               uint32_t* __restrict__ n_refb) {
@@ -251,15 +254,16 @@ HD void fill_meta(avo_read_meta& m, int32_t start, int32_t end, uint8_t mapq, ui
 }
 
 __global__ void k_synth_write(avo_synth_params P, int64_t first, int64_t n, avo_read_meta* __restrict__ meta,
-                              uint8_t* __restrict__ bases4, uint8_t* __restrict__ quals,
+                              uint8_t* __restrict__ payload,
                               const uint32_t* __restrict__ op_off, uint32_t* __restrict__ ops,
                               const uint32_t* __restrict__ refb_off, uint8_t* __restrict__ refb) {
   const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (j >= n) return;
-  const uint32_t lpad = even_up((uint32_t)P.read_len);
+  const uint32_t lpad = blocks_of((uint32_t)P.read_len);
   WriteSink w;
-  w.bases4 = bases4; w.quals = quals; w.ops = ops; w.refb = refb;
-  w.bi = (uint64_t)j * lpad; w.oi = op_off[j]; w.fi = refb_off[j];
+  w.payload = payload; w.ops = ops; w.refb = refb;
+  w.blk0 = (uint64_t)j * lpad; w.oi = op_off[j]; w.fi = refb_off[j];
+  w.begin(lpad);
   int32_t s, e; uint8_t mq, fl;
   synth_read(P, first + j, w, &s, &e, &mq, &fl);
   w.finish();
@@ -292,7 +296,7 @@ static int check_synth(const avo_synth_params* p, int64_t first, int64_t n) {
   if (!p || n < 0 || first < 0 || first + n > p->n_reads_total) return AVO_E_INVALID;
   if (p->read_len < 30 || p->read_len > 1000 || p->max_indel < 1 || p->max_indel > 20) return AVO_E_INVALID;
   if ((int64_t)p->contig_len < (int64_t)p->read_len + 2 * p->max_indel + 4) return AVO_E_INVALID;
-  const uint64_t lpad = (uint64_t)((p->read_len + 1) & ~1);
+  const uint64_t lpad = (uint64_t)blocks_of((uint32_t)p->read_len);
   if ((uint64_t)n * lpad > 0xFFFFFFFFull) return AVO_E_INVALID;
   return AVO_OK;
 }
@@ -303,7 +307,7 @@ int avo_synth_host(const avo_synth_params* p, int64_t first, int64_t n, int64_t*
                    avo_packed_out* out) {
   int rc = check_synth(p, first, n);
   if (rc != AVO_OK) return rc;
-  const uint32_t lpad = (uint32_t)((p->read_len + 1) & ~1);
+  const uint32_t lpad = blocks_of((uint32_t)p->read_len);
   uint64_t to = 0, tf = 0;
   if (!out) {
     for (int64_t j = 0; j < n; ++j) {
@@ -324,15 +328,16 @@ int avo_synth_host(const avo_synth_params* p, int64_t first, int64_t n, int64_t*
         j >= out->n_reads)
       return AVO_E_CAPACITY;
     WriteSink w;
-    w.bases4 = out->bases4; w.quals = out->quals; w.ops = out->ops; w.refb = out->refb;
-    w.bi = (uint64_t)j * lpad; w.oi = to; w.fi = tf;
+    w.payload = out->payload; w.ops = out->ops; w.refb = out->refb;
+    w.blk0 = (uint64_t)j * lpad; w.oi = to; w.fi = tf;
+    w.begin(lpad);
     synth_read(*p, first + j, w, &s, &e, &mq, &fl);
     w.finish();
     fill_meta(out->meta[j], s, e, mq, fl, (uint32_t)(j * lpad), (uint32_t)to, (uint32_t)tf, c.n_ops,
               w.qhead, (uint32_t)p->read_len);
     to += c.n_ops; tf += c.n_refb;
   }
-  out->n_reads = n; out->n_bases = (int64_t)n * lpad; out->n_ops = (int64_t)to; out->n_refb = (int64_t)tf;
+  out->n_reads = n; out->n_blocks = (int64_t)n * lpad; out->n_ops = (int64_t)to; out->n_refb = (int64_t)tf;
   if (n_ops) *n_ops = (int64_t)to;
   if (n_refb) *n_refb = (int64_t)tf;
   return AVO_OK;
@@ -373,8 +378,8 @@ int avo_synth_device(const avo_synth_params* p, int64_t first, int64_t n, uint32
     return AVO_OK;
   }
   if (n > 0)
-    k_synth_write<<<grid, 128, 0, s>>>(*p, first, n, out->meta, out->bases4, out->quals, op_off_dev,
-                                       out->ops, refb_off_dev, out->refb);
+    k_synth_write<<<grid, 128, 0, s>>>(*p, first, n, out->meta, out->payload, op_off_dev, out->ops,
+                                       refb_off_dev, out->refb);
   cudaError_t e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) { cudaGetLastError(); return AVO_E_CUDA; }
   return AVO_OK;

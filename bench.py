@@ -140,7 +140,7 @@ def oracle_sample(B, p, first, n, contig_id=0):
     del dev
     m = h.meta
     rs = oracle.reads_from_packed("chr20", m["start"], m["end"], m["mapq"], m["flags"], m["seq_off"],
-                                  m["l_seq"], h.bases4, h.quals, m["op_off"], m["n_ops"], h.ops,
+                                  m["l_seq"], h.payload, m["op_off"], m["n_ops"], h.ops,
                                   m["refb_off"], h.refb)
     return oracle, rs
 
@@ -380,7 +380,7 @@ class ReadBatchPinned:
     def __init__(self, dev, B):
         import torch
         self.tensors = {}
-        b = B.ReadBatch(dev.n_reads, dev.n_bases, dev.n_ops, dev.n_refb, dev.contig_id)
+        b = B.ReadBatch(dev.n_reads, dev.n_blocks, dev.n_ops, dev.n_refb, dev.contig_id)
         for name, dt in B.READ_COLUMNS:
             t = getattr(dev, name)
             h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)

@@ -19,13 +19,16 @@
  *  - `mem` says where a struct's buffers live: AVO_MEM_HOST or AVO_MEM_DEVICE (pointers valid on
  *    the context's GPU).  Host batches should be page-locked (cudaHostAlloc / cudaHostRegister,
  *    e.g. the shim's direct ByteBuffers registered once): the per-read records, operators and
- *    mismatch bytes are then copied at full PCIe rate and the two large columns (bases4, quals)
- *    are read in place, only the 32-byte sectors the kernels touch (avo_params.host_payload).
+ *    mismatch bytes are then copied at full PCIe rate and the large column (payload)
+ *    is read in place, only the 32-byte sectors the kernels touch (avo_params.host_payload).
  *  - All functions return 0 (AVO_OK) or a negative avo_status; nothing throws or aborts.
  *    A malformed read is skipped, never an error (BiallelicGenotyper.scala:385-391).
  *  - A context is bound to one GPU and is NOT thread-safe; use one per thread.
  *  - Coordinates are 0-based half-open (ADAM); bases are 4-bit BAM codes (=ACMGRSVTWYHKDBN),
  *    two per byte, even index in the HIGH nibble; qualities are raw phred (no +33).
+ *  - Bases and qualities of a read travel together in 32-byte payload blocks (AVO_BLOCK_BASES = 20
+ *    bases per block: bytes 0..9 the 4-bit bases, bytes 10..29 the qualities, bytes 30..31 zero),
+ *    so the base and the quality of a position are one memory sector.
  *  - There is no CPU fallback: without a usable CUDA device avo_ctx_create fails.
  */
 #ifndef AVOCADO_B200_H
@@ -52,6 +55,7 @@ typedef enum {
 
 enum { AVO_MEM_HOST = 0, AVO_MEM_DEVICE = 1 };
 enum { AVO_MAX_PLOIDY = 7 };
+enum { AVO_BLOCK_BASES = 20, AVO_BLOCK_BYTES = 32 };
 
 /* alignment operators after merging CIGAR with MD (ObservationOperator.scala:42-171):
  * op word = (length << 4) | code */
@@ -86,7 +90,7 @@ int avo_ctx_set_stream(avo_ctx* ctx, void* cuda_stream);
 typedef struct {
   int32_t start;     /* AlignmentRecord.start */
   int32_t end;       /* AlignmentRecord.end */
-  uint32_t seq_off;  /* index of the read's first base in bases4 / quals (even) */
+  uint32_t seq_off;  /* index of the read's first 32-byte block in payload */
   uint32_t op_off;   /* index of the read's first operator in ops */
   uint32_t refb_off; /* byte index of the read's first entry in refb */
   uint16_t n_ops;    /* number of operators (0: the reference could not extract any) */
@@ -112,15 +116,14 @@ typedef struct {
  * the canonical summation order). */
 typedef struct {
   int64_t n_reads;
-  int64_t n_bases; /* bases4 / quals entries (reads start on even indices) */
+  int64_t n_blocks; /* payload blocks (a read of l_seq bases owns ceil(l_seq / 20) consecutive blocks) */
   int64_t n_ops;
   int64_t n_refb;  /* refb bytes (< 2^31) */
   int32_t contig_id; /* rank of this contig in the site table's contig order */
   int32_t mem;
   avo_batch_stats stats;
   const avo_read_meta* meta; /* [n_reads] */
-  const uint8_t* bases4;     /* [(n_bases+1)/2] */
-  const uint8_t* quals;      /* [n_bases] */
+  const uint8_t* payload;    /* [n_blocks * 32] bases + qualities, see "Conventions" */
   const uint32_t* ops;       /* [n_ops] */
   const uint8_t* refb;       /* [n_refb] in operator order: a MISMATCH op of length n holds n bytes
                                 (reference base << 4) | read base, a DEL op its n deleted reference
@@ -158,9 +161,9 @@ typedef struct {
   int32_t max_mapq;           /* call(maxMapQ = 93) */
   int32_t min_phred_discover; /* optPhredThreshold.getOrElse(0) */
   int32_t min_obs_discover;   /* optMinObservations; < 0 = None (distinct); keep count > this */
-  int32_t host_payload;       /* AVO_MEM_HOST batches: 0 = read bases4 / quals in place over PCIe when
-                                 they are page-locked and the mode touches them sparsely (variant-only
-                                 calling, discovery), 1 = always copy them to the device */
+  int32_t host_payload;       /* AVO_MEM_HOST batches: 0 = read the payload in place over PCIe when
+                                 it is page-locked and the mode touches it sparsely (variant-only
+                                 calling, discovery), 1 = always copy it to the device */
   int32_t reserved;
 } avo_params;
 
@@ -228,7 +231,7 @@ typedef struct {
   int32_t n_tile_launches; /* of which tile kernels (1 per stage unless a buffer overflowed) */
   int64_t h2d_bytes;
   int64_t d2h_bytes;
-  int32_t payload_in_place; /* 1: bases4 / quals were read from pinned host memory, not copied */
+  int32_t payload_in_place; /* 1: the payload was read from pinned host memory, not copied */
   int32_t reserved;
 } avo_timing;
 int avo_get_timing(const avo_ctx* ctx, avo_timing* out);
@@ -339,13 +342,13 @@ typedef struct {
 } avo_text_reads;
 
 typedef struct {
-  int64_t n_reads, n_bases, n_ops, n_refb; /* in: capacities; out: used */
+  int64_t n_reads, n_blocks, n_ops, n_refb; /* in: capacities; out: used */
   avo_read_meta* meta;
-  uint8_t* bases4; uint8_t* quals; uint32_t* ops; uint8_t* refb;
+  uint8_t* payload; uint32_t* ops; uint8_t* refb;
   int64_t* source_index; /* [n_reads] index of each packed read in the input (may be NULL) */
 } avo_packed_out;
 
-int avo_pack_bounds(const avo_text_reads* in, int64_t* n_reads, int64_t* n_bases, int64_t* n_ops,
+int avo_pack_bounds(const avo_text_reads* in, int64_t* n_reads, int64_t* n_blocks, int64_t* n_ops,
                     int64_t* n_refb);
 int avo_pack_reads(const avo_text_reads* in, avo_packed_out* out);
 

@@ -1267,8 +1267,7 @@ static std::shared_ptr<ReadSet> readsFromPacked(
     py::array_t<uint8_t, py::array::c_style | py::array::forcecast> flags,
     py::array_t<uint32_t, py::array::c_style | py::array::forcecast> seqOff,
     py::array_t<uint32_t, py::array::c_style | py::array::forcecast> lSeq,
-    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> bases4,
-    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> quals,
+    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> payload,
     py::array_t<uint32_t, py::array::c_style | py::array::forcecast> opOff,
     py::array_t<uint32_t, py::array::c_style | py::array::forcecast> nOps,
     py::array_t<uint32_t, py::array::c_style | py::array::forcecast> ops,
@@ -1279,7 +1278,7 @@ static std::shared_ptr<ReadSet> readsFromPacked(
   const size_t n = (size_t)start.size();
   auto st = start.unchecked<1>(); auto en = end.unchecked<1>(); auto mq = mapq.unchecked<1>();
   auto fl = flags.unchecked<1>(); auto so = seqOff.unchecked<1>(); auto ls = lSeq.unchecked<1>();
-  auto b4 = bases4.unchecked<1>(); auto ql = quals.unchecked<1>(); auto oo = opOff.unchecked<1>();
+  auto pl = payload.unchecked<1>(); auto oo = opOff.unchecked<1>();
   auto no = nOps.unchecked<1>(); auto op = ops.unchecked<1>(); auto fo = refbOff.unchecked<1>();
   auto fb = refb.unchecked<1>();
   auto nib = [](const auto& a, uint64_t i) -> int { int b = a(i >> 1); return (i & 1) ? (b & 15) : (b >> 4); };
@@ -1290,8 +1289,17 @@ static std::shared_ptr<ReadSet> readsFromPacked(
     r.start = st(i); r.end = en(i);
     r.negativeStrand = fl(i) & 1;
     r.hasMapq = !(fl(i) & 2); r.mapq = mq(i);
-    const uint64_t b0 = so(i), b1 = b0 + ls(i);
-    for (uint64_t b = b0; b < b1; ++b) { r.seq.push_back(NIBS[nib(b4, b)]); r.qual.push_back((char)(ql(b) + 33)); }
+    // payload: 32-byte blocks of 20 bases (bytes 0..9, 4 bit each) + their 20 qualities (bytes 10..29)
+    const uint64_t blk0 = so(i);
+    auto baseAt = [&](uint64_t k) -> int {
+      const uint64_t c = k / 20, w = k % 20;
+      const int v = pl((blk0 + c) * 32 + (w >> 1));
+      return (w & 1) ? (v & 15) : (v >> 4);
+    };
+    for (uint64_t k = 0; k < ls(i); ++k) {
+      r.seq.push_back(NIBS[baseAt(k)]);
+      r.qual.push_back((char)(pl((blk0 + k / 20) * 32 + 10 + k % 20) + 33));
+    }
     uint64_t f = fo(i);   // byte index into refb
     uint64_t ridx = 0;    // read bases consumed
     long run = 0;
@@ -1306,7 +1314,7 @@ static std::shared_ptr<ReadSet> readsFromPacked(
         for (uint32_t j = 0; j < len; ++j) {
           const int pr = fb(f++);
           // the low nibble repeats the read base: a packer / generator consistency check
-          if ((pr & 15) != nib(b4, b0 + ridx + j))
+          if ((pr & 15) != baseAt(ridx + j))
             throw std::runtime_error("packed batch: mismatch pair does not repeat the read base");
           md += std::to_string(run); md.push_back(NIBS[pr >> 4]); run = 0;
         }

@@ -65,7 +65,7 @@ def oracle_reads_from_batch(oracle, batch, contig="ctg"):
     b = batch.to_host()
     m = b.meta
     return oracle.reads_from_packed(contig, m["start"], m["end"], m["mapq"], m["flags"], m["seq_off"],
-                                    m["l_seq"], b.bases4, b.quals, m["op_off"], m["n_ops"], b.ops,
+                                    m["l_seq"], b.payload, m["op_off"], m["n_ops"], b.ops,
                                     m["refb_off"], b.refb)
 
 

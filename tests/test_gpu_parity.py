@@ -129,8 +129,7 @@ def test_synthetic_batch_matches_oracle(oracle, ctx, seed, n_reads, contig_len, 
     host = B.synth_host(p)
     dev = B.synth_device(p)
     dh = dev.to_host()
-    used = {"bases4": (host.n_bases + 1) // 2, "quals": host.n_bases, "ops": host.n_ops,
-            "refb": host.n_refb}
+    used = {"payload": host.n_blocks * 32, "ops": host.n_ops, "refb": host.n_refb}
     for name, _ in B.READ_COLUMNS:      # host and device generators agree byte for byte
         n = used.get(name, len(getattr(host, name)))
         assert np.array_equal(getattr(host, name)[:n], getattr(dh, name)[:n]), name
@@ -226,13 +225,13 @@ def test_discovery_exact_path_for_exotic_bases(oracle, ctx):
 
 
 def test_pinned_host_batch_is_read_in_place(ctx):
-    """A page-locked host batch keeps bases4 / quals on the host (the kernels gather single
+    """A page-locked host batch keeps the payload on the host (the kernels gather single
     sectors over PCIe); results are identical to the copied path and to device-resident input."""
     import torch
     from avocado_b200 import batch as B
     p = B.synth_params(seed=9, n_reads_total=30000, contig_len=80000)
     host = B.synth_host(p)
-    pinned = B.ReadBatch(host.n_reads, host.n_bases, host.n_ops, host.n_refb, host.contig_id, stats=host.stats)
+    pinned = B.ReadBatch(host.n_reads, host.n_blocks, host.n_ops, host.n_refb, host.contig_id, stats=host.stats)
     keep = []
     for name, dt in B.READ_COLUMNS:
         a = getattr(host, name)

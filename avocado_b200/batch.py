@@ -25,7 +25,7 @@ META_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("seq_off", "<u4"), ("o
 assert META_DTYPE.itemsize == 32
 
 READ_COLUMNS = [("meta", META_DTYPE), ("payload", np.uint8), ("ops", np.uint32), ("refb", np.uint8)]
-BLOCK_BASES, BLOCK_BYTES = 20, 32     # payload: 20 bases (4 bit) + their 20 qualities per 32-byte block
+BLOCK_BASES, BLOCK_BYTES = 10, 16     # payload: 10 bases (4 bit) + their 10 qualities per 16-byte block
 
 
 def blocks_of(l_seq):

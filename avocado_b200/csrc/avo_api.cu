@@ -135,6 +135,8 @@ int validate_reads(avo_ctx* ctx, const avo_read_batch* r) {
       (r->n_refb > 0 && !r->refb))
     return fail(ctx, AVO_E_INVALID, "read batch has NULL columns");
   if (r->mem != AVO_MEM_HOST && r->mem != AVO_MEM_DEVICE) return fail(ctx, AVO_E_INVALID, "bad reads->mem");
+  if (((uintptr_t)r->payload & 15u) || ((uintptr_t)r->meta & 15u))
+    return fail(ctx, AVO_E_INVALID, "reads->payload and reads->meta must be 16-byte aligned");
   return AVO_OK;
 }
 

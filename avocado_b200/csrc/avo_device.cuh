@@ -10,12 +10,12 @@ __device__ __forceinline__ uint32_t nib_at(const uint8_t* __restrict__ p, uint32
   return (i & 1u) ? (b & 15u) : (b >> 4);
 }
 
-// Payload accessors: base / quality i of the read whose first block is blk0 (one sector for both)
+// Payload accessors: base / quality i of the read whose first block is blk0.
 __device__ __forceinline__ const uint8_t* pl_block(const uint8_t* __restrict__ pl, uint32_t blk0, uint32_t i,
                                                     uint32_t& w) {
   const uint32_t c = i / (uint32_t)AVO_BLOCK_BASES;
   w = i - c * (uint32_t)AVO_BLOCK_BASES;
-  return pl + ((size_t)(blk0 + c) << 5);
+  return pl + ((size_t)(blk0 + c) << 4);
 }
 __device__ __forceinline__ uint32_t pl_base(const uint8_t* __restrict__ pl, uint32_t blk0, uint32_t i) {
   uint32_t w;
@@ -26,7 +26,20 @@ __device__ __forceinline__ uint32_t pl_base(const uint8_t* __restrict__ pl, uint
 __device__ __forceinline__ uint32_t pl_qual(const uint8_t* __restrict__ pl, uint32_t blk0, uint32_t i) {
   uint32_t w;
   const uint8_t* b = pl_block(pl, blk0, i, w);
-  return __ldg(b + 10 + w);
+  return __ldg(b + 5 + w);
+}
+// both with one 16-byte load (one memory / PCIe request per observed position)
+__device__ __forceinline__ void pl_base_qual(const uint8_t* __restrict__ pl, uint32_t blk0, uint32_t i,
+                                             uint32_t& base, uint32_t& qual) {
+  uint32_t w;
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(pl_block(pl, blk0, i, w)));
+  auto byte_at = [&](uint32_t k) -> uint32_t {
+    const uint32_t word = (k < 4u) ? v.x : (k < 8u) ? v.y : (k < 12u) ? v.z : v.w;
+    return (word >> (8u * (k & 3u))) & 255u;
+  };
+  const uint32_t bb = byte_at(w >> 1);
+  base = (w & 1u) ? (bb & 15u) : (bb >> 4);
+  qual = byte_at(5u + w);
 }
 
 // The 32-byte read record is fetched as two 16-byte halves.

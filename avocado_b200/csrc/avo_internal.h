@@ -16,7 +16,7 @@ struct DReads {
   const avo_read_meta* meta;   // 32-byte record per read (include/avocado_b200.h)
   int2* coords;                // (start, end) per read: dense copy written by the first kernel that
                                // streams the records (k_batch_stats / k_discover_tiles), read by the join
-  const uint8_t* payload;      // 32-byte blocks: 20 bases (4 bit) + their 20 qualities
+  const uint8_t* payload;      // 16-byte blocks: 10 bases (4 bit) + their 10 qualities
   const uint32_t* ops;
   const uint8_t* refb;
 };

@@ -66,16 +66,17 @@ __device__ inline Cls classify(const DReads& R, const ReadCtx& rc, int32_t vs, i
           ++n_obs; ++n_nonempty;
           all_isref = all_isref && isref;
           if (first || insVar) {
-            const uint32_t b = pl_base(R.payload, rc.sb, bi);
+            uint32_t b, bq;
+            pl_base_qual(R.payload, rc.sb, bi, b, bq);       // base and quality: one 16-byte load
             if (first) {
               head_isref = isref;
-              head_q = (int32_t)pl_qual(R.payload, rc.sb, bi);
+              head_q = (int32_t)bq;
               head_eq_alt = (alt_len == 1 && b == nib_at(alleles4, altoff));
             }
             if (insVar) {
               const bool eq = (alt_len == 2 && b == nib_at(alleles4, altoff + 1));
               if (eq) {
-                if (n_ins_eq == 0) { inseq_q = (int32_t)pl_qual(R.payload, rc.sb, bi); inseq_isref = isref; }
+                if (n_ins_eq == 0) { inseq_q = (int32_t)bq; inseq_isref = isref; }
                 ++n_ins_eq;
               } else if (lead_kind == 0) { lead_kind = 1; lead_first = b; }
             }

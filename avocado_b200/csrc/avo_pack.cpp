@@ -246,15 +246,15 @@ int avo_pack_reads(const avo_text_reads* in, avo_packed_out* out) {
     m.l_seq = (uint32_t)lseq;
     m.qhead = 0;
     if (out->source_index) out->source_index[r] = i;
-    memset(out->payload + (nb << 5), 0, (size_t)lpad << 5);
+    memset(out->payload + (nb << 4), 0, (size_t)lpad << 4);
     for (int64_t k = 0; k < lseq; ++k) {
       const uint64_t c = (uint64_t)k / AVO_BLOCK_BASES, w = (uint64_t)k - c * AVO_BLOCK_BASES;
-      uint8_t* blk = out->payload + ((nb + c) << 5);
+      uint8_t* blk = out->payload + ((nb + c) << 4);
       const uint8_t nibv = NIB.t[(unsigned char)seq[k]];
       blk[w >> 1] |= (w & 1) ? nibv : (uint8_t)(nibv << 4);
       int q = (k < lqual) ? (int)(unsigned char)qual[k] - 33 : 0;
       q = q < 0 ? 0 : (q > 255 ? 255 : q);
-      blk[10 + w] = (uint8_t)q;
+      blk[5 + w] = (uint8_t)q;
       if (k < 4) m.qhead |= (uint32_t)q << (8 * k);
     }
     for (size_t k = 0; k < sc.ops.size(); ++k) out->ops[no + k] = sc.ops[k];

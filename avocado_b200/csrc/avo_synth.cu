@@ -211,8 +211,8 @@ struct WriteSink {
   HD void base(uint32_t nib, uint32_t q) {
     if (nb < 4) qhead |= q << (8 * nb);
     const uint32_t c = nb / AVO_BLOCK_BASES, w = nb - c * AVO_BLOCK_BASES;
-    uint8_t* b = payload + ((blk0 + c) << 5);
-    b[10 + w] = (uint8_t)q;
+    uint8_t* b = payload + ((blk0 + c) << 4);
+    b[5 + w] = (uint8_t)q;
     if (w & 1) b[w >> 1] = (uint8_t)((pend_b << 4) | nib); else { pend_b = nib; b[w >> 1] = (uint8_t)(nib << 4); }
     ++nb;
   }
@@ -227,8 +227,8 @@ struct WriteSink {
     n_pend = 0;
   }
   HD void begin(uint32_t n_blocks) {     // unused slots and the two pad bytes of every block are zero
-    uint4* z = reinterpret_cast<uint4*>(payload + (blk0 << 5));
-    for (uint32_t k = 0; k < 2 * n_blocks; ++k) z[k] = make_uint4(0, 0, 0, 0);
+    uint4* z = reinterpret_cast<uint4*>(payload + (blk0 << 4));
+    for (uint32_t k = 0; k < n_blocks; ++k) z[k] = make_uint4(0, 0, 0, 0);
   }
   HD void finish() {}
 };

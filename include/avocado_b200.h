@@ -26,9 +26,9 @@
  *  - A context is bound to one GPU and is NOT thread-safe; use one per thread.
  *  - Coordinates are 0-based half-open (ADAM); bases are 4-bit BAM codes (=ACMGRSVTWYHKDBN),
  *    two per byte, even index in the HIGH nibble; qualities are raw phred (no +33).
- *  - Bases and qualities of a read travel together in 32-byte payload blocks (AVO_BLOCK_BASES = 20
- *    bases per block: bytes 0..9 the 4-bit bases, bytes 10..29 the qualities, bytes 30..31 zero),
- *    so the base and the quality of a position are one memory sector.
+ *  - Bases and qualities of a read travel together in 16-byte payload blocks (AVO_BLOCK_BASES = 10
+ *    bases per block: bytes 0..4 the 4-bit bases, bytes 5..14 the qualities, byte 15 zero), so the
+ *    base and the quality of a position come with ONE 16-byte load.
  *  - There is no CPU fallback: without a usable CUDA device avo_ctx_create fails.
  */
 #ifndef AVOCADO_B200_H
@@ -55,7 +55,7 @@ typedef enum {
 
 enum { AVO_MEM_HOST = 0, AVO_MEM_DEVICE = 1 };
 enum { AVO_MAX_PLOIDY = 7 };
-enum { AVO_BLOCK_BASES = 20, AVO_BLOCK_BYTES = 32 };
+enum { AVO_BLOCK_BASES = 10, AVO_BLOCK_BYTES = 16 };
 
 /* alignment operators after merging CIGAR with MD (ObservationOperator.scala:42-171):
  * op word = (length << 4) | code */
@@ -90,7 +90,7 @@ int avo_ctx_set_stream(avo_ctx* ctx, void* cuda_stream);
 typedef struct {
   int32_t start;     /* AlignmentRecord.start */
   int32_t end;       /* AlignmentRecord.end */
-  uint32_t seq_off;  /* index of the read's first 32-byte block in payload */
+  uint32_t seq_off;  /* index of the read's first 16-byte block in payload */
   uint32_t op_off;   /* index of the read's first operator in ops */
   uint32_t refb_off; /* byte index of the read's first entry in refb */
   uint16_t n_ops;    /* number of operators (0: the reference could not extract any) */
@@ -116,14 +116,14 @@ typedef struct {
  * the canonical summation order). */
 typedef struct {
   int64_t n_reads;
-  int64_t n_blocks; /* payload blocks (a read of l_seq bases owns ceil(l_seq / 20) consecutive blocks) */
+  int64_t n_blocks; /* payload blocks (a read of l_seq bases owns ceil(l_seq / 10) consecutive blocks) */
   int64_t n_ops;
   int64_t n_refb;  /* refb bytes (< 2^31) */
   int32_t contig_id; /* rank of this contig in the site table's contig order */
   int32_t mem;
   avo_batch_stats stats;
   const avo_read_meta* meta; /* [n_reads] */
-  const uint8_t* payload;    /* [n_blocks * 32] bases + qualities, see "Conventions" */
+  const uint8_t* payload;    /* [n_blocks * 16] bases + qualities, 16-byte aligned, see "Conventions" */
   const uint32_t* ops;       /* [n_ops] */
   const uint8_t* refb;       /* [n_refb] in operator order: a MISMATCH op of length n holds n bytes
                                 (reference base << 4) | read base, a DEL op its n deleted reference

@@ -1289,16 +1289,16 @@ static std::shared_ptr<ReadSet> readsFromPacked(
     r.start = st(i); r.end = en(i);
     r.negativeStrand = fl(i) & 1;
     r.hasMapq = !(fl(i) & 2); r.mapq = mq(i);
-    // payload: 32-byte blocks of 20 bases (bytes 0..9, 4 bit each) + their 20 qualities (bytes 10..29)
+    // payload: 16-byte blocks of 10 bases (bytes 0..4, 4 bit each) + their 10 qualities (bytes 5..14)
     const uint64_t blk0 = so(i);
     auto baseAt = [&](uint64_t k) -> int {
-      const uint64_t c = k / 20, w = k % 20;
-      const int v = pl((blk0 + c) * 32 + (w >> 1));
+      const uint64_t c = k / 10, w = k % 10;
+      const int v = pl((blk0 + c) * 16 + (w >> 1));
       return (w & 1) ? (v & 15) : (v >> 4);
     };
     for (uint64_t k = 0; k < ls(i); ++k) {
       r.seq.push_back(NIBS[baseAt(k)]);
-      r.qual.push_back((char)(pl((blk0 + k / 20) * 32 + 10 + k % 20) + 33));
+      r.qual.push_back((char)(pl((blk0 + k / 10) * 16 + 5 + k % 10) + 33));
     }
     uint64_t f = fo(i);   // byte index into refb
     uint64_t ridx = 0;    // read bases consumed

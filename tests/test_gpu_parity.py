@@ -129,7 +129,7 @@ def test_synthetic_batch_matches_oracle(oracle, ctx, seed, n_reads, contig_len, 
     host = B.synth_host(p)
     dev = B.synth_device(p)
     dh = dev.to_host()
-    used = {"payload": host.n_blocks * 32, "ops": host.n_ops, "refb": host.n_refb}
+    used = {"payload": host.n_blocks * 16, "ops": host.n_ops, "refb": host.n_refb}
     for name, _ in B.READ_COLUMNS:      # host and device generators agree byte for byte
         n = used.get(name, len(getattr(host, name)))
         assert np.array_equal(getattr(host, name)[:n], getattr(dh, name)[:n]), name

@@ -38,7 +38,7 @@ class ReadBatchStruct(C.Structure):
                 ("n_refb", C.c_int64), ("contig_id", C.c_int32), ("mem", C.c_int32),
                 ("stats_min_start", C.c_int32), ("stats_max_end", C.c_int32),
                 ("stats_max_span", C.c_int32), ("stats_valid", C.c_int32),
-                ("meta", P), ("payload", P), ("ops", P), ("refb", P)]
+                ("meta", P), ("payload", P), ("ops", P), ("refb", P), ("wire_meta", P), ("wire_ops", P)]
 
 
 class SitesStruct(C.Structure):
@@ -135,7 +135,7 @@ EXPORTED_SYMBOLS = [
     "avo_ctx_create", "avo_ctx_destroy", "avo_last_error", "avo_version", "avo_ctx_set_stream",
     "avo_get_timing", "avo_discover", "avo_call", "avo_discover_and_call",
     "avo_call_all_sites", "avo_joint_counts", "avo_joint",
-    "avo_pack_bounds", "avo_pack_reads", "avo_synth_default_params", "avo_synth_host",
+    "avo_pack_wire", "avo_pack_bounds", "avo_pack_reads", "avo_synth_default_params", "avo_synth_host",
     "avo_synth_device",
 ]
 
@@ -174,6 +174,7 @@ def load():
                                        C.POINTER(SiteResultsStruct), C.POINTER(RefModelOutStruct)]
     lib.avo_joint_counts.argtypes = [P, C.POINTER(JointInStruct), P, P]
     lib.avo_joint.argtypes = [P, C.POINTER(JointInStruct), C.POINTER(JointOutStruct)]
+    lib.avo_pack_wire.argtypes = [C.POINTER(ReadBatchStruct), P, P]
     lib.avo_pack_bounds.argtypes = [C.POINTER(TextReadsStruct)] + [C.POINTER(C.c_int64)] * 4
     lib.avo_pack_reads.argtypes = [C.POINTER(TextReadsStruct), C.POINTER(PackedOutStruct)]
     lib.avo_synth_default_params.argtypes = [C.POINTER(SynthParamsStruct)]

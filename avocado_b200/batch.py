@@ -24,6 +24,11 @@ META_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("seq_off", "<u4"), ("o
                        ("qhead", "<u4"), ("l_seq", "<u4")])
 assert META_DTYPE.itemsize == 32
 
+# avo_read_wire: the compact 16-byte wire form of the record (offsets are rebuilt on the device)
+WIRE_DTYPE = np.dtype([("start", "<i4"), ("span", "<u2"), ("l_seq", "<u2"), ("n_ops", "u1"), ("n_refb", "u1"),
+                       ("mapq", "u1"), ("flags", "u1"), ("qhead", "<u4")])
+assert WIRE_DTYPE.itemsize == 16
+
 READ_COLUMNS = [("meta", META_DTYPE), ("payload", np.uint8), ("ops", np.uint32), ("refb", np.uint8)]
 BLOCK_BASES, BLOCK_BYTES = 10, 16     # payload: 10 bases (4 bit) + their 10 qualities per 16-byte block
 
@@ -59,6 +64,25 @@ class ReadBatch:
     refb: object = None
     source_index: Optional[np.ndarray] = None
     stats: Optional[tuple] = None   # (min_start, max_end, max_span): avo_batch_stats, optional
+    wire_meta: Optional[np.ndarray] = None   # host batches: compact wire columns (avo_pack_wire)
+    wire_ops: Optional[np.ndarray] = None
+
+    def with_wire(self, alloc=None):
+        """Adds the compact wire columns (host batches): the library then copies 16-byte records
+        and 16-bit operators instead of `meta` / `ops`.  `alloc(n_bytes) -> uint8 ndarray` lets the
+        caller supply pinned memory.  Returns False when the batch does not fit the compact form."""
+        assert not self.on_device
+        alloc = alloc or (lambda n: np.zeros(n, np.uint8))
+        wm = alloc(max(self.n_reads, 1) * 16).view(WIRE_DTYPE)
+        wo = alloc(max(self.n_ops, 1) * 2).view(np.uint16)
+        s = self.as_struct()
+        rc = L.load().avo_pack_wire(C.byref(s), wm.ctypes.data, wo.ctypes.data)
+        if rc == L.AVO_E_UNSUPPORTED:
+            return False
+        if rc != 0:
+            raise L.AvocadoError(rc, "avo_pack_wire failed")
+        self.wire_meta, self.wire_ops = wm[:self.n_reads], wo[:max(self.n_ops, 1)]
+        return True
 
     def with_stats(self):
         """Fills `stats` (what a packer knows for free) so that the library can skip its own
@@ -96,6 +120,8 @@ class ReadBatch:
             s.stats_valid = 1
         for name, _ in READ_COLUMNS:
             setattr(s, name, _ptr(getattr(self, name)))
+        if self.wire_meta is not None and self.wire_ops is not None and not self.on_device:
+            s.wire_meta, s.wire_ops = _ptr(self.wire_meta), _ptr(self.wire_ops)
         return s
 
     def nbytes(self):

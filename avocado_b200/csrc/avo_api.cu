@@ -19,7 +19,7 @@ namespace {
 constexpr int32_t LNK_N = 1 << 16;
 
 enum Slot {
-  SL_META, SL_COORDS, SL_PAYLOAD, SL_OPS, SL_REFB,
+  SL_META, SL_COORDS, SL_PAYLOAD, SL_OPS, SL_REFB, SL_WIRE_META, SL_WIRE_OPS, SL_WIRE_OFFS,
   SL_S_CONTIG, SL_S_START, SL_S_REFLEN, SL_S_ALTLEN, SL_S_AOFF, SL_S_ALLELES, SL_S_END, SL_S_PME,
   SL_S_COUNT,
   SL_CNV, SL_STATS, SL_SMALL, SL_RIDX, SL_SIDX, SL_TEMP, SL_LUT,
@@ -130,12 +130,16 @@ int validate_reads(avo_ctx* ctx, const avo_read_batch* r) {
   if (r->n_blocks < 0 || r->n_blocks > (int64_t)UINT32_MAX || r->n_ops < 0 ||
       r->n_ops > (int64_t)UINT32_MAX || r->n_refb < 0 || r->n_refb > (int64_t)INT32_MAX)
     return fail(ctx, AVO_E_INVALID, "batch totals must fit 32-bit offsets; split the batch");
-  if (r->n_reads > 0 && !r->meta) return fail(ctx, AVO_E_INVALID, "read batch has no meta column");
-  if ((r->n_blocks > 0 && !r->payload) || (r->n_ops > 0 && !r->ops) ||
+  const bool wire = r->wire_meta && r->wire_ops;
+  if ((r->wire_meta != nullptr) != (r->wire_ops != nullptr) && r->n_ops > 0)
+    return fail(ctx, AVO_E_INVALID, "wire_meta and wire_ops go together");
+  if (wire && r->mem != AVO_MEM_HOST) return fail(ctx, AVO_E_INVALID, "wire columns are for host batches");
+  if (r->n_reads > 0 && !r->meta && !wire) return fail(ctx, AVO_E_INVALID, "read batch has no meta column");
+  if ((r->n_blocks > 0 && !r->payload) || (r->n_ops > 0 && !r->ops && !wire) ||
       (r->n_refb > 0 && !r->refb))
     return fail(ctx, AVO_E_INVALID, "read batch has NULL columns");
   if (r->mem != AVO_MEM_HOST && r->mem != AVO_MEM_DEVICE) return fail(ctx, AVO_E_INVALID, "bad reads->mem");
-  if (((uintptr_t)r->payload & 15u) || ((uintptr_t)r->meta & 15u))
+  if (((uintptr_t)r->payload & 15u) || ((uintptr_t)r->meta & 15u) || ((uintptr_t)r->wire_meta & 15u))
     return fail(ctx, AVO_E_INVALID, "reads->payload and reads->meta must be 16-byte aligned");
   return AVO_OK;
 }
@@ -151,8 +155,27 @@ int upload_reads(avo_ctx* ctx, const avo_read_batch* r, bool sparse, DReads* R) 
     CKS(get_buf(ctx, SL_COORDS, n * sizeof(int2), &c));
     R->coords = (int2*)c;
   }
-  CKS(stage_in(ctx, SL_META, r->meta, n, r->mem, &R->meta));
-  CKS(stage_in(ctx, SL_OPS, r->ops, (size_t)r->n_ops, r->mem, &R->ops));
+  if (r->wire_meta && r->wire_ops && r->mem == AVO_MEM_HOST) {
+    // compact wire columns: half the bytes over PCIe; offsets rebuilt by a scan on the device
+    const avo_read_wire* dw;
+    const uint16_t* dwo;
+    CKS(stage_in(ctx, SL_WIRE_META, r->wire_meta, n, r->mem, &dw));
+    CKS(stage_in(ctx, SL_WIRE_OPS, r->wire_ops, (size_t)r->n_ops, r->mem, &dwo));
+    void *dm, *dops, *doffs, *temp;
+    CKS(get_buf(ctx, SL_META, n * sizeof(avo_read_meta), &dm));
+    CKS(get_buf(ctx, SL_OPS, (size_t)r->n_ops * 4, &dops));
+    CKS(get_buf(ctx, SL_WIRE_OFFS, n * 12, &doffs));
+    const size_t tb = wire_temp_bytes(r->n_reads);
+    CKS(get_buf(ctx, SL_TEMP, tb, &temp));
+    CK(launch_wire_expand(dw, dwo, r->n_reads, r->n_ops, doffs, (avo_read_meta*)dm, (uint32_t*)dops, temp, tb,
+                          ctx->stream));
+    ctx->timing.n_launches += 3;
+    R->meta = (const avo_read_meta*)dm;
+    R->ops = (const uint32_t*)dops;
+  } else {
+    CKS(stage_in(ctx, SL_META, r->meta, n, r->mem, &R->meta));
+    CKS(stage_in(ctx, SL_OPS, r->ops, (size_t)r->n_ops, r->mem, &R->ops));
+  }
   CKS(stage_in(ctx, SL_REFB, r->refb, (size_t)r->n_refb, r->mem, &R->refb));
   if (sparse && r->mem == AVO_MEM_HOST && r->n_blocks > 0) {
     const uint8_t* b = mapped_alias(r->payload);

@@ -113,6 +113,12 @@ struct BatchStats {
   int32_t unsorted;   // != 0 if start[] is not non-decreasing
 };
 
+// compact wire columns -> full records / operators on the device (avo_setup.cu)
+size_t wire_temp_bytes(int64_t n_reads);
+cudaError_t launch_wire_expand(const avo_read_wire* wire, const uint16_t* wire_ops, int64_t n_reads,
+                               int64_t n_ops, void* offs /* 12 B x n_reads */, avo_read_meta* meta,
+                               uint32_t* ops, void* d_temp, size_t temp_bytes, cudaStream_t s);
+
 // device -> device column copies done by one launch
 struct ColumnCopies {
   int n;

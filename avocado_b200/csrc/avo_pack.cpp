@@ -185,6 +185,32 @@ bool kept(const avo_text_reads* in, int64_t i) {
 
 extern "C" {
 
+int avo_pack_wire(const avo_read_batch* full, avo_read_wire* wire_meta, uint16_t* wire_ops) {
+  if (!full || full->mem != AVO_MEM_HOST || (full->n_reads > 0 && (!full->meta || !wire_meta)) ||
+      (full->n_ops > 0 && (!full->ops || !wire_ops)))
+    return AVO_E_INVALID;
+  // the compact form drops the offsets: the columns must be laid out read after read without gaps
+  uint64_t blk = 0, op = 0, fb = 0;
+  for (int64_t r = 0; r < full->n_reads; ++r) {
+    const avo_read_meta& m = full->meta[r];
+    const uint64_t nfb = (r + 1 < full->n_reads ? (uint64_t)full->meta[r + 1].refb_off : (uint64_t)full->n_refb) - m.refb_off;
+    const int64_t span = (int64_t)m.end - (int64_t)m.start;
+    if (m.seq_off != blk || m.op_off != op || m.refb_off != fb) return AVO_E_UNSUPPORTED;
+    if (span < 0 || span > 0xFFFF || m.l_seq > 0xFFFFu || m.n_ops > 0xFFu || nfb > 0xFFu) return AVO_E_UNSUPPORTED;
+    avo_read_wire& w = wire_meta[r];
+    w.start = m.start; w.span = (uint16_t)span; w.l_seq = (uint16_t)m.l_seq; w.n_ops = (uint8_t)m.n_ops;
+    w.n_refb = (uint8_t)nfb; w.mapq = m.mapq; w.flags = m.flags; w.qhead = m.qhead;
+    blk += (m.l_seq + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES; op += m.n_ops; fb += nfb;
+  }
+  if ((int64_t)blk != full->n_blocks || (int64_t)op != full->n_ops || (int64_t)fb != full->n_refb)
+    return AVO_E_UNSUPPORTED;
+  for (int64_t i = 0; i < full->n_ops; ++i) {
+    if (full->ops[i] > 0xFFFFu) return AVO_E_UNSUPPORTED;     // operator of 4096 bases or more
+    wire_ops[i] = (uint16_t)full->ops[i];
+  }
+  return AVO_OK;
+}
+
 int avo_pack_bounds(const avo_text_reads* in, int64_t* n_reads, int64_t* n_blocks, int64_t* n_ops,
                     int64_t* n_refb) {
   if (!in || !n_reads || !n_blocks || !n_ops || !n_refb) return AVO_E_INVALID;

@@ -2,6 +2,7 @@
 // table's derived columns (end, prefix-max end = the Forest fast-path test), the coarse position
 // index that replaces per-tile binary searches, and the logFactorial table.
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include <algorithm>
 
@@ -157,6 +158,59 @@ cudaError_t launch_build_index(const DReads& R, const DSites& S, const BatchStat
   const int32_t nb = index_bins(h);
   k_build_index<<<(nb + 1 + 255) / 256, 256, 0, s>>>(R, S, h.min_start, nb, h.max_end, ridx, sidx,
                                                       s_range);
+  return cudaGetLastError();
+}
+
+// ---- compact wire form -> records: the offsets are prefix sums of the per-read sizes ----------------
+struct Off3 { uint32_t b, o, f; };
+struct Off3Sum {
+  __host__ __device__ Off3 operator()(const Off3& x, const Off3& y) const { return Off3{x.b + y.b, x.o + y.o, x.f + y.f}; }
+};
+struct WireSizes {
+  __host__ __device__ Off3 operator()(const avo_read_wire& w) const {
+    return Off3{((uint32_t)w.l_seq + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES, w.n_ops, w.n_refb};
+  }
+};
+
+__global__ void k_wire_expand(const avo_read_wire* __restrict__ wire, const Off3* __restrict__ offs, int64_t n,
+                              avo_read_meta* __restrict__ meta) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wire + r));
+  const Off3 o = offs[r];
+  const int32_t start = (int32_t)wv.x;
+  const uint32_t span = wv.y & 0xFFFFu, l_seq = wv.y >> 16;
+  const uint32_t n_ops = wv.z & 0xFFu, mapq = (wv.z >> 16) & 0xFFu, flags = wv.z >> 24;
+  int4 a, b;
+  a.x = start; a.y = start + (int32_t)span; a.z = (int32_t)o.b; a.w = (int32_t)o.o;
+  b.x = (int32_t)o.f; b.y = (int32_t)(n_ops | (mapq << 16) | (flags << 24)); b.z = (int32_t)wv.w; b.w = (int32_t)l_seq;
+  reinterpret_cast<int4*>(meta + r)[0] = a;
+  reinterpret_cast<int4*>(meta + r)[1] = b;
+}
+
+__global__ void k_wire_ops(const uint16_t* __restrict__ w, int64_t n, uint32_t* __restrict__ ops) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) ops[i] = (uint32_t)__ldg(w + i);      // (length << 4) | code in both widths
+}
+
+size_t wire_temp_bytes(int64_t n) {
+  size_t a = 0;
+  cub::TransformInputIterator<Off3, WireSizes, const avo_read_wire*> it(nullptr, WireSizes());
+  cub::DeviceScan::ExclusiveScan((void*)nullptr, a, it, (Off3*)nullptr, Off3Sum(), Off3{0, 0, 0}, (int)n);
+  return a + 256;
+}
+
+cudaError_t launch_wire_expand(const avo_read_wire* wire, const uint16_t* wire_ops, int64_t n_reads,
+                               int64_t n_ops, void* offs, avo_read_meta* meta, uint32_t* ops,
+                               void* d_temp, size_t temp_bytes, cudaStream_t s) {
+  if (n_reads > 0) {
+    cub::TransformInputIterator<Off3, WireSizes, const avo_read_wire*> it(wire, WireSizes());
+    cudaError_t e = cub::DeviceScan::ExclusiveScan(d_temp, temp_bytes, it, (Off3*)offs, Off3Sum(), Off3{0, 0, 0},
+                                                   (int)n_reads, s);
+    if (e != cudaSuccess) return e;
+    k_wire_expand<<<(unsigned)((n_reads + 255) / 256), 256, 0, s>>>(wire, (const Off3*)offs, n_reads, meta);
+  }
+  if (n_ops > 0) k_wire_ops<<<(unsigned)((n_ops + 255) / 256), 256, 0, s>>>(wire_ops, n_ops, ops);
   return cudaGetLastError();
 }
 

@@ -324,6 +324,7 @@ def main():
         from avocado_b200.parallel import plan_region_shards
         K = max(1, args.e2e_bins)
         hb = host.batch
+        host_wire = host.wire
         shards = plan_region_shards(hb.meta["start"], hb.meta["end"], K, max_site_len=64)
         bins = [host.pinned_slice(sh.read_lo, sh.read_hi) for sh in shards]
         T = max(1, min(args.e2e_threads, K))
@@ -375,7 +376,7 @@ def main():
                "d2h_bytes_per_step": int(sum(t["d2h_bytes"] for t in last)) * world,
                "ms_per_step": ms_b / args.steps,
                "region_bins": K, "host_threads": T,
-               "payload_in_place": bool(last[-1]["payload_in_place"]),
+               "payload_in_place": bool(last[-1]["payload_in_place"]), "wire_form": bool(host_wire),
                "single_call": {"value": total_reads * args.steps / (ms_h / 1e3), "ms_per_step": ms_h / args.steps,
                                "ms_h2d": statistics.mean(t["ms_h2d"] for t in t_h),
                                "ms_discover": statistics.mean(t["ms_discover"] for t in t_h),
@@ -383,7 +384,7 @@ def main():
                                "ms_d2h": statistics.mean(t["ms_d2h"] for t in t_h)},
                "note": "pinned host batch through the C ABI (avo_discover_and_call), %d region bins pipelined by %d "
                        "host threads (one context + stream each): records, operators and mismatch bytes are copied "
-                       "(h2d_bytes_per_step), bases and qualities stay in host memory and the kernels read only "
+                       "in the compact wire form (h2d_bytes_per_step), bases and qualities stay in host memory and the kernels read only "
                        "the 16-byte blocks they need over PCIe; D2H of the site table and all result columns "
                        "included" % (K, T)}
         pool.shutdown()
@@ -444,6 +445,7 @@ class ReadBatchPinned:
         b.stats = dev.stats
         self.batch = b
         self.B = B
+        self.wire = self.add_wire(b, "all")
 
     def pinned_slice(self, lo, hi):
         """Reads [lo, hi) as a batch of their own: views of the pinned columns, offsets rebased in a
@@ -453,7 +455,18 @@ class ReadBatchPinned:
         m = torch.from_numpy(s.meta.view("uint8")).pin_memory()
         self.tensors[("meta", lo, hi)] = m
         s.meta = m.numpy().view(self.B.META_DTYPE)
+        self.add_wire(s, (lo, hi))
         return s
+
+    def add_wire(self, batch, key):
+        """The packer's compact wire columns (avo_pack_wire), in pinned memory."""
+        import torch
+
+        def alloc(n):
+            t = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            self.tensors[("wire", key, len(self.tensors))] = t
+            return t.numpy()
+        return batch.with_wire(alloc)
 
 
 if __name__ == "__main__":

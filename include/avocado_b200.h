@@ -112,6 +112,22 @@ typedef struct {
   int32_t valid;
 } avo_batch_stats;
 
+/* Compact wire form of the record (optional, host batches): the three offsets of avo_read_meta are
+ * prefix sums of l_seq (in payload blocks), n_ops and n_refb, so they need not cross PCIe; the
+ * library rebuilds the 32-byte records on the device (one scan + one expansion kernel).  A batch
+ * can use it when every read has end - start and l_seq below 65536 and fewer than 256 operators
+ * and refb bytes, and every operator is shorter than 4096 (avo_pack_wire checks). */
+typedef struct {
+  int32_t start;
+  uint16_t span;    /* end - start */
+  uint16_t l_seq;
+  uint8_t n_ops;
+  uint8_t n_refb;   /* refb bytes of the read */
+  uint8_t mapq;
+  uint8_t flags;
+  uint32_t qhead;
+} avo_read_wire;    /* 16 bytes */
+
 /* One batch = reads of ONE contig, sorted by start (ties in any order; the order of the batch is
  * the canonical summation order). */
 typedef struct {
@@ -128,6 +144,10 @@ typedef struct {
   const uint8_t* refb;       /* [n_refb] in operator order: a MISMATCH op of length n holds n bytes
                                 (reference base << 4) | read base, a DEL op its n deleted reference
                                 bases as nibbles (high first) padded to (n+1)/2 bytes */
+  /* optional compact wire columns (AVO_MEM_HOST only): when both are non-NULL they are what is
+   * copied to the device and `meta` / `ops` are ignored (may be NULL) */
+  const avo_read_wire* wire_meta; /* [n_reads] */
+  const uint16_t* wire_ops;       /* [n_ops] (length << 4) | code */
 } avo_read_batch;
 
 /* Variant sites, sorted by (contig, start, start + ref_len); unique.  Replaces the Variant
@@ -347,6 +367,10 @@ typedef struct {
   uint8_t* payload; uint32_t* ops; uint8_t* refb;
   int64_t* source_index; /* [n_reads] index of each packed read in the input (may be NULL) */
 } avo_packed_out;
+
+/* Full records / operators (host) -> compact wire columns (host).  AVO_E_UNSUPPORTED when a read or
+ * an operator does not fit the compact form (the batch then travels in the full form). */
+int avo_pack_wire(const avo_read_batch* full, avo_read_wire* wire_meta, uint16_t* wire_ops);
 
 int avo_pack_bounds(const avo_text_reads* in, int64_t* n_reads, int64_t* n_blocks, int64_t* n_ops,
                     int64_t* n_refb);

@@ -270,3 +270,27 @@ def test_two_gpu_region_and_sample_sharding():
                         os.path.join(root, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "multi_gpu_check ok" in r.stdout
+
+
+def test_wire_form_gives_the_same_results(ctx):
+    """Host batches in the compact wire form (16-byte records, 16-bit operators; offsets rebuilt on
+    the device) produce exactly the rows of the full form, for discovery, call and gVCF rows."""
+    from avocado_b200 import batch as B
+    p = B.synth_params(seed=12, n_reads_total=25000, contig_len=70000, first_pos=123)
+    full = B.synth_host(p)
+    wire = B.synth_host(p)
+    assert wire.with_wire()
+    wire.meta = np.zeros(1, B.META_DTYPE)[:0]      # prove that only the wire columns are used
+    wire.ops = np.zeros(1, np.uint32)
+    # (as_struct passes whatever is there; the library must not touch meta / ops)
+    s_full, c_full = ctx.discover_and_call_packed(full, phred=25, min_obs=5)
+    s_wire, c_wire = ctx.discover_and_call_packed(wire, phred=25, min_obs=5)
+    assert s_full.n == s_wire.n > 20 and np.array_equal(s_full.start, s_wire.start)
+    assert np.array_equal(s_full.alleles4, s_wire.alleles4) and np.array_equal(s_full.count, s_wire.count)
+    for k in c_full:
+        assert np.array_equal(np.asarray(c_full[k]), np.asarray(c_wire[k]), equal_nan=True), k
+    a = ctx.call_all_sites_packed(full, s_full)
+    b = ctx.call_all_sites_packed(wire, s_full)
+    assert np.array_equal(a[1], b[1])
+    for k in a[2]:
+        assert np.array_equal(np.asarray(a[2][k]), np.asarray(b[2][k]), equal_nan=True), k

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(L.EXPORTED_SYMBOLS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert C.sizeof(L.ReadBatchStruct) == 4 * 8 + 2 * 4 + 4 * 4 + 4 * 8
+    assert C.sizeof(L.ReadBatchStruct) == 4 * 8 + 2 * 4 + 4 * 4 + 6 * 8
 
 
 @pytest.mark.parametrize("name", FIXTURES)
@@ -80,3 +80,27 @@ def test_synthetic_host_batch_is_consistent(oracle):
     rs2 = oracle_reads_from_batch(oracle, s)
     for j in (0, 57, 199):
         assert oracle.read_as_dict(rs2, j) == oracle.read_as_dict(rs, 100 + j)
+
+
+def test_wire_columns_hold_the_same_information():
+    """avo_pack_wire: the compact records drop only the offsets (prefix sums) and the operators
+    keep their bits; batches that do not fit are refused, not truncated."""
+    from avocado_b200 import _lib as L, batch as B
+    p = B.synth_params(seed=4, n_reads_total=3000, contig_len=20000)
+    b = B.synth_host(p)
+    assert b.with_wire()
+    m, w = b.meta, b.wire_meta
+    for f in ("start", "l_seq", "n_ops", "mapq", "flags", "qhead"):
+        assert np.array_equal(m[f].astype(np.int64), w[f].astype(np.int64)), f
+    assert np.array_equal(m["end"].astype(np.int64), w["start"].astype(np.int64) + w["span"])
+    blocks = (w["l_seq"].astype(np.int64) + 9) // 10
+    assert np.array_equal(np.concatenate([[0], np.cumsum(blocks)[:-1]]), m["seq_off"])
+    assert np.array_equal(np.concatenate([[0], np.cumsum(w["n_ops"].astype(np.int64))[:-1]]), m["op_off"])
+    assert np.array_equal(np.concatenate([[0], np.cumsum(w["n_refb"].astype(np.int64))[:-1]]), m["refb_off"])
+    assert np.array_equal(b.wire_ops[:b.n_ops].astype(np.uint32), b.ops[:b.n_ops])
+    long_op = B.synth_host(p)
+    long_op.ops[0] = (5000 << 4) | 0
+    assert not long_op.with_wire()
+    gap = B.synth_host(p)
+    gap.meta["op_off"][5] += 1
+    assert not gap.with_wire()

@@ -246,7 +246,7 @@ typedef struct {
   float ms_observe;   /* observe/classify/reduce/genotype kernel (+ its set-up kernels) */
   float ms_d2h;
   float ms_discover_tiles; /* k_discover_tiles alone */
-  float ms_call_tiles;     /* k_call_tiles alone */
+  float ms_call_tiles;     /* the call stage's kernels: buckets, join, observe, reduce */
   int32_t n_launches;      /* kernels launched by the call */
   int32_t n_tile_launches; /* of which tile kernels (1 per stage unless a buffer overflowed) */
   int64_t h2d_bytes;

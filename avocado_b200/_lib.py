@@ -127,7 +127,7 @@ class SynthParamsStruct(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("contig_len", C.c_int32), ("first_pos", C.c_int32),
                 ("n_reads_total", C.c_int64), ("read_len", C.c_int32), ("max_indel", C.c_int32),
                 ("snp_rate", C.c_double), ("indel_rate", C.c_double), ("triallelic_frac", C.c_double),
-                ("softclip_frac", C.c_double)]
+                ("softclip_frac", C.c_double), ("sample", C.c_uint64)]
 
 
 # every symbol declared in include/avocado_b200.h and include/avocado_b200_synth.h

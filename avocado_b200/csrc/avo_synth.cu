@@ -31,6 +31,11 @@ HD double u01(uint64_t h) { return (double)(h >> 11) * (1.0 / 9007199254740992.0
 
 HD uint32_t code_of(uint32_t two_bit) { return 1u << two_bit; }   // A=1 C=2 G=4 T=8
 
+// seed of the per-sample streams (genotypes, reads); the default sample keeps the batch seed
+HD uint64_t sample_seed(const avo_synth_params& P) {
+  return P.sample ? mix64(P.seed ^ (P.sample * 0x9E3779B97F4A7C15ull)) : P.seed;
+}
+
 HD uint32_t ref_base(const avo_synth_params& P, int64_t p) {
   return (uint32_t)(hash3(P.seed, 1, (uint64_t)p, 0) & 3u);
 }
@@ -49,10 +54,12 @@ HD TruthVar truth_at(const avo_synth_params& P, int64_t p) {
   const double u = u01(h);
   if (u >= P.snp_rate + P.indel_rate) return v;
   const uint64_t g = hash3(P.seed, 3, (uint64_t)p, 0);
-  const bool hom = (g % 3u) == 0;                 // het : hom-alt = 2 : 1
-  const int hap = (int)((g >> 8) & 1u);
-  v.on[0] = hom || hap == 0;
-  v.on[1] = hom || hap == 1;
+  const uint64_t gs = P.sample ? hash3(sample_seed(P), 3, (uint64_t)p, 0) : g;   // this sample's genotype
+  const bool hom = (gs % 3u) == 0;                // het : hom-alt = 2 : 1
+  const int hap = (int)((gs >> 8) & 1u);
+  const bool carrier = !P.sample || ((gs >> 40) & 3u) != 0;
+  v.on[0] = carrier && (hom || hap == 0);
+  v.on[1] = carrier && (hom || hap == 1);
   if (u < P.snp_rate) {
     v.kind = 1;
     const uint32_t r = ref_base(P, p);
@@ -63,7 +70,7 @@ HD TruthVar truth_at(const avo_synth_params& P, int64_t p) {
       uint32_t a1 = (a0 + 1u) & 3u;
       if (a1 == r) a1 = (a1 + 1u) & 3u;
       v.alt[1] = a1;
-      v.on[0] = v.on[1] = true;
+      v.on[0] = v.on[1] = carrier;
     }
   } else {
     v.kind = ((g >> 20) & 1u) ? 2 : 3;
@@ -108,8 +115,9 @@ HD int draw_mapq(uint64_t h) {
 }
 
 HD int64_t read_start(const avo_synth_params& P, int64_t i) {
+  const uint64_t SS = sample_seed(P);
   const int64_t usable = (int64_t)P.contig_len - P.read_len - 2 * P.max_indel - 2;
-  const double f = ((double)i + u01(hash3(P.seed, 5, (uint64_t)i, 0))) / (double)P.n_reads_total;
+  const double f = ((double)i + u01(hash3(SS, 5, (uint64_t)i, 0))) / (double)P.n_reads_total;
   int64_t s = (int64_t)(f * (double)usable);
   if (s < 0) s = 0;
   if (s > usable) s = usable;
@@ -122,12 +130,13 @@ HD int64_t read_start(const avo_synth_params& P, int64_t i) {
 template <typename Sink>
 HD void synth_read(const avo_synth_params& P, int64_t i, Sink& out, int32_t* o_start, int32_t* o_end,
                    uint8_t* o_mapq, uint8_t* o_flags) {
-  const uint64_t hr = hash3(P.seed, 6, (uint64_t)i, 0);
+  const uint64_t SS = sample_seed(P);
+  const uint64_t hr = hash3(SS, 6, (uint64_t)i, 0);
   const int hap = (int)(hr & 1u);
   const bool neg = (hr >> 1) & 1u;
   const int L = P.read_len;
   int clip_lead = 0, clip_trail = 0;
-  if (u01(hash3(P.seed, 7, (uint64_t)i, 0)) < P.softclip_frac) {
+  if (u01(hash3(SS, 7, (uint64_t)i, 0)) < P.softclip_frac) {
     const int c = 1 + (int)((hr >> 8) % 20u);
     if ((hr >> 2) & 1u) clip_lead = c; else clip_trail = c;
   }
@@ -139,16 +148,16 @@ HD void synth_read(const avo_synth_params& P, int64_t i, Sink& out, int32_t* o_s
   uint32_t run_code = AVO_OP_MATCH;
   auto flush = [&]() { if (run_len) { out.op((uint32_t)run_len, run_code); run_len = 0; } };
   auto seq_base = [&](uint32_t truth2, int k) -> uint32_t {   // apply sequencing error; emit base
-    const int q = draw_qual(hash3(P.seed, 8, (uint64_t)i, (uint64_t)k));
+    const int q = draw_qual(hash3(SS, 8, (uint64_t)i, (uint64_t)k));
     uint32_t b = truth2;
-    const uint64_t he = hash3(P.seed, 9, (uint64_t)i, (uint64_t)k);
+    const uint64_t he = hash3(SS, 9, (uint64_t)i, (uint64_t)k);
     if (u01(he) < err_prob(q)) b = (truth2 + 1u + (uint32_t)((he >> 56) % 3u)) & 3u;
     out.base(code_of(b), (uint32_t)q);
     return b;
   };
   if (clip_lead) {
     for (int k = 0; k < clip_lead; ++k)
-      seq_base((uint32_t)(hash3(P.seed, 10, (uint64_t)i, (uint64_t)k) & 3u), emitted++);
+      seq_base((uint32_t)(hash3(SS, 10, (uint64_t)i, (uint64_t)k) & 3u), emitted++);
     out.op((uint32_t)clip_lead, AVO_OP_SOFTCLIP);
   }
   const int body = L - clip_trail;   // read bases that take part in the alignment (incl. lead clip)
@@ -183,12 +192,12 @@ HD void synth_read(const avo_synth_params& P, int64_t i, Sink& out, int32_t* o_s
   flush();
   if (clip_trail) {
     for (int k = 0; k < clip_trail; ++k)
-      seq_base((uint32_t)(hash3(P.seed, 10, (uint64_t)i, (uint64_t)(100 + k)) & 3u), emitted++);
+      seq_base((uint32_t)(hash3(SS, 10, (uint64_t)i, (uint64_t)(100 + k)) & 3u), emitted++);
     out.op((uint32_t)clip_trail, AVO_OP_SOFTCLIP);
   }
   *o_start = (int32_t)start;
   *o_end = (int32_t)p;
-  *o_mapq = (uint8_t)draw_mapq(hash3(P.seed, 12, (uint64_t)i, 0));
+  *o_mapq = (uint8_t)draw_mapq(hash3(SS, 12, (uint64_t)i, 0));
   *o_flags = neg ? AVO_READ_NEGATIVE_STRAND : 0;
 }
 
@@ -289,6 +298,7 @@ int avo_synth_default_params(avo_synth_params* p) {
   p->indel_rate = 1.0e-4;
   p->triallelic_frac = 0.01;
   p->softclip_frac = 0.02;
+  p->sample = 0;
   return AVO_OK;
 }
 

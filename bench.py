@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=READS_C2, help="reads per GPU (default: configs[1])")
-    ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="reads in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=8_000_000, help="reads in the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-bins", type=int, default=8, help="region bins the e2e leg is cut into")
     ap.add_argument("--e2e-threads", type=int, default=3,

@@ -27,6 +27,9 @@ typedef struct {
   double indel_rate;
   double triallelic_frac; /* fraction of SNV sites carrying two different alts */
   double softclip_frac;   /* fraction of reads soft-clipped 1..20 bases at one end */
+  uint64_t sample;        /* 0: the default sample.  Other values: another sample of the same cohort:
+                             same reference and truth variant sites / alleles, its own genotypes
+                             (carrier with p = 3/4, then het : hom-alt = 2 : 1) and its own reads */
 } avo_synth_params;
 
 int avo_synth_default_params(avo_synth_params* p);

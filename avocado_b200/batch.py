@@ -322,7 +322,7 @@ def text_columns(records: Sequence[AlignmentRecord]):
 
 def pack_reads(records: Sequence[AlignmentRecord], contig_id=0, keep=None, sort=True) -> ReadBatch:
     """Packs mapped reads of ONE contig, (stably) sorted by start, into a host ReadBatch.
-    ``keep`` optionally selects reads (the PrefilterReads predicate lives in prefilter.py)."""
+    ``keep`` optionally selects reads (``prefilter.prefilter_mask`` gives the PrefilterReads predicate)."""
     lib = L.load()
     idx = [i for i, r in enumerate(records) if r.readMapped and r.start is not None and
            (keep is None or keep[i])]

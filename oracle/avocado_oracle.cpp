@@ -1198,6 +1198,112 @@ static JointSiteOut annotateSite(const std::vector<JointGenotypeIn>& gts) {
   return out;
 }
 
+// ---------------------------------------------------------------------------
+// CORE/util/RewriteHets.scala:60-170 and CORE/util/HardFilterGenotypes.scala:176-660 -- the two
+// per-genotype passes the CLI applies to call()'s output (CLI/BiallelicGenotyper.scala:279-282).
+// Alleles are coded 0 = REF, 1 = ALT, 2 = OTHER_ALT, 3 = NO_CALL.  Optional fields mirror the Avro
+// nullables the reference's own unit tests leave unset.
+// ---------------------------------------------------------------------------
+struct FilterGt {
+  bool hasAlt = true;
+  int refLen = 1, altLen = 1;
+  std::vector<int> alleles;
+  std::optional<int> gq, dp, adp;
+  std::optional<float> fs, rms;
+};
+
+struct FilterArgs {          // HardFilterGenotypesArgs + RewriteHetsArgs; a filter is on iff its value > 0
+  int minQuality = 30;
+  float minHetSnpQualityByDepth = 2.0f, minHomSnpQualityByDepth = 1.0f;
+  float minHetIndelQualityByDepth = 2.0f, minHomIndelQualityByDepth = 1.0f;
+  float maxSnpPhredStrandBias = -1.0f, maxIndelPhredStrandBias = -1.0f;
+  float minSnpRMSMappingQuality = 30.0f, minIndelRMSMappingQuality = -1.0f;
+  int minSnpDepth = 10, maxSnpDepth = 200, minIndelDepth = 10, maxIndelDepth = 200;
+  float minHetSnpAltAllelicFraction = 0.333f, maxHetSnpAltAllelicFraction = 0.666f, minHomSnpAltAllelicFraction = 0.666f;
+  float minHetIndelAltAllelicFraction = 0.333f, maxHetIndelAltAllelicFraction = 0.666f, minHomIndelAltAllelicFraction = 0.666f;
+  bool disableHetSnpRewriting = false, disableHetIndelRewriting = false;
+};
+
+static bool shouldRewrite(const FilterGt& g, float maxSnpAf, float maxIndelAf, bool snps, bool indels) {   // RewriteHets.scala:95-126
+  if (!g.hasAlt) return false;
+  const bool isSnp = g.refLen == 1 && g.altLen == 1;
+  int numAlts = 0;
+  for (int a : g.alleles) numAlts += a == 1;
+  const bool isHet = numAlts != 0 && numAlts != (int)g.alleles.size();
+  auto checkAf = [&](float af) { return g.dp && g.adp ? ((float)*g.adp / (float)*g.dp) >= af : false; };
+  if (snps && isSnp && isHet) return checkAf(maxSnpAf);
+  if (indels && !isSnp && isHet) return checkAf(maxIndelAf);
+  return false;
+}
+
+static FilterGt rewriteGenotype(FilterGt g) {                                                             // :134-143
+  for (int& a : g.alleles) a = 1;
+  g.gq.reset();
+  return g;
+}
+
+struct FilterResult { bool emitted = false, filtersApplied = false, passed = false; std::vector<std::string> failed; };
+
+static FilterResult filterGenotype(const FilterGt& g, const FilterArgs& A, bool filterRefGenotypes, bool emitAll) {   // HardFilterGenotypes.scala:632-660
+  FilterResult r;
+  auto anyAlt = [&] { for (int a : g.alleles) if (a == 1) return true; return false; };
+  const bool qualOk = !g.gq || *g.gq > A.minQuality;                                                     // :346-349
+  const bool emit = emitAll || ((filterRefGenotypes ? anyAlt() : true) && qualOk);                        // :363-371
+  if (!g.hasAlt) { r.emitted = true; return r; }                                                         // :656-658
+  if (!emit) return r;
+  r.emitted = true;
+  const bool snp = g.refLen == 1 && g.altLen == 1;
+  bool allAlt = true, allAltOrOther = true;
+  for (int a : g.alleles) { allAlt = allAlt && a == 1; allAltOrOther = allAltOrOther && (a == 1 || a == 2); }
+  std::optional<float> af;
+  if (g.dp && g.adp) af = (float)*g.adp / (float)*g.dp;                                                  // :512-517
+  int nFilters = 0;
+  auto qd = [&](float minQd, const char* msg, bool hom) {                                                // :381-402
+    if (!(minQd > 0.0f)) return;
+    ++nFilters;
+    if ((!allAlt && !hom) || (allAlt && hom))
+      if (g.dp && g.gq && ((float)*g.gq / (float)*g.dp) < minQd) r.failed.push_back(msg);
+  };
+  auto mq = [&](float minMq, const char* msg) {                                                          // :488-500
+    if (!(minMq > 0.0f)) return;
+    ++nFilters;
+    if (g.rms && *g.rms < minMq) r.failed.push_back(msg);
+  };
+  auto fs = [&](float maxFs, const char* msg) {                                                          // :420-432
+    if (!(maxFs > 0.0f)) return;
+    ++nFilters;
+    if (g.fs && *g.fs > maxFs) r.failed.push_back(msg);
+  };
+  auto minDp = [&](int v, const char* msg) { if (v > 0) { ++nFilters; if (g.dp && *g.dp < v) r.failed.push_back(msg); } };   // :464-475
+  auto maxDp = [&](int v, const char* msg) { if (v > 0) { ++nFilters; if (g.dp && *g.dp > v) r.failed.push_back(msg); } };   // :442-453
+  auto minAf = [&](float v, const char* msg, bool hom) {                                                 // :531-549
+    if (!(v > 0.0f)) return;
+    ++nFilters;
+    if (((!allAlt && !hom) || (allAlt && hom)) && af && *af <= v) r.failed.push_back(msg);
+  };
+  auto maxAf = [&](float v, const char* msg) {                                                           // :561-580 (het-alt counts as hom)
+    if (!(v > 0.0f)) return;
+    ++nFilters;
+    if (!allAltOrOther && af && *af > v) r.failed.push_back(msg);
+  };
+  if (snp) {                                                                                             // :258-298
+    qd(A.minHetSnpQualityByDepth, "HETSNPQD", false); qd(A.minHomSnpQualityByDepth, "HOMSNPQD", true);
+    mq(A.minSnpRMSMappingQuality, "SNPMQ"); fs(A.maxSnpPhredStrandBias, "SNPFS");
+    minDp(A.minSnpDepth, "SNPMINDP"); maxDp(A.maxSnpDepth, "SNPMAXDP");
+    minAf(A.minHetSnpAltAllelicFraction, "HETSNPMINAF", false); maxAf(A.maxHetSnpAltAllelicFraction, "HETSNPMAXAF");
+    minAf(A.minHomSnpAltAllelicFraction, "HOMSNPMINAF", true);
+  } else {                                                                                               // :304-344
+    qd(A.minHetIndelQualityByDepth, "HETINDELQD", false); qd(A.minHomIndelQualityByDepth, "HOMINDELQD", true);
+    mq(A.minIndelRMSMappingQuality, "INDELMQ"); fs(A.maxIndelPhredStrandBias, "INDELFS");
+    minDp(A.minIndelDepth, "INDELMINDP"); maxDp(A.maxIndelDepth, "INDELMAXDP");
+    minAf(A.minHetIndelAltAllelicFraction, "HETINDELMINAF", false); maxAf(A.maxHetIndelAltAllelicFraction, "HETINDELMAXAF");
+    minAf(A.minHomIndelAltAllelicFraction, "HOMINDELMINAF", true);
+  }
+  r.filtersApplied = nFilters > 0;                                                                       // :590-617
+  r.passed = r.failed.empty();
+  return r;
+}
+
 }  // namespace orc
 
 // ===========================================================================
@@ -1659,6 +1765,59 @@ PYBIND11_MODULE(avocado_oracle, m) {
       gl.append(e);
     }
     d["genotypes"] = gl;
+    return d;
+  });
+  // ---- RewriteHets / HardFilterGenotypes ----------------------------------------------------
+  auto gtFromDict = [](const py::dict& d) {
+    FilterGt g;
+    auto has = [&](const char* k) { return d.contains(k) && !d[k].is_none(); };
+    g.hasAlt = has("alt");
+    if (has("ref")) g.refLen = (int)d["ref"].cast<std::string>().size();
+    if (g.hasAlt) g.altLen = (int)d["alt"].cast<std::string>().size();
+    g.alleles = d["alleles"].cast<std::vector<int>>();
+    if (has("gq")) g.gq = d["gq"].cast<int>();
+    if (has("dp")) g.dp = d["dp"].cast<int>();
+    if (has("adp")) g.adp = d["adp"].cast<int>();
+    if (has("fs")) g.fs = d["fs"].cast<float>();
+    if (has("rms")) g.rms = d["rms"].cast<float>();
+    return g;
+  };
+  auto argsFromDict = [](const py::dict& d) {
+    FilterArgs a;
+#define AVO_ARG(name, type) if (d.contains(#name)) a.name = d[#name].cast<type>();
+    AVO_ARG(minQuality, int) AVO_ARG(minHetSnpQualityByDepth, float) AVO_ARG(minHomSnpQualityByDepth, float)
+    AVO_ARG(minHetIndelQualityByDepth, float) AVO_ARG(minHomIndelQualityByDepth, float)
+    AVO_ARG(maxSnpPhredStrandBias, float) AVO_ARG(maxIndelPhredStrandBias, float)
+    AVO_ARG(minSnpRMSMappingQuality, float) AVO_ARG(minIndelRMSMappingQuality, float)
+    AVO_ARG(minSnpDepth, int) AVO_ARG(maxSnpDepth, int) AVO_ARG(minIndelDepth, int) AVO_ARG(maxIndelDepth, int)
+    AVO_ARG(minHetSnpAltAllelicFraction, float) AVO_ARG(maxHetSnpAltAllelicFraction, float)
+    AVO_ARG(minHomSnpAltAllelicFraction, float) AVO_ARG(minHetIndelAltAllelicFraction, float)
+    AVO_ARG(maxHetIndelAltAllelicFraction, float) AVO_ARG(minHomIndelAltAllelicFraction, float)
+    AVO_ARG(disableHetSnpRewriting, bool) AVO_ARG(disableHetIndelRewriting, bool)
+#undef AVO_ARG
+    return a;
+  };
+  m.def("should_rewrite", [gtFromDict](const py::dict& g, float maxSnpAf, float maxIndelAf, bool snps, bool indels) {
+    return shouldRewrite(gtFromDict(g), maxSnpAf, maxIndelAf, snps, indels);
+  });
+  // rewrite_and_filter: RewriteHets(args) then HardFilterGenotypes(args, filterRefGenotypes, emitAllGenotypes)
+  m.def("rewrite_and_filter", [gtFromDict, argsFromDict](const py::dict& gd, const py::dict& ad, bool filterRef,
+                                                         bool emitAll, bool rewrite) {
+    FilterGt g = gtFromDict(gd);
+    const FilterArgs a = argsFromDict(ad);
+    bool rewritten = false;
+    if (rewrite && shouldRewrite(g, a.maxHetSnpAltAllelicFraction, a.maxHetIndelAltAllelicFraction,
+                                 !a.disableHetSnpRewriting, !a.disableHetIndelRewriting)) {
+      g = rewriteGenotype(g);
+      rewritten = true;
+    }
+    const FilterResult r = filterGenotype(g, a, filterRef, emitAll);
+    py::dict d;
+    d["rewritten"] = rewritten;
+    d["alleles"] = g.alleles;
+    d["gq"] = g.gq ? py::object(py::int_(*g.gq)) : py::object(py::none());
+    d["emitted"] = r.emitted; d["filtersApplied"] = r.filtersApplied; d["filtersPassed"] = r.passed;
+    d["filtersFailed"] = r.failed;
     return d;
   });
 }

@@ -105,6 +105,36 @@ class PackedOutStruct(C.Structure):
                 ("refb", P), ("source_index", P)]
 
 
+FILTER_PARAM_FIELDS = [
+    ("min_quality", C.c_int32), ("filter_ref_genotypes", C.c_int32), ("emit_all_genotypes", C.c_int32),
+    ("disable_het_snp_rewriting", C.c_int32), ("disable_het_indel_rewriting", C.c_int32),
+    ("min_snp_depth", C.c_int32), ("max_snp_depth", C.c_int32), ("min_indel_depth", C.c_int32),
+    ("max_indel_depth", C.c_int32),
+    ("min_het_snp_quality_by_depth", C.c_float), ("min_hom_snp_quality_by_depth", C.c_float),
+    ("min_het_indel_quality_by_depth", C.c_float), ("min_hom_indel_quality_by_depth", C.c_float),
+    ("max_snp_phred_strand_bias", C.c_float), ("max_indel_phred_strand_bias", C.c_float),
+    ("min_snp_rms_mapping_quality", C.c_float), ("min_indel_rms_mapping_quality", C.c_float),
+    ("min_het_snp_alt_allelic_fraction", C.c_float), ("max_het_snp_alt_allelic_fraction", C.c_float),
+    ("min_hom_snp_alt_allelic_fraction", C.c_float), ("min_het_indel_alt_allelic_fraction", C.c_float),
+    ("max_het_indel_alt_allelic_fraction", C.c_float), ("min_hom_indel_alt_allelic_fraction", C.c_float)]
+
+
+class FilterParamsStruct(C.Structure):
+    _fields_ = FILTER_PARAM_FIELDS
+
+
+FILTER_OUT_COLUMNS = [("emit", "uint8"), ("rewritten", "uint8"), ("filters_applied", "uint8"),
+                      ("filters_failed", "uint32"), ("n_alt", "int32"), ("n_ref", "int32"), ("gq_valid", "uint8")]
+FILTER_NAMES = ["HETSNPQD", "HOMSNPQD", "SNPMQ", "SNPFS", "SNPMINDP", "SNPMAXDP", "HETSNPMINAF", "HETSNPMAXAF",
+                "HOMSNPMINAF", "HETINDELQD", "HOMINDELQD", "INDELMQ", "INDELFS", "INDELMINDP", "INDELMAXDP",
+                "HETINDELMINAF", "HETINDELMAXAF", "HOMINDELMINAF"]
+
+
+class FilterOutStruct(C.Structure):
+    _fields_ = [("n", C.c_int64), ("mem", C.c_int32), ("reserved", C.c_int32)] + \
+               [(n, P) for n, _ in FILTER_OUT_COLUMNS]
+
+
 class JointInStruct(C.Structure):
     _fields_ = [("n_sites", C.c_int64), ("n_samples", C.c_int32), ("n_states", C.c_int32),
                 ("mem", C.c_int32), ("reserved", C.c_int32), ("present", P), ("n_alt", P), ("n_ref", P),
@@ -134,7 +164,7 @@ class SynthParamsStruct(C.Structure):
 EXPORTED_SYMBOLS = [
     "avo_ctx_create", "avo_ctx_destroy", "avo_last_error", "avo_version", "avo_ctx_set_stream",
     "avo_get_timing", "avo_discover", "avo_call", "avo_discover_and_call",
-    "avo_call_all_sites", "avo_joint_counts", "avo_joint",
+    "avo_call_all_sites", "avo_filter_genotypes", "avo_joint_counts", "avo_joint",
     "avo_pack_wire", "avo_pack_bounds", "avo_pack_reads", "avo_synth_default_params", "avo_synth_host",
     "avo_synth_device",
 ]
@@ -172,6 +202,8 @@ def load():
     lib.avo_call_all_sites.argtypes = [P, C.POINTER(ReadBatchStruct), C.POINTER(SitesStruct),
                                        C.POINTER(CnvStruct), C.POINTER(ParamsStruct),
                                        C.POINTER(SiteResultsStruct), C.POINTER(RefModelOutStruct)]
+    lib.avo_filter_genotypes.argtypes = [P, C.POINTER(SiteResultsStruct), P, P, C.POINTER(FilterParamsStruct),
+                                         C.POINTER(FilterOutStruct)]
     lib.avo_joint_counts.argtypes = [P, C.POINTER(JointInStruct), P, P]
     lib.avo_joint.argtypes = [P, C.POINTER(JointInStruct), C.POINTER(JointOutStruct)]
     lib.avo_pack_wire.argtypes = [C.POINTER(ReadBatchStruct), P, P]

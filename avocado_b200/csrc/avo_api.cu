@@ -29,6 +29,7 @@ enum Slot {
   SL_C_RBASE, SL_C_BLEN, SL_C_BOFF, SL_C_BUCKETS,
   SL_AS_FLAG, SL_AS_JPOS, SL_AS_JR, SL_AS_JIDX, SL_AS_COVER, SL_AS_SCOVER, SL_AS_WCOUNT, SL_AS_WBASE,
   SL_AS_RES, SL_AS_START,
+  SL_F_IN, SL_F_OUT,
   SL_J_PRESENT, SL_J_NALT, SL_J_NREF, SL_J_NOTHER, SL_J_NOCALL, SL_J_GL, SL_J_ALT, SL_J_CALLED, SL_J_OUT,
   SL_TABLE, SL_TCOUNT, SL_KEYS_A, SL_KEYS_B, SL_VALS_A, SL_VALS_B, SL_FOOT, SL_AOFF,
   SL_COUNT_
@@ -915,6 +916,79 @@ int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_c
   }
   CKS(call_internal(ctx, R, hs, T, cnv, params, true, results));
   CKS(finish_call(ctx, true, true));
+  return AVO_OK;
+}
+
+// ---- RewriteHets + HardFilterGenotypes ---------------------------------------------------------------
+int avo_filter_genotypes(avo_ctx* ctx, const avo_site_results* rows, const int32_t* ref_len,
+                         const int32_t* alt_len, const avo_filter_params* params, avo_filter_out* out) {
+  CKS(begin_call(ctx));
+  if (!rows || !params || !out) return fail(ctx, AVO_E_INVALID, "NULL argument");
+  if (rows->n_sites < 0 || out->n != rows->n_sites) return fail(ctx, AVO_E_INVALID, "out->n != rows->n_sites");
+  if (out->mem != rows->mem || (rows->mem != AVO_MEM_HOST && rows->mem != AVO_MEM_DEVICE))
+    return fail(ctx, AVO_E_INVALID, "rows and out must live in the same memory");
+  const size_t n = (size_t)rows->n_sites;
+  if (n == 0) return AVO_OK;
+  if (!ref_len || !rows->emitted || !rows->n_alt || !rows->n_ref || !rows->n_other || !rows->gq ||
+      !rows->total_cov || !rows->allele_cov || !rows->fisher || !rows->rms_mapq || !out->emit ||
+      !out->rewritten || !out->filters_applied || !out->filters_failed || !out->n_alt || !out->n_ref ||
+      !out->gq_valid)
+    return fail(ctx, AVO_E_INVALID, "NULL column");
+  DFilterIn I{};
+  I.n = rows->n_sites;
+  DFilterOut O{};
+  const size_t osz[7] = {n, n, n, n * 4, n * 4, n * 4, n};
+  void* odst[7] = {out->emit, out->rewritten, out->filters_applied, out->filters_failed, out->n_alt,
+                   out->n_ref, out->gq_valid};
+  void* odev[7];
+  if (rows->mem == AVO_MEM_DEVICE) {
+    I.emitted = rows->emitted; I.ref_len = ref_len; I.alt_len = alt_len; I.n_alt = rows->n_alt;
+    I.n_ref = rows->n_ref; I.n_other = rows->n_other; I.gq = rows->gq; I.total_cov = rows->total_cov;
+    I.allele_cov = rows->allele_cov; I.fisher = rows->fisher; I.rms_mapq = rows->rms_mapq;
+    for (int k = 0; k < 7; ++k) odev[k] = odst[k];
+  } else {
+    // one staging block in, one out
+    const void* src[11] = {rows->emitted, ref_len, alt_len, rows->n_alt, rows->n_ref, rows->n_other, rows->gq,
+                           rows->total_cov, rows->allele_cov, rows->fisher, rows->rms_mapq};
+    const size_t isz[11] = {n, n * 4, alt_len ? n * 4 : 0, n * 4, n * 4, n * 4, n * 4, n * 4, n * 4, n * 4, n * 4};
+    size_t off[12]; off[0] = 0;
+    for (int k = 0; k < 11; ++k) off[k + 1] = off[k] + align_up(isz[k], 256);
+    void* blk;
+    CKS(get_buf(ctx, SL_F_IN, off[11], &blk));
+    const char* b = (const char*)blk;
+    for (int k = 0; k < 11; ++k)
+      if (isz[k]) {
+        CK(cudaMemcpyAsync((char*)blk + off[k], src[k], isz[k], cudaMemcpyHostToDevice, ctx->stream));
+        ctx->timing.h2d_bytes += (int64_t)isz[k];
+      }
+    I.emitted = (const uint8_t*)(b + off[0]); I.ref_len = (const int32_t*)(b + off[1]);
+    I.alt_len = alt_len ? (const int32_t*)(b + off[2]) : nullptr;
+    I.n_alt = (const int32_t*)(b + off[3]); I.n_ref = (const int32_t*)(b + off[4]);
+    I.n_other = (const int32_t*)(b + off[5]); I.gq = (const int32_t*)(b + off[6]);
+    I.total_cov = (const int32_t*)(b + off[7]); I.allele_cov = (const int32_t*)(b + off[8]);
+    I.fisher = (const float*)(b + off[9]); I.rms_mapq = (const float*)(b + off[10]);
+    size_t oo[8]; oo[0] = 0;
+    for (int k = 0; k < 7; ++k) oo[k + 1] = oo[k] + align_up(osz[k], 256);
+    void* ob;
+    CKS(get_buf(ctx, SL_F_OUT, oo[7], &ob));
+    for (int k = 0; k < 7; ++k) odev[k] = (char*)ob + oo[k];
+  }
+  O.emit = (uint8_t*)odev[0]; O.rewritten = (uint8_t*)odev[1]; O.filters_applied = (uint8_t*)odev[2];
+  O.filters_failed = (uint32_t*)odev[3]; O.n_alt = (int32_t*)odev[4]; O.n_ref = (int32_t*)odev[5];
+  O.gq_valid = (uint8_t*)odev[6];
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  CK(launch_filter_genotypes(I, *params, O, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  ctx->timing.n_launches += 1;
+  if (rows->mem == AVO_MEM_HOST)
+    for (int k = 0; k < 7; ++k) {
+      CK(cudaMemcpyAsync(odst[k], odev[k], osz[k], cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->timing.d2h_bytes += (int64_t)osz[k];
+    }
+  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.ms_total = ev_ms(ctx, 0, 7);
+  ctx->timing.ms_observe = ev_ms(ctx, 4, 5);
   return AVO_OK;
 }
 

@@ -105,6 +105,23 @@ cudaError_t launch_joint_counts(const DJointIn& J, int32_t* alt, int32_t* called
 cudaError_t launch_joint_recall(const DJointIn& J, const int32_t* alt, const int32_t* called,
                                 const DJointOut& O, const double* lgam, cudaStream_t s);
 
+// ---- RewriteHets + HardFilterGenotypes (avo_filter.cu) ------------------------------------------
+struct DFilterIn {
+  int64_t n;
+  const uint8_t* emitted;
+  const int32_t *ref_len, *alt_len;     // alt_len may be null (no alternate allele anywhere)
+  const int32_t *n_alt, *n_ref, *n_other, *gq, *total_cov, *allele_cov;
+  const float *fisher, *rms_mapq;
+};
+struct DFilterOut {
+  uint8_t *emit, *rewritten, *filters_applied;
+  uint32_t* filters_failed;
+  int32_t *n_alt, *n_ref;
+  uint8_t* gq_valid;
+};
+cudaError_t launch_filter_genotypes(const DFilterIn& I, const avo_filter_params& A, const DFilterOut& O,
+                                    cudaStream_t s);
+
 // batch statistics produced by k_batch_stats
 struct BatchStats {
   int32_t min_start;

@@ -70,5 +70,9 @@ class Genotype:
     # set by JointAnnotatorCaller
     genotypePosteriors: Optional[List[float]] = None
     genotypePriors: Optional[List[float]] = None
+    # set by HardFilterGenotypes (VariantCallingAnnotations.filtersApplied / filtersPassed / filtersFailed)
+    filtersApplied: Optional[bool] = None
+    filtersPassed: Optional[bool] = None
+    filtersFailed: Optional[List[str]] = None
     # raw per-site aggregate (Observation), kept for parity checks
     observation: dict = field(default_factory=dict)

@@ -293,6 +293,46 @@ int avo_call_all_sites(avo_ctx* ctx, const avo_read_batch* reads, const avo_site
                        const avo_cnv* cnv, const avo_params* params, avo_site_results* out,
                        avo_ref_model_out* ref_model);
 
+/* ---- RewriteHets + HardFilterGenotypes (the CLI's post passes, CLI/BiallelicGenotyper.scala:279-282) -- */
+/* Thresholds of RewriteHetsArgs (RewriteHets.scala:24-49) and HardFilterGenotypesArgs
+ * (HardFilterGenotypes.scala:34-166); a hard filter is applied iff its threshold is > 0. */
+typedef struct {
+  int32_t min_quality;
+  int32_t filter_ref_genotypes;  /* HardFilterGenotypes.apply(filterRefGenotypes): the CLI passes !scoreAllSites */
+  int32_t emit_all_genotypes;
+  int32_t disable_het_snp_rewriting;
+  int32_t disable_het_indel_rewriting;
+  int32_t min_snp_depth, max_snp_depth, min_indel_depth, max_indel_depth;
+  float min_het_snp_quality_by_depth, min_hom_snp_quality_by_depth;
+  float min_het_indel_quality_by_depth, min_hom_indel_quality_by_depth;
+  float max_snp_phred_strand_bias, max_indel_phred_strand_bias;
+  float min_snp_rms_mapping_quality, min_indel_rms_mapping_quality;
+  float min_het_snp_alt_allelic_fraction, max_het_snp_alt_allelic_fraction, min_hom_snp_alt_allelic_fraction;
+  float min_het_indel_alt_allelic_fraction, max_het_indel_alt_allelic_fraction, min_hom_indel_alt_allelic_fraction;
+} avo_filter_params;
+
+/* bits of filters_failed, in the order of the reference's filter lists (:258-344):
+ * bit k (SNP) / bit 9 + k (INDEL), k = 0 HET*QD, 1 HOM*QD, 2 *MQ, 3 *FS, 4 *MINDP, 5 *MAXDP,
+ * 6 HET*MINAF, 7 HET*MAXAF, 8 HOM*MINAF */
+typedef struct {
+  int64_t n;
+  int32_t mem;
+  int32_t reserved;
+  uint8_t* emit;            /* [n] the genotype survives filterGenotype (:632-660) */
+  uint8_t* rewritten;       /* [n] RewriteHets rewrote it: alleles all ALT, genotypeQuality unset */
+  uint8_t* filters_applied; /* [n] VariantCallingAnnotations.filtersApplied */
+  uint32_t* filters_failed; /* [n] bit set of failed filters; filtersPassed = applied && failed == 0 */
+  int32_t* n_alt;           /* [n] alleles after rewriting: ALT x n_alt ++ REF x n_ref ++ OTHER_ALT x (unchanged) */
+  int32_t* n_ref;
+  uint8_t* gq_valid;        /* [n] 0: genotypeQuality was unset by the rewrite */
+} avo_filter_out;
+
+/* rows = the columns avo_call / avo_call_all_sites produced (rows->mem says where they and the
+ * other arrays live).  ref_len / alt_len: allele lengths per row; alt_len NULL or < 0 = no alternate
+ * allele (reference-model rows). */
+int avo_filter_genotypes(avo_ctx* ctx, const avo_site_results* rows, const int32_t* ref_len,
+                         const int32_t* alt_len, const avo_filter_params* params, avo_filter_out* out);
+
 /* ---- joint calling: JointAnnotatorCaller.apply (JointAnnotatorCaller.scala:52-64, 74-281) ------ */
 /* Genotypes of S samples at the same N (squared-off) sites, sample-major: entry [s * n_sites + i].
  * The per-sample columns are the ones avo_call produces (n_alt, n_ref, n_other, gl). */

@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=8_000_000, help="reads in the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-bins", type=int, default=8, help="region bins the e2e leg is cut into")
-    ap.add_argument("--e2e-threads", type=int, default=3,
+    ap.add_argument("--e2e-threads", type=int, default=4,
                     help="host threads (one context + stream each) that pipeline the e2e bins")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()

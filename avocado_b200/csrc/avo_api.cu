@@ -489,24 +489,24 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
   void *d_rbase, *d_blen, *d_boff, *d_buckets;
   CKS(get_buf(ctx, SL_C_RBASE, (size_t)(T.n + 1) * 4, &d_rbase));
   CKS(get_buf(ctx, SL_C_BLEN, (size_t)(T.n + 1) * 4, &d_blen));
-  CKS(get_buf(ctx, SL_C_BOFF, (size_t)(T.n + 1) * 4, &d_boff));
+  CKS(get_buf(ctx, SL_C_BOFF, (size_t)(T.n + 1) * 8, &d_boff));
   const size_t tb2 = call_scan_temp_bytes(T.n);
   CKS(get_buf(ctx, SL_TEMP, tb2, &d_temp));
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   int nl = 0;
   size_t n_slots = 0;
   if (R.n > 0 && S.c_hi > S.c_lo) {
-    CK(launch_call_buckets(R, S, X, hs, (int32_t*)d_rbase, (uint32_t*)d_blen, (uint32_t*)d_boff, d_temp, tb2,
+    CK(launch_call_buckets(R, S, X, hs, (int32_t*)d_rbase, (uint32_t*)d_blen, (uint64_t*)d_boff, d_temp, tb2,
                            ctx->stream, &nl));
-    CK(cudaMemcpyAsync(ctx->h_small, (uint32_t*)d_boff + S.c_hi, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_small, (uint64_t*)d_boff + S.c_hi, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    n_slots = (size_t)(uint32_t)ctx->h_small[0];
+    n_slots = (size_t)*reinterpret_cast<const uint64_t*>(ctx->h_small);
   }
   CKS(get_buf(ctx, SL_C_BUCKETS, n_slots * 4, &d_buckets));
   void* d_jlist;
   CKS(get_buf(ctx, SL_AS_JR, (size_t)R.n * 12, &d_jlist));
   CK(launch_call_tiles(R, S, C, P, D, X, (const int32_t*)d_rbase, (const uint32_t*)d_blen,
-                       (const uint32_t*)d_boff, (uint32_t*)d_buckets, n_slots, d_jlist, small + 8,
+                       (const uint64_t*)d_boff, (uint32_t*)d_buckets, n_slots, d_jlist, small + 8,
                        ctx->num_sms, ctx->stream, &nl));
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
   ctx->timing.n_launches += nl;

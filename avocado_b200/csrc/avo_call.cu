@@ -20,6 +20,7 @@
 //  k_call_reduce   one THREAD per site scans its bucket in slot order = batch read order, adds the
 //                  table rows in fp64 in that order (the oracle's order), and emits the row.
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include "avo_device.cuh"
 #include "avo_observe.cuh"
@@ -69,7 +70,7 @@ __global__ void k_site_buckets(DReads R, DSites S, DIndex X, int32_t max_span, i
 // observes, written to that site's bucket (BG:195-393 incl. the other-alt pass and copy number).
 __device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
                              int32_t r, int32_t a, int32_t b, const int32_t* __restrict__ rbase,
-                             const uint32_t* __restrict__ boff, uint32_t* __restrict__ buckets) {
+                             const uint64_t* __restrict__ boff, uint32_t* __restrict__ buckets) {
   const MetaA ma = load_meta_a(R.meta, r);
   const MetaB mb = load_meta_b(R.meta, r);
   // observeRead throws for such reads (BG:385-391: skipped); no operators -> no observations
@@ -193,7 +194,7 @@ k_call_join(DReads R, DSites S, DIndex X, JoinedRead* __restrict__ list, int32_t
 __global__ void __launch_bounds__(OBS_THREADS, AVO_CALL_MINB)
 k_call_observe(DReads R, DSites S, DCnv C, DCallParams P, const JoinedRead* __restrict__ list,
                const int32_t* __restrict__ n_list, const int32_t* __restrict__ rbase,
-               const uint32_t* __restrict__ boff, uint32_t* __restrict__ buckets) {
+               const uint64_t* __restrict__ boff, uint32_t* __restrict__ buckets) {
   const int32_t n = *n_list;
   for (int32_t i = blockIdx.x * OBS_THREADS + threadIdx.x; i < n; i += gridDim.x * OBS_THREADS) {
     const JoinedRead j = list[i];
@@ -207,7 +208,7 @@ k_call_observe(DReads R, DSites S, DCnv C, DCallParams P, const JoinedRead* __re
 // so only the selected category's array is touched.
 template <int NS>
 __global__ void __launch_bounds__(128)
-k_call_reduce(DSites S, DCallParams P, DResults O, const uint32_t* __restrict__ boff,
+k_call_reduce(DSites S, DCallParams P, DResults O, const uint64_t* __restrict__ boff,
               const uint32_t* __restrict__ blen, const uint32_t* __restrict__ buckets) {
   const int32_t j = S.c_lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= S.c_hi) return;
@@ -264,22 +265,29 @@ k_call_reduce(DSites S, DCallParams P, DResults O, const uint32_t* __restrict__ 
 }
 
 // ---- launchers --------------------------------------------------------------------------------------
+// bucket lengths are 32-bit, their prefix sums 64-bit (a batch with one very long read span can need
+// more than 2^32 slots; the allocation then fails cleanly instead of the offsets wrapping)
+struct LenTo64 {
+  __host__ __device__ unsigned long long operator()(uint32_t v) const { return (unsigned long long)v; }
+};
 size_t call_scan_temp_bytes(int32_t n) {
   size_t a = 0;
-  cub::DeviceScan::ExclusiveSum((void*)nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, n + 1);
+  cub::TransformInputIterator<unsigned long long, LenTo64, const uint32_t*> it(nullptr, LenTo64());
+  cub::DeviceScan::ExclusiveSum((void*)nullptr, a, it, (unsigned long long*)nullptr, n + 1);
   return a + 256;
 }
 
 // rbase / blen / boff: [S.n + 1] scratch.  boff[c_hi] (device) = total number of slots.
 cudaError_t launch_call_buckets(const DReads& R, const DSites& S, const DIndex& X, const BatchStats& hstats, int32_t* rbase,
-                                uint32_t* blen, uint32_t* boff, void* d_temp, size_t temp_bytes,
+                                uint32_t* blen, uint64_t* boff, void* d_temp, size_t temp_bytes,
                                 cudaStream_t s, int* n_launches) {
   const int32_t n = S.c_hi - S.c_lo;
   if (n <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(blen + S.c_hi, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
   k_site_buckets<<<(n + 127) / 128, 128, 0, s>>>(R, S, X, hstats.max_span, rbase, blen);
-  e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, blen + S.c_lo, boff + S.c_lo, n + 1, s);
+  cub::TransformInputIterator<unsigned long long, LenTo64, const uint32_t*> it(blen + S.c_lo, LenTo64());
+  e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, it, (unsigned long long*)(boff + S.c_lo), n + 1, s);
   if (e != cudaSuccess) return e;
   if (n_launches) *n_launches += 2;
   return cudaGetLastError();
@@ -287,7 +295,7 @@ cudaError_t launch_call_buckets(const DReads& R, const DSites& S, const DIndex& 
 
 cudaError_t launch_call_tiles(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
                               const DResults& out, const DIndex& X, const int32_t* rbase,
-                              const uint32_t* blen, const uint32_t* boff, uint32_t* buckets,
+                              const uint32_t* blen, const uint64_t* boff, uint32_t* buckets,
                               size_t n_slots, void* joined_list, int32_t* d_counter, int num_sms,
                               cudaStream_t s, int* n_launches) {
   cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int32_t), s);

@@ -164,11 +164,11 @@ cudaError_t launch_build_site_index(const DSites& S, const BatchStats& hstats, i
 // call: per-site buckets (one slot per read that can overlap the site), observe, reduce
 size_t call_scan_temp_bytes(int32_t n);
 cudaError_t launch_call_buckets(const DReads& R, const DSites& S, const DIndex& X, const BatchStats& hstats, int32_t* rbase,
-                                uint32_t* blen, uint32_t* boff, void* d_temp, size_t temp_bytes,
+                                uint32_t* blen, uint64_t* boff, void* d_temp, size_t temp_bytes,
                                 cudaStream_t s, int* n_launches);
 cudaError_t launch_call_tiles(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
                               const DResults& out, const DIndex& X, const int32_t* rbase,
-                              const uint32_t* blen, const uint32_t* boff, uint32_t* buckets,
+                              const uint32_t* blen, const uint64_t* boff, uint32_t* buckets,
                               size_t n_slots, void* joined_list /* 12 B x n_reads */, int32_t* d_counter,
                               int num_sms, cudaStream_t s, int* n_launches);
 

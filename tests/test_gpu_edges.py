@@ -257,3 +257,49 @@ def test_forest_quirk_and_multi_contig_table(oracle, ctx):
         assert g.readDepth == want_all["totalCoverage"][j] and g.genotypeQuality == want_all["genotypeQuality"][j]
         cn = int(want_all["copyNumber"][j])
         assert g.genotypeLikelihoods == list(want_all["genotypeLikelihoods"][j][:cn + 1])
+
+
+def test_one_very_long_read_span(oracle, ctx):
+    """A read with a huge deletion makes the look-back (max read span) cover the whole batch: the
+    per-site buckets then hold a slot for every read.  Results must not change."""
+    from avocado_b200.genotyping import BiallelicGenotyper
+    from avocado_b200.records import AlignmentRecord
+    rng = np.random.default_rng(23)
+    bases = "ACGT"
+    ref = "".join(bases[i] for i in rng.integers(0, 4, 61000))
+    recs = []
+    for i in range(900):
+        s = int(rng.integers(0, 60000 - 120)) if i % 3 else int(rng.integers(100, 400))
+        ln = int(rng.integers(60, 110))
+        seq = list(ref[s:s + ln])
+        md, run = "", 0
+        for k in range(ln):
+            if (s + k) % 97 == 0:                                  # a shared SNV every 97 bases
+                md += "%d%s" % (run, seq[k]); run = 0
+                seq[k] = bases[(bases.index(seq[k]) + 1) % 4]
+            else:
+                run += 1
+        md += str(run)
+        recs.append(AlignmentRecord(readMapped=True, contigName="1", start=s, end=s + ln, sequence="".join(seq),
+                                    qual="".join(chr(33 + int(q)) for q in rng.integers(25, 41, ln)),
+                                    cigar="%dM" % ln, mismatchingPositions=md, mapq=50, readName="r%d" % i))
+    # the long one: 50 bases, a 50 kb deletion, 50 bases
+    s = 200
+    seq = ref[s:s + 50] + ref[s + 50 + 50000:s + 100 + 50000]
+    recs.append(AlignmentRecord(readMapped=True, contigName="1", start=s, end=s + 100 + 50000, sequence=seq,
+                                qual="I" * 100, cigar="50M50000D50M",
+                                mismatchingPositions="50^%s50" % ref[s + 50:s + 50 + 50000], mapq=50, readName="long"))
+    recs.sort(key=lambda r: r.start)
+    want_v = oracle.discover(oracle.reads_from_dicts([r.as_dict() for r in recs]), 20, 2)
+    want = oracle.call(oracle.reads_from_dicts([r.as_dict() for r in recs]),
+                       [(c, s_, e, r, a) for c, s_, e, r, a, _ in want_v], 2, [], False, 93, 93, 1)
+    gts = BiallelicGenotyper.discoverAndCall(recs, optPhredThreshold=20, optMinObservations=2, samples=["s"], ctx=ctx)
+    okey = {(int(s_), r, a): j for j, (s_, r, a) in enumerate(zip(want["start"], want["referenceAllele"],
+                                                                   want["alternateAllele"]))}
+    assert {(g.start, g.variant.referenceAllele, g.variant.alternateAllele) for g in gts} == set(okey)
+    assert len(gts) > 20
+    for g in gts:
+        j = okey[(g.start, g.variant.referenceAllele, g.variant.alternateAllele)]
+        assert (g.readDepth, g.alternateReadDepth, g.genotypeQuality) == \
+            (want["totalCoverage"][j], want["alleleCoverage"][j], want["genotypeQuality"][j])
+        assert g.genotypeLikelihoods == list(want["genotypeLikelihoods"][j][:3])

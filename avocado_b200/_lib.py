@@ -135,6 +135,21 @@ class FilterOutStruct(C.Structure):
                [(n, P) for n, _ in FILTER_OUT_COLUMNS]
 
 
+class SampleRowsStruct(C.Structure):
+    _fields_ = [("variants", C.POINTER(SitesStruct)), ("variant_rows", C.POINTER(SiteResultsStruct)),
+                ("n_ref_model", C.c_int64), ("ref_model_start", P), ("ref_model_rows", C.POINTER(SiteResultsStruct))]
+
+
+SQUARE_OUT_COLUMNS = [("kind", "uint8", 1), ("src", "int32", 1), ("n_alt", "int32", 1), ("n_ref", "int32", 1),
+                      ("n_other", "int32", 1), ("gl", "float64", "ns")]
+SQ_ABSENT, SQ_SCORED, SQ_EXCISED_VARIANT, SQ_EXCISED_REF_MODEL = range(4)
+
+
+class SquareOutStruct(C.Structure):
+    _fields_ = [("n_sites", C.c_int64), ("n_states", C.c_int32), ("mem", C.c_int32)] + \
+               [(n, P) for n, _, _ in SQUARE_OUT_COLUMNS]
+
+
 class JointInStruct(C.Structure):
     _fields_ = [("n_sites", C.c_int64), ("n_samples", C.c_int32), ("n_states", C.c_int32),
                 ("mem", C.c_int32), ("reserved", C.c_int32), ("present", P), ("n_alt", P), ("n_ref", P),
@@ -164,7 +179,7 @@ class SynthParamsStruct(C.Structure):
 EXPORTED_SYMBOLS = [
     "avo_ctx_create", "avo_ctx_destroy", "avo_last_error", "avo_version", "avo_ctx_set_stream",
     "avo_get_timing", "avo_discover", "avo_call", "avo_discover_and_call",
-    "avo_call_all_sites", "avo_filter_genotypes", "avo_joint_counts", "avo_joint",
+    "avo_call_all_sites", "avo_filter_genotypes", "avo_square_off", "avo_joint_counts", "avo_joint",
     "avo_pack_wire", "avo_pack_bounds", "avo_pack_reads", "avo_synth_default_params", "avo_synth_host",
     "avo_synth_device",
 ]
@@ -204,6 +219,7 @@ def load():
                                        C.POINTER(SiteResultsStruct), C.POINTER(RefModelOutStruct)]
     lib.avo_filter_genotypes.argtypes = [P, C.POINTER(SiteResultsStruct), P, P, C.POINTER(FilterParamsStruct),
                                          C.POINTER(FilterOutStruct)]
+    lib.avo_square_off.argtypes = [P, C.POINTER(SitesStruct), C.POINTER(SampleRowsStruct), C.POINTER(SquareOutStruct)]
     lib.avo_joint_counts.argtypes = [P, C.POINTER(JointInStruct), P, P]
     lib.avo_joint.argtypes = [P, C.POINTER(JointInStruct), C.POINTER(JointOutStruct)]
     lib.avo_pack_wire.argtypes = [C.POINTER(ReadBatchStruct), P, P]

@@ -919,6 +919,91 @@ int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_c
   return AVO_OK;
 }
 
+// ---- SquareOffReferenceModel.squareOffSite ----------------------------------------------------------
+int avo_square_off(avo_ctx* ctx, const avo_sites* cohort, const avo_sample_rows* sample, avo_square_out* out) {
+  CKS(begin_call(ctx));
+  if (!cohort || !sample || !out || !sample->variants || !sample->variant_rows || !sample->ref_model_rows)
+    return fail(ctx, AVO_E_INVALID, "NULL argument");
+  const avo_sites* V = sample->variants;
+  const avo_site_results* VR = sample->variant_rows;
+  const avo_site_results* RR = sample->ref_model_rows;
+  const int mem = out->mem;
+  if ((mem != AVO_MEM_HOST && mem != AVO_MEM_DEVICE) || cohort->mem != mem || V->mem != mem || VR->mem != mem ||
+      RR->mem != mem)
+    return fail(ctx, AVO_E_INVALID, "all tables must live in the memory out->mem names");
+  if (out->n_sites != cohort->n || VR->n_sites != V->n || cohort->n >= INT32_MAX || V->n >= INT32_MAX ||
+      sample->n_ref_model >= INT32_MAX || sample->n_ref_model < 0)
+    return fail(ctx, AVO_E_INVALID, "inconsistent table sizes");
+  const int ns = out->n_states;
+  if (ns < 2 || ns > AVO_MAX_PLOIDY + 1 || VR->n_states != ns || (sample->n_ref_model > 0 && RR->n_states != ns))
+    return fail(ctx, AVO_E_INVALID, "n_states must agree");
+  const size_t N = (size_t)cohort->n, nv = (size_t)V->n, nr = (size_t)sample->n_ref_model;
+  if (N == 0) return AVO_OK;
+  // host tables are staged through stream-ordered allocations (this entry point is not a hot loop)
+  std::vector<void*> tmp;
+  auto release = [&]() { for (void* q : tmp) cudaFreeAsync(q, ctx->stream); };
+  cudaError_t cerr = cudaSuccess;
+  auto in = [&](const void* src, size_t bytes) -> const void* {
+    if (mem == AVO_MEM_DEVICE || bytes == 0 || !src) return src;
+    void* d = nullptr;
+    if (cerr == cudaSuccess) cerr = cudaMallocAsync(&d, bytes, ctx->stream);
+    if (cerr == cudaSuccess) { tmp.push_back(d); cerr = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream); }
+    ctx->timing.h2d_bytes += (int64_t)bytes;
+    return d;
+  };
+  int32_t max_ref_len = 1;
+  if (mem == AVO_MEM_HOST) {
+    for (size_t k = 0; k < nv; ++k) max_ref_len = std::max(max_ref_len, V->ref_len[k]);
+  } else {
+    max_ref_len = 1 << 16;    // device tables: bound of the allele length (uint16 in discovery keys)
+  }
+  DSquareIn I{};
+  I.n_sites = (int32_t)N; I.n_v = (int32_t)nv; I.n_r = (int32_t)nr; I.ns = ns; I.v_max_ref_len = max_ref_len;
+  I.c_start = (const int32_t*)in(cohort->start, N * 4); I.c_ref_len = (const int32_t*)in(cohort->ref_len, N * 4);
+  I.c_alt_len = (const int32_t*)in(cohort->alt_len, N * 4);
+  I.c_allele_off = (const uint32_t*)in(cohort->allele_off, (N + 1) * 4);
+  I.c_alleles4 = (const uint8_t*)in(cohort->alleles4, (size_t)(cohort->n_allele_nibbles + 1) / 2);
+  I.v_start = (const int32_t*)in(V->start, nv * 4); I.v_ref_len = (const int32_t*)in(V->ref_len, nv * 4);
+  I.v_alt_len = (const int32_t*)in(V->alt_len, nv * 4); I.v_allele_off = (const uint32_t*)in(V->allele_off, (nv + 1) * 4);
+  I.v_alleles4 = (const uint8_t*)in(V->alleles4, (size_t)(V->n_allele_nibbles + 1) / 2);
+  I.v_emitted = (const uint8_t*)in(VR->emitted, nv); I.v_n_alt = (const int32_t*)in(VR->n_alt, nv * 4);
+  I.v_n_ref = (const int32_t*)in(VR->n_ref, nv * 4); I.v_n_other = (const int32_t*)in(VR->n_other, nv * 4);
+  I.v_gl = (const double*)in(VR->gl, nv * ns * 8); I.v_nonref_gl = (const double*)in(VR->nonref_gl, nv * ns * 8);
+  I.r_start = (const int32_t*)in(sample->ref_model_start, nr * 4); I.r_emitted = (const uint8_t*)in(RR->emitted, nr);
+  I.r_n_alt = (const int32_t*)in(RR->n_alt, nr * 4); I.r_n_ref = (const int32_t*)in(RR->n_ref, nr * 4);
+  I.r_n_other = (const int32_t*)in(RR->n_other, nr * 4); I.r_nonref_gl = (const double*)in(RR->nonref_gl, nr * ns * 8);
+  DSquareOut O{};
+  const size_t osz[6] = {N, N * 4, N * 4, N * 4, N * 4, N * ns * 8};
+  void* odst[6] = {out->kind, out->src, out->n_alt, out->n_ref, out->n_other, out->gl};
+  void* odev[6];
+  for (int k = 0; k < 6; ++k) {
+    if (!odst[k]) { release(); return fail(ctx, AVO_E_INVALID, "square-off output has NULL columns"); }
+    odev[k] = odst[k];
+    if (mem == AVO_MEM_HOST && cerr == cudaSuccess) {
+      cerr = cudaMallocAsync(&odev[k], osz[k], ctx->stream);
+      if (cerr == cudaSuccess) tmp.push_back(odev[k]);
+    }
+  }
+  if (cerr != cudaSuccess) { release(); return fail(ctx, AVO_E_CUDA, "staging failed: %s", cudaGetErrorString(cerr)); }
+  O.kind = (uint8_t*)odev[0]; O.src = (int32_t*)odev[1]; O.n_alt = (int32_t*)odev[2]; O.n_ref = (int32_t*)odev[3];
+  O.n_other = (int32_t*)odev[4]; O.gl = (double*)odev[5];
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  CK(launch_square_off(I, O, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  ctx->timing.n_launches += 1;
+  if (mem == AVO_MEM_HOST)
+    for (int k = 0; k < 6; ++k) {
+      CK(cudaMemcpyAsync(odst[k], odev[k], osz[k], cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->timing.d2h_bytes += (int64_t)osz[k];
+    }
+  release();
+  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.ms_total = ev_ms(ctx, 0, 7);
+  ctx->timing.ms_observe = ev_ms(ctx, 4, 5);
+  return AVO_OK;
+}
+
 // ---- RewriteHets + HardFilterGenotypes ---------------------------------------------------------------
 int avo_filter_genotypes(avo_ctx* ctx, const avo_site_results* rows, const int32_t* ref_len,
                          const int32_t* alt_len, const avo_filter_params* params, avo_filter_out* out) {

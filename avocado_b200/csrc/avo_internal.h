@@ -122,6 +122,20 @@ struct DFilterOut {
 cudaError_t launch_filter_genotypes(const DFilterIn& I, const avo_filter_params& A, const DFilterOut& O,
                                     cudaStream_t s);
 
+// ---- SquareOffReferenceModel (avo_squareoff.cu) ---------------------------------------------------
+struct DSquareIn {
+  int32_t n_sites, n_v, n_r, ns, v_max_ref_len;
+  const int32_t *c_start, *c_ref_len, *c_alt_len; const uint32_t* c_allele_off; const uint8_t* c_alleles4;
+  const int32_t *v_start, *v_ref_len, *v_alt_len; const uint32_t* v_allele_off; const uint8_t* v_alleles4;
+  const uint8_t* v_emitted; const int32_t *v_n_alt, *v_n_ref, *v_n_other; const double *v_gl, *v_nonref_gl;
+  const int32_t* r_start; const uint8_t* r_emitted; const int32_t *r_n_alt, *r_n_ref, *r_n_other;
+  const double* r_nonref_gl;
+};
+struct DSquareOut {
+  uint8_t* kind; int32_t* src; int32_t *n_alt, *n_ref, *n_other; double* gl;
+};
+cudaError_t launch_square_off(const DSquareIn& I, const DSquareOut& O, cudaStream_t s);
+
 // batch statistics produced by k_batch_stats
 struct BatchStats {
   int32_t min_start;

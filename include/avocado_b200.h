@@ -333,6 +333,37 @@ typedef struct {
 int avo_filter_genotypes(avo_ctx* ctx, const avo_site_results* rows, const int32_t* ref_len,
                          const int32_t* alt_len, const avo_filter_params* params, avo_filter_out* out);
 
+/* ---- SquareOffReferenceModel.squareOffSite (SquareOffReferenceModel.scala:176-244) ---------------- */
+/* One sample's gVCF rows (the outputs of avo_call_all_sites for that sample) joined to the cohort's
+ * site list: one row of the (samples x sites) matrix avo_joint consumes.  All tables are those of
+ * ONE contig.  kind[j]: how the sample is represented at site j. */
+enum {
+  AVO_SQ_ABSENT = 0,            /* no genotype of the sample overlaps the site */
+  AVO_SQ_SCORED = 1,            /* hasScoredVariant: the sample's own row for exactly this variant */
+  AVO_SQ_EXCISED_VARIANT = 2,   /* excised from an overlapping variant row: gl := its nonReferenceLikelihoods */
+  AVO_SQ_EXCISED_REF_MODEL = 3  /* excised from the reference-model row at the site */
+};
+typedef struct {
+  const avo_sites* variants;          /* the sample's variant table (as given to avo_call_all_sites) */
+  const avo_site_results* variant_rows;
+  int64_t n_ref_model;                /* the sample's reference-model rows */
+  const int32_t* ref_model_start;     /* [n_ref_model] ascending */
+  const avo_site_results* ref_model_rows;
+} avo_sample_rows;
+typedef struct {
+  int64_t n_sites;   /* == cohort->n */
+  int32_t n_states;
+  int32_t mem;
+  uint8_t* kind;     /* [N] AVO_SQ_* */
+  int32_t* src;      /* [N] row index in the table `kind` names, or -1 */
+  int32_t* n_alt;    /* [N] alleles of the representing genotype */
+  int32_t* n_ref;
+  int32_t* n_other;
+  double* gl;        /* [N * n_states] genotypeLikelihoods of the squared-off genotype */
+} avo_square_out;
+/* Every table lives where out->mem says (all host or all device). */
+int avo_square_off(avo_ctx* ctx, const avo_sites* cohort, const avo_sample_rows* sample, avo_square_out* out);
+
 /* ---- joint calling: JointAnnotatorCaller.apply (JointAnnotatorCaller.scala:52-64, 74-281) ------ */
 /* Genotypes of S samples at the same N (squared-off) sites, sample-major: entry [s * n_sites + i].
  * The per-sample columns are the ones avo_call produces (n_alt, n_ref, n_other, gl). */

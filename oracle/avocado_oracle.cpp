@@ -1304,6 +1304,53 @@ static FilterResult filterGenotype(const FilterGt& g, const FilterArgs& A, bool 
   return r;
 }
 
+// ---------------------------------------------------------------------------
+// CORE/genotyping/SquareOffReferenceModel.scala:68-245 -- cohort site extraction from per-sample
+// gVCF genotypes and the squaring off of every site against every sample.
+// ---------------------------------------------------------------------------
+static int trimRight(const std::string& ref, const std::string& alt) {               // :95-117
+  if (ref.empty() || alt.empty()) return 0;
+  size_t i = ref.size(), j = alt.size();
+  int trimmed = 0;
+  for (;;) {
+    --i; --j;
+    if (ref[i] != alt[j]) return trimmed;
+    if (!(i > 0 && j > 0)) return trimmed;        // one of the iterators is exhausted
+    ++trimmed;
+  }
+}
+
+struct SqGt {            // what squareOffSite reads of a Genotype
+  std::string sample, contig, ref, alt;
+  bool hasAlt = false;
+  long start = 0, end = 0;
+  int row = -1;          // caller's handle
+};
+
+// squareOffSite (:176-189) for one sample: index into `gts` of the genotype that represents the
+// sample at the variant and whether it was excised from an overlapping genotype (its
+// genotypeLikelihoods are then replaced by its nonReferenceLikelihoods, :224-244).
+// `find` takes the first overlapping genotype in Spark's (unspecified) grouping order; the canonical
+// order fixed here and in the kernel: lowest (start, end), a genotype with an alternate allele
+// before one without.
+static std::pair<int, bool> squareOffSample(const std::string& contig, long start, long end, const std::string& ref,
+                                            const std::string& alt, const std::vector<SqGt>& gts) {
+  for (size_t k = 0; k < gts.size(); ++k) {                                           // hasScoredVariant :198-208
+    const SqGt& g = gts[k];
+    if (g.start == start && g.end == end && g.contig == contig && g.ref == ref && g.hasAlt && g.alt == alt)
+      return {(int)k, false};
+  }
+  int best = -1;
+  for (size_t k = 0; k < gts.size(); ++k) {                                           // excise :224-232
+    const SqGt& g = gts[k];
+    if (!(g.contig == contig && g.start < end && g.end > start)) continue;
+    if (best < 0) { best = (int)k; continue; }
+    const SqGt& b = gts[best];
+    if (std::make_tuple(g.start, g.end, g.hasAlt ? 0 : 1) < std::make_tuple(b.start, b.end, b.hasAlt ? 0 : 1)) best = (int)k;
+  }
+  return {best, best >= 0};
+}
+
 }  // namespace orc
 
 // ===========================================================================
@@ -1819,5 +1866,21 @@ PYBIND11_MODULE(avocado_oracle, m) {
     d["emitted"] = r.emitted; d["filtersApplied"] = r.filtersApplied; d["filtersPassed"] = r.passed;
     d["filtersFailed"] = r.failed;
     return d;
+  });
+  // ---- SquareOffReferenceModel ---------------------------------------------------------------
+  m.def("trim_right", &trimRight);
+  // square_off_sample(variant (contig, start, end, ref, alt), genotypes [(contig, start, end, ref, alt|None)])
+  //   -> (index of the genotype used or -1, excised?)
+  m.def("square_off_sample", [](const std::tuple<std::string, long, long, std::string, std::string>& v,
+                                const std::vector<std::tuple<std::string, long, long, std::string, py::object>>& gts) {
+    std::vector<SqGt> g;
+    for (auto& t : gts) {
+      SqGt x;
+      x.contig = std::get<0>(t); x.start = std::get<1>(t); x.end = std::get<2>(t); x.ref = std::get<3>(t);
+      x.hasAlt = !std::get<4>(t).is_none();
+      if (x.hasAlt) x.alt = std::get<4>(t).cast<std::string>();
+      g.push_back(x);
+    }
+    return squareOffSample(std::get<0>(v), std::get<1>(v), std::get<2>(v), std::get<3>(v), std::get<4>(v), g);
   });
 }

@@ -150,6 +150,14 @@ class SquareOutStruct(C.Structure):
                [(n, P) for n, _, _ in SQUARE_OUT_COLUMNS]
 
 
+class TrioStruct(C.Structure):
+    _fields_ = [("n_sites", C.c_int64), ("mem", C.c_int32), ("reserved", C.c_int32), ("present", P), ("n_alt", P),
+                ("n_ref", P), ("n_other", P), ("n_nocall", P), ("kept", P), ("child_action", P), ("filled", P)]
+
+
+TRIO_UNCHANGED, TRIO_PHASED, TRIO_NO_CALL, TRIO_PHASED_ALT_REF, TRIO_PHASED_REF_ALT = range(5)
+
+
 class JointInStruct(C.Structure):
     _fields_ = [("n_sites", C.c_int64), ("n_samples", C.c_int32), ("n_states", C.c_int32),
                 ("mem", C.c_int32), ("reserved", C.c_int32), ("present", P), ("n_alt", P), ("n_ref", P),
@@ -179,7 +187,7 @@ class SynthParamsStruct(C.Structure):
 EXPORTED_SYMBOLS = [
     "avo_ctx_create", "avo_ctx_destroy", "avo_last_error", "avo_version", "avo_ctx_set_stream",
     "avo_get_timing", "avo_discover", "avo_call", "avo_discover_and_call",
-    "avo_call_all_sites", "avo_filter_genotypes", "avo_square_off", "avo_joint_counts", "avo_joint",
+    "avo_call_all_sites", "avo_filter_genotypes", "avo_square_off", "avo_trio_call", "avo_joint_counts", "avo_joint",
     "avo_pack_wire", "avo_pack_bounds", "avo_pack_reads", "avo_synth_default_params", "avo_synth_host",
     "avo_synth_device",
 ]
@@ -220,6 +228,7 @@ def load():
     lib.avo_filter_genotypes.argtypes = [P, C.POINTER(SiteResultsStruct), P, P, C.POINTER(FilterParamsStruct),
                                          C.POINTER(FilterOutStruct)]
     lib.avo_square_off.argtypes = [P, C.POINTER(SitesStruct), C.POINTER(SampleRowsStruct), C.POINTER(SquareOutStruct)]
+    lib.avo_trio_call.argtypes = [P, C.POINTER(TrioStruct)]
     lib.avo_joint_counts.argtypes = [P, C.POINTER(JointInStruct), P, P]
     lib.avo_joint.argtypes = [P, C.POINTER(JointInStruct), C.POINTER(JointOutStruct)]
     lib.avo_pack_wire.argtypes = [C.POINTER(ReadBatchStruct), P, P]

@@ -1004,6 +1004,54 @@ int avo_square_off(avo_ctx* ctx, const avo_sites* cohort, const avo_sample_rows*
   return AVO_OK;
 }
 
+// ---- TrioCaller ------------------------------------------------------------------------------------
+int avo_trio_call(avo_ctx* ctx, avo_trio* t) {
+  CKS(begin_call(ctx));
+  if (!t) return fail(ctx, AVO_E_INVALID, "trio is NULL");
+  if (t->n_sites < 0 || (t->mem != AVO_MEM_HOST && t->mem != AVO_MEM_DEVICE)) return fail(ctx, AVO_E_INVALID, "bad trio");
+  const size_t n = (size_t)t->n_sites;
+  if (n == 0) return AVO_OK;
+  if (!t->n_alt || !t->n_ref || !t->n_other || !t->kept || !t->child_action || !t->filled)
+    return fail(ctx, AVO_E_INVALID, "trio has NULL columns");
+  std::vector<void*> tmp;
+  cudaError_t cerr = cudaSuccess;
+  auto in = [&](const void* src, size_t bytes) -> const void* {
+    if (t->mem == AVO_MEM_DEVICE || !src) return src;
+    void* d = nullptr;
+    if (cerr == cudaSuccess) cerr = cudaMallocAsync(&d, bytes, ctx->stream);
+    if (cerr == cudaSuccess) { tmp.push_back(d); cerr = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream); }
+    return d;
+  };
+  DTrioIn I{};
+  I.n_sites = t->n_sites;
+  I.present = (const uint8_t*)in(t->present, 3 * n);
+  I.n_alt = (const int32_t*)in(t->n_alt, 12 * n); I.n_ref = (const int32_t*)in(t->n_ref, 12 * n);
+  I.n_other = (const int32_t*)in(t->n_other, 12 * n); I.n_nocall = (const int32_t*)in(t->n_nocall, 12 * n);
+  void* odst[3] = {t->kept, t->child_action, t->filled};
+  void* odev[3] = {t->kept, t->child_action, t->filled};
+  if (t->mem == AVO_MEM_HOST)
+    for (int k = 0; k < 3 && cerr == cudaSuccess; ++k) {
+      cerr = cudaMallocAsync(&odev[k], n, ctx->stream);
+      if (cerr == cudaSuccess) tmp.push_back(odev[k]);
+    }
+  if (cerr != cudaSuccess) {
+    for (void* q : tmp) cudaFreeAsync(q, ctx->stream);
+    return fail(ctx, AVO_E_CUDA, "staging failed: %s", cudaGetErrorString(cerr));
+  }
+  DTrioOut O{(uint8_t*)odev[0], (uint8_t*)odev[1], (uint8_t*)odev[2]};
+  cerr = launch_trio(I, O, ctx->stream);
+  ctx->timing.n_launches += 1;
+  if (cerr == cudaSuccess && t->mem == AVO_MEM_HOST)
+    for (int k = 0; k < 3 && cerr == cudaSuccess; ++k)
+      cerr = cudaMemcpyAsync(odst[k], odev[k], n, cudaMemcpyDeviceToHost, ctx->stream);
+  for (void* q : tmp) cudaFreeAsync(q, ctx->stream);
+  if (cerr != cudaSuccess) return fail(ctx, AVO_E_CUDA, "trio: %s", cudaGetErrorString(cerr));
+  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.ms_total = ev_ms(ctx, 0, 7);
+  return AVO_OK;
+}
+
 // ---- RewriteHets + HardFilterGenotypes ---------------------------------------------------------------
 int avo_filter_genotypes(avo_ctx* ctx, const avo_site_results* rows, const int32_t* ref_len,
                          const int32_t* alt_len, const avo_filter_params* params, avo_filter_out* out) {

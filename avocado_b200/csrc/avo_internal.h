@@ -136,6 +136,11 @@ struct DSquareOut {
 };
 cudaError_t launch_square_off(const DSquareIn& I, const DSquareOut& O, cudaStream_t s);
 
+// ---- TrioCaller (avo_trio.cu) ------------------------------------------------------------------------
+struct DTrioIn { int64_t n_sites; const uint8_t* present; const int32_t *n_alt, *n_ref, *n_other, *n_nocall; };
+struct DTrioOut { uint8_t *kept, *child_action, *filled; };
+cudaError_t launch_trio(const DTrioIn& I, const DTrioOut& O, cudaStream_t s);
+
 // batch statistics produced by k_batch_stats
 struct BatchStats {
   int32_t min_start;

@@ -74,5 +74,7 @@ class Genotype:
     filtersApplied: Optional[bool] = None
     filtersPassed: Optional[bool] = None
     filtersFailed: Optional[List[str]] = None
+    # set by TrioCaller
+    phased: bool = False
     # raw per-site aggregate (Observation), kept for parity checks
     observation: dict = field(default_factory=dict)

@@ -364,6 +364,33 @@ typedef struct {
 /* Every table lives where out->mem says (all host or all device). */
 int avo_square_off(avo_ctx* ctx, const avo_sites* cohort, const avo_sample_rows* sample, avo_square_out* out);
 
+/* ---- TrioCaller.processVariant (TrioCaller.scala:86-221) ------------------------------------------ */
+enum {
+  AVO_TRIO_UNCHANGED = 0,      /* child genotype kept as it is */
+  AVO_TRIO_PHASED = 1,         /* confirmed: phased = true, alleles as called */
+  AVO_TRIO_NO_CALL = 2,        /* inconsistent with the parents: NO_CALL x 2, genotypeQuality unset */
+  AVO_TRIO_PHASED_ALT_REF = 3, /* het phased from the first parent: alleles [ALT, REF], phased */
+  AVO_TRIO_PHASED_REF_ALT = 4  /* het phased from the second parent: alleles [REF, ALT], phased */
+};
+/* The three samples (first parent, second parent, child) at N sites: the rows s = 0, 1, 2 of the
+ * (samples x sites) matrix, sample-major like avo_joint_in.  Outputs per site: kept (the site has an
+ * ALT allele before and after processing, :92-96), child_action (AVO_TRIO_*), filled (bit s set:
+ * sample s had no genotype and is emitted as NO_CALL x 2, :209-216). */
+typedef struct {
+  int64_t n_sites;
+  int32_t mem;
+  int32_t reserved;
+  const uint8_t* present;  /* [3*N] NULL = all present */
+  const int32_t* n_alt;    /* [3*N] */
+  const int32_t* n_ref;
+  const int32_t* n_other;
+  const int32_t* n_nocall; /* NULL = none */
+  uint8_t* kept;           /* [N] out */
+  uint8_t* child_action;   /* [N] out */
+  uint8_t* filled;         /* [N] out */
+} avo_trio;
+int avo_trio_call(avo_ctx* ctx, avo_trio* trio);
+
 /* ---- joint calling: JointAnnotatorCaller.apply (JointAnnotatorCaller.scala:52-64, 74-281) ------ */
 /* Genotypes of S samples at the same N (squared-off) sites, sample-major: entry [s * n_sites + i].
  * The per-sample columns are the ones avo_call produces (n_alt, n_ref, n_other, gl). */

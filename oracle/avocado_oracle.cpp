@@ -1351,6 +1351,53 @@ static std::pair<int, bool> squareOffSample(const std::string& contig, long star
   return {best, best >= 0};
 }
 
+// ---------------------------------------------------------------------------
+// CORE/genotyping/TrioCaller.scala:86-221 -- per-site trio consistency / phasing.
+// A genotype is its allele list (0 REF, 1 ALT, 2 OTHER_ALT, 3 NO_CALL); absent = has == false.
+// ---------------------------------------------------------------------------
+struct TrioGt { bool has = false; std::vector<int> alleles; };
+struct TrioOut {
+  bool kept = false;                 // survives both filterRef passes (:92-96)
+  int childAction = 0;               // 0 unchanged, 1 phased as is, 2 replaced by NO_CALL x 2 (GQ unset),
+                                     // 3 phased [ALT, REF] (from first parent), 4 phased [REF, ALT]
+  bool filled[3] = {false, false, false};   // sample replaced by a NO_CALL genotype (:209-216)
+  std::vector<int> childAlleles;
+};
+
+static bool trioAnyAlt(const TrioGt& g) { if (!g.has) return false; for (int a : g.alleles) if (a == 1) return true; return false; }
+
+static TrioOut trioProcess(const TrioGt& p1, const TrioGt& p2, const TrioGt& ch) {
+  TrioOut o;
+  if (!(trioAnyAlt(p1) || trioAnyAlt(p2) || trioAnyAlt(ch))) return o;               // filterRef :104-111
+  o.childAlleles = ch.alleles;
+  if (p1.has && p2.has && ch.has) {                                                   // :141-206
+    auto ok = [](const TrioGt& g) {
+      if (g.alleles.size() != 2) return false;
+      for (int a : g.alleles) if (a == 3 || a == 2) return false;
+      return true;
+    };
+    if (ok(p1) && ok(p2) && ok(ch)) {
+      auto st = [](const TrioGt& g) { int n = 0; for (int a : g.alleles) n += a == 1; return n; };
+      const int s1 = st(p1), s2 = st(p2), sc = st(ch);
+      if (sc == 0) o.childAction = (s1 == 2 || s2 == 2) ? 2 : 1;
+      else if (sc == 2) o.childAction = (s1 == 0 || s2 == 0) ? 2 : 1;
+      else if ((s1 == 0 && s2 == 0) || (s1 == 2 && s2 == 2)) o.childAction = 2;
+      else if (s1 == 1 && s2 == 1) o.childAction = 0;
+      else o.childAction = s1 != 0 ? 3 : 4;
+    }
+  } else {
+    o.filled[0] = !p1.has; o.filled[1] = !p2.has; o.filled[2] = !ch.has;
+    if (!ch.has) o.childAlleles = {3, 3};
+  }
+  if (o.childAction == 2) o.childAlleles = {3, 3};
+  else if (o.childAction == 3) o.childAlleles = {1, 0};
+  else if (o.childAction == 4) o.childAlleles = {0, 1};
+  bool anyAlt = trioAnyAlt(p1) || trioAnyAlt(p2);
+  for (int a : o.childAlleles) anyAlt = anyAlt || a == 1;
+  o.kept = anyAlt;                                                                    // second filterRef :95
+  return o;
+}
+
 }  // namespace orc
 
 // ===========================================================================
@@ -1882,5 +1929,15 @@ PYBIND11_MODULE(avocado_oracle, m) {
       g.push_back(x);
     }
     return squareOffSample(std::get<0>(v), std::get<1>(v), std::get<2>(v), std::get<3>(v), std::get<4>(v), g);
+  });
+  // ---- TrioCaller ---------------------------------------------------------------------------------
+  // trio_process(first parent alleles | None, second parent | None, child | None)
+  m.def("trio_process", [](py::object a, py::object b, py::object c) {
+    auto mk = [](py::object o) { TrioGt g; if (!o.is_none()) { g.has = true; g.alleles = o.cast<std::vector<int>>(); } return g; };
+    const TrioOut r = trioProcess(mk(a), mk(b), mk(c));
+    py::dict d;
+    d["kept"] = r.kept; d["childAction"] = r.childAction; d["childAlleles"] = r.childAlleles;
+    d["filled"] = std::vector<bool>{r.filled[0], r.filled[1], r.filled[2]};
+    return d;
   });
 }

@@ -216,7 +216,7 @@ k_as_tiles(DReads R, DSites S, DCnv C, DCallParams P, DResults O, int32_t* __res
   A.sq = sq;
   A.allele_fwd = c_afw; A.other_fwd = c_ofw; A.allele_cov = c_acov; A.other_cov = c_ocov; A.total_cov = c_tot;
   A.first_is_ref = first_is_ref; A.copy_number = first_cn; A.seen = seen;
-  finalize_site(P, O, row, A);
+  finalize_site<true>(P, O, row, A);     // rows are written completely: the output needs no clearing
 }
 
 // ---- host side ------------------------------------------------------------------------------

@@ -557,23 +557,33 @@ int allsites_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const
   if (!ro->start) return fail(ctx, AVO_E_INVALID, "ref_model->start is NULL");
   rows->n_sites = total;
   CKS(check_results(ctx, rows));
+  nl = 0;
+  if (rows->mem == AVO_MEM_DEVICE) {
+    // device output: the kernel writes every column of every row straight into the caller's arrays
+    DResults D;
+    D.ns = P.ns;
+    D.emitted = rows->emitted; D.allele_fwd = rows->allele_fwd; D.other_fwd = rows->other_fwd;
+    D.allele_cov = rows->allele_cov; D.other_cov = rows->other_cov; D.total_cov = rows->total_cov;
+    D.square_mapq = rows->square_mapq; D.ref_ll = rows->ref_ll; D.allele_ll = rows->allele_ll;
+    D.other_ll = rows->other_ll; D.nonref_ll = rows->nonref_ll; D.first_is_ref = rows->first_is_ref;
+    D.copy_number = rows->copy_number; D.n_alt = rows->n_alt; D.n_ref = rows->n_ref; D.n_other = rows->n_other;
+    D.qual = rows->qual; D.gq = rows->gq; D.sb = rows->sb; D.fisher = rows->fisher; D.rms_mapq = rows->rms_mapq;
+    D.gl = rows->gl; D.nonref_gl = rows->nonref_gl;
+    CK(launch_allsites_tiles(R, S, C, P, D, ro->start, X, A, n_joined, hs.max_span, ctx->stream, &nl));
+    ctx->timing.n_launches += nl;
+    return AVO_OK;
+  }
   const ResLayout L = res_layout(total, P.ns);
   void *d_res, *d_start;
   CKS(get_buf(ctx, SL_AS_RES, L.total, &d_res));
   CKS(get_buf(ctx, SL_AS_START, (size_t)total * 4, &d_start));
-  CK(cudaMemsetAsync(d_res, 0, L.total, ctx->stream));
   DResults D;
   res_pointers(d_res, L, P.ns, &D);
-  nl = 0;
   CK(launch_allsites_tiles(R, S, C, P, D, (int32_t*)d_start, X, A, n_joined, hs.max_span, ctx->stream, &nl));
   ctx->timing.n_launches += nl;
   CKS(export_results(ctx, D, total, P.ns, rows));
-  if (rows->mem == AVO_MEM_DEVICE) {
-    CK(cudaMemcpyAsync(ro->start, d_start, (size_t)total * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-  } else {
-    CK(cudaMemcpyAsync(ro->start, d_start, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->timing.d2h_bytes += total * 4;
-  }
+  CK(cudaMemcpyAsync(ro->start, d_start, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->timing.d2h_bytes += total * 4;
   return AVO_OK;
 }
 

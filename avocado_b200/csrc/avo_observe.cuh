@@ -215,9 +215,27 @@ __device__ __forceinline__ int32_t double_to_int(double d) {   // Scala Double.t
 }
 
 // BG:579-616, 677-748 for one reduced site; writes the result row.
+// a row that received no observation: every column zero (the caller's arrays need not be cleared)
+__device__ inline void zero_site(const DResults& O, int32_t site, int ns) {
+  O.emitted[site] = 0;
+  O.allele_fwd[site] = 0; O.other_fwd[site] = 0; O.allele_cov[site] = 0; O.other_cov[site] = 0; O.total_cov[site] = 0;
+  O.square_mapq[site] = 0.0; O.first_is_ref[site] = 0; O.copy_number[site] = 0;
+  O.n_alt[site] = 0; O.n_ref[site] = 0; O.n_other[site] = 0; O.qual[site] = 0.0; O.gq[site] = 0;
+  O.fisher[site] = 0.f; O.rms_mapq[site] = 0.f;
+  for (int k = 0; k < 4; ++k) O.sb[(int64_t)site * 4 + k] = 0;
+  for (int g = 0; g < ns; ++g) {
+    const int64_t i = (int64_t)site * ns + g;
+    O.ref_ll[i] = 0.0; O.allele_ll[i] = 0.0; O.other_ll[i] = 0.0; O.nonref_ll[i] = 0.0; O.gl[i] = 0.0; O.nonref_gl[i] = 0.0;
+  }
+}
+
+template <bool ZERO_UNSEEN = false>
 __device__ inline void finalize_site(const DCallParams& P, const DResults& O, int32_t site, const SiteAcc& A) {
   const int ns = P.ns;
-  if (!A.seen) { O.emitted[site] = 0; return; }
+  if (!A.seen) {
+    if (ZERO_UNSEEN) zero_site(O, site, ns); else O.emitted[site] = 0;
+    return;
+  }
   O.emitted[site] = 1;
   O.allele_fwd[site] = A.allele_fwd; O.other_fwd[site] = A.other_fwd;
   O.allele_cov[site] = A.allele_cov; O.other_cov[site] = A.other_cov; O.total_cov[site] = A.total_cov;

@@ -8,11 +8,14 @@ sites; the CLI default, CLI/BiallelicGenotyper.scala:255-263) over one synthetic
 BASELINE.json configs[1] shape: single-sample 60x chr20 (64 Mb), 150 bp reads = 25.6 M reads.
 
   value     reads/s with the packed batch already resident in HBM (device pointers through the C ABI)
-  e2e       the same call with HOST (pinned) buffers: H2D of the whole batch and D2H of the site
-            table + per-site results are inside the timed region
-  roofline  dominant kernel (k_call_tiles or k_discover_tiles, whichever is longer), algorithmic
-            bytes = bytes of the packed batch (every input byte once) + result rows,
-            divided by that kernel's CUDA-event duration; peak = MEASURED_PEAKS.json hbm_gbs
+  e2e       the same C-ABI call with HOST (pinned) buffers, the batch cut into region bins that a few
+            host threads (one context + stream each) pipeline: H2D of the records / operators /
+            mismatch bytes (compact wire form), in-place payload reads over PCIe, D2H of the site
+            table + all per-site results are inside the timed region; `single_call` = one bin
+  roofline  the longest kernel (k_discover_tiles, or the call stage's kernels together): measured
+            DRAM bytes per launch (ncu, profiles/traffic.json) / its CUDA-event duration, because the
+            kernels are sparse (SURVEY.md 8d anti-inflation rule); `full_scan_step` = every packed
+            input byte once over the whole step; peak = MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the CPU oracle (a C++ restatement of the reference; the Scala/Spark reference
             cannot run here: no JVM) on a bounded sample of the same workload, 1 thread
 

@@ -18,16 +18,19 @@
 
 namespace avo {
 
-constexpr int DISC_THREADS = 256;
+#ifndef AVO_DISC_THREADS
+#define AVO_DISC_THREADS 512
+#endif
+constexpr int DISC_THREADS = AVO_DISC_THREADS;
 #ifndef AVO_DISC_W
-#define AVO_DISC_W 2048
+#define AVO_DISC_W 4096
 #endif
 #ifndef AVO_DISC_MINB
-#define AVO_DISC_MINB 6
+#define AVO_DISC_MINB 3
 #endif
 constexpr int DISC_W = AVO_DISC_W;  // reference positions owned by one tile
 #ifndef AVO_DISC_HB
-#define AVO_DISC_HB 8
+#define AVO_DISC_HB 2
 #endif
 constexpr int DISC_HB = AVO_DISC_HB;        // hot positions histogrammed per pass-2 batch
 constexpr uint32_t NOT_HOT = 0xFFFFFFFFu;
@@ -200,7 +203,8 @@ __global__ void __launch_bounds__(DISC_THREADS, AVO_DISC_MINB)
 k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep count > min_count */,
                  int32_t n_tiles, int32_t max_span, int32_t max_end, int32_t verify, DDiscoverOut out,
                  DIndelList L, int32_t* __restrict__ tile_counter, int32_t* __restrict__ flags) {
-  __shared__ DiscSmem sm;
+  extern __shared__ __align__(16) unsigned char disc_smem_raw[];     // sizeof(DiscSmem), may exceed 48 KB
+  DiscSmem& sm = *reinterpret_cast<DiscSmem*>(disc_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int BPT = DISC_W / IDX_G;
   constexpr int PER_T = DISC_W / DISC_THREADS;
@@ -417,12 +421,14 @@ cudaError_t launch_discover_tiles(const DReads& R, int32_t thr, int32_t min_obs,
   if (R.n == 0) return cudaSuccess;
   const int64_t span = (int64_t)hstats.max_end - (int64_t)hstats.min_start;
   const int32_t n_tiles = (int32_t)max((int64_t)1, (span + DISC_W - 1) / DISC_W);
+  e = cudaFuncSetAttribute(k_discover_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiscSmem));
+  if (e != cudaSuccess) return e;
   int blocks_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_discover_tiles, DISC_THREADS, 0);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_discover_tiles, DISC_THREADS, sizeof(DiscSmem));
   if (e != cudaSuccess) return e;
   const int grid = (int)min((int64_t)n_tiles, (int64_t)num_sms * max(1, blocks_per_sm));
   const int32_t min_count = min_obs < 0 ? 0 : min_obs;  // distinct == count > 0
-  k_discover_tiles<<<grid, DISC_THREADS, 0, s>>>(R, X, thr, min_count, n_tiles, hstats.max_span,
+  k_discover_tiles<<<grid, DISC_THREADS, sizeof(DiscSmem), s>>>(R, X, thr, min_count, n_tiles, hstats.max_span,
                                                  hstats.max_end, verify, out, indels, d_tile_counter,
                                                  d_flags);
   if (n_launches) *n_launches += 1;

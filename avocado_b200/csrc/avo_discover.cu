@@ -239,8 +239,9 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
       const int64_t o = (int64_t)pos - wlo;
       if (o < 0 || o >= DISC_W) return;
       const uint32_t refn = (pair >> 4) & 15u, altn = pair & 15u;
-      if (__popc(refn) != 1 || __popc(altn) != 1) { sm.exotic = 1; return; }
-      const int ai = __ffs(altn) - 1;                                 // A C G T -> 0 1 2 3
+      // A C G T are the nibbles 1 2 4 8 (bits of 0x116); anything else takes the exact path
+      if (!(((0x116u >> refn) & (0x116u >> altn)) & 1u)) { sm.exotic = 1; return; }
+      const int ai = (int)((altn >> 1) - (altn >> 3));                // 1 2 4 8 -> 0 1 2 3
       atomicAdd(&sm.cnt[ai >> 1][o], 1u << ((ai & 1) * 16));
       atomicOr(&sm.refm[o >> 3], refn << ((o & 7) * 4));
     };

@@ -99,6 +99,12 @@ class TextReadsStruct(C.Structure):
                 ("qual", P), ("qual_off", P), ("keep", P)]
 
 
+class TextOutStruct(C.Structure):
+    _fields_ = [("cigar_bytes", C.c_int64), ("md_bytes", C.c_int64), ("seq_bytes", C.c_int64),
+                ("start", P), ("end", P), ("mapq", P), ("rec_flags", P), ("cigar", P), ("cigar_off", P),
+                ("md", P), ("md_off", P), ("seq", P), ("qual", P), ("seq_off", P)]
+
+
 class PackedOutStruct(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("n_blocks", C.c_int64), ("n_ops", C.c_int64),
                 ("n_refb", C.c_int64), ("meta", P), ("payload", P), ("ops", P),
@@ -188,8 +194,8 @@ EXPORTED_SYMBOLS = [
     "avo_ctx_create", "avo_ctx_destroy", "avo_last_error", "avo_version", "avo_ctx_set_stream",
     "avo_get_timing", "avo_discover", "avo_call", "avo_discover_and_call",
     "avo_call_all_sites", "avo_filter_genotypes", "avo_square_off", "avo_trio_call", "avo_joint_counts", "avo_joint",
-    "avo_pack_wire", "avo_pack_bounds", "avo_pack_reads", "avo_synth_default_params", "avo_synth_host",
-    "avo_synth_device",
+    "avo_pack_wire", "avo_pack_bounds", "avo_pack_reads", "avo_pack_reads_mt", "avo_synth_default_params",
+    "avo_synth_host", "avo_synth_device", "avo_synth_text",
 ]
 
 _lib = None
@@ -234,6 +240,8 @@ def load():
     lib.avo_pack_wire.argtypes = [C.POINTER(ReadBatchStruct), P, P]
     lib.avo_pack_bounds.argtypes = [C.POINTER(TextReadsStruct)] + [C.POINTER(C.c_int64)] * 4
     lib.avo_pack_reads.argtypes = [C.POINTER(TextReadsStruct), C.POINTER(PackedOutStruct)]
+    lib.avo_pack_reads_mt.argtypes = [C.POINTER(TextReadsStruct), C.POINTER(PackedOutStruct), C.c_int]
+    lib.avo_synth_text.argtypes = [C.POINTER(ReadBatchStruct), C.c_int64, C.c_int64, C.POINTER(TextOutStruct)]
     lib.avo_synth_default_params.argtypes = [C.POINTER(SynthParamsStruct)]
     lib.avo_synth_host.argtypes = [C.POINTER(SynthParamsStruct), C.c_int64, C.c_int64,
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64),

@@ -330,30 +330,46 @@ def pack_reads(records: Sequence[AlignmentRecord], contig_id=0, keep=None, sort=
         idx.sort(key=lambda i: records[i].start)   # Python's sort is stable
     recs = [records[i] for i in idx]
     cols = text_columns(recs)
+    b = pack_text_columns(cols, contig_id=contig_id)
+    b.source_index = np.array([idx[j] for j in b.source_index], np.int64)
+    return b
+
+
+def pack_text_columns(cols, contig_id=0, threads=1, keep=None) -> ReadBatch:
+    """avo_pack_reads_mt over text columns (the dict ``text_columns`` / ``text_columns_of`` return):
+    PrefilterReads' ``keep`` mask + extractAlignmentOperators + payload packing, on ``threads`` host
+    threads.  The reads must already be those of one contig, sorted by start."""
+    lib = L.load()
     t = L.TextReadsStruct()
-    t.n = len(recs)
+    t.n = len(cols["start"])
     keepalive = []
     for name in ("start", "end", "mapq"):
         setattr(t, name, cols[name].ctypes.data)
     t.rec_flags = cols["flags"].ctypes.data
     for name in ("cigar", "md", "seq", "qual"):
-        buf = C.create_string_buffer(cols[name], len(cols[name]) + 1)
-        keepalive.append(buf)
-        setattr(t, name, C.cast(buf, C.c_void_p).value)
+        blob = cols[name]
+        if isinstance(blob, (bytes, bytearray)):
+            blob = np.frombuffer(bytes(blob) + b"\0", np.uint8)
+        keepalive.append(blob)
+        setattr(t, name, blob.ctypes.data)
         setattr(t, name + "_off", cols[name + "_off"].ctypes.data)
-    t.keep = None
+    if keep is not None:
+        keep = np.ascontiguousarray(keep, np.uint8)
+        t.keep = keep.ctypes.data
+    else:
+        t.keep = None
     nr, nb, no, nf = (C.c_int64() for _ in range(4))
     rc = lib.avo_pack_bounds(C.byref(t), C.byref(nr), C.byref(nb), C.byref(no), C.byref(nf))
     if rc != 0:
         raise L.AvocadoError(rc, "avo_pack_bounds failed")
     out = L.PackedOutStruct()
-    arrs = dict(meta=np.zeros(max(nr.value, 1), META_DTYPE), payload=np.zeros(max(nb.value, 1) * BLOCK_BYTES, np.uint8),
-                ops=np.zeros(max(no.value, 1), np.uint32),
-                refb=np.zeros(max(nf.value, 1), np.uint8), source_index=np.zeros(max(nr.value, 1), np.int64))
+    arrs = dict(meta=np.empty(max(nr.value, 1), META_DTYPE), payload=np.empty(max(nb.value, 1) * BLOCK_BYTES, np.uint8),
+                ops=np.empty(max(no.value, 1), np.uint32),
+                refb=np.empty(max(nf.value, 1), np.uint8), source_index=np.empty(max(nr.value, 1), np.int64))
     out.n_reads, out.n_blocks, out.n_ops, out.n_refb = nr.value, nb.value, no.value, nf.value
     for k, a in arrs.items():
         setattr(out, k, a.ctypes.data)
-    rc = lib.avo_pack_reads(C.byref(t), C.byref(out))
+    rc = lib.avo_pack_reads_mt(C.byref(t), C.byref(out), int(threads))
     if rc != 0:
         raise L.AvocadoError(rc, "avo_pack_reads failed")
     b = ReadBatch(out.n_reads, out.n_blocks, out.n_ops, out.n_refb, contig_id)
@@ -361,8 +377,33 @@ def pack_reads(records: Sequence[AlignmentRecord], contig_id=0, keep=None, sort=
     b.payload = arrs["payload"][:max(out.n_blocks, 1) * BLOCK_BYTES]
     b.ops = arrs["ops"][:max(out.n_ops, 1)]
     b.refb = arrs["refb"][:max(out.n_refb, 1)]
-    b.source_index = np.array([idx[j] for j in arrs["source_index"][:out.n_reads]], np.int64)
+    b.source_index = arrs["source_index"][:out.n_reads]
     return b.with_stats()
+
+
+def text_columns_of(batch: ReadBatch, first=0, n=None):
+    """Text columns (CIGAR with M runs, MD, sequence, phred+33 qualities) of reads [first, first+n)
+    of a packed host batch (avo_synth_text): bench / test infrastructure."""
+    lib = L.load()
+    n = batch.n_reads - first if n is None else n
+    rb = batch.as_struct()
+    out = L.TextOutStruct()
+    rc = lib.avo_synth_text(C.byref(rb), first, n, C.byref(out))
+    if rc != 0:
+        raise L.AvocadoError(rc, "avo_synth_text(count) failed")
+    cols = dict(start=np.empty(n, np.int64), end=np.empty(n, np.int64), mapq=np.empty(n, np.int32),
+                flags=np.empty(n, np.uint8), cigar=np.empty(out.cigar_bytes + 1, np.uint8),
+                cigar_off=np.empty(n + 1, np.int64), md=np.empty(out.md_bytes + 1, np.uint8),
+                md_off=np.empty(n + 1, np.int64), seq=np.empty(out.seq_bytes + 1, np.uint8),
+                qual=np.empty(out.seq_bytes + 1, np.uint8), seq_off=np.empty(n + 1, np.int64))
+    for k in ("start", "end", "mapq", "cigar", "cigar_off", "md", "md_off", "seq", "qual", "seq_off"):
+        setattr(out, k, cols[k].ctypes.data)
+    out.rec_flags = cols["flags"].ctypes.data
+    rc = lib.avo_synth_text(C.byref(rb), first, n, C.byref(out))
+    if rc != 0:
+        raise L.AvocadoError(rc, "avo_synth_text failed")
+    cols["qual_off"] = cols["seq_off"]
+    return cols
 
 
 # ---------------------------------------------------------------------------------------------

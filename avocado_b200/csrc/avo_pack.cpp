@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/avocado_b200.h"
@@ -51,22 +52,42 @@ bool parse_cigar(const char* s, size_t n, std::vector<Elem>& out) {
   return true;
 }
 
-bool is_md_base(char c) { return strchr("ACGTNUKMRSWBVHDX", c) != nullptr; }
+struct MdBase {
+  bool ok[256];
+  MdBase() {
+    memset(ok, 0, sizeof ok);
+    for (const char* c = "ACGTNUKMRSWBVHDX"; *c; ++c) { ok[(unsigned char)*c] = true; ok[(unsigned char)tolower(*c)] = true; }
+  }
+};
+const MdBase MD_BASE;
 
-// MD tag -> per-reference-offset maps (ADAM MdTag semantics: see oracle/avocado_oracle.cpp)
-bool parse_md(const char* s, size_t n, std::vector<char>& mism, std::vector<char>& del) {
-  mism.clear(); del.clear();
+// two sequence characters -> one payload byte (high nibble first)
+struct PairTable {
+  uint8_t t[65536];
+  PairTable() {
+    for (int a = 0; a < 256; ++a)
+      for (int b = 0; b < 256; ++b) t[a | (b << 8)] = (uint8_t)((NIB.t[a] << 4) | NIB.t[b]);
+  }
+};
+const PairTable PAIR;
+
+// One MD event: the reference base recorded for alignment offset `off` (ADAM MdTag semantics: see
+// oracle/avocado_oracle.cpp): a mismatch, or a deleted base.
+struct MdEvent { uint64_t off; char base; bool del; };
+
+// MD tag -> events in offset order.  false: malformed (the reference's MdTag would throw)
+bool parse_md(const char* s, size_t n, std::vector<MdEvent>& ev) {
+  ev.clear();
   if (n == 0) return true;
   size_t off = 0;
-  size_t ref = 0;
-  auto grow = [&](size_t upto) { if (mism.size() < upto) { mism.resize(upto, 0); del.resize(upto, 0); } };
+  uint64_t ref = 0;
   auto read_matches = [&]() -> bool {
     size_t j = off;
     uint64_t v = 0;
-    while (j < n && isdigit((unsigned char)s[j])) { v = v * 10 + (uint64_t)(s[j] - '0'); if (v > 0x7FFFFFFFu) return false; ++j; }
+    while (j < n && (unsigned)(s[j] - '0') <= 9u) { v = v * 10 + (uint64_t)(s[j] - '0'); if (v > 0x7FFFFFFFu) return false; ++j; }
     if (j == off) return false;
     off = j;
-    ref += (size_t)v;
+    ref += v;
     return true;
   };
   if (!read_matches()) return false;
@@ -74,14 +95,9 @@ bool parse_md(const char* s, size_t n, std::vector<char>& mism, std::vector<char
     bool is_del = false;
     if (s[off] == '^') { is_del = true; ++off; }
     size_t j = off;
-    while (j < n && is_md_base((char)toupper((unsigned char)s[j]))) ++j;
+    while (j < n && MD_BASE.ok[(unsigned char)s[j]]) ++j;
     if (j == off) return false;
-    grow(ref + (j - off));
-    for (size_t k = off; k < j; ++k) {
-      const char c = (char)toupper((unsigned char)s[k]);
-      if (is_del) del[ref] = c; else mism[ref] = c;
-      ++ref;
-    }
+    for (size_t k = off; k < j; ++k) ev.push_back({ref++, (char)toupper((unsigned char)s[k]), is_del});
     off = j;
     if (!read_matches()) return false;
   }
@@ -90,46 +106,60 @@ bool parse_md(const char* s, size_t n, std::vector<char>& mism, std::vector<char
 
 struct Scratch {
   std::vector<Elem> cigar;
-  std::vector<char> mism, del;
+  std::vector<MdEvent> md;
   std::vector<uint32_t> ops;
   std::vector<uint8_t> refb;
 };
-
-inline char lookup(const std::vector<char>& m, size_t i) { return i < m.size() ? m[i] : 0; }
 
 // returns false when the reference's extractAlignmentOperators would throw or return empty
 // refb bytes: MISMATCH -> one (reference base << 4) | read base byte per position, DEL -> the deleted
 // reference bases as nibbles, high first, padded to whole bytes.
 // `seq`/`lseq` give the read bases for the pairs (0 = N when the sequence is too short; such reads
 // are dropped by the caller anyway).
+// The CIGAR is walked with a cursor into the MD events: an M element takes the mismatches recorded
+// inside its span (deleted bases recorded there are ignored, as a lookup in MdTag's mismatch map
+// would), X needs a mismatch and D a deleted base at every one of its offsets.
 bool extract_ops(const char* cig, size_t ncig, bool has_cigar, const char* md, size_t nmd, bool has_md,
                  const char* seq, int64_t lseq, Scratch& sc, uint32_t* read_len_needed) {
   sc.ops.clear(); sc.refb.clear();
   *read_len_needed = 0;
   if (!has_cigar || (ncig == 1 && cig[0] == '*') || !has_md) return false;
   if (!parse_cigar(cig, ncig, sc.cigar)) return false;
-  if (!parse_md(md, nmd, sc.mism, sc.del)) return false;
-  size_t idx = 0;
-  uint32_t need = 0;   // read bases consumed so far == index of the next read base
+  if (!parse_md(md, nmd, sc.md)) return false;
+  const MdEvent* ev = sc.md.data();
+  const size_t nev = sc.md.size();
+  size_t cur = 0;       // first event at or after the current alignment offset
+  uint64_t idx = 0;
+  uint32_t need = 0;    // read bases consumed so far == index of the next read base
   auto push = [&](uint32_t len, uint32_t code) { sc.ops.push_back((len << 4) | code); };
-  auto read_nib = [&](uint32_t ri) -> uint8_t {
+  auto read_nib = [&](uint64_t ri) -> uint8_t {
     return (int64_t)ri < lseq ? NIB.t[(unsigned char)seq[ri]] : (uint8_t)15;
+  };
+  // the event recorded for offset `o`, or NULL
+  auto at = [&](uint64_t o) -> const MdEvent* {
+    while (cur < nev && ev[cur].off < o) ++cur;
+    return (cur < nev && ev[cur].off == o) ? &ev[cur] : nullptr;
   };
   for (const Elem& e : sc.cigar) {
     if (e.len == 0 && e.op != 'S' && e.op != 'H') return false;  // 0-length M asserts; 0I divides by zero
     switch (e.op) {
       case 'M': {
-        uint32_t run = 0;
-        bool in_mis = false;
-        for (uint32_t k = 0; k < e.len; ++k) {
-          const char b = lookup(sc.mism, idx + k);
-          const bool mis = b != 0;
-          if (k > 0 && mis != in_mis) { push(run, in_mis ? AVO_OP_MISMATCH : AVO_OP_MATCH); run = 0; }
-          in_mis = mis;
-          ++run;
-          if (mis) sc.refb.push_back((uint8_t)((NIB.t[(unsigned char)b] << 4) | read_nib(need + k)));
+        const uint64_t hi = idx + e.len;
+        uint64_t pos = idx;                                  // next offset not yet covered by an operator
+        while (cur < nev && ev[cur].off < idx) ++cur;
+        while (cur < nev && ev[cur].off < hi) {
+          if (ev[cur].del) { ++cur; continue; }
+          const uint64_t k = ev[cur].off;
+          if (k > pos) push((uint32_t)(k - pos), AVO_OP_MATCH);
+          uint32_t run = 0;
+          while (cur < nev && !ev[cur].del && ev[cur].off == k + run && k + run < hi) {
+            sc.refb.push_back((uint8_t)((NIB.t[(unsigned char)ev[cur].base] << 4) | read_nib(need + (k - idx) + run)));
+            ++run; ++cur;
+          }
+          push(run, AVO_OP_MISMATCH);
+          pos = k + run;
         }
-        push(run, in_mis ? AVO_OP_MISMATCH : AVO_OP_MATCH);
+        if (pos < hi) push((uint32_t)(hi - pos), AVO_OP_MATCH);
         idx += e.len; need += e.len;
         break;
       }
@@ -139,9 +169,9 @@ bool extract_ops(const char* cig, size_t ncig, bool has_cigar, const char* md, s
         break;
       case 'X':
         for (uint32_t k = 0; k < e.len; ++k) {
-          const char b = lookup(sc.mism, idx + k);
-          if (!b) return false;
-          sc.refb.push_back((uint8_t)((NIB.t[(unsigned char)b] << 4) | read_nib(need + k)));
+          const MdEvent* m = at(idx + k);
+          if (!m || m->del) return false;
+          sc.refb.push_back((uint8_t)((NIB.t[(unsigned char)m->base] << 4) | read_nib((uint64_t)need + k)));
         }
         push(e.len, AVO_OP_MISMATCH);
         idx += e.len; need += e.len;
@@ -152,9 +182,9 @@ bool extract_ops(const char* cig, size_t ncig, bool has_cigar, const char* md, s
         break;
       case 'D':
         for (uint32_t k = 0; k < e.len; ++k) {
-          const char b = lookup(sc.del, idx + k);
-          if (!b) return false;
-          const uint8_t nb = NIB.t[(unsigned char)b];
+          const MdEvent* m = at(idx + k);
+          if (!m || !m->del) return false;
+          const uint8_t nb = NIB.t[(unsigned char)m->base];
           if (k & 1) sc.refb.back() |= nb; else sc.refb.push_back((uint8_t)(nb << 4));
         }
         push(e.len, AVO_OP_DEL);
@@ -179,6 +209,101 @@ bool kept(const avo_text_reads* in, int64_t i) {
   if (!(in->rec_flags[i] & 1)) return false;             // unmapped reads never reach the path
   if (in->start[i] < 0) return false;
   return in->keep ? in->keep[i] != 0 : true;
+}
+
+// Packing is split over contiguous chunks of the input, one per thread: payload blocks and records
+// go straight to their final place (their offsets only need the sequence lengths), operators and
+// mismatch bytes are collected per chunk and copied once the chunk totals are known.
+struct Chunk {
+  int64_t i0 = 0, i1 = 0;        // input reads
+  int64_t r0 = 0, n_kept = 0;    // packed reads
+  uint64_t blk0 = 0, n_blk = 0;  // payload blocks
+  uint64_t op0 = 0, fb0 = 0;     // final offsets of the chunk's operators / mismatch bytes
+  std::vector<uint32_t> ops;
+  std::vector<uint8_t> refb;
+  int rc = AVO_OK;
+};
+
+void pack_chunk(const avo_text_reads* in, avo_packed_out* out, Chunk& ch) {
+  Scratch sc;
+  int64_t r = ch.r0;
+  uint64_t nb = ch.blk0;
+  ch.ops.reserve((size_t)ch.n_kept * 4);
+  ch.refb.reserve((size_t)ch.n_kept * 2);
+  for (int64_t i = ch.i0; i < ch.i1; ++i) {
+    if (!kept(in, i)) continue;
+    const uint8_t rf = in->rec_flags[i];
+    const char* seq = in->seq + in->seq_off[i];
+    const int64_t lseq = in->seq_off[i + 1] - in->seq_off[i];
+    const char* qual = in->qual + in->qual_off[i];
+    const int64_t lqual = in->qual_off[i + 1] - in->qual_off[i];
+    uint32_t need = 0;
+    bool ok = extract_ops(in->cigar + in->cigar_off[i], (size_t)(in->cigar_off[i + 1] - in->cigar_off[i]),
+                          rf & 4, in->md + in->md_off[i], (size_t)(in->md_off[i + 1] - in->md_off[i]),
+                          rf & 8, seq, lseq, sc, &need);
+    uint8_t flags = (rf & 2) ? AVO_READ_NEGATIVE_STRAND : 0;
+    const bool has_mapq = (rf & 16) && in->mapq[i] >= 0;
+    // observeRead indexes sequence and qualities up to the CIGAR's read length
+    if (!has_mapq || (int64_t)need > lseq || (int64_t)need > lqual) flags |= AVO_READ_SKIP_CALL;
+    // discovery additionally indexes qual(i) from 0 and sequence up to the same length: a read
+    // whose strings are too short would crash the reference job; it is dropped here instead
+    if (ok && ((int64_t)need > lseq || (int64_t)need > lqual)) ok = false;
+    if (!ok || sc.ops.size() > 0xFFFFu) { sc.ops.clear(); sc.refb.clear(); }
+    const uint64_t lpad = ((uint64_t)lseq + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES;   // payload blocks of the read
+    if (ch.ops.size() + sc.ops.size() > 0xFFFFFFFFull || ch.refb.size() + sc.refb.size() > 0xFFFFFFFFull) {
+      ch.rc = AVO_E_INVALID;   // split the batch
+      return;
+    }
+    avo_read_meta& m = out->meta[r];
+    m.start = (int32_t)in->start[i];
+    m.end = (int32_t)in->end[i];
+    const int mq = has_mapq ? in->mapq[i] : 0;
+    m.mapq = (uint8_t)(mq > 255 ? 255 : mq);
+    m.flags = flags;
+    m.seq_off = (uint32_t)nb;
+    m.op_off = (uint32_t)ch.ops.size();        // chunk-relative until the totals are known
+    m.refb_off = (uint32_t)ch.refb.size();
+    m.n_ops = (uint16_t)sc.ops.size();
+    m.l_seq = (uint32_t)lseq;
+    if (out->source_index) out->source_index[r] = i;
+    // payload: 10 bases in bytes 0..4 (high nibble first), their qualities in bytes 5..14, byte 15 = 0
+    uint8_t* blk = out->payload + (nb << 4);
+    const int64_t full = (lseq < lqual ? lseq : lqual) / AVO_BLOCK_BASES;   // blocks with 10 bases and 10 qualities
+    for (int64_t c = 0; c < full; ++c, blk += AVO_BLOCK_BYTES) {
+      const unsigned char* sp = (const unsigned char*)seq + c * AVO_BLOCK_BASES;
+      const unsigned char* qp = (const unsigned char*)qual + c * AVO_BLOCK_BASES;
+      for (int j = 0; j < 5; ++j) blk[j] = PAIR.t[sp[2 * j] | (sp[2 * j + 1] << 8)];
+      for (int w = 0; w < AVO_BLOCK_BASES; ++w) blk[5 + w] = (uint8_t)(qp[w] < 33 ? 0 : qp[w] - 33);
+      blk[15] = 0;
+    }
+    if ((uint64_t)full < lpad) {
+      memset(blk, 0, (size_t)(lpad - (uint64_t)full) << 4);
+      for (int64_t k = full * AVO_BLOCK_BASES; k < lseq; ++k) {
+        const uint64_t c = (uint64_t)k / AVO_BLOCK_BASES, w = (uint64_t)k - c * AVO_BLOCK_BASES;
+        uint8_t* b = out->payload + ((nb + c) << 4);
+        const uint8_t nibv = NIB.t[(unsigned char)seq[k]];
+        b[w >> 1] |= (w & 1) ? nibv : (uint8_t)(nibv << 4);
+        int q = (k < lqual) ? (int)(unsigned char)qual[k] - 33 : 0;
+        b[5 + w] = (uint8_t)(q < 0 ? 0 : q);
+      }
+    }
+    m.qhead = 0;
+    for (int64_t k = 0; k < 4 && k < lseq; ++k)
+      m.qhead |= (uint32_t)out->payload[(nb << 4) + 5 + (uint64_t)k] << (8 * k);
+    ch.ops.insert(ch.ops.end(), sc.ops.begin(), sc.ops.end());
+    ch.refb.insert(ch.refb.end(), sc.refb.begin(), sc.refb.end());
+    nb += lpad;
+    ++r;
+  }
+}
+
+template <typename F>
+void run_chunks(std::vector<Chunk>& chunks, F&& f) {
+  if (chunks.size() == 1) { f(chunks[0]); return; }
+  std::vector<std::thread> pool;
+  pool.reserve(chunks.size());
+  for (Chunk& ch : chunks) pool.emplace_back([&f, &ch]() { f(ch); });
+  for (std::thread& t : pool) t.join();
 }
 
 }  // namespace
@@ -229,67 +354,47 @@ int avo_pack_bounds(const avo_text_reads* in, int64_t* n_reads, int64_t* n_block
   return AVO_OK;
 }
 
-int avo_pack_reads(const avo_text_reads* in, avo_packed_out* out) {
-  if (!in || !out) return AVO_E_INVALID;
-  Scratch sc;
-  int64_t r = 0;
-  uint64_t nb = 0, no = 0, nf = 0;
-  for (int64_t i = 0; i < in->n; ++i) {
-    if (!kept(in, i)) continue;
-    if (r >= out->n_reads) return AVO_E_CAPACITY;
-    const uint8_t rf = in->rec_flags[i];
-    const char* seq = in->seq + in->seq_off[i];
-    const int64_t lseq = in->seq_off[i + 1] - in->seq_off[i];
-    const char* qual = in->qual + in->qual_off[i];
-    const int64_t lqual = in->qual_off[i + 1] - in->qual_off[i];
-    uint32_t need = 0;
-    bool ok = extract_ops(in->cigar + in->cigar_off[i], (size_t)(in->cigar_off[i + 1] - in->cigar_off[i]),
-                          rf & 4, in->md + in->md_off[i], (size_t)(in->md_off[i + 1] - in->md_off[i]),
-                          rf & 8, seq, lseq, sc, &need);
-    uint8_t flags = (rf & 2) ? AVO_READ_NEGATIVE_STRAND : 0;
-    const bool has_mapq = (rf & 16) && in->mapq[i] >= 0;
-    // observeRead indexes sequence and qualities up to the CIGAR's read length
-    if (!has_mapq || (int64_t)need > lseq || (int64_t)need > lqual) flags |= AVO_READ_SKIP_CALL;
-    // discovery additionally indexes qual(i) from 0 and sequence up to the same length: a read
-    // whose strings are too short would crash the reference job; it is dropped here instead
-    if (ok && ((int64_t)need > lseq || (int64_t)need > lqual)) ok = false;
-    if (!ok || sc.ops.size() > 0xFFFFu) { sc.ops.clear(); sc.refb.clear(); }
-    const uint64_t lpad = ((uint64_t)lseq + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES;   // payload blocks of the read
-    if ((int64_t)(nb + lpad) > out->n_blocks || (int64_t)(no + sc.ops.size()) > out->n_ops ||
-        (int64_t)(nf + sc.refb.size()) > out->n_refb)
-      return AVO_E_CAPACITY;
-    if (nb + lpad > 0xFFFFFFFFull) return AVO_E_INVALID;   // split the batch
-    avo_read_meta& m = out->meta[r];
-    m.start = (int32_t)in->start[i];
-    m.end = (int32_t)in->end[i];
-    const int mq = has_mapq ? in->mapq[i] : 0;
-    m.mapq = (uint8_t)(mq > 255 ? 255 : mq);
-    m.flags = flags;
-    m.seq_off = (uint32_t)nb;
-    m.op_off = (uint32_t)no;
-    m.refb_off = (uint32_t)nf;
-    m.n_ops = (uint16_t)sc.ops.size();
-    m.l_seq = (uint32_t)lseq;
-    m.qhead = 0;
-    if (out->source_index) out->source_index[r] = i;
-    memset(out->payload + (nb << 4), 0, (size_t)lpad << 4);
-    for (int64_t k = 0; k < lseq; ++k) {
-      const uint64_t c = (uint64_t)k / AVO_BLOCK_BASES, w = (uint64_t)k - c * AVO_BLOCK_BASES;
-      uint8_t* blk = out->payload + ((nb + c) << 4);
-      const uint8_t nibv = NIB.t[(unsigned char)seq[k]];
-      blk[w >> 1] |= (w & 1) ? nibv : (uint8_t)(nibv << 4);
-      int q = (k < lqual) ? (int)(unsigned char)qual[k] - 33 : 0;
-      q = q < 0 ? 0 : (q > 255 ? 255 : q);
-      blk[5 + w] = (uint8_t)q;
-      if (k < 4) m.qhead |= (uint32_t)q << (8 * k);
+int avo_pack_reads_mt(const avo_text_reads* in, avo_packed_out* out, int n_threads) {
+  if (!in || !out || in->n < 0) return AVO_E_INVALID;
+  int64_t T = n_threads < 1 ? 1 : (n_threads > 256 ? 256 : n_threads);
+  if (T > (in->n + 4095) / 4096) T = (in->n + 4095) / 4096;     // not worth a thread below 4096 reads
+  if (T < 1) T = 1;
+  std::vector<Chunk> chunks((size_t)T);
+  for (int64_t t = 0; t < T; ++t) { chunks[t].i0 = in->n * t / T; chunks[t].i1 = in->n * (t + 1) / T; }
+  // records and payload blocks per chunk: sequence lengths only
+  run_chunks(chunks, [in](Chunk& ch) {
+    for (int64_t i = ch.i0; i < ch.i1; ++i) {
+      if (!kept(in, i)) continue;
+      ++ch.n_kept;
+      ch.n_blk += (uint64_t)((in->seq_off[i + 1] - in->seq_off[i]) + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES;
     }
-    for (size_t k = 0; k < sc.ops.size(); ++k) out->ops[no + k] = sc.ops[k];
-    for (size_t k = 0; k < sc.refb.size(); ++k) out->refb[nf + k] = sc.refb[k];
-    nb += lpad; no += sc.ops.size(); nf += sc.refb.size();
-    ++r;
+  });
+  int64_t r = 0;
+  uint64_t nb = 0;
+  for (Chunk& ch : chunks) { ch.r0 = r; ch.blk0 = nb; r += ch.n_kept; nb += ch.n_blk; }
+  if (r > out->n_reads || (int64_t)nb > out->n_blocks) return AVO_E_CAPACITY;
+  if (nb > 0xFFFFFFFFull) return AVO_E_INVALID;   // split the batch
+  run_chunks(chunks, [in, out](Chunk& ch) { pack_chunk(in, out, ch); });
+  uint64_t no = 0, nf = 0;
+  for (Chunk& ch : chunks) {
+    if (ch.rc != AVO_OK) return ch.rc;
+    ch.op0 = no; ch.fb0 = nf; no += ch.ops.size(); nf += ch.refb.size();
   }
+  if ((int64_t)no > out->n_ops || (int64_t)nf > out->n_refb) return AVO_E_CAPACITY;
+  if (no > 0xFFFFFFFFull || nf > 0xFFFFFFFFull) return AVO_E_INVALID;
+  run_chunks(chunks, [out](Chunk& ch) {
+    if (!ch.ops.empty()) memcpy(out->ops + ch.op0, ch.ops.data(), ch.ops.size() * sizeof(uint32_t));
+    if (!ch.refb.empty()) memcpy(out->refb + ch.fb0, ch.refb.data(), ch.refb.size());
+    if (ch.op0 || ch.fb0)
+      for (int64_t k = ch.r0; k < ch.r0 + ch.n_kept; ++k) {
+        out->meta[k].op_off += (uint32_t)ch.op0;
+        out->meta[k].refb_off += (uint32_t)ch.fb0;
+      }
+  });
   out->n_reads = r; out->n_blocks = (int64_t)nb; out->n_ops = (int64_t)no; out->n_refb = (int64_t)nf;
   return AVO_OK;
 }
+
+int avo_pack_reads(const avo_text_reads* in, avo_packed_out* out) { return avo_pack_reads_mt(in, out, 1); }
 
 }  // extern "C"

@@ -473,6 +473,8 @@ int avo_pack_wire(const avo_read_batch* full, avo_read_wire* wire_meta, uint16_t
 int avo_pack_bounds(const avo_text_reads* in, int64_t* n_reads, int64_t* n_blocks, int64_t* n_ops,
                     int64_t* n_refb);
 int avo_pack_reads(const avo_text_reads* in, avo_packed_out* out);
+/* The same over n_threads host threads (contiguous chunks of the input; identical output). */
+int avo_pack_reads_mt(const avo_text_reads* in, avo_packed_out* out, int n_threads);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,20 @@ int avo_synth_device(const avo_synth_params* p, int64_t first, int64_t n, uint32
                      uint32_t* refb_off_dev, int64_t* n_ops, int64_t* n_refb, avo_packed_out* out,
                      void* cuda_stream);
 
+/* Text form (CIGAR with M runs, MD tag, sequence, phred+33 qualities) of reads [first, first+n) of a
+ * packed HOST batch: the input avo_pack_reads takes.  Call once with cigar == NULL to get the blob
+ * sizes (cigar_bytes / md_bytes / seq_bytes are then outputs), then with buffers; the offset arrays
+ * hold n + 1 entries and qual shares seq's offsets. */
+typedef struct {
+  int64_t cigar_bytes, md_bytes, seq_bytes; /* in: capacities; out: used */
+  int64_t* start; int64_t* end; int32_t* mapq; uint8_t* rec_flags;
+  char* cigar; int64_t* cigar_off;
+  char* md;    int64_t* md_off;
+  char* seq;   char* qual; int64_t* seq_off;
+} avo_text_out;
+
+int avo_synth_text(const avo_read_batch* batch, int64_t first, int64_t n, avo_text_out* out);
+
 #ifdef __cplusplus
 }
 #endif

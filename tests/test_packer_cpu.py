@@ -104,3 +104,36 @@ def test_wire_columns_hold_the_same_information():
     gap = B.synth_host(p)
     gap.meta["op_off"][5] += 1
     assert not gap.with_wire()
+
+
+def _same_batch(a, b):
+    assert (a.n_reads, a.n_blocks, a.n_ops, a.n_refb) == (b.n_reads, b.n_blocks, b.n_ops, b.n_refb)
+    for f in a.meta.dtype.names:
+        assert np.array_equal(a.meta[f], b.meta[f]), f
+    assert np.array_equal(a.payload[:a.n_blocks * 16], b.payload[:a.n_blocks * 16])
+    assert np.array_equal(a.ops[:a.n_ops], b.ops[:a.n_ops])
+    assert np.array_equal(a.refb[:a.n_refb], b.refb[:a.n_refb])
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_text_round_trip_reproduces_the_packed_batch(threads):
+    """pack(text(batch)) == batch, byte for byte: CIGAR M runs + MD carry everything the operators do
+    (ObservationOperator.scala:42-171), and the threaded packer writes what the serial one does."""
+    from avocado_b200 import batch as B
+    n = 60000
+    p = B.synth_params(contig_len=n * 150 // 40, n_reads_total=n, softclip_frac=0.1, indel_rate=5e-4)
+    b = B.synth_host(p)
+    cols = B.text_columns_of(b)
+    assert cols["cigar_off"][-1] > 4 * n and cols["md_off"][-1] > 3 * n
+    _same_batch(b, B.pack_text_columns(cols, threads=threads))
+
+
+def test_threaded_packer_matches_serial_on_the_reference_fixtures():
+    from avocado_b200 import batch as B
+    recs = [r for name in FIXTURES[:4] for r in load_fixture(name)[0] if r.readMapped]
+    recs = recs * 12                       # enough reads for several chunks
+    recs.sort(key=lambda r: r.start)
+    cols = B.text_columns(recs)
+    keep = np.array([(i % 7) != 3 for i in range(len(recs))], np.uint8)
+    for k in (None, keep):
+        _same_batch(B.pack_text_columns(cols, threads=1, keep=k), B.pack_text_columns(cols, threads=4, keep=k))

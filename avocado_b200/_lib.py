@@ -194,7 +194,7 @@ EXPORTED_SYMBOLS = [
     "avo_ctx_create", "avo_ctx_destroy", "avo_last_error", "avo_version", "avo_ctx_set_stream",
     "avo_get_timing", "avo_discover", "avo_call", "avo_discover_and_call",
     "avo_call_all_sites", "avo_filter_genotypes", "avo_square_off", "avo_trio_call", "avo_joint_counts", "avo_joint",
-    "avo_pack_wire", "avo_pack_bounds", "avo_pack_reads", "avo_pack_reads_mt", "avo_synth_default_params",
+    "avo_pack_wire", "avo_pack_bounds", "avo_pack_reads", "avo_pack_reads_mt", "avo_pack_reads_device", "avo_synth_default_params",
     "avo_synth_host", "avo_synth_device", "avo_synth_text",
 ]
 
@@ -241,6 +241,7 @@ def load():
     lib.avo_pack_bounds.argtypes = [C.POINTER(TextReadsStruct)] + [C.POINTER(C.c_int64)] * 4
     lib.avo_pack_reads.argtypes = [C.POINTER(TextReadsStruct), C.POINTER(PackedOutStruct)]
     lib.avo_pack_reads_mt.argtypes = [C.POINTER(TextReadsStruct), C.POINTER(PackedOutStruct), C.c_int]
+    lib.avo_pack_reads_device.argtypes = [P, C.POINTER(TextReadsStruct), C.c_int32, C.POINTER(PackedOutStruct)]
     lib.avo_synth_text.argtypes = [C.POINTER(ReadBatchStruct), C.c_int64, C.c_int64, C.POINTER(TextOutStruct)]
     lib.avo_synth_default_params.argtypes = [C.POINTER(SynthParamsStruct)]
     lib.avo_synth_host.argtypes = [C.POINTER(SynthParamsStruct), C.c_int64, C.c_int64,

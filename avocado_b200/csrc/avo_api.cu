@@ -30,6 +30,8 @@ enum Slot {
   SL_AS_FLAG, SL_AS_JPOS, SL_AS_JR, SL_AS_JIDX, SL_AS_COVER, SL_AS_SCOVER, SL_AS_WCOUNT, SL_AS_WBASE,
   SL_AS_RES, SL_AS_START,
   SL_F_IN, SL_F_OUT,
+  SL_T_START, SL_T_END, SL_T_MAPQ, SL_T_FLAGS, SL_T_CIGAR, SL_T_CIGAR_OFF, SL_T_MD, SL_T_MD_OFF, SL_T_SEQ,
+  SL_T_SEQ_OFF, SL_T_QUAL, SL_T_QUAL_OFF, SL_T_KEEP, SL_T_COUNTS, SL_T_OFFSETS,
   SL_J_PRESENT, SL_J_NALT, SL_J_NREF, SL_J_NOTHER, SL_J_NOCALL, SL_J_GL, SL_J_ALT, SL_J_CALLED, SL_J_OUT,
   SL_TABLE, SL_TCOUNT, SL_KEYS_A, SL_KEYS_B, SL_VALS_A, SL_VALS_B, SL_FOOT, SL_AOFF,
   SL_COUNT_
@@ -926,6 +928,79 @@ int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_c
   }
   CKS(call_internal(ctx, R, hs, T, cnv, params, true, results));
   CKS(finish_call(ctx, true, true));
+  return AVO_OK;
+}
+
+// ---- PrefilterReads' mask + extractAlignmentOperators + payload packing, on the device -----------------
+int avo_pack_reads_device(avo_ctx* ctx, const avo_text_reads* in, int32_t in_mem, avo_packed_out* out) {
+  CKS(begin_call(ctx));
+  if (!in || !out || in->n < 0 || in->n >= (int64_t)INT32_MAX) return fail(ctx, AVO_E_INVALID, "bad text batch");
+  if (in_mem != AVO_MEM_HOST && in_mem != AVO_MEM_DEVICE) return fail(ctx, AVO_E_INVALID, "bad in_mem");
+  const size_t n = (size_t)in->n;
+  if (n && (!in->start || !in->end || !in->mapq || !in->rec_flags || !in->cigar_off || !in->md_off ||
+            !in->seq_off || !in->qual_off))
+    return fail(ctx, AVO_E_INVALID, "text batch has NULL columns");
+  if (!out->meta || !out->payload || !out->ops || !out->refb)
+    return fail(ctx, AVO_E_INVALID, "output columns must be device buffers sized from avo_pack_bounds");
+  if ((uintptr_t)out->meta & 15u || (uintptr_t)out->payload & 15u)
+    return fail(ctx, AVO_E_INVALID, "out->meta and out->payload must be 16-byte aligned");
+  if (n == 0) { out->n_reads = out->n_blocks = out->n_ops = out->n_refb = 0; return AVO_OK; }
+  // blob sizes = the last offsets
+  int64_t tot[4];
+  const int64_t* offs[4] = {in->cigar_off, in->md_off, in->seq_off, in->qual_off};
+  for (int k = 0; k < 4; ++k) {
+    if (in_mem == AVO_MEM_HOST) tot[k] = offs[k][n];
+    else CK(cudaMemcpyAsync(&tot[k], offs[k] + n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (in_mem == AVO_MEM_DEVICE) CK(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 4; ++k)
+    if (tot[k] < 0) return fail(ctx, AVO_E_INVALID, "negative blob size");
+  if ((tot[0] && !in->cigar) || (tot[1] && !in->md) || (tot[2] && !in->seq) || (tot[3] && !in->qual))
+    return fail(ctx, AVO_E_INVALID, "text batch has NULL blobs");
+  DText T;
+  T.n = in->n;
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CKS(stage_in(ctx, SL_T_START, in->start, n, in_mem, &T.start));
+  CKS(stage_in(ctx, SL_T_END, in->end, n, in_mem, &T.end));
+  CKS(stage_in(ctx, SL_T_MAPQ, in->mapq, n, in_mem, &T.mapq));
+  CKS(stage_in(ctx, SL_T_FLAGS, in->rec_flags, n, in_mem, &T.rec_flags));
+  CKS(stage_in(ctx, SL_T_CIGAR, in->cigar, (size_t)tot[0], in_mem, &T.cigar));
+  CKS(stage_in(ctx, SL_T_CIGAR_OFF, in->cigar_off, n + 1, in_mem, &T.cigar_off));
+  CKS(stage_in(ctx, SL_T_MD, in->md, (size_t)tot[1], in_mem, &T.md));
+  CKS(stage_in(ctx, SL_T_MD_OFF, in->md_off, n + 1, in_mem, &T.md_off));
+  CKS(stage_in(ctx, SL_T_SEQ, in->seq, (size_t)tot[2], in_mem, &T.seq));
+  CKS(stage_in(ctx, SL_T_SEQ_OFF, in->seq_off, n + 1, in_mem, &T.seq_off));
+  if (in->qual == in->seq) T.qual = T.seq; else CKS(stage_in(ctx, SL_T_QUAL, in->qual, (size_t)tot[3], in_mem, &T.qual));
+  if (in->qual_off == in->seq_off) T.qual_off = T.seq_off;
+  else CKS(stage_in(ctx, SL_T_QUAL_OFF, in->qual_off, n + 1, in_mem, &T.qual_off));
+  T.keep = nullptr;
+  if (in->keep) CKS(stage_in(ctx, SL_T_KEEP, in->keep, n, in_mem, &T.keep));
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  void *d_counts, *d_offsets, *d_temp;
+  const size_t tb = pack_scan_temp_bytes(in->n);
+  CKS(get_buf(ctx, SL_T_COUNTS, (n + 1) * sizeof(uint4), &d_counts));
+  CKS(get_buf(ctx, SL_T_OFFSETS, (n + 1) * sizeof(PackOffsets), &d_offsets));
+  CKS(get_buf(ctx, SL_TEMP, tb, &d_temp));
+  CK(launch_pack_count(T, (uint4*)d_counts, (PackOffsets*)d_offsets, d_temp, tb, ctx->stream, &ctx->timing.n_launches));
+  PackOffsets total;
+  CK(cudaMemcpyAsync(&total, (PackOffsets*)d_offsets + n, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (total.b > 0xFFFFFFFFull || total.o > 0xFFFFFFFFull || total.f > 0x7FFFFFFFull)
+    return fail(ctx, AVO_E_INVALID, "batch totals must fit 32-bit offsets; split the batch");
+  if ((int64_t)total.k > out->n_reads || (int64_t)total.b > out->n_blocks || (int64_t)total.o > out->n_ops ||
+      (int64_t)total.f > out->n_refb)
+    return fail(ctx, AVO_E_CAPACITY, "packed output too small: need %llu reads, %llu blocks, %llu operators, %llu bytes",
+                (unsigned long long)total.k, (unsigned long long)total.b, (unsigned long long)total.o,
+                (unsigned long long)total.f);
+  DPacked P;
+  P.meta = out->meta; P.payload = out->payload; P.ops = out->ops; P.refb = out->refb; P.source_index = out->source_index;
+  CK(launch_pack_write(T, (const PackOffsets*)d_offsets, P, ctx->stream, &ctx->timing.n_launches));
+  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  out->n_reads = (int64_t)total.k; out->n_blocks = (int64_t)total.b; out->n_ops = (int64_t)total.o;
+  out->n_refb = (int64_t)total.f;
+  ctx->timing.ms_total = ev_ms(ctx, 0, 7);
+  ctx->timing.ms_h2d = ev_ms(ctx, 0, 1);
   return AVO_OK;
 }
 

@@ -156,6 +156,33 @@ cudaError_t launch_wire_expand(const avo_read_wire* wire, const uint16_t* wire_o
                                uint32_t* ops, void* d_temp, size_t temp_bytes, cudaStream_t s);
 
 // device -> device column copies done by one launch
+// ---- the packer on the device (avo_packdev.cu) ------------------------------------------------------
+struct DText {                   // avo_text_reads with device pointers
+  int64_t n;
+  const int64_t *start, *end;
+  const int32_t* mapq;
+  const uint8_t* rec_flags;
+  const char* cigar; const int64_t* cigar_off;
+  const char* md;    const int64_t* md_off;
+  const char* seq;   const int64_t* seq_off;
+  const char* qual;  const int64_t* qual_off;
+  const uint8_t* keep;           // may be NULL
+};
+struct PackOffsets { uint64_t k, b, o, f; };   // packed record, payload block, operator, mismatch byte
+struct DPacked {
+  avo_read_meta* meta;
+  uint8_t* payload;
+  uint32_t* ops;
+  uint8_t* refb;
+  int64_t* source_index;         // may be NULL
+};
+size_t pack_scan_temp_bytes(int64_t n);
+// counts[n + 1] and offsets[n + 1]: offsets[n] holds the totals
+cudaError_t launch_pack_count(const DText& T, uint4* counts, PackOffsets* offsets, void* temp, size_t temp_bytes,
+                              cudaStream_t s, int* n_launches);
+cudaError_t launch_pack_write(const DText& T, const PackOffsets* offsets, const DPacked& out, cudaStream_t s,
+                              int* n_launches);
+
 struct ColumnCopies {
   int n;
   void* dst[32];

@@ -90,6 +90,68 @@ class Context:
         self.lib.avo_get_timing(self.h, C.byref(t))
         return {k: getattr(t, k) for k, _ in L.TimingStruct._fields_}
 
+    # ---- the packer on the device ---------------------------------------------------------------
+    def pack_text_device(self, cols, contig_id=0, keep=None, out=None, source_index=False) -> ReadBatch:
+        """avo_pack_reads_device: text columns (``batch.text_columns`` layout; numpy arrays, ideally
+        page-locked, or torch device tensors) -> a packed ReadBatch in device memory.  ``out``
+        optionally supplies reusable device buffers {meta, payload, ops, refb} of sufficient size."""
+        import torch
+        on_dev = not isinstance(cols["start"], np.ndarray)
+        n = int(cols["start"].shape[0])
+        t = L.TextReadsStruct()
+        t.n = n
+        hold = []
+
+        def col(name, dtype):
+            a = cols[name]
+            if isinstance(a, (bytes, bytearray)):
+                a = np.frombuffer(bytes(a) + b"\0", np.uint8)
+            hold.append(a)
+            return _ptr(a)
+
+        def last(name):
+            a = cols[name]
+            return int(a[n]) if n or len(a) else 0
+
+        t.start, t.end, t.mapq = col("start", np.int64), col("end", np.int64), col("mapq", np.int32)
+        t.rec_flags = col("flags", np.uint8)
+        for name in ("cigar", "md", "seq", "qual"):
+            setattr(t, name, col(name, np.uint8))
+            setattr(t, name + "_off", col(name + "_off", np.int64))
+        if keep is not None:
+            keep = keep if not isinstance(keep, np.ndarray) else np.ascontiguousarray(keep, np.uint8)
+            hold.append(keep)
+            t.keep = _ptr(keep)
+        else:
+            t.keep = None
+        # upper bounds from the blob sizes (what avo_pack_bounds sums read by read)
+        cb, mb, sb = last("cigar_off"), last("md_off"), last("seq_off")
+        cap = dict(meta=n, payload=sb // 10 + n, ops=cb // 2 + n + 2 * mb, refb=mb + n)
+        dev = "cuda:%d" % self.device
+        if out is None:
+            out = {}
+        with torch.cuda.device(dev):
+            for k, unit, dt in (("meta", 32, np.uint8), ("payload", 16, np.uint8), ("ops", 1, np.uint32), ("refb", 1, np.uint8)):
+                if k not in out or out[k].numel() < max(cap[k] * unit, 1):
+                    out[k] = _device_empty(cap[k] * unit, dt, dev)
+            if source_index and ("source_index" not in out or out["source_index"].numel() < max(n, 1)):
+                out["source_index"] = _device_empty(n, np.int64, dev)
+        po = L.PackedOutStruct()
+        po.n_reads, po.n_blocks, po.n_ops, po.n_refb = (out["meta"].numel() // 32, out["payload"].numel() // 16,
+                                                        out["ops"].numel(), out["refb"].numel())
+        po.meta, po.payload, po.ops, po.refb = (out[k].data_ptr() for k in ("meta", "payload", "ops", "refb"))
+        po.source_index = out["source_index"].data_ptr() if source_index else None
+        self._check(self.lib.avo_pack_reads_device(self.h, C.byref(t), L.MEM_DEVICE if on_dev else L.MEM_HOST,
+                                                   C.byref(po)))
+        b = ReadBatch(po.n_reads, po.n_blocks, po.n_ops, po.n_refb, contig_id)
+        b.meta = out["meta"][:max(po.n_reads, 1) * 32]
+        b.payload = out["payload"][:max(po.n_blocks, 1) * 16]
+        b.ops = out["ops"][:max(po.n_ops, 1)]
+        b.refb = out["refb"][:max(po.n_refb, 1)]
+        if source_index:
+            b.source_index = out["source_index"][:po.n_reads]
+        return b
+
     # ---- raw entry points over packed data ------------------------------------------------------
     host_payload = 0    # avo_params.host_payload: 0 = pinned host payload read in place, 1 = copy
 

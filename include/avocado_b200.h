@@ -475,6 +475,10 @@ int avo_pack_bounds(const avo_text_reads* in, int64_t* n_reads, int64_t* n_block
 int avo_pack_reads(const avo_text_reads* in, avo_packed_out* out);
 /* The same over n_threads host threads (contiguous chunks of the input; identical output). */
 int avo_pack_reads_mt(const avo_text_reads* in, avo_packed_out* out, int n_threads);
+/* The same on the device: the text columns (in_mem: AVO_MEM_HOST, ideally page-locked, or
+ * AVO_MEM_DEVICE) are packed into DEVICE buffers `out` (capacities in, used counts out; identical
+ * bytes).  The result is an AVO_MEM_DEVICE avo_read_batch for avo_discover / avo_call / ... */
+int avo_pack_reads_device(avo_ctx* ctx, const avo_text_reads* in, int32_t in_mem, avo_packed_out* out);
 
 #ifdef __cplusplus
 }

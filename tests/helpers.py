@@ -131,3 +131,94 @@ def compare_call(site_keys, cols, want, exact_fp=True):
     if exact_fp:
         assert stats["fp_bit_identical"], "floating-point columns are within tolerance but not bit-identical"
     return stats
+
+
+NIB_CHARS = "=ACMGRSVTWYHKDBN"
+
+
+def ops_string(batch, i):
+    """Operators of packed read i in the oracle's notation ("2=,1X:A,1D:C,2I,1S")."""
+    m = batch.meta[i]
+    rb = int(m["refb_off"])
+    out = []
+    for k in range(int(m["n_ops"])):
+        op = int(batch.ops[int(m["op_off"]) + k])
+        ln, code = op >> 4, op & 15
+        c = "=XIDSH"[code]
+        if c == "X":
+            out.append("%dX:%s" % (ln, "".join(NIB_CHARS[int(batch.refb[rb + j]) >> 4] for j in range(ln))))
+            rb += ln
+        elif c == "D":
+            s = "".join(NIB_CHARS[(int(batch.refb[rb + j // 2]) >> (0 if j & 1 else 4)) & 15] for j in range(ln))
+            out.append("%dD:%s" % (ln, s))
+            rb += (ln + 1) // 2
+        else:
+            out.append("%d%s" % (ln, c))
+    return ",".join(out)
+
+
+def fuzz_records(seed, n):
+    """Reads with well-formed, slightly broken and random CIGAR / MD strings (packer fuzzing)."""
+    import random
+    from avocado_b200.records import AlignmentRecord
+    rng = random.Random(seed)
+    recs = []
+    for i in range(n):
+        # a consistent alignment first
+        cig, md, rlen, run = [], [], 0, 0
+        last_del = False
+        for _ in range(rng.randint(1, 6)):
+            kind = rng.choice("MMMMIDSX=")
+            ln = rng.randint(1, 12)
+            if kind in "M=X":
+                if kind == "=":
+                    run += ln
+                else:
+                    for _k in range(ln):
+                        if kind == "X" or rng.random() < 0.15:
+                            md.append("%d%s" % (run, rng.choice("ACGTN")))
+                            run = 0
+                        else:
+                            run += 1
+                rlen += ln
+                last_del = False
+            elif kind == "D":
+                md.append("%d^%s" % (run, "".join(rng.choice("ACGT") for _k in range(ln))))
+                run = 0
+            else:
+                rlen += ln
+            cig.append("%d%s" % (ln, kind))
+        md.append(str(run))
+        cigar, mdtag = "".join(cig), "".join(md)
+        mode = rng.random()
+        if mode < 0.25:          # break one of the strings
+            which = rng.random()
+            def mutate(s, alphabet):
+                if not s:
+                    return rng.choice(alphabet)
+                j = rng.randrange(len(s))
+                r = rng.random()
+                if r < 0.4:
+                    return s[:j] + rng.choice(alphabet) + s[j + 1:]
+                if r < 0.7:
+                    return s[:j] + s[j + 1:]
+                return s[:j] + rng.choice(alphabet) + s[j:]
+            if which < 0.5:
+                cigar = mutate(cigar, "0123456789MIDNSHP=X*")
+            else:
+                mdtag = mutate(mdtag, "0123456789ACGTNacgtXU^Z")
+        elif mode < 0.32:        # random junk
+            cigar = "".join(rng.choice("0123456789MIDSH=X") for _ in range(rng.randint(0, 8)))
+            mdtag = "".join(rng.choice("0123456789ACGT^") for _ in range(rng.randint(0, 8)))
+        slen = rlen if rng.random() < 0.9 else max(0, rlen + rng.randint(-3, 3))
+        qlen = slen if rng.random() < 0.9 else max(0, slen + rng.randint(-3, 3))
+        start = 100 + i * 3
+        recs.append(AlignmentRecord(
+            readMapped=rng.random() > 0.03, contigName="c", start=start, end=start + rlen,
+            cigar=None if rng.random() < 0.03 else cigar,
+            mismatchingPositions=None if rng.random() < 0.03 else mdtag,
+            sequence="".join(rng.choice("ACGTNacgtRY=") if rng.random() < 0.05 else rng.choice("ACGT") for _ in range(slen)),
+            qual="".join(chr(33 + rng.choice([0, 2, 12, 25, 37, 41, 60, 93])) for _ in range(qlen)),
+            mapq=None if rng.random() < 0.03 else rng.choice([0, 5, 20, 60, 255, 300]),
+            readNegativeStrand=rng.random() < 0.5, recordGroupSample="s", readName="r%d" % i))
+    return recs

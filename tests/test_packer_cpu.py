@@ -137,3 +137,35 @@ def test_threaded_packer_matches_serial_on_the_reference_fixtures():
     keep = np.array([(i % 7) != 3 for i in range(len(recs))], np.uint8)
     for k in (None, keep):
         _same_batch(B.pack_text_columns(cols, threads=1, keep=k), B.pack_text_columns(cols, threads=4, keep=k))
+
+
+def test_packer_agrees_with_the_oracle_on_fuzzed_cigar_and_md(oracle):
+    """extractAlignmentOperators (ObservationOperator.scala:42-171) on consistent, slightly broken
+    and random CIGAR / MD strings: the packed operators are the oracle's, and reads the oracle
+    throws on are packed with zero operators."""
+    from avocado_b200 import batch as B
+    from helpers import fuzz_records, ops_string
+    recs = [r for r in fuzz_records(11, 6000) if r.readMapped]
+    b = B.pack_reads(recs, sort=False)
+    assert b.n_reads == len(recs)
+    thrown = kept = 0
+    for i, r in enumerate(recs):
+        try:
+            want = oracle.extract_alignment_operators(r.as_dict())
+        except RuntimeError:
+            want = ""
+            thrown += 1
+        need = sum(int(x[:-1].split(":")[0][:-1] if ":" in x else x[:-1]) for x in want.split(",") if x and
+                   (x.split(":")[0][-1] in "=XIS")) if want else 0
+        if want and (need > len(r.sequence) or need > len(r.qual)):
+            want = ""            # the packer drops reads whose strings are shorter than the CIGAR
+        if want and re.search(r"(?<![0-9])0+[MIDX=]", r.cigar):
+            want = ""            # ... and reads with a zero-length non-clip element (htsjdk calls them invalid)
+        # the packed form holds BAM's 4-bit codes: MD letters outside them (U, X) are stored as N
+        want = ",".join(x.split(":")[0] + ":" + re.sub("[UX]", "N", x.split(":")[1]) if ":" in x else x
+                        for x in want.split(","))
+        want = ",".join(x for x in want.split(",") if x not in ("0S", "0H"))   # empty clips are not stored
+        got = ops_string(b, i)
+        assert got == want, (i, r.cigar, r.mismatchingPositions, got, want)
+        kept += bool(want)
+    assert thrown > 300 and kept > 3000

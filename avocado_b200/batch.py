@@ -335,10 +335,11 @@ def pack_reads(records: Sequence[AlignmentRecord], contig_id=0, keep=None, sort=
     return b
 
 
-def pack_text_columns(cols, contig_id=0, threads=1, keep=None) -> ReadBatch:
+def pack_text_columns(cols, contig_id=0, threads=1, keep=None, out=None) -> ReadBatch:
     """avo_pack_reads_mt over text columns (the dict ``text_columns`` / ``text_columns_of`` return):
     PrefilterReads' ``keep`` mask + extractAlignmentOperators + payload packing, on ``threads`` host
-    threads.  The reads must already be those of one contig, sorted by start."""
+    threads.  The reads must already be those of one contig, sorted by start.  ``out`` optionally
+    holds reusable output arrays {meta, payload, ops, refb, source_index} (e.g. page-locked)."""
     lib = L.load()
     t = L.TextReadsStruct()
     t.n = len(cols["start"])
@@ -362,11 +363,16 @@ def pack_text_columns(cols, contig_id=0, threads=1, keep=None) -> ReadBatch:
     rc = lib.avo_pack_bounds(C.byref(t), C.byref(nr), C.byref(nb), C.byref(no), C.byref(nf))
     if rc != 0:
         raise L.AvocadoError(rc, "avo_pack_bounds failed")
+    arrs = out if out is not None else {}
+    want = dict(meta=(max(nr.value, 1), META_DTYPE), payload=(max(nb.value, 1) * BLOCK_BYTES, np.uint8),
+                ops=(max(no.value, 1), np.uint32), refb=(max(nf.value, 1), np.uint8),
+                source_index=(max(nr.value, 1), np.int64))
+    for k, (cnt, dt) in want.items():
+        if k not in arrs or arrs[k].size < cnt:
+            arrs[k] = np.empty(cnt, dt)
     out = L.PackedOutStruct()
-    arrs = dict(meta=np.empty(max(nr.value, 1), META_DTYPE), payload=np.empty(max(nb.value, 1) * BLOCK_BYTES, np.uint8),
-                ops=np.empty(max(no.value, 1), np.uint32),
-                refb=np.empty(max(nf.value, 1), np.uint8), source_index=np.empty(max(nr.value, 1), np.int64))
-    out.n_reads, out.n_blocks, out.n_ops, out.n_refb = nr.value, nb.value, no.value, nf.value
+    out.n_reads, out.n_blocks, out.n_ops, out.n_refb = (arrs["meta"].size, arrs["payload"].size // BLOCK_BYTES,
+                                                        arrs["ops"].size, arrs["refb"].size)
     for k, a in arrs.items():
         setattr(out, k, a.ctypes.data)
     rc = lib.avo_pack_reads_mt(C.byref(t), C.byref(out), int(threads))

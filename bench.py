@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--e2e-bins", type=int, default=8, help="region bins the e2e leg is cut into")
     ap.add_argument("--e2e-threads", type=int, default=4,
                     help="host threads (one context + stream each) that pipeline the e2e bins")
+    ap.add_argument("--no-text", action="store_true", help="skip the from-text leg of e2e")
+    ap.add_argument("--text-reads", type=int, default=6_400_000, help="reads of the from-text sample")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -392,6 +394,87 @@ def main():
                        "in the compact wire form (h2d_bytes_per_step), bases and qualities stay in host memory and the kernels read only "
                        "the 16-byte blocks they need over PCIe; D2H of the site table and all result columns "
                        "included" % (K, T)}
+        # ---- the same from TEXT records (N1: the packer inside the timed region) -------------------
+        # CIGAR / MD / sequence / quality strings of a bounded sample of the bins, in pinned memory.
+        # Device route: the text crosses PCIe, avo_pack_reads_device packs it in HBM and
+        # avo_discover_and_call runs on the device-resident batch.  Host route beside it:
+        # avo_pack_reads_mt on all host threads (pack only; the packed batch would then take the e2e path).
+        if not args.no_text:
+            n_text_bins, acc = 0, 0
+            while n_text_bins < K and acc < args.text_reads:
+                acc += bins[n_text_bins].n_reads
+                n_text_bins += 1
+            keep_alive = []
+
+            def pin(a):
+                t = torch.from_numpy(a.view(np.uint8) if a.dtype.names else a).pin_memory()
+                keep_alive.append(t)
+                return t.numpy().view(a.dtype)
+            tcols = []
+            for i in range(n_text_bins):
+                c = B.text_columns_of(bins[i])
+                qo = c.pop("qual_off")
+                c = {k: pin(v) for k, v in c.items()}
+                c["qual_off"] = c["seq_off"] if qo is not None else None
+                tcols.append(c)
+            text_bytes = sum(v.nbytes for c in tcols for k, v in c.items() if k != "qual_off")
+            reuse = [dict() for _ in range(T)]
+
+            def run_text_thread(t):
+                out = []
+                for i in range(t, n_text_bins, T):
+                    pb = ctxs[t].pack_text_device(tcols[i], out=reuse[t])
+                    tp = ctxs[t].timing()
+                    s_i, c_i = ctxs[t].discover_and_call_packed(pb, ploidy=2, phred=25, min_obs=5,
+                                                                capacity=1 << 18, copy=False)
+                    out.append((pb.n_reads, s_i.n, tp, ctxs[t].timing()))
+                return out
+
+            def step_text():
+                return [x for part in pool.map(run_text_thread, range(T)) for x in part]
+
+            for _ in range(2):
+                step_text()
+            barrier()
+            e0.record(stream)
+            for _ in range(args.steps):
+                t_t = step_text()
+            barrier()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t_txt = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
+            if use_dist:
+                dist.all_reduce(t_txt, op=dist.ReduceOp.MAX)
+            ms_t = float(t_txt.item())
+            n_text = sum(x[0] for x in t_t)
+            assert n_text == acc
+            # host packer, all threads, into reused page-locked output arrays
+            hthreads = os.cpu_count() or 1
+            hout = {}
+            B.pack_text_columns(tcols[0], threads=hthreads, out=hout)
+            hout = {k: pin(v) for k, v in hout.items()}
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                B.pack_text_columns(tcols[0], threads=hthreads, out=hout)
+            dt_h = (time.perf_counter() - t0) / args.steps
+            t0 = time.perf_counter()
+            B.pack_text_columns(tcols[0], threads=1, out=hout)
+            dt_1 = time.perf_counter() - t0
+            e2e["from_text"] = {
+                "value": n_text * world / (ms_t / 1e3), "unit": "reads/s", "ms_per_step": ms_t,
+                "sample": "%d of the %d region bins (%d reads), %d host threads" % (n_text_bins, K, n_text, T),
+                "h2d_bytes_per_step": int(sum(x[2]["h2d_bytes"] + x[3]["h2d_bytes"] for x in t_t)),
+                "d2h_bytes_per_step": int(sum(x[3]["d2h_bytes"] for x in t_t)),
+                "text_bytes_per_read": text_bytes / n_text,
+                "pack_ms_per_bin": statistics.mean(x[2]["ms_total"] for x in t_t),
+                "pack_h2d_ms_per_bin": statistics.mean(x[2]["ms_h2d"] for x in t_t),
+                "host_packer": {"threads": hthreads, "reads_per_s": tcols[0]["start"].shape[0] / dt_h,
+                                "reads_per_s_1_thread": tcols[0]["start"].shape[0] / dt_1,
+                                "note": "avo_pack_reads_mt on one bin, pack only"},
+                "note": "AlignmentRecord text columns (CIGAR, MD, sequence, qualities) in pinned host memory -> "
+                        "avo_pack_reads_device (H2D + pack in HBM) -> avo_discover_and_call on the device batch -> "
+                        "D2H of sites and result columns"}
+            del tcols, keep_alive
         pool.shutdown()
         for c in ctxs:
             c.close()

@@ -149,6 +149,11 @@ struct BatchStats {
   int32_t unsorted;   // != 0 if start[] is not non-decreasing
 };
 
+size_t wire8_temp_bytes(int64_t n_reads);
+cudaError_t launch_wire8_expand(const avo_read_wire8* wire, const uint16_t* wire_ops, const avo_wire_exception* exc,
+                                int64_t n_exc, int32_t base, int64_t n_reads, int64_t n_ops, void* offs /* 8 B x n */,
+                                void* sizes /* 8 B x n */, avo_read_meta* meta, uint32_t* ops, void* d_temp,
+                                size_t temp_bytes, cudaStream_t s, int* n_launches);
 // compact wire columns -> full records / operators on the device (avo_setup.cu)
 size_t wire_temp_bytes(int64_t n_reads);
 cudaError_t launch_wire_expand(const avo_read_wire* wire, const uint16_t* wire_ops, int64_t n_reads,

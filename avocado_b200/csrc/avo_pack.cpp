@@ -336,6 +336,50 @@ int avo_pack_wire(const avo_read_batch* full, avo_read_wire* wire_meta, uint16_t
   return AVO_OK;
 }
 
+int avo_pack_wire8(const avo_read_batch* full, avo_read_wire8* wire8_meta, uint16_t* wire_ops,
+                   avo_wire_exception* exc, int64_t exc_capacity, int64_t* n_exc, int32_t* base) {
+  if (!full || full->mem != AVO_MEM_HOST || !n_exc || !base || (full->n_reads > 0 && (!full->meta || !wire8_meta)) ||
+      (full->n_ops > 0 && (!full->ops || !wire_ops)) || (exc_capacity > 0 && !exc) || exc_capacity < 0)
+    return AVO_E_INVALID;
+  uint64_t blk = 0, op = 0, fb = 0;
+  int64_t ne = 0;
+  int32_t prev = full->n_reads ? full->meta[0].start : 0;
+  *base = prev;
+  for (int64_t r = 0; r < full->n_reads; ++r) {
+    const avo_read_meta& m = full->meta[r];
+    const uint64_t nfb = (r + 1 < full->n_reads ? (uint64_t)full->meta[r + 1].refb_off : (uint64_t)full->n_refb) - m.refb_off;
+    if (m.seq_off != blk || m.op_off != op || m.refb_off != fb) return AVO_E_UNSUPPORTED;
+    const int64_t d = (int64_t)m.start - (int64_t)prev;
+    if (d < 0 || d > 0x3FFF || m.n_ops > 0xFFu || m.flags > 3u) return AVO_E_UNSUPPORTED;
+    // what the operators imply
+    uint64_t span = 0, lseq = 0, nrefb = 0;
+    for (uint32_t k = 0; k < m.n_ops; ++k) {
+      const uint32_t o = full->ops[m.op_off + k], len = o >> 4, code = o & 15u;
+      if (o > 0xFFFFu) return AVO_E_UNSUPPORTED;      // operator of 4096 bases or more
+      if (code == AVO_OP_MATCH || code == AVO_OP_MISMATCH || code == AVO_OP_DEL) span += len;
+      if (code == AVO_OP_MATCH || code == AVO_OP_MISMATCH || code == AVO_OP_INS || code == AVO_OP_SOFTCLIP) lseq += len;
+      if (code == AVO_OP_MISMATCH) nrefb += len;
+      if (code == AVO_OP_DEL) nrefb += (len + 1) >> 1;
+    }
+    if (nrefb != nfb) return AVO_E_UNSUPPORTED;
+    if ((int64_t)m.start + (int64_t)span != (int64_t)m.end || lseq != m.l_seq) {
+      if (ne >= exc_capacity) return AVO_E_UNSUPPORTED;
+      exc[ne].index = (uint32_t)r; exc[ne].l_seq = m.l_seq; exc[ne].end = m.end; exc[ne].reserved = 0;
+      ++ne;
+    }
+    avo_read_wire8& w = wire8_meta[r];
+    w.dstart_flags = (uint16_t)(((uint32_t)d << 2) | m.flags);
+    w.n_ops = (uint8_t)m.n_ops; w.mapq = m.mapq; w.qhead = m.qhead;
+    for (uint32_t k = 0; k < m.n_ops; ++k) wire_ops[m.op_off + k] = (uint16_t)full->ops[m.op_off + k];
+    prev = m.start;
+    blk += (m.l_seq + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES; op += m.n_ops; fb += nfb;
+  }
+  if ((int64_t)blk != full->n_blocks || (int64_t)op != full->n_ops || (int64_t)fb != full->n_refb)
+    return AVO_E_UNSUPPORTED;
+  *n_exc = ne;
+  return AVO_OK;
+}
+
 int avo_pack_bounds(const avo_text_reads* in, int64_t* n_reads, int64_t* n_blocks, int64_t* n_ops,
                     int64_t* n_refb) {
   if (!in || !n_reads || !n_blocks || !n_ops || !n_refb) return AVO_E_INVALID;

@@ -221,6 +221,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     per, contig = workload(args, world)
+    site_cap = max(1 << 18, per // 128)      # rows for discovered sites (about 1 per 360 reads)
     p = synth_for_rank(B, per, contig, rank, world)
     dev = B.synth_device(p, first=rank * per, n=per, device="cuda:%d" % local)
     torch.cuda.synchronize()
@@ -229,7 +230,7 @@ def main():
     ctx.set_stream(stream.cuda_stream)
 
     def step_device():
-        return ctx.discover_and_call_packed(dev, ploidy=2, phred=25, min_obs=5, capacity=1 << 18,
+        return ctx.discover_and_call_packed(dev, ploidy=2, phred=25, min_obs=5, capacity=site_cap,
                                             device_out=True, copy=False)
 
     def barrier():
@@ -244,7 +245,7 @@ def main():
 
     def step_host():
         return ctx.discover_and_call_packed(host.batch, ploidy=2, phred=25, min_obs=5,
-                                            capacity=1 << 18, copy=False)
+                                            capacity=site_cap, copy=False)
 
     # ---- device-resident throughput (value) -----------------------------------------------------
     for _ in range(args.warmup):
@@ -342,7 +343,7 @@ def main():
             out = []
             for i in range(t, K, T):
                 s_i, c_i = ctxs[t].discover_and_call_packed(bins[i], ploidy=2, phred=25, min_obs=5,
-                                                            capacity=1 << 18, copy=False)
+                                                            capacity=site_cap, copy=False)
                 st = np.asarray(s_i.start[:s_i.n], np.int64)
                 out.append((int(((st >= shards[i].lo) & (st < shards[i].hi)).sum()), ctxs[t].timing()))
             return out
@@ -383,7 +384,7 @@ def main():
                "d2h_bytes_per_step": int(sum(t["d2h_bytes"] for t in last)) * world,
                "ms_per_step": ms_b / args.steps,
                "region_bins": K, "host_threads": T,
-               "payload_in_place": bool(last[-1]["payload_in_place"]), "wire_form": bool(host_wire),
+               "payload_in_place": bool(last[-1]["payload_in_place"]), "wire_form": ("wire8" if hb.wire8_meta is not None else "wire16") if host_wire else None,
                "single_call": {"value": total_reads * args.steps / (ms_h / 1e3), "ms_per_step": ms_h / args.steps,
                                "ms_h2d": statistics.mean(t["ms_h2d"] for t in t_h),
                                "ms_discover": statistics.mean(t["ms_discover"] for t in t_h),
@@ -426,7 +427,7 @@ def main():
                     pb = ctxs[t].pack_text_device(tcols[i], out=reuse[t])
                     tp = ctxs[t].timing()
                     s_i, c_i = ctxs[t].discover_and_call_packed(pb, ploidy=2, phred=25, min_obs=5,
-                                                                capacity=1 << 18, copy=False)
+                                                                capacity=site_cap, copy=False)
                     out.append((pb.n_reads, s_i.n, tp, ctxs[t].timing()))
                 return out
 
@@ -554,7 +555,7 @@ class ReadBatchPinned:
             t = torch.empty(n, dtype=torch.uint8, pin_memory=True)
             self.tensors[("wire", key, len(self.tensors))] = t
             return t.numpy()
-        return batch.with_wire(alloc)
+        return batch.with_wire8(alloc) or batch.with_wire(alloc)
 
 
 if __name__ == "__main__":

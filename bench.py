@@ -11,7 +11,10 @@ BASELINE.json configs[1] shape: single-sample 60x chr20 (64 Mb), 150 bp reads = 
   e2e       the same C-ABI call with HOST (pinned) buffers, the batch cut into region bins that a few
             host threads (one context + stream each) pipeline: H2D of the records / operators /
             mismatch bytes (compact wire form), in-place payload reads over PCIe, D2H of the site
-            table + all per-site results are inside the timed region; `single_call` = one bin
+            table + all per-site results are inside the timed region; `single_call` = one bin;
+            `from_text` = a bounded sample of the bins starting from AlignmentRecord TEXT columns
+            (CIGAR, MD, sequence, qualities): avo_pack_reads_device + avo_discover_and_call, with the
+            threaded host packer (avo_pack_reads_mt) timed beside it
   roofline  the longest kernel (k_discover_tiles, or the call stage's kernels together): measured
             DRAM bytes per launch (ncu, profiles/traffic.json) / its CUDA-event duration, because the
             kernels are sparse (SURVEY.md 8d anti-inflation rule); `full_scan_step` = every packed
@@ -449,18 +452,23 @@ def main():
             ms_t = float(t_txt.item())
             n_text = sum(x[0] for x in t_t)
             assert n_text == acc
-            # host packer, all threads, into reused page-locked output arrays
-            hthreads = os.cpu_count() or 1
-            hout = {}
-            B.pack_text_columns(tcols[0], threads=hthreads, out=hout)
-            hout = {k: pin(v) for k, v in hout.items()}
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
+            # host packer, all threads, into reused page-locked output arrays (rank 0 only)
+            host_packer = None
+            if rank == 0:
+                hthreads = os.cpu_count() or 1
+                hout = {}
                 B.pack_text_columns(tcols[0], threads=hthreads, out=hout)
-            dt_h = (time.perf_counter() - t0) / args.steps
-            t0 = time.perf_counter()
-            B.pack_text_columns(tcols[0], threads=1, out=hout)
-            dt_1 = time.perf_counter() - t0
+                hout = {k: pin(v) for k, v in hout.items()}
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    B.pack_text_columns(tcols[0], threads=hthreads, out=hout)
+                dt_h = (time.perf_counter() - t0) / args.steps
+                t0 = time.perf_counter()
+                B.pack_text_columns(tcols[0], threads=1, out=hout)
+                dt_1 = time.perf_counter() - t0
+                host_packer = {"threads": hthreads, "reads_per_s": tcols[0]["start"].shape[0] / dt_h,
+                               "reads_per_s_1_thread": tcols[0]["start"].shape[0] / dt_1,
+                               "note": "avo_pack_reads_mt on one bin, pack only"}
             e2e["from_text"] = {
                 "value": n_text * world / (ms_t / 1e3), "unit": "reads/s", "ms_per_step": ms_t,
                 "sample": "%d of the %d region bins (%d reads), %d host threads" % (n_text_bins, K, n_text, T),
@@ -469,9 +477,7 @@ def main():
                 "text_bytes_per_read": text_bytes / n_text,
                 "pack_ms_per_bin": statistics.mean(x[2]["ms_total"] for x in t_t),
                 "pack_h2d_ms_per_bin": statistics.mean(x[2]["ms_h2d"] for x in t_t),
-                "host_packer": {"threads": hthreads, "reads_per_s": tcols[0]["start"].shape[0] / dt_h,
-                                "reads_per_s_1_thread": tcols[0]["start"].shape[0] / dt_1,
-                                "note": "avo_pack_reads_mt on one bin, pack only"},
+                "host_packer": host_packer,
                 "note": "AlignmentRecord text columns (CIGAR, MD, sequence, qualities) in pinned host memory -> "
                         "avo_pack_reads_device (H2D + pack in HBM) -> avo_discover_and_call on the device batch -> "
                         "D2H of sites and result columns"}

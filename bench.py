@@ -513,7 +513,8 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "stages_ms": {"discover": statistics.mean(t["ms_discover"] for t in tim),
                           "call": statistics.mean(t["ms_observe"] for t in tim),
-                          "d2h": statistics.mean(t["ms_d2h"] for t in tim)},
+                          "d2h": statistics.mean(t["ms_d2h"] for t in tim),
+                          "call_total": statistics.mean(t["ms_total"] for t in tim)},
             "sites_discovered": int(n_sites), "sites_emitted": emitted_dev,
         }
         print(json.dumps(line))

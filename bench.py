@@ -194,7 +194,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the Scala/Spark reference cannot run here (no JVM); this is the C++ oracle port of its semantics",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def config_dict(args, per, contig, world):
@@ -206,7 +206,26 @@ def config_dict(args, per, contig, world):
             "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (per * 270 / 1e9)}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: everything libraries print there (NCCL's version banner,
+    torchrun notices) is sent to stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    claim_stdout()
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -517,7 +536,7 @@ def main():
                           "call_total": statistics.mean(t["ms_total"] for t in tim)},
             "sites_discovered": int(n_sites), "sites_emitted": emitted_dev,
         }
-        print(json.dumps(line))
+        emit(line)
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()

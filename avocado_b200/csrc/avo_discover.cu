@@ -18,15 +18,17 @@
 
 namespace avo {
 
+// Tile shape (measured, profiles/README.md r2): 1536 resident threads per SM in any split run at
+// the same occupancy; the smallest CTAs lose least to the barriers between a tile's phases.
 #ifndef AVO_DISC_THREADS
-#define AVO_DISC_THREADS 512
+#define AVO_DISC_THREADS 256
 #endif
 constexpr int DISC_THREADS = AVO_DISC_THREADS;
 #ifndef AVO_DISC_W
-#define AVO_DISC_W 4096
+#define AVO_DISC_W 2048
 #endif
 #ifndef AVO_DISC_MINB
-#define AVO_DISC_MINB 3
+#define AVO_DISC_MINB 6
 #endif
 constexpr int DISC_W = AVO_DISC_W;  // reference positions owned by one tile
 #ifndef AVO_DISC_HB

@@ -56,7 +56,7 @@ class CnvStruct(C.Structure):
 class ParamsStruct(C.Structure):
     _fields_ = [("ploidy", C.c_int32), ("score_all_sites", C.c_int32), ("max_quality", C.c_int32),
                 ("max_mapq", C.c_int32), ("min_phred_discover", C.c_int32),
-                ("min_obs_discover", C.c_int32), ("host_payload", C.c_int32), ("reserved", C.c_int32)]
+                ("min_obs_discover", C.c_int32), ("host_payload", C.c_int32), ("gather_threads", C.c_int32)]
 
 
 class SitesOutStruct(C.Structure):
@@ -92,7 +92,8 @@ class TimingStruct(C.Structure):
                 ("ms_observe", C.c_float), ("ms_d2h", C.c_float), ("ms_discover_tiles", C.c_float),
                 ("ms_call_tiles", C.c_float), ("n_launches", C.c_int32),
                 ("n_tile_launches", C.c_int32), ("h2d_bytes", C.c_int64),
-                ("d2h_bytes", C.c_int64), ("payload_in_place", C.c_int32), ("reserved", C.c_int32)]
+                ("d2h_bytes", C.c_int64), ("payload_in_place", C.c_int32), ("reserved", C.c_int32),
+                ("gathered_blocks", C.c_int64)]
 
 
 class TextReadsStruct(C.Structure):

@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <thread>
+
 #include "avo_internal.h"
 
 using namespace avo;
@@ -27,6 +29,7 @@ enum Slot {
   SL_U_START, SL_U_REFLEN, SL_U_ALTLEN, SL_U_COUNT, SL_U_SRC,
   SL_L_POS, SL_L_LENS, SL_L_NIBS, SL_L_SRC, SL_L_BLK, SL_L_HASH,
   SL_C_RBASE, SL_C_BLEN, SL_C_BOFF, SL_C_BUCKETS,
+  SL_G_NBLK, SL_G_SLOT, SL_G_CLO, SL_G_IDX, SL_G_BLK0, SL_G_COMPACT,
   SL_AS_FLAG, SL_AS_JPOS, SL_AS_JR, SL_AS_JIDX, SL_AS_COVER, SL_AS_SCOVER, SL_AS_WCOUNT, SL_AS_WBASE,
   SL_AS_RES, SL_AS_START,
   SL_F_IN, SL_F_OUT,
@@ -58,6 +61,18 @@ struct avo_ctx {
   int64_t indel_guess = 0;         // indel candidates seen by the previous discovery (sizes the table)
   BatchStats* h_stats = nullptr;   // pinned
   int32_t* h_small = nullptr;      // pinned scratch (16 ints)
+  // device -> host results travel through one page-locked staging buffer (a few large DMA copies
+  // instead of one pageable copy per column) and are scattered to the caller's arrays after the sync
+  struct Pending { void* dst; size_t off; size_t bytes; };
+  uint8_t* h_stage = nullptr;
+  size_t h_stage_cap = 0, h_stage_used = 0, h_stage_want = 0;
+  std::vector<Pending> pending;
+  // host-gathered payload (avo_params.host_payload == 2): set per call by upload_reads
+  const uint8_t* gather_src = nullptr;   // the caller's host payload, read by the library's threads
+  int gather_threads = 0;
+  uint32_t* h_gidx = nullptr;      // pinned: block indices from the device
+  uint8_t* h_gblk = nullptr;       // pinned: the gathered blocks
+  size_t h_gcap = 0;               // capacity of both, in blocks
 };
 
 namespace {
@@ -116,6 +131,34 @@ int stage_in(avo_ctx* ctx, int slot, const T* src, size_t count, int mem, const 
   return AVO_OK;
 }
 
+// Device -> host copy of `total` bytes whose pieces go to nsc host arrays: staged when the staging
+// buffer has room (it grows to the previous call's demand at the next begin_call), direct otherwise.
+struct Scatter { void* dst; size_t off; size_t bytes; };
+int d2h_block(avo_ctx* ctx, const void* d_src, size_t total, const Scatter* sc, int nsc) {
+  if (total == 0) return AVO_OK;
+  constexpr size_t STAGE_MAX = (size_t)128 << 20;     // gVCF-sized outputs go straight to the caller
+  const size_t at = (ctx->h_stage_used + 255) & ~(size_t)255;
+  if (at + total <= STAGE_MAX) ctx->h_stage_want = std::max(ctx->h_stage_want, at + total);
+  ctx->timing.d2h_bytes += (int64_t)total;
+  if (at + total <= ctx->h_stage_cap) {
+    CK(cudaMemcpyAsync(ctx->h_stage + at, d_src, total, cudaMemcpyDeviceToHost, ctx->stream));
+    for (int k = 0; k < nsc; ++k)
+      if (sc[k].bytes) ctx->pending.push_back({sc[k].dst, at + sc[k].off, sc[k].bytes});
+    ctx->h_stage_used = at + total;
+    return AVO_OK;
+  }
+  for (int k = 0; k < nsc; ++k)
+    if (sc[k].bytes)
+      CK(cudaMemcpyAsync(sc[k].dst, (const char*)d_src + sc[k].off, sc[k].bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return AVO_OK;
+}
+
+// after the stream is idle
+void scatter_pending(avo_ctx* ctx) {
+  for (const auto& p : ctx->pending) memcpy(p.dst, ctx->h_stage + p.off, p.bytes);
+  ctx->pending.clear();
+}
+
 // Page-locked host memory is mapped into the device address space (UVA): returns the pointer the
 // kernels can dereference, or null when `p` is pageable / unknown to the runtime.
 template <typename T>
@@ -152,8 +195,9 @@ int validate_reads(avo_ctx* ctx, const avo_read_batch* r) {
 
 // sparse: the mode reads the payload only at variant sites and indels, so a page-locked host
 // batch keeps it where it is and the kernels fetch single sectors over PCIe
-int upload_reads(avo_ctx* ctx, const avo_read_batch* r, bool sparse, DReads* R) {
+int upload_reads(avo_ctx* ctx, const avo_read_batch* r, bool sparse, DReads* R, const avo_params* params = nullptr) {
   const size_t n = (size_t)r->n_reads;
+  ctx->gather_src = nullptr;
   R->n = r->n_reads;
   R->contig = r->contig_id;
   {
@@ -207,6 +251,11 @@ int upload_reads(avo_ctx* ctx, const avo_read_batch* r, bool sparse, DReads* R) 
     if (b) {
       R->payload = b;
       ctx->timing.payload_in_place = 1;
+      if (params && params->host_payload == 2) {     // the call stage gathers its blocks on the host
+        ctx->gather_src = r->payload;
+        ctx->gather_threads = params->gather_threads > 0 ? std::min(params->gather_threads, 64) : 4;
+        ctx->timing.payload_in_place = 2;
+      }
       return AVO_OK;
     }
   }
@@ -219,6 +268,16 @@ int begin_call(avo_ctx* ctx) {
   ctx->err.clear();
   CK(cudaSetDevice(ctx->device));
   memset(&ctx->timing, 0, sizeof ctx->timing);
+  ctx->pending.clear();
+  ctx->h_stage_used = 0;
+  if (ctx->h_stage_want > ctx->h_stage_cap) {
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+    const size_t want = ctx->h_stage_want + ctx->h_stage_want / 4 + 4096;
+    if (cudaMallocHost(&ctx->h_stage, want) == cudaSuccess) ctx->h_stage_cap = want;
+    else cudaGetLastError();              // no staging: copies go straight to the caller's arrays
+  }
+  ctx->h_stage_want = 0;
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   return AVO_OK;
 }
@@ -388,12 +447,18 @@ int export_results(avo_ctx* ctx, const DResults& D, int64_t n, int ns, avo_site_
     ctx->timing.n_launches += 1;
     return AVO_OK;
   }
+  // the columns live in one device block (res_layout): one DMA, scattered after the sync
+  Scatter sc[23];
+  int nsc = 0;
+  size_t end = 0;
+  const char* base = (const char*)D.emitted;
   for (auto& x : c) {
     if (x.bytes == 0) continue;
-    CK(cudaMemcpyAsync(x.dst, x.src, x.bytes, kind, ctx->stream));
-    ctx->timing.d2h_bytes += (int64_t)x.bytes;
+    const size_t off = (size_t)((const char*)x.src - base);
+    sc[nsc++] = Scatter{x.dst, off, x.bytes};
+    end = std::max(end, off + x.bytes);
   }
-  return AVO_OK;
+  return d2h_block(ctx, base, end, sc, nsc);
 }
 
 int check_params(avo_ctx* ctx, const avo_params* p) {
@@ -410,6 +475,71 @@ int check_params(avo_ctx* ctx, const avo_params* p) {
 // and the read index in SL_RIDX is current.
 int allsites_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const DSites& S, const DCnv& C,
                       const DCallParams& P, const DIndex& X, avo_ref_model_out* ro);
+
+// host_payload == 2: the device lists the payload blocks the joined reads need, host threads copy
+// them out of the caller's payload into a dense page-locked array, one DMA brings them back.
+int gather_payload(avo_ctx* ctx, const DReads& R, const DSites& S, const void* d_jlist, const int32_t* d_n_joined,
+                   const uint8_t** compact, const uint32_t** blk0, int* nl) {
+  CK(cudaMemcpyAsync(ctx->h_small, d_n_joined, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const int32_t nj = ctx->h_small[0];
+  if (nj <= 0) return AVO_OK;
+  void *d_nblk, *d_slot, *d_clo, *d_temp, *d_idx, *d_b0, *d_cmp;
+  CKS(get_buf(ctx, SL_G_NBLK, (size_t)(nj + 1) * 4, &d_nblk));
+  CKS(get_buf(ctx, SL_G_SLOT, (size_t)(nj + 1) * 4, &d_slot));
+  CKS(get_buf(ctx, SL_G_CLO, (size_t)(nj + 1) * 4, &d_clo));
+  const size_t tb = call_gather_temp_bytes(nj);
+  CKS(get_buf(ctx, SL_TEMP, tb, &d_temp));
+  CK(launch_call_gather_plan(R, S, d_jlist, nj, (uint32_t*)d_nblk, (uint32_t*)d_slot, (uint32_t*)d_clo, d_temp, tb,
+                             ctx->stream, nl));
+  CK(cudaMemcpyAsync(ctx->h_small, (uint32_t*)d_slot + nj, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t total = (size_t)(uint32_t)ctx->h_small[0];
+  CKS(get_buf(ctx, SL_G_BLK0, (size_t)nj * 4, &d_b0));
+  CKS(get_buf(ctx, SL_G_IDX, total * 4, &d_idx));
+  CKS(get_buf(ctx, SL_G_COMPACT, total * AVO_BLOCK_BYTES, &d_cmp));
+  CK(launch_call_blocklist(R, d_jlist, nj, (const uint32_t*)d_nblk, (const uint32_t*)d_slot, (const uint32_t*)d_clo,
+                           (uint32_t*)d_idx, (uint32_t*)d_b0, ctx->stream, nl));
+  *blk0 = (const uint32_t*)d_b0;
+  *compact = (const uint8_t*)d_cmp;
+  if (total == 0) return AVO_OK;
+  if (ctx->h_gcap < total) {
+    if (ctx->h_gidx) cudaFreeHost(ctx->h_gidx);
+    if (ctx->h_gblk) cudaFreeHost(ctx->h_gblk);
+    ctx->h_gidx = nullptr; ctx->h_gblk = nullptr; ctx->h_gcap = 0;
+    const size_t want = total + total / 4 + 1024;
+    if (cudaMallocHost(&ctx->h_gidx, want * 4) != cudaSuccess || cudaMallocHost(&ctx->h_gblk, want * AVO_BLOCK_BYTES) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, AVO_E_NOMEM, "page-locked staging for %zu payload blocks", want);
+    }
+    ctx->h_gcap = want;
+  }
+  CK(cudaMemcpyAsync(ctx->h_gidx, d_idx, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.d2h_bytes += (int64_t)(total * 4);
+  {
+    struct Blk { uint64_t a, b; };
+    const Blk* src = reinterpret_cast<const Blk*>(ctx->gather_src);
+    Blk* dst = reinterpret_cast<Blk*>(ctx->h_gblk);
+    const uint32_t* idx = ctx->h_gidx;
+    const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->gather_threads, total / 4096 + 1));
+    auto work = [=](int t) {
+      const size_t lo = total * (size_t)t / (size_t)T, hi = total * (size_t)(t + 1) / (size_t)T;
+      for (size_t k = lo; k < hi; ++k) {
+        if (k + 24 < hi) __builtin_prefetch(src + idx[k + 24], 0, 0);
+        dst[k] = src[idx[k]];
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (std::thread& th : pool) th.join();
+  }
+  CK(cudaMemcpyAsync(d_cmp, ctx->h_gblk, total * AVO_BLOCK_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->timing.h2d_bytes += (int64_t)(total * AVO_BLOCK_BYTES);
+  ctx->timing.gathered_blocks = (int64_t)total;
+  return AVO_OK;
+}
 
 int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const DevSites& T,
                   const avo_cnv* cnv, const avo_params* p, bool fresh, avo_site_results* out,
@@ -529,9 +659,12 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
   CKS(get_buf(ctx, SL_C_BUCKETS, n_slots * 4, &d_buckets));
   void* d_jlist;
   CKS(get_buf(ctx, SL_AS_JR, (size_t)R.n * 12, &d_jlist));
-  CK(launch_call_tiles(R, S, C, P, D, X, (const int32_t*)d_rbase, (const uint32_t*)d_blen,
-                       (const uint64_t*)d_boff, (uint32_t*)d_buckets, n_slots, d_jlist, small + 8,
-                       ctx->num_sms, ctx->stream, &nl));
+  CK(launch_call_join(R, S, X, (uint32_t*)d_buckets, n_slots, d_jlist, small + 8, ctx->num_sms, ctx->stream, &nl));
+  const uint8_t* d_compact = nullptr;
+  const uint32_t* d_blk0 = nullptr;
+  if (ctx->gather_src && R.n > 0 && S.c_hi > S.c_lo) CKS(gather_payload(ctx, R, S, d_jlist, small + 8, &d_compact, &d_blk0, &nl));
+  CK(launch_call_observe(R, S, C, P, D, (const int32_t*)d_rbase, (const uint32_t*)d_blen, (const uint64_t*)d_boff,
+                         (uint32_t*)d_buckets, d_jlist, small + 8, d_compact, d_blk0, ctx->num_sms, ctx->stream, &nl));
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
   ctx->timing.n_launches += nl;
   ctx->timing.n_tile_launches += nl;
@@ -747,20 +880,23 @@ int export_sites(avo_ctx* ctx, const DevSites& T, avo_sites_out* o) {
     ctx->timing.n_launches += 1;
     return AVO_OK;
   }
-  CK(cudaMemcpyAsync(o->start, T.start, n * 4, kind, ctx->stream));
-  CK(cudaMemcpyAsync(o->ref_len, T.ref_len, n * 4, kind, ctx->stream));
-  CK(cudaMemcpyAsync(o->alt_len, T.alt_len, n * 4, kind, ctx->stream));
-  CK(cudaMemcpyAsync(o->allele_off, T.allele_off, (n + 1) * 4, kind, ctx->stream));
-  CK(cudaMemcpyAsync(o->alleles4, T.alleles4, ((size_t)T.n_nibbles + 1) / 2, kind, ctx->stream));
-  if (o->count) CK(cudaMemcpyAsync(o->count, T.count, n * 4, kind, ctx->stream));
-  if (kind == cudaMemcpyDeviceToHost)
-    ctx->timing.d2h_bytes += (int64_t)(n * 16 + 4 + ((size_t)T.n_nibbles + 1) / 2 + (o->count ? n * 4 : 0));
+  auto one = [&](void* dst, const void* src, size_t bytes) {
+    const Scatter sc{dst, 0, bytes};
+    return d2h_block(ctx, src, bytes, &sc, 1);
+  };
+  CKS(one(o->start, T.start, n * 4));
+  CKS(one(o->ref_len, T.ref_len, n * 4));
+  CKS(one(o->alt_len, T.alt_len, n * 4));
+  CKS(one(o->allele_off, T.allele_off, (n + 1) * 4));
+  CKS(one(o->alleles4, T.alleles4, ((size_t)T.n_nibbles + 1) / 2));
+  if (o->count) CKS(one(o->count, T.count, n * 4));
   return AVO_OK;
 }
 
 int finish_call(avo_ctx* ctx, bool did_discover, bool did_call) {
   CK(cudaEventRecord(ctx->ev[7], ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  scatter_pending(ctx);
   avo_timing& t = ctx->timing;
   t.ms_total = ev_ms(ctx, 0, 7);
   t.ms_h2d = ev_ms(ctx, 0, 1);
@@ -832,6 +968,9 @@ void avo_ctx_destroy(avo_ctx* ctx) {
   if (ctx->d_lgam) cudaFree(ctx->d_lgam);
   if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->h_gidx) cudaFreeHost(ctx->h_gidx);
+  if (ctx->h_gblk) cudaFreeHost(ctx->h_gblk);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   cudaGetLastError();
@@ -858,7 +997,7 @@ int avo_discover(avo_ctx* ctx, const avo_read_batch* reads, const avo_params* pa
   CKS(validate_reads(ctx, reads));
   if (!params) return fail(ctx, AVO_E_INVALID, "params is NULL");
   DReads R;
-  CKS(upload_reads(ctx, reads, params->host_payload == 0, &R));
+  CKS(upload_reads(ctx, reads, params->host_payload != 1, &R));
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   BatchStats hs;
   const bool hinted = stats_from_hints(reads, &hs);
@@ -885,7 +1024,7 @@ static int call_entry(avo_ctx* ctx, const avo_read_batch* reads, const avo_sites
   if (!sites->start || !sites->ref_len || !sites->alt_len || !sites->allele_off || !sites->alleles4)
     return fail(ctx, AVO_E_INVALID, "sites has NULL columns");
   DReads R;
-  CKS(upload_reads(ctx, reads, params->host_payload == 0 && !ref_model, &R));
+  CKS(upload_reads(ctx, reads, params->host_payload != 1 && !ref_model, &R, params));
   DevSites T;
   T.n = (int32_t)sites->n;
   T.n_nibbles = (uint32_t)sites->n_allele_nibbles;
@@ -929,7 +1068,7 @@ int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_c
     return fail(ctx, AVO_E_INVALID, "score_all_sites: discover with avo_discover, then avo_call_all_sites");
   CKS(check_results(ctx, results));
   DReads R;
-  CKS(upload_reads(ctx, reads, params->host_payload == 0 && !params->score_all_sites, &R));
+  CKS(upload_reads(ctx, reads, params->host_payload != 1 && !params->score_all_sites, &R, params));
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   BatchStats hs;
   const bool hinted = stats_from_hints(reads, &hs);

@@ -217,11 +217,22 @@ size_t call_scan_temp_bytes(int32_t n);
 cudaError_t launch_call_buckets(const DReads& R, const DSites& S, const DIndex& X, const BatchStats& hstats, int32_t* rbase,
                                 uint32_t* blen, uint64_t* boff, void* d_temp, size_t temp_bytes,
                                 cudaStream_t s, int* n_launches);
-cudaError_t launch_call_tiles(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
-                              const DResults& out, const DIndex& X, const int32_t* rbase,
-                              const uint32_t* blen, const uint64_t* boff, uint32_t* buckets,
-                              size_t n_slots, void* joined_list /* 12 B x n_reads */, int32_t* d_counter,
-                              int num_sms, cudaStream_t s, int* n_launches);
+// join -> (optional host gather of the payload blocks the joined reads need) -> observe + reduce
+cudaError_t launch_call_join(const DReads& R, const DSites& S, const DIndex& X, uint32_t* buckets, size_t n_slots,
+                             void* joined_list /* 12 B x n_reads */, int32_t* d_counter, int num_sms,
+                             cudaStream_t s, int* n_launches);
+size_t call_gather_temp_bytes(int32_t n_joined);
+cudaError_t launch_call_gather_plan(const DReads& R, const DSites& S, const void* joined_list, int32_t n_joined,
+                                    uint32_t* nblk, uint32_t* slot, uint32_t* clo, void* d_temp, size_t temp_bytes,
+                                    cudaStream_t s, int* n_launches);
+cudaError_t launch_call_blocklist(const DReads& R, const void* joined_list, int32_t n_joined, const uint32_t* nblk,
+                                  const uint32_t* slot, const uint32_t* clo, uint32_t* idx, uint32_t* blk0,
+                                  cudaStream_t s, int* n_launches);
+cudaError_t launch_call_observe(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
+                                const DResults& out, const int32_t* rbase, const uint32_t* blen,
+                                const uint64_t* boff, uint32_t* buckets, const void* joined_list,
+                                const int32_t* d_counter, const uint8_t* compact, const uint32_t* blk0,
+                                int num_sms, cudaStream_t s, int* n_launches);
 
 // scoreAllSites reference-model rows (avo_allsites.cu).  All pointers are device scratch.
 struct AllSitesPlan {

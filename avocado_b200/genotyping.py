@@ -153,11 +153,14 @@ class Context:
         return b
 
     # ---- raw entry points over packed data ------------------------------------------------------
-    host_payload = 0    # avo_params.host_payload: 0 = pinned host payload read in place, 1 = copy
+    host_payload = 0    # avo_params.host_payload: 0 = pinned host payload read in place, 1 = copy,
+    #                     2 = read in place by discovery, gathered by host threads for the call stage
+    gather_threads = 0  # avo_params.gather_threads (0 = the library's default)
 
     def _params(self, ploidy=2, max_quality=93, max_mapq=93, phred=0, min_obs=None, score_all=False):
         p = L.ParamsStruct()
         p.host_payload = self.host_payload
+        p.gather_threads = self.gather_threads
         p.ploidy, p.score_all_sites = ploidy, int(bool(score_all))
         p.max_quality, p.max_mapq = max_quality, max_mapq
         p.min_phred_discover = phred

@@ -51,8 +51,13 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=8_000_000, help="reads in the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-bins", type=int, default=8, help="region bins the e2e leg is cut into")
-    ap.add_argument("--e2e-threads", type=int, default=4,
-                    help="host threads (one context + stream each) that pipeline the e2e bins")
+    ap.add_argument("--e2e-threads", type=int, default=0,
+                    help="host threads (one context + stream each) that work through the e2e bins "
+                         "(0 = min(8, host threads / (2 x ranks)))")
+    ap.add_argument("--e2e-payload", type=int, default=2, help="avo_params.host_payload of the e2e leg: 0 in place, "
+                    "1 copy, 2 in place for discovery + host-gathered blocks for the call stage")
+    ap.add_argument("--gather-threads", type=int, default=2,
+                    help="avo_params.gather_threads: host threads gathering payload blocks per call")
     ap.add_argument("--no-text", action="store_true", help="skip the from-text leg of e2e")
     ap.add_argument("--text-reads", type=int, default=6_400_000, help="reads of the from-text sample")
     ap.add_argument("--no-cpu", action="store_true")
@@ -265,6 +270,8 @@ def main():
     # that the two timed regions run back to back under the clock sampler
     host = None if args.no_e2e else ReadBatchPinned(dev, B)
 
+    ctx.host_payload, ctx.gather_threads = args.e2e_payload, args.gather_threads   # host batches only
+
     def step_host():
         return ctx.discover_and_call_packed(host.batch, ploidy=2, phred=25, min_obs=5,
                                             capacity=site_cap, copy=False)
@@ -357,34 +364,44 @@ def main():
         host_wire = host.wire
         shards = plan_region_shards(hb.meta["start"], hb.meta["end"], K, max_site_len=64)
         bins = [host.pinned_slice(sh.read_lo, sh.read_hi) for sh in shards]
-        T = max(1, min(args.e2e_threads, K))
+        T = args.e2e_threads or max(2, min(8, (os.cpu_count() or 8) // (2 * world)))
+        T = max(1, min(T, K))
         ctxs = [Context(local) for _ in range(T)]
+        for c in ctxs:                 # the call stage's payload blocks are gathered by host threads
+            c.host_payload, c.gather_threads = args.e2e_payload, args.gather_threads
         pool = ThreadPoolExecutor(T)
 
-        def run_thread(t):        # thread t takes bins t, t + T, ... on its own context / stream
+        def run_thread(t, steps=1):   # thread t takes bins t, t + T, ... on its own context / stream
             out = []
-            for i in range(t, K, T):
-                s_i, c_i = ctxs[t].discover_and_call_packed(bins[i], ploidy=2, phred=25, min_obs=5,
-                                                            capacity=site_cap, copy=False)
-                st = np.asarray(s_i.start[:s_i.n], np.int64)
-                out.append((int(((st >= shards[i].lo) & (st < shards[i].hi)).sum()), ctxs[t].timing()))
+            for _step in range(steps):
+                out.append([])
+                for i in range(t, K, T):
+                    w0 = time.perf_counter()
+                    s_i, c_i = ctxs[t].discover_and_call_packed(bins[i], ploidy=2, phred=25, min_obs=5,
+                                                                capacity=site_cap, copy=False)
+                    w1 = time.perf_counter()
+                    st = np.asarray(s_i.start[:s_i.n], np.int64)
+                    tm = ctxs[t].timing()
+                    tm["wall"] = (i, t, w0, w1)
+                    out[-1].append((int(((st >= shards[i].lo) & (st < shards[i].hi)).sum()), tm))
             return out
 
-        def step_bins():
-            return [x for part in pool.map(run_thread, range(T)) for x in part]
+        def step_bins(steps=1):
+            """`steps` passes over all bins.  Every host thread runs its bins of successive passes back
+            to back, like executor threads working through a stream of partitions: there is no barrier
+            between passes, so the H2D phase of one bin overlaps the call stage of another."""
+            parts = list(pool.map(lambda t: run_thread(t, steps), range(T)))
+            return [[x for part in parts for x in part[k]] for k in range(steps)]
 
-        for _ in range(2):
-            step_bins()
+        step_bins(2)
         barrier()
         e0.record(stream)
-        t_b = []
-        for _ in range(args.steps):
-            t_b.append(step_bins())
+        t_b = step_bins(args.steps)
         barrier()
         e1.record(stream)
         torch.cuda.synchronize()
         ms_b = e0.elapsed_time(e1)
-        assert sum(n for n, _ in t_b[-1]) == n_sites_dev, "region bins must reproduce the site count"
+        assert all(sum(n for n, _ in tb) == n_sites_dev for tb in t_b), "region bins must reproduce the site count"
         # one bin = the plain single call
         barrier()
         e0.record(stream)
@@ -401,22 +418,36 @@ def main():
             dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
         ms_b, ms_h = float(t_dev[0].item()), float(t_dev[1].item())
         last = [t for _, t in t_b[-1]]
+        if os.environ.get("AVO_BENCH_DEBUG"):
+            w00 = min(t["wall"][2] for t in last)
+            for t in last:
+                print("bin %d thread %d: wall %.2f..%.2f  total %.2f h2d %.2f discover %.2f call %.2f d2h %.2f blocks %d" % (
+                    t["wall"][0], t["wall"][1], (t["wall"][2] - w00) * 1e3, (t["wall"][3] - w00) * 1e3,
+                    t["ms_total"], t["ms_h2d"], t["ms_discover"], t["ms_observe"], t["ms_d2h"], t["gathered_blocks"]),
+                    file=sys.stderr)
         e2e = {"value": total_reads * args.steps / (ms_b / 1e3), "unit": "reads/s",
                "h2d_bytes_per_step": int(sum(t["h2d_bytes"] for t in last)) * world,
                "d2h_bytes_per_step": int(sum(t["d2h_bytes"] for t in last)) * world,
                "ms_per_step": ms_b / args.steps,
                "region_bins": K, "host_threads": T,
-               "payload_in_place": bool(last[-1]["payload_in_place"]), "wire_form": ("wire8" if hb.wire8_meta is not None else "wire16") if host_wire else None,
+               "payload_in_place": bool(last[-1]["payload_in_place"]),
+               "payload_mode": {0: "copied", 1: "read in place over PCIe",
+                                2: "discovery reads in place, call-stage blocks gathered by host threads"}[
+                                    int(last[-1]["payload_in_place"])],
+               "gathered_blocks_per_step": int(sum(t["gathered_blocks"] for t in last)) * world,
+               "gather_threads_per_call": args.gather_threads, "wire_form": ("wire8" if hb.wire8_meta is not None else "wire16") if host_wire else None,
                "single_call": {"value": total_reads * args.steps / (ms_h / 1e3), "ms_per_step": ms_h / args.steps,
                                "ms_h2d": statistics.mean(t["ms_h2d"] for t in t_h),
                                "ms_discover": statistics.mean(t["ms_discover"] for t in t_h),
                                "ms_call": statistics.mean(t["ms_observe"] for t in t_h),
                                "ms_d2h": statistics.mean(t["ms_d2h"] for t in t_h)},
-               "note": "pinned host batch through the C ABI (avo_discover_and_call), %d region bins pipelined by %d "
-                       "host threads (one context + stream each): records, operators and mismatch bytes are copied "
-                       "in the compact wire form (h2d_bytes_per_step), bases and qualities stay in host memory and the kernels read only "
-                       "the 16-byte blocks they need over PCIe; D2H of the site table and all result columns "
-                       "included" % (K, T)}
+               "note": "pinned host batch through the C ABI (avo_discover_and_call), %d region bins worked through by %d "
+                       "host threads (one context + stream each; the K steps are K passes over the bins with no barrier "
+                       "between passes, like executor threads on a stream of partitions): records, operators and mismatch "
+                       "bytes are copied in the compact wire form, bases and qualities stay in host memory: discovery reads "
+                       "the few blocks it needs in place over PCIe, the call stage's blocks are listed by the device, "
+                       "gathered by host threads and sent as one dense copy (all inside h2d / d2h_bytes_per_step); D2H of "
+                       "the site table and all result columns included" % (K, T)}
         # ---- the same from TEXT records (N1: the packer inside the timed region) -------------------
         # CIGAR / MD / sequence / quality strings of a bounded sample of the bins, in pinned memory.
         # Device route: the text crosses PCIe, avo_pack_reads_device packs it in HBM and

@@ -210,8 +210,12 @@ typedef struct {
   int32_t min_obs_discover;   /* optMinObservations; < 0 = None (distinct); keep count > this */
   int32_t host_payload;       /* AVO_MEM_HOST batches: 0 = read the payload in place over PCIe when
                                  it is page-locked and the mode touches it sparsely (variant-only
-                                 calling, discovery), 1 = always copy it to the device */
-  int32_t reserved;
+                                 calling, discovery), 1 = always copy it to the device, 2 = as 0, but the
+                                 call stage's blocks are gathered by host threads: the device lists the
+                                 16-byte blocks the joined reads need, the library copies them out of the
+                                 payload into a dense page-locked array and sends that (one PCIe request
+                                 per block becomes one DMA) */
+  int32_t gather_threads;     /* host threads for host_payload == 2 (0 = 4) */
 } avo_params;
 
 /* ---- outputs ------------------------------------------------------------------------------ */
@@ -278,8 +282,10 @@ typedef struct {
   int32_t n_tile_launches; /* of which tile kernels (1 per stage unless a buffer overflowed) */
   int64_t h2d_bytes;
   int64_t d2h_bytes;
-  int32_t payload_in_place; /* 1: the payload was read from pinned host memory, not copied */
+  int32_t payload_in_place; /* 1: the payload was read from pinned host memory, not copied; 2: and the call
+                               stage's blocks were gathered on the host */
   int32_t reserved;
+  int64_t gathered_blocks;  /* host_payload == 2: 16-byte blocks gathered on the host */
 } avo_timing;
 int avo_get_timing(const avo_ctx* ctx, avo_timing* out);
 

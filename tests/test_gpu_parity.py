@@ -240,13 +240,15 @@ def test_pinned_host_batch_is_read_in_place(ctx):
         v = t.numpy()
         setattr(pinned, name, v.view(dt) if v.dtype != np.dtype(dt) else v)
     outs = []
-    for batch, payload, in_place in ((pinned, 0, 1), (pinned, 1, 0), (host, 0, 0)):
+    for batch, payload, in_place in ((pinned, 0, 1), (pinned, 1, 0), (host, 0, 0), (pinned, 2, 2), (host, 2, 0)):
         ctx.host_payload = payload
         try:
             sites, cols = ctx.discover_and_call_packed(batch, phred=25, min_obs=5)
         finally:
             ctx.host_payload = 0
-        assert ctx.timing()["payload_in_place"] == in_place
+        t = ctx.timing()
+        assert t["payload_in_place"] == in_place
+        assert (t["gathered_blocks"] > 1000) == (in_place == 2)
         outs.append((sites, cols))
     for sites, cols in outs[1:]:
         assert np.array_equal(sites.start, outs[0][0].start)
@@ -318,3 +320,50 @@ def test_wire8_exceptions_reach_the_device(ctx):
     c_wire = ctx.call_packed(wire, s_full)
     for k in c_full:
         assert np.array_equal(np.asarray(c_full[k]), np.asarray(c_wire[k]), equal_nan=True), k
+
+
+def _pinned_copy(B, host):
+    import torch
+    pinned = B.ReadBatch(host.n_reads, host.n_blocks, host.n_ops, host.n_refb, host.contig_id, stats=host.stats)
+    keep = []
+    for name, dt in B.READ_COLUMNS:
+        a = getattr(host, name)
+        t = torch.from_numpy(a.view(np.uint8) if a.dtype == B.META_DTYPE else B._torch_view(a)).pin_memory()
+        keep.append(t)
+        v = t.numpy()
+        setattr(pinned, name, v.view(dt) if v.dtype != np.dtype(dt) else v)
+    pinned._keep = keep
+    return pinned
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_host_gathered_payload_gives_the_same_rows(ctx, threads):
+    """host_payload = 2: the call stage works on payload blocks gathered by host threads (the device
+    lists them); rows are bit-identical to the in-place path on an indel- and clip-rich batch, for
+    avo_call against a foreign site table too, and on the reference's indel fixtures."""
+    from avocado_b200 import batch as B
+    from helpers import load_fixture
+    p = B.synth_params(seed=21, n_reads_total=40000, contig_len=60000, indel_rate=2e-3, snp_rate=3e-3,
+                       softclip_frac=0.3, triallelic_frac=0.05)
+    batches = [_pinned_copy(B, B.synth_host(p))]
+    for name in ("NA12878.chr1.832736", "NA12878.chr1.875159", "NA12878.1_1777263", "NA12878.chr1.905130"):
+        try:
+            recs = [r for r in load_fixture(name)[0] if r.readMapped]
+        except FileNotFoundError:
+            continue
+        batches.append(_pinned_copy(B, B.pack_reads(recs)))
+    assert len(batches) >= 2
+    for batch in batches:
+        rows = []
+        for mode in (0, 2):
+            ctx.host_payload, ctx.gather_threads = mode, threads
+            try:
+                sites = ctx.discover_packed(batch, phred=10, min_obs=1)
+                cols = ctx.call_packed(batch, sites)
+                assert ctx.timing()["payload_in_place"] == (2 if mode else 1)
+            finally:
+                ctx.host_payload, ctx.gather_threads = 0, 0
+            rows.append((sites, cols))
+        assert rows[0][0].n == rows[1][0].n > 0
+        for k in rows[0][1]:
+            assert np.array_equal(np.asarray(rows[0][1][k]), np.asarray(rows[1][1][k]), equal_nan=True), k

@@ -270,7 +270,9 @@ def main():
     # that the two timed regions run back to back under the clock sampler
     host = None if args.no_e2e else ReadBatchPinned(dev, B)
 
-    ctx.host_payload, ctx.gather_threads = args.e2e_payload, args.gather_threads   # host batches only
+    # host batches only; the single call has the host to itself and gathers with all its threads
+    ctx.host_payload = args.e2e_payload
+    ctx.gather_threads = max(args.gather_threads, (os.cpu_count() or 8) // max(1, int(os.environ.get("WORLD_SIZE", "1"))))
 
     def step_host():
         return ctx.discover_and_call_packed(host.batch, ploidy=2, phred=25, min_obs=5,

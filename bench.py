@@ -54,8 +54,9 @@ def parse_args():
     ap.add_argument("--e2e-threads", type=int, default=0,
                     help="host threads (one context + stream each) that work through the e2e bins "
                          "(0 = min(8, host threads / (2 x ranks)))")
-    ap.add_argument("--e2e-payload", type=int, default=2, help="avo_params.host_payload of the e2e leg: 0 in place, "
-                    "1 copy, 2 in place for discovery + host-gathered blocks for the call stage")
+    ap.add_argument("--e2e-payload", type=int, default=-1, help="avo_params.host_payload of the e2e leg: 0 in place, "
+                    "1 copy, 2 in place for discovery + host-gathered blocks for the call stage "
+                    "(-1 = 2 when the rank has 12 or more host threads to itself, else 0)")
     ap.add_argument("--gather-threads", type=int, default=2,
                     help="avo_params.gather_threads: host threads gathering payload blocks per call")
     ap.add_argument("--no-text", action="store_true", help="skip the from-text leg of e2e")
@@ -235,6 +236,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     rank, world, local = dist_env()
+    cpus_per_rank = max(1, (os.cpu_count() or 8) // world)
+    if args.e2e_payload < 0:        # gathering on the host needs cores; reading in place needs none
+        args.e2e_payload = 2 if cpus_per_rank >= 12 else 0
     import numpy as np
     import torch
     from avocado_b200 import batch as B
@@ -366,7 +370,7 @@ def main():
         host_wire = host.wire
         shards = plan_region_shards(hb.meta["start"], hb.meta["end"], K, max_site_len=64)
         bins = [host.pinned_slice(sh.read_lo, sh.read_hi) for sh in shards]
-        T = args.e2e_threads or max(2, min(8, (os.cpu_count() or 8) // (2 * world)))
+        T = args.e2e_threads or (max(2, min(8, cpus_per_rank // 2)) if args.e2e_payload == 2 else 4)
         T = max(1, min(T, K))
         ctxs = [Context(local) for _ in range(T)]
         for c in ctxs:                 # the call stage's payload blocks are gathered by host threads

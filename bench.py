@@ -100,7 +100,7 @@ class ClockSampler:
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None

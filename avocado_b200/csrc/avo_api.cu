@@ -70,6 +70,7 @@ struct avo_ctx {
   // host-gathered payload (avo_params.host_payload == 2): set per call by upload_reads
   const uint8_t* gather_src = nullptr;   // the caller's host payload, read by the library's threads
   int gather_threads = 0;
+  size_t slots_guess = 0;          // bucket slots of the previous call stage (+ 1/8): capacity of the next
   uint32_t* h_gidx = nullptr;      // pinned: block indices from the device
   uint8_t* h_gblk = nullptr;       // pinned: the gathered blocks
   size_t h_gcap = 0;               // capacity of both, in blocks
@@ -648,27 +649,51 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
   CKS(get_buf(ctx, SL_TEMP, tb2, &d_temp));
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   int nl = 0;
-  size_t n_slots = 0;
-  if (R.n > 0 && S.c_hi > S.c_lo) {
+  const bool work = R.n > 0 && S.c_hi > S.c_lo;
+  if (work)
     CK(launch_call_buckets(R, S, X, hs, (int32_t*)d_rbase, (uint32_t*)d_blen, (uint64_t*)d_boff, d_temp, tb2,
                            ctx->stream, &nl));
-    CK(cudaMemcpyAsync(ctx->h_small, (uint64_t*)d_boff + S.c_hi, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    n_slots = (size_t)*reinterpret_cast<const uint64_t*>(ctx->h_small);
-  }
-  CKS(get_buf(ctx, SL_C_BUCKETS, n_slots * 4, &d_buckets));
   void* d_jlist;
   CKS(get_buf(ctx, SL_AS_JR, (size_t)R.n * 12, &d_jlist));
-  CK(launch_call_join(R, S, X, (uint32_t*)d_buckets, n_slots, d_jlist, small + 8, ctx->num_sms, ctx->stream, &nl));
-  const uint8_t* d_compact = nullptr;
-  const uint32_t* d_blk0 = nullptr;
-  if (ctx->gather_src && R.n > 0 && S.c_hi > S.c_lo) CKS(gather_payload(ctx, R, S, d_jlist, small + 8, &d_compact, &d_blk0, &nl));
-  CK(launch_call_observe(R, S, C, P, D, (const int32_t*)d_rbase, (const uint32_t*)d_blen, (const uint64_t*)d_boff,
-                         (uint32_t*)d_buckets, d_jlist, small + 8, d_compact, d_blk0, ctx->num_sms, ctx->stream, &nl));
-  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  // The number of bucket slots is known on the device.  Instead of waiting for it, the stage runs
+  // with the previous call's count (+ 1/8) as capacity, the kernels never write past it, and the
+  // count is checked with the results; a stage that ran out of slots is rerun with the exact count.
+  uint64_t* h_slots = reinterpret_cast<uint64_t*>(ctx->h_small + 12);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const bool speculative = attempt == 0 && work && ctx->slots_guess > 0 && !ctx->gather_src;
+    size_t n_slots = 0;
+    if (work) {
+      CK(cudaMemcpyAsync(h_slots, (uint64_t*)d_boff + S.c_hi, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      if (speculative) {
+        n_slots = ctx->slots_guess;
+      } else {
+        CK(cudaStreamSynchronize(ctx->stream));
+        n_slots = (size_t)*h_slots;
+        ctx->slots_guess = n_slots + n_slots / 8 + 1024;
+      }
+    }
+    CKS(get_buf(ctx, SL_C_BUCKETS, n_slots * 4, &d_buckets));
+    CK(launch_call_join(R, S, X, (uint32_t*)d_buckets, n_slots, d_jlist, small + 8, ctx->num_sms, ctx->stream, &nl));
+    const uint8_t* d_compact = nullptr;
+    const uint32_t* d_blk0 = nullptr;
+    if (ctx->gather_src && work) CKS(gather_payload(ctx, R, S, d_jlist, small + 8, &d_compact, &d_blk0, &nl));
+    CK(launch_call_observe(R, S, C, P, D, (const int32_t*)d_rbase, (const uint32_t*)d_blen, (const uint64_t*)d_boff,
+                           (uint32_t*)d_buckets, n_slots, d_jlist, small + 8, d_compact, d_blk0, ctx->num_sms,
+                           ctx->stream, &nl));
+    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    const size_t mark = ctx->pending.size(), used = ctx->h_stage_used;
+    CKS(export_results(ctx, D, T.n, ns, out));
+    if (!speculative) break;
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t actual = (size_t)*h_slots;
+    ctx->slots_guess = actual + actual / 8 + 1024;
+    if (actual <= n_slots) break;
+    ctx->pending.resize(mark);              // too few slots: forget the exported rows and run again
+    ctx->h_stage_used = used;
+    CK(cudaMemsetAsync(d_res, 0, L.total, ctx->stream));
+  }
   ctx->timing.n_launches += nl;
   ctx->timing.n_tile_launches += nl;
-  CKS(export_results(ctx, D, T.n, ns, out));
   if (ref_out) CKS(allsites_internal(ctx, R, hs, S, C, P, X, ref_out));
   return AVO_OK;
 }

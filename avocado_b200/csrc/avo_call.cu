@@ -73,7 +73,7 @@ __global__ void k_site_buckets(DReads R, DSites S, DIndex X, int32_t max_span, i
 __device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
                              int32_t r, int32_t a, int32_t b, const int32_t* __restrict__ rbase,
                              const uint64_t* __restrict__ boff, uint32_t* __restrict__ buckets,
-                             bool blk0_given = false, uint32_t blk0 = 0) {
+                             uint64_t n_slots, bool blk0_given = false, uint32_t blk0 = 0) {
   const MetaA ma = load_meta_a(R.meta, r);
   const MetaB mb = load_meta_b(R.meta, r);
   // observeRead throws for such reads (BG:385-391: skipped); no operators -> no observations
@@ -119,8 +119,9 @@ __device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, co
     const int q = (c.q < 0) ? P.max_quality : min(P.max_quality, c.q);  // BG:451 least() skips null
     if (q < 1 || mq < 1) continue;                        // no such row in the score table: dropped
     const int cn = copy_number_for(C, P.base_ploidy, rc.start, rc.end, js, js + __ldg(S.ref_len + j));
-    buckets[(size_t)__ldg(boff + j) + (uint32_t)(r - __ldg(rbase + j))] =
-        make_record(c.cat, rc.fwd, q, mq, cn - P.min_ploidy);
+    // n_slots may be a guess carried over from the previous call (the host checks it afterwards)
+    const uint64_t at = __ldg(boff + j) + (uint32_t)(r - __ldg(rbase + j));
+    if (at < n_slots) buckets[at] = make_record(c.cat, rc.fwd, q, mq, cn - P.min_ploidy);
   }
 }
 
@@ -197,14 +198,14 @@ k_call_join(DReads R, DSites S, DIndex X, JoinedRead* __restrict__ list, int32_t
 __global__ void __launch_bounds__(OBS_THREADS, AVO_CALL_MINB)
 k_call_observe(DReads R, DSites S, DCnv C, DCallParams P, const JoinedRead* __restrict__ list,
                const int32_t* __restrict__ n_list, const int32_t* __restrict__ rbase,
-               const uint64_t* __restrict__ boff, uint32_t* __restrict__ buckets,
+               const uint64_t* __restrict__ boff, uint32_t* __restrict__ buckets, uint64_t n_slots,
                const uint8_t* __restrict__ compact, const uint32_t* __restrict__ blk0) {
   const int32_t n = *n_list;
   const bool gathered = compact != nullptr;
   if (gathered) R.payload = compact;
   for (int32_t i = blockIdx.x * OBS_THREADS + threadIdx.x; i < n; i += gridDim.x * OBS_THREADS) {
     const JoinedRead j = list[i];
-    observe_read(R, S, C, P, j.r, j.a, j.b, rbase, boff, buckets, gathered, gathered ? blk0[i] : 0u);
+    observe_read(R, S, C, P, j.r, j.a, j.b, rbase, boff, buckets, n_slots, gathered, gathered ? blk0[i] : 0u);
   }
 }
 
@@ -299,11 +300,12 @@ k_call_blocklist(DReads R, const JoinedRead* __restrict__ list, int32_t n, const
 template <int NS>
 __global__ void __launch_bounds__(128)
 k_call_reduce(DSites S, DCallParams P, DResults O, const uint64_t* __restrict__ boff,
-              const uint32_t* __restrict__ blen, const uint32_t* __restrict__ buckets) {
+              const uint32_t* __restrict__ blen, const uint32_t* __restrict__ buckets, uint64_t n_slots) {
   const int32_t j = S.c_lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= S.c_hi) return;
   const uint32_t* __restrict__ bk = buckets + (size_t)__ldg(boff + j);
   const uint32_t n = __ldg(blen + j);
+  if (__ldg(boff + j) + n > n_slots) return;   // guessed capacity too small: the host reruns the stage
   const int ns = P.ns;
   SiteAcc A;
   for (int c = 0; c < 4; ++c)
@@ -432,7 +434,7 @@ cudaError_t launch_call_blocklist(const DReads& R, const void* joined_list, int3
 // compact / blk0: the host-gathered payload blocks and every joined read's first-block slot, or NULL
 cudaError_t launch_call_observe(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
                                 const DResults& out, const int32_t* rbase, const uint32_t* blen,
-                                const uint64_t* boff, uint32_t* buckets, const void* joined_list,
+                                const uint64_t* boff, uint32_t* buckets, size_t n_slots, const void* joined_list,
                                 const int32_t* d_counter, const uint8_t* compact, const uint32_t* blk0,
                                 int num_sms, cudaStream_t s, int* n_launches) {
   if (R.n == 0 || S.c_hi <= S.c_lo) return cudaSuccess;
@@ -440,12 +442,12 @@ cudaError_t launch_call_observe(const DReads& R, const DSites& S, const DCnv& C,
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_call_observe, OBS_THREADS, 0);
   if (e != cudaSuccess) return e;
   k_call_observe<<<num_sms * max(1, blocks_per_sm), OBS_THREADS, 0, s>>>(
-      R, S, C, P, (const JoinedRead*)joined_list, d_counter, rbase, boff, buckets, compact, blk0);
+      R, S, C, P, (const JoinedRead*)joined_list, d_counter, rbase, boff, buckets, (uint64_t)n_slots, compact, blk0);
   const int32_t n = S.c_hi - S.c_lo;
   if (P.ns <= 3)
-    k_call_reduce<3><<<(n + 127) / 128, 128, 0, s>>>(S, P, out, boff, blen, buckets);
+    k_call_reduce<3><<<(n + 127) / 128, 128, 0, s>>>(S, P, out, boff, blen, buckets, (uint64_t)n_slots);
   else
-    k_call_reduce<NSMAX><<<(n + 127) / 128, 128, 0, s>>>(S, P, out, boff, blen, buckets);
+    k_call_reduce<NSMAX><<<(n + 127) / 128, 128, 0, s>>>(S, P, out, boff, blen, buckets, (uint64_t)n_slots);
   if (n_launches) *n_launches += 2;
   return cudaGetLastError();
 }

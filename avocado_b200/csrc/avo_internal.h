@@ -230,9 +230,9 @@ cudaError_t launch_call_blocklist(const DReads& R, const void* joined_list, int3
                                   cudaStream_t s, int* n_launches);
 cudaError_t launch_call_observe(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
                                 const DResults& out, const int32_t* rbase, const uint32_t* blen,
-                                const uint64_t* boff, uint32_t* buckets, const void* joined_list,
-                                const int32_t* d_counter, const uint8_t* compact, const uint32_t* blk0,
-                                int num_sms, cudaStream_t s, int* n_launches);
+                                const uint64_t* boff, uint32_t* buckets, size_t n_slots /* capacity of buckets */,
+                                const void* joined_list, const int32_t* d_counter, const uint8_t* compact,
+                                const uint32_t* blk0, int num_sms, cudaStream_t s, int* n_launches);
 
 // scoreAllSites reference-model rows (avo_allsites.cu).  All pointers are device scratch.
 struct AllSitesPlan {

@@ -303,3 +303,26 @@ def test_one_very_long_read_span(oracle, ctx):
         assert (g.readDepth, g.alternateReadDepth, g.genotypeQuality) == \
             (want["totalCoverage"][j], want["alleleCoverage"][j], want["genotypeQuality"][j])
         assert g.genotypeLikelihoods == list(want["genotypeLikelihoods"][j][:3])
+
+
+def test_bucket_capacity_guess_is_checked():
+    """The call stage runs with the previous call's bucket count as capacity; a larger batch than the
+    one before overflows that guess and the stage is rerun: rows equal a fresh context's."""
+    from avocado_b200 import batch as B
+    from avocado_b200.genotyping import Context
+    small = B.synth_host(B.synth_params(seed=3, n_reads_total=2000, contig_len=8000))
+    big = B.synth_host(B.synth_params(seed=4, n_reads_total=60000, contig_len=150000))
+    a, b = Context(0), Context(0)
+    try:
+        a.discover_and_call_packed(small, phred=25, min_obs=5)
+        got = [a.discover_and_call_packed(big, phred=25, min_obs=5) for _ in range(2)]   # rerun, then a good guess
+        a.discover_and_call_packed(small, phred=25, min_obs=5)                           # guess far too large
+        got.append(a.discover_and_call_packed(big, phred=25, min_obs=5))
+        want_s, want_c = b.discover_and_call_packed(big, phred=25, min_obs=5)
+    finally:
+        a.close(); b.close()
+    assert want_s.n > 100
+    for s, c in got:
+        assert np.array_equal(s.start, want_s.start)
+        for k in want_c:
+            assert np.array_equal(np.asarray(c[k]), np.asarray(want_c[k]), equal_nan=True), k

@@ -73,7 +73,7 @@ __device__ __forceinline__ void set_bits(uint32_t* __restrict__ bm, int64_t lo, 
 // joined list (in read order) + coverage bitmap of the positions that may receive a row
 __global__ void k_as_scatter(DReads R, DSites S, DIndex X, const int32_t* __restrict__ flag,
                              const int32_t* __restrict__ jpos, JoinedRead* __restrict__ jr,
-                             uint32_t* __restrict__ cover, int64_t p0, int64_t nbits) {
+                             int2* __restrict__ jcoord, uint32_t* __restrict__ cover, int64_t p0, int64_t nbits) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= R.n || !flag[r]) return;
   int32_t a, b;
@@ -81,6 +81,7 @@ __global__ void k_as_scatter(DReads R, DSites S, DIndex X, const int32_t* __rest
   JoinedRead j; j.r = (int32_t)r; j.a = a; j.b = b;
   jr[jpos[r]] = j;
   const MetaA ma = load_meta_a(R.meta, r);
+  jcoord[jpos[r]] = make_int2(ma.start, ma.end);     // dense (start, end) of the joined reads
   // observations are keyed at [start - 1, end): an insertion before the first aligned base is
   // anchored one position to the left of the read
   const int64_t lo = max((int64_t)ma.start - 1 - p0, (int64_t)0), hi = min((int64_t)ma.end - p0, nbits);
@@ -104,25 +105,22 @@ __global__ void k_as_window_counts(const uint32_t* __restrict__ cover, int32_t n
   counts[w] = c;
 }
 
-// jidx[k] = first joined read whose start is >= win0 + k * IDX_G   (k = 0..nb; jidx[nb] = n_joined)
-__global__ void k_as_jidx(DReads R, const JoinedRead* __restrict__ jr, int32_t n_joined, DIndex X,
-                          int32_t* __restrict__ jidx) {
-  const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k > X.nb) return;
-  if (k == X.nb) { jidx[k] = n_joined; return; }
-  const int64_t key = (int64_t)X.win0 + (int64_t)k * IDX_G;
-  int32_t lo = 0, hi = n_joined;
-  while (lo < hi) {
-    const int32_t mid = lo + ((hi - lo) >> 1);
-    if ((int64_t)meta_start(R.meta, jr[mid].r) < key) lo = mid + 1; else hi = mid;
-  }
-  jidx[k] = lo;
+// jfine[k] = first joined read whose start is >= p0 + 32 k   (k = 0..n_fine; jfine[n_fine] = n_joined).
+// The joined list is in read order = sorted by start: read j fills the entries between its
+// predecessor's start and its own.
+__global__ void k_as_jfine(const int2* __restrict__ jcoord, int32_t n_joined, int64_t p0, int64_t n_fine,
+                           int32_t* __restrict__ jfine) {
+  const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > n_joined) return;
+  const int64_t b_prev = (j == 0) ? -1 : min(((int64_t)jcoord[j - 1].x - p0) >> 5, n_fine);
+  const int64_t b_cur = (j == n_joined) ? n_fine : min(((int64_t)jcoord[j].x - p0) >> 5, n_fine);
+  for (int64_t b = b_prev + 1; b <= b_cur; ++b) jfine[b] = j;
 }
 
 template <int NS>
 __global__ void __launch_bounds__(AS_THREADS)
 k_as_tiles(DReads R, DSites S, DCnv C, DCallParams P, DResults O, int32_t* __restrict__ o_start, DIndex X,
-           const JoinedRead* __restrict__ jr, const int32_t* __restrict__ jidx,
+           const JoinedRead* __restrict__ jr, const int2* __restrict__ jcoord, const int32_t* __restrict__ jfine,
            const uint32_t* __restrict__ cover, const uint32_t* __restrict__ site_cover,
            const int32_t* __restrict__ win_base, int64_t p0, int64_t nbits, int32_t max_span) {
   const int lane = threadIdx.x & 31;
@@ -168,12 +166,15 @@ k_as_tiles(DReads R, DSites S, DCnv C, DCallParams P, DResults O, int32_t* __res
     if (!seen) { seen = 1; first_is_ref = is_ref; first_cn = cn; }
   };
 
-  const int32_t jLo = __ldg(jidx + idx_bin_floor(X, wlo - max_span - 1));
-  const int32_t jHi = __ldg(jidx + idx_bin_ceil(X, wlo + 33));
+  // joined reads that can reach the warp's positions: start in (wlo - max_span, wlo + 32]
+  const int64_t fb = (wbit - (int64_t)max_span - 1) >> 5;
+  const int32_t jLo = __ldg(jfine + (fb < 0 ? 0 : fb));
+  const int32_t jHi = __ldg(jfine + min((wbit >> 5) + 2, nbits >> 5));
   for (int32_t j = jLo; j < jHi; ++j) {
+    const int2 se = __ldg(jcoord + j);
+    if ((int64_t)se.y <= wlo || (int64_t)se.x - 1 >= wlo + 32) continue;          // warp-uniform
     const JoinedRead J = jr[j];
     const MetaA ma = load_meta_a(R.meta, J.r);
-    if ((int64_t)ma.end <= wlo || (int64_t)ma.start - 1 >= wlo + 32) continue;    // warp-uniform
     const MetaB mb = load_meta_b(R.meta, J.r);
     const bool fwd = !(mb.flags & AVO_READ_NEGATIVE_STRAND);
     int32_t pos = ma.start;
@@ -239,7 +240,7 @@ cudaError_t launch_allsites_plan(const DReads& R, const DSites& S, const DIndex&
   e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, A.flag, A.jpos, (int)(R.n + 1), s);
   if (e != cudaSuccess) return e;
   if (R.n > 0)
-    k_as_scatter<<<gr, 256, 0, s>>>(R, S, X, A.flag, A.jpos, (JoinedRead*)A.jr, A.cover, A.p0, A.nbits);
+    k_as_scatter<<<gr, 256, 0, s>>>(R, S, X, A.flag, A.jpos, (JoinedRead*)A.jr, A.jcoord, A.cover, A.p0, A.nbits);
   if (S.c_hi > S.c_lo)
     k_as_site_cover<<<(S.c_hi - S.c_lo + 255) / 256, 256, 0, s>>>(S, A.site_cover, A.p0, A.nbits);
   if ((e = cudaMemsetAsync(A.win_count + A.n_win, 0, 4, s)) != cudaSuccess) return e;
@@ -254,13 +255,13 @@ cudaError_t launch_allsites_tiles(const DReads& R, const DSites& S, const DCnv& 
                                   const DResults& O, int32_t* o_start, const DIndex& X,
                                   const AllSitesPlan& A, int32_t n_joined, int32_t max_span,
                                   cudaStream_t s, int* n_launches) {
-  k_as_jidx<<<(X.nb + 1 + 255) / 256, 256, 0, s>>>(R, (const JoinedRead*)A.jr, n_joined, X, A.jidx);
+  k_as_jfine<<<(n_joined + 1 + 255) / 256, 256, 0, s>>>(A.jcoord, n_joined, A.p0, A.nbits >> 5, A.jfine);
   const unsigned grid = (unsigned)((A.nbits + AS_THREADS - 1) / AS_THREADS);
   if (P.ns <= 3)
-    k_as_tiles<3><<<grid, AS_THREADS, 0, s>>>(R, S, C, P, O, o_start, X, (const JoinedRead*)A.jr, A.jidx,
+    k_as_tiles<3><<<grid, AS_THREADS, 0, s>>>(R, S, C, P, O, o_start, X, (const JoinedRead*)A.jr, A.jcoord, A.jfine,
                                               A.cover, A.site_cover, A.win_base, A.p0, A.nbits, max_span);
   else
-    k_as_tiles<NSMAX><<<grid, AS_THREADS, 0, s>>>(R, S, C, P, O, o_start, X, (const JoinedRead*)A.jr, A.jidx,
+    k_as_tiles<NSMAX><<<grid, AS_THREADS, 0, s>>>(R, S, C, P, O, o_start, X, (const JoinedRead*)A.jr, A.jcoord, A.jfine,
                                                   A.cover, A.site_cover, A.win_base, A.p0, A.nbits, max_span);
   if (n_launches) *n_launches += 2;
   return cudaGetLastError();

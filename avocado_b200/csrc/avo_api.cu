@@ -30,7 +30,7 @@ enum Slot {
   SL_L_POS, SL_L_LENS, SL_L_NIBS, SL_L_SRC, SL_L_BLK, SL_L_HASH,
   SL_C_RBASE, SL_C_BLEN, SL_C_BOFF, SL_C_BUCKETS,
   SL_G_NBLK, SL_G_SLOT, SL_G_CLO, SL_G_IDX, SL_G_BLK0, SL_G_COMPACT,
-  SL_AS_FLAG, SL_AS_JPOS, SL_AS_JR, SL_AS_JIDX, SL_AS_COVER, SL_AS_SCOVER, SL_AS_WCOUNT, SL_AS_WBASE,
+  SL_AS_FLAG, SL_AS_JPOS, SL_AS_JR, SL_AS_JIDX, SL_AS_JCOORD, SL_AS_COVER, SL_AS_SCOVER, SL_AS_WCOUNT, SL_AS_WBASE,
   SL_AS_RES, SL_AS_START,
   SL_F_IN, SL_F_OUT,
   SL_T_START, SL_T_END, SL_T_MAPQ, SL_T_FLAGS, SL_T_CIGAR, SL_T_CIGAR_OFF, SL_T_MD, SL_T_MD_OFF, SL_T_SEQ,
@@ -716,7 +716,8 @@ int allsites_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const
   CKS(get_buf(ctx, SL_AS_FLAG, (size_t)(R.n + 1) * 4, &q)); A.flag = (int32_t*)q;
   CKS(get_buf(ctx, SL_AS_JPOS, (size_t)(R.n + 1) * 4, &q)); A.jpos = (int32_t*)q;
   CKS(get_buf(ctx, SL_AS_JR, (size_t)R.n * 12, &q)); A.jr = q;
-  CKS(get_buf(ctx, SL_AS_JIDX, (size_t)(X.nb + 1) * 4, &q)); A.jidx = (int32_t*)q;
+  CKS(get_buf(ctx, SL_AS_JIDX, (size_t)(A.nbits / 32 + 1) * 4, &q)); A.jfine = (int32_t*)q;
+  CKS(get_buf(ctx, SL_AS_JCOORD, (size_t)R.n * 8, &q)); A.jcoord = (int2*)q;
   CKS(get_buf(ctx, SL_AS_COVER, (size_t)A.nbits / 8, &q)); A.cover = (uint32_t*)q;
   CKS(get_buf(ctx, SL_AS_SCOVER, (size_t)A.nbits / 8, &q)); A.site_cover = (uint32_t*)q;
   CKS(get_buf(ctx, SL_AS_WCOUNT, (size_t)(A.n_win + 1) * 4, &q)); A.win_count = (int32_t*)q;

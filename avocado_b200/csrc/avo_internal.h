@@ -242,7 +242,8 @@ struct AllSitesPlan {
   int32_t* flag;       // [n_reads + 1] joined flag per read
   int32_t* jpos;       // [n_reads + 1] exclusive scan of flag
   void* jr;            // [n_joined] (read, a, b)
-  int32_t* jidx;       // [nb + 1] coarse index into jr
+  int2* jcoord;        // [n_joined] (start, end) of the joined reads
+  int32_t* jfine;      // [nbits / 32 + 1] first joined read starting at or after p0 + 32 k
   uint32_t* cover;     // positions that may receive a row
   uint32_t* site_cover;// positions covered by a variant site
   int32_t* win_count;  // [n_win + 1]

@@ -131,6 +131,11 @@ bool extract_ops(const char* cig, size_t ncig, bool has_cigar, const char* md, s
   size_t cur = 0;       // first event at or after the current alignment offset
   uint64_t idx = 0;
   uint32_t need = 0;    // read bases consumed so far == index of the next read base
+  // The read base stored next to a mismatch's reference base is discovery's alternate allele, and
+  // discovery indexes the read its own way (DiscoverVariants.scala:139-172, 189-193): soft clips
+  // count before the first aligned operator and are ignored after it.
+  uint64_t didx = 0;
+  bool aligned_seen = false;
   auto push = [&](uint32_t len, uint32_t code) { sc.ops.push_back((len << 4) | code); };
   auto read_nib = [&](uint64_t ri) -> uint8_t {
     return (int64_t)ri < lseq ? NIB.t[(unsigned char)seq[ri]] : (uint8_t)15;
@@ -153,32 +158,32 @@ bool extract_ops(const char* cig, size_t ncig, bool has_cigar, const char* md, s
           if (k > pos) push((uint32_t)(k - pos), AVO_OP_MATCH);
           uint32_t run = 0;
           while (cur < nev && !ev[cur].del && ev[cur].off == k + run && k + run < hi) {
-            sc.refb.push_back((uint8_t)((NIB.t[(unsigned char)ev[cur].base] << 4) | read_nib(need + (k - idx) + run)));
+            sc.refb.push_back((uint8_t)((NIB.t[(unsigned char)ev[cur].base] << 4) | read_nib(didx + (k - idx) + run)));
             ++run; ++cur;
           }
           push(run, AVO_OP_MISMATCH);
           pos = k + run;
         }
         if (pos < hi) push((uint32_t)(hi - pos), AVO_OP_MATCH);
-        idx += e.len; need += e.len;
+        idx += e.len; need += e.len; didx += e.len; aligned_seen = true;
         break;
       }
       case '=':
         push(e.len, AVO_OP_MATCH);
-        idx += e.len; need += e.len;
+        idx += e.len; need += e.len; didx += e.len; aligned_seen = true;
         break;
       case 'X':
         for (uint32_t k = 0; k < e.len; ++k) {
           const MdEvent* m = at(idx + k);
           if (!m || m->del) return false;
-          sc.refb.push_back((uint8_t)((NIB.t[(unsigned char)m->base] << 4) | read_nib((uint64_t)need + k)));
+          sc.refb.push_back((uint8_t)((NIB.t[(unsigned char)m->base] << 4) | read_nib(didx + k)));
         }
         push(e.len, AVO_OP_MISMATCH);
-        idx += e.len; need += e.len;
+        idx += e.len; need += e.len; didx += e.len; aligned_seen = true;
         break;
       case 'I':
         push(e.len, AVO_OP_INS);
-        need += e.len;
+        need += e.len; didx += e.len;
         break;
       case 'D':
         for (uint32_t k = 0; k < e.len; ++k) {
@@ -193,6 +198,7 @@ bool extract_ops(const char* cig, size_t ncig, bool has_cigar, const char* md, s
       case 'S':
         if (e.len) push(e.len, AVO_OP_SOFTCLIP);
         need += e.len;
+        if (!aligned_seen) didx += e.len;
         break;
       case 'H':
         if (e.len) push(e.len, AVO_OP_HARDCLIP);

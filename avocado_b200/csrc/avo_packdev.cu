@@ -122,6 +122,10 @@ __device__ Extracted extract_ops(const char* cig, int ncig, bool has_cigar, cons
   ev.begin(md, nmd);
   uint64_t idx = 0;
   uint32_t need = 0, no = 0, nf = 0;
+  // discovery's own read index (DiscoverVariants.scala:139-172, 189-193): soft clips count before
+  // the first aligned operator and are ignored after it; it picks the read base stored with a mismatch
+  uint64_t didx = 0;
+  bool aligned_seen = false;
   auto push = [&](uint32_t len, uint32_t code) { if (WRITE) ops[no] = (len << 4) | code; ++no; };
   auto read_nib = [&](uint64_t ri) -> uint32_t { return (int64_t)ri < lseq ? nib_of((unsigned char)seq[ri]) : 15u; };
   int i = 0;
@@ -141,7 +145,7 @@ __device__ Extracted extract_ops(const char* cig, int ncig, bool has_cigar, cons
           if (k > pos) push((uint32_t)(k - pos), AVO_OP_MATCH);
           uint32_t run = 0;
           while (ev.valid() && !ev.del && ev.ref == k + run && k + run < hi) {
-            if (WRITE) refb[nf] = (uint8_t)((nib_of((unsigned char)ev.base()) << 4) | read_nib(need + (k - idx) + run));
+            if (WRITE) refb[nf] = (uint8_t)((nib_of((unsigned char)ev.base()) << 4) | read_nib(didx + (k - idx) + run));
             ++nf; ++run;
             ev.next();
           }
@@ -149,26 +153,26 @@ __device__ Extracted extract_ops(const char* cig, int ncig, bool has_cigar, cons
           pos = k + run;
         }
         if (pos < hi) push((uint32_t)(hi - pos), AVO_OP_MATCH);
-        idx += len; need += len;
+        idx += len; need += len; didx += len; aligned_seen = true;
         break;
       }
       case '=':
         push(len, AVO_OP_MATCH);
-        idx += len; need += len;
+        idx += len; need += len; didx += len; aligned_seen = true;
         break;
       case 'X':
         for (uint32_t k = 0; k < len; ++k) {
           while (ev.valid() && ev.ref < idx + k) ev.next();
           if (!ev.valid() || ev.ref != idx + k || ev.del) return x;
-          if (WRITE) refb[nf] = (uint8_t)((nib_of((unsigned char)ev.base()) << 4) | read_nib((uint64_t)need + k));
+          if (WRITE) refb[nf] = (uint8_t)((nib_of((unsigned char)ev.base()) << 4) | read_nib(didx + k));
           ++nf;
         }
         push(len, AVO_OP_MISMATCH);
-        idx += len; need += len;
+        idx += len; need += len; didx += len; aligned_seen = true;
         break;
       case 'I':
         push(len, AVO_OP_INS);
-        need += len;
+        need += len; didx += len;
         break;
       case 'D':
         for (uint32_t k = 0; k < len; ++k) {
@@ -186,6 +190,7 @@ __device__ Extracted extract_ops(const char* cig, int ncig, bool has_cigar, cons
       case 'S':
         if (len) push(len, AVO_OP_SOFTCLIP);
         need += len;
+        if (!aligned_seen) didx += len;
         break;
       case 'H':
         if (len) push(len, AVO_OP_HARDCLIP);

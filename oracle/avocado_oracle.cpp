@@ -1501,7 +1501,10 @@ static std::shared_ptr<ReadSet> readsFromPacked(
       r.qual.push_back((char)(pl((blk0 + k / 10) * 16 + 5 + k % 10) + 33));
     }
     uint64_t f = fo(i);   // byte index into refb
-    uint64_t ridx = 0;    // read bases consumed
+    // read index the way DiscoverVariants counts it (DiscoverVariants.scala:139-172, 189-193): soft
+    // clips count before the first aligned operator and are ignored after it
+    uint64_t ridx = 0;
+    bool aligned = false;
     long run = 0;
     std::string md;
     bool any = false;
@@ -1509,22 +1512,24 @@ static std::shared_ptr<ReadSet> readsFromPacked(
       const uint32_t w = op(k), len = w >> 4, code = w & 15;
       any = true;
       r.cigar += std::to_string(len) + "=XIDSH"[code];
-      if (code == 0) { run += len; ridx += len; }
+      if (code == 0) { run += len; ridx += len; aligned = true; }
       else if (code == 1) {
         for (uint32_t j = 0; j < len; ++j) {
           const int pr = fb(f++);
-          // the low nibble repeats the read base: a packer / generator consistency check
-          if ((pr & 15) != baseAt(ridx + j))
+          // the low nibble repeats the read base discovery takes as the alternate allele: a packer /
+          // generator consistency check (a base past the end of the sequence is stored as N)
+          const int want = ridx + j < ls(i) ? baseAt(ridx + j) : 15;
+          if ((pr & 15) != want)
             throw std::runtime_error("packed batch: mismatch pair does not repeat the read base");
           md += std::to_string(run); md.push_back(NIBS[pr >> 4]); run = 0;
         }
-        ridx += len;
+        ridx += len; aligned = true;
       } else if (code == 3) {
         md += std::to_string(run) + "^";
         for (uint32_t j = 0; j < len; ++j) md.push_back(NIBS[nib(fb, 2 * f + j)]);
         f += (len + 1) / 2;
         run = 0;
-      } else if (code == 2 || code == 4) ridx += len;
+      } else if (code == 2 || (code == 4 && !aligned)) ridx += len;
     }
     md += std::to_string(run);
     r.hasCigar = any; r.hasMd = any;

@@ -213,8 +213,12 @@ def fuzz_records(seed, n):
         slen = rlen if rng.random() < 0.9 else max(0, rlen + rng.randint(-3, 3))
         qlen = slen if rng.random() < 0.9 else max(0, slen + rng.randint(-3, 3))
         start = 100 + i * 3
+        # AlignmentRecord.end follows from the CIGAR (ADAM derives it); unparsable CIGARs keep a guess
+        import re
+        span = sum(int(n) for n, op in re.findall(r"(\d+)([MIDNSHP=X])", cigar) if op in "M=XDN") \
+            if re.fullmatch(r"(\d+[MIDNSHP=X])+", cigar) else rlen
         recs.append(AlignmentRecord(
-            readMapped=rng.random() > 0.03, contigName="c", start=start, end=start + rlen,
+            readMapped=rng.random() > 0.03, contigName="c", start=start, end=start + span,
             cigar=None if rng.random() < 0.03 else cigar,
             mismatchingPositions=None if rng.random() < 0.03 else mdtag,
             sequence="".join(rng.choice("ACGTNacgtRY=") if rng.random() < 0.05 else rng.choice("ACGT") for _ in range(slen)),

@@ -326,3 +326,32 @@ def test_bucket_capacity_guess_is_checked():
         assert np.array_equal(s.start, want_s.start)
         for k in want_c:
             assert np.array_equal(np.asarray(c[k]), np.asarray(want_c[k]), equal_nan=True), k
+
+
+@pytest.mark.parametrize("seed,min_obs", [(1, 1), (2, 1), (3, 0)])
+def test_messy_reads_against_the_oracle(oracle, ctx, seed, min_obs):
+    """Short reads with every operator mix the packer accepts (insertions at read ends, deletions next
+    to insertions, clips, X runs, N / IUPAC bases, mapq 0 and 255, reads whose strings are too short):
+    dense, overlapping candidate sites; discovery, variant calls and gVCF rows equal the oracle's."""
+    from avocado_b200 import batch as B
+    from helpers import fuzz_records
+    recs = [r for r in fuzz_records(100 + seed, 5000) if r.readMapped]
+    batch = B.pack_reads(recs, sort=False)
+    assert (batch.meta["n_ops"] == 0).any() and (batch.meta["flags"] & 2).any()
+    rs = oracle_reads_from_batch(oracle, batch)
+    want_v = oracle.discover(rs, 10, min_obs)
+    sites = ctx.discover_packed(batch, phred=10, min_obs=min_obs)
+    got = [(v.start, v.referenceAllele, v.alternateAllele) for v in sites.to_variants(["ctg"])]
+    assert sorted(got) == sorted((s, r, a) for _, s, _, r, a, _ in want_v)
+    assert len(got) > 50
+    variants = [(c, s, e, r, a) for c, s, e, r, a, _ in want_v]
+    want = oracle.call(rs, variants, 2, [], False, 93, 93, 1)
+    cols = ctx.call_packed(batch, sites)
+    keys = [("ctg", s, r, a) for s, r, a in got]
+    st = compare_call(keys, cols, want)
+    assert st["sites"] > 30
+    want_all = oracle.call(rs, variants, 2, [], True, 93, 93, 1)
+    c2, rstart, rcols = ctx.call_all_sites_packed(batch, sites)
+    keys2 = keys + [("ctg", int(s), "N", None) for s in rstart]
+    merged = {k: np.concatenate([np.asarray(c2[k]), np.asarray(rcols[k])]) for k in c2}
+    compare_call(keys2, merged, want_all)

@@ -355,3 +355,11 @@ def test_messy_reads_against_the_oracle(oracle, ctx, seed, min_obs):
     keys2 = keys + [("ctg", int(s), "N", None) for s in rstart]
     merged = {k: np.concatenate([np.asarray(c2[k]), np.asarray(rcols[k])]) for k in c2}
     compare_call(keys2, merged, want_all)
+    # another ploidy, copy-number variants across the batch, tighter quality caps
+    cnvs = [("ctg", 2000, 6000, 4), ("ctg", 9000, 9100, 1), ("ctg", 12000, 20000, 2)]
+    want3 = oracle.call(rs, variants, 3, list(cnvs), True, 40, 50, 1)
+    c3, rstart3, rcols3 = ctx.call_all_sites_packed(batch, sites, ploidy=3, cnvs=cnvs, contig_rank={"ctg": 0},
+                                                    max_quality=40, max_mapq=50)
+    keys3 = keys + [("ctg", int(s), "N", None) for s in rstart3]
+    merged3 = {k: np.concatenate([np.asarray(c3[k]), np.asarray(rcols3[k])]) for k in c3}
+    compare_call(keys3, merged3, want3)

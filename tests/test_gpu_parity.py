@@ -352,7 +352,9 @@ def test_host_gathered_payload_gives_the_same_rows(ctx, threads):
         except FileNotFoundError:
             continue
         batches.append(_pinned_copy(B, B.pack_reads(recs)))
-    assert len(batches) >= 2
+    from helpers import fuzz_records
+    batches.append(_pinned_copy(B, B.pack_reads([r for r in fuzz_records(55, 6000) if r.readMapped], sort=False)))
+    assert len(batches) >= 3
     for batch in batches:
         rows = []
         for mode in (0, 2):

@@ -7,7 +7,7 @@
 // "N", no alternate), end = start + 1 (DiscoveredVariant.scala:59-61); the observation is scored
 // as REF when it is a sequence match and as a plain (ALT-flagged) observation otherwise, and
 // the rows of one position are summed like any other site (BG:475-500).  Observations that do
-// overlap a variant go to that variant exactly as in variant-only mode (k_call_tiles).
+// overlap a variant go to that variant exactly as in variant-only mode (avo_call.cu).
 //
 // Work layout: one thread per reference position (a warp owns 32 consecutive positions); the
 // warp walks the joined reads that overlap its positions IN READ ORDER, every lane keeping the

@@ -369,3 +369,18 @@ def test_host_gathered_payload_gives_the_same_rows(ctx, threads):
         assert rows[0][0].n == rows[1][0].n > 0
         for k in rows[0][1]:
             assert np.array_equal(np.asarray(rows[0][1][k]), np.asarray(rows[1][1][k]), equal_nan=True), k
+
+
+def test_c_example_runs_through_the_c_abi(tmp_path):
+    """examples/discover_and_call.c: the path from plain C, linked against the shared library."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "dac")
+    lib = os.path.join(root, "avocado_b200")
+    subprocess.check_call(["gcc", "-O2", "-std=c11", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "examples", "discover_and_call.c"), "-o", exe, "-L", lib,
+                           "-lavocado_b200", "-Wl,-rpath," + lib])
+    r = subprocess.run([exe, "30000"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "30000 reads ->" in r.stdout and "GQ" in r.stdout

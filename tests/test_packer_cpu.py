@@ -225,3 +225,13 @@ def test_wire8_columns_hold_the_same_information():
     unsorted = B.synth_host(p)
     unsorted.meta["start"][7] -= 500
     assert not unsorted.with_wire8()
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI: both headers and the C example compile as C11 (no C++, no torch types)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    obj = str(tmp_path / "example.o")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-c",
+                           os.path.join(root, "examples", "discover_and_call.c"), "-o", obj])
+    assert os.path.getsize(obj) > 0

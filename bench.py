@@ -56,7 +56,7 @@ def parse_args():
                          "(0 = min(8, host threads / (2 x ranks)))")
     ap.add_argument("--e2e-payload", type=int, default=-1, help="avo_params.host_payload of the e2e leg: 0 in place, "
                     "1 copy, 2 in place for discovery + host-gathered blocks for the call stage "
-                    "(-1 = 2 when the rank has 12 or more host threads to itself, else 0)")
+                    "(-1 = 2 when the rank has 16 or more host threads to itself, else 0)")
     ap.add_argument("--gather-threads", type=int, default=2,
                     help="avo_params.gather_threads: host threads gathering payload blocks per call")
     ap.add_argument("--no-text", action="store_true", help="skip the from-text leg of e2e")
@@ -238,7 +238,7 @@ def main():
     rank, world, local = dist_env()
     cpus_per_rank = max(1, (os.cpu_count() or 8) // world)
     if args.e2e_payload < 0:        # gathering on the host needs cores; reading in place needs none
-        args.e2e_payload = 2 if cpus_per_rank >= 12 else 0
+        args.e2e_payload = 2 if cpus_per_rank >= 16 else 0
     import numpy as np
     import torch
     from avocado_b200 import batch as B

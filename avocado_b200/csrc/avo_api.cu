@@ -673,7 +673,7 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
       }
     }
     CKS(get_buf(ctx, SL_C_BUCKETS, n_slots * 4, &d_buckets));
-    CK(launch_call_join(R, S, X, (uint32_t*)d_buckets, n_slots, d_jlist, small + 8, ctx->num_sms, ctx->stream, &nl));
+    CK(launch_call_join(R, S, X, hs.max_span, (uint32_t*)d_buckets, n_slots, d_jlist, small + 8, ctx->num_sms, ctx->stream, &nl));
     const uint8_t* d_compact = nullptr;
     const uint32_t* d_blk0 = nullptr;
     if (ctx->gather_src && work) CKS(gather_payload(ctx, R, S, d_jlist, small + 8, &d_compact, &d_blk0, &nl));

@@ -135,12 +135,12 @@ struct JoinedRead { int32_t r, a, b; };
 // path of every 512 reads.
 constexpr int JOIN_THREADS = 256;
 constexpr int JOIN_WARPS = JOIN_THREADS / 32;
-constexpr int JOIN_UNROLL = 2;
 constexpr int JOIN_FLUSH = 96;
-constexpr int JOIN_CAP = JOIN_FLUSH + 32 * JOIN_UNROLL;
+constexpr int JOIN_CAP = JOIN_FLUSH + 32;
 
 __global__ void __launch_bounds__(JOIN_THREADS)
-k_call_join(DReads R, DSites S, DIndex X, JoinedRead* __restrict__ list, int32_t* __restrict__ n_list) {
+k_call_join(DReads R, DSites S, DIndex X, int32_t max_span, JoinedRead* __restrict__ list,
+            int32_t* __restrict__ n_list) {
   __shared__ JoinedRead stage[JOIN_WARPS][JOIN_CAP];
   const int lane = threadIdx.x & 31;
   JoinedRead* st = stage[threadIdx.x >> 5];
@@ -154,42 +154,63 @@ k_call_join(DReads R, DSites S, DIndex X, JoinedRead* __restrict__ list, int32_t
     cnt = 0;
     __syncwarp();
   };
-  const int64_t n_blocks = (R.n + 31) / 32;
-  const int64_t stride = (int64_t)gridDim.x * JOIN_WARPS * JOIN_UNROLL;
-  for (int64_t blk = ((int64_t)blockIdx.x * JOIN_WARPS + (threadIdx.x >> 5)) * JOIN_UNROLL; blk < n_blocks;
-       blk += stride) {
-    int2 se[JOIN_UNROLL];
-    bool in[JOIN_UNROLL];
-#pragma unroll
-    for (int u = 0; u < JOIN_UNROLL; ++u) {
-      const int64_t r = (blk + u) * 32 + lane;
-      in[u] = r < R.n;
-      se[u] = in[u] ? __ldg(R.coords + r) : make_int2(0, 0);          // start, end
+  // sites that start in the index bins [lo, hi] touches, or an earlier site reaching past lo
+  auto may_join = [&](int32_t lo, int64_t hi, int32_t& hLo, int32_t& hHi) -> bool {
+    hLo = (lo <= X.win0) ? S.c_lo : __ldg(X.sidx + idx_bin_floor(X, lo));
+    const int64_t d = hi - X.win0;
+    const int64_t k = d < 0 ? 0 : d / IDX_G + 1;
+    hHi = (k >= X.nb) ? S.c_hi : __ldg(X.sidx + (int32_t)k);
+    return hLo < hHi || (hLo > S.c_lo && __ldg(S.pme + hLo - 1) > lo);
+  };
+  const int64_t n_blocks = (R.n + 31) / 32;               // blocks of 32 consecutive reads
+  const int64_t n_super = (n_blocks + 31) / 32;           // 32 blocks per warp iteration
+  const int64_t stride = (int64_t)gridDim.x * JOIN_WARPS;
+  for (int64_t sb = (int64_t)blockIdx.x * JOIN_WARPS + (threadIdx.x >> 5); sb < n_super; sb += stride) {
+    // ---- one LANE per block: the reads of a block are neighbours (sorted by start), so the block
+    // is tested like one long read [first start, last start + max_span): 4 of 5 blocks have no site
+    // in reach at 1.1 sites / kb and are done after two loads
+    bool may = false;
+    {
+      const int64_t blk = sb * 32 + lane;
+      if (blk < n_blocks) {
+        const int64_t r0 = blk * 32, r1 = min(r0 + 31, R.n - 1);
+        int32_t hLo, hHi;
+        const int32_t bmin = __ldg(R.coords + r0).x;
+        const int64_t bmax = (int64_t)__ldg(R.coords + r1).x + max_span;     // >= every end of the block
+        may = may_join(bmin, bmax, hLo, hHi);
+        if (may && hHi - hLo <= 8 && !(hLo > S.c_lo && __ldg(S.pme + hLo - 1) > bmin)) {
+          // the bins are 256 bp wide: look at the few sites they hold
+          may = false;
+          for (int32_t k = hLo; k < hHi; ++k)
+            may = may || ((int64_t)__ldg(S.start + k) < bmax && __ldg(S.end + k) > bmin);
+        }
+      }
     }
-#pragma unroll
-    for (int u = 0; u < JOIN_UNROLL; ++u) {
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, may);
+    // ---- the other blocks, one lane per read
+    while (todo) {
+      const int bi = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int64_t r = (sb * 32 + bi) * 32 + lane;
       int32_t a = 0, b = 0;
       bool joined = false;
-      if (in[u]) {
-        // sites that start in the index bins the read touches, or an earlier site reaching past its start
-        const int32_t hLo = (se[u].x <= X.win0) ? S.c_lo : __ldg(X.sidx + idx_bin_floor(X, se[u].x));
-        const int64_t d = (int64_t)se[u].y - X.win0;
-        const int64_t k = d < 0 ? 0 : d / IDX_G + 1;
-        const int32_t hHi = (k >= X.nb) ? S.c_hi : __ldg(X.sidx + (int32_t)k);
-        if (hLo < hHi || (hLo > S.c_lo && __ldg(S.pme + hLo - 1) > se[u].x)) {
-          forest_get(S, R.contig, se[u].x, se[u].y, hLo, hHi, a, b);
+      if (r < R.n) {
+        const int2 se = __ldg(R.coords + r);                                // start, end
+        int32_t hLo, hHi;
+        if (may_join(se.x, (int64_t)se.y, hLo, hHi)) {
+          forest_get(S, R.contig, se.x, se.y, hLo, hHi, a, b);
           joined = a < b;                                   // no overlapping variant: read dropped
         }
       }
       const unsigned m = __ballot_sync(0xFFFFFFFFu, joined);
       if (joined) {
-        JoinedRead j; j.r = (int32_t)((blk + u) * 32 + lane); j.a = a; j.b = b;
+        JoinedRead j; j.r = (int32_t)r; j.a = a; j.b = b;
         st[cnt + __popc(m & lt)] = j;
       }
       cnt += __popc(m);
+      __syncwarp();
+      if (cnt >= JOIN_FLUSH) flush();
     }
-    __syncwarp();
-    if (cnt >= JOIN_FLUSH) flush();
   }
   if (cnt > 0) flush();
 }
@@ -385,8 +406,9 @@ cudaError_t launch_call_buckets(const DReads& R, const DSites& S, const DIndex& 
   return cudaGetLastError();
 }
 
-cudaError_t launch_call_join(const DReads& R, const DSites& S, const DIndex& X, uint32_t* buckets, size_t n_slots,
-                             void* joined_list, int32_t* d_counter, int num_sms, cudaStream_t s, int* n_launches) {
+cudaError_t launch_call_join(const DReads& R, const DSites& S, const DIndex& X, int32_t max_span, uint32_t* buckets,
+                             size_t n_slots, void* joined_list, int32_t* d_counter, int num_sms, cudaStream_t s,
+                             int* n_launches) {
   cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int32_t), s);
   if (e != cudaSuccess) return e;
   if (R.n == 0 || S.c_hi <= S.c_lo) return cudaSuccess;
@@ -397,9 +419,11 @@ cudaError_t launch_call_join(const DReads& R, const DSites& S, const DIndex& X, 
   int bps = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_call_join, JOIN_THREADS, 0);
   if (e != cudaSuccess) return e;
-  const int64_t want = ((R.n + 31) / 32 + JOIN_WARPS * JOIN_UNROLL - 1) / (JOIN_WARPS * JOIN_UNROLL);
-  const int grid = (int)min(want, (int64_t)num_sms * max(1, bps));
-  k_call_join<<<grid, JOIN_THREADS, 0, s>>>(R, S, X, (JoinedRead*)joined_list, d_counter);
+  // a warp takes 1024 reads per iteration; at least four iterations per warp keep the tail short
+  const int64_t n_super = ((R.n + 31) / 32 + 31) / 32;
+  const int64_t want = (n_super + 4 * JOIN_WARPS - 1) / (4 * JOIN_WARPS);
+  const int grid = (int)max((int64_t)1, min(want, (int64_t)num_sms * max(1, bps)));
+  k_call_join<<<grid, JOIN_THREADS, 0, s>>>(R, S, X, max_span, (JoinedRead*)joined_list, d_counter);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }

@@ -218,9 +218,9 @@ cudaError_t launch_call_buckets(const DReads& R, const DSites& S, const DIndex& 
                                 uint32_t* blen, uint64_t* boff, void* d_temp, size_t temp_bytes,
                                 cudaStream_t s, int* n_launches);
 // join -> (optional host gather of the payload blocks the joined reads need) -> observe + reduce
-cudaError_t launch_call_join(const DReads& R, const DSites& S, const DIndex& X, uint32_t* buckets, size_t n_slots,
-                             void* joined_list /* 12 B x n_reads */, int32_t* d_counter, int num_sms,
-                             cudaStream_t s, int* n_launches);
+cudaError_t launch_call_join(const DReads& R, const DSites& S, const DIndex& X, int32_t max_span /* >= every end - start */,
+                             uint32_t* buckets, size_t n_slots, void* joined_list /* 12 B x n_reads */,
+                             int32_t* d_counter, int num_sms, cudaStream_t s, int* n_launches);
 size_t call_gather_temp_bytes(int32_t n_joined);
 cudaError_t launch_call_gather_plan(const DReads& R, const DSites& S, const void* joined_list, int32_t n_joined,
                                     uint32_t* nblk, uint32_t* slot, uint32_t* clo, void* d_temp, size_t temp_bytes,

@@ -27,7 +27,10 @@
 
 namespace avo {
 
-constexpr int OBS_THREADS = 256;
+#ifndef AVO_OBS_THREADS
+#define AVO_OBS_THREADS 256
+#endif
+constexpr int OBS_THREADS = AVO_OBS_THREADS;
 constexpr int MAX_LOCAL_SITES = 32;  // per-read category cache
 #ifndef AVO_CALL_MINB
 #define AVO_CALL_MINB 6

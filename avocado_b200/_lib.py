@@ -39,7 +39,7 @@ class ReadBatchStruct(C.Structure):
                 ("stats_min_start", C.c_int32), ("stats_max_end", C.c_int32),
                 ("stats_max_span", C.c_int32), ("stats_valid", C.c_int32),
                 ("meta", P), ("payload", P), ("ops", P), ("refb", P), ("wire_meta", P), ("wire_ops", P),
-                ("wire8_meta", P), ("wire8_exc", P), ("n_wire8_exc", C.c_int64), ("wire8_base", C.c_int32),
+                ("wire6_meta", P), ("wire6_exc", P), ("n_wire6_exc", C.c_int64), ("wire6_base", C.c_int32),
                 ("reserved", C.c_int32)]
 
 
@@ -197,7 +197,7 @@ EXPORTED_SYMBOLS = [
     "avo_ctx_create", "avo_ctx_destroy", "avo_last_error", "avo_version", "avo_ctx_set_stream",
     "avo_get_timing", "avo_discover", "avo_call", "avo_discover_and_call",
     "avo_call_all_sites", "avo_filter_genotypes", "avo_square_off", "avo_trio_call", "avo_joint_counts", "avo_joint",
-    "avo_pack_wire", "avo_pack_wire8", "avo_pack_bounds", "avo_pack_reads", "avo_pack_reads_mt", "avo_pack_reads_device", "avo_synth_default_params",
+    "avo_pack_wire", "avo_pack_wire6", "avo_pack_bounds", "avo_pack_reads", "avo_pack_reads_mt", "avo_pack_reads_device", "avo_synth_default_params",
     "avo_synth_host", "avo_synth_device", "avo_synth_text",
 ]
 
@@ -241,7 +241,7 @@ def load():
     lib.avo_joint_counts.argtypes = [P, C.POINTER(JointInStruct), P, P]
     lib.avo_joint.argtypes = [P, C.POINTER(JointInStruct), C.POINTER(JointOutStruct)]
     lib.avo_pack_wire.argtypes = [C.POINTER(ReadBatchStruct), P, P]
-    lib.avo_pack_wire8.argtypes = [C.POINTER(ReadBatchStruct), P, P, P, C.c_int64, C.POINTER(C.c_int64),
+    lib.avo_pack_wire6.argtypes = [C.POINTER(ReadBatchStruct), P, P, P, C.c_int64, C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int32)]
     lib.avo_pack_bounds.argtypes = [C.POINTER(TextReadsStruct)] + [C.POINTER(C.c_int64)] * 4
     lib.avo_pack_reads.argtypes = [C.POINTER(TextReadsStruct), C.POINTER(PackedOutStruct)]

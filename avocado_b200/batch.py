@@ -29,10 +29,10 @@ WIRE_DTYPE = np.dtype([("start", "<i4"), ("span", "<u2"), ("l_seq", "<u2"), ("n_
                        ("mapq", "u1"), ("flags", "u1"), ("qhead", "<u4")])
 assert WIRE_DTYPE.itemsize == 16
 
-# avo_read_wire8 / avo_wire_exception: the 8-byte form (start differences; sizes implied by the operators)
-WIRE8_DTYPE = np.dtype([("dstart_flags", "<u2"), ("n_ops", "u1"), ("mapq", "u1"), ("qhead", "<u4")])
+# avo_read_wire6 / avo_wire_exception: the 6-byte form (start differences; sizes implied by the operators)
+WIRE6_DTYPE = np.dtype([("dstart_flags", "<u2"), ("n_ops", "u1"), ("mapq", "u1"), ("q0", "u1"), ("q1", "u1")])
 WIRE_EXC_DTYPE = np.dtype([("index", "<u4"), ("l_seq", "<u4"), ("end", "<i4"), ("reserved", "<u4")])
-assert WIRE8_DTYPE.itemsize == 8 and WIRE_EXC_DTYPE.itemsize == 16
+assert WIRE6_DTYPE.itemsize == 6 and WIRE_EXC_DTYPE.itemsize == 16
 
 READ_COLUMNS = [("meta", META_DTYPE), ("payload", np.uint8), ("ops", np.uint32), ("refb", np.uint8)]
 BLOCK_BASES, BLOCK_BYTES = 10, 16     # payload: 10 bases (4 bit) + their 10 qualities per 16-byte block
@@ -71,29 +71,29 @@ class ReadBatch:
     stats: Optional[tuple] = None   # (min_start, max_end, max_span): avo_batch_stats, optional
     wire_meta: Optional[np.ndarray] = None   # host batches: compact wire columns (avo_pack_wire)
     wire_ops: Optional[np.ndarray] = None
-    wire8_meta: Optional[np.ndarray] = None  # host batches: the 8-byte form (avo_pack_wire8), with wire_ops
-    wire8_exc: Optional[np.ndarray] = None
-    wire8_base: int = 0
+    wire6_meta: Optional[np.ndarray] = None  # host batches: the 6-byte form (avo_pack_wire6), with wire_ops
+    wire6_exc: Optional[np.ndarray] = None
+    wire6_base: int = 0
 
-    def with_wire8(self, alloc=None, max_exceptions=None):
-        """Adds the 8-byte wire columns (host batches): start differences, sizes implied by the
+    def with_wire6(self, alloc=None, max_exceptions=None):
+        """Adds the 6-byte wire columns (host batches): start differences, sizes implied by the
         operators, exceptions listed.  Returns False when the batch does not fit the form."""
         assert not self.on_device
         alloc = alloc or (lambda n: np.zeros(n, np.uint8))
         cap = max(16, self.n_reads // 64) if max_exceptions is None else max_exceptions
-        wm = alloc(max(self.n_reads, 1) * 8).view(WIRE8_DTYPE)
+        wm = alloc(max(self.n_reads, 1) * 6).view(WIRE6_DTYPE)
         wo = alloc(max(self.n_ops, 1) * 2).view(np.uint16)
         ex = alloc(max(cap, 1) * 16).view(WIRE_EXC_DTYPE)
         ne, base = C.c_int64(), C.c_int32()
         s = self.as_struct()
-        rc = L.load().avo_pack_wire8(C.byref(s), wm.ctypes.data, wo.ctypes.data, ex.ctypes.data, cap,
+        rc = L.load().avo_pack_wire6(C.byref(s), wm.ctypes.data, wo.ctypes.data, ex.ctypes.data, cap,
                                      C.byref(ne), C.byref(base))
         if rc == L.AVO_E_UNSUPPORTED:
             return False
         if rc != 0:
-            raise L.AvocadoError(rc, "avo_pack_wire8 failed")
-        self.wire8_meta, self.wire_ops = wm[:self.n_reads], wo[:max(self.n_ops, 1)]
-        self.wire8_exc, self.wire8_base = ex[:ne.value], base.value
+            raise L.AvocadoError(rc, "avo_pack_wire6 failed")
+        self.wire6_meta, self.wire_ops = wm[:self.n_reads], wo[:max(self.n_ops, 1)]
+        self.wire6_exc, self.wire6_base = ex[:ne.value], base.value
         return True
 
     def with_wire(self, alloc=None):
@@ -151,10 +151,10 @@ class ReadBatch:
             setattr(s, name, _ptr(getattr(self, name)))
         if self.wire_meta is not None and self.wire_ops is not None and not self.on_device:
             s.wire_meta, s.wire_ops = _ptr(self.wire_meta), _ptr(self.wire_ops)
-        if self.wire8_meta is not None and self.wire_ops is not None and not self.on_device:
-            s.wire8_meta, s.wire_ops = _ptr(self.wire8_meta), _ptr(self.wire_ops)
-            s.wire8_exc = _ptr(self.wire8_exc) if len(self.wire8_exc) else None
-            s.n_wire8_exc, s.wire8_base = len(self.wire8_exc), self.wire8_base
+        if self.wire6_meta is not None and self.wire_ops is not None and not self.on_device:
+            s.wire6_meta, s.wire_ops = _ptr(self.wire6_meta), _ptr(self.wire_ops)
+            s.wire6_exc = _ptr(self.wire6_exc) if len(self.wire6_exc) else None
+            s.n_wire6_exc, s.wire6_base = len(self.wire6_exc), self.wire6_base
         return s
 
     def nbytes(self):

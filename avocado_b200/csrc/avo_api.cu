@@ -177,11 +177,11 @@ int validate_reads(avo_ctx* ctx, const avo_read_batch* r) {
   if (r->n_blocks < 0 || r->n_blocks > (int64_t)UINT32_MAX || r->n_ops < 0 ||
       r->n_ops > (int64_t)UINT32_MAX || r->n_refb < 0 || r->n_refb > (int64_t)INT32_MAX)
     return fail(ctx, AVO_E_INVALID, "batch totals must fit 32-bit offsets; split the batch");
-  const bool wire = (r->wire_meta || r->wire8_meta) && r->wire_ops;
-  if (((r->wire_meta != nullptr) || (r->wire8_meta != nullptr)) != (r->wire_ops != nullptr) && r->n_ops > 0)
-    return fail(ctx, AVO_E_INVALID, "wire_meta / wire8_meta and wire_ops go together");
-  if (r->wire8_meta && (r->n_wire8_exc < 0 || r->n_wire8_exc > r->n_reads || (r->n_wire8_exc > 0 && !r->wire8_exc)))
-    return fail(ctx, AVO_E_INVALID, "bad wire8 exception list");
+  const bool wire = (r->wire_meta || r->wire6_meta) && r->wire_ops;
+  if (((r->wire_meta != nullptr) || (r->wire6_meta != nullptr)) != (r->wire_ops != nullptr) && r->n_ops > 0)
+    return fail(ctx, AVO_E_INVALID, "wire_meta / wire6_meta and wire_ops go together");
+  if (r->wire6_meta && (r->n_wire6_exc < 0 || r->n_wire6_exc > r->n_reads || (r->n_wire6_exc > 0 && !r->wire6_exc)))
+    return fail(ctx, AVO_E_INVALID, "bad wire6 exception list");
   if (wire && r->mem != AVO_MEM_HOST) return fail(ctx, AVO_E_INVALID, "wire columns are for host batches");
   if (r->n_reads > 0 && !r->meta && !wire) return fail(ctx, AVO_E_INVALID, "read batch has no meta column");
   if ((r->n_blocks > 0 && !r->payload) || (r->n_ops > 0 && !r->ops && !wire) ||
@@ -189,7 +189,7 @@ int validate_reads(avo_ctx* ctx, const avo_read_batch* r) {
     return fail(ctx, AVO_E_INVALID, "read batch has NULL columns");
   if (r->mem != AVO_MEM_HOST && r->mem != AVO_MEM_DEVICE) return fail(ctx, AVO_E_INVALID, "bad reads->mem");
   if (((uintptr_t)r->payload & 15u) || ((uintptr_t)r->meta & 15u) || ((uintptr_t)r->wire_meta & 15u) ||
-      ((uintptr_t)r->wire8_meta & 7u) || ((uintptr_t)r->wire8_exc & 15u))
+      ((uintptr_t)r->wire6_meta & 1u) || ((uintptr_t)r->wire6_exc & 15u))
     return fail(ctx, AVO_E_INVALID, "reads->payload and reads->meta must be 16-byte aligned");
   return AVO_OK;
 }
@@ -201,30 +201,32 @@ int upload_reads(avo_ctx* ctx, const avo_read_batch* r, bool sparse, DReads* R, 
   ctx->gather_src = nullptr;
   R->n = r->n_reads;
   R->contig = r->contig_id;
+  R->qhead_short = 0;
   {
     void* c;
     CKS(get_buf(ctx, SL_COORDS, n * sizeof(int2), &c));
     R->coords = (int2*)c;
   }
-  if (r->wire8_meta && r->wire_ops && r->mem == AVO_MEM_HOST) {
-    // 8-byte records: starts, ends, lengths and offsets are rebuilt on the device
-    const avo_read_wire8* dw;
+  if (r->wire6_meta && r->wire_ops && r->mem == AVO_MEM_HOST) {
+    // 6-byte records: starts, ends, lengths and offsets are rebuilt on the device; two head qualities
+    const avo_read_wire6* dw;
     const uint16_t* dwo;
     const avo_wire_exception* dexc = nullptr;
-    CKS(stage_in(ctx, SL_WIRE_META, r->wire8_meta, n, r->mem, &dw));
+    CKS(stage_in(ctx, SL_WIRE_META, r->wire6_meta, n, r->mem, &dw));
     CKS(stage_in(ctx, SL_WIRE_OPS, r->wire_ops, (size_t)r->n_ops, r->mem, &dwo));
-    if (r->n_wire8_exc > 0) CKS(stage_in(ctx, SL_WIRE_EXC, r->wire8_exc, (size_t)r->n_wire8_exc, r->mem, &dexc));
+    if (r->n_wire6_exc > 0) CKS(stage_in(ctx, SL_WIRE_EXC, r->wire6_exc, (size_t)r->n_wire6_exc, r->mem, &dexc));
     void *dm, *dops, *doffs, *dsizes, *temp;
     CKS(get_buf(ctx, SL_META, n * sizeof(avo_read_meta), &dm));
     CKS(get_buf(ctx, SL_OPS, (size_t)r->n_ops * 4, &dops));
     CKS(get_buf(ctx, SL_WIRE_OFFS, n * 12, &doffs));
     CKS(get_buf(ctx, SL_WIRE_SIZES, n * 8, &dsizes));
-    const size_t tb = wire8_temp_bytes(r->n_reads);
+    const size_t tb = wire6_temp_bytes(r->n_reads);
     CKS(get_buf(ctx, SL_TEMP, tb, &temp));
-    CK(launch_wire8_expand(dw, dwo, dexc, r->n_wire8_exc, r->wire8_base, r->n_reads, r->n_ops, doffs, dsizes,
+    CK(launch_wire6_expand(dw, dwo, dexc, r->n_wire6_exc, r->wire6_base, r->n_reads, r->n_ops, doffs, dsizes,
                            (avo_read_meta*)dm, (uint32_t*)dops, temp, tb, ctx->stream, &ctx->timing.n_launches));
     R->meta = (const avo_read_meta*)dm;
     R->ops = (const uint32_t*)dops;
+    R->qhead_short = 1;
   } else if (r->wire_meta && r->wire_ops && r->mem == AVO_MEM_HOST) {
     // compact wire columns: half the bytes over PCIe; offsets rebuilt by a scan on the device
     const avo_read_wire* dw;

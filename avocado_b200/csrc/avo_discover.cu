@@ -68,8 +68,9 @@ __device__ __forceinline__ void walk_mismatch(const DReads& R, uint32_t len, int
                                               uint32_t sb, uint32_t qhead, int32_t thr, SnpF&& snp) {
   // qual(i), not qual(idx + i): the first four qualities of the read travel in the record
   if ((int32_t)(qhead & 255u) >= thr) snp(pos, (uint32_t)__ldg(R.refb + rb));
+  const uint32_t in_head = R.qhead_short ? 2u : 4u;      // the 6-byte wire form carries two of them
   for (uint32_t i = 1; i < len; ++i) {
-    const int32_t q = (i < 4) ? (int32_t)((qhead >> (8 * i)) & 255u) : (int32_t)pl_qual(R.payload, sb, i);
+    const int32_t q = (i < in_head) ? (int32_t)((qhead >> (8 * i)) & 255u) : (int32_t)pl_qual(R.payload, sb, i);
     if (q >= thr) snp(pos + (int32_t)i, (uint32_t)__ldg(R.refb + rb + i));
   }
 }

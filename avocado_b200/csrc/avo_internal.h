@@ -19,6 +19,7 @@ struct DReads {
   const uint8_t* payload;      // 16-byte blocks: 10 bases (4 bit) + their 10 qualities
   const uint32_t* ops;
   const uint8_t* refb;
+  int32_t qhead_short;         // 1: only the first two bytes of meta.qhead are valid (6-byte wire form)
 };
 static_assert(sizeof(avo_read_meta) == 32, "avo_read_meta must be one 32-byte sector");
 
@@ -149,8 +150,8 @@ struct BatchStats {
   int32_t unsorted;   // != 0 if start[] is not non-decreasing
 };
 
-size_t wire8_temp_bytes(int64_t n_reads);
-cudaError_t launch_wire8_expand(const avo_read_wire8* wire, const uint16_t* wire_ops, const avo_wire_exception* exc,
+size_t wire6_temp_bytes(int64_t n_reads);
+cudaError_t launch_wire6_expand(const avo_read_wire6* wire, const uint16_t* wire_ops, const avo_wire_exception* exc,
                                 int64_t n_exc, int32_t base, int64_t n_reads, int64_t n_ops, void* offs /* 8 B x n */,
                                 void* sizes /* 8 B x n */, avo_read_meta* meta, uint32_t* ops, void* d_temp,
                                 size_t temp_bytes, cudaStream_t s, int* n_launches);

@@ -342,9 +342,9 @@ int avo_pack_wire(const avo_read_batch* full, avo_read_wire* wire_meta, uint16_t
   return AVO_OK;
 }
 
-int avo_pack_wire8(const avo_read_batch* full, avo_read_wire8* wire8_meta, uint16_t* wire_ops,
+int avo_pack_wire6(const avo_read_batch* full, avo_read_wire6* wire6_meta, uint16_t* wire_ops,
                    avo_wire_exception* exc, int64_t exc_capacity, int64_t* n_exc, int32_t* base) {
-  if (!full || full->mem != AVO_MEM_HOST || !n_exc || !base || (full->n_reads > 0 && (!full->meta || !wire8_meta)) ||
+  if (!full || full->mem != AVO_MEM_HOST || !n_exc || !base || (full->n_reads > 0 && (!full->meta || !wire6_meta)) ||
       (full->n_ops > 0 && (!full->ops || !wire_ops)) || (exc_capacity > 0 && !exc) || exc_capacity < 0)
     return AVO_E_INVALID;
   uint64_t blk = 0, op = 0, fb = 0;
@@ -373,9 +373,9 @@ int avo_pack_wire8(const avo_read_batch* full, avo_read_wire8* wire8_meta, uint1
       exc[ne].index = (uint32_t)r; exc[ne].l_seq = m.l_seq; exc[ne].end = m.end; exc[ne].reserved = 0;
       ++ne;
     }
-    avo_read_wire8& w = wire8_meta[r];
+    avo_read_wire6& w = wire6_meta[r];
     w.dstart_flags = (uint16_t)(((uint32_t)d << 2) | m.flags);
-    w.n_ops = (uint8_t)m.n_ops; w.mapq = m.mapq; w.qhead = m.qhead;
+    w.n_ops = (uint8_t)m.n_ops; w.mapq = m.mapq; w.q0 = (uint8_t)(m.qhead & 255u); w.q1 = (uint8_t)((m.qhead >> 8) & 255u);
     for (uint32_t k = 0; k < m.n_ops; ++k) wire_ops[m.op_off + k] = (uint16_t)full->ops[m.op_off + k];
     prev = m.start;
     blk += (m.l_seq + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES; op += m.n_ops; fb += nfb;

@@ -214,25 +214,26 @@ cudaError_t launch_wire_expand(const avo_read_wire* wire, const uint16_t* wire_o
   return cudaGetLastError();
 }
 
-// ---- 8-byte wire form -> records: starts and operator offsets from one scan, then the sizes the
+// ---- 6-byte wire form -> records: starts and operator offsets from one scan, then the sizes the
 // operators imply (end, l_seq, payload blocks, refb bytes), exceptions, a second scan for the
 // payload / refb offsets.
-struct W8A { uint32_t o; uint32_t s; };          // operators, start difference
-struct W8ASum { __host__ __device__ W8A operator()(const W8A& x, const W8A& y) const { return W8A{x.o + y.o, x.s + y.s}; } };
-struct W8AIn {
-  __host__ __device__ W8A operator()(const avo_read_wire8& w) const { return W8A{w.n_ops, (uint32_t)(w.dstart_flags >> 2)}; }
+struct W6A { uint32_t o; uint32_t s; };          // operators, start difference
+struct W6ASum { __host__ __device__ W6A operator()(const W6A& x, const W6A& y) const { return W6A{x.o + y.o, x.s + y.s}; } };
+struct W6AIn {
+  __host__ __device__ W6A operator()(const avo_read_wire6& w) const { return W6A{w.n_ops, (uint32_t)(w.dstart_flags >> 2)}; }
 };
-struct W8B { uint32_t b; uint32_t f; };          // payload blocks, refb bytes
-struct W8BSum { __host__ __device__ W8B operator()(const W8B& x, const W8B& y) const { return W8B{x.b + y.b, x.f + y.f}; } };
+struct W6B { uint32_t b; uint32_t f; };          // payload blocks, refb bytes
+struct W6BSum { __host__ __device__ W6B operator()(const W6B& x, const W6B& y) const { return W6B{x.b + y.b, x.f + y.f}; } };
 
-__global__ void k_wire8_records(const avo_read_wire8* __restrict__ wire, const W8A* __restrict__ offs,
+__global__ void k_wire6_records(const avo_read_wire6* __restrict__ wire, const W6A* __restrict__ offs,
                                 const uint16_t* __restrict__ wops, int64_t n, int32_t base,
-                                avo_read_meta* __restrict__ meta, W8B* __restrict__ sizes) {
+                                avo_read_meta* __restrict__ meta, W6B* __restrict__ sizes) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= n) return;
-  const uint2 wv = __ldg(reinterpret_cast<const uint2*>(wire + r));
-  const W8A o = offs[r];
-  const uint32_t d = (wv.x & 0xFFFFu) >> 2, flags = wv.x & 3u, n_ops = (wv.x >> 16) & 0xFFu, mapq = wv.x >> 24;
+  const uint16_t* w16 = reinterpret_cast<const uint16_t*>(wire + r);
+  const uint32_t h0 = __ldg(w16), h1 = __ldg(w16 + 1), h2 = __ldg(w16 + 2);
+  const W6A o = offs[r];
+  const uint32_t d = h0 >> 2, flags = h0 & 3u, n_ops = h1 & 0xFFu, mapq = h1 >> 8;
   const int32_t start = base + (int32_t)(o.s + d);
   uint32_t span = 0, lseq = 0, nrefb = 0;
   for (uint32_t k = 0; k < n_ops; ++k) {
@@ -243,14 +244,14 @@ __global__ void k_wire8_records(const avo_read_wire8* __restrict__ wire, const W
   }
   int4 a, b;
   a.x = start; a.y = start + (int32_t)span; a.z = 0; a.w = (int32_t)o.o;
-  b.x = 0; b.y = (int32_t)(n_ops | (mapq << 16) | (flags << 24)); b.z = (int32_t)wv.y; b.w = (int32_t)lseq;
+  b.x = 0; b.y = (int32_t)(n_ops | (mapq << 16) | (flags << 24)); b.z = (int32_t)h2; b.w = (int32_t)lseq;   // qhead: q0, q1 only
   reinterpret_cast<int4*>(meta + r)[0] = a;
   reinterpret_cast<int4*>(meta + r)[1] = b;
-  sizes[r] = W8B{(lseq + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES, nrefb};
+  sizes[r] = W6B{(lseq + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES, nrefb};
 }
 
-__global__ void k_wire8_exceptions(const avo_wire_exception* __restrict__ exc, int64_t n_exc, int64_t n,
-                                   avo_read_meta* __restrict__ meta, W8B* __restrict__ sizes) {
+__global__ void k_wire6_exceptions(const avo_wire_exception* __restrict__ exc, int64_t n_exc, int64_t n,
+                                   avo_read_meta* __restrict__ meta, W6B* __restrict__ sizes) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_exc) return;
   const avo_wire_exception e = exc[i];
@@ -260,40 +261,40 @@ __global__ void k_wire8_exceptions(const avo_wire_exception* __restrict__ exc, i
   sizes[e.index].b = (e.l_seq + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES;
 }
 
-__global__ void k_wire8_offsets(const W8B* __restrict__ offs, int64_t n, avo_read_meta* __restrict__ meta) {
+__global__ void k_wire6_offsets(const W6B* __restrict__ offs, int64_t n, avo_read_meta* __restrict__ meta) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= n) return;
-  const W8B o = offs[r];
+  const W6B o = offs[r];
   meta[r].seq_off = o.b;
   meta[r].refb_off = o.f;
 }
 
-size_t wire8_temp_bytes(int64_t n) {
+size_t wire6_temp_bytes(int64_t n) {
   size_t a = 0, b = 0;
-  cub::TransformInputIterator<W8A, W8AIn, const avo_read_wire8*> it(nullptr, W8AIn());
-  cub::DeviceScan::ExclusiveScan((void*)nullptr, a, it, (W8A*)nullptr, W8ASum(), W8A{0, 0}, (int)n);
-  cub::DeviceScan::ExclusiveScan((void*)nullptr, b, (const W8B*)nullptr, (W8B*)nullptr, W8BSum(), W8B{0, 0}, (int)n);
+  cub::TransformInputIterator<W6A, W6AIn, const avo_read_wire6*> it(nullptr, W6AIn());
+  cub::DeviceScan::ExclusiveScan((void*)nullptr, a, it, (W6A*)nullptr, W6ASum(), W6A{0, 0}, (int)n);
+  cub::DeviceScan::ExclusiveScan((void*)nullptr, b, (const W6B*)nullptr, (W6B*)nullptr, W6BSum(), W6B{0, 0}, (int)n);
   return (a > b ? a : b) + 256;
 }
 
 // offs: n x 8 bytes, sizes: n x 8 bytes (scanned in place)
-cudaError_t launch_wire8_expand(const avo_read_wire8* wire, const uint16_t* wire_ops, const avo_wire_exception* exc,
+cudaError_t launch_wire6_expand(const avo_read_wire6* wire, const uint16_t* wire_ops, const avo_wire_exception* exc,
                                 int64_t n_exc, int32_t base, int64_t n_reads, int64_t n_ops, void* offs, void* sizes,
                                 avo_read_meta* meta, uint32_t* ops, void* d_temp, size_t temp_bytes, cudaStream_t s,
                                 int* n_launches) {
   if (n_reads > 0) {
     const unsigned grid = (unsigned)((n_reads + 255) / 256);
-    cub::TransformInputIterator<W8A, W8AIn, const avo_read_wire8*> it(wire, W8AIn());
-    cudaError_t e = cub::DeviceScan::ExclusiveScan(d_temp, temp_bytes, it, (W8A*)offs, W8ASum(), W8A{0, 0},
+    cub::TransformInputIterator<W6A, W6AIn, const avo_read_wire6*> it(wire, W6AIn());
+    cudaError_t e = cub::DeviceScan::ExclusiveScan(d_temp, temp_bytes, it, (W6A*)offs, W6ASum(), W6A{0, 0},
                                                    (int)n_reads, s);
     if (e != cudaSuccess) return e;
-    k_wire8_records<<<grid, 256, 0, s>>>(wire, (const W8A*)offs, wire_ops, n_reads, base, meta, (W8B*)sizes);
+    k_wire6_records<<<grid, 256, 0, s>>>(wire, (const W6A*)offs, wire_ops, n_reads, base, meta, (W6B*)sizes);
     if (n_exc > 0)
-      k_wire8_exceptions<<<(unsigned)((n_exc + 255) / 256), 256, 0, s>>>(exc, n_exc, n_reads, meta, (W8B*)sizes);
-    e = cub::DeviceScan::ExclusiveScan(d_temp, temp_bytes, (const W8B*)sizes, (W8B*)sizes, W8BSum(), W8B{0, 0},
+      k_wire6_exceptions<<<(unsigned)((n_exc + 255) / 256), 256, 0, s>>>(exc, n_exc, n_reads, meta, (W6B*)sizes);
+    e = cub::DeviceScan::ExclusiveScan(d_temp, temp_bytes, (const W6B*)sizes, (W6B*)sizes, W6BSum(), W6B{0, 0},
                                        (int)n_reads, s);
     if (e != cudaSuccess) return e;
-    k_wire8_offsets<<<grid, 256, 0, s>>>((const W8B*)sizes, n_reads, meta);
+    k_wire6_offsets<<<grid, 256, 0, s>>>((const W6B*)sizes, n_reads, meta);
     if (n_launches) *n_launches += 6 + (n_exc > 0);
   }
   if (n_ops > 0) {

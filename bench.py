@@ -441,7 +441,7 @@ def main():
                                 2: "discovery reads in place, call-stage blocks gathered by host threads"}[
                                     int(last[-1]["payload_in_place"])],
                "gathered_blocks_per_step": int(sum(t["gathered_blocks"] for t in last)) * world,
-               "gather_threads_per_call": args.gather_threads, "wire_form": ("wire8" if hb.wire8_meta is not None else "wire16") if host_wire else None,
+               "gather_threads_per_call": args.gather_threads, "wire_form": ("wire6" if hb.wire6_meta is not None else "wire16") if host_wire else None,
                "single_call": {"value": total_reads * args.steps / (ms_h / 1e3), "ms_per_step": ms_h / args.steps,
                                "ms_h2d": statistics.mean(t["ms_h2d"] for t in t_h),
                                "ms_discover": statistics.mean(t["ms_discover"] for t in t_h),
@@ -618,7 +618,7 @@ class ReadBatchPinned:
             t = torch.empty(n, dtype=torch.uint8, pin_memory=True)
             self.tensors[("wire", key, len(self.tensors))] = t
             return t.numpy()
-        return batch.with_wire8(alloc) or batch.with_wire(alloc)
+        return batch.with_wire6(alloc) or batch.with_wire(alloc)
 
 
 if __name__ == "__main__":

@@ -128,19 +128,20 @@ typedef struct {
   uint32_t qhead;
 } avo_read_wire;    /* 16 bytes */
 
-/* Tighter wire form, 8 bytes per read: the start travels as the difference to the previous read's
- * start (the batch is sorted), and end, l_seq and the refb byte count follow from the read's
- * operators (end - start = lengths of = X D, l_seq = lengths of = X I S, refb bytes = X lengths +
- * (D length + 1) / 2), so the library recomputes them on the device.  The few reads for which that
- * does not hold (no operators, strings longer than the CIGAR's read length) are listed as
- * exceptions.  A batch can use it when it fits avo_read_wire and every start difference is below
- * 16384 (avo_pack_wire8 checks). */
+/* Tighter wire form, 6 bytes per read: the start travels as the difference to the previous read's
+ * start (the batch is sorted), end, l_seq and the refb byte count follow from the read's operators
+ * (end - start = lengths of = X D, l_seq = lengths of = X I S, refb bytes = X lengths +
+ * (D length + 1) / 2) and are recomputed on the device, and of the four head qualities (avo_read_meta.qhead)
+ * only the first two travel: discovery fetches the others from the payload in the rare mismatch run of
+ * three or more bases.  The few reads whose sizes do not follow from their operators (no operators,
+ * strings longer than the CIGAR's read length) are listed as exceptions.  A batch can use it when it
+ * fits avo_read_wire and every start difference is below 16384 (avo_pack_wire6 checks). */
 typedef struct {
-  uint16_t dstart_flags; /* ((start - previous read's start) << 2) | flags; first read: start - wire8_base */
+  uint16_t dstart_flags; /* ((start - previous read's start) << 2) | flags; first read: start - wire6_base */
   uint8_t n_ops;
   uint8_t mapq;
-  uint32_t qhead;
-} avo_read_wire8;   /* 8 bytes */
+  uint8_t q0, q1;        /* qual(0), qual(1) of the read */
+} avo_read_wire6;   /* 6 bytes */
 
 typedef struct {
   uint32_t index;  /* read index in the batch, ascending */
@@ -169,11 +170,11 @@ typedef struct {
    * copied to the device and `meta` / `ops` are ignored (may be NULL) */
   const avo_read_wire* wire_meta; /* [n_reads] */
   const uint16_t* wire_ops;       /* [n_ops] (length << 4) | code */
-  /* or the 8-byte form (with wire_ops): takes precedence over wire_meta when non-NULL */
-  const avo_read_wire8* wire8_meta;     /* [n_reads] */
-  const avo_wire_exception* wire8_exc;  /* [n_wire8_exc] */
-  int64_t n_wire8_exc;
-  int32_t wire8_base;                   /* start of the first read minus its stored difference */
+  /* or the 6-byte form (with wire_ops): takes precedence over wire_meta when non-NULL */
+  const avo_read_wire6* wire6_meta;     /* [n_reads] */
+  const avo_wire_exception* wire6_exc;  /* [n_wire6_exc] */
+  int64_t n_wire6_exc;
+  int32_t wire6_base;                   /* start of the first read minus its stored difference */
   int32_t reserved;
 } avo_read_batch;
 
@@ -502,9 +503,9 @@ typedef struct {
 /* Full records / operators (host) -> compact wire columns (host).  AVO_E_UNSUPPORTED when a read or
  * an operator does not fit the compact form (the batch then travels in the full form). */
 int avo_pack_wire(const avo_read_batch* full, avo_read_wire* wire_meta, uint16_t* wire_ops);
-/* ... -> the 8-byte form.  exc holds exc_capacity entries; *n_exc and *base are outputs (they go into
- * avo_read_batch.n_wire8_exc / wire8_base).  AVO_E_UNSUPPORTED as above, or with too many exceptions. */
-int avo_pack_wire8(const avo_read_batch* full, avo_read_wire8* wire8_meta, uint16_t* wire_ops,
+/* ... -> the 6-byte form.  exc holds exc_capacity entries; *n_exc and *base are outputs (they go into
+ * avo_read_batch.n_wire6_exc / wire6_base).  AVO_E_UNSUPPORTED as above, or with too many exceptions. */
+int avo_pack_wire6(const avo_read_batch* full, avo_read_wire6* wire6_meta, uint16_t* wire_ops,
                    avo_wire_exception* exc, int64_t exc_capacity, int64_t* n_exc, int32_t* base);
 
 int avo_pack_bounds(const avo_text_reads* in, int64_t* n_reads, int64_t* n_blocks, int64_t* n_ops,

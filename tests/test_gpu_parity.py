@@ -274,16 +274,16 @@ def test_two_gpu_region_and_sample_sharding():
     assert "multi_gpu_check ok" in r.stdout
 
 
-@pytest.mark.parametrize("form", ["wire16", "wire8"])
+@pytest.mark.parametrize("form", ["wire16", "wire6"])
 def test_wire_form_gives_the_same_results(ctx, form):
-    """Host batches in the compact wire forms (16-byte records, or 8-byte records with start
+    """Host batches in the compact wire forms (16-byte records, or 6-byte records with start
     differences and sizes implied by the operators; 16-bit operators; offsets rebuilt on the device)
     produce exactly the rows of the full form, for discovery, call and gVCF rows."""
     from avocado_b200 import batch as B
     p = B.synth_params(seed=12, n_reads_total=25000, contig_len=70000, first_pos=123, softclip_frac=0.1)
     full = B.synth_host(p)
     wire = B.synth_host(p)
-    assert wire.with_wire() if form == "wire16" else wire.with_wire8()
+    assert wire.with_wire() if form == "wire16" else wire.with_wire6()
     wire.meta = np.zeros(1, B.META_DTYPE)[:0]      # prove that only the wire columns are used
     wire.ops = np.zeros(1, np.uint32)
     # (as_struct passes whatever is there; the library must not touch meta / ops)
@@ -300,15 +300,15 @@ def test_wire_form_gives_the_same_results(ctx, form):
         assert np.array_equal(np.asarray(a[2][k]), np.asarray(b[2][k]), equal_nan=True), k
 
 
-def test_wire8_exceptions_reach_the_device(ctx):
+def test_wire6_exceptions_reach_the_device(ctx):
     """Reads whose end / l_seq do not follow from their operators (failed extractions, strings longer
-    than the CIGAR) travel as exceptions of the 8-byte form; discovery sees the same batch."""
+    than the CIGAR) travel as exceptions of the 6-byte form; discovery sees the same batch."""
     from avocado_b200 import batch as B
     from helpers import fuzz_records
     recs = [r for r in fuzz_records(9, 30000) if r.readMapped]
     full = B.pack_reads(recs, sort=False)
     wire = B.pack_reads(recs, sort=False)
-    assert wire.with_wire8(max_exceptions=wire.n_reads) and len(wire.wire8_exc) > 100
+    assert wire.with_wire6(max_exceptions=wire.n_reads) and len(wire.wire6_exc) > 100
     wire.meta = np.zeros(1, B.META_DTYPE)[:0]
     wire.ops = np.zeros(1, np.uint32)
     s_full = ctx.discover_packed(full, phred=10, min_obs=1)

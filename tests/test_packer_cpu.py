@@ -171,16 +171,17 @@ def test_packer_agrees_with_the_oracle_on_fuzzed_cigar_and_md(oracle):
     assert thrown > 300 and kept > 3000
 
 
-def _expand_wire8(b):
-    """numpy restatement of the device-side expansion of the 8-byte form -> META_DTYPE records"""
+def _expand_wire6(b):
+    """numpy restatement of the device-side expansion of the 6-byte form -> META_DTYPE records"""
     from avocado_b200 import batch as B
-    w, ops = b.wire8_meta, b.wire_ops.astype(np.int64)
+    w, ops = b.wire6_meta, b.wire_ops.astype(np.int64)
     n = len(w)
     m = np.zeros(n, B.META_DTYPE)
     d = (w["dstart_flags"] >> 2).astype(np.int64)
-    m["start"] = b.wire8_base + np.cumsum(d)
+    m["start"] = b.wire6_base + np.cumsum(d)
     m["flags"] = w["dstart_flags"] & 3
-    m["n_ops"], m["mapq"], m["qhead"] = w["n_ops"], w["mapq"], w["qhead"]
+    m["n_ops"], m["mapq"] = w["n_ops"], w["mapq"]
+    m["qhead"] = w["q0"].astype(np.uint32) | (w["q1"].astype(np.uint32) << 8)
     op_off = np.concatenate([[0], np.cumsum(w["n_ops"].astype(np.int64))])
     m["op_off"] = op_off[:-1]
     ln, code = ops >> 4, ops & 15
@@ -189,7 +190,7 @@ def _expand_wire8(b):
     lseq = per((code <= 1) | (code == 2) | (code == 4), ln)
     nrefb = per(code == 1, ln) + per(code == 3, (ln + 1) >> 1)
     end = m["start"].astype(np.int64) + span
-    for e in b.wire8_exc:
+    for e in b.wire6_exc:
         lseq[e["index"]] = e["l_seq"]
         end[e["index"]] = e["end"]
     m["end"], m["l_seq"] = end, lseq
@@ -198,33 +199,35 @@ def _expand_wire8(b):
     return m
 
 
-def test_wire8_columns_hold_the_same_information():
-    """avo_pack_wire8: 8 bytes per read; starts as differences, end / l_seq / refb bytes implied by the
+def test_wire6_columns_hold_the_same_information():
+    """avo_pack_wire6: 6 bytes per read; starts as differences, end / l_seq / refb bytes implied by the
     operators, the reads for which that fails listed as exceptions."""
     from avocado_b200 import batch as B
     from helpers import fuzz_records
     p = B.synth_params(seed=4, n_reads_total=3000, contig_len=20000, softclip_frac=0.2)
     b = B.synth_host(p)
-    assert b.with_wire8() and len(b.wire8_exc) == 0
-    got = _expand_wire8(b)
+    assert b.with_wire6() and len(b.wire6_exc) == 0
+    got = _expand_wire6(b)
     for f in b.meta.dtype.names:
-        assert np.array_equal(got[f], b.meta[f]), f
+        want = b.meta[f] & 0xFFFF if f == "qhead" else b.meta[f]      # two of the four head qualities travel
+        assert np.array_equal(got[f], want), f
     # fuzzed reads: failed extractions (no operators) and over-long strings become exceptions
     recs = [r for r in fuzz_records(5, 3000) if r.readMapped]
     fz = B.pack_reads(recs, sort=False)
-    assert fz.with_wire8(max_exceptions=fz.n_reads)
-    assert 0 < len(fz.wire8_exc) < fz.n_reads
-    got = _expand_wire8(fz)
+    assert fz.with_wire6(max_exceptions=fz.n_reads)
+    assert 0 < len(fz.wire6_exc) < fz.n_reads
+    got = _expand_wire6(fz)
     for f in fz.meta.dtype.names:
-        assert np.array_equal(got[f], fz.meta[f]), f
-    assert not fz.with_wire8(max_exceptions=3)
+        want = fz.meta[f] & 0xFFFF if f == "qhead" else fz.meta[f]
+        assert np.array_equal(got[f], want), f
+    assert not fz.with_wire6(max_exceptions=3)
     far = B.synth_host(p)
     far.meta["start"][100:] += 20000                  # a start difference that does not fit 14 bits
     far.meta["end"][100:] += 20000
-    assert not far.with_wire8()
+    assert not far.with_wire6()
     unsorted = B.synth_host(p)
     unsorted.meta["start"][7] -= 500
-    assert not unsorted.with_wire8()
+    assert not unsorted.with_wire6()
 
 
 def test_headers_are_plain_c(tmp_path):

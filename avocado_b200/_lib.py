@@ -39,7 +39,7 @@ class ReadBatchStruct(C.Structure):
                 ("stats_min_start", C.c_int32), ("stats_max_end", C.c_int32),
                 ("stats_max_span", C.c_int32), ("stats_valid", C.c_int32),
                 ("meta", P), ("payload", P), ("ops", P), ("refb", P), ("wire_meta", P), ("wire_ops", P),
-                ("wire6_meta", P), ("wire6_exc", P), ("n_wire6_exc", C.c_int64), ("wire6_base", C.c_int32),
+                ("wire6_meta", P), ("wire6_oplen", P), ("wire6_opcode", P), ("wire6_exc", P), ("n_wire6_exc", C.c_int64), ("wire6_base", C.c_int32),
                 ("reserved", C.c_int32)]
 
 
@@ -241,7 +241,7 @@ def load():
     lib.avo_joint_counts.argtypes = [P, C.POINTER(JointInStruct), P, P]
     lib.avo_joint.argtypes = [P, C.POINTER(JointInStruct), C.POINTER(JointOutStruct)]
     lib.avo_pack_wire.argtypes = [C.POINTER(ReadBatchStruct), P, P]
-    lib.avo_pack_wire6.argtypes = [C.POINTER(ReadBatchStruct), P, P, P, C.c_int64, C.POINTER(C.c_int64),
+    lib.avo_pack_wire6.argtypes = [C.POINTER(ReadBatchStruct), P, P, P, P, C.c_int64, C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int32)]
     lib.avo_pack_bounds.argtypes = [C.POINTER(TextReadsStruct)] + [C.POINTER(C.c_int64)] * 4
     lib.avo_pack_reads.argtypes = [C.POINTER(TextReadsStruct), C.POINTER(PackedOutStruct)]

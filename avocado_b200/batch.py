@@ -71,7 +71,9 @@ class ReadBatch:
     stats: Optional[tuple] = None   # (min_start, max_end, max_span): avo_batch_stats, optional
     wire_meta: Optional[np.ndarray] = None   # host batches: compact wire columns (avo_pack_wire)
     wire_ops: Optional[np.ndarray] = None
-    wire6_meta: Optional[np.ndarray] = None  # host batches: the 6-byte form (avo_pack_wire6), with wire_ops
+    wire6_meta: Optional[np.ndarray] = None  # host batches: the 6-byte form (avo_pack_wire6) ...
+    wire6_oplen: Optional[np.ndarray] = None   # ... with its operators: a length byte
+    wire6_opcode: Optional[np.ndarray] = None  # ... and a code nibble each
     wire6_exc: Optional[np.ndarray] = None
     wire6_base: int = 0
 
@@ -82,17 +84,18 @@ class ReadBatch:
         alloc = alloc or (lambda n: np.zeros(n, np.uint8))
         cap = max(16, self.n_reads // 64) if max_exceptions is None else max_exceptions
         wm = alloc(max(self.n_reads, 1) * 6).view(WIRE6_DTYPE)
-        wo = alloc(max(self.n_ops, 1) * 2).view(np.uint16)
+        wl = alloc(max(self.n_ops, 1))
+        wc = alloc(max((self.n_ops + 1) // 2, 1))
         ex = alloc(max(cap, 1) * 16).view(WIRE_EXC_DTYPE)
         ne, base = C.c_int64(), C.c_int32()
         s = self.as_struct()
-        rc = L.load().avo_pack_wire6(C.byref(s), wm.ctypes.data, wo.ctypes.data, ex.ctypes.data, cap,
+        rc = L.load().avo_pack_wire6(C.byref(s), wm.ctypes.data, wl.ctypes.data, wc.ctypes.data, ex.ctypes.data, cap,
                                      C.byref(ne), C.byref(base))
         if rc == L.AVO_E_UNSUPPORTED:
             return False
         if rc != 0:
             raise L.AvocadoError(rc, "avo_pack_wire6 failed")
-        self.wire6_meta, self.wire_ops = wm[:self.n_reads], wo[:max(self.n_ops, 1)]
+        self.wire6_meta, self.wire6_oplen, self.wire6_opcode = wm[:self.n_reads], wl, wc
         self.wire6_exc, self.wire6_base = ex[:ne.value], base.value
         return True
 
@@ -151,8 +154,9 @@ class ReadBatch:
             setattr(s, name, _ptr(getattr(self, name)))
         if self.wire_meta is not None and self.wire_ops is not None and not self.on_device:
             s.wire_meta, s.wire_ops = _ptr(self.wire_meta), _ptr(self.wire_ops)
-        if self.wire6_meta is not None and self.wire_ops is not None and not self.on_device:
-            s.wire6_meta, s.wire_ops = _ptr(self.wire6_meta), _ptr(self.wire_ops)
+        if self.wire6_meta is not None and self.wire6_oplen is not None and not self.on_device:
+            s.wire6_meta = _ptr(self.wire6_meta)
+            s.wire6_oplen, s.wire6_opcode = _ptr(self.wire6_oplen), _ptr(self.wire6_opcode)
             s.wire6_exc = _ptr(self.wire6_exc) if len(self.wire6_exc) else None
             s.n_wire6_exc, s.wire6_base = len(self.wire6_exc), self.wire6_base
         return s

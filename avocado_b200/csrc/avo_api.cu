@@ -21,7 +21,7 @@ namespace {
 constexpr int32_t LNK_N = 1 << 16;
 
 enum Slot {
-  SL_META, SL_COORDS, SL_PAYLOAD, SL_OPS, SL_REFB, SL_WIRE_META, SL_WIRE_OPS, SL_WIRE_OFFS, SL_WIRE_SIZES, SL_WIRE_EXC,
+  SL_META, SL_COORDS, SL_PAYLOAD, SL_OPS, SL_REFB, SL_WIRE_META, SL_WIRE_OPS, SL_WIRE_OPC, SL_WIRE_OFFS, SL_WIRE_SIZES, SL_WIRE_EXC,
   SL_S_CONTIG, SL_S_START, SL_S_REFLEN, SL_S_ALTLEN, SL_S_AOFF, SL_S_ALLELES, SL_S_END, SL_S_PME,
   SL_S_COUNT,
   SL_CNV, SL_STATS, SL_SMALL, SL_RIDX, SL_SIDX, SL_TEMP, SL_LUT,
@@ -177,9 +177,11 @@ int validate_reads(avo_ctx* ctx, const avo_read_batch* r) {
   if (r->n_blocks < 0 || r->n_blocks > (int64_t)UINT32_MAX || r->n_ops < 0 ||
       r->n_ops > (int64_t)UINT32_MAX || r->n_refb < 0 || r->n_refb > (int64_t)INT32_MAX)
     return fail(ctx, AVO_E_INVALID, "batch totals must fit 32-bit offsets; split the batch");
-  const bool wire = (r->wire_meta || r->wire6_meta) && r->wire_ops;
-  if (((r->wire_meta != nullptr) || (r->wire6_meta != nullptr)) != (r->wire_ops != nullptr) && r->n_ops > 0)
-    return fail(ctx, AVO_E_INVALID, "wire_meta / wire6_meta and wire_ops go together");
+  const bool wire6 = r->wire6_meta && (r->n_ops == 0 || (r->wire6_oplen && r->wire6_opcode));
+  const bool wire = wire6 || (r->wire_meta && r->wire_ops);
+  if (r->wire6_meta && !wire6) return fail(ctx, AVO_E_INVALID, "wire6_meta needs wire6_oplen and wire6_opcode");
+  if (!r->wire6_meta && (r->wire_meta != nullptr) != (r->wire_ops != nullptr) && r->n_ops > 0)
+    return fail(ctx, AVO_E_INVALID, "wire_meta and wire_ops go together");
   if (r->wire6_meta && (r->n_wire6_exc < 0 || r->n_wire6_exc > r->n_reads || (r->n_wire6_exc > 0 && !r->wire6_exc)))
     return fail(ctx, AVO_E_INVALID, "bad wire6 exception list");
   if (wire && r->mem != AVO_MEM_HOST) return fail(ctx, AVO_E_INVALID, "wire columns are for host batches");
@@ -207,13 +209,16 @@ int upload_reads(avo_ctx* ctx, const avo_read_batch* r, bool sparse, DReads* R, 
     CKS(get_buf(ctx, SL_COORDS, n * sizeof(int2), &c));
     R->coords = (int2*)c;
   }
-  if (r->wire6_meta && r->wire_ops && r->mem == AVO_MEM_HOST) {
+  if (r->wire6_meta && r->mem == AVO_MEM_HOST) {
     // 6-byte records: starts, ends, lengths and offsets are rebuilt on the device; two head qualities
     const avo_read_wire6* dw;
-    const uint16_t* dwo;
+    const uint8_t *dol = nullptr, *doc = nullptr;
     const avo_wire_exception* dexc = nullptr;
     CKS(stage_in(ctx, SL_WIRE_META, r->wire6_meta, n, r->mem, &dw));
-    CKS(stage_in(ctx, SL_WIRE_OPS, r->wire_ops, (size_t)r->n_ops, r->mem, &dwo));
+    if (r->n_ops > 0) {
+      CKS(stage_in(ctx, SL_WIRE_OPS, r->wire6_oplen, (size_t)r->n_ops, r->mem, &dol));
+      CKS(stage_in(ctx, SL_WIRE_OPC, r->wire6_opcode, (size_t)(r->n_ops + 1) / 2, r->mem, &doc));
+    }
     if (r->n_wire6_exc > 0) CKS(stage_in(ctx, SL_WIRE_EXC, r->wire6_exc, (size_t)r->n_wire6_exc, r->mem, &dexc));
     void *dm, *dops, *doffs, *dsizes, *temp;
     CKS(get_buf(ctx, SL_META, n * sizeof(avo_read_meta), &dm));
@@ -222,7 +227,7 @@ int upload_reads(avo_ctx* ctx, const avo_read_batch* r, bool sparse, DReads* R, 
     CKS(get_buf(ctx, SL_WIRE_SIZES, n * 8, &dsizes));
     const size_t tb = wire6_temp_bytes(r->n_reads);
     CKS(get_buf(ctx, SL_TEMP, tb, &temp));
-    CK(launch_wire6_expand(dw, dwo, dexc, r->n_wire6_exc, r->wire6_base, r->n_reads, r->n_ops, doffs, dsizes,
+    CK(launch_wire6_expand(dw, dol, doc, dexc, r->n_wire6_exc, r->wire6_base, r->n_reads, r->n_ops, doffs, dsizes,
                            (avo_read_meta*)dm, (uint32_t*)dops, temp, tb, ctx->stream, &ctx->timing.n_launches));
     R->meta = (const avo_read_meta*)dm;
     R->ops = (const uint32_t*)dops;

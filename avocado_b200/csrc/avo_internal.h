@@ -151,7 +151,8 @@ struct BatchStats {
 };
 
 size_t wire6_temp_bytes(int64_t n_reads);
-cudaError_t launch_wire6_expand(const avo_read_wire6* wire, const uint16_t* wire_ops, const avo_wire_exception* exc,
+cudaError_t launch_wire6_expand(const avo_read_wire6* wire, const uint8_t* oplen, const uint8_t* opcode,
+                                const avo_wire_exception* exc,
                                 int64_t n_exc, int32_t base, int64_t n_reads, int64_t n_ops, void* offs /* 8 B x n */,
                                 void* sizes /* 8 B x n */, avo_read_meta* meta, uint32_t* ops, void* d_temp,
                                 size_t temp_bytes, cudaStream_t s, int* n_launches);

@@ -342,11 +342,14 @@ int avo_pack_wire(const avo_read_batch* full, avo_read_wire* wire_meta, uint16_t
   return AVO_OK;
 }
 
-int avo_pack_wire6(const avo_read_batch* full, avo_read_wire6* wire6_meta, uint16_t* wire_ops,
-                   avo_wire_exception* exc, int64_t exc_capacity, int64_t* n_exc, int32_t* base) {
+int avo_pack_wire6(const avo_read_batch* full, avo_read_wire6* wire6_meta, uint8_t* wire6_oplen,
+                   uint8_t* wire6_opcode, avo_wire_exception* exc, int64_t exc_capacity, int64_t* n_exc,
+                   int32_t* base) {
   if (!full || full->mem != AVO_MEM_HOST || !n_exc || !base || (full->n_reads > 0 && (!full->meta || !wire6_meta)) ||
-      (full->n_ops > 0 && (!full->ops || !wire_ops)) || (exc_capacity > 0 && !exc) || exc_capacity < 0)
+      (full->n_ops > 0 && (!full->ops || !wire6_oplen || !wire6_opcode)) || (exc_capacity > 0 && !exc) ||
+      exc_capacity < 0)
     return AVO_E_INVALID;
+  if (full->n_ops > 0) memset(wire6_opcode, 0, (size_t)(full->n_ops + 1) / 2);
   uint64_t blk = 0, op = 0, fb = 0;
   int64_t ne = 0;
   int32_t prev = full->n_reads ? full->meta[0].start : 0;
@@ -361,7 +364,7 @@ int avo_pack_wire6(const avo_read_batch* full, avo_read_wire6* wire6_meta, uint1
     uint64_t span = 0, lseq = 0, nrefb = 0;
     for (uint32_t k = 0; k < m.n_ops; ++k) {
       const uint32_t o = full->ops[m.op_off + k], len = o >> 4, code = o & 15u;
-      if (o > 0xFFFFu) return AVO_E_UNSUPPORTED;      // operator of 4096 bases or more
+      if (len > 0xFFu) return AVO_E_UNSUPPORTED;      // operator of 256 bases or more
       if (code == AVO_OP_MATCH || code == AVO_OP_MISMATCH || code == AVO_OP_DEL) span += len;
       if (code == AVO_OP_MATCH || code == AVO_OP_MISMATCH || code == AVO_OP_INS || code == AVO_OP_SOFTCLIP) lseq += len;
       if (code == AVO_OP_MISMATCH) nrefb += len;
@@ -376,7 +379,12 @@ int avo_pack_wire6(const avo_read_batch* full, avo_read_wire6* wire6_meta, uint1
     avo_read_wire6& w = wire6_meta[r];
     w.dstart_flags = (uint16_t)(((uint32_t)d << 2) | m.flags);
     w.n_ops = (uint8_t)m.n_ops; w.mapq = m.mapq; w.q0 = (uint8_t)(m.qhead & 255u); w.q1 = (uint8_t)((m.qhead >> 8) & 255u);
-    for (uint32_t k = 0; k < m.n_ops; ++k) wire_ops[m.op_off + k] = (uint16_t)full->ops[m.op_off + k];
+    for (uint32_t k = 0; k < m.n_ops; ++k) {
+      const uint64_t i = (uint64_t)m.op_off + k;
+      const uint32_t o = full->ops[i];
+      wire6_oplen[i] = (uint8_t)(o >> 4);
+      wire6_opcode[i >> 1] |= (uint8_t)((o & 15u) << ((i & 1) * 4));
+    }
     prev = m.start;
     blk += (m.l_seq + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES; op += m.n_ops; fb += nfb;
   }

@@ -225,8 +225,15 @@ struct W6AIn {
 struct W6B { uint32_t b; uint32_t f; };          // payload blocks, refb bytes
 struct W6BSum { __host__ __device__ W6B operator()(const W6B& x, const W6B& y) const { return W6B{x.b + y.b, x.f + y.f}; } };
 
+// operators of the 6-byte form: a length byte and a code nibble each -> (length << 4) | code
+__global__ void k_wire6_ops(const uint8_t* __restrict__ oplen, const uint8_t* __restrict__ opcode, int64_t n,
+                            uint32_t* __restrict__ ops) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) ops[i] = ((uint32_t)__ldg(oplen + i) << 4) | (((uint32_t)__ldg(opcode + (i >> 1)) >> ((i & 1) * 4)) & 15u);
+}
+
 __global__ void k_wire6_records(const avo_read_wire6* __restrict__ wire, const W6A* __restrict__ offs,
-                                const uint16_t* __restrict__ wops, int64_t n, int32_t base,
+                                const uint32_t* __restrict__ wops, int64_t n, int32_t base,
                                 avo_read_meta* __restrict__ meta, W6B* __restrict__ sizes) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= n) return;
@@ -278,17 +285,21 @@ size_t wire6_temp_bytes(int64_t n) {
 }
 
 // offs: n x 8 bytes, sizes: n x 8 bytes (scanned in place)
-cudaError_t launch_wire6_expand(const avo_read_wire6* wire, const uint16_t* wire_ops, const avo_wire_exception* exc,
-                                int64_t n_exc, int32_t base, int64_t n_reads, int64_t n_ops, void* offs, void* sizes,
-                                avo_read_meta* meta, uint32_t* ops, void* d_temp, size_t temp_bytes, cudaStream_t s,
-                                int* n_launches) {
+cudaError_t launch_wire6_expand(const avo_read_wire6* wire, const uint8_t* oplen, const uint8_t* opcode,
+                                const avo_wire_exception* exc, int64_t n_exc, int32_t base, int64_t n_reads,
+                                int64_t n_ops, void* offs, void* sizes, avo_read_meta* meta, uint32_t* ops,
+                                void* d_temp, size_t temp_bytes, cudaStream_t s, int* n_launches) {
+  if (n_ops > 0) {
+    k_wire6_ops<<<(unsigned)((n_ops + 255) / 256), 256, 0, s>>>(oplen, opcode, n_ops, ops);
+    if (n_launches) *n_launches += 1;
+  }
   if (n_reads > 0) {
     const unsigned grid = (unsigned)((n_reads + 255) / 256);
     cub::TransformInputIterator<W6A, W6AIn, const avo_read_wire6*> it(wire, W6AIn());
     cudaError_t e = cub::DeviceScan::ExclusiveScan(d_temp, temp_bytes, it, (W6A*)offs, W6ASum(), W6A{0, 0},
                                                    (int)n_reads, s);
     if (e != cudaSuccess) return e;
-    k_wire6_records<<<grid, 256, 0, s>>>(wire, (const W6A*)offs, wire_ops, n_reads, base, meta, (W6B*)sizes);
+    k_wire6_records<<<grid, 256, 0, s>>>(wire, (const W6A*)offs, ops, n_reads, base, meta, (W6B*)sizes);
     if (n_exc > 0)
       k_wire6_exceptions<<<(unsigned)((n_exc + 255) / 256), 256, 0, s>>>(exc, n_exc, n_reads, meta, (W6B*)sizes);
     e = cub::DeviceScan::ExclusiveScan(d_temp, temp_bytes, (const W6B*)sizes, (W6B*)sizes, W6BSum(), W6B{0, 0},
@@ -296,10 +307,6 @@ cudaError_t launch_wire6_expand(const avo_read_wire6* wire, const uint16_t* wire
     if (e != cudaSuccess) return e;
     k_wire6_offsets<<<grid, 256, 0, s>>>((const W6B*)sizes, n_reads, meta);
     if (n_launches) *n_launches += 6 + (n_exc > 0);
-  }
-  if (n_ops > 0) {
-    k_wire_ops<<<(unsigned)((n_ops + 255) / 256), 256, 0, s>>>(wire_ops, n_ops, ops);
-    if (n_launches) *n_launches += 1;
   }
   return cudaGetLastError();
 }

@@ -142,6 +142,8 @@ typedef struct {
   uint8_t mapq;
   uint8_t q0, q1;        /* qual(0), qual(1) of the read */
 } avo_read_wire6;   /* 6 bytes */
+/* With it the operators travel as 12 bits each: one length byte (every operator shorter than 256) and
+ * one code nibble (two per byte, the even operator in the low nibble). */
 
 typedef struct {
   uint32_t index;  /* read index in the batch, ascending */
@@ -170,8 +172,10 @@ typedef struct {
    * copied to the device and `meta` / `ops` are ignored (may be NULL) */
   const avo_read_wire* wire_meta; /* [n_reads] */
   const uint16_t* wire_ops;       /* [n_ops] (length << 4) | code */
-  /* or the 6-byte form (with wire_ops): takes precedence over wire_meta when non-NULL */
+  /* or the 6-byte form (with wire6_oplen / wire6_opcode): takes precedence over wire_meta when non-NULL */
   const avo_read_wire6* wire6_meta;     /* [n_reads] */
+  const uint8_t* wire6_oplen;           /* [n_ops] operator lengths */
+  const uint8_t* wire6_opcode;          /* [(n_ops + 1) / 2] operator codes, 4 bits each */
   const avo_wire_exception* wire6_exc;  /* [n_wire6_exc] */
   int64_t n_wire6_exc;
   int32_t wire6_base;                   /* start of the first read minus its stored difference */
@@ -505,8 +509,9 @@ typedef struct {
 int avo_pack_wire(const avo_read_batch* full, avo_read_wire* wire_meta, uint16_t* wire_ops);
 /* ... -> the 6-byte form.  exc holds exc_capacity entries; *n_exc and *base are outputs (they go into
  * avo_read_batch.n_wire6_exc / wire6_base).  AVO_E_UNSUPPORTED as above, or with too many exceptions. */
-int avo_pack_wire6(const avo_read_batch* full, avo_read_wire6* wire6_meta, uint16_t* wire_ops,
-                   avo_wire_exception* exc, int64_t exc_capacity, int64_t* n_exc, int32_t* base);
+int avo_pack_wire6(const avo_read_batch* full, avo_read_wire6* wire6_meta, uint8_t* wire6_oplen,
+                   uint8_t* wire6_opcode, avo_wire_exception* exc, int64_t exc_capacity, int64_t* n_exc,
+                   int32_t* base);
 
 int avo_pack_bounds(const avo_text_reads* in, int64_t* n_reads, int64_t* n_blocks, int64_t* n_ops,
                     int64_t* n_refb);

@@ -226,3 +226,9 @@ def fuzz_records(seed, n):
             mapq=None if rng.random() < 0.03 else rng.choice([0, 5, 20, 60, 255, 300]),
             readNegativeStrand=rng.random() < 0.5, recordGroupSample="s", readName="r%d" % i))
     return recs
+
+
+def short_operators(recs, limit=255):
+    """Records whose CIGAR elements are all at most `limit` long (the 6-byte wire form carries one length byte)."""
+    import re
+    return [r for r in recs if r.cigar is None or all(int(x) <= limit for x in re.findall(r"\d+", r.cigar))]

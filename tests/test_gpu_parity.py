@@ -304,8 +304,8 @@ def test_wire6_exceptions_reach_the_device(ctx):
     """Reads whose end / l_seq do not follow from their operators (failed extractions, strings longer
     than the CIGAR) travel as exceptions of the 6-byte form; discovery sees the same batch."""
     from avocado_b200 import batch as B
-    from helpers import fuzz_records
-    recs = [r for r in fuzz_records(9, 30000) if r.readMapped]
+    from helpers import fuzz_records, short_operators
+    recs = short_operators([r for r in fuzz_records(9, 30000) if r.readMapped])
     full = B.pack_reads(recs, sort=False)
     wire = B.pack_reads(recs, sort=False)
     assert wire.with_wire6(max_exceptions=wire.n_reads) and len(wire.wire6_exc) > 100

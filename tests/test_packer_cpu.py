@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(L.EXPORTED_SYMBOLS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert C.sizeof(L.ReadBatchStruct) == 4 * 8 + 2 * 4 + 4 * 4 + 6 * 8 + 3 * 8 + 2 * 4
+    assert C.sizeof(L.ReadBatchStruct) == 4 * 8 + 2 * 4 + 4 * 4 + 6 * 8 + 5 * 8 + 2 * 4
 
 
 @pytest.mark.parametrize("name", FIXTURES)
@@ -174,8 +174,11 @@ def test_packer_agrees_with_the_oracle_on_fuzzed_cigar_and_md(oracle):
 def _expand_wire6(b):
     """numpy restatement of the device-side expansion of the 6-byte form -> META_DTYPE records"""
     from avocado_b200 import batch as B
-    w, ops = b.wire6_meta, b.wire_ops.astype(np.int64)
+    w = b.wire6_meta
     n = len(w)
+    k = np.arange(b.n_ops)
+    ops = (b.wire6_oplen[:b.n_ops].astype(np.int64) << 4) | ((b.wire6_opcode[k >> 1] >> ((k & 1) * 4)) & 15)
+    assert np.array_equal(ops, b.ops[:b.n_ops].astype(np.int64))
     m = np.zeros(n, B.META_DTYPE)
     d = (w["dstart_flags"] >> 2).astype(np.int64)
     m["start"] = b.wire6_base + np.cumsum(d)
@@ -212,7 +215,8 @@ def test_wire6_columns_hold_the_same_information():
         want = b.meta[f] & 0xFFFF if f == "qhead" else b.meta[f]      # two of the four head qualities travel
         assert np.array_equal(got[f], want), f
     # fuzzed reads: failed extractions (no operators) and over-long strings become exceptions
-    recs = [r for r in fuzz_records(5, 3000) if r.readMapped]
+    from helpers import short_operators
+    recs = short_operators([r for r in fuzz_records(5, 3000) if r.readMapped])
     fz = B.pack_reads(recs, sort=False)
     assert fz.with_wire6(max_exceptions=fz.n_reads)
     assert 0 < len(fz.wire6_exc) < fz.n_reads
@@ -228,6 +232,9 @@ def test_wire6_columns_hold_the_same_information():
     unsorted = B.synth_host(p)
     unsorted.meta["start"][7] -= 500
     assert not unsorted.with_wire6()
+    long_op = B.synth_host(p)
+    long_op.ops[0] = (300 << 4) | 0                   # an operator that needs more than a length byte
+    assert not long_op.with_wire6() and long_op.with_wire() is not None
 
 
 def test_headers_are_plain_c(tmp_path):

@@ -29,7 +29,7 @@ enum Slot {
   SL_U_START, SL_U_REFLEN, SL_U_ALTLEN, SL_U_COUNT, SL_U_SRC,
   SL_L_POS, SL_L_LENS, SL_L_NIBS, SL_L_SRC, SL_L_BLK, SL_L_HASH,
   SL_C_RBASE, SL_C_BLEN, SL_C_BOFF, SL_C_BUCKETS,
-  SL_G_NBLK, SL_G_SLOT, SL_G_CLO, SL_G_IDX, SL_G_BLK0, SL_G_COMPACT,
+  SL_G_PBASE, SL_G_NBLK, SL_G_SLOT, SL_G_CLO, SL_G_IDX, SL_G_BLK0, SL_G_COMPACT,
   SL_AS_FLAG, SL_AS_JPOS, SL_AS_JR, SL_AS_JIDX, SL_AS_JCOORD, SL_AS_COVER, SL_AS_SCOVER, SL_AS_WCOUNT, SL_AS_WBASE,
   SL_AS_RES, SL_AS_START,
   SL_F_IN, SL_F_OUT,
@@ -487,27 +487,35 @@ int allsites_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const
 // host_payload == 2: the device lists the payload blocks the joined reads need, host threads copy
 // them out of the caller's payload into a dense page-locked array, one DMA brings them back.
 int gather_payload(avo_ctx* ctx, const DReads& R, const DSites& S, const void* d_jlist, const int32_t* d_n_joined,
-                   const uint8_t** compact, const uint32_t** blk0, int* nl) {
+                   const uint8_t** compact, const uint32_t** pbase, const uint32_t** blk0, int* nl) {
   CK(cudaMemcpyAsync(ctx->h_small, d_n_joined, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const int32_t nj = ctx->h_small[0];
   if (nj <= 0) return AVO_OK;
-  void *d_nblk, *d_slot, *d_clo, *d_temp, *d_idx, *d_b0, *d_cmp;
-  CKS(get_buf(ctx, SL_G_NBLK, (size_t)(nj + 1) * 4, &d_nblk));
-  CKS(get_buf(ctx, SL_G_SLOT, (size_t)(nj + 1) * 4, &d_slot));
-  CKS(get_buf(ctx, SL_G_CLO, (size_t)(nj + 1) * 4, &d_clo));
-  const size_t tb = call_gather_temp_bytes(nj);
+  void *d_pbase, *d_nblk, *d_slot, *d_clo, *d_temp, *d_idx, *d_b0, *d_cmp;
+  CKS(get_buf(ctx, SL_G_PBASE, (size_t)(nj + 1) * 4, &d_pbase));
+  size_t tb = call_gather_temp_bytes(nj);
   CKS(get_buf(ctx, SL_TEMP, tb, &d_temp));
-  CK(launch_call_gather_plan(R, S, d_jlist, nj, (uint32_t*)d_nblk, (uint32_t*)d_slot, (uint32_t*)d_clo, d_temp, tb,
-                             ctx->stream, nl));
-  CK(cudaMemcpyAsync(ctx->h_small, (uint32_t*)d_slot + nj, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(launch_call_pairs(d_jlist, nj, (uint32_t*)d_pbase, d_temp, tb, ctx->stream, nl));
+  CK(cudaMemcpyAsync(ctx->h_small, (uint32_t*)d_pbase + nj, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const int64_t np = (int64_t)(uint32_t)ctx->h_small[0];      // (read, site) pairs
+  CKS(get_buf(ctx, SL_G_NBLK, (size_t)(np + 1) * 4, &d_nblk));
+  CKS(get_buf(ctx, SL_G_SLOT, (size_t)(np + 1) * 4, &d_slot));
+  CKS(get_buf(ctx, SL_G_CLO, (size_t)(np + 1) * 4, &d_clo));
+  tb = call_gather_temp_bytes(np);
+  CKS(get_buf(ctx, SL_TEMP, tb, &d_temp));
+  CK(launch_call_gather_plan(R, S, d_jlist, nj, (const uint32_t*)d_pbase, np, (uint32_t*)d_nblk, (uint32_t*)d_slot,
+                             (uint32_t*)d_clo, d_temp, tb, ctx->stream, nl));
+  CK(cudaMemcpyAsync(ctx->h_small, (uint32_t*)d_slot + np, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const size_t total = (size_t)(uint32_t)ctx->h_small[0];
-  CKS(get_buf(ctx, SL_G_BLK0, (size_t)nj * 4, &d_b0));
+  CKS(get_buf(ctx, SL_G_BLK0, (size_t)(np + 1) * 4, &d_b0));
   CKS(get_buf(ctx, SL_G_IDX, total * 4, &d_idx));
   CKS(get_buf(ctx, SL_G_COMPACT, total * AVO_BLOCK_BYTES, &d_cmp));
-  CK(launch_call_blocklist(R, d_jlist, nj, (const uint32_t*)d_nblk, (const uint32_t*)d_slot, (const uint32_t*)d_clo,
-                           (uint32_t*)d_idx, (uint32_t*)d_b0, ctx->stream, nl));
+  CK(launch_call_blocklist(R, d_jlist, nj, (const uint32_t*)d_pbase, (const uint32_t*)d_nblk, (const uint32_t*)d_slot,
+                           (const uint32_t*)d_clo, (uint32_t*)d_idx, (uint32_t*)d_b0, ctx->stream, nl));
+  *pbase = (const uint32_t*)d_pbase;
   *blk0 = (const uint32_t*)d_b0;
   *compact = (const uint8_t*)d_cmp;
   if (total == 0) return AVO_OK;
@@ -682,10 +690,10 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
     CKS(get_buf(ctx, SL_C_BUCKETS, n_slots * 4, &d_buckets));
     CK(launch_call_join(R, S, X, hs.max_span, (uint32_t*)d_buckets, n_slots, d_jlist, small + 8, ctx->num_sms, ctx->stream, &nl));
     const uint8_t* d_compact = nullptr;
-    const uint32_t* d_blk0 = nullptr;
-    if (ctx->gather_src && work) CKS(gather_payload(ctx, R, S, d_jlist, small + 8, &d_compact, &d_blk0, &nl));
+    const uint32_t *d_pbase = nullptr, *d_blk0 = nullptr;
+    if (ctx->gather_src && work) CKS(gather_payload(ctx, R, S, d_jlist, small + 8, &d_compact, &d_pbase, &d_blk0, &nl));
     CK(launch_call_observe(R, S, C, P, D, (const int32_t*)d_rbase, (const uint32_t*)d_blen, (const uint64_t*)d_boff,
-                           (uint32_t*)d_buckets, n_slots, d_jlist, small + 8, d_compact, d_blk0, ctx->num_sms,
+                           (uint32_t*)d_buckets, n_slots, d_jlist, small + 8, d_compact, d_pbase, d_blk0, ctx->num_sms,
                            ctx->stream, &nl));
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
     const size_t mark = ctx->pending.size(), used = ctx->h_stage_used;

@@ -71,12 +71,15 @@ __global__ void k_site_buckets(DReads R, DSites S, DIndex X, int32_t max_span, i
 
 // Everything one joined read contributes: one record per site of its Forest range [a, b) that it
 // observes, written to that site's bucket (BG:195-393 incl. the other-alt pass and copy number).
-// blk0 = first payload block of the read: its seq_off, or, when the payload was gathered on the
-// host, the read's slot in the compact block array minus the first block gathered for it.
+// pair_blk0 (host-gathered payload only): for site a + k of the read, the slot of the blocks gathered
+// for that (read, site) pair in the compact array minus the first block gathered -- what takes the
+// place of the read's seq_off while that site is classified.  PAIRS is a template parameter so that
+// the device-resident route compiles to a kernel that never looks at pair_blk0.
+template <bool PAIRS>
 __device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
                              int32_t r, int32_t a, int32_t b, const int32_t* __restrict__ rbase,
                              const uint64_t* __restrict__ boff, uint32_t* __restrict__ buckets,
-                             uint64_t n_slots, bool blk0_given = false, uint32_t blk0 = 0) {
+                             uint64_t n_slots, const uint32_t* __restrict__ pair_blk0) {
   const MetaA ma = load_meta_a(R.meta, r);
   const MetaB mb = load_meta_b(R.meta, r);
   // observeRead throws for such reads (BG:385-391: skipped); no operators -> no observations
@@ -86,9 +89,13 @@ __device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, co
   rc.end = ma.end;
   rc.ob = ma.op_off;
   rc.no = mb.n_ops;
-  rc.sb = blk0_given ? blk0 : ma.seq_off;
+  rc.sb = ma.seq_off;
   rc.mapq = mb.mapq;
   rc.fwd = !(mb.flags & AVO_READ_NEGATIVE_STRAND);
+  auto classify_at = [&](int32_t j) {
+    if (PAIRS) rc.sb = pair_blk0[j - a];
+    return classify_site(R, rc, S, j);
+  };
 
   const int ns = b - a;
   uint32_t cats[MAX_LOCAL_SITES];
@@ -96,26 +103,26 @@ __device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, co
   const bool cached = ns <= MAX_LOCAL_SITES;
   if (cached) {
     for (int j = 0; j < ns; ++j) {
-      const Cls c = classify_site(R, rc, S, a + j);
+      const Cls c = classify_at(a + j);
       if (c.cat == CAT_EXC) return;                       // BG:385-391: the whole read is skipped
       cats[j] = c.cat;
       qs[j] = c.q;
     }
   } else {
     for (int j = 0; j < ns; ++j)
-      if (classify_site(R, rc, S, a + j).cat == CAT_EXC) return;
+      if (classify_at(a + j).cat == CAT_EXC) return;
   }
 
   const int mq = min(P.max_mapq, (int)rc.mapq);           // BG:452
   for (int32_t j = a; j < b; ++j) {
     Cls c;
-    if (cached) { c.cat = cats[j - a]; c.q = qs[j - a]; } else c = classify_site(R, rc, S, j);
+    if (cached) { c.cat = cats[j - a]; c.q = qs[j - a]; } else c = classify_at(j);
     if (c.cat == CAT_NONE) continue;
     const int32_t js = __ldg(S.start + j), je = __ldg(S.end + j);
     if (c.cat == CAT_NONREF) {                            // BG:359-373 other-alt pass
       for (int32_t k = a; k < b; ++k) {
         if (!(__ldg(S.start + k) < je && __ldg(S.end + k) > js)) continue;
-        const uint32_t kc = cached ? cats[k - a] : classify_site(R, rc, S, k).cat;
+        const uint32_t kc = cached ? cats[k - a] : classify_at(k).cat;
         if (kc == CAT_ALT) { c.cat = CAT_OTHER; break; }
       }
     }
@@ -218,18 +225,21 @@ k_call_join(DReads R, DSites S, DIndex X, int32_t max_span, JoinedRead* __restri
   if (cnt > 0) flush();
 }
 
-// Observation + classification: one thread per joined read.
+// Observation + classification: one thread per joined read.  GATHERED: the payload is the dense array
+// the host gathered (compact), addressed per (read, site) pair through pbase / blk0.
+template <bool GATHERED>
 __global__ void __launch_bounds__(OBS_THREADS, AVO_CALL_MINB)
 k_call_observe(DReads R, DSites S, DCnv C, DCallParams P, const JoinedRead* __restrict__ list,
                const int32_t* __restrict__ n_list, const int32_t* __restrict__ rbase,
                const uint64_t* __restrict__ boff, uint32_t* __restrict__ buckets, uint64_t n_slots,
-               const uint8_t* __restrict__ compact, const uint32_t* __restrict__ blk0) {
+               const uint8_t* __restrict__ compact, const uint32_t* __restrict__ pbase,
+               const uint32_t* __restrict__ blk0) {
   const int32_t n = *n_list;
-  const bool gathered = compact != nullptr;
-  if (gathered) R.payload = compact;
+  if (GATHERED) R.payload = compact;
   for (int32_t i = blockIdx.x * OBS_THREADS + threadIdx.x; i < n; i += gridDim.x * OBS_THREADS) {
     const JoinedRead j = list[i];
-    observe_read(R, S, C, P, j.r, j.a, j.b, rbase, boff, buckets, n_slots, gathered, gathered ? blk0[i] : 0u);
+    observe_read<GATHERED>(R, S, C, P, j.r, j.a, j.b, rbase, boff, buckets, n_slots,
+                           GATHERED ? blk0 + pbase[i] : nullptr);
   }
 }
 
@@ -240,81 +250,88 @@ k_call_observe(DReads R, DSites S, DCnv C, DCallParams P, const JoinedRead* __re
 // a dense array with its own cores, and one DMA brings them over.
 //
 // Read indices classify() touches for site [vs, ve): the aligned bases at reference positions in
-// [vs, ve) and the bases of insertions at positions in (vs, ve] (avo_observe.cuh).  Per joined read
-// the union over its sites is gathered as one range of blocks.
-__device__ bool read_index_range(const DReads& R, const DSites& S, uint32_t ob, uint32_t no, int32_t start,
-                                 int32_t a, int32_t b, uint32_t* lo_out, uint32_t* hi_out) {
+// [vs, ve) and the bases of insertions at positions in (vs, ve] (avo_observe.cuh): one range of
+// blocks per (read, site) pair.  pbase[i] = pairs of the joined reads before i (pair = site of the
+// read's Forest range, observed or not).
+__device__ bool read_index_range(const DReads& R, uint32_t ob, uint32_t no, int32_t start, int32_t vs, int32_t ve,
+                                 uint32_t* lo_out, uint32_t* hi_out) {
   uint32_t lo = 0xFFFFFFFFu, hi = 0;
   bool any = false;
-  for (int32_t j = a; j < b; ++j) {
-    const int32_t vs = __ldg(S.start + j), ve = vs + __ldg(S.ref_len + j);
-    int32_t pos = start;
-    uint32_t ridx = 0;
-    for (uint32_t k = 0; k < no; ++k) {
-      const uint32_t op = __ldg(R.ops + ob + k);
-      const int len = (int)(op >> 4);
-      const uint32_t code = op & 15u;
-      if (code == AVO_OP_SOFTCLIP) { ridx += len; continue; }
-      if (code == AVO_OP_HARDCLIP) continue;
-      if (code == AVO_OP_MATCH || code == AVO_OP_MISMATCH) {
-        const int32_t l = max(pos, vs), h = min(pos + len, ve);
-        if (l < h) {
-          lo = min(lo, ridx + (uint32_t)(l - pos));
-          hi = max(hi, ridx + (uint32_t)(h - 1 - pos));
-          any = true;
-        }
-        pos += len; ridx += len;
-      } else if (code == AVO_OP_INS) {
-        if (pos - 1 < ve && pos > vs && len > 0) {
-          lo = min(lo, ridx);
-          hi = max(hi, ridx + (uint32_t)len - 1);
-          any = true;
-        }
-        ridx += len;
-      } else if (code == AVO_OP_DEL) {
-        pos += len;
+  int32_t pos = start;
+  uint32_t ridx = 0;
+  for (uint32_t k = 0; k < no; ++k) {
+    const uint32_t op = __ldg(R.ops + ob + k);
+    const int len = (int)(op >> 4);
+    const uint32_t code = op & 15u;
+    if (code == AVO_OP_SOFTCLIP) { ridx += len; continue; }
+    if (code == AVO_OP_HARDCLIP) continue;
+    if (code == AVO_OP_MATCH || code == AVO_OP_MISMATCH) {
+      const int32_t l = max(pos, vs), h = min(pos + len, ve);
+      if (l < h) {
+        lo = min(lo, ridx + (uint32_t)(l - pos));
+        hi = max(hi, ridx + (uint32_t)(h - 1 - pos));
+        any = true;
       }
-      if (pos > ve) break;
+      pos += len; ridx += len;
+    } else if (code == AVO_OP_INS) {
+      if (pos - 1 < ve && pos > vs && len > 0) {
+        lo = min(lo, ridx);
+        hi = max(hi, ridx + (uint32_t)len - 1);
+        any = true;
+      }
+      ridx += len;
+    } else if (code == AVO_OP_DEL) {
+      pos += len;
     }
+    if (pos > ve) break;
   }
   *lo_out = lo; *hi_out = hi;
   return any;
 }
 
+struct PairsOf {
+  __host__ __device__ uint32_t operator()(const JoinedRead& j) const { return (uint32_t)(j.b - j.a); }
+};
+
 __global__ void __launch_bounds__(256)
-k_call_ranges(DReads R, DSites S, const JoinedRead* __restrict__ list, int32_t n, uint32_t* __restrict__ nblk,
-              uint32_t* __restrict__ clo) {
+k_call_ranges(DReads R, DSites S, const JoinedRead* __restrict__ list, int32_t n, const uint32_t* __restrict__ pbase,
+              uint32_t* __restrict__ nblk, uint32_t* __restrict__ clo) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
-  uint32_t cnt = 0, c0 = 0;
-  if (i < n) {
-    const JoinedRead j = list[i];
-    const MetaA ma = load_meta_a(R.meta, j.r);
-    const MetaB mb = load_meta_b(R.meta, j.r);
-    uint32_t lo, hi;
-    if (!(mb.flags & AVO_READ_SKIP_CALL) && mb.n_ops != 0 &&
-        read_index_range(R, S, ma.op_off, mb.n_ops, ma.start, j.a, j.b, &lo, &hi)) {
-      // never past the read's own blocks (an operator list longer than the sequence is caught by the
-      // packer; this keeps a malformed batch from indexing another read's payload)
-      const uint32_t last = mb.l_seq ? (mb.l_seq - 1) / AVO_BLOCK_BASES : 0u;
+  if (i == n) { nblk[pbase[n]] = 0; return; }     // the scan's last element is the total
+  const JoinedRead j = list[i];
+  const MetaA ma = load_meta_a(R.meta, j.r);
+  const MetaB mb = load_meta_b(R.meta, j.r);
+  const bool skip = (mb.flags & AVO_READ_SKIP_CALL) || mb.n_ops == 0;
+  // never past the read's own blocks (an operator list longer than the sequence is caught by the
+  // packer; this keeps a malformed batch from indexing another read's payload)
+  const uint32_t last = mb.l_seq ? (mb.l_seq - 1) / AVO_BLOCK_BASES : 0u;
+  for (int32_t s = j.a; s < j.b; ++s) {
+    uint32_t cnt = 0, c0 = 0, lo, hi;
+    const int32_t vs = __ldg(S.start + s);
+    if (!skip && read_index_range(R, ma.op_off, mb.n_ops, ma.start, vs, vs + __ldg(S.ref_len + s), &lo, &hi)) {
       c0 = min(lo / AVO_BLOCK_BASES, last);
       cnt = min(hi / AVO_BLOCK_BASES, last) - c0 + 1;
     }
+    const uint32_t p = pbase[i] + (uint32_t)(s - j.a);
+    nblk[p] = cnt;
+    clo[p] = c0;
   }
-  nblk[i] = cnt;       // nblk[n] = 0: the scan's last element is the total
-  clo[i] = c0;
 }
 
 __global__ void __launch_bounds__(256)
-k_call_blocklist(DReads R, const JoinedRead* __restrict__ list, int32_t n, const uint32_t* __restrict__ nblk,
-                 const uint32_t* __restrict__ slot, const uint32_t* __restrict__ clo, uint32_t* __restrict__ idx,
-                 uint32_t* __restrict__ blk0) {
+k_call_blocklist(DReads R, const JoinedRead* __restrict__ list, int32_t n, const uint32_t* __restrict__ pbase,
+                 const uint32_t* __restrict__ nblk, const uint32_t* __restrict__ slot, const uint32_t* __restrict__ clo,
+                 uint32_t* __restrict__ idx, uint32_t* __restrict__ blk0) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t s = slot[i], c0 = clo[i], cnt = nblk[i];
-  const uint32_t seq_off = load_meta_a(R.meta, list[i].r).seq_off;
-  for (uint32_t k = 0; k < cnt; ++k) idx[s + k] = seq_off + c0 + k;
-  blk0[i] = s - c0;    // block c of the read lives at compact[(s - c0) + c]: 32-bit wrap-around is fine
+  const JoinedRead j = list[i];
+  const uint32_t seq_off = load_meta_a(R.meta, j.r).seq_off;
+  for (uint32_t p = pbase[i]; p < pbase[i] + (uint32_t)(j.b - j.a); ++p) {
+    const uint32_t s = slot[p], c0 = clo[p], cnt = nblk[p];
+    for (uint32_t k = 0; k < cnt; ++k) idx[s + k] = seq_off + c0 + k;
+    blk0[p] = s - c0;  // block c of the read lives at compact[(s - c0) + c]: 32-bit wrap-around is fine
+  }
 }
 
 // ---- per-site ordered reduction + genotype ---------------------------------------------------------
@@ -431,45 +448,59 @@ cudaError_t launch_call_join(const DReads& R, const DSites& S, const DIndex& X, 
   return cudaGetLastError();
 }
 
-size_t call_gather_temp_bytes(int32_t n_joined) {
+size_t call_gather_temp_bytes(int64_t n) {
   size_t a = 0;
-  cub::DeviceScan::ExclusiveSum((void*)nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, n_joined + 1);
+  cub::DeviceScan::ExclusiveSum((void*)nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(n + 1));
   return a + 256;
 }
 
-// nblk / slot / clo: [n_joined + 1]; slot[n_joined] (device) = number of blocks to gather
+// pbase: [n_joined + 1] pairs before every joined read; pbase[n_joined] (device) = number of pairs
+cudaError_t launch_call_pairs(const void* joined_list, int32_t n_joined, uint32_t* pbase, void* d_temp,
+                              size_t temp_bytes, cudaStream_t s, int* n_launches) {
+  cub::TransformInputIterator<uint32_t, PairsOf, const JoinedRead*> it((const JoinedRead*)joined_list, PairsOf());
+  // the element past the list is never read by the exclusive sum's last output
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, it, pbase, n_joined + 1, s);
+  if (n_launches) *n_launches += 1;
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+// nblk / slot: [n_pairs + 1], clo: [n_pairs]; slot[n_pairs] (device) = number of blocks to gather
 cudaError_t launch_call_gather_plan(const DReads& R, const DSites& S, const void* joined_list, int32_t n_joined,
-                                    uint32_t* nblk, uint32_t* slot, uint32_t* clo, void* d_temp, size_t temp_bytes,
-                                    cudaStream_t s, int* n_launches) {
-  k_call_ranges<<<(n_joined + 1 + 255) / 256, 256, 0, s>>>(R, S, (const JoinedRead*)joined_list, n_joined, nblk, clo);
-  cudaError_t e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, (const uint32_t*)nblk, slot, n_joined + 1, s);
+                                    const uint32_t* pbase, int64_t n_pairs, uint32_t* nblk, uint32_t* slot,
+                                    uint32_t* clo, void* d_temp, size_t temp_bytes, cudaStream_t s, int* n_launches) {
+  k_call_ranges<<<(n_joined + 1 + 255) / 256, 256, 0, s>>>(R, S, (const JoinedRead*)joined_list, n_joined, pbase, nblk,
+                                                          clo);
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, (const uint32_t*)nblk, slot, (int)(n_pairs + 1), s);
   if (e != cudaSuccess) return e;
   if (n_launches) *n_launches += 2;
   return cudaGetLastError();
 }
 
-cudaError_t launch_call_blocklist(const DReads& R, const void* joined_list, int32_t n_joined, const uint32_t* nblk,
-                                  const uint32_t* slot, const uint32_t* clo, uint32_t* idx, uint32_t* blk0,
-                                  cudaStream_t s, int* n_launches) {
+cudaError_t launch_call_blocklist(const DReads& R, const void* joined_list, int32_t n_joined, const uint32_t* pbase,
+                                  const uint32_t* nblk, const uint32_t* slot, const uint32_t* clo, uint32_t* idx,
+                                  uint32_t* blk0, cudaStream_t s, int* n_launches) {
   if (n_joined <= 0) return cudaSuccess;
-  k_call_blocklist<<<(n_joined + 255) / 256, 256, 0, s>>>(R, (const JoinedRead*)joined_list, n_joined, nblk, slot, clo,
-                                                          idx, blk0);
+  k_call_blocklist<<<(n_joined + 255) / 256, 256, 0, s>>>(R, (const JoinedRead*)joined_list, n_joined, pbase, nblk, slot,
+                                                          clo, idx, blk0);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }
 
-// compact / blk0: the host-gathered payload blocks and every joined read's first-block slot, or NULL
+// compact / pbase / blk0: the host-gathered payload blocks, the first pair of every joined read and
+// every pair's block offset, or NULL
 cudaError_t launch_call_observe(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
                                 const DResults& out, const int32_t* rbase, const uint32_t* blen,
                                 const uint64_t* boff, uint32_t* buckets, size_t n_slots, const void* joined_list,
-                                const int32_t* d_counter, const uint8_t* compact, const uint32_t* blk0,
-                                int num_sms, cudaStream_t s, int* n_launches) {
+                                const int32_t* d_counter, const uint8_t* compact, const uint32_t* pbase,
+                                const uint32_t* blk0, int num_sms, cudaStream_t s, int* n_launches) {
   if (R.n == 0 || S.c_hi <= S.c_lo) return cudaSuccess;
   int blocks_per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_call_observe, OBS_THREADS, 0);
+  auto kernel = compact ? k_call_observe<true> : k_call_observe<false>;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, OBS_THREADS, 0);
   if (e != cudaSuccess) return e;
-  k_call_observe<<<num_sms * max(1, blocks_per_sm), OBS_THREADS, 0, s>>>(
-      R, S, C, P, (const JoinedRead*)joined_list, d_counter, rbase, boff, buckets, (uint64_t)n_slots, compact, blk0);
+  kernel<<<num_sms * max(1, blocks_per_sm), OBS_THREADS, 0, s>>>(
+      R, S, C, P, (const JoinedRead*)joined_list, d_counter, rbase, boff, buckets, (uint64_t)n_slots, compact, pbase,
+      blk0);
   const int32_t n = S.c_hi - S.c_lo;
   if (P.ns <= 3)
     k_call_reduce<3><<<(n + 127) / 128, 128, 0, s>>>(S, P, out, boff, blen, buckets, (uint64_t)n_slots);

@@ -223,18 +223,21 @@ cudaError_t launch_call_buckets(const DReads& R, const DSites& S, const DIndex& 
 cudaError_t launch_call_join(const DReads& R, const DSites& S, const DIndex& X, int32_t max_span /* >= every end - start */,
                              uint32_t* buckets, size_t n_slots, void* joined_list /* 12 B x n_reads */,
                              int32_t* d_counter, int num_sms, cudaStream_t s, int* n_launches);
-size_t call_gather_temp_bytes(int32_t n_joined);
+size_t call_gather_temp_bytes(int64_t n);
+cudaError_t launch_call_pairs(const void* joined_list, int32_t n_joined, uint32_t* pbase /* n_joined + 1 */,
+                              void* d_temp, size_t temp_bytes, cudaStream_t s, int* n_launches);
 cudaError_t launch_call_gather_plan(const DReads& R, const DSites& S, const void* joined_list, int32_t n_joined,
-                                    uint32_t* nblk, uint32_t* slot, uint32_t* clo, void* d_temp, size_t temp_bytes,
-                                    cudaStream_t s, int* n_launches);
-cudaError_t launch_call_blocklist(const DReads& R, const void* joined_list, int32_t n_joined, const uint32_t* nblk,
-                                  const uint32_t* slot, const uint32_t* clo, uint32_t* idx, uint32_t* blk0,
-                                  cudaStream_t s, int* n_launches);
+                                    const uint32_t* pbase, int64_t n_pairs, uint32_t* nblk, uint32_t* slot,
+                                    uint32_t* clo, void* d_temp, size_t temp_bytes, cudaStream_t s, int* n_launches);
+cudaError_t launch_call_blocklist(const DReads& R, const void* joined_list, int32_t n_joined, const uint32_t* pbase,
+                                  const uint32_t* nblk, const uint32_t* slot, const uint32_t* clo, uint32_t* idx,
+                                  uint32_t* blk0, cudaStream_t s, int* n_launches);
 cudaError_t launch_call_observe(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
                                 const DResults& out, const int32_t* rbase, const uint32_t* blen,
                                 const uint64_t* boff, uint32_t* buckets, size_t n_slots /* capacity of buckets */,
                                 const void* joined_list, const int32_t* d_counter, const uint8_t* compact,
-                                const uint32_t* blk0, int num_sms, cudaStream_t s, int* n_launches);
+                                const uint32_t* pbase, const uint32_t* blk0, int num_sms, cudaStream_t s,
+                                int* n_launches);
 
 // scoreAllSites reference-model rows (avo_allsites.cu).  All pointers are device scratch.
 struct AllSitesPlan {

@@ -146,7 +146,8 @@ class FilterOutStruct(C.Structure):
 
 class SampleRowsStruct(C.Structure):
     _fields_ = [("variants", C.POINTER(SitesStruct)), ("variant_rows", C.POINTER(SiteResultsStruct)),
-                ("n_ref_model", C.c_int64), ("ref_model_start", P), ("ref_model_rows", C.POINTER(SiteResultsStruct))]
+                ("n_ref_model", C.c_int64), ("ref_model_start", P), ("ref_model_rows", C.POINTER(SiteResultsStruct)),
+                ("ref_model_len", P), ("ref_model_max_len", C.c_int32), ("reserved", C.c_int32)]
 
 
 SQUARE_OUT_COLUMNS = [("kind", "uint8", 1), ("src", "int32", 1), ("n_alt", "int32", 1), ("n_ref", "int32", 1),

@@ -1244,8 +1244,22 @@ int avo_square_off(avo_ctx* ctx, const avo_sites* cohort, const avo_sample_rows*
   } else {
     max_ref_len = 1 << 16;    // device tables: bound of the allele length (uint16 in discovery keys)
   }
+  int32_t max_block_len = 1;
+  if (sample->ref_model_len) {
+    max_block_len = sample->ref_model_max_len;
+    if (mem == AVO_MEM_HOST) {
+      for (size_t k = 0; k < nr; ++k) {
+        if (sample->ref_model_len[k] < 1) return fail(ctx, AVO_E_INVALID, "ref_model_len[%zu] < 1", k);
+        max_block_len = std::max(max_block_len, sample->ref_model_len[k]);
+      }
+    } else if (max_block_len <= 0) {
+      max_block_len = 1 << 16;
+    }
+  }
   DSquareIn I{};
   I.n_sites = (int32_t)N; I.n_v = (int32_t)nv; I.n_r = (int32_t)nr; I.ns = ns; I.v_max_ref_len = max_ref_len;
+  I.r_max_len = max_block_len;
+  I.r_len = (const int32_t*)in(sample->ref_model_len, nr * 4);
   I.c_start = (const int32_t*)in(cohort->start, N * 4); I.c_ref_len = (const int32_t*)in(cohort->ref_len, N * 4);
   I.c_alt_len = (const int32_t*)in(cohort->alt_len, N * 4);
   I.c_allele_off = (const uint32_t*)in(cohort->allele_off, (N + 1) * 4);

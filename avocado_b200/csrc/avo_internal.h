@@ -125,11 +125,11 @@ cudaError_t launch_filter_genotypes(const DFilterIn& I, const avo_filter_params&
 
 // ---- SquareOffReferenceModel (avo_squareoff.cu) ---------------------------------------------------
 struct DSquareIn {
-  int32_t n_sites, n_v, n_r, ns, v_max_ref_len;
+  int32_t n_sites, n_v, n_r, ns, v_max_ref_len, r_max_len;
   const int32_t *c_start, *c_ref_len, *c_alt_len; const uint32_t* c_allele_off; const uint8_t* c_alleles4;
   const int32_t *v_start, *v_ref_len, *v_alt_len; const uint32_t* v_allele_off; const uint8_t* v_alleles4;
   const uint8_t* v_emitted; const int32_t *v_n_alt, *v_n_ref, *v_n_other; const double *v_gl, *v_nonref_gl;
-  const int32_t* r_start; const uint8_t* r_emitted; const int32_t *r_n_alt, *r_n_ref, *r_n_other;
+  const int32_t *r_start, *r_len /* NULL: 1 */; const uint8_t* r_emitted; const int32_t *r_n_alt, *r_n_ref, *r_n_other;
   const double* r_nonref_gl;
 };
 struct DSquareOut {

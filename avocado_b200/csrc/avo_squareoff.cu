@@ -11,7 +11,8 @@
 //                                 (start, end), a genotype with an alternate allele before a
 //                                 reference-model one.
 // One thread per cohort site; the sample's variant rows and reference-model rows are both sorted
-// by start, so both look-ups are binary searches plus a short scan.
+// by start, so both look-ups are binary searches plus a short scan.  Reference-model rows cover one
+// position (what avo_call_all_sites emits) or, with r_len, a block of positions (banded gVCFs).
 #include "avo_device.cuh"
 
 namespace avo {
@@ -49,11 +50,22 @@ __global__ void k_square_off(DSquareIn I, DSquareOut O) {
       if (!I.v_emitted[k] || e <= vs) continue;
       if (s < bs || (s == bs && e < be)) { bs = s; be = e; kind = AVO_SQ_EXCISED_VARIANT; src = k; }
     }
-    for (int32_t k = lower_bound_i32(I.r_start, 0, I.n_r, vs); k < I.n_r && __ldg(I.r_start + k) < ve; ++k) {
-      if (!I.r_emitted[k]) continue;
-      const int32_t s = __ldg(I.r_start + k), e = s + 1;
-      if (s < bs || (s == bs && e < be)) { bs = s; be = e; kind = AVO_SQ_EXCISED_REF_MODEL; src = k; }
-      break;                                  // later reference-model rows start later
+    if (!I.r_len) {
+      for (int32_t k = lower_bound_i32(I.r_start, 0, I.n_r, vs); k < I.n_r && __ldg(I.r_start + k) < ve; ++k) {
+        if (!I.r_emitted[k]) continue;
+        const int32_t s = __ldg(I.r_start + k), e = s + 1;
+        if (s < bs || (s == bs && e < be)) { bs = s; be = e; kind = AVO_SQ_EXCISED_REF_MODEL; src = k; }
+        break;                                // later reference-model rows start later
+      }
+    } else {
+      // blocks: a row that starts before the site may still reach it
+      const int64_t rlo = (int64_t)vs - I.r_max_len + 1;
+      for (int32_t k = lower_bound_i32(I.r_start, 0, I.n_r, (int32_t)max(rlo, (int64_t)INT32_MIN));
+           k < I.n_r && __ldg(I.r_start + k) < ve; ++k) {
+        const int32_t s = __ldg(I.r_start + k), e = s + __ldg(I.r_len + k);
+        if (!I.r_emitted[k] || e <= vs) continue;
+        if (s < bs || (s == bs && e < be)) { bs = s; be = e; kind = AVO_SQ_EXCISED_REF_MODEL; src = k; }
+      }
     }
   }
   O.kind[j] = (uint8_t)kind;

@@ -65,9 +65,12 @@ def _results_struct(cols, n, ns, mem):
 
 
 def square_off_packed(ctx, cohort: SiteTable, sample_sites: SiteTable, sample_cols: Dict[str, object],
-                      ref_start, ref_cols: Dict[str, object], n_states: int) -> Dict[str, object]:
+                      ref_start, ref_cols: Dict[str, object], n_states: int, ref_len=None,
+                      ref_max_len: int = 0) -> Dict[str, object]:
     """avo_square_off for one sample: `sample_sites` / `sample_cols` are the table and variant rows
     given to / returned by call_all_sites_packed, `ref_start` / `ref_cols` its reference-model rows.
+    `ref_len` (optional): the rows are blocks covering [start, start + len) as in a banded gVCF;
+    `ref_max_len` bounds the lengths of device-resident blocks.
     Returns the SQUARE_OUT_COLUMNS (one row per cohort site)."""
     dev = cohort.on_device
     mem = L.MEM_DEVICE if dev else L.MEM_HOST
@@ -77,9 +80,13 @@ def square_off_packed(ctx, cohort: SiteTable, sample_sites: SiteTable, sample_co
     rr, k2 = _results_struct(ref_cols, n_r, n_states, mem)
     if not dev:
         ref_start = np.ascontiguousarray(ref_start, np.int32)
+        if ref_len is not None:
+            ref_len = np.ascontiguousarray(ref_len, np.int32)
     sr = L.SampleRowsStruct()
     sr.variants, sr.variant_rows = C.pointer(vs), C.pointer(vr)
     sr.n_ref_model, sr.ref_model_start, sr.ref_model_rows = n_r, _ptr(ref_start), C.pointer(rr)
+    if ref_len is not None:
+        sr.ref_model_len, sr.ref_model_max_len = _ptr(ref_len), int(ref_max_len)
     out = L.SquareOutStruct()
     out.n_sites, out.n_states, out.mem = cohort.n, n_states, mem
     res = {}

@@ -387,6 +387,12 @@ typedef struct {
   int64_t n_ref_model;                /* the sample's reference-model rows */
   const int32_t* ref_model_start;     /* [n_ref_model] ascending */
   const avo_site_results* ref_model_rows;
+  /* Reference-model BLOCKS (banded gVCFs, e.g. rows that did not come from avo_call_all_sites):
+   * row k covers [start, start + ref_model_len[k]).  NULL = every row covers one position.
+   * ref_model_max_len bounds the lengths (0 with device tables = "unknown": 65536 is assumed). */
+  const int32_t* ref_model_len;       /* [n_ref_model] >= 1, or NULL */
+  int32_t ref_model_max_len;
+  int32_t reserved;
 } avo_sample_rows;
 typedef struct {
   int64_t n_sites;   /* == cohort->n */

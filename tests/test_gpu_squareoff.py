@@ -105,3 +105,91 @@ def test_gvcf_cohort_square_off_and_joint(oracle, ctx):
             assert abs(jo["quality"][i] - site["quality"]) <= 1e-6 * max(1.0, abs(site["quality"]))
             n_checked += 1
     assert n_checked > 20
+
+
+def test_banded_reference_model_blocks(oracle, ctx):
+    """Reference-model rows as BLOCKS (a banded gVCF, SquareOffReferenceModel.scala:224-232 takes any
+    genotype whose region overlaps the site): the per-position rows of one sample are merged into
+    blocks of 1-40 positions and squared off against another sample's variants."""
+    import torch
+    from avocado_b200 import _lib as L, batch as B
+    from avocado_b200.squareoff import square_off_packed
+    contig_len, ns = 30000, 3
+    tabs = []
+    for s in range(2):
+        p = B.synth_params(seed=57, sample=s + 1, n_reads_total=contig_len * 10 // 150, contig_len=contig_len, first_pos=2000)
+        b = B.synth_host(p)
+        sites = ctx.discover_packed(b, phred=25, min_obs=2)
+        tabs.append((sites,) + tuple(ctx.call_all_sites_packed(b, sites)))
+    sites, cols, rstart, rcols = tabs[0]
+    rstart = np.asarray(rstart)
+    r_em = np.asarray(rcols["emitted"]).astype(bool)
+    # blocks: runs of consecutive emitted positions cut at random lengths; the first row stands for the block
+    rng = np.random.default_rng(5)
+    first, length = [], []
+    k = 0
+    while k < len(rstart):
+        if not r_em[k]:
+            k += 1
+            continue
+        want, n = int(rng.integers(1, 41)), 1
+        while n < want and k + n < len(rstart) and r_em[k + n] and rstart[k + n] == rstart[k] + n:
+            n += 1
+        first.append(k); length.append(n)
+        k += n
+    first, length = np.asarray(first), np.asarray(length, np.int32)
+    assert length.max() > 20 and len(first) > 200
+    bstart = rstart[first].astype(np.int32)
+    bcols = {name: np.ascontiguousarray(np.asarray(a)[first]) for name, a in rcols.items()}
+    # cohort: the other sample's variants (most of them shared) + made-up SNVs and deletions at random
+    # positions, which only reference-model blocks (or nothing) can represent
+    from avocado_b200.records import Variant
+    cohort_v = {v.as_tuple(): v for v in tabs[1][0].to_variants(["ctg"])}
+    for pos in rng.integers(2000, contig_len - 100, 200):
+        n = int(rng.integers(0, 31)) if pos % 4 == 0 else 0
+        v = Variant("ctg", int(pos), int(pos) + n + 1, "A" * (n + 1), "C" if n == 0 else "A")
+        cohort_v.setdefault(v.as_tuple(), v)
+    cohort_v = list(cohort_v.values())
+    table = B.sites_from_variants(cohort_v, {"ctg": 0})
+    table.contig = None
+    cohort = [cohort_v[i] for i in table.order]
+    out = square_off_packed(ctx, table, sites, cols, bstart, bcols, ns, ref_len=length)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    dt = B.SiteTable(table.n, table.n_allele_nibbles, d(table.start), d(table.ref_len), d(table.alt_len),
+                     d(table.allele_off.view(np.int32)), d(table.alleles4))
+    ds = B.SiteTable(sites.n, sites.n_allele_nibbles, d(sites.start), d(sites.ref_len), d(sites.alt_len),
+                     d(sites.allele_off.view(np.int32)), d(sites.alleles4))
+    out_d = square_off_packed(ctx, dt, ds, {k: d(v) for k, v in cols.items()}, d(bstart),
+                              {k: d(v) for k, v in bcols.items()}, ns, ref_len=d(length), ref_max_len=int(length.max()))
+    for k in out:
+        assert np.array_equal(np.asarray(out[k]), out_d[k].cpu().numpy(), equal_nan=True), k
+    sv = sites.to_variants(["ctg"])
+    v_em = np.asarray(cols["emitted"]).astype(bool)
+    bend = bstart + length
+    kinds, reached_from_before = set(), 0
+    for j, v in enumerate(cohort):
+        gts, handle = [], []
+        for k, x in enumerate(sv):
+            if v_em[k] and x.start < v.end + 2 and x.end > v.start - 2:
+                gts.append(("ctg", x.start, x.end, x.referenceAllele, x.alternateAllele)); handle.append(("v", k))
+        for k in np.nonzero((bstart < v.end + 2) & (bend > v.start - 2))[0]:
+            gts.append(("ctg", int(bstart[k]), int(bend[k]), "N", None)); handle.append(("r", int(k)))
+        idx, excised = oracle.square_off_sample(("ctg", v.start, v.end, v.referenceAllele, v.alternateAllele), gts)
+        kind = int(out["kind"][j])
+        kinds.add(kind)
+        if idx < 0:
+            assert kind == L.SQ_ABSENT
+            continue
+        tab, k = handle[idx]
+        want_kind = L.SQ_SCORED if not excised else (L.SQ_EXCISED_VARIANT if tab == "v" else L.SQ_EXCISED_REF_MODEL)
+        assert (kind, int(out["src"][j])) == (want_kind, k), (j, v, gts)
+        src = cols if tab == "v" else bcols
+        assert np.array_equal(out["gl"][j], src["gl"][k] if not excised else src["nonref_gl"][k])
+        assert (int(out["n_alt"][j]), int(out["n_ref"][j]), int(out["n_other"][j])) == \
+            (int(src["n_alt"][k]), int(src["n_ref"][k]), int(src["n_other"][k]))
+        reached_from_before += tab == "r" and bstart[k] < v.start
+    assert {L.SQ_ABSENT, L.SQ_SCORED, L.SQ_EXCISED_REF_MODEL} <= kinds and reached_from_before > 20
+    # a block length below 1 is refused
+    bad = length.copy(); bad[3] = 0
+    with pytest.raises(Exception):
+        square_off_packed(ctx, table, sites, cols, bstart, bcols, ns, ref_len=bad)

@@ -245,3 +245,30 @@ def test_headers_are_plain_c(tmp_path):
     subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-c",
                            os.path.join(root, "examples", "discover_and_call.c"), "-o", obj])
     assert os.path.getsize(obj) > 0
+
+
+def test_ctypes_mirrors_have_the_sizes_of_the_c_structs(tmp_path):
+    """Every struct that crosses the C ABI: sizeof in C (gcc on include/*.h) == ctypes.sizeof of the mirror."""
+    import subprocess
+    from avocado_b200 import _lib as L
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = {
+        "avo_read_batch": L.ReadBatchStruct, "avo_sites": L.SitesStruct, "avo_cnv": L.CnvStruct,
+        "avo_params": L.ParamsStruct, "avo_sites_out": L.SitesOutStruct, "avo_site_results": L.SiteResultsStruct,
+        "avo_ref_model_out": L.RefModelOutStruct, "avo_timing": L.TimingStruct, "avo_text_reads": L.TextReadsStruct,
+        "avo_text_out": L.TextOutStruct, "avo_packed_out": L.PackedOutStruct, "avo_filter_params": L.FilterParamsStruct,
+        "avo_filter_out": L.FilterOutStruct, "avo_sample_rows": L.SampleRowsStruct, "avo_square_out": L.SquareOutStruct,
+        "avo_trio": L.TrioStruct, "avo_joint_in": L.JointInStruct, "avo_joint_out": L.JointOutStruct,
+        "avo_synth_params": L.SynthParamsStruct,
+    }
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "avocado_b200.h"\n#include "avocado_b200_synth.h"\nint main(void) {\n' +
+                   "".join('  printf("%s %%zu\\n", sizeof(%s));\n' % (n, n) for n in pairs) +
+                   '  printf("avo_read_meta %zu\\navo_read_wire %zu\\navo_read_wire6 %zu\\n", sizeof(avo_read_meta), '
+                   'sizeof(avo_read_wire), sizeof(avo_read_wire6));\n  return 0;\n}\n')
+    exe = str(tmp_path / "sizes")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", exe])
+    got = dict(line.split() for line in subprocess.check_output([exe], text=True).splitlines())
+    for name, mirror in pairs.items():
+        assert int(got[name]) == C.sizeof(mirror), name
+    assert (int(got["avo_read_meta"]), int(got["avo_read_wire"]), int(got["avo_read_wire6"])) == (32, 16, 6)

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -967,6 +968,16 @@ int avo_ctx_create(int device, avo_ctx** out) {
   ctx->device = device;
   auto bail = [&](int code) { avo_ctx_destroy(ctx); return code; };
   if (cudaSetDevice(device) != cudaSuccess) return bail(AVO_E_CUDA);
+  // How host threads wait for the device (cudaStreamSynchronize): the CUDA default spins.  With many
+  // contexts per process (one per executor thread) AVO_SYNC=blocking|yield frees the cores for the
+  // threads that gather payload blocks.  Process-wide (it is a device flag); unset = leave as is.
+  if (const char* mode = std::getenv("AVO_SYNC")) {
+    const std::string m(mode);
+    const unsigned f = m == "blocking" ? cudaDeviceScheduleBlockingSync : m == "yield" ? cudaDeviceScheduleYield
+                     : m == "spin" ? cudaDeviceScheduleSpin : cudaDeviceScheduleAuto;
+    cudaSetDeviceFlags(f);
+    cudaGetLastError();
+  }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(AVO_E_CUDA);
   ctx->num_sms = prop.multiProcessorCount;

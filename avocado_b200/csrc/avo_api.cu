@@ -983,7 +983,10 @@ int avo_ctx_create(int device, avo_ctx** out) {
   ctx->num_sms = prop.multiProcessorCount;
   // the kernels gather single 32-byte sectors (one quality / base sector per mismatch or site):
   // ask L2 to fetch 32 B on a miss instead of the default 64 B (a hint; ignored if unsupported)
-  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+#ifndef AVO_L2_FETCH
+#define AVO_L2_FETCH 32
+#endif
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, AVO_L2_FETCH);
   cudaGetLastError();
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(AVO_E_CUDA);
   ctx->stream = ctx->own_stream;

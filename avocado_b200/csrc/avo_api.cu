@@ -670,7 +670,7 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
     CK(launch_call_buckets(R, S, X, hs, (int32_t*)d_rbase, (uint32_t*)d_blen, (uint64_t*)d_boff, d_temp, tb2,
                            ctx->stream, &nl));
   void* d_jlist;
-  CKS(get_buf(ctx, SL_AS_JR, (size_t)R.n * 12, &d_jlist));
+  CKS(get_buf(ctx, SL_AS_JR, (size_t)(R.n + 1) * 12 /* + 1: the pair scan loads one element past the list */, &d_jlist));
   // The number of bucket slots is known on the device.  Instead of waiting for it, the stage runs
   // with the previous call's count (+ 1/8) as capacity, the kernels never write past it, and the
   // count is checked with the results; a stage that ran out of slots is rerun with the exact count.

@@ -76,5 +76,7 @@ class Genotype:
     filtersFailed: Optional[List[str]] = None
     # set by TrioCaller
     phased: bool = False
+    # gVCF blocks read from a file (FORMAT MIN_DP)
+    minReadDepth: Optional[int] = None
     # raw per-site aggregate (Observation), kept for parity checks
     observation: dict = field(default_factory=dict)

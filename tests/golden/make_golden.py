@@ -57,5 +57,22 @@ def main():
         print(name, len(recs), os.path.getsize(path))
 
 
+VCF_FIXTURES = ["trio.1_837214.vcf", "trio.1_837214.phased.vcf", "gvcf_multiallelic.g.vcf", "random.vcf"]
+
+
+def copy_vcfs():
+    """The reference's VCF test resources, byte for byte (they are data: the input and the expected
+    output of TrioCallerSuite.scala:239-251, the inputs of SquareOffReferenceModelSuite.scala:51-76 and
+    HardFilterGenotypesSuite.scala:368-375) -> tests/golden/vcf/."""
+    import shutil
+    out_dir = os.path.join(os.path.dirname(__file__), "vcf")
+    os.makedirs(out_dir, exist_ok=True)
+    for name in VCF_FIXTURES:
+        shutil.copyfile(os.path.join(RES, name), os.path.join(out_dir, name))
+        os.chmod(os.path.join(out_dir, name), 0o644)
+        print(name, os.path.getsize(os.path.join(out_dir, name)))
+
+
 if __name__ == "__main__":
     main()
+    copy_vcfs()

@@ -193,3 +193,46 @@ def test_banded_reference_model_blocks(oracle, ctx):
     bad = length.copy(); bad[3] = 0
     with pytest.raises(Exception):
         square_off_packed(ctx, table, sites, cols, bstart, bcols, ns, ref_len=bad)
+
+
+def test_reference_gvcf_fixture_squares_off_like_the_oracle(oracle, ctx):
+    """The reference's banded gVCF (gvcf_multiallelic.g.vcf, SquareOffReferenceModelSuite.scala:51-76):
+    loadGenotypes -> extractVariants -> avo_square_off with reference-model blocks, per contig, against
+    the oracle's squareOffSite; plus sites made up inside and between its blocks."""
+    import os
+    from avocado_b200 import _lib as L, batch as B, vcf as V
+    from avocado_b200.records import ALT, Variant
+    from avocado_b200.squareoff import extract_variants, square_off_packed
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vcf", "gvcf_multiallelic.g.vcf")
+    gts, header = V.load_genotypes(path)
+    found = extract_variants([g.variant for g in gts], [ALT in g.alleles for g in gts])
+    assert len(found) == 3
+    kinds = set()
+    for contig in sorted({g.contigName for g in gts}):
+        mine = [g for g in gts if g.contigName == contig]
+        table, vrows, vcols, rstart, rlen, rrows, rcols = V.sample_tables(mine, "NA12878i")
+        sites = {v.as_tuple(): v for v in found if v.contigName == contig}
+        for g in mine:                                   # made-up SNVs at block starts, ends and just past them
+            for pos in (g.start, g.end - 1, g.end):
+                v = Variant(contig, pos, pos + 1, "A", "C")
+                sites.setdefault(v.as_tuple(), v)
+        cohort_v = list(sites.values())
+        cohort = B.sites_from_variants(cohort_v)
+        cohort.contig = None
+        out = square_off_packed(ctx, cohort, table, vcols, rstart, rcols, 3, ref_len=rlen)
+        all_rows = [("v", k, g) for k, g in enumerate(vrows)] + [("r", k, g) for k, g in enumerate(rrows)]
+        olist = [(contig, g.start, g.end, g.variant.referenceAllele, g.variant.alternateAllele) for _, _, g in all_rows]
+        for j, i in enumerate(cohort.order):
+            v = cohort_v[i]
+            idx, excised = oracle.square_off_sample(v.as_tuple(), olist)
+            kind = int(out["kind"][j])
+            kinds.add(kind)
+            if idx < 0:
+                assert kind == L.SQ_ABSENT, v
+                continue
+            tab, k, g = all_rows[idx]
+            want = L.SQ_SCORED if not excised else (L.SQ_EXCISED_VARIANT if tab == "v" else L.SQ_EXCISED_REF_MODEL)
+            assert (kind, int(out["src"][j])) == (want, k), (v, olist[idx])
+            src = vcols if tab == "v" else rcols
+            assert np.array_equal(out["gl"][j], src["gl"][k] if not excised else src["nonref_gl"][k])
+    assert {L.SQ_ABSENT, L.SQ_EXCISED_VARIANT, L.SQ_EXCISED_REF_MODEL} <= kinds

@@ -66,3 +66,18 @@ def test_reference_suite_cases_through_the_mirror(ctx):
     vc, = run([gt("proband", ["REF", "ALT"]), gt("parent1", ["REF"]), gt("parent2", ["REF", "ALT"])])          # :133-153
     assert vc.genotypes[2].alleles == ["REF", "ALT"] and not vc.genotypes[2].phased
     assert run([gt("proband", ["REF", "REF"]), gt("parent1", ["REF", "REF"])]) == []                           # :84-98
+
+
+def test_trio_vcf_end_to_end_matches_the_reference_file(ctx, tmp_path):
+    """TrioCallerSuite.scala:239-251 on the GPU path: loadGenotypes(trio.1_837214.vcf) -> TrioCaller
+    (avo_trio_call) -> saveAsVcf, compared byte for byte with the reference's trio.1_837214.phased.vcf."""
+    import os
+    from avocado_b200 import vcf as V
+    from avocado_b200.trio import TrioCaller
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vcf")
+    gts, header = V.load_genotypes(os.path.join(gold, "trio.1_837214.vcf"))
+    contexts = TrioCaller.apply(gts, "NA12891", "NA12892", "NA12878", ctx=ctx)
+    out = tmp_path / "trio.vcf"
+    V.write_vcf(out, header, contexts)
+    with open(out, "rb") as a, open(os.path.join(gold, "trio.1_837214.phased.vcf"), "rb") as b:
+        assert a.read() == b.read()

@@ -384,3 +384,32 @@ def test_c_example_runs_through_the_c_abi(tmp_path):
     r = subprocess.run([exe, "30000"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "30000 reads ->" in r.stdout and "GQ" in r.stdout
+
+
+def test_called_genotypes_survive_a_vcf_round_trip(ctx, tmp_path):
+    """discoverAndCall -> RewriteHets + HardFilterGenotypes -> saveAsVcf text -> loadGenotypes: every field
+    the VCF carries comes back as it was written (float32 text is Java's shortest form, PL is rounded phred)."""
+    from avocado_b200 import vcf as V
+    from avocado_b200.filters import FilterArgs, rewrite_and_filter
+    from avocado_b200.genotyping import BiallelicGenotyper
+    recs = load_fixture("NA12878.1_5274547")[0]          # two overlapping deletions: ALT + OTHER_ALT at both sites
+    gts = BiallelicGenotyper.discoverAndCall(recs, optPhredThreshold=18, optMinObservations=3, samples=["NA12878"], ctx=ctx)
+    gts = rewrite_and_filter(gts, FilterArgs(), ctx=ctx)
+    assert len(gts) == 2
+    header = V.default_header(["NA12878"], [(gts[0].contigName, 249250621)], FilterArgs())
+    path = tmp_path / "calls.vcf"
+    V.write_vcf(path, header, V.group_by_variant(gts))
+    back, h2 = V.load_genotypes(path)
+    assert h2.samples == ["NA12878"] and h2.lines == header.sorted_lines()
+    key = lambda g: g.variant.as_tuple()
+    back = {key(g): g for g in back}
+    assert len(back) == len(gts)
+    for g in gts:
+        b = back[key(g)]
+        assert b.alleles == g.alleles and b.genotypeQuality == g.genotypeQuality and b.phased == g.phased
+        assert (b.readDepth, b.referenceReadDepth, b.alternateReadDepth) == (g.readDepth, g.referenceReadDepth, g.alternateReadDepth)
+        assert b.strandBiasComponents == list(g.strandBiasComponents)
+        assert np.float32(b.rmsMapQ) == np.float32(g.rmsMapQ)
+        assert np.float32(b.fisherStrandBiasPValue) == np.float32(g.fisherStrandBiasPValue)
+        assert (b.filtersApplied, b.filtersPassed, b.filtersFailed) == (g.filtersApplied, g.filtersPassed, list(g.filtersFailed or []))
+        assert V._pl_of(b.genotypeLikelihoods) == V._pl_of(g.genotypeLikelihoods)

@@ -383,7 +383,9 @@ def format_record(vc: VariantContext, samples: Sequence[str]) -> str:
         cols.append(":".join(vals))
     qual = "."
     if vc.quality is not None and not math.isnan(vc.quality):
-        qual = ("%.2f" % vc.quality)
+        qual = "%.2f" % vc.quality            # htsjdk VCFEncoder.formatQualValue: two decimals, ".00" dropped
+        if qual.endswith(".00"):
+            qual = qual[:-3]
     alt = v.alternateAllele if v.alternateAllele is not None else NON_REF
     head = [v.contigName, str(v.start + 1), ".", v.referenceAllele, alt, qual, ".", "."]
     return "\t".join(head + ([":".join(keys)] + cols if samples else []))

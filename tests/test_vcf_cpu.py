@@ -114,3 +114,12 @@ def test_gvcf_extract_variants_matches_the_reference_suite():
                                         (float("nan"), "NaN")])
 def test_java_float_text(value, text):
     assert V.java_float_to_string(value) == text
+
+
+def test_site_quality_text(tmp_path):
+    from avocado_b200.joint import VariantContext
+    gts, header = V.load_genotypes(os.path.join(GOLD, "trio.1_837214.vcf"))
+    vc = V.group_by_variant(gts)[0]
+    for q, text in ((16.07, "16.07"), (564.734, "564.73"), (30.0, "30"), (float("nan"), ".")):
+        line = V.format_record(VariantContext(vc.variant, q, vc.genotypes, float("nan")), header.samples)
+        assert line.split("\t")[5] == text

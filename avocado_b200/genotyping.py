@@ -53,6 +53,26 @@ class CopyNumberMap:
     def maxPloidy(self):
         return max([self.basePloidy] + [c[3] for c in self.cnvs])
 
+    @property
+    def variantsByContig(self) -> Dict[str, List[Tuple[int, int, int]]]:
+        """contig -> [(start, end, copyNumber)] sorted by region (CopyNumberMap.scala:56-61)."""
+        out: Dict[str, List[Tuple[int, int, int]]] = {}
+        for c, s, e, n in self.cnvs:
+            out.setdefault(c, []).append((s, e, n))
+        return {c: sorted(v, key=lambda t: (t[0], t[1])) for c, v in out.items()}
+
+    def overlappingVariants(self, contig: str, start: int, end: int) -> List[Tuple[int, int, int]]:
+        """CopyNumberMap.scala:103-111: dropWhile(!overlaps).takeWhile(overlaps) over the contig's sorted list."""
+        out, seen = [], False
+        for s, e, n in self.variantsByContig.get(contig, []):
+            hit = e > start and s < end
+            if hit:
+                out.append((s, e, n))
+                seen = True
+            elif seen:
+                break
+        return out
+
 
 class Context:
     """One avo_ctx: bound to one GPU, not thread-safe."""

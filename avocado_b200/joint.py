@@ -106,17 +106,66 @@ def joint_call_sharded(ctx, cols, group=None) -> Dict[str, object]:
 
 
 @dataclass
+class VariantSummary:
+    """CORE/genotyping/VariantSummary.scala:39-146: genotype depths rolled up to the site (None = unset)."""
+    readDepth: Optional[int] = None
+    referenceReadDepth: Optional[int] = None
+    forwardReadDepth: Optional[int] = None
+    reverseReadDepth: Optional[int] = None
+    forwardReferenceReadDepth: Optional[int] = None
+    reverseReferenceReadDepth: Optional[int] = None
+
+    @staticmethod
+    def of(g: Genotype) -> "VariantSummary":                                       # :39-70
+        sb = list(g.strandBiasComponents or [])
+        if not sb:
+            return VariantSummary(g.readDepth, g.referenceReadDepth)
+        if len(sb) != 4:
+            raise ValueError("Genotype (%r) has an illegal number of strand bias components." % (g,))
+        rfs, rrs, afs, ars = (int(x) for x in sb)          # 0,1 ref; 2,3 alt; 0,2 forward; 1,3 reverse
+        return VariantSummary(g.readDepth, g.referenceReadDepth, rfs + afs, rrs + ars, rfs, rrs)
+
+    def merge(self, o: "VariantSummary") -> "VariantSummary":                      # :95-119
+        def add(a, b):
+            return a + b if a is not None and b is not None else a if a is not None else b
+        return VariantSummary(*(add(getattr(self, f.name), getattr(o, f.name)) for f in dataclasses.fields(self)))
+
+    def to_annotation(self, existing: Optional[Dict[str, int]] = None) -> Dict[str, int]:      # :126-145
+        """VariantAnnotation fields: the variant's current annotation with every set field replaced."""
+        names = {"readDepth": "readDepth", "referenceReadDepth": "referenceReadDepth",
+                 "forwardReadDepth": "forwardReadDepth", "reverseReadDepth": "reverseReadDepth",
+                 "forwardReferenceReadDepth": "referenceForwardReadDepth",
+                 "reverseReferenceReadDepth": "referenceReverseReadDepth"}
+        out = dict(existing or {})
+        for mine, theirs in names.items():
+            if getattr(self, mine) is not None:
+                out[theirs] = int(getattr(self, mine))
+        return out
+
+
+def calculate_annotations(genotypes: Sequence[Genotype], existing: Optional[Dict[str, int]] = None) -> Dict[str, int]:
+    """JointAnnotatorCaller.calculateAnnotations (:141-147): site.genotypes.map(VariantSummary(_)).reduce(_.merge(_))."""
+    acc = None
+    for g in genotypes:
+        v = VariantSummary.of(g)
+        acc = v if acc is None else acc.merge(v)
+    return (acc or VariantSummary()).to_annotation(existing)
+
+
+@dataclass
 class VariantContext:
     """One squared-off site: the variant (with its joint quality) and the genotypes of all samples."""
     variant: Variant
     quality: float
     genotypes: List[Genotype]
     minorAlleleFrequency: float
+    annotation: Optional[Dict[str, int]] = None       # the rolled-up VariantAnnotation depths (VariantSummary)
 
 
 class JointAnnotatorCaller:
-    """CORE/genotyping/JointAnnotatorCaller.scala (the rolled-up VariantAnnotation of :141-147 is
-    formatting downstream of the hot path and is not produced here)."""
+    """CORE/genotyping/JointAnnotatorCaller.scala: the recall and the site quality run on the GPU
+    (avo_joint); the rolled-up depth annotation of :141-147 is a handful of integer sums per site over
+    fields the device never sees (read depths, strand bias components) and is added here on the host."""
 
     @staticmethod
     def apply(genotypes: Sequence[Genotype], ctx=None) -> List[VariantContext]:
@@ -168,5 +217,8 @@ class JointAnnotatorCaller:
                     new.alleles = [ALT] * int(out["n_alt"][s, i]) + [REF] * int(out["n_ref"][s, i])
                     new.genotypeQuality = int(out["gq"][s, i])
                 gts.append(new)
-            sites.append(VariantContext(Variant(*key), float(out["quality"][i]), gts, float(out["maf"][i])))
+            site_gts = [where[(s, i)] for s in range(S) if (s, i) in where]
+            # :85-90: "if we have more than one sample, roll up annotations"
+            ann = calculate_annotations(site_gts) if len(site_gts) > 1 else None
+            sites.append(VariantContext(Variant(*key), float(out["quality"][i]), gts, float(out["maf"][i]), ann))
         return sites

@@ -10,7 +10,8 @@
 // known-answer test and SAM fixture the reference's own suites hold for the
 // path (BiallelicGenotyperSuite, DiscoverVariantsSuite, ObserverSuite,
 // ObservationOperatorSuite, TreeRegionJoinSuite, JointAnnotatorCallerSuite,
-// LogUtilsSuite, LogPhredSuite); expectations are transcribed into
+// LogUtilsSuite, LogPhredSuite, CopyNumberMapSuite, VariantSummarySuite,
+// ObservationSuite, and the filter / square-off / trio suites); expectations are transcribed into
 // tests/golden/ with file:line citations.  The reference itself (Scala 2.11 /
 // Spark 2.2 / ADAM 0.24) cannot be compiled or run in this image (no JVM).
 //
@@ -1352,6 +1353,86 @@ static std::pair<int, bool> squareOffSample(const std::string& contig, long star
 }
 
 // ---------------------------------------------------------------------------
+// CORE/genotyping/VariantSummary.scala:39-146 -- the per-site roll-up of genotype depths
+// JointAnnotatorCaller.calculateAnnotations (:141-147) attaches to the variant.  -1 = None.
+// ---------------------------------------------------------------------------
+struct VariantSummaryO {
+  int readDepth = -1, referenceReadDepth = -1, forwardReadDepth = -1, reverseReadDepth = -1,
+      forwardReferenceReadDepth = -1, reverseReferenceReadDepth = -1;
+};
+
+static VariantSummaryO variantSummaryOf(int readDepth, int referenceReadDepth, const std::vector<int>& sbc) {  // :39-70
+  VariantSummaryO v;
+  v.readDepth = readDepth;
+  v.referenceReadDepth = referenceReadDepth;
+  if (!sbc.empty()) {
+    if (sbc.size() != 4) throw std::invalid_argument("Genotype has an illegal number of strand bias components.");  // :49-50
+    const int rfs = sbc[0], rrs = sbc[1], afs = sbc[2], ars = sbc[3];             // 0,1 ref; 2,3 alt; 0,2 fwd; 1,3 rev
+    v.forwardReadDepth = rfs + afs;
+    v.reverseReadDepth = rrs + ars;
+    v.forwardReferenceReadDepth = rfs;
+    v.reverseReferenceReadDepth = rrs;
+  }
+  return v;
+}
+
+static int mergeOptions(int a, int b) {                                              // :95-103
+  if (a >= 0 && b >= 0) return a + b;
+  return a >= 0 ? a : b;
+}
+
+static VariantSummaryO variantSummaryMerge(const VariantSummaryO& a, const VariantSummaryO& b) {   // :111-119
+  VariantSummaryO v;
+  v.readDepth = mergeOptions(a.readDepth, b.readDepth);
+  v.referenceReadDepth = mergeOptions(a.referenceReadDepth, b.referenceReadDepth);
+  v.forwardReadDepth = mergeOptions(a.forwardReadDepth, b.forwardReadDepth);
+  v.reverseReadDepth = mergeOptions(a.reverseReadDepth, b.reverseReadDepth);
+  v.forwardReferenceReadDepth = mergeOptions(a.forwardReferenceReadDepth, b.forwardReferenceReadDepth);
+  v.reverseReferenceReadDepth = mergeOptions(a.reverseReferenceReadDepth, b.reverseReferenceReadDepth);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// CORE/models/Observation.scala:22-175 -- the per-site aggregate as a record: its invariants
+// (:106-112) and the two derived forms.  Neither invert nor nullOut is called on the path (the
+// nullOut of BG:320-351 is SummarizedObservation's); they are here because ObservationSuite pins them.
+// ---------------------------------------------------------------------------
+struct ObservationRec {
+  int alleleForwardStrand, otherForwardStrand;
+  double squareMapQ;
+  std::vector<double> referenceLogLikelihoods, alleleLogLikelihoods, otherLogLikelihoods, nonRefLogLikelihoods;
+  int alleleCoverage, otherCoverage, totalCoverage;
+  bool isRef;
+  int copyNumber;
+
+  void check() const {                                                               // :106-112
+    const int coverage = alleleCoverage + otherCoverage;
+    if (!(copyNumber <= (int)otherLogLikelihoods.size() - 1 && copyNumber <= (int)referenceLogLikelihoods.size() - 1 &&
+          copyNumber > 0))
+      throw std::invalid_argument("assertion failed: copy number vs likelihood lengths");
+    if (!(squareMapQ >= 0.0)) throw std::invalid_argument("assertion failed: squareMapQ");
+    if (!(alleleCoverage >= 0 && otherCoverage >= 0 && coverage >= 0 && totalCoverage > 0))
+      throw std::invalid_argument("assertion failed: coverage");
+    if (!(alleleForwardStrand >= 0 && alleleCoverage >= alleleForwardStrand && otherForwardStrand >= 0 &&
+          otherCoverage >= otherForwardStrand))
+      throw std::invalid_argument("assertion failed: forward strand counts");
+  }
+  ObservationRec invert() const {                                                    // :137-150
+    ObservationRec o{otherForwardStrand, alleleForwardStrand, squareMapQ, referenceLogLikelihoods,
+                     otherLogLikelihoods, alleleLogLikelihoods, nonRefLogLikelihoods, otherCoverage,
+                     alleleCoverage, totalCoverage, !isRef, copyNumber};
+    o.check();
+    return o;
+  }
+  ObservationRec nullOut() const {                                                   // :158-171
+    ObservationRec o{0, 0, 0.0, referenceLogLikelihoods, std::vector<double>(alleleLogLikelihoods.size(), 0.0),
+                     alleleLogLikelihoods, nonRefLogLikelihoods, 0, 0, totalCoverage, false, copyNumber};
+    o.check();
+    return o;
+  }
+};
+
+// ---------------------------------------------------------------------------
 // CORE/genotyping/TrioCaller.scala:86-221 -- per-site trio consistency / phasing.
 // A genotype is its allele list (0 REF, 1 ALT, 2 OTHER_ALT, 3 NO_CALL); absent = has == false.
 // ---------------------------------------------------------------------------
@@ -1945,4 +2026,83 @@ PYBIND11_MODULE(avocado_oracle, m) {
     d["filled"] = std::vector<bool>{r.filled[0], r.filled[1], r.filled[2]};
     return d;
   });
+  // ---- VariantSummary ------------------------------------------------------------------------------
+  // variant_summary([(readDepth | None, referenceReadDepth | None, strandBiasComponents) | 6-tuple of
+  // Optional ints]) -> the merged summary (calculateAnnotations: map(VariantSummary(_)).reduce(_.merge(_)))
+  m.def("variant_summary", [](const std::vector<py::object>& items) {
+    auto opt = [](py::handle h) { return h.is_none() ? -1 : h.cast<int>(); };
+    bool first = true;
+    VariantSummaryO acc;
+    for (const py::object& it : items) {
+      py::tuple t = it.cast<py::tuple>();
+      VariantSummaryO v;
+      if (t.size() == 3) {
+        v = variantSummaryOf(opt(t[0]), opt(t[1]), t[2].cast<std::vector<int>>());
+      } else {
+        v.readDepth = opt(t[0]); v.referenceReadDepth = opt(t[1]); v.forwardReadDepth = opt(t[2]);
+        v.reverseReadDepth = opt(t[3]); v.forwardReferenceReadDepth = opt(t[4]); v.reverseReferenceReadDepth = opt(t[5]);
+      }
+      acc = first ? v : variantSummaryMerge(acc, v);
+      first = false;
+    }
+    auto out = [](int x) { return x < 0 ? py::object(py::none()) : py::object(py::int_(x)); };
+    py::dict d;
+    d["readDepth"] = out(acc.readDepth); d["referenceReadDepth"] = out(acc.referenceReadDepth);
+    d["forwardReadDepth"] = out(acc.forwardReadDepth); d["reverseReadDepth"] = out(acc.reverseReadDepth);
+    d["forwardReferenceReadDepth"] = out(acc.forwardReferenceReadDepth);
+    d["reverseReferenceReadDepth"] = out(acc.reverseReferenceReadDepth);
+    return d;
+  });
+  // ---- CopyNumberMap -------------------------------------------------------------------------------
+  // copy_number_map(basePloidy, [(contig, start, end, featureType)], query (contig, start, end) | None):
+  // CopyNumberMap.apply (CORE/models/CopyNumberMap.scala:45-64: DUP -> base + 1, DEL -> base - 1, others
+  // dropped; per contig sorted by region), min / maxPloidy (:81-95), overlappingVariants (:103-111)
+  m.def("copy_number_map", [](int basePloidy, const std::vector<std::tuple<std::string, long, long, std::string>>& features,
+                              py::object query) {
+    std::vector<std::tuple<std::string, long, long, int>> cnvs;
+    for (auto& f : features) {
+      if (std::get<3>(f) == "DUP") cnvs.emplace_back(std::get<0>(f), std::get<1>(f), std::get<2>(f), basePloidy + 1);
+      else if (std::get<3>(f) == "DEL") cnvs.emplace_back(std::get<0>(f), std::get<1>(f), std::get<2>(f), basePloidy - 1);
+    }
+    const CopyNumberMap cm = makeCnm(basePloidy, cnvs);
+    py::dict d, by;
+    d["basePloidy"] = cm.basePloidy; d["minPloidy"] = cm.minPloidy(); d["maxPloidy"] = cm.maxPloidy();
+    for (auto& kv : cm.variantsByContig) {
+      py::list l;
+      for (auto& p : kv.second) l.append(py::make_tuple(p.first.start, p.first.end, p.second));
+      by[py::str(kv.first)] = l;
+    }
+    d["variantsByContig"] = by;
+    if (!query.is_none()) {
+      auto q = query.cast<std::tuple<std::string, long, long>>();
+      py::list l;
+      for (auto& p : cm.overlappingVariants(Region{std::get<0>(q), std::get<1>(q), std::get<2>(q)}))
+        l.append(py::make_tuple(p.first.start, p.first.end, p.second));
+      d["overlapping"] = l;
+    }
+    return d;
+  }, py::arg("basePloidy"), py::arg("features"), py::arg("query") = py::none());
+  // ---- Observation (record) ------------------------------------------------------------------------
+  // observation(afs, ofs, squareMapQ, ref, allele, other, nonRef, alleleCov, otherCov, totalCoverage = 1,
+  //             isRef = true, op = "check" | "invert" | "nullOut"): the companion apply of
+  // CORE/models/Observation.scala:22-46 (copyNumber = len(allele) - 1), the invariants and derived forms
+  m.def("observation", [](int afs, int ofs, double sq, std::vector<double> ref, std::vector<double> allele,
+                          std::vector<double> other, std::vector<double> nonref, int acov, int ocov, int tcov,
+                          bool isRef, const std::string& op) {
+    ObservationRec o{afs, ofs, sq, ref, allele, other, nonref, acov, ocov, tcov, isRef, (int)allele.size() - 1};
+    o.check();
+    if (op == "invert") o = o.invert();
+    else if (op == "nullOut") o = o.nullOut();
+    py::dict d;
+    d["alleleForwardStrand"] = o.alleleForwardStrand; d["otherForwardStrand"] = o.otherForwardStrand;
+    d["squareMapQ"] = o.squareMapQ; d["referenceLogLikelihoods"] = o.referenceLogLikelihoods;
+    d["alleleLogLikelihoods"] = o.alleleLogLikelihoods; d["otherLogLikelihoods"] = o.otherLogLikelihoods;
+    d["nonRefLogLikelihoods"] = o.nonRefLogLikelihoods; d["alleleCoverage"] = o.alleleCoverage;
+    d["otherCoverage"] = o.otherCoverage; d["totalCoverage"] = o.totalCoverage; d["isRef"] = o.isRef;
+    d["copyNumber"] = o.copyNumber;
+    return d;
+  }, py::arg("alleleForwardStrand"), py::arg("otherForwardStrand"), py::arg("squareMapQ"),
+     py::arg("referenceLogLikelihoods"), py::arg("alleleLogLikelihoods"), py::arg("otherLogLikelihoods"),
+     py::arg("nonRefLogLikelihoods"), py::arg("alleleCoverage"), py::arg("otherCoverage"),
+     py::arg("totalCoverage") = 1, py::arg("isRef") = true, py::arg("op") = "check");
 }

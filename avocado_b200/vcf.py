@@ -298,6 +298,18 @@ def load_variants(path) -> List[Variant]:
     return [v for rec in records for v, alt_index, _ in _split(rec) if alt_index is not None]
 
 
+def merge_discovered(paths: Sequence[str]) -> List[Variant]:
+    """CLI/MergeDiscovered.scala:52-62: the variants of several files with duplicates (same contig, start,
+    end, alleles) dropped -- the union of per-sample discovery every sample is then called against."""
+    seen, out = set(), []
+    for path in paths:
+        for v in load_variants(path):
+            if v.as_tuple() not in seen:
+                seen.add(v.as_tuple())
+                out.append(v)
+    return out
+
+
 def reference_model_blocks(genotypes: Sequence[Genotype], sample: str) -> Tuple[np.ndarray, np.ndarray, List[Genotype]]:
     """The reference-model genotypes of one sample as (start, length, rows) sorted by start: what
     avo_square_off takes as ref_model_start / ref_model_len for a banded gVCF."""

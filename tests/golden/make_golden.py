@@ -67,8 +67,9 @@ def copy_vcfs():
     import shutil
     out_dir = os.path.join(os.path.dirname(__file__), "vcf")
     os.makedirs(out_dir, exist_ok=True)
-    for name in VCF_FIXTURES:
-        shutil.copyfile(os.path.join(RES, name), os.path.join(out_dir, name))
+    cli = "/root/reference/avocado-cli/src/test/resources"     # MergeDiscoveredSuite.scala:25-33
+    for src_dir, name in [(RES, n) for n in VCF_FIXTURES] + [(cli, "NA12878.1_907170_AG2A.vcf"), (cli, "NA12878.1_907170_A2C.vcf")]:
+        shutil.copyfile(os.path.join(src_dir, name), os.path.join(out_dir, name))
         os.chmod(os.path.join(out_dir, name), 0o644)
         print(name, os.path.getsize(os.path.join(out_dir, name)))
 

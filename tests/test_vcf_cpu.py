@@ -123,3 +123,10 @@ def test_site_quality_text(tmp_path):
     for q, text in ((16.07, "16.07"), (564.734, "564.73"), (30.0, "30"), (float("nan"), ".")):
         line = V.format_record(VariantContext(vc.variant, q, vc.genotypes, float("nan")), header.samples)
         assert line.split("\t")[5] == text
+
+
+def test_merge_variants_discovered_from_two_samples():
+    """MergeDiscoveredSuite.scala:25-33: two site lists sharing one variant -> 3 distinct variants."""
+    merged = V.merge_discovered([os.path.join(GOLD, "NA12878.1_907170_A2C.vcf"), os.path.join(GOLD, "NA12878.1_907170_AG2A.vcf")])
+    assert sorted(v.as_tuple() for v in merged) == [("1", 907167, 907168, "A", "T"), ("1", 907169, 907170, "A", "C"),
+                                                    ("1", 907169, 907171, "AG", "A")]

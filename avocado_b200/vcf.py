@@ -158,7 +158,7 @@ def java_float_to_string(x: float) -> str:
 
 def _pl_of(log_likelihoods: Sequence[float]) -> List[int]:
     # PhredUtils.logProbabilityToPhred on every likelihood (natural log -> phred, rounded)
-    return [int(round(-ll / LN10_DIV_10)) + 0 for ll in log_likelihoods]
+    return [int(round(-ll / LN10_DIV_10)) for ll in log_likelihoods]
 
 
 # ---- reading ---------------------------------------------------------------------------------------

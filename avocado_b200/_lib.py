@@ -186,6 +186,20 @@ class JointOutStruct(C.Structure):
                 ("mem", C.c_int32), ("reserved", C.c_int32)] + [(n, P) for n, _, _ in JOINT_OUT_COLUMNS]
 
 
+class DepthsInStruct(C.Structure):
+    _fields_ = [("n_sites", C.c_int64), ("n_samples", C.c_int32), ("mem", C.c_int32), ("present", P),
+                ("read_depth", P), ("ref_read_depth", P), ("sb", P)]
+
+
+SITE_DEPTH_COLUMNS = ["read_depth", "ref_read_depth", "fwd_read_depth", "rev_read_depth", "ref_fwd_read_depth",
+                      "ref_rev_read_depth"]
+
+
+class SiteDepthsStruct(C.Structure):
+    _fields_ = [("n_sites", C.c_int64), ("mem", C.c_int32), ("reserved", C.c_int32), ("annotated", P)] + \
+               [(n, P) for n in SITE_DEPTH_COLUMNS]
+
+
 class SynthParamsStruct(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("contig_len", C.c_int32), ("first_pos", C.c_int32),
                 ("n_reads_total", C.c_int64), ("read_len", C.c_int32), ("max_indel", C.c_int32),
@@ -197,7 +211,7 @@ class SynthParamsStruct(C.Structure):
 EXPORTED_SYMBOLS = [
     "avo_ctx_create", "avo_ctx_destroy", "avo_last_error", "avo_version", "avo_ctx_set_stream",
     "avo_get_timing", "avo_discover", "avo_call", "avo_discover_and_call",
-    "avo_call_all_sites", "avo_filter_genotypes", "avo_square_off", "avo_trio_call", "avo_joint_counts", "avo_joint",
+    "avo_call_all_sites", "avo_filter_genotypes", "avo_square_off", "avo_trio_call", "avo_joint_counts", "avo_joint", "avo_joint_depths",
     "avo_pack_wire", "avo_pack_wire6", "avo_pack_bounds", "avo_pack_reads", "avo_pack_reads_mt", "avo_pack_reads_device", "avo_synth_default_params",
     "avo_synth_host", "avo_synth_device", "avo_synth_text",
 ]
@@ -241,6 +255,7 @@ def load():
     lib.avo_trio_call.argtypes = [P, C.POINTER(TrioStruct)]
     lib.avo_joint_counts.argtypes = [P, C.POINTER(JointInStruct), P, P]
     lib.avo_joint.argtypes = [P, C.POINTER(JointInStruct), C.POINTER(JointOutStruct)]
+    lib.avo_joint_depths.argtypes = [P, C.POINTER(DepthsInStruct), C.POINTER(SiteDepthsStruct)]
     lib.avo_pack_wire.argtypes = [C.POINTER(ReadBatchStruct), P, P]
     lib.avo_pack_wire6.argtypes = [C.POINTER(ReadBatchStruct), P, P, P, P, C.c_int64, C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int32)]

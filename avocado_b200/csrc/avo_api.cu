@@ -37,6 +37,7 @@ enum Slot {
   SL_T_START, SL_T_END, SL_T_MAPQ, SL_T_FLAGS, SL_T_CIGAR, SL_T_CIGAR_OFF, SL_T_MD, SL_T_MD_OFF, SL_T_SEQ,
   SL_T_SEQ_OFF, SL_T_QUAL, SL_T_QUAL_OFF, SL_T_KEEP, SL_T_COUNTS, SL_T_OFFSETS,
   SL_J_PRESENT, SL_J_NALT, SL_J_NREF, SL_J_NOTHER, SL_J_NOCALL, SL_J_GL, SL_J_ALT, SL_J_CALLED, SL_J_OUT,
+  SL_JD_DP, SL_JD_REFDP, SL_JD_SB, SL_JD_OUT,
   SL_TABLE, SL_TCOUNT, SL_KEYS_A, SL_KEYS_B, SL_VALS_A, SL_VALS_B, SL_FOOT, SL_AOFF,
   SL_COUNT_
 };
@@ -1482,6 +1483,57 @@ int avo_joint_counts(avo_ctx* ctx, const avo_joint_in* in, int32_t* alt_alleles,
   CK(cudaEventRecord(ctx->ev[7], ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->timing.ms_total = ev_ms(ctx, 0, 7);
+  return AVO_OK;
+}
+
+int avo_joint_depths(avo_ctx* ctx, const avo_depths_in* in, avo_site_depths* out) {
+  CKS(begin_call(ctx));
+  if (!in || !out) return fail(ctx, AVO_E_INVALID, "NULL argument");
+  if (in->n_sites < 0 || in->n_samples < 1 || out->n_sites != in->n_sites)
+    return fail(ctx, AVO_E_INVALID, "depths: bad n_sites / n_samples");
+  if ((in->mem != AVO_MEM_HOST && in->mem != AVO_MEM_DEVICE) || out->mem != in->mem)
+    return fail(ctx, AVO_E_INVALID, "depths: input and output must live in the same memory");
+  const size_t n = (size_t)in->n_sites, sn = n * (size_t)in->n_samples;
+  if (n == 0) return AVO_OK;
+  int32_t* ocol[6] = {out->read_depth, out->ref_read_depth, out->fwd_read_depth, out->rev_read_depth,
+                      out->ref_fwd_read_depth, out->ref_rev_read_depth};
+  if (!out->annotated) return fail(ctx, AVO_E_INVALID, "depths output has NULL columns");
+  for (int f = 0; f < 6; ++f)
+    if (!ocol[f]) return fail(ctx, AVO_E_INVALID, "depths output has NULL columns");
+  if (in->mem == AVO_MEM_DEVICE && in->sb && ((uintptr_t)in->sb & 15u))
+    return fail(ctx, AVO_E_INVALID, "depths: sb must be 16-byte aligned");
+  DDepthsIn I{};
+  I.n_sites = in->n_sites; I.n_samples = in->n_samples;
+  if (in->present) CKS(stage_in(ctx, SL_J_PRESENT, in->present, sn, in->mem, &I.present));
+  if (in->read_depth) CKS(stage_in(ctx, SL_JD_DP, in->read_depth, sn, in->mem, &I.read_depth));
+  if (in->ref_read_depth) CKS(stage_in(ctx, SL_JD_REFDP, in->ref_read_depth, sn, in->mem, &I.ref_read_depth));
+  if (in->sb) CKS(stage_in(ctx, SL_JD_SB, in->sb, sn * 4, in->mem, &I.sb));
+  DDepthsOut O{};
+  O.annotated = out->annotated;
+  for (int f = 0; f < 6; ++f) O.col[f] = ocol[f];
+  char* d_out = nullptr;
+  const size_t col_bytes = (n * 4 + 255) & ~(size_t)255;
+  if (in->mem == AVO_MEM_HOST) {
+    void* q;
+    CKS(get_buf(ctx, SL_JD_OUT, 7 * col_bytes, &q));
+    d_out = (char*)q;
+    O.annotated = (uint8_t*)d_out;
+    for (int f = 0; f < 6; ++f) O.col[f] = (int32_t*)(d_out + (size_t)(f + 1) * col_bytes);
+  }
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  CK(launch_joint_depths(I, O, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  ctx->timing.n_launches += 1;
+  if (in->mem == AVO_MEM_HOST) {
+    CK(cudaMemcpyAsync(out->annotated, O.annotated, n, cudaMemcpyDeviceToHost, ctx->stream));
+    for (int f = 0; f < 6; ++f)
+      CK(cudaMemcpyAsync(ocol[f], O.col[f], n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->timing.d2h_bytes += (int64_t)(n * 25);
+  }
+  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.ms_total = ev_ms(ctx, 0, 7);
+  ctx->timing.ms_observe = ev_ms(ctx, 4, 5);
   return AVO_OK;
 }
 

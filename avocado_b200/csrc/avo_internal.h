@@ -103,6 +103,12 @@ struct DJointOut {
   int32_t *n_alt, *n_ref, *gq;
 };
 cudaError_t launch_joint_counts(const DJointIn& J, int32_t* alt, int32_t* called, cudaStream_t s);
+struct DDepthsIn {
+  int64_t n_sites; int32_t n_samples;
+  const uint8_t* present; const int32_t *read_depth, *ref_read_depth, *sb;    // each may be null
+};
+struct DDepthsOut { uint8_t* annotated; int32_t* col[6]; };
+cudaError_t launch_joint_depths(const DDepthsIn& I, const DDepthsOut& O, cudaStream_t s);
 cudaError_t launch_joint_recall(const DJointIn& J, const int32_t* alt, const int32_t* called,
                                 const DJointOut& O, const double* lgam, cudaStream_t s);
 

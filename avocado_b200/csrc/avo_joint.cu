@@ -35,6 +35,39 @@ __global__ void k_joint_counts(DJointIn J, int32_t* __restrict__ alt, int32_t* _
   called[i] = c;
 }
 
+// calculateAnnotations (JointAnnotatorCaller.scala:141-147): VariantSummary of every genotype of the site,
+// merged (VariantSummary.scala:95-119: a field is the sum over the genotypes that have it).  One thread per
+// site; the loads of a warp are 32 neighbouring sites of one sample (coalesced).
+__global__ void k_joint_depths(DDepthsIn I, DDepthsOut O) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= I.n_sites) return;
+  int32_t sum[6] = {0, 0, 0, 0, 0, 0};
+  bool has[6] = {false, false, false, false, false, false};
+  int32_t n_gt = 0;
+  for (int s = 0; s < I.n_samples; ++s) {
+    const int64_t k = (int64_t)s * I.n_sites + i;
+    if (I.present && !I.present[k]) continue;
+    ++n_gt;
+    if (I.read_depth) { const int32_t v = __ldg(I.read_depth + k); if (v >= 0) { sum[0] += v; has[0] = true; } }
+    if (I.ref_read_depth) { const int32_t v = __ldg(I.ref_read_depth + k); if (v >= 0) { sum[1] += v; has[1] = true; } }
+    if (I.sb) {
+      const int4 b = __ldg(reinterpret_cast<const int4*>(I.sb) + k);      // ref fwd, ref rev, alt fwd, alt rev
+      if (b.x >= 0) {
+        sum[2] += b.x + b.z; sum[3] += b.y + b.w; sum[4] += b.x; sum[5] += b.y;   // VariantSummary.scala:52-65
+        has[2] = has[3] = has[4] = has[5] = true;
+      }
+    }
+  }
+  O.annotated[i] = n_gt > 1;                                                // :85-90
+  for (int f = 0; f < 6; ++f) O.col[f][i] = has[f] ? sum[f] : -1;
+}
+
+cudaError_t launch_joint_depths(const DDepthsIn& I, const DDepthsOut& O, cudaStream_t s) {
+  if (I.n_sites == 0) return cudaSuccess;
+  k_joint_depths<<<(unsigned)((I.n_sites + 127) / 128), 128, 0, s>>>(I, O);
+  return cudaGetLastError();
+}
+
 // LogUtils.sumLogProbabilities over n <= NS values (sorted descending, stable)
 template <int NS>
 __device__ double sum_log_probabilities(const double* p, int n) {

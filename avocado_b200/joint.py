@@ -77,6 +77,34 @@ def joint_call(ctx, n_sites, n_samples, n_states, n_alt, n_ref, n_other, gl, pre
     return shaped
 
 
+def joint_depths(ctx, n_sites, n_samples, read_depth=None, ref_read_depth=None, sb=None, present=None
+                 ) -> Dict[str, object]:
+    """avo_joint_depths on (samples x sites) columns (numpy or torch CUDA, sample-major; sb is [S, N, 4]):
+    the per-site VariantAnnotation depths of calculateAnnotations and the `annotated` flag (-1 = unset)."""
+    given = [a for a in (read_depth, ref_read_depth, sb, present) if a is not None]
+    dev = bool(given) and _is_dev(given[0])
+    i = L.DepthsInStruct()
+    i.n_sites, i.n_samples, i.mem = n_sites, n_samples, L.MEM_DEVICE if dev else L.MEM_HOST
+    keep = []
+    for name, a, dt in (("present", present, np.uint8), ("read_depth", read_depth, np.int32),
+                        ("ref_read_depth", ref_read_depth, np.int32), ("sb", sb, np.int32)):
+        if a is None:
+            continue
+        if not dev:
+            a = np.ascontiguousarray(a, dt)
+            keep.append(a)
+        setattr(i, name, _ptr(a))
+    o = L.SiteDepthsStruct()
+    o.n_sites, o.mem = n_sites, i.mem
+    out = {}
+    for name, dt in [("annotated", np.uint8)] + [(c, np.int32) for c in L.SITE_DEPTH_COLUMNS]:
+        a = _device_empty(n_sites, dt, "cuda:%d" % ctx.device) if dev else np.zeros(max(n_sites, 1), dt)
+        out[name] = a
+        setattr(o, name, _ptr(a))
+    ctx._check(ctx.lib.avo_joint_depths(ctx.h, C.byref(i), C.byref(o)))
+    return {k: v[:n_sites] for k, v in out.items()}
+
+
 MINUS_TEN_DIV_LOG10 = -10.0 / np.log(10.0)
 
 
@@ -163,9 +191,8 @@ class VariantContext:
 
 
 class JointAnnotatorCaller:
-    """CORE/genotyping/JointAnnotatorCaller.scala: the recall and the site quality run on the GPU
-    (avo_joint); the rolled-up depth annotation of :141-147 is a handful of integer sums per site over
-    fields the device never sees (read depths, strand bias components) and is added here on the host."""
+    """CORE/genotyping/JointAnnotatorCaller.scala: recall and site quality (avo_joint) and the rolled-up
+    depth annotation of :141-147 (avo_joint_depths) on the GPU."""
 
     @staticmethod
     def apply(genotypes: Sequence[Genotype], ctx=None) -> List[VariantContext]:
@@ -197,6 +224,20 @@ class JointAnnotatorCaller:
             where[(s, i)] = g
         out = joint_call(ctx, n, S, ns, cnt[ALT].ravel(), cnt[REF].ravel(), cnt[OTHER_ALT].ravel(),
                          gl.ravel(), present.ravel(), cnt[NO_CALL].ravel())
+        # calculateAnnotations (:141-147) for every site: avo_joint_depths
+        dp, refdp, sb = -np.ones((S, n), np.int32), -np.ones((S, n), np.int32), -np.ones((S, n, 4), np.int32)
+        for (s, i), g in where.items():
+            dp[s, i] = -1 if g.readDepth is None else g.readDepth
+            refdp[s, i] = -1 if g.referenceReadDepth is None else g.referenceReadDepth
+            comp = list(g.strandBiasComponents or [])
+            if comp:
+                if len(comp) != 4:                                          # VariantSummary.scala:49-50 (require)
+                    raise ValueError("Genotype (%r) has an illegal number of strand bias components." % (g,))
+                sb[s, i] = comp
+        depths = joint_depths(ctx, n, S, dp.ravel(), refdp.ravel(), sb.ravel(), present.ravel())
+        ann_names = dict(zip(L.SITE_DEPTH_COLUMNS, ("readDepth", "referenceReadDepth", "forwardReadDepth",
+                                                    "reverseReadDepth", "referenceForwardReadDepth",
+                                                    "referenceReverseReadDepth")))
         sites: List[VariantContext] = []
         for key, i in keys.items():
             if not out["site_emitted"][i]:
@@ -217,8 +258,9 @@ class JointAnnotatorCaller:
                     new.alleles = [ALT] * int(out["n_alt"][s, i]) + [REF] * int(out["n_ref"][s, i])
                     new.genotypeQuality = int(out["gq"][s, i])
                 gts.append(new)
-            site_gts = [where[(s, i)] for s in range(S) if (s, i) in where]
             # :85-90: "if we have more than one sample, roll up annotations"
-            ann = calculate_annotations(site_gts) if len(site_gts) > 1 else None
+            ann = None
+            if depths["annotated"][i]:
+                ann = {ann_names[c]: int(depths[c][i]) for c in L.SITE_DEPTH_COLUMNS if depths[c][i] >= 0}
             sites.append(VariantContext(Variant(*key), float(out["quality"][i]), gts, float(out["maf"][i]), ann))
         return sites

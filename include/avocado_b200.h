@@ -485,6 +485,35 @@ int avo_joint_counts(avo_ctx* ctx, const avo_joint_in* in, int32_t* alt_alleles,
 /* annotateSite for every site. */
 int avo_joint(avo_ctx* ctx, const avo_joint_in* in, avo_joint_out* out);
 
+/* The depth roll-up annotateSite attaches to the variant (JointAnnotatorCaller.calculateAnnotations,
+ * JointAnnotatorCaller.scala:85-90, 141-147; VariantSummary.scala:39-146): per site, the sums over the
+ * site's genotypes of readDepth, referenceReadDepth and of the strand-bias components
+ * (forward = sb[0] + sb[2], reverse = sb[1] + sb[3], reference forward = sb[0], reference reverse = sb[1]),
+ * each sum over the genotypes that have the field (Option merge: None only if no genotype has it).
+ * Same (samples x sites) sample-major layout as avo_joint_in. */
+typedef struct {
+  int64_t n_sites;
+  int32_t n_samples;
+  int32_t mem;
+  const uint8_t* present;        /* [S*N] 1 iff the sample has a genotype at the site; NULL = all */
+  const int32_t* read_depth;     /* [S*N] < 0 = unset; NULL = unset everywhere */
+  const int32_t* ref_read_depth; /* [S*N] < 0 = unset; NULL = unset everywhere */
+  const int32_t* sb;             /* [S*N*4] strandBiasComponents, sb[4k] < 0 = the genotype has none; NULL = none */
+} avo_depths_in;
+typedef struct {
+  int64_t n_sites;
+  int32_t mem;
+  int32_t reserved;
+  uint8_t* annotated;            /* [N] 1 iff the site has more than one genotype (:85-90: else no annotation) */
+  int32_t* read_depth;           /* [N] the six VariantAnnotation fields, -1 = unset */
+  int32_t* ref_read_depth;
+  int32_t* fwd_read_depth;
+  int32_t* rev_read_depth;
+  int32_t* ref_fwd_read_depth;
+  int32_t* ref_rev_read_depth;
+} avo_site_depths;
+int avo_joint_depths(avo_ctx* ctx, const avo_depths_in* in, avo_site_depths* out);
+
 /* ---- host-side packer (PrefilterReads + ObservationOperator.extractAlignmentOperators) ------ */
 /* Text columns of AlignmentRecords (blobs + [n+1] offsets; has_* bits in rec_flags:
  * bit0 readMapped, bit1 readNegativeStrand, bit2 cigar present, bit3 MD present, bit4 mapq present).

@@ -162,3 +162,64 @@ def test_joint_record_api_follows_the_reference_suite(ctx):
     assert g0.nonReferenceLikelihoods == [] and len(g0.genotypePosteriors) == 3
     assert abs(sum(math.exp(x) for x in g0.genotypePosteriors) - 1.0) < 1e-6
     assert JointAnnotatorCaller.apply([gt("s0", ["REF", "REF"], [0.0, -1.0, -2.0])], ctx=ctx) == []
+
+
+def test_site_depth_roll_up_matches_oracle(oracle, ctx):
+    """avo_joint_depths = JointAnnotatorCaller.calculateAnnotations (:85-90, :141-147; VariantSummary.scala:39-146)
+    at every site of a random (samples x sites) matrix with unset fields and absent genotypes, host and
+    device memory; then the record-level mirror against the host restatement."""
+    import torch
+    from avocado_b200 import _lib as L
+    from avocado_b200.joint import joint_depths
+    rng = np.random.default_rng(12)
+    S, N = 7, 3000
+    present = (rng.random((S, N)) > 0.25).astype(np.uint8)
+    present[:, :40] = 0
+    present[0, 20:40] = 1                                   # sites with no and with exactly one genotype
+    dp = np.where(rng.random((S, N)) > 0.2, rng.integers(0, 300, (S, N)), -1).astype(np.int32)
+    refdp = np.where(rng.random((S, N)) > 0.3, rng.integers(0, 200, (S, N)), -1).astype(np.int32)
+    sb = rng.integers(0, 80, (S, N, 4)).astype(np.int32)
+    sb[rng.random((S, N)) > 0.6] = -1
+    out = joint_depths(ctx, N, S, dp.ravel(), refdp.ravel(), sb.ravel(), present.ravel())
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a.ravel())).cuda()
+    out_d = joint_depths(ctx, N, S, d(dp), d(refdp), d(sb), d(present))
+    for k in out:
+        assert np.array_equal(np.asarray(out[k]), out_d[k].cpu().numpy()), k
+    names = dict(zip(L.SITE_DEPTH_COLUMNS, ("readDepth", "referenceReadDepth", "forwardReadDepth", "reverseReadDepth",
+                                            "forwardReferenceReadDepth", "reverseReferenceReadDepth")))
+    opt = lambda v: None if v < 0 else int(v)
+    for i in range(N):
+        idx = [s for s in range(S) if present[s, i]]
+        assert bool(out["annotated"][i]) == (len(idx) > 1)
+        if not idx:
+            assert all(out[c][i] == -1 for c in L.SITE_DEPTH_COLUMNS)
+            continue
+        want = oracle.variant_summary([(opt(dp[s, i]), opt(refdp[s, i]), [] if sb[s, i, 0] < 0 else sb[s, i].tolist())
+                                       for s in idx])
+        for c, name in names.items():
+            assert opt(out[c][i]) == want[name], (i, c)
+    # all genotypes present, no optional column at all
+    bare = joint_depths(ctx, N, S, dp.ravel())
+    assert np.all(bare["annotated"] == 1) and np.all(bare["ref_read_depth"] == -1) and np.all(bare["fwd_read_depth"] == -1)
+    assert np.array_equal(bare["read_depth"], np.where((dp >= 0).any(0), np.where(dp >= 0, dp, 0).sum(0), -1))
+
+
+def test_joint_caller_attaches_the_depth_annotation(ctx):
+    from avocado_b200.joint import JointAnnotatorCaller, calculate_annotations
+    from avocado_b200.records import ALT, REF, Genotype, Variant
+    ln = np.log
+    def gt(sample, pos, alleles, dp, refdp, sb):
+        v = Variant("ctg", pos, pos + 1, "A", "T")
+        return Genotype(variant=v, contigName="ctg", start=pos, end=pos + 1, sampleId=sample, alleles=alleles,
+                        genotypeQuality=30, genotypeLikelihoods=[ln(0.1), ln(0.8), ln(0.1)], nonReferenceLikelihoods=[],
+                        strandBiasComponents=sb, readDepth=dp, referenceReadDepth=refdp, alternateReadDepth=None,
+                        rmsMapQ=60.0, fisherStrandBiasPValue=0.0)
+    gts = [gt("a", 10, [REF, ALT], 10, 5, [2, 3, 4, 1]), gt("b", 10, [REF, ALT], 12, None, []),
+           gt("c", 10, [ALT, ALT], None, 7, [3, 4, 2, 3]), gt("a", 20, [REF, ALT], 9, 4, [1, 1, 1, 1])]
+    sites = {vc.variant.start: vc for vc in JointAnnotatorCaller.apply(gts, ctx=ctx)}
+    assert sites[10].annotation == calculate_annotations(gts[:3]) == \
+        {"readDepth": 22, "referenceReadDepth": 12, "forwardReadDepth": 11, "reverseReadDepth": 11,
+         "referenceForwardReadDepth": 5, "referenceReverseReadDepth": 7}
+    assert sites[20].annotation is None                     # one genotype at the site: no roll-up (:85-90)
+    with pytest.raises(ValueError):
+        JointAnnotatorCaller.apply([gt("a", 10, [REF, ALT], 1, 1, [0, 1, 2]), gt("b", 10, [REF, ALT], 1, 1, [])], ctx=ctx)

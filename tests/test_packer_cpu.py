@@ -259,7 +259,7 @@ def test_ctypes_mirrors_have_the_sizes_of_the_c_structs(tmp_path):
         "avo_text_out": L.TextOutStruct, "avo_packed_out": L.PackedOutStruct, "avo_filter_params": L.FilterParamsStruct,
         "avo_filter_out": L.FilterOutStruct, "avo_sample_rows": L.SampleRowsStruct, "avo_square_out": L.SquareOutStruct,
         "avo_trio": L.TrioStruct, "avo_joint_in": L.JointInStruct, "avo_joint_out": L.JointOutStruct,
-        "avo_synth_params": L.SynthParamsStruct,
+        "avo_synth_params": L.SynthParamsStruct, "avo_depths_in": L.DepthsInStruct, "avo_site_depths": L.SiteDepthsStruct,
     }
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "avocado_b200.h"\n#include "avocado_b200_synth.h"\nint main(void) {\n' +

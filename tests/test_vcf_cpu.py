@@ -130,3 +130,36 @@ def test_merge_variants_discovered_from_two_samples():
     merged = V.merge_discovered([os.path.join(GOLD, "NA12878.1_907170_A2C.vcf"), os.path.join(GOLD, "NA12878.1_907170_AG2A.vcf")])
     assert sorted(v.as_tuple() for v in merged) == [("1", 907167, 907168, "A", "T"), ("1", 907169, 907170, "A", "C"),
                                                     ("1", 907169, 907171, "AG", "A")]
+
+
+def test_reader_handles_ragged_records(tmp_path):
+    """Lines the fixtures do not contain: sites only, haploid and missing GT, phased input, dropped trailing
+    fields, a record without FORMAT values for one sample."""
+    text = "\n".join([
+        "##fileformat=VCFv4.2", "##contig=<ID=c2,length=100>", "##contig=<ID=c10,length=100>",
+        "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ts1\ts2",
+        "c10\t5\t.\tA\tT\t12.5\t.\t.\tGT:DP:GQ\t1\t./.",
+        "c2\t7\trs1\tAC\tA,<NON_REF>\t.\tPASS\tDP=3;DB\tGT:AD:PL\t0|1:3,4,0:10,0,20,30,40,50\t.",
+        "c2\t9\t.\tG\t<NON_REF>\t.\t.\tEND=20\tGT:DP\t0/0:8\t0/0",
+    ]) + "\n"
+    path = tmp_path / "ragged.vcf"
+    path.write_text(text)
+    gts, header = V.load_genotypes(path)
+    assert header.contigs == ["c2", "c10"] and header.samples == ["s1", "s2"] and len(gts) == 6
+    g = {(x.contigName, x.start, x.sampleId): x for x in gts}
+    assert g[("c10", 4, "s1")].alleles == [ALT] and g[("c10", 4, "s2")].alleles == [NO_CALL, NO_CALL]
+    d = g[("c2", 6, "s1")]
+    assert d.phased and d.alleles == [REF, ALT] and (d.referenceReadDepth, d.alternateReadDepth) == (3, 4)
+    assert np.allclose(d.genotypeLikelihoods, -np.array([10, 0, 20]) * np.log(10) / 10)
+    assert np.allclose(d.nonReferenceLikelihoods, -np.array([10, 30, 50]) * np.log(10) / 10)
+    assert g[("c2", 6, "s2")].alleles == [] and g[("c2", 6, "s2")].readDepth is None
+    b = g[("c2", 8, "s1")]
+    assert (b.start, b.end, b.variant.alternateAllele, b.readDepth) == (8, 20, None, 8)
+    assert [v.as_tuple() for v in V.load_variants(path)] == [("c10", 4, 5, "A", "T"), ("c2", 6, 8, "AC", "A")]
+    # written back: contigs in header order (c2 before c10), missing genotypes as ./.
+    out = tmp_path / "back.vcf"
+    V.write_vcf(out, header, V.group_by_variant(gts))
+    lines = [ln for ln in out.read_text().splitlines() if not ln.startswith("#")]
+    assert [ln.split("\t")[0] for ln in lines] == ["c2", "c2", "c10"]
+    assert lines[0].split("\t")[8:] == ["GT:AD:PL", "0|1:3,4:10,0,20", "./."]
+    assert lines[2].split("\t")[8:] == ["GT", "1", "./."]

@@ -79,13 +79,43 @@ gl = -np.abs(rng.normal(0, 6, (hi - lo, N, ns)))
 cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 cols = dict(n_sites=N, n_samples=hi - lo, n_states=ns, n_alt=cu(n_alt.ravel()), n_ref=cu((2 - n_alt).ravel()),
             n_other=cu(np.zeros_like(n_alt).ravel()), gl=cu(gl.ravel()))
+def per_call(fn, reps=30, warm_s=1.0):
+    """Median wall time per call (host clock around a synchronised call) and median of the library's own
+    CUDA-event total, after at least warm_s seconds of calls (an idle GPU needs that to clock up)."""
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < warm_s:
+        fn()
+        torch.cuda.synchronize()
+    wall, lib = [], []
+    for _ in range(reps):
+        t = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        wall.append((time.perf_counter() - t) * 1e3)
+        lib.append(ctx.timing()["ms_total"])
+    return float(np.median(wall)), float(np.median(lib))
+
+
 if world > 1:
     ms_j, _ = timed(lambda: joint_call_sharded(ctx, cols))
+    ms_lib = None
 else:
-    ms_j, _ = timed(lambda: joint_call(ctx, **cols))
-out["joint"] = {"samples": S, "sites": N, "ms": ms_j, "genotypes_per_s": S * N / (ms_j / 1e3),
+    ms_j, ms_lib = per_call(lambda: joint_call(ctx, **cols))
+out["joint"] = {"samples": S, "sites": N, "ms": ms_j, "ms_library_events": ms_lib, "genotypes_per_s": S * N / (ms_j / 1e3),
                 "note": "avo_joint (+ avo_joint_counts and two NCCL all-reduces when sharded), device-resident, "
                         "incl. output allocation by the Python wrapper"}
+# the depth roll-up of the same matrix (avo_joint_depths): 28 B in per genotype, 25 B out per site
+from avocado_b200.joint import joint_depths  # noqa: E402
+n_loc = hi - lo
+dp = cu(rng.integers(0, 60, (n_loc, N)).astype(np.int32).ravel())
+refdp = cu(rng.integers(0, 40, (n_loc, N)).astype(np.int32).ravel())
+sbc = cu(rng.integers(0, 20, (n_loc, N, 4)).astype(np.int32).ravel())
+ms_d, ms_d_lib = per_call(lambda: joint_depths(ctx, N, n_loc, dp, refdp, sbc))
+bytes_d = n_loc * N * 24 + N * 25
+out["joint_depths"] = {"samples": n_loc, "sites": N, "ms": ms_d, "ms_library_events": ms_d_lib,
+                       "gbps": bytes_d / (ms_d_lib / 1e3) / 1e9,
+                       "note": "avo_joint_depths on this rank's samples, device-resident, incl. output allocation "
+                               "by the Python wrapper; gbps = (24 B per genotype in + 25 B per site out) / library-event time"}
 if rank == 0:
     print(json.dumps(out))
 if world > 1:

@@ -105,6 +105,40 @@ def joint_depths(ctx, n_sites, n_samples, read_depth=None, ref_read_depth=None, 
     return {k: v[:n_sites] for k, v in out.items()}
 
 
+def reduce_site_depths(local: Dict[str, object], n_genotypes, group=None) -> Dict[str, object]:
+    """The exchange step of the depth roll-up when the cohort is sharded by sample: `local`
+    is this rank's joint_depths output (-1 = unset), `n_genotypes` its genotypes per site.  One all-reduce
+    (sum) of 13 int32 vectors -- the six sums, how many ranks have each field, the genotype counts -- gives
+    every rank the cohort's columns: a field is unset only if no rank has it (VariantSummary.merge is
+    associative), a site is annotated when the cohort has more than one genotype there.
+    CUDA tensors (NCCL) or numpy arrays (gloo)."""
+    import torch
+    import torch.distributed as dist
+    dev = _is_dev(local[L.SITE_DEPTH_COLUMNS[0]])
+    t = lambda a: a if dev else torch.from_numpy(np.ascontiguousarray(a))
+    cols = [t(local[c]).to(torch.int32) for c in L.SITE_DEPTH_COLUMNS]
+    pack = torch.stack([c.clamp(min=0) for c in cols] + [(c >= 0).to(torch.int32) for c in cols] +
+                       [t(n_genotypes).to(torch.int32)])
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)
+    out = {c: torch.where(pack[6 + k] > 0, pack[k], torch.full_like(pack[k], -1)) for k, c in enumerate(L.SITE_DEPTH_COLUMNS)}
+    out["annotated"] = (pack[12] > 1).to(torch.uint8)
+    return out if dev else {k: v.numpy() for k, v in out.items()}
+
+
+def joint_depths_sharded(ctx, n_sites, n_samples, read_depth=None, ref_read_depth=None, sb=None, present=None,
+                         group=None) -> Dict[str, object]:
+    """avo_joint_depths on this rank's samples, then reduce_site_depths over the ranks of `group`."""
+    local = joint_depths(ctx, n_sites, n_samples, read_depth, ref_read_depth, sb, present)
+    if present is None:
+        import torch
+        cnt = torch.full((n_sites,), n_samples, dtype=torch.int32, device=local["annotated"].device) \
+            if _is_dev(local["annotated"]) else np.full(n_sites, n_samples, np.int32)
+    else:
+        cnt = present.reshape(n_samples, n_sites).sum(0)
+    return reduce_site_depths(local, cnt, group)
+
+
 MINUS_TEN_DIV_LOG10 = -10.0 / np.log(10.0)
 
 

@@ -6,7 +6,8 @@
 Checks, on real GPUs, that (1) region-sharded discoverAndCall (avocado_b200.parallel) returns on
 every rank exactly the rows a single GPU computes for the whole batch, and (2) sample-sharded joint
 calling (avocado_b200.joint.joint_call_sharded: all-reduce of allele counts and of posterior sums
-over NCCL) reproduces the single-GPU cohort result.  Exits non-zero on any mismatch."""
+over NCCL) reproduces the single-GPU cohort result, and (3) so does the sample-sharded depth roll-up
+(joint_depths_sharded: one all-reduce of 13 int32 vectors).  Exits non-zero on any mismatch."""
 import os
 import sys
 
@@ -67,6 +68,20 @@ def main():
     em = ref["site_emitted"].astype(bool)
     assert np.allclose(q[em], q1[em], rtol=1e-9, atol=1e-9)
     assert np.array_equal(out["alt_alleles"].cpu().numpy(), n_alt.sum(0))
+    # ---- (3) the depth roll-up of the same cohort, sharded by sample -----------------------------
+    from avocado_b200.joint import joint_depths, joint_depths_sharded
+    present = (rng.random((S, N)) > 0.4).astype(np.uint8)
+    present[:, :50] = 0
+    present[1, 25:50] = 1
+    dp = np.where(rng.random((S, N)) > 0.3, rng.integers(0, 90, (S, N)), -1).astype(np.int32)
+    refdp = np.where(rng.random((S, N)) > 0.3, rng.integers(0, 90, (S, N)), -1).astype(np.int32)
+    sb = rng.integers(0, 30, (S, N, 4)).astype(np.int32)
+    sb[rng.random((S, N)) > 0.5] = -1
+    got = joint_depths_sharded(ctx, N, hi - lo, cu(dp[lo:hi].ravel()), cu(refdp[lo:hi].ravel()), cu(sb[lo:hi].ravel()),
+                               cu(present[lo:hi].ravel()))
+    want = joint_depths(ctx, N, S, dp.ravel(), refdp.ravel(), sb.ravel(), present.ravel())
+    for k, v in want.items():
+        assert np.array_equal(got[k].cpu().numpy(), np.asarray(v)), "depth column %s differs on rank %d" % (k, rank)
     dist.barrier()
     if rank == 0:
         print("multi_gpu_check ok: world=%d, %d sites region-sharded, %d x %d joint" % (world, table.n, S, N))

@@ -138,3 +138,66 @@ def _count_worker(rank, world, port, out_path):
             np.save(out_path, t.numpy())
     finally:
         dist.destroy_process_group()
+
+
+def test_depth_roll_up_reduced_over_gloo(tmp_path):
+    """The exchange of the depth roll-up for a cohort sharded by sample (joint.reduce_site_depths): per-rank
+    summaries (the oracle's VariantSummary stands in for avo_joint_depths, as in the other tests of this file)
+    reduced over two ranks equal the summary over all samples, unset fields and single-genotype sites included."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "depths.npz")
+    mp.spawn(_depth_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    want, count = _depth_columns(*_depth_inputs(), 0, 6)
+    for k, v in want.items():
+        assert np.array_equal(got[k], v), k
+    assert np.array_equal(got["annotated"], (count > 1).astype(np.uint8))
+    assert (got["read_depth"] == -1).any() and (got["annotated"] == 0).any() and (got["fwd_read_depth"] >= 0).any()
+
+
+def _depth_inputs():
+    rng = np.random.default_rng(21)
+    S, N = 6, 200
+    present = rng.random((S, N)) > 0.5
+    present[:, :10] = False
+    present[4, 5:10] = True
+    dp = np.where(rng.random((S, N)) > 0.5, rng.integers(0, 90, (S, N)), -1)
+    refdp = np.where(rng.random((S, N)) > 0.5, rng.integers(0, 90, (S, N)), -1)
+    sb = rng.integers(0, 30, (S, N, 4))
+    sb[rng.random((S, N)) > 0.4] = -1
+    return present, dp, refdp, sb
+
+
+def _depth_columns(present, dp, refdp, sb, lo, hi):
+    """What avo_joint_depths returns for samples [lo, hi): the oracle's merged VariantSummary per site."""
+    import avocado_oracle as oracle
+    from avocado_b200 import _lib as L
+    names = dict(zip(L.SITE_DEPTH_COLUMNS, ("readDepth", "referenceReadDepth", "forwardReadDepth", "reverseReadDepth",
+                                            "forwardReferenceReadDepth", "reverseReferenceReadDepth")))
+    N = present.shape[1]
+    cols = {c: -np.ones(N, np.int32) for c in L.SITE_DEPTH_COLUMNS}
+    opt = lambda v: None if v < 0 else int(v)
+    for i in range(N):
+        idx = [s for s in range(lo, hi) if present[s, i]]
+        if not idx:
+            continue
+        o = oracle.variant_summary([(opt(dp[s, i]), opt(refdp[s, i]), [] if sb[s, i, 0] < 0 else sb[s, i].tolist())
+                                    for s in idx])
+        for c, n in names.items():
+            cols[c][i] = -1 if o[n] is None else o[n]
+    return cols, present[lo:hi].sum(0).astype(np.int32)
+
+
+def _depth_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    from avocado_b200.joint import reduce_site_depths
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        local, count = _depth_columns(*_depth_inputs(), rank * 3, rank * 3 + 3)
+        out = reduce_site_depths(local, count)
+        if rank == 0:
+            np.savez(out_path, **out)
+    finally:
+        dist.destroy_process_group()

@@ -3,7 +3,7 @@
 CLI/TrioGenotyper.scala:230) and `saveAsVcf` (CLI/Jointer.scala:137-145, TrioCallerSuite.scala:239-251).
 
 ADAM (adam-core 0.24.0, `VariantContextConverter`) and htsjdk are not under /root/reference; what
-this module follows is pinned by the reference's own fixtures, committed under tests/golden/vcf/:
+this module follows is pinned by the reference's own fixtures, committed (gzip-compressed) under tests/golden/vcf/:
 
 * `trio.1_837214.vcf` -> TrioCaller -> `trio.1_837214.phased.vcf` compared byte for byte by the
   reference (TrioCallerSuite.scala:239-251): header order, FORMAT key order, Java float text, GT
@@ -18,6 +18,7 @@ float text beyond Float.toString's plain range) follows the VCF 4.2 text and is 
 """
 from __future__ import annotations
 
+import gzip
 import math
 from dataclasses import dataclass, field
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
@@ -177,8 +178,10 @@ class VcfRecord:
 
 
 def read_vcf(path) -> Tuple[VcfHeader, List[VcfRecord]]:
+    """Plain or gzip / bgzip compressed (.gz) VCF text."""
     header, records = VcfHeader(), []
-    with open(path, "rt") as fh:
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "rt") as fh:
         for raw in fh:
             line = raw.rstrip("\n").rstrip("\r")
             if not line:

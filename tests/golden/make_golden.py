@@ -61,17 +61,18 @@ VCF_FIXTURES = ["trio.1_837214.vcf", "trio.1_837214.phased.vcf", "gvcf_multialle
 
 
 def copy_vcfs():
-    """The reference's VCF test resources, byte for byte (they are data: the input and the expected
-    output of TrioCallerSuite.scala:239-251, the inputs of SquareOffReferenceModelSuite.scala:51-76 and
-    HardFilterGenotypesSuite.scala:368-375) -> tests/golden/vcf/."""
-    import shutil
+    """The reference's VCF test resources (they are data: the input and the expected output of
+    TrioCallerSuite.scala:239-251, the inputs of SquareOffReferenceModelSuite.scala:51-76,
+    HardFilterGenotypesSuite.scala:368-375 and MergeDiscoveredSuite.scala:25-33), gzip-compressed with a
+    fixed time stamp -> tests/golden/vcf/*.vcf.gz (decompressed they are the reference's bytes)."""
     out_dir = os.path.join(os.path.dirname(__file__), "vcf")
     os.makedirs(out_dir, exist_ok=True)
     cli = "/root/reference/avocado-cli/src/test/resources"     # MergeDiscoveredSuite.scala:25-33
     for src_dir, name in [(RES, n) for n in VCF_FIXTURES] + [(cli, "NA12878.1_907170_AG2A.vcf"), (cli, "NA12878.1_907170_A2C.vcf")]:
-        shutil.copyfile(os.path.join(src_dir, name), os.path.join(out_dir, name))
-        os.chmod(os.path.join(out_dir, name), 0o644)
-        print(name, os.path.getsize(os.path.join(out_dir, name)))
+        with open(os.path.join(src_dir, name), "rb") as src, \
+                gzip.GzipFile(os.path.join(out_dir, name + ".gz"), "wb", mtime=0) as dst:
+            dst.write(src.read())
+        print(name, os.path.getsize(os.path.join(out_dir, name + ".gz")))
 
 
 if __name__ == "__main__":

@@ -203,7 +203,7 @@ def test_reference_gvcf_fixture_squares_off_like_the_oracle(oracle, ctx):
     from avocado_b200 import _lib as L, batch as B, vcf as V
     from avocado_b200.records import ALT, Variant
     from avocado_b200.squareoff import extract_variants, square_off_packed
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vcf", "gvcf_multiallelic.g.vcf")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vcf", "gvcf_multiallelic.g.vcf.gz")
     gts, header = V.load_genotypes(path)
     found = extract_variants([g.variant for g in gts], [ALT in g.alleles for g in gts])
     assert len(found) == 3

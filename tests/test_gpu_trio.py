@@ -75,9 +75,10 @@ def test_trio_vcf_end_to_end_matches_the_reference_file(ctx, tmp_path):
     from avocado_b200 import vcf as V
     from avocado_b200.trio import TrioCaller
     gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vcf")
-    gts, header = V.load_genotypes(os.path.join(gold, "trio.1_837214.vcf"))
+    import gzip
+    gts, header = V.load_genotypes(os.path.join(gold, "trio.1_837214.vcf.gz"))
     contexts = TrioCaller.apply(gts, "NA12891", "NA12892", "NA12878", ctx=ctx)
     out = tmp_path / "trio.vcf"
     V.write_vcf(out, header, contexts)
-    with open(out, "rb") as a, open(os.path.join(gold, "trio.1_837214.phased.vcf"), "rb") as b:
+    with open(out, "rb") as a, gzip.open(os.path.join(gold, "trio.1_837214.phased.vcf.gz"), "rb") as b:
         assert a.read() == b.read()

@@ -1,4 +1,4 @@
-"""VCF in / out (avocado_b200/vcf.py) against the reference's own VCF fixtures (tests/golden/vcf/, copied
+"""VCF in / out (avocado_b200/vcf.py) against the reference's own VCF fixtures (tests/golden/vcf/*.vcf.gz, made
 by tests/golden/make_golden.py): the byte-for-byte expectation of TrioCallerSuite.scala:239-251, the
 loadGenotypes -> extractVariants expectations of SquareOffReferenceModelSuite.scala:51-76 and the header
 lines of HardFilterGenotypesSuite.scala:368-375.  The trio decision itself comes from the oracle here
@@ -18,12 +18,13 @@ CODE = {REF: 0, ALT: 1, OTHER_ALT: 2, NO_CALL: 3}
 
 
 def _bytes(path):
-    with open(path, "rb") as fh:
+    import gzip
+    with (gzip.open if str(path).endswith(".gz") else open)(path, "rb") as fh:
         return fh.read()
 
 
 def test_round_trip_reproduces_the_input_file(tmp_path):
-    gts, header = V.load_genotypes(os.path.join(GOLD, "trio.1_837214.vcf"))
+    gts, header = V.load_genotypes(os.path.join(GOLD, "trio.1_837214.vcf.gz"))
     assert header.samples == ["NA12891", "NA12892", "NA12878"] and len(gts) == 3
     g = gts[1]
     assert (g.contigName, g.start, g.end, g.variant.referenceAllele, g.variant.alternateAllele) == ("chr1", 837213, 837214, "G", "C")
@@ -35,12 +36,12 @@ def test_round_trip_reproduces_the_input_file(tmp_path):
     assert gts[0].filtersFailed == ["HETSNPMINAF"] and not gts[0].filtersPassed
     out = tmp_path / "same.vcf"
     V.write_vcf(out, header, V.group_by_variant(gts))
-    assert _bytes(out) == _bytes(os.path.join(GOLD, "trio.1_837214.vcf")) + b"\n"      # the input lacks the final newline
+    assert _bytes(out) == _bytes(os.path.join(GOLD, "trio.1_837214.vcf.gz")) + b"\n"      # the input lacks the final newline
 
 
 def test_trio_call_end_to_end_matches_the_reference_file(oracle, tmp_path):
     """TrioCallerSuite.scala:239-251: loadGenotypes -> TrioCaller -> saveAsVcf == trio.1_837214.phased.vcf."""
-    gts, header = V.load_genotypes(os.path.join(GOLD, "trio.1_837214.vcf"))
+    gts, header = V.load_genotypes(os.path.join(GOLD, "trio.1_837214.vcf.gz"))
     by = {g.sampleId: g for g in gts}
     p1, p2, ch = by["NA12891"], by["NA12892"], by["NA12878"]
     r = oracle.trio_process(*[[CODE[a] for a in g.alleles] for g in (p1, p2, ch)])
@@ -49,11 +50,11 @@ def test_trio_call_end_to_end_matches_the_reference_file(oracle, tmp_path):
     child = dataclasses.replace(ch, phased=True, alleles=[names[a] for a in r["childAlleles"]])
     out = tmp_path / "trio.vcf"
     V.write_vcf(out, header, V.group_by_variant([p1, p2, child]))
-    assert _bytes(out) == _bytes(os.path.join(GOLD, "trio.1_837214.phased.vcf"))
+    assert _bytes(out) == _bytes(os.path.join(GOLD, "trio.1_837214.phased.vcf.gz"))
 
 
 def test_default_header_lines_are_those_of_the_reference_files():
-    ref_lines = set(V.read_vcf(os.path.join(GOLD, "trio.1_837214.phased.vcf"))[0].lines)
+    ref_lines = set(V.read_vcf(os.path.join(GOLD, "trio.1_837214.phased.vcf.gz"))[0].lines)
     for ln in V.DEFAULT_FORMAT_LINES + V.DEFAULT_INFO_LINES:
         assert ln in ref_lines, ln
     assert len([ln for ln in ref_lines if ln.startswith("##FORMAT") or ln.startswith("##INFO")]) == \
@@ -72,7 +73,7 @@ def test_default_header_lines_are_those_of_the_reference_files():
 def test_adding_filters_adds_eighteen_header_lines():
     """HardFilterGenotypesSuite.scala:368-375 ("test adding filters": every filter enabled -> + 18 lines)."""
     every = FilterArgs(maxSnpPhredStrandBias=20.0, maxIndelPhredStrandBias=20.0, minIndelRMSMappingQuality=30.0)
-    _, header = V.load_genotypes(os.path.join(GOLD, "random.vcf"))
+    _, header = V.load_genotypes(os.path.join(GOLD, "random.vcf.gz"))
     assert len(header.with_lines(V.filter_header_lines(every)).lines) == len(header.lines) + 18
     assert len(V.filter_header_lines(FilterArgs())) == 15          # the CLI defaults leave three filters off
 
@@ -80,7 +81,7 @@ def test_adding_filters_adds_eighteen_header_lines():
 def test_gvcf_extract_variants_matches_the_reference_suite():
     """SquareOffReferenceModelSuite.scala:51-76 on gvcf_multiallelic.g.vcf."""
     from avocado_b200.squareoff import extract_variants
-    gts, header = V.load_genotypes(os.path.join(GOLD, "gvcf_multiallelic.g.vcf"))
+    gts, header = V.load_genotypes(os.path.join(GOLD, "gvcf_multiallelic.g.vcf.gz"))
     assert header.samples == ["NA12878i"]
     found = extract_variants([g.variant for g in gts], [ALT in g.alleles for g in gts])
     assert len(found) == 3 and all(v.contigName == "chr22" for v in found)
@@ -105,7 +106,7 @@ def test_gvcf_extract_variants_matches_the_reference_suite():
     assert np.allclose(snv.genotypeLikelihoods, -np.array([41, 3, 0]) * np.log(10.0) / 10)
     assert np.allclose(snv.nonReferenceLikelihoods, -np.array([41, 41, 41]) * np.log(10.0) / 10)
     assert (snv.referenceReadDepth, snv.alternateReadDepth) == (0, 1)
-    assert V.load_variants(os.path.join(GOLD, "gvcf_multiallelic.g.vcf"))[0].as_tuple() == ("chr22", 16157602, 16157603, "G", "C")
+    assert V.load_variants(os.path.join(GOLD, "gvcf_multiallelic.g.vcf.gz"))[0].as_tuple() == ("chr22", 16157602, 16157603, "G", "C")
 
 
 @pytest.mark.parametrize("value,text", [(6.689699, "6.689699"), (-0.0, "-0.0"), (60.0, "60.0"), (59.357906, "59.357906"),
@@ -118,7 +119,7 @@ def test_java_float_text(value, text):
 
 def test_site_quality_text(tmp_path):
     from avocado_b200.joint import VariantContext
-    gts, header = V.load_genotypes(os.path.join(GOLD, "trio.1_837214.vcf"))
+    gts, header = V.load_genotypes(os.path.join(GOLD, "trio.1_837214.vcf.gz"))
     vc = V.group_by_variant(gts)[0]
     for q, text in ((16.07, "16.07"), (564.734, "564.73"), (30.0, "30"), (float("nan"), ".")):
         line = V.format_record(VariantContext(vc.variant, q, vc.genotypes, float("nan")), header.samples)
@@ -127,7 +128,7 @@ def test_site_quality_text(tmp_path):
 
 def test_merge_variants_discovered_from_two_samples():
     """MergeDiscoveredSuite.scala:25-33: two site lists sharing one variant -> 3 distinct variants."""
-    merged = V.merge_discovered([os.path.join(GOLD, "NA12878.1_907170_A2C.vcf"), os.path.join(GOLD, "NA12878.1_907170_AG2A.vcf")])
+    merged = V.merge_discovered([os.path.join(GOLD, "NA12878.1_907170_A2C.vcf.gz"), os.path.join(GOLD, "NA12878.1_907170_AG2A.vcf.gz")])
     assert sorted(v.as_tuple() for v in merged) == [("1", 907167, 907168, "A", "T"), ("1", 907169, 907170, "A", "C"),
                                                     ("1", 907169, 907171, "AG", "A")]
 

@@ -105,6 +105,13 @@ constexpr int DISC_WARPS = DISC_THREADS / 32;
 constexpr int DISC_Q = 256;             // indel events of one tile kept in shared memory
 constexpr int DISC_SHORT = 3;           // reads with at most this many operators are walked at once
 constexpr int DISC_LONGQ = 1024;        // reads with more operators: walked afterwards, lanes full
+#ifdef AVO_DISC_CQ
+// Experiment (off by default, NOT yet run on a GPU; profiles/r6_discover_regions.txt): SNV candidates are
+// queued per warp while the reads are walked and counted afterwards by all 32 lanes, instead of being
+// counted on the spot by the ~10 lanes that hold a mismatch at that step of their walk.
+constexpr int DISC_CQ = 96;             // queued candidates per warp
+constexpr int DISC_CQ_DRAIN = 48;       // counted once this many are waiting
+#endif
 
 struct __align__(16) DiscSmem {
   // fast path: SNV candidate counts per position and alternate base, two 16-bit fields per word
@@ -121,6 +128,10 @@ struct __align__(16) DiscSmem {
   int32_t n_long;
   int32_t exotic;                       // a candidate with a non-ACGT base was seen: use the slow path
   int32_t hotpos[DISC_HB];              // window offsets of the current batch's hot positions
+#ifdef AVO_DISC_CQ
+  uint32_t cq[DISC_WARPS][DISC_CQ];     // (window offset << 8) | (ref << 4 | alt)
+  int32_t cq_n[DISC_WARPS];             // candidates appended since the warp's last drain (may exceed DISC_CQ)
+#endif
 };
 
 __device__ __forceinline__ void disc_indel_append(const DReads& R, const DIndelList& L, int32_t pos,
@@ -214,6 +225,9 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
 
   for (int i = tid; i < 2 * DISC_W; i += DISC_THREADS) (&sm.cnt[0][0])[i] = 0;
   for (int i = tid; i < DISC_W / 8; i += DISC_THREADS) sm.refm[i] = 0;
+#ifdef AVO_DISC_CQ
+  if (lane == 0) sm.cq_n[warp] = 0;
+#endif
   for (;;) {
     __syncthreads();
     if (tid == 0) { sm.tile = atomicAdd(tile_counter, 1); sm.n_q = 0; sm.n_long = 0; sm.exotic = 0; }
@@ -238,6 +252,46 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
     // one match, or one mismatch run after the leading match, and are handled on the spot; the
     // others are queued and walked afterwards so that no lane idles while a neighbour works
     // through a long operator list.
+#ifdef AVO_DISC_CQ
+    auto count_candidate = [&](uint32_t o, uint32_t pair) {
+      const uint32_t refn = (pair >> 4) & 15u, altn = pair & 15u;
+      if (!(((0x116u >> refn) & (0x116u >> altn)) & 1u)) { sm.exotic = 1; return; }
+      const int ai = (int)((altn >> 1) - (altn >> 3));
+      atomicAdd(&sm.cnt[ai >> 1][o], 1u << ((ai & 1) * 16));
+      atomicOr(&sm.refm[o >> 3], refn << ((o & 7) * 4));
+    };
+    // wlo fits in 32 bits (win0 <= wlo < max_end); a candidate of a read in [rLo, rHi) lies within
+    // max_span + DISC_W of it, so the unsigned difference cannot wrap into the window
+    const uint32_t wlo32 = (uint32_t)(int32_t)wlo;
+    auto snp = [&](int32_t pos, uint32_t pair) {
+      const uint32_t o = (uint32_t)pos - wlo32;
+      if (o >= (uint32_t)DISC_W) return;
+      // the lanes that arrive here together take consecutive slots: one shared atomic per group
+      const unsigned grp = __activemask();
+      const int leader = __ffs(grp) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&sm.cq_n[warp], __popc(grp));
+      base = __shfl_sync(grp, base, leader);
+      const int slot = base + __popc(grp & ((1u << lane) - 1u));
+      if (slot < DISC_CQ) sm.cq[warp][slot] = (o << 8) | (pair & 255u);
+      else count_candidate(o, pair);                       // queue full: counted on the spot
+    };
+    auto drain = [&]() {                                   // every lane of the warp must call it
+      __syncwarp();
+      const int n = min(sm.cq_n[warp], DISC_CQ);
+      for (int i = lane; i < n; i += 32) {
+        const uint32_t e = sm.cq[warp][i];
+        count_candidate(e >> 8, e & 255u);
+      }
+      __syncwarp();
+      if (lane == 0) sm.cq_n[warp] = 0;
+      __syncwarp();
+    };
+    for (int32_t r0 = rLo; r0 < rHi; r0 += DISC_THREADS) {   // the same trip count for every lane of a warp
+      const int32_t r = r0 + tid;
+      if (r < rHi) do {
+      const MetaA a = load_meta_a(R.meta, r);
+#else
     auto snp = [&](int32_t pos, uint32_t pair) {
       const int64_t o = (int64_t)pos - wlo;
       if (o < 0 || o >= DISC_W) return;
@@ -250,6 +304,7 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
     };
     for (int32_t r = rLo + tid; r < rHi; r += DISC_THREADS) {
       const MetaA a = load_meta_a(R.meta, r);
+#endif
       const MetaB m = load_meta_b(R.meta, r);
       if (r >= rOwn) {
         if (R.coords) R.coords[r] = make_int2(a.start, a.end);   // dense (start, end) copy for the join
@@ -272,13 +327,31 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
       }
     general:
       {
+#ifdef AVO_DISC_AGG
+        // experiment (off by default, not yet run on a GPU): one shared atomic per group of lanes, not per lane
+        const unsigned grp = __activemask();
+        const int leader = __ffs(grp) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&sm.n_long, __popc(grp));
+        base = __shfl_sync(grp, base, leader);
+        const int slot = base + __popc(grp & ((1u << lane) - 1u));
+#else
         const int slot = atomicAdd(&sm.n_long, 1);
+#endif
         if (slot < DISC_LONGQ) { sm.longq[slot] = r; continue; }
       }
       walk_discover(R, a, m, thr, snp, [&](uint32_t k, int32_t anchor) {
         if ((int64_t)anchor >= wlo && (int64_t)anchor < wlo + DISC_W) disc_handle_indel(R, L, r, k, thr);
       });
+#ifdef AVO_DISC_CQ
+      } while (0);                       // `continue` above leaves the read, not the warp's iteration
+      __syncwarp();
+      if (sm.cq_n[warp] >= DISC_CQ_DRAIN) drain();
+#endif
     }
+#ifdef AVO_DISC_CQ
+    drain();
+#endif
     __syncthreads();
     {
       const int nl = min(sm.n_long, DISC_LONGQ);
@@ -292,6 +365,9 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
                         else disc_handle_indel(R, L, r, k, thr);
                       });
       }
+#ifdef AVO_DISC_CQ
+      drain();                           // before the barrier: the emission below reads the counters
+#endif
     }
     __syncthreads();
     {

@@ -1,11 +1,12 @@
 #!/bin/bash
-# The prepared k_discover_tiles experiments, end to end.
+# The prepared kernel experiments (k_discover_tiles candidate queue /
+# aggregated slots, k_call_observe locate-and-prefetch), end to end.
 #   here (no GPU):  bash scripts/try_disc_variants.sh build
 #   GPU box:        bash scripts/try_disc_variants.sh run        (parity tests per variant, then the A/B bench)
 # A variant is only worth adopting if every parity test passes with AVO_LIB pointing at it.
 set -u
-VARIANTS=(cq agg cqagg)
-FLAGS=("-DAVO_DISC_CQ" "-DAVO_DISC_AGG" "-DAVO_DISC_CQ -DAVO_DISC_AGG")
+VARIANTS=(cq agg cqagg loc)
+FLAGS=("-DAVO_DISC_CQ" "-DAVO_DISC_AGG" "-DAVO_DISC_CQ -DAVO_DISC_AGG" "-DAVO_OBS_LOCATE")
 if [ "${1:-}" = "build" ]; then
   args=()
   for i in "${!VARIANTS[@]}"; do args+=("${VARIANTS[$i]}" "${FLAGS[$i]}"); done

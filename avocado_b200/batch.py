@@ -212,6 +212,46 @@ class ReadBatch:
         return out.with_stats() if self.stats is not None else out
 
 
+def merge_batches(batches: Sequence[ReadBatch]) -> ReadBatch:
+    """The union of several batches of ONE contig as a batch of its own, stably sorted by start
+    (`reads.union(...)` of CLI/TrioGenotyper.scala:216: discovery over a trio counts the candidates
+    of all three samples together).  Payload, operator and mismatch columns are concatenated, the
+    records are merged and their three offsets rebased.  Host (numpy) or device (torch) batches."""
+    assert len(batches) > 0 and len({b.on_device for b in batches}) == 1
+    assert len({b.contig_id for b in batches}) == 1
+    dev = batches[0].on_device
+    out = ReadBatch(sum(b.n_reads for b in batches), sum(b.n_blocks for b in batches),
+                    sum(b.n_ops for b in batches), sum(b.n_refb for b in batches), batches[0].contig_id)
+    blk = np.cumsum([0] + [b.n_blocks for b in batches])
+    ops = np.cumsum([0] + [b.n_ops for b in batches])
+    rfb = np.cumsum([0] + [b.n_refb for b in batches])
+    if dev:
+        import torch
+        recs = []
+        for k, b in enumerate(batches):
+            m = b.meta[:b.n_reads * 32].view(torch.int32).view(-1, 8).clone()
+            m[:, 2] += int(blk[k]); m[:, 3] += int(ops[k]); m[:, 4] += int(rfb[k])    # wraps like uint32
+            recs.append(m)
+        m = torch.cat(recs)
+        order = torch.sort(m[:, 0], stable=True).indices
+        out.meta = m[order].contiguous().view(torch.uint8).view(-1)
+        out.payload = torch.cat([b.payload[:b.n_blocks * BLOCK_BYTES] for b in batches] + [batches[0].payload[:0].new_zeros(16)])
+        out.ops = torch.cat([b.ops[:b.n_ops] for b in batches] + [batches[0].ops[:0].new_zeros(4)])
+        out.refb = torch.cat([b.refb[:b.n_refb] for b in batches] + [batches[0].refb[:0].new_zeros(16)])
+    else:
+        recs = []
+        for k, b in enumerate(batches):
+            m = b.meta[:b.n_reads].copy()
+            m["seq_off"] += np.uint32(blk[k]); m["op_off"] += np.uint32(ops[k]); m["refb_off"] += np.uint32(rfb[k])
+            recs.append(m)
+        m = np.concatenate(recs)
+        out.meta = np.ascontiguousarray(m[np.argsort(m["start"], kind="stable")])
+        out.payload = np.concatenate([b.payload[:b.n_blocks * BLOCK_BYTES] for b in batches] + [np.zeros(16, np.uint8)])
+        out.ops = np.concatenate([b.ops[:b.n_ops] for b in batches] + [np.zeros(4, np.uint32)])
+        out.refb = np.concatenate([b.refb[:b.n_refb] for b in batches] + [np.zeros(16, np.uint8)])
+    return out.with_stats()
+
+
 _TORCH_VIEW = {np.dtype(np.uint32): np.int32, np.dtype(np.uint16): np.int16}
 
 

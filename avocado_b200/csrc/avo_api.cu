@@ -28,7 +28,7 @@ enum Slot {
   SL_CNV, SL_STATS, SL_SMALL, SL_RIDX, SL_SIDX, SL_TEMP, SL_LUT,
   SL_RES,                      // one block holding every result column
   SL_U_START, SL_U_REFLEN, SL_U_ALTLEN, SL_U_COUNT, SL_U_SRC,
-  SL_L_POS, SL_L_LENS, SL_L_NIBS, SL_L_SRC, SL_L_BLK, SL_L_HASH,
+  SL_L_POS, SL_L_REFLEN, SL_L_ALTLEN, SL_L_NIBS, SL_L_SRC, SL_L_BLK, SL_L_HASH,
   SL_C_RBASE, SL_C_BLEN, SL_C_BOFF, SL_C_BUCKETS,
   SL_G_PBASE, SL_G_NBLK, SL_G_SLOT, SL_G_CLO, SL_G_IDX, SL_G_BLK0, SL_G_COMPACT,
   SL_AS_FLAG, SL_AS_JPOS, SL_AS_JR, SL_AS_JIDX, SL_AS_JCOORD, SL_AS_COVER, SL_AS_SCOVER, SL_AS_WCOUNT, SL_AS_WBASE,
@@ -61,6 +61,7 @@ struct avo_ctx {
   avo_timing timing{};
   cudaEvent_t ev[8] = {};
   int64_t indel_guess = 0;         // indel candidates seen by the previous discovery (sizes the table)
+  int disc_blocks_per_sm = 0;      // resident CTAs of k_discover_tiles per SM (occupancy query, once)
   BatchStats* h_stats = nullptr;   // pinned
   int32_t* h_small = nullptr;      // pinned scratch (16 ints)
   // device -> host results travel through one page-locked staging buffer (a few large DMA copies
@@ -206,6 +207,8 @@ int upload_reads(avo_ctx* ctx, const avo_read_batch* r, bool sparse, DReads* R, 
   R->n = r->n_reads;
   R->contig = r->contig_id;
   R->qhead_short = 0;
+  R->n_ops = r->n_ops;
+  R->n_refb = r->n_refb;
   {
     void* c;
     CKS(get_buf(ctx, SL_COORDS, n * sizeof(int2), &c));
@@ -821,7 +824,8 @@ int discover_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, bool 
     U.n = small + 10;
     Lst.capacity = (int32_t)std::min<int64_t>(lcap, INT32_MAX);
     CKS(get_buf(ctx, SL_L_POS, (size_t)lcap * 4, &q)); Lst.pos = (int32_t*)q;
-    CKS(get_buf(ctx, SL_L_LENS, (size_t)lcap * 4, &q)); Lst.lens = (uint32_t*)q;
+    CKS(get_buf(ctx, SL_L_REFLEN, (size_t)lcap * 4, &q)); Lst.ref_len = (int32_t*)q;
+    CKS(get_buf(ctx, SL_L_ALTLEN, (size_t)lcap * 4, &q)); Lst.alt_len = (int32_t*)q;
     CKS(get_buf(ctx, SL_L_NIBS, (size_t)lcap * 4, &q)); Lst.nibs = (uint32_t*)q;
     CKS(get_buf(ctx, SL_L_SRC, (size_t)lcap * 4, &q)); Lst.src = (uint32_t*)q;
     CKS(get_buf(ctx, SL_L_BLK, (size_t)lcap * 4, &q)); Lst.blk = (uint32_t*)q;
@@ -837,7 +841,7 @@ int discover_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, bool 
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     int nl = 0;
     CK(launch_discover_tiles(R, p->min_phred_discover, p->min_obs_discover, X, hs, verify ? 1 : 0, U, Lst,
-                             small + 8, small + 9, ctx->num_sms, ctx->stream, &nl));
+                             small + 8, small + 9, ctx->num_sms, &ctx->disc_blocks_per_sm, ctx->stream, &nl));
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     ctx->timing.n_launches += nl;
     ctx->timing.n_tile_launches += nl;

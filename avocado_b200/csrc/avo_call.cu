@@ -75,10 +75,6 @@ __global__ void k_site_buckets(DReads R, DSites S, DIndex X, int32_t max_span, i
 // for that (read, site) pair in the compact array minus the first block gathered -- what takes the
 // place of the read's seq_off while that site is classified.  PAIRS is a template parameter so that
 // the device-resident route compiles to a kernel that never looks at pair_blk0.
-#ifdef AVO_OBS_LOCATE
-__device__ bool read_index_range(const DReads& R, uint32_t ob, uint32_t no, int32_t start, int32_t vs, int32_t ve,
-                                 uint32_t* lo_out, uint32_t* hi_out);
-#endif
 
 template <bool PAIRS>
 __device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
@@ -103,20 +99,6 @@ __device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, co
   };
 
   const int ns = b - a;
-#ifdef AVO_OBS_LOCATE
-  // Experiment (off by default, not yet run on a GPU; profiles/r6_lanes_k_call_observe.txt): the lanes of a
-  // warp reach the payload block of "their" site at different steps of their operator walks, so few
-  // loads are in flight at a time.  Locate first (operators only), ask L2 for every block, then classify.
-  for (int j = 0; j < ns; ++j) {
-    const int32_t vs = __ldg(S.start + a + j);
-    uint32_t lo, hi;
-    if (read_index_range(R, rc.ob, rc.no, rc.start, vs, vs + __ldg(S.ref_len + a + j), &lo, &hi)) {
-      uint32_t w;
-      const uint8_t* blk = pl_block(R.payload, PAIRS ? pair_blk0[j] : rc.sb, lo, w);
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(blk));
-    }
-  }
-#endif
   uint32_t cats[MAX_LOCAL_SITES];
   int32_t qs[MAX_LOCAL_SITES];
   const bool cached = ns <= MAX_LOCAL_SITES;

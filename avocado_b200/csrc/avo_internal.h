@@ -20,6 +20,7 @@ struct DReads {
   const uint32_t* ops;
   const uint8_t* refb;
   int32_t qhead_short;         // 1: only the first two bytes of meta.qhead are valid (6-byte wire form)
+  int64_t n_ops, n_refb;       // entries of ops / bytes of refb (bounds of the staged copies)
 };
 static_assert(sizeof(avo_read_meta) == 32, "avo_read_meta must be one 32-byte sector");
 
@@ -284,7 +285,8 @@ struct DIndelList {
   int32_t capacity;
   int32_t* n;           // device counter
   int32_t* pos;
-  uint32_t* lens;       // (ref_len << 16) | alt_len
+  int32_t* ref_len;     // full 32-bit lengths: operators are 28-bit (a 70 kb deletion is one candidate)
+  int32_t* alt_len;
   uint32_t* nibs;       // (lastRef nibble << 4) | anchor (alt[0] / read base) nibble
   uint32_t* src;        // INS: index (within the read) of the first inserted base; DEL: nibble index (2 * byte) into refb
   uint32_t* blk;        // INS: the read's first payload block
@@ -298,7 +300,7 @@ cudaError_t launch_discover_tiles(const DReads& R, int32_t thr, int32_t min_obs 
                                   const DIndex& X, const BatchStats& hstats, int verify,
                                   const DDiscoverOut& out, const DIndelList& indels,
                                   int32_t* d_tile_counter, int32_t* d_flags, int num_sms,
-                                  cudaStream_t s, int* n_launches);
+                                  int* blocks_per_sm, cudaStream_t s, int* n_launches);
 
 // groups the *L.n (device counter) indel candidates; survivors are appended to `out`, their
 // allele-nibble footprints added to *d_nib, their number to *d_nsurv.  Sets DISC_FLAG_TABLE_FULL

@@ -130,9 +130,14 @@ __global__ void k_joint_recall(DJointIn J, const int32_t* __restrict__ alt, cons
       const int n = min(copies + 1, ns);                         // genotypeLikelihoods.size
       const double* gl = J.gl + k * ns;
       double nn[JNS], prior[JNS];
-      if (priors_defined && others == 0 && n >= 1) {             // :191-234
+      // allele counts come from the caller: a negative count is not a genotype (left untouched, flags 0);
+      // more copies than the lgamma table holds (AVO_MAX_PLOIDY + 2) fall back to the device lgamma
+      const bool sane = o_alt >= 0 && o_ref >= 0 && others >= 0;
+      auto lg = [&](int v) { return v <= AVO_MAX_PLOIDY + 2 ? lgam[v] : lgamma((double)v); };
+      if (!sane) {
+      } else if (priors_defined && others == 0 && n >= 1) {      // :191-234
         for (int c = 0; c < n; ++c) {                            // breeze Binomial.logProbabilityOf
-          const double comb = __dadd_rn(__dadd_rn(lgam[copies + 1], -lgam[c + 1]), -lgam[copies - c + 1]);
+          const double comb = __dadd_rn(__dadd_rn(lg(copies + 1), -lg(c + 1)), -lg(copies - c + 1));
           prior[c] = __dadd_rn(__dadd_rn(comb, __dmul_rn((double)c, lp)), __dmul_rn((double)(copies - c), lq));
           nn[c] = __dadd_rn(prior[c], gl[c]);
         }

@@ -254,6 +254,7 @@ void pack_chunk(const avo_text_reads* in, avo_packed_out* out, Chunk& ch) {
     // discovery additionally indexes qual(i) from 0 and sequence up to the same length: a read
     // whose strings are too short would crash the reference job; it is dropped here instead
     if (ok && ((int64_t)need > lseq || (int64_t)need > lqual)) ok = false;
+    if (ok && sc.ops.size() > 0xFFFFu) flags |= AVO_READ_OPS_DROPPED;   // does not fit the record: flagged, not silent
     if (!ok || sc.ops.size() > 0xFFFFu) { sc.ops.clear(); sc.refb.clear(); }
     const uint64_t lpad = ((uint64_t)lseq + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES;   // payload blocks of the read
     if (ch.ops.size() + sc.ops.size() > 0xFFFFFFFFull || ch.refb.size() + sc.refb.size() > 0xFFFFFFFFull) {

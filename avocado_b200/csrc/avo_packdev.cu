@@ -234,7 +234,9 @@ __device__ __forceinline__ Extracted extract_read(const ReadText& t, uint32_t* o
   // a read whose strings are shorter than the CIGAR's read length is dropped from discovery;
   // more than 65535 operators do not fit the record
   if (x.ok && ((int64_t)x.need > t.lseq || (int64_t)x.need > t.lqual)) x.ok = false;
-  if (flags_out) *flags_out = ((int64_t)x.need > t.lseq || (int64_t)x.need > t.lqual) ? AVO_READ_SKIP_CALL : 0;
+  if (flags_out)
+    *flags_out = (((int64_t)x.need > t.lseq || (int64_t)x.need > t.lqual) ? AVO_READ_SKIP_CALL : 0) |
+                 ((x.ok && x.n_ops > 0xFFFFu) ? AVO_READ_OPS_DROPPED : 0);      // flagged, not silent
   if (!x.ok || x.n_ops > 0xFFFFu) { x.n_ops = 0; x.n_refb = 0; }
   return x;
 }
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(128) k_pack_records(DText T, const PackOffsets
     q = q < 0 ? 0 : q;
     qhead |= (uint32_t)q << (8 * k);
   }
-  const uint8_t flags = (uint8_t)(((t.rf & 2) ? AVO_READ_NEGATIVE_STRAND : 0) | (has_mapq ? skip : AVO_READ_SKIP_CALL));
+  const uint8_t flags = (uint8_t)(((t.rf & 2) ? AVO_READ_NEGATIVE_STRAND : 0) | skip | (has_mapq ? 0 : AVO_READ_SKIP_CALL));
   // the record as two 16-byte stores: (start, end, seq_off, op_off | refb_off, n_ops/mapq/flags, qhead, l_seq)
   uint4* rec = reinterpret_cast<uint4*>(out.meta + o.k);
   rec[0] = make_uint4((uint32_t)(int32_t)T.start[i], (uint32_t)(int32_t)T.end[i], (uint32_t)o.b, (uint32_t)o.o);

@@ -71,9 +71,13 @@ enum {
 /* flags[] bits */
 enum {
   AVO_READ_NEGATIVE_STRAND = 1, /* AlignmentRecord.readNegativeStrand */
-  AVO_READ_SKIP_CALL = 2        /* the reference's observeRead would throw for this read (null mapq,
+  AVO_READ_SKIP_CALL = 2,       /* the reference's observeRead would throw for this read (null mapq,
                                    sequence/qual shorter than the CIGAR): skipped by call(), still
                                    walked by discover() */
+  AVO_READ_OPS_DROPPED = 4      /* set by the packers on a read with more than 65535 operators (the
+                                   limit of BAM's own CIGAR field and of avo_read_meta.n_ops): the
+                                   record is kept without operators, so the read takes no part in
+                                   discovery or calling; callers that need to know count this bit */
 };
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */

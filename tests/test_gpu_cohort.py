@@ -90,3 +90,58 @@ def test_cohort_discover_call_joint_matches_oracle(oracle, ctx, n_samples, cover
                 assert [1] * int(out["n_alt"][s, i]) + [0] * int(out["n_ref"][s, i]) == g["alleles"]
         n_joint += 1
     assert n_joint > 20
+
+
+def test_trio_discovers_once_over_the_union_of_the_reads(oracle, ctx):
+    """CLI/TrioGenotyper.scala:216-273 (BASELINE.json configs[2]): the three samples' reads are
+    merged, DiscoverVariants runs ONCE over the union (so `count > minObservations` sees the
+    candidates of all three samples), every sample is called against that table, and TrioCaller
+    post-processes the sites.  Every stage on the GPU through the C ABI, against the oracle."""
+    from avocado_b200 import batch as B
+    from avocado_b200.trio import trio_call_packed
+    contig_len, coverage = 80000, 10       # low enough that single samples miss sites the union finds
+    n_reads = contig_len * coverage // 150
+    batches = [B.synth_host(B.synth_params(seed=91, sample=s + 1, n_reads_total=n_reads, contig_len=contig_len,
+                                           first_pos=3000)) for s in range(3)]
+    union = B.merge_batches(batches)
+    assert union.n_reads == 3 * n_reads and np.all(np.diff(union.meta["start"].astype(np.int64)) >= 0)
+    rs_union = oracle_reads_from_batch(oracle, union)
+    want_v = oracle.discover(rs_union, 25, 5)
+    table = ctx.discover_packed(union, phred=25, min_obs=5)
+    got = [(v.start, v.end, v.referenceAllele, v.alternateAllele) for v in table.to_variants(["ctg"])]
+    assert sorted(zip(got, table.count.tolist())) == sorted(((s, e, r, a), n) for _, s, e, r, a, n in want_v)
+    # the union finds sites no single sample would: per-sample discovery is a different candidate set
+    per_sample = set()
+    for b in batches:
+        t = ctx.discover_packed(b, phred=25, min_obs=5)
+        per_sample |= {(v.start, v.referenceAllele, v.alternateAllele) for v in t.to_variants(["ctg"])}
+    assert {(s, r, a) for (s, e, r, a) in got} != per_sample
+    # the device merge gives the same union batch
+    import torch
+    union_d = B.merge_batches([b.to_device("cuda:%d" % ctx.device) for b in batches])
+    table_d = ctx.discover_packed(union_d, phred=25, min_obs=5)
+    assert np.array_equal(table_d.start, table.start) and np.array_equal(table_d.count, table.count)
+    keys = [("ctg", s, r, a) for (s, e, r, a) in got]
+    variants = [("ctg", s, e, r, a) for (s, e, r, a) in got]
+    N = table.n
+    cnt = {k: np.zeros((3, N), np.int32) for k in ("n_alt", "n_ref", "n_other")}
+    present = np.zeros((3, N), np.uint8)
+    for s, b in enumerate(batches):
+        cols = ctx.call_packed(b, table)
+        want = oracle.call(oracle_reads_from_batch(oracle, b), variants, 2, [], False, 93, 93, 1)
+        compare_call(keys, cols, want)                     # bit-identical per-sample rows
+        present[s] = cols["emitted"]
+        for k in cnt:
+            cnt[k][s] = cols[k]
+    out = trio_call_packed(ctx, N, cnt["n_alt"].ravel(), cnt["n_ref"].ravel(), cnt["n_other"].ravel(), present.ravel())
+    kept = 0
+    for i in range(N):
+        gts = [([1] * int(cnt["n_alt"][s, i]) + [0] * int(cnt["n_ref"][s, i]) + [2] * int(cnt["n_other"][s, i]))
+               if present[s, i] else None for s in range(3)]
+        w = oracle.trio_process(*gts)
+        assert bool(out["kept"][i]) == w["kept"]
+        if w["kept"]:
+            assert int(out["child_action"][i]) == w["childAction"]
+            assert [bool(out["filled"][i] >> s & 1) for s in range(3)] == w["filled"]
+            kept += 1
+    assert kept > 20

@@ -305,6 +305,49 @@ def test_one_very_long_read_span(oracle, ctx):
         assert g.genotypeLikelihoods == list(want["genotypeLikelihoods"][j][:3])
 
 
+def test_deletion_longer_than_65535_bases_keeps_its_allele(oracle, ctx):
+    """Operators are 28-bit; a 70 kb deletion seen by enough reads is ONE candidate whose reference
+    allele is 70 001 bases long (the indel list used to keep both lengths in 16 bits and
+    such a site came out as ref_len 4465 with the wrong alleles)."""
+    from avocado_b200.genotyping import BiallelicGenotyper, DiscoverVariants
+    from avocado_b200.records import AlignmentRecord
+    rng = np.random.default_rng(5)
+    D = 70000
+    ref = "".join("ACGT"[i] for i in rng.integers(0, 4, D + 400))
+    recs = []
+    for i in range(4):                       # > minObservations = 2
+        s = 100 + 3 * i
+        a = 140 - s
+        seq = ref[s:s + a] + ref[s + a + D:s + a + D + 40]
+        recs.append(AlignmentRecord(readMapped=True, contigName="1", start=s, end=s + a + D + 40, sequence=seq,
+                                    qual="I" * (a + 40), cigar="%dM%dD40M" % (a, D),
+                                    mismatchingPositions="%d^%s40" % (a, ref[s + a:s + a + D]), mapq=50, readName="d%d" % i))
+    for i in range(4):                       # ten bases on, one base shorter: another candidate
+        s = 90 + i
+        a = 150 - s
+        seq = ref[s:s + a] + ref[s + a + D - 1:s + a + D - 1 + 30]
+        recs.append(AlignmentRecord(readMapped=True, contigName="1", start=s, end=s + a + D - 1 + 30, sequence=seq,
+                                    qual="I" * (a + 30), cigar="%dM%dD30M" % (a, D - 1),
+                                    mismatchingPositions="%d^%s30" % (a, ref[s + a:s + a + D - 1]), mapq=50,
+                                    readName="e%d" % i))
+    recs.sort(key=lambda r: r.start)
+    rs = oracle.reads_from_dicts([r.as_dict() for r in recs])
+    want_v = oracle.discover(rs, 20, 2)
+    assert sorted(len(r) for _, _, _, r, _, _ in want_v) == [D, D + 1]
+    got_v = DiscoverVariants(recs, 20, 2, ctx=ctx)
+    assert sorted(v.as_tuple() for v in got_v) == sorted((c, s, e, r, a) for c, s, e, r, a, _ in want_v)
+    want = oracle.call(rs, [(c, s, e, r, a) for c, s, e, r, a, _ in want_v], 2, [], False, 93, 93, 1)
+    gts = BiallelicGenotyper.discoverAndCall(recs, optPhredThreshold=20, optMinObservations=2, samples=["s"], ctx=ctx)
+    okey = {(int(s_), r, a): j for j, (s_, r, a) in enumerate(zip(want["start"], want["referenceAllele"],
+                                                                   want["alternateAllele"]))}
+    assert {(g.start, g.variant.referenceAllele, g.variant.alternateAllele) for g in gts} == set(okey)
+    for g in gts:
+        j = okey[(g.start, g.variant.referenceAllele, g.variant.alternateAllele)]
+        assert (g.readDepth, g.alternateReadDepth, g.genotypeQuality) == \
+            (want["totalCoverage"][j], want["alleleCoverage"][j], want["genotypeQuality"][j])
+        assert g.alleles == ["ALT"] * int(want["nAlt"][j]) + ["REF"] * int(want["nRef"][j]) + ["OTHER_ALT"] * int(want["nOther"][j])
+
+
 def test_bucket_capacity_guess_is_checked():
     """The call stage runs with the previous call's bucket count as capacity; a larger batch than the
     one before overflows that guess and the stage is rerun: rows equal a fresh context's."""

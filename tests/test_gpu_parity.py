@@ -156,6 +156,32 @@ def test_synthetic_batch_matches_oracle(oracle, ctx, seed, n_reads, contig_len, 
         assert np.array_equal(np.asarray(cols[k]), np.asarray(cols2[k]), equal_nan=True), k
 
 
+def test_baseline_configs0_at_its_own_size(oracle, ctx):
+    """BASELINE.json configs[0] in full -- single-sample BiallelicGenotyper over a synthetic 1 Mb
+    region at 30x, 150 bp reads = 2.0e5 reads -- against the single-thread oracle: the discovered
+    table incl. counts, and every result column bit-identical."""
+    from avocado_b200 import batch as B
+    n_reads, contig_len = 200_000, 1_000_000
+    p = B.synth_params(seed=0xA70CAD0, n_reads_total=n_reads, contig_len=contig_len)
+    dev = B.synth_device(p)
+    host = dev.to_host()
+    rs = oracle_reads_from_batch(oracle, host)
+    want_v = oracle.discover(rs, 25, 5)
+    assert len(want_v) > 800                       # about 1.1 sites / kb
+    sites, cols = ctx.discover_and_call_packed(dev, ploidy=2, phred=25, min_obs=5, capacity=1 << 14)
+    got = [(v.start, v.end, v.referenceAllele, v.alternateAllele) for v in sites.to_variants(["ctg"])]
+    assert sorted(zip(got, sites.count.tolist())) == sorted(((s, e, r, a), n) for _, s, e, r, a, n in want_v)
+    want = oracle.call(rs, [(c, s, e, r, a) for c, s, e, r, a, _ in want_v], 2, [], False, 93, 93, 1)
+    st = compare_call([("ctg", s, r, a) for (s, e, r, a) in got], cols, want, exact_fp=True)
+    assert st["sites"] > 800 and st["fp_bit_identical"]
+    # the same batch from pinned-style host columns (compact wire form when it fits) gives the same rows
+    host.with_wire6() or host.with_wire()
+    sites_h, cols_h = ctx.discover_and_call_packed(host, ploidy=2, phred=25, min_obs=5, capacity=1 << 14)
+    assert np.array_equal(sites_h.start, sites.start) and np.array_equal(sites_h.count, sites.count)
+    for k in cols:
+        assert np.array_equal(np.asarray(cols[k]), np.asarray(cols_h[k]), equal_nan=True), k
+
+
 def test_empty_sites_and_unsorted_reads_are_errors(ctx):
     from avocado_b200 import _lib as L, batch as B
     from avocado_b200.genotyping import BiallelicGenotyper

@@ -25,7 +25,7 @@ enum Slot {
   SL_META, SL_COORDS, SL_PAYLOAD, SL_OPS, SL_REFB, SL_WIRE_META, SL_WIRE_OPS, SL_WIRE_OPC, SL_WIRE_OFFS, SL_WIRE_SIZES, SL_WIRE_EXC,
   SL_S_CONTIG, SL_S_START, SL_S_REFLEN, SL_S_ALTLEN, SL_S_AOFF, SL_S_ALLELES, SL_S_END, SL_S_PME,
   SL_S_COUNT,
-  SL_CNV, SL_STATS, SL_SMALL, SL_RIDX, SL_SIDX, SL_TEMP, SL_LUT,
+  SL_CNV, SL_STATS, SL_SMALL, SL_RIDX, SL_SIDX, SL_TEMP, SL_LUT, SL_ARENA, SL_U_NEXT, SL_PACK,
   SL_RES,                      // one block holding every result column
   SL_U_START, SL_U_REFLEN, SL_U_ALTLEN, SL_U_COUNT, SL_U_SRC,
   SL_L_POS, SL_L_REFLEN, SL_L_ALTLEN, SL_L_NIBS, SL_L_SRC, SL_L_BLK, SL_L_HASH,
@@ -61,6 +61,8 @@ struct avo_ctx {
   avo_timing timing{};
   cudaEvent_t ev[8] = {};
   int64_t indel_guess = 0;         // indel candidates seen by the previous discovery (sizes the table)
+  int64_t site_guess = 0;          // survivors / allele nibbles of the previous discovery (+ margin): the
+  int64_t nib_guess = 0;           // capacities the next one runs with (checked when its counts arrive)
   int disc_blocks_per_sm = 0;      // resident CTAs of k_discover_tiles per SM (occupancy query, once)
   BatchStats* h_stats = nullptr;   // pinned
   int32_t* h_small = nullptr;      // pinned scratch (16 ints)
@@ -361,7 +363,7 @@ int ensure_lut(avo_ctx* ctx, int minp, int maxp, int maxq, int maxmq, const doub
 
 // ---- device-resident site table ------------------------------------------------------------------
 struct DevSites {
-  int32_t n = 0;
+  int32_t n = 0;                // rows (tables assembled on the device: known after the chain's sync)
   uint32_t n_nibbles = 0;
   const int32_t* contig = nullptr;
   const int32_t* start = nullptr;
@@ -370,6 +372,20 @@ struct DevSites {
   const uint32_t* allele_off = nullptr;
   const uint8_t* alleles4 = nullptr;
   const int32_t* count = nullptr;
+  // tables assembled on the device in this launch chain: capacities, the header, derived columns
+  const DSiteHdr* hdr = nullptr;
+  int32_t cap = 0;
+  uint32_t nib_cap = 0;
+  const int32_t* end = nullptr;
+  const int32_t* pme = nullptr;
+  const int32_t* sidx = nullptr;
+  bool caller_arrays = false;   // the columns ARE the caller's device arrays (nothing to export)
+};
+
+// words of the SL_SMALL block (int32): what the kernels count for the host
+enum SmallWord {
+  SW_UNSORTED = 0, SW_CRANGE = 1 /* 2 */, SW_SRANGE = 4 /* 2 */, SW_TILE = 8, SW_FLAGS = 9, SW_NOUT = 10, SW_NINDEL = 11,
+  SW_JOIN = 14, SW_HDR = 16 /* DSiteHdr: 8 words */, SW_COUNT_ = 32
 };
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -562,10 +578,14 @@ int gather_payload(avo_ctx* ctx, const DReads& R, const DSites& S, const void* d
   return AVO_OK;
 }
 
+// `fresh`: the table was assembled by discover_enqueue on the same batch earlier in this launch chain:
+// sorted and single-contig by construction, sizes in its device header, derived columns and site index
+// already there -- nothing here waits for the device; *slots_used (pinned) receives the bucket slots the
+// stage needed, to be compared with *slots_cap after the chain's sync.
 int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const DevSites& T,
                   const avo_cnv* cnv, const avo_params* p, bool fresh, avo_site_results* out,
-                  avo_ref_model_out* ref_out = nullptr) {
-  if (T.n == 0)
+                  avo_ref_model_out* ref_out = nullptr, DResults* res_out = nullptr, size_t* slots_cap = nullptr) {
+  if (!fresh && T.n == 0)
     return fail(ctx, AVO_E_EMPTY_SITES,
                 "empty variant set: the reference throws here (TreeRegionJoin.scala:77)");
   // copy-number map: ploidy range over ALL CNVs (CopyNumberMap.min/maxPloidy), list of this contig
@@ -587,7 +607,9 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
   const int ns = maxp + 1;
   if (out->n_states != ns)
     return fail(ctx, AVO_E_INVALID, "results->n_states must be max ploidy + 1 = %d", ns);
-  if (out->n_sites != T.n) return fail(ctx, AVO_E_INVALID, "results->n_sites != number of sites");
+  if (!fresh && out->n_sites != T.n) return fail(ctx, AVO_E_INVALID, "results->n_sites != number of sites");
+  // rows the stage may touch: the table's (a fresh table: its capacity, bounded by the caller's rows)
+  const int32_t rows = fresh ? (int32_t)std::min<int64_t>(T.cap, out->mem == AVO_MEM_DEVICE ? out->n_sites : T.cap) : T.n;
 
   DCnv C{};
   C.n = (int32_t)cs.size();
@@ -610,62 +632,74 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
   P.ten_div_log10 = 10.0 / std::log(10.0);
   P.log10 = std::log(10.0);
 
-  // derived site columns + sortedness + contig range
+  void *d_small, *d_temp;
+  CKS(get_buf(ctx, SL_SMALL, SW_COUNT_ * 4, &d_small));
+  int32_t* small = (int32_t*)d_small;
   DSites S{};
-  S.n = T.n;
+  S.n = rows;
   S.contig = T.contig; S.start = T.start; S.ref_len = T.ref_len; S.alt_len = T.alt_len;
   S.allele_off = T.allele_off; S.alleles4 = T.alleles4;
-  void *d_end, *d_pme, *d_small, *d_temp;
-  CKS(get_buf(ctx, SL_S_END, (size_t)T.n * 4, &d_end));
-  CKS(get_buf(ctx, SL_S_PME, (size_t)T.n * 4, &d_pme));
-  CKS(get_buf(ctx, SL_SMALL, 64, &d_small));
-  const size_t tb = site_setup_temp_bytes(T.n);
-  CKS(get_buf(ctx, SL_TEMP, tb, &d_temp));
-  int32_t* small = (int32_t*)d_small;   // [0] unsorted, [1..2] contig range, [4..5] s_range
-  CK(launch_site_setup(T.n, T.contig, T.start, T.ref_len, (int32_t*)d_end, (int32_t*)d_pme, small,
-                       d_temp, tb, ctx->stream));
-  ctx->timing.n_launches += 2;
+  const int32_t nb = index_bins(hs);
+  void *d_ridx, *d_sidx;
+  CKS(get_buf(ctx, SL_RIDX, (size_t)(nb + 1) * 4, &d_ridx));
+  DIndex X{};
   if (fresh) {
-    S.c_lo = 0; S.c_hi = T.n;
+    S.hdr = T.hdr; S.cap = rows; S.c_lo = 0; S.c_hi = rows; S.midpoint = 1;
+    S.end = T.end; S.pme = T.pme;
+    X = DIndex{hs.min_start, nb, (const int32_t*)d_ridx, T.sidx, &T.hdr->s_begin};
   } else {
-    CK(launch_contig_range(T.n, T.contig, R.contig, small + 1, ctx->stream));
+    // derived site columns + sortedness + contig range
+    void *d_end, *d_pme;
+    CKS(get_buf(ctx, SL_S_END, (size_t)T.n * 4, &d_end));
+    CKS(get_buf(ctx, SL_S_PME, (size_t)T.n * 4, &d_pme));
+    const size_t tb = site_setup_temp_bytes(T.n);
+    CKS(get_buf(ctx, SL_TEMP, tb, &d_temp));
+    CK(launch_site_setup(T.n, T.contig, T.start, T.ref_len, (int32_t*)d_end, (int32_t*)d_pme, small + SW_UNSORTED,
+                         d_temp, tb, ctx->stream));
+    ctx->timing.n_launches += 2;
+    CK(launch_contig_range(T.n, T.contig, R.contig, small + SW_CRANGE, ctx->stream));
     ctx->timing.n_launches += 1;
     CK(cudaMemcpyAsync(ctx->h_small, small, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->h_small[0]) return fail(ctx, AVO_E_UNSORTED, "sites are not sorted by (contig, start, end)");
     S.c_lo = ctx->h_small[1]; S.c_hi = ctx->h_small[2];
+    S.end = (const int32_t*)d_end; S.pme = (const int32_t*)d_pme;
+    int mp = 1;                                                  // TreeRegionJoin.scala:66-72
+    while (!(2 * (int64_t)mp >= (int64_t)S.n)) mp *= 2;
+    S.midpoint = mp;
+    CKS(get_buf(ctx, SL_SIDX, (size_t)(nb + 1) * 4, &d_sidx));
+    CK(launch_build_index(R, S, hs, (int32_t*)d_ridx, (int32_t*)d_sidx, small + SW_SRANGE, ctx->stream));
+    ctx->timing.n_launches += 1;
+    X = DIndex{hs.min_start, nb, (const int32_t*)d_ridx, (const int32_t*)d_sidx, small + SW_SRANGE};
   }
-  S.end = (const int32_t*)d_end; S.pme = (const int32_t*)d_pme;
-  int mp = 1;                                                  // TreeRegionJoin.scala:66-72
-  while (!(2 * (int64_t)mp >= (int64_t)S.n)) mp *= 2;
-  S.midpoint = mp;
 
-  // coarse index
-  const int32_t nb = index_bins(hs);
-  void *d_ridx, *d_sidx;
-  CKS(get_buf(ctx, SL_RIDX, (size_t)(nb + 1) * 4, &d_ridx));
-  CKS(get_buf(ctx, SL_SIDX, (size_t)(nb + 1) * 4, &d_sidx));
-  if (fresh)
-    CK(launch_build_site_index(S, hs, (int32_t*)d_sidx, small + 4, ctx->stream));
-  else
-    CK(launch_build_index(R, S, hs, (int32_t*)d_ridx, (int32_t*)d_sidx, small + 4, ctx->stream));
-  ctx->timing.n_launches += 1;
-  DIndex X{hs.min_start, nb, (const int32_t*)d_ridx, (const int32_t*)d_sidx, small + 4};
-
-  // results block (zeroed: untouched sites are "not emitted")
-  const ResLayout L = res_layout(T.n, ns);
-  void* d_res;
-  CKS(get_buf(ctx, SL_RES, L.total, &d_res));
-  CK(cudaMemsetAsync(d_res, 0, L.total, ctx->stream));
+  // results: straight into the caller's device arrays (fresh tables), else one block holding every column
   DResults D;
-  res_pointers(d_res, L, ns, &D);
+  void* d_res = nullptr;
+  const ResLayout L = res_layout(rows, ns);
+  if (fresh && out->mem == AVO_MEM_DEVICE) {
+    D.ns = ns;
+    D.emitted = out->emitted; D.allele_fwd = out->allele_fwd; D.other_fwd = out->other_fwd;
+    D.allele_cov = out->allele_cov; D.other_cov = out->other_cov; D.total_cov = out->total_cov;
+    D.square_mapq = out->square_mapq; D.ref_ll = out->ref_ll; D.allele_ll = out->allele_ll;
+    D.other_ll = out->other_ll; D.nonref_ll = out->nonref_ll; D.first_is_ref = out->first_is_ref;
+    D.copy_number = out->copy_number; D.n_alt = out->n_alt; D.n_ref = out->n_ref; D.n_other = out->n_other;
+    D.qual = out->qual; D.gq = out->gq; D.sb = out->sb; D.fisher = out->fisher; D.rms_mapq = out->rms_mapq;
+    D.gl = out->gl; D.nonref_gl = out->nonref_gl;
+  } else {
+    CKS(get_buf(ctx, SL_RES, L.total, &d_res));
+    // a multi-contig table has rows this batch never touches; a fresh table's rows are all written
+    if (!fresh) CK(cudaMemsetAsync(d_res, 0, L.total, ctx->stream));
+    res_pointers(d_res, L, ns, &D);
+  }
+  if (res_out) *res_out = D;
 
   // per-site buckets: one 32-bit slot per read that can overlap the site
   void *d_rbase, *d_blen, *d_boff, *d_buckets;
-  CKS(get_buf(ctx, SL_C_RBASE, (size_t)(T.n + 1) * 4, &d_rbase));
-  CKS(get_buf(ctx, SL_C_BLEN, (size_t)(T.n + 1) * 4, &d_blen));
-  CKS(get_buf(ctx, SL_C_BOFF, (size_t)(T.n + 1) * 8, &d_boff));
-  const size_t tb2 = call_scan_temp_bytes(T.n);
+  CKS(get_buf(ctx, SL_C_RBASE, (size_t)(rows + 1) * 4, &d_rbase));
+  CKS(get_buf(ctx, SL_C_BLEN, (size_t)(rows + 1) * 4, &d_blen));
+  CKS(get_buf(ctx, SL_C_BOFF, (size_t)(rows + 1) * 8, &d_boff));
+  const size_t tb2 = call_scan_temp_bytes(rows);
   CKS(get_buf(ctx, SL_TEMP, tb2, &d_temp));
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   int nl = 0;
@@ -678,13 +712,14 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
   // The number of bucket slots is known on the device.  Instead of waiting for it, the stage runs
   // with the previous call's count (+ 1/8) as capacity, the kernels never write past it, and the
   // count is checked with the results; a stage that ran out of slots is rerun with the exact count.
-  uint64_t* h_slots = reinterpret_cast<uint64_t*>(ctx->h_small + 12);
+  uint64_t* h_slots = reinterpret_cast<uint64_t*>(ctx->h_small + 48);
   for (int attempt = 0; attempt < 2; ++attempt) {
-    const bool speculative = attempt == 0 && work && ctx->slots_guess > 0 && !ctx->gather_src;
+    const bool speculative = work && !ctx->gather_src && (fresh || (attempt == 0 && ctx->slots_guess > 0));
     size_t n_slots = 0;
     if (work) {
       CK(cudaMemcpyAsync(h_slots, (uint64_t*)d_boff + S.c_hi, 8, cudaMemcpyDeviceToHost, ctx->stream));
       if (speculative) {
+        if (ctx->slots_guess == 0) ctx->slots_guess = (size_t)R.n / 2 + (1u << 20);   // first call of the context
         n_slots = ctx->slots_guess;
       } else {
         CK(cudaStreamSynchronize(ctx->stream));
@@ -693,14 +728,18 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
       }
     }
     CKS(get_buf(ctx, SL_C_BUCKETS, n_slots * 4, &d_buckets));
-    CK(launch_call_join(R, S, X, hs.max_span, (uint32_t*)d_buckets, n_slots, d_jlist, small + 8, ctx->num_sms, ctx->stream, &nl));
+    CK(launch_call_join(R, S, X, hs.max_span, (uint32_t*)d_buckets, n_slots, d_jlist, small + SW_JOIN, ctx->num_sms, ctx->stream, &nl));
     const uint8_t* d_compact = nullptr;
     const uint32_t *d_pbase = nullptr, *d_blk0 = nullptr;
-    if (ctx->gather_src && work) CKS(gather_payload(ctx, R, S, d_jlist, small + 8, &d_compact, &d_pbase, &d_blk0, &nl));
+    if (ctx->gather_src && work) CKS(gather_payload(ctx, R, S, d_jlist, small + SW_JOIN, &d_compact, &d_pbase, &d_blk0, &nl));
     CK(launch_call_observe(R, S, C, P, D, (const int32_t*)d_rbase, (const uint32_t*)d_blen, (const uint64_t*)d_boff,
-                           (uint32_t*)d_buckets, n_slots, d_jlist, small + 8, d_compact, d_pbase, d_blk0, ctx->num_sms,
+                           (uint32_t*)d_buckets, n_slots, d_jlist, small + SW_JOIN, d_compact, d_pbase, d_blk0, ctx->num_sms,
                            ctx->stream, &nl));
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    if (fresh) {                            // the caller checks *h_slots against *slots_cap after its sync
+      if (slots_cap) *slots_cap = work ? n_slots : SIZE_MAX;
+      break;
+    }
     const size_t mark = ctx->pending.size(), used = ctx->h_stage_used;
     CKS(export_results(ctx, D, T.n, ns, out));
     if (!speculative) break;
@@ -790,117 +829,149 @@ int allsites_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const
   return AVO_OK;
 }
 
-// DiscoverVariants on a device batch; leaves the sorted site table in ctx buffers.  One host
-// round trip: the tile kernel and the indel grouping run back to back on device-side counts, then
-// the counters come back together.  verify: hs holds the caller's bounds, checked by the kernel.
-int discover_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, bool verify,
-                      const avo_params* p, DevSites* T) {
-  void *d_small, *d_ridx;
-  CKS(get_buf(ctx, SL_SMALL, 64, &d_small));
-  // [8] tile counter, [9] flags, [10] out.n, [11] indel n, [12] indel survivors' nibbles, [13] indel survivors
+// ---- DiscoverVariants on a device batch, as one launch chain with no host round trip ---------------
+// index -> tile kernel -> indel grouping -> k_assemble_sites.  Every size the kernels need lives in
+// device memory; the host supplies CAPACITIES (the previous call's counts plus a margin, or the
+// caller's arrays) and reads the counts back when the whole chain -- for avo_discover_and_call that
+// includes the call stage -- has been queued.  discover_check then says whether a capacity was too small.
+struct DiscCaps { int64_t ucap = 0, lcap = 0, tguess = 0, site_cap = 0, nib_cap = 0; };
+
+void initial_caps(avo_ctx* ctx, const DReads& R, DiscCaps* c) {
+  c->ucap = ctx->site_guess > 0 ? ctx->site_guess : std::max<int64_t>(1 << 16, R.n / 8);
+  c->lcap = std::max<int64_t>(1 << 16, std::max<int64_t>(R.n / 8, ctx->indel_guess + ctx->indel_guess / 8 + 1024));
+  c->tguess = std::max<int64_t>(1 << 15, ctx->indel_guess + ctx->indel_guess / 4);
+  c->site_cap = c->ucap;
+  c->nib_cap = ctx->nib_guess > 0 ? ctx->nib_guess : 4 * c->ucap;
+}
+
+// dst: where the table goes.  sites_out in device memory with all columns -> the caller's arrays, else
+// context buffers of the guessed capacities.
+int discover_enqueue(avo_ctx* ctx, const DReads& R, const BatchStats& hs, bool verify, const avo_params* p,
+                     const DiscCaps& c, const avo_sites_out* o, DevSites* T) {
+  void *d_small, *d_ridx, *d_sidx, *q;
+  CKS(get_buf(ctx, SL_SMALL, SW_COUNT_ * 4, &d_small));
   int32_t* small = (int32_t*)d_small;
   const int32_t nb = index_bins(hs);
   CKS(get_buf(ctx, SL_RIDX, (size_t)(nb + 1) * 4, &d_ridx));
+  CKS(get_buf(ctx, SL_SIDX, (size_t)(nb + 1) * 4, &d_sidx));
   DSites none{};
-  CK(launch_build_index(R, none, hs, (int32_t*)d_ridx, nullptr, nullptr, ctx->stream));
-  ctx->timing.n_launches += 1;
   DIndex X{hs.min_start, nb, (const int32_t*)d_ridx, nullptr, nullptr};
 
-  int64_t ucap = std::max<int64_t>(1 << 16, R.n / 8);
-  int64_t lcap = std::max<int64_t>(1 << 16, R.n / 8);
-  int64_t tguess = std::max<int64_t>(1 << 15, ctx->indel_guess + ctx->indel_guess / 4);
   DDiscoverOut U{};
   DIndelList Lst{};
-  int32_t n_out = 0, n_indel = 0, nib_indel = 0, n_surv = 0;
-  for (int attempt = 0;; ++attempt) {
-    if (attempt > 4) return fail(ctx, AVO_E_NOMEM, "discovery buffers kept overflowing");
-    void* q;
-    U.capacity = (int32_t)std::min<int64_t>(ucap, INT32_MAX);
-    CKS(get_buf(ctx, SL_U_START, (size_t)ucap * 4, &q)); U.start = (int32_t*)q;
-    CKS(get_buf(ctx, SL_U_REFLEN, (size_t)ucap * 4, &q)); U.ref_len = (int32_t*)q;
-    CKS(get_buf(ctx, SL_U_ALTLEN, (size_t)ucap * 4, &q)); U.alt_len = (int32_t*)q;
-    CKS(get_buf(ctx, SL_U_COUNT, (size_t)ucap * 4, &q)); U.count = (int32_t*)q;
-    CKS(get_buf(ctx, SL_U_SRC, (size_t)ucap * 8, &q)); U.src = (uint64_t*)q;
-    U.n = small + 10;
-    Lst.capacity = (int32_t)std::min<int64_t>(lcap, INT32_MAX);
-    CKS(get_buf(ctx, SL_L_POS, (size_t)lcap * 4, &q)); Lst.pos = (int32_t*)q;
-    CKS(get_buf(ctx, SL_L_REFLEN, (size_t)lcap * 4, &q)); Lst.ref_len = (int32_t*)q;
-    CKS(get_buf(ctx, SL_L_ALTLEN, (size_t)lcap * 4, &q)); Lst.alt_len = (int32_t*)q;
-    CKS(get_buf(ctx, SL_L_NIBS, (size_t)lcap * 4, &q)); Lst.nibs = (uint32_t*)q;
-    CKS(get_buf(ctx, SL_L_SRC, (size_t)lcap * 4, &q)); Lst.src = (uint32_t*)q;
-    CKS(get_buf(ctx, SL_L_BLK, (size_t)lcap * 4, &q)); Lst.blk = (uint32_t*)q;
-    CKS(get_buf(ctx, SL_L_HASH, (size_t)lcap * 4, &q)); Lst.hash = (uint32_t*)q;
-    Lst.n = small + 11;
-    uint32_t tsize = 1024;
-    while ((int64_t)tsize < 2 * tguess) tsize <<= 1;
-    void *d_table, *d_tcount;
-    CKS(get_buf(ctx, SL_TABLE, (size_t)tsize * 8, &d_table));
-    CKS(get_buf(ctx, SL_TCOUNT, (size_t)tsize * 4, &d_tcount));
-    CK(cudaMemsetAsync(small + 8, 0, 6 * sizeof(int32_t), ctx->stream));
+  const int64_t ucap = c.ucap, lcap = c.lcap;
+  U.capacity = (int32_t)std::min<int64_t>(ucap, INT32_MAX - 1);
+  CKS(get_buf(ctx, SL_U_START, (size_t)ucap * 4, &q)); U.start = (int32_t*)q;
+  CKS(get_buf(ctx, SL_U_REFLEN, (size_t)ucap * 4, &q)); U.ref_len = (int32_t*)q;
+  CKS(get_buf(ctx, SL_U_ALTLEN, (size_t)ucap * 4, &q)); U.alt_len = (int32_t*)q;
+  CKS(get_buf(ctx, SL_U_COUNT, (size_t)ucap * 4, &q)); U.count = (int32_t*)q;
+  CKS(get_buf(ctx, SL_U_SRC, (size_t)ucap * 8, &q)); U.src = (uint64_t*)q;
+  CKS(get_buf(ctx, SL_U_NEXT, (size_t)ucap * 4, &q)); U.next = (int32_t*)q;
+  U.n = small + SW_NOUT;
+  U.win0 = hs.min_start;
+  Lst.capacity = (int32_t)std::min<int64_t>(lcap, INT32_MAX - 1);
+  CKS(get_buf(ctx, SL_L_POS, (size_t)lcap * 4, &q)); Lst.pos = (int32_t*)q;
+  CKS(get_buf(ctx, SL_L_REFLEN, (size_t)lcap * 4, &q)); Lst.ref_len = (int32_t*)q;
+  CKS(get_buf(ctx, SL_L_ALTLEN, (size_t)lcap * 4, &q)); Lst.alt_len = (int32_t*)q;
+  CKS(get_buf(ctx, SL_L_NIBS, (size_t)lcap * 4, &q)); Lst.nibs = (uint32_t*)q;
+  CKS(get_buf(ctx, SL_L_SRC, (size_t)lcap * 4, &q)); Lst.src = (uint32_t*)q;
+  CKS(get_buf(ctx, SL_L_BLK, (size_t)lcap * 4, &q)); Lst.blk = (uint32_t*)q;
+  CKS(get_buf(ctx, SL_L_HASH, (size_t)lcap * 4, &q)); Lst.hash = (uint32_t*)q;
+  Lst.n = small + SW_NINDEL;
+  uint32_t tsize = 1024;
+  while ((int64_t)tsize < 2 * c.tguess) tsize <<= 1;
+  // one arena, one memset: the tile buckets, the indel hash table and its counts
+  const int32_t n_tiles = discover_tiles(hs);
+  const size_t a_tiles = align_up((size_t)n_tiles * sizeof(TileBucket), 256), a_table = (size_t)tsize * 8, a_tcount = (size_t)tsize * 4;
+  CKS(get_buf(ctx, SL_ARENA, a_tiles + a_table + a_tcount, &q));
+  char* arena = (char*)q;
+  U.tiles = (TileBucket*)arena;
+  unsigned long long* d_table = (unsigned long long*)(arena + a_tiles);
+  int32_t* d_tcount = (int32_t*)(arena + a_tiles + a_table);
+  CK(cudaMemsetAsync(arena, 0, a_tiles + a_table + a_tcount, ctx->stream));
+  CK(cudaMemsetAsync(small + SW_TILE, 0, (SW_COUNT_ - SW_TILE) * sizeof(int32_t), ctx->stream));
 
-    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    int nl = 0;
-    CK(launch_discover_tiles(R, p->min_phred_discover, p->min_obs_discover, X, hs, verify ? 1 : 0, U, Lst,
-                             small + 8, small + 9, ctx->num_sms, &ctx->disc_blocks_per_sm, ctx->stream, &nl));
-    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-    ctx->timing.n_launches += nl;
-    ctx->timing.n_tile_launches += nl;
-    nl = 0;
-    CK(launch_indel_group(R, Lst, (unsigned long long*)d_table, (int32_t*)d_tcount, tsize,
-                          p->min_obs_discover, U, small + 12, small + 13, small + 9, ctx->num_sms,
-                          ctx->stream, &nl));
-    ctx->timing.n_launches += nl;
-    CK(cudaMemcpyAsync(ctx->h_small, small + 9, 5 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    const int32_t flags = ctx->h_small[0];
-    n_out = ctx->h_small[1]; n_indel = ctx->h_small[2]; nib_indel = ctx->h_small[3]; n_surv = ctx->h_small[4];
-    if (flags & DISC_FLAG_UNSORTED) return fail(ctx, AVO_E_UNSORTED, "reads are not sorted by start");
-    if (flags & DISC_FLAG_BAD_STATS)
-      return fail(ctx, AVO_E_INVALID, "reads->stats does not bound the batch (max_end / max_span too small)");
-    ctx->indel_guess = n_indel;
-    bool again = false;
-    if (n_indel > lcap) { lcap = (int64_t)n_indel + n_indel / 8 + 1024; again = true; }
-    if (flags & DISC_FLAG_TABLE_FULL) { tguess = std::max<int64_t>(2 * tguess, n_indel); again = true; }
-    // without the table the survivors of the indel pass are unknown: at most n_indel
-    const int64_t need_u = (int64_t)n_out + ((flags & DISC_FLAG_TABLE_FULL) ? (int64_t)n_indel : 0);
-    if (need_u > ucap) { ucap = need_u + need_u / 8 + 1024; again = true; }
-    if (!again) break;
+  // where the table goes
+  DSiteTableOut D{};
+  const bool to_caller = o && o->mem == AVO_MEM_DEVICE && o->start && o->ref_len && o->alt_len && o->allele_off && o->alleles4 &&
+                         o->capacity > 0;
+  if (to_caller) {
+    D.cap = (int32_t)std::min<int64_t>(o->capacity, INT32_MAX - 1);
+    D.nib_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(o->allele_capacity, 0), UINT32_MAX);
+    D.start = o->start; D.ref_len = o->ref_len; D.alt_len = o->alt_len; D.allele_off = o->allele_off; D.alleles4 = o->alleles4;
+    D.count = o->count;
+  } else {
+    D.cap = (int32_t)std::min<int64_t>(c.site_cap, INT32_MAX - 1);
+    D.nib_cap = (uint32_t)std::min<int64_t>(c.nib_cap, UINT32_MAX);
+    CKS(get_buf(ctx, SL_S_START, (size_t)D.cap * 4, &q)); D.start = (int32_t*)q;
+    CKS(get_buf(ctx, SL_S_REFLEN, (size_t)D.cap * 4, &q)); D.ref_len = (int32_t*)q;
+    CKS(get_buf(ctx, SL_S_ALTLEN, (size_t)D.cap * 4, &q)); D.alt_len = (int32_t*)q;
+    CKS(get_buf(ctx, SL_S_AOFF, (size_t)(D.cap + 1) * 4, &q)); D.allele_off = (uint32_t*)q;
+    CKS(get_buf(ctx, SL_S_ALLELES, (size_t)D.nib_cap / 2 + 16, &q)); D.alleles4 = (uint8_t*)q;
   }
+  if (!D.count) { CKS(get_buf(ctx, SL_S_COUNT, (size_t)D.cap * 4, &q)); D.count = (int32_t*)q; }
+  CKS(get_buf(ctx, SL_S_END, (size_t)D.cap * 4, &q)); D.end = (int32_t*)q;
+  CKS(get_buf(ctx, SL_S_PME, (size_t)D.cap * 4, &q)); D.pme = (int32_t*)q;
+  D.sidx = (int32_t*)d_sidx;
+  D.hdr = (DSiteHdr*)(small + SW_HDR);
 
-  // sort + materialise
-  T->n = n_out;
-  T->n_nibbles = 0;
-  T->contig = nullptr;
-  if (n_out == 0) return AVO_OK;
-  const uint32_t total = 2u * (uint32_t)(n_out - n_surv) + (uint32_t)nib_indel;   // SNVs: 2 nibbles each
-  void *ka, *kb, *va, *vb, *foot, *aoff, *temp;
-  CKS(get_buf(ctx, SL_KEYS_A, (size_t)n_out * 8, &ka));
-  CKS(get_buf(ctx, SL_KEYS_B, (size_t)n_out * 8, &kb));
-  CKS(get_buf(ctx, SL_VALS_A, (size_t)n_out * 4, &va));
-  CKS(get_buf(ctx, SL_VALS_B, (size_t)n_out * 4, &vb));
-  CKS(get_buf(ctx, SL_FOOT, (size_t)n_out * 4, &foot));
-  CKS(get_buf(ctx, SL_AOFF, (size_t)n_out * 4, &aoff));
-  const size_t tb = assemble_temp_bytes(n_out);
-  CKS(get_buf(ctx, SL_TEMP, tb, &temp));
+  CK(launch_build_index(R, none, hs, (int32_t*)d_ridx, nullptr, nullptr, ctx->stream));
+  ctx->timing.n_launches += 1;
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   int nl = 0;
-  CK(launch_assemble_sites(R, Lst, U, n_out, hs.min_start, hs.max_end, (unsigned long long*)ka,
-                           (unsigned long long*)kb, (int32_t*)va, (int32_t*)vb, (uint32_t*)foot,
-                           (uint32_t*)aoff, temp, tb, ctx->stream, &nl));
-  void *o_start, *o_ref, *o_alt, *o_aoff, *o_all, *o_cnt;
-  CKS(get_buf(ctx, SL_S_START, (size_t)n_out * 4, &o_start));
-  CKS(get_buf(ctx, SL_S_REFLEN, (size_t)n_out * 4, &o_ref));
-  CKS(get_buf(ctx, SL_S_ALTLEN, (size_t)n_out * 4, &o_alt));
-  CKS(get_buf(ctx, SL_S_AOFF, (size_t)(n_out + 1) * 4, &o_aoff));
-  CKS(get_buf(ctx, SL_S_ALLELES, (size_t)total / 2 + 16, &o_all));
-  CKS(get_buf(ctx, SL_S_COUNT, (size_t)n_out * 4, &o_cnt));
-  CK(launch_fill_sites(R, Lst, U, n_out, (const int32_t*)vb, (const uint32_t*)aoff, (int32_t*)o_start,
-                       (int32_t*)o_ref, (int32_t*)o_alt, (uint32_t*)o_aoff, (uint8_t*)o_all,
-                       (int32_t*)o_cnt, total, ctx->stream, &nl));
+  CK(launch_discover_tiles(R, p->min_phred_discover, p->min_obs_discover, X, hs, verify ? 1 : 0, U, Lst,
+                           small + SW_TILE, small + SW_FLAGS, ctx->num_sms, &ctx->disc_blocks_per_sm, ctx->stream, &nl));
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timing.n_tile_launches += nl;
+  CK(launch_indel_group(R, Lst, d_table, d_tcount, tsize, p->min_obs_discover, U, small + SW_FLAGS, ctx->num_sms,
+                        ctx->stream, &nl));
+  CK(launch_assemble_sites(R, Lst, U, hs, nb, D, ctx->stream, &nl));
   ctx->timing.n_launches += nl;
-  T->n_nibbles = total;
-  T->start = (const int32_t*)o_start; T->ref_len = (const int32_t*)o_ref;
-  T->alt_len = (const int32_t*)o_alt; T->allele_off = (const uint32_t*)o_aoff;
-  T->alleles4 = (const uint8_t*)o_all; T->count = (const int32_t*)o_cnt;
+
+  T->n = 0; T->n_nibbles = 0; T->contig = nullptr;
+  T->start = D.start; T->ref_len = D.ref_len; T->alt_len = D.alt_len; T->allele_off = D.allele_off;
+  T->alleles4 = D.alleles4; T->count = D.count;
+  T->hdr = D.hdr; T->cap = D.cap; T->nib_cap = D.nib_cap; T->end = D.end; T->pme = D.pme; T->sidx = D.sidx;
+  T->caller_arrays = to_caller;
+  return AVO_OK;
+}
+
+// queues the copy of the counters (to be read after the next synchronisation)
+int discover_fetch_counts(avo_ctx* ctx) {
+  void* d_small;
+  CKS(get_buf(ctx, SL_SMALL, SW_COUNT_ * 4, &d_small));
+  CK(cudaMemcpyAsync(ctx->h_small, (int32_t*)d_small + SW_TILE, (SW_COUNT_ - SW_TILE) * sizeof(int32_t),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  return AVO_OK;
+}
+
+// After the sync.  AVO_OK: *again says whether a capacity of `c` was too small (c is then grown).
+int discover_check(avo_ctx* ctx, DiscCaps* c, DevSites* T, bool* again) {
+  const int32_t* w = ctx->h_small - SW_TILE;          // w[SW_x] = word SW_x of the device block
+  const int32_t flags = w[SW_FLAGS];
+  const int64_t n_out = w[SW_NOUT], n_indel = w[SW_NINDEL];
+  DSiteHdr h;
+  memcpy(&h, w + SW_HDR, sizeof h);
+  *again = false;
+  if (flags & DISC_FLAG_UNSORTED) return fail(ctx, AVO_E_UNSORTED, "reads are not sorted by start");
+  if (flags & DISC_FLAG_BAD_STATS)
+    return fail(ctx, AVO_E_INVALID, "reads->stats does not bound the batch (max_end / max_span too small)");
+  ctx->indel_guess = n_indel;
+  if (n_indel > c->lcap) { c->lcap = n_indel + n_indel / 8 + 1024; *again = true; }
+  if (flags & DISC_FLAG_TABLE_FULL) { c->tguess = std::max<int64_t>(2 * c->tguess, n_indel); *again = true; }
+  // without the table the survivors of the indel pass are unknown: at most n_indel
+  const int64_t need_u = n_out + ((flags & DISC_FLAG_TABLE_FULL) ? n_indel : 0);
+  if (need_u > c->ucap) { c->ucap = need_u + need_u / 8 + 1024; *again = true; }
+  if (!*again) {
+    ctx->site_guess = (int64_t)h.n + h.n / 8 + 1024;
+    ctx->nib_guess = (int64_t)h.n_nibbles + h.n_nibbles / 8 + 4096;
+    if (!T->caller_arrays) {           // the context's own arrays: grow and rerun; the caller's: reported
+      if (h.n > c->site_cap) { c->site_cap = ctx->site_guess; *again = true; }
+      if ((int64_t)h.n_nibbles > c->nib_cap) { c->nib_cap = ctx->nib_guess; *again = true; }
+    }
+    T->n = h.n;
+    T->n_nibbles = h.n_nibbles;
+  }
   return AVO_OK;
 }
 
@@ -912,7 +983,7 @@ int export_sites(avo_ctx* ctx, const DevSites& T, avo_sites_out* o) {
   if (!fits)
     return fail(ctx, AVO_E_CAPACITY, "sites_out too small: need %d entries, %u allele nibbles", T.n,
                 T.n_nibbles);
-  if (T.n == 0) return AVO_OK;
+  if (T.n == 0 || T.caller_arrays) return AVO_OK;
   if (!o->start || !o->ref_len || !o->alt_len || !o->allele_off || !o->alleles4)
     return fail(ctx, AVO_E_INVALID, "sites_out has NULL columns");
   const cudaMemcpyKind kind = (o->mem == AVO_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -998,7 +1069,7 @@ int avo_ctx_create(int device, avo_ctx** out) {
   for (auto& ev : ctx->ev)
     if (cudaEventCreate(&ev) != cudaSuccess) return bail(AVO_E_CUDA);
   if (cudaMallocHost(&ctx->h_stats, sizeof(BatchStats)) != cudaSuccess) return bail(AVO_E_CUDA);
-  if (cudaMallocHost(&ctx->h_small, 16 * sizeof(int32_t)) != cudaSuccess) return bail(AVO_E_CUDA);
+  if (cudaMallocHost(&ctx->h_small, 64 * sizeof(int32_t)) != cudaSuccess) return bail(AVO_E_CUDA);
   // ln table (host libm) and logFactorial table (device, reference summation order)
   std::vector<double> lnk(LNK_N);
   lnk[0] = 0.0;
@@ -1056,6 +1127,7 @@ int avo_discover(avo_ctx* ctx, const avo_read_batch* reads, const avo_params* pa
   CKS(begin_call(ctx));
   CKS(validate_reads(ctx, reads));
   if (!params) return fail(ctx, AVO_E_INVALID, "params is NULL");
+  if (!out) return fail(ctx, AVO_E_INVALID, "sites_out is NULL");
   DReads R;
   CKS(upload_reads(ctx, reads, params->host_payload != 1, &R));
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -1063,7 +1135,17 @@ int avo_discover(avo_ctx* ctx, const avo_read_batch* reads, const avo_params* pa
   const bool hinted = stats_from_hints(reads, &hs);
   if (!hinted) CKS(batch_stats(ctx, R, &hs));
   DevSites T;
-  CKS(discover_internal(ctx, R, hs, hinted, params, &T));
+  DiscCaps caps;
+  initial_caps(ctx, R, &caps);
+  for (int attempt = 0;; ++attempt) {
+    if (attempt > 5) return fail(ctx, AVO_E_NOMEM, "discovery buffers kept overflowing");
+    CKS(discover_enqueue(ctx, R, hs, hinted, params, caps, out, &T));
+    CKS(discover_fetch_counts(ctx));
+    CK(cudaStreamSynchronize(ctx->stream));
+    bool again = false;
+    CKS(discover_check(ctx, &caps, &T, &again));
+    if (!again) break;
+  }
   CK(cudaEventRecord(ctx->ev[6], ctx->stream));
   const int rc = export_sites(ctx, T, out);
   CKS(finish_call(ctx, true, false));
@@ -1127,19 +1209,52 @@ int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_c
   if (params->score_all_sites)
     return fail(ctx, AVO_E_INVALID, "score_all_sites: discover with avo_discover, then avo_call_all_sites");
   CKS(check_results(ctx, results));
+  if (!sites_out) return fail(ctx, AVO_E_INVALID, "sites_out is NULL");
+  if (results->mem != AVO_MEM_HOST && results->mem != AVO_MEM_DEVICE) return fail(ctx, AVO_E_INVALID, "bad results->mem");
   DReads R;
   CKS(upload_reads(ctx, reads, params->host_payload != 1 && !params->score_all_sites, &R, params));
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   BatchStats hs;
   const bool hinted = stats_from_hints(reads, &hs);
   if (!hinted) CKS(batch_stats(ctx, R, &hs));
+  // One launch chain: discovery, the table, the call stage.  Capacities are the previous call's counts
+  // plus a margin; all counts come back with one copy when everything is queued.
+  const int64_t res_cap = results->n_sites;
+  const bool gathered = ctx->gather_src != nullptr;    // host-gathered payload: the call stage talks to the host anyway
   DevSites T;
-  CKS(discover_internal(ctx, R, hs, hinted, params, &T));
-  CK(cudaEventRecord(ctx->ev[6], ctx->stream));
-  const int64_t cap = results->n_sites;
+  DResults D;
+  DiscCaps caps;
+  initial_caps(ctx, R, &caps);
+  uint64_t* h_slots = reinterpret_cast<uint64_t*>(ctx->h_small + 48);
+  for (int attempt = 0;; ++attempt) {
+    if (attempt > 6) return fail(ctx, AVO_E_NOMEM, "discovery / call buffers kept overflowing");
+    CKS(discover_enqueue(ctx, R, hs, hinted, params, caps, sites_out, &T));
+    CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+    size_t slots_cap = SIZE_MAX;
+    if (gathered) {      // the table's size first (this route synchronises inside the call stage as well)
+      CKS(discover_fetch_counts(ctx));
+      CK(cudaStreamSynchronize(ctx->stream));
+      bool again = false;
+      CKS(discover_check(ctx, &caps, &T, &again));
+      if (again) continue;
+      if (T.n == 0) break;
+    }
+    *h_slots = 0;
+    CKS(call_internal(ctx, R, hs, T, cnv, params, true, results, nullptr, &D, &slots_cap));
+    CKS(discover_fetch_counts(ctx));
+    CK(cudaStreamSynchronize(ctx->stream));
+    bool again = false;
+    CKS(discover_check(ctx, &caps, &T, &again));
+    if (slots_cap != SIZE_MAX) {
+      const size_t actual = (size_t)*h_slots;
+      ctx->slots_guess = actual + actual / 8 + 1024;
+      if (actual > slots_cap) again = true;
+    }
+    if (!again) break;
+  }
   results->n_sites = T.n;
   int rc = export_sites(ctx, T, sites_out);
-  if (rc == AVO_OK && cap < T.n)
+  if (rc == AVO_OK && res_cap < T.n)
     rc = fail(ctx, AVO_E_CAPACITY, "results too small: need %d rows", T.n);
   if (rc != AVO_OK) { finish_call(ctx, true, false); return rc; }
   if (T.n == 0) {
@@ -1147,7 +1262,39 @@ int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_c
     return fail(ctx, AVO_E_EMPTY_SITES,
                 "no variants discovered: the reference throws here (TreeRegionJoin.scala:77)");
   }
-  CKS(call_internal(ctx, R, hs, T, cnv, params, true, results));
+  if (results->mem == AVO_MEM_HOST) {
+    // the rows of every column, packed by one launch, cross PCIe as one copy
+    const int ns = D.ns;
+    const size_t n = (size_t)T.n;
+    struct { void* dst; const void* src; size_t bytes; } c[] = {
+        {results->emitted, D.emitted, n}, {results->allele_fwd, D.allele_fwd, n * 4},
+        {results->other_fwd, D.other_fwd, n * 4}, {results->allele_cov, D.allele_cov, n * 4},
+        {results->other_cov, D.other_cov, n * 4}, {results->total_cov, D.total_cov, n * 4},
+        {results->square_mapq, D.square_mapq, n * 8}, {results->ref_ll, D.ref_ll, n * ns * 8},
+        {results->allele_ll, D.allele_ll, n * ns * 8}, {results->other_ll, D.other_ll, n * ns * 8},
+        {results->nonref_ll, D.nonref_ll, n * ns * 8}, {results->first_is_ref, D.first_is_ref, n},
+        {results->copy_number, D.copy_number, n * 4}, {results->n_alt, D.n_alt, n * 4},
+        {results->n_ref, D.n_ref, n * 4}, {results->n_other, D.n_other, n * 4},
+        {results->qual, D.qual, n * 8}, {results->gq, D.gq, n * 4}, {results->sb, D.sb, n * 16},
+        {results->fisher, D.fisher, n * 4}, {results->rms_mapq, D.rms_mapq, n * 4},
+        {results->gl, D.gl, n * ns * 8}, {results->nonref_gl, D.nonref_gl, n * ns * 8}};
+    size_t total = 0;
+    for (auto& x : c) total += align_up(x.bytes, 16);
+    void* d_pack;
+    CKS(get_buf(ctx, SL_PACK, total, &d_pack));
+    ColumnCopies cc{};
+    Scatter sc[23];
+    size_t off = 0;
+    for (auto& x : c) {
+      cc.dst[cc.n] = (char*)d_pack + off; cc.src[cc.n] = x.src; cc.bytes[cc.n] = x.bytes;
+      sc[cc.n] = Scatter{x.dst, off, x.bytes};
+      ++cc.n;
+      off += align_up(x.bytes, 16);
+    }
+    CK(launch_copy_columns(cc, ctx->stream));
+    ctx->timing.n_launches += 1;
+    CKS(d2h_block(ctx, d_pack, total, sc, cc.n));
+  }
   CKS(finish_call(ctx, true, true));
   return AVO_OK;
 }

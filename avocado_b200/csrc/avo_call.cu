@@ -59,10 +59,13 @@ __device__ __forceinline__ int32_t first_read_at(const DReads& R, const DIndex& 
   return lo;
 }
 
-__global__ void k_site_buckets(DReads R, DSites S, DIndex X, int32_t max_span, int32_t* __restrict__ rbase,
-                               uint32_t* __restrict__ len) {
-  const int32_t j = S.c_lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= S.c_hi) return;
+__global__ void k_site_buckets(DReads R, DSites S_in, DIndex X, int32_t max_span, int32_t n_grid,
+                               int32_t* __restrict__ rbase, uint32_t* __restrict__ len) {
+  const DSites S = resolve_sites(S_in);
+  const int32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_grid) return;
+  const int32_t j = S.c_lo + idx;
+  if (j >= S.c_hi) { len[j] = 0; return; }     // past the table (capacity rows, the scan's sentinel)
   const int32_t a = first_read_at(R, X, (int64_t)__ldg(S.start + j) - max_span + 1);
   const int32_t b = max(a, first_read_at(R, X, (int64_t)__ldg(S.end + j)));
   rbase[j] = a;
@@ -150,9 +153,12 @@ constexpr int JOIN_FLUSH = 96;
 constexpr int JOIN_CAP = JOIN_FLUSH + 32;
 
 __global__ void __launch_bounds__(JOIN_THREADS)
-k_call_join(DReads R, DSites S, DIndex X, int32_t max_span, JoinedRead* __restrict__ list,
+k_call_join(DReads R, DSites S_in, DIndex X, int32_t max_span, JoinedRead* __restrict__ list,
             int32_t* __restrict__ n_list) {
   __shared__ JoinedRead stage[JOIN_WARPS][JOIN_CAP];
+  const DSites S = resolve_sites(S_in);
+  // nothing to join; or the table did not fit its arrays (its index points past them: the host reruns)
+  if (S.c_hi <= S.c_lo || (S.hdr && S.hdr->n > S.cap)) return;
   const int lane = threadIdx.x & 31;
   JoinedRead* st = stage[threadIdx.x >> 5];
   const unsigned lt = (1u << lane) - 1u;
@@ -230,11 +236,12 @@ k_call_join(DReads R, DSites S, DIndex X, int32_t max_span, JoinedRead* __restri
 // the host gathered (compact), addressed per (read, site) pair through pbase / blk0.
 template <bool GATHERED>
 __global__ void __launch_bounds__(OBS_THREADS, AVO_CALL_MINB)
-k_call_observe(DReads R, DSites S, DCnv C, DCallParams P, const JoinedRead* __restrict__ list,
+k_call_observe(DReads R, DSites S_in, DCnv C, DCallParams P, const JoinedRead* __restrict__ list,
                const int32_t* __restrict__ n_list, const int32_t* __restrict__ rbase,
                const uint64_t* __restrict__ boff, uint32_t* __restrict__ buckets, uint64_t n_slots,
                const uint8_t* __restrict__ compact, const uint32_t* __restrict__ pbase,
                const uint32_t* __restrict__ blk0) {
+  const DSites S = resolve_sites(S_in);
   const int32_t n = *n_list;
   if (GATHERED) R.payload = compact;
   for (int32_t i = blockIdx.x * OBS_THREADS + threadIdx.x; i < n; i += gridDim.x * OBS_THREADS) {
@@ -341,8 +348,9 @@ k_call_blocklist(DReads R, const JoinedRead* __restrict__ list, int32_t n, const
 // so only the selected category's array is touched.
 template <int NS>
 __global__ void __launch_bounds__(128)
-k_call_reduce(DSites S, DCallParams P, DResults O, const uint64_t* __restrict__ boff,
+k_call_reduce(DSites S_in, DCallParams P, DResults O, const uint64_t* __restrict__ boff,
               const uint32_t* __restrict__ blen, const uint32_t* __restrict__ buckets, uint64_t n_slots) {
+  const DSites S = resolve_sites(S_in);
   const int32_t j = S.c_lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= S.c_hi) return;
   const uint32_t* __restrict__ bk = buckets + (size_t)__ldg(boff + j);
@@ -395,7 +403,7 @@ k_call_reduce(DSites S, DCallParams P, DResults O, const uint64_t* __restrict__ 
   A.sq = sq;
   A.allele_fwd = c_afw; A.other_fwd = c_ofw; A.allele_cov = c_acov; A.other_cov = c_ocov; A.total_cov = c_tot;
   A.first_is_ref = first_is_ref; A.copy_number = first_cn; A.seen = seen;
-  finalize_site(P, O, j, A);
+  finalize_site<true>(P, O, j, A);        // a site nobody observed gets a row of zeros: no clearing pass
 }
 
 // ---- launchers --------------------------------------------------------------------------------------
@@ -415,13 +423,11 @@ size_t call_scan_temp_bytes(int32_t n) {
 cudaError_t launch_call_buckets(const DReads& R, const DSites& S, const DIndex& X, const BatchStats& hstats, int32_t* rbase,
                                 uint32_t* blen, uint64_t* boff, void* d_temp, size_t temp_bytes,
                                 cudaStream_t s, int* n_launches) {
-  const int32_t n = S.c_hi - S.c_lo;
+  const int32_t n = S.c_hi - S.c_lo;      // rows to cover (a header table: its capacity)
   if (n <= 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(blen + S.c_hi, 0, sizeof(uint32_t), s);
-  if (e != cudaSuccess) return e;
-  k_site_buckets<<<(n + 127) / 128, 128, 0, s>>>(R, S, X, hstats.max_span, rbase, blen);
+  k_site_buckets<<<(n + 1 + 127) / 128, 128, 0, s>>>(R, S, X, hstats.max_span, n + 1, rbase, blen);
   cub::TransformInputIterator<unsigned long long, LenTo64, const uint32_t*> it(blen + S.c_lo, LenTo64());
-  e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, it, (unsigned long long*)(boff + S.c_lo), n + 1, s);
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, it, (unsigned long long*)(boff + S.c_lo), n + 1, s);
   if (e != cudaSuccess) return e;
   if (n_launches) *n_launches += 2;
   return cudaGetLastError();

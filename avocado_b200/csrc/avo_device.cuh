@@ -62,6 +62,17 @@ __device__ __forceinline__ int32_t meta_start(const avo_read_meta* __restrict__ 
   return __ldg(&m[r].start);
 }
 
+// A table assembled earlier in the same launch chain carries its sizes in device memory (DSiteHdr);
+// kernels call this first.  Rows beyond the arrays' capacity do not exist for the kernels (the host
+// sees the true count in the header and reruns with larger arrays).
+__device__ __forceinline__ DSites resolve_sites(DSites S) {
+  if (S.hdr) {
+    const int32_t n = min(S.hdr->n, S.cap);
+    S.n = n; S.c_lo = 0; S.c_hi = n; S.midpoint = S.hdr->midpoint;
+  }
+  return S;
+}
+
 __device__ __forceinline__ int32_t site_contig(const DSites& S, int32_t k) {
   return S.contig ? __ldg(S.contig + k) : 0;
 }

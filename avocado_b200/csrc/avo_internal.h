@@ -24,10 +24,22 @@ struct DReads {
 };
 static_assert(sizeof(avo_read_meta) == 32, "avo_read_meta must be one 32-byte sector");
 
+// What the device knows about a site table that the host has not seen yet (a table assembled by
+// k_assemble_sites in the same launch chain): kernels read their sizes from here.
+struct DSiteHdr {
+  int32_t n;           // rows (may exceed the capacity the table was assembled into: the host reruns)
+  int32_t midpoint;    // Forest.midpoint over those rows
+  uint32_t n_nibbles;  // allele nibbles (same remark)
+  int32_t s_begin, s_end;   // DIndex.s_range of the table against its own batch: {0, n}
+  int32_t reserved[3];
+};
+
 struct DSites {
   int32_t n;          // total entries in the table (all contigs)
   int32_t c_lo, c_hi; // index range of the batch's contig
   int32_t midpoint;   // Forest.midpoint (TreeRegionJoin.scala:66-72) over the whole table
+  const DSiteHdr* hdr; // not null: n / c_hi / midpoint above are capacities, the real ones are here
+  int32_t cap;         // rows the arrays hold (hdr tables)
   const int32_t* contig; // may be null (all zero)
   const int32_t* start;
   const int32_t* end;    // start + ref_len (built by k_site_setup)
@@ -270,6 +282,13 @@ cudaError_t launch_allsites_tiles(const DReads& R, const DSites& S, const DCnv& 
                                   cudaStream_t s, int* n_launches);
 
 // discovery
+// per 2048-base tile of the genome: the survivors that start in it, as a linked list
+struct TileBucket {
+  int32_t head;         // last survivor linked in + 1 (0: none)
+  int32_t cnt;          // survivors
+  uint32_t nib;         // their allele nibbles (even-aligned footprints)
+  int32_t max_rel_end;  // max(end - win0) over them (0: none)
+};
 struct DDiscoverOut {
   // unsorted candidate survivors appended by the kernels
   int32_t capacity;
@@ -279,6 +298,9 @@ struct DDiscoverOut {
   int32_t* alt_len;
   int32_t* count;
   uint64_t* src;        // where the allele content lives: see avo_discover.cu
+  int32_t* next;        // next survivor of the same tile + 1 (0: end of list)
+  TileBucket* tiles;    // [n_tiles], zeroed before the tile kernel
+  int32_t win0;         // reference position of tile 0
 };
 
 struct DIndelList {
@@ -302,24 +324,27 @@ cudaError_t launch_discover_tiles(const DReads& R, int32_t thr, int32_t min_obs 
                                   int32_t* d_tile_counter, int32_t* d_flags, int num_sms,
                                   int* blocks_per_sm, cudaStream_t s, int* n_launches);
 
-// groups the *L.n (device counter) indel candidates; survivors are appended to `out`, their
-// allele-nibble footprints added to *d_nib, their number to *d_nsurv.  Sets DISC_FLAG_TABLE_FULL
-// (and does nothing) when the table is too small for *L.n.
+// groups the *L.n (device counter) indel candidates; survivors are appended to `out` and linked into
+// their tiles.  Sets DISC_FLAG_TABLE_FULL (and does nothing) when the table is too small for *L.n.
 cudaError_t launch_indel_group(const DReads& R, const DIndelList& L, unsigned long long* table,
                                int32_t* tcount, uint32_t tsize, int32_t min_obs,
-                               const DDiscoverOut& out, int32_t* d_nib, int32_t* d_nsurv,
-                               int32_t* d_flags, int num_sms, cudaStream_t s, int* n_launches);
-size_t assemble_temp_bytes(int32_t n);
+                               const DDiscoverOut& out, int32_t* d_flags, int num_sms, cudaStream_t s,
+                               int* n_launches);
+int32_t discover_tiles(const BatchStats& hstats);   // tiles k_discover_tiles cuts the batch into
+// Sorted site table from the per-tile survivor lists, in one launch: rows in (start, ref_len, alt_len,
+// alleles) order, derived columns (end, prefix-max end), the site index of the batch's bins and the
+// header.  Rows / nibbles beyond the capacities are counted in the header but not written.
+struct DSiteTableOut {
+  int32_t cap; uint32_t nib_cap;
+  int32_t *start, *ref_len, *alt_len, *count, *end, *pme;
+  uint32_t* allele_off;      // [cap + 1]
+  uint8_t* alleles4;
+  int32_t* sidx;             // [nb + 1]
+  DSiteHdr* hdr;
+};
 cudaError_t launch_assemble_sites(const DReads& R, const DIndelList& L, const DDiscoverOut& U,
-                                  int32_t n, int32_t min_start, int32_t max_end,
-                                  unsigned long long* keys_a, unsigned long long* keys_b,
-                                  int32_t* vals_a, int32_t* vals_b, uint32_t* foot, uint32_t* aoff,
-                                  void* d_temp, size_t temp_bytes, cudaStream_t s, int* n_launches);
-cudaError_t launch_fill_sites(const DReads& R, const DIndelList& L, const DDiscoverOut& U, int32_t n,
-                              const int32_t* vals, const uint32_t* aoff, int32_t* o_start,
-                              int32_t* o_ref_len, int32_t* o_alt_len, uint32_t* o_aoff,
-                              uint8_t* o_alleles, int32_t* o_count, uint32_t total_nibbles,
-                              cudaStream_t s, int* n_launches);
+                                  const BatchStats& hstats, int32_t nb, const DSiteTableOut& T,
+                                  cudaStream_t s, int* n_launches);
 cudaError_t launch_contig_range(int32_t n, const int32_t* contig, int32_t c, int32_t* d_range,
                                 cudaStream_t s);
 

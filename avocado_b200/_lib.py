@@ -20,15 +20,16 @@ AVO_E_EMPTY_SITES = -4
 AVO_E_UNSORTED = -5
 AVO_E_UNSUPPORTED = -6
 AVO_E_NOMEM = -7
+AVO_E_RETRY = -8
 MEM_HOST, MEM_DEVICE = 0, 1
 MAX_PLOIDY = 7
 
 OP_MATCH, OP_MISMATCH, OP_INS, OP_DEL, OP_SOFTCLIP, OP_HARDCLIP = range(6)
-READ_NEGATIVE_STRAND, READ_SKIP_CALL = 1, 2
+READ_NEGATIVE_STRAND, READ_SKIP_CALL, READ_OPS_DROPPED = 1, 2, 4
 
 STATUS_NAMES = {0: "AVO_OK", -1: "AVO_E_INVALID", -2: "AVO_E_CUDA", -3: "AVO_E_CAPACITY",
                 -4: "AVO_E_EMPTY_SITES", -5: "AVO_E_UNSORTED", -6: "AVO_E_UNSUPPORTED",
-                -7: "AVO_E_NOMEM"}
+                -7: "AVO_E_NOMEM", -8: "AVO_E_RETRY"}
 
 P = C.c_void_p
 
@@ -64,6 +65,12 @@ class SitesOutStruct(C.Structure):
                 ("n_allele_nibbles", C.c_int64), ("mem", C.c_int32), ("reserved", C.c_int32),
                 ("start", P), ("ref_len", P), ("alt_len", P), ("allele_off", P), ("alleles4", P),
                 ("count", P)]
+
+
+class ShardPlanStruct(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("own_lo", C.c_int32), ("own_hi", C.c_int32),
+                ("site_cap", C.c_int64), ("allele_cap", C.c_int64), ("row_cap", C.c_int64),
+                ("n_states", C.c_int32), ("reserved", C.c_int32)]
 
 
 RESULT_COLUMNS = [
@@ -214,6 +221,7 @@ EXPORTED_SYMBOLS = [
     "avo_call_all_sites", "avo_filter_genotypes", "avo_square_off", "avo_trio_call", "avo_joint_counts", "avo_joint", "avo_joint_depths",
     "avo_pack_wire", "avo_pack_wire6", "avo_pack_bounds", "avo_pack_reads", "avo_pack_reads_mt", "avo_pack_reads_device", "avo_synth_default_params",
     "avo_synth_host", "avo_synth_device", "avo_synth_text",
+    "avo_shard_table_block_bytes", "avo_shard_rows_block_bytes", "avo_shard_discover", "avo_shard_call", "avo_shard_finish",
 ]
 
 _lib = None
@@ -271,6 +279,15 @@ def load():
     lib.avo_synth_device.argtypes = [C.POINTER(SynthParamsStruct), C.c_int64, C.c_int64, P, P,
                                      C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                      C.POINTER(PackedOutStruct), P]
+    lib.avo_shard_table_block_bytes.argtypes = [C.POINTER(ShardPlanStruct)]
+    lib.avo_shard_table_block_bytes.restype = C.c_int64
+    lib.avo_shard_rows_block_bytes.argtypes = [C.POINTER(ShardPlanStruct)]
+    lib.avo_shard_rows_block_bytes.restype = C.c_int64
+    lib.avo_shard_discover.argtypes = [P, C.POINTER(ReadBatchStruct), C.POINTER(ParamsStruct), C.POINTER(ShardPlanStruct), P]
+    lib.avo_shard_call.argtypes = [P, C.POINTER(CnvStruct), C.POINTER(ParamsStruct), C.POINTER(ShardPlanStruct), P,
+                                   C.POINTER(SitesOutStruct), P]
+    lib.avo_shard_finish.argtypes = [P, C.POINTER(ShardPlanStruct), P, P, C.POINTER(SitesOutStruct),
+                                     C.POINTER(SiteResultsStruct), C.POINTER(ShardPlanStruct)]
     _lib = lib
     return lib
 

@@ -25,7 +25,7 @@ enum Slot {
   SL_META, SL_COORDS, SL_PAYLOAD, SL_OPS, SL_REFB, SL_WIRE_META, SL_WIRE_OPS, SL_WIRE_OPC, SL_WIRE_OFFS, SL_WIRE_SIZES, SL_WIRE_EXC,
   SL_S_CONTIG, SL_S_START, SL_S_REFLEN, SL_S_ALTLEN, SL_S_AOFF, SL_S_ALLELES, SL_S_END, SL_S_PME,
   SL_S_COUNT,
-  SL_CNV, SL_STATS, SL_SMALL, SL_RIDX, SL_SIDX, SL_TEMP, SL_LUT, SL_ARENA, SL_U_NEXT, SL_PACK,
+  SL_CNV, SL_STATS, SL_SMALL, SL_RIDX, SL_SIDX, SL_TEMP, SL_LUT, SL_ARENA, SL_U_NEXT, SL_PACK, SL_G_END, SL_G_PME, SL_G_SIDX, SL_G_COUNT,
   SL_RES,                      // one block holding every result column
   SL_U_START, SL_U_REFLEN, SL_U_ALTLEN, SL_U_COUNT, SL_U_SRC,
   SL_L_POS, SL_L_REFLEN, SL_L_ALTLEN, SL_L_NIBS, SL_L_SRC, SL_L_BLK, SL_L_HASH,
@@ -46,6 +46,9 @@ struct Buf { void* p = nullptr; size_t cap = 0; };
 
 }  // namespace
 
+struct ShardState;
+void free_shard_state(struct avo_ctx* ctx);
+
 struct avo_ctx {
   int device = 0;
   int num_sms = 0;
@@ -64,6 +67,7 @@ struct avo_ctx {
   int64_t site_guess = 0;          // survivors / allele nibbles of the previous discovery (+ margin): the
   int64_t nib_guess = 0;           // capacities the next one runs with (checked when its counts arrive)
   int disc_blocks_per_sm = 0;      // resident CTAs of k_discover_tiles per SM (occupancy query, once)
+  ShardState* shard = nullptr;     // between avo_shard_discover / _call / _finish
   BatchStats* h_stats = nullptr;   // pinned
   int32_t* h_small = nullptr;      // pinned scratch (16 ints)
   // device -> host results travel through one page-locked staging buffer (a few large DMA copies
@@ -385,7 +389,7 @@ struct DevSites {
 // words of the SL_SMALL block (int32): what the kernels count for the host
 enum SmallWord {
   SW_UNSORTED = 0, SW_CRANGE = 1 /* 2 */, SW_SRANGE = 4 /* 2 */, SW_TILE = 8, SW_FLAGS = 9, SW_NOUT = 10, SW_NINDEL = 11,
-  SW_JOIN = 14, SW_HDR = 16 /* DSiteHdr: 8 words */, SW_COUNT_ = 32
+  SW_JOIN = 14, SW_HDR = 16 /* DSiteHdr: 8 words */, SW_HDR2 = 24 /* the global table's, sharded runs */, SW_COUNT_ = 32
 };
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -1028,6 +1032,19 @@ int finish_call(avo_ctx* ctx, bool did_discover, bool did_call) {
 
 }  // namespace
 
+// what avo_shard_discover leaves for avo_shard_call / avo_shard_finish
+struct ShardState {
+  DReads R{};
+  BatchStats hs{};
+  DevSites T_loc, T_glob;
+  DResults D{};
+  DiscCaps caps;
+  size_t slots_cap = SIZE_MAX;
+  int ns = 0;
+  int phase = 0;
+};
+void free_shard_state(avo_ctx* ctx) { delete ctx->shard; ctx->shard = nullptr; }
+
 // ---- public entry points -------------------------------------------------------------------------
 extern "C" {
 
@@ -1102,6 +1119,7 @@ void avo_ctx_destroy(avo_ctx* ctx) {
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_gidx) cudaFreeHost(ctx->h_gidx);
   if (ctx->h_gblk) cudaFreeHost(ctx->h_gblk);
+  free_shard_state(ctx);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   cudaGetLastError();
@@ -1296,6 +1314,190 @@ int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_c
     CKS(d2h_block(ctx, d_pack, total, sc, cc.n));
   }
   CKS(finish_call(ctx, true, true));
+  return AVO_OK;
+}
+
+// ---- region-sharded discoverAndCall: three phases around the framework's two all-gathers ------------
+static int check_plan(avo_ctx* ctx, const avo_shard_plan* pl) {
+  if (!pl) return fail(ctx, AVO_E_INVALID, "shard plan is NULL");
+  if (pl->world < 1 || pl->world > AVO_MAX_SHARDS || pl->rank < 0 || pl->rank >= pl->world)
+    return fail(ctx, AVO_E_INVALID, "shard plan: bad rank / world (at most %d ranks)", AVO_MAX_SHARDS);
+  if (pl->site_cap < 1 || pl->site_cap >= INT32_MAX / 8 || pl->row_cap < 1 || pl->row_cap >= INT32_MAX / 8 ||
+      pl->allele_cap < 16 || (pl->allele_cap & 15) || pl->allele_cap >= INT32_MAX)
+    return fail(ctx, AVO_E_INVALID, "shard plan: bad capacities (allele_cap must be a multiple of 16)");
+  if (pl->own_lo > pl->own_hi) return fail(ctx, AVO_E_INVALID, "shard plan: own_lo > own_hi");
+  return AVO_OK;
+}
+
+int64_t avo_shard_table_block_bytes(const avo_shard_plan* pl) {
+  return pl ? (int64_t)shard_table_block_bytes(pl->site_cap, pl->allele_cap) : 0;
+}
+int64_t avo_shard_rows_block_bytes(const avo_shard_plan* pl) {
+  return pl ? (int64_t)shard_rows_block_bytes(pl->row_cap, pl->n_states) : 0;
+}
+
+int avo_shard_discover(avo_ctx* ctx, const avo_read_batch* reads, const avo_params* params,
+                       const avo_shard_plan* pl, void* table_block) {
+  CKS(begin_call(ctx));
+  CKS(validate_reads(ctx, reads));
+  CKS(check_params(ctx, params));
+  CKS(check_plan(ctx, pl));
+  if (!table_block || ((uintptr_t)table_block & 15u)) return fail(ctx, AVO_E_INVALID, "table_block must be a 16-byte aligned device buffer");
+  if (!ctx->shard) ctx->shard = new (std::nothrow) ShardState();
+  if (!ctx->shard) return fail(ctx, AVO_E_NOMEM, "out of host memory");
+  ShardState& st = *ctx->shard;
+  st.phase = 0;
+  CKS(upload_reads(ctx, reads, params->host_payload != 1, &st.R, params));
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  const bool hinted = stats_from_hints(reads, &st.hs);
+  if (!hinted) CKS(batch_stats(ctx, st.R, &st.hs));
+  initial_caps(ctx, st.R, &st.caps);
+  CKS(discover_enqueue(ctx, st.R, st.hs, hinted, params, st.caps, nullptr, &st.T_loc));
+  void* d_small;
+  CKS(get_buf(ctx, SL_SMALL, SW_COUNT_ * 4, &d_small));
+  ShardTableIn T{st.T_loc.hdr, st.T_loc.cap, st.T_loc.nib_cap, st.T_loc.start, st.T_loc.ref_len, st.T_loc.alt_len,
+                 st.T_loc.count, st.T_loc.pme, st.T_loc.allele_off, st.T_loc.alleles4};
+  ShardLocalCaps C{SW_FLAGS, SW_NOUT, SW_NINDEL, (int32_t)std::min<int64_t>(st.caps.ucap, INT32_MAX - 1),
+                   (int32_t)std::min<int64_t>(st.caps.lcap, INT32_MAX - 1)};
+  CK(launch_shard_owned(T, pl->own_lo, pl->own_hi, (const int32_t*)d_small, C, table_block, (int32_t)pl->site_cap,
+                        (int32_t)pl->allele_cap, ctx->num_sms, ctx->stream));
+  ctx->timing.n_launches += 1;
+  CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  st.phase = 1;
+  return AVO_OK;
+}
+
+int avo_shard_call(avo_ctx* ctx, const avo_cnv* cnv, const avo_params* params, const avo_shard_plan* pl,
+                   const void* gathered_tables, avo_sites_out* gs, void* rows_block) {
+  if (!ctx) return AVO_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CKS(check_params(ctx, params));
+  CKS(check_plan(ctx, pl));
+  if (!ctx->shard || ctx->shard->phase != 1) return fail(ctx, AVO_E_INVALID, "avo_shard_call follows avo_shard_discover");
+  if (!gathered_tables || !rows_block || ((uintptr_t)rows_block & 15u)) return fail(ctx, AVO_E_INVALID, "NULL / unaligned block");
+  if (!gs || gs->mem != AVO_MEM_DEVICE || !gs->start || !gs->ref_len || !gs->alt_len || !gs->allele_off || !gs->alleles4 ||
+      gs->capacity < 1)
+    return fail(ctx, AVO_E_INVALID, "global_sites must be device arrays with a capacity");
+  ShardState& st = *ctx->shard;
+  void *d_small, *q;
+  CKS(get_buf(ctx, SL_SMALL, SW_COUNT_ * 4, &d_small));
+  int32_t* small = (int32_t*)d_small;
+  const int32_t nb = index_bins(st.hs);
+  DSiteTableOut G{};
+  G.cap = (int32_t)std::min<int64_t>(gs->capacity, INT32_MAX - 1);
+  G.nib_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(gs->allele_capacity, 0), UINT32_MAX);
+  G.start = gs->start; G.ref_len = gs->ref_len; G.alt_len = gs->alt_len; G.allele_off = gs->allele_off; G.alleles4 = gs->alleles4;
+  G.count = gs->count;
+  CKS(get_buf(ctx, SL_G_END, (size_t)G.cap * 4, &q)); G.end = (int32_t*)q;
+  CKS(get_buf(ctx, SL_G_PME, (size_t)G.cap * 4, &q)); G.pme = (int32_t*)q;
+  CKS(get_buf(ctx, SL_G_SIDX, (size_t)(nb + 1) * 4, &q)); G.sidx = (int32_t*)q;
+  G.hdr = (DSiteHdr*)(small + SW_HDR2);
+  CK(launch_shard_concat(gathered_tables, pl->world, (int32_t)pl->site_cap, (int32_t)pl->allele_cap, G, ctx->num_sms, ctx->stream));
+  DevSites& T = st.T_glob;
+  T = DevSites();
+  T.start = G.start; T.ref_len = G.ref_len; T.alt_len = G.alt_len; T.allele_off = G.allele_off; T.alleles4 = G.alleles4;
+  T.count = G.count; T.hdr = G.hdr; T.cap = G.cap; T.nib_cap = G.nib_cap; T.end = G.end; T.pme = G.pme; T.sidx = G.sidx;
+  T.caller_arrays = true;
+  {
+    DSites S{};
+    S.hdr = T.hdr; S.cap = T.cap; S.n = T.cap; S.c_hi = T.cap; S.start = T.start; S.pme = T.pme;
+    CK(launch_shard_site_index(S, st.hs, nb, G.sidx, G.hdr, ctx->stream));
+  }
+  ctx->timing.n_launches += 2;
+  // the call stage against the global table; rows into the context's block (host-style destination)
+  avo_site_results fake{};
+  fake.mem = AVO_MEM_HOST; fake.n_states = pl->n_states; fake.n_sites = T.cap;
+  uint64_t* h_slots = reinterpret_cast<uint64_t*>(ctx->h_small + 48);
+  *h_slots = 0;
+  CKS(call_internal(ctx, st.R, st.hs, T, cnv, params, true, &fake, nullptr, &st.D, &st.slots_cap));
+  st.ns = st.D.ns;
+  void* d_boff = ctx->bufs[SL_C_BOFF].p;
+  const uint64_t* d_slots = st.slots_cap != SIZE_MAX ? (const uint64_t*)d_boff + std::min<int64_t>(T.cap, fake.n_sites) : nullptr;
+  CK(launch_shard_pack_rows(st.D, st.ns, gathered_tables, pl->world, pl->rank, (int32_t)pl->site_cap, (int32_t)pl->allele_cap,
+                            d_slots, st.slots_cap == SIZE_MAX ? 0 : (uint64_t)st.slots_cap, rows_block, (int32_t)pl->row_cap,
+                            ctx->num_sms, ctx->stream));
+  ctx->timing.n_launches += 1;
+  st.phase = 2;
+  return AVO_OK;
+}
+
+int avo_shard_finish(avo_ctx* ctx, const avo_shard_plan* pl, const void* gathered_tables, const void* gathered_rows,
+                     avo_sites_out* gs, avo_site_results* gr, avo_shard_plan* needed) {
+  if (!ctx) return AVO_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CKS(check_plan(ctx, pl));
+  if (!ctx->shard || ctx->shard->phase != 2) return fail(ctx, AVO_E_INVALID, "avo_shard_finish follows avo_shard_call");
+  if (!gathered_tables || !gathered_rows || !gs) return fail(ctx, AVO_E_INVALID, "NULL argument");
+  CKS(check_results(ctx, gr));
+  if (gr->mem != AVO_MEM_DEVICE) return fail(ctx, AVO_E_INVALID, "global_results must be device arrays");
+  ShardState& st = *ctx->shard;
+  st.phase = 0;
+  if (gr->n_states != st.ns) return fail(ctx, AVO_E_INVALID, "global_results->n_states must be %d", st.ns);
+  DResults O;
+  O.ns = st.ns;
+  O.emitted = gr->emitted; O.allele_fwd = gr->allele_fwd; O.other_fwd = gr->other_fwd; O.allele_cov = gr->allele_cov;
+  O.other_cov = gr->other_cov; O.total_cov = gr->total_cov; O.square_mapq = gr->square_mapq; O.ref_ll = gr->ref_ll;
+  O.allele_ll = gr->allele_ll; O.other_ll = gr->other_ll; O.nonref_ll = gr->nonref_ll; O.first_is_ref = gr->first_is_ref;
+  O.copy_number = gr->copy_number; O.n_alt = gr->n_alt; O.n_ref = gr->n_ref; O.n_other = gr->n_other; O.qual = gr->qual;
+  O.gq = gr->gq; O.sb = gr->sb; O.fisher = gr->fisher; O.rms_mapq = gr->rms_mapq; O.gl = gr->gl; O.nonref_gl = gr->nonref_gl;
+  const int64_t out_rows = gr->n_sites;
+  CK(launch_shard_unpack_rows(gathered_rows, pl->world, (int32_t)pl->row_cap, st.ns, O, out_rows, ctx->num_sms, ctx->stream));
+  ctx->timing.n_launches += 1;
+  // headers of both gathers + this rank's own counters, one synchronisation
+  const size_t tb = shard_table_block_bytes(pl->site_cap, pl->allele_cap), rb = shard_rows_block_bytes(pl->row_cap, st.ns);
+  std::vector<ShardHdr> ht(pl->world), hr(pl->world);
+  for (int r = 0; r < pl->world; ++r) {
+    CK(cudaMemcpyAsync(&ht[r], (const char*)gathered_tables + (size_t)r * tb, sizeof(ShardHdr), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&hr[r], (const char*)gathered_rows + (size_t)r * rb, sizeof(ShardHdr), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CKS(discover_fetch_counts(ctx));
+  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  // this rank's own capacities (grown for the next run if short; the flags in its header told everyone)
+  bool again_local = false;
+  {
+    DevSites t = st.T_loc;
+    const int rc = discover_check(ctx, &st.caps, &t, &again_local);
+    if (rc != AVO_OK && rc != AVO_E_UNSORTED && rc != AVO_E_INVALID) return rc;
+    if (again_local) {            // remember the larger capacities for the next avo_shard_discover
+      ctx->site_guess = std::max(ctx->site_guess, st.caps.ucap);
+      ctx->indel_guess = std::max<int64_t>(ctx->indel_guess, st.caps.lcap);
+      ctx->nib_guess = std::max(ctx->nib_guess, st.caps.nib_cap);
+    }
+    if (st.slots_cap != SIZE_MAX) {
+      const size_t actual = (size_t)*reinterpret_cast<uint64_t*>(ctx->h_small + 48);
+      ctx->slots_guess = actual + actual / 8 + 1024;
+    }
+  }
+  int32_t flags = 0;
+  int64_t rows = 0, bytes = 0, max_rows = 0, max_bytes = 0;
+  for (int r = 0; r < pl->world; ++r) {
+    flags |= ht[r].flags | hr[r].flags;
+    rows += ht[r].n_rows; bytes += ht[r].n_bytes;
+    max_rows = std::max<int64_t>(max_rows, ht[r].n_rows); max_bytes = std::max<int64_t>(max_bytes, ht[r].n_bytes);
+  }
+  ctx->timing.ms_total = ev_ms(ctx, 0, 7);
+  ctx->timing.ms_discover = ev_ms(ctx, 1, 6);
+  ctx->timing.ms_discover_tiles = ev_ms(ctx, 2, 3);
+  ctx->timing.ms_call_tiles = ev_ms(ctx, 4, 5);
+  if (flags & SHARD_UNSORTED) return fail(ctx, AVO_E_UNSORTED, "reads are not sorted by start (on some rank)");
+  if (flags & SHARD_BAD_STATS) return fail(ctx, AVO_E_INVALID, "reads->stats does not bound the batch (on some rank)");
+  if (needed) {
+    *needed = *pl;
+    needed->site_cap = max_rows + max_rows / 8 + 256;
+    needed->allele_cap = (max_bytes + max_bytes / 8 + 4096 + 15) & ~(int64_t)15;
+    needed->row_cap = needed->site_cap;
+  }
+  gs->n = rows;
+  gs->n_allele_nibbles = 2 * bytes;
+  gr->n_sites = rows;
+  if (flags & SHARD_BLOCK_FULL)
+    return fail(ctx, AVO_E_CAPACITY, "shard blocks too small: a rank owns %lld rows / %lld allele bytes", (long long)max_rows,
+                (long long)max_bytes);
+  if (flags & SHARD_RETRY) return fail(ctx, AVO_E_RETRY, "a rank ran out of an internal capacity; run the step again");
+  if (rows > gs->capacity || 2 * bytes > gs->allele_capacity || rows > out_rows)
+    return fail(ctx, AVO_E_CAPACITY, "global tables too small: need %lld rows, %lld allele nibbles", (long long)rows,
+                (long long)(2 * bytes));
   return AVO_OK;
 }
 

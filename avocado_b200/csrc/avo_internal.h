@@ -217,6 +217,38 @@ struct ColumnCopies {
 };
 cudaError_t launch_copy_columns(const ColumnCopies& cc, cudaStream_t s);
 
+// ---- region-sharded discoverAndCall (avo_shard.cu) ---------------------------------------------------
+constexpr int AVO_MAX_SHARDS = 64;
+constexpr int AVO_RESULT_COLUMNS = 23;
+enum : int32_t { SHARD_RETRY = 1, SHARD_UNSORTED = 2, SHARD_BAD_STATS = 4, SHARD_BLOCK_FULL = 8 };
+struct ShardHdr {          // first 32 bytes of a table block and of a rows block
+  int32_t n_rows;          // rows this rank owns (may exceed the block's capacity: SHARD_BLOCK_FULL)
+  int32_t n_bytes;         // their allele bytes
+  int32_t flags;           // SHARD_*
+  int32_t max_end;         // table block: furthest site end up to the rank's last owned row
+  int32_t reserved[4];
+};
+static_assert(sizeof(ShardHdr) == 32, "block header");
+struct ShardTableIn {      // a rank's own table (assembled by k_assemble_sites)
+  const DSiteHdr* hdr; int32_t cap; uint32_t nib_cap;
+  const int32_t *start, *ref_len, *alt_len, *count, *pme; const uint32_t* allele_off; const uint8_t* alleles4;
+};
+struct ShardLocalCaps { int32_t w_flags, w_nout, w_nindel; int32_t ucap, lcap; };   // counter words, capacities
+size_t shard_table_block_bytes(int64_t cap, int64_t acap);
+size_t shard_rows_block_bytes(int64_t cap, int ns);
+cudaError_t launch_shard_owned(const ShardTableIn& T, int32_t own_lo, int32_t own_hi, const int32_t* counters,
+                               const ShardLocalCaps& C, void* block, int32_t cap, int32_t acap, int num_sms, cudaStream_t s);
+struct DSiteTableOut;
+cudaError_t launch_shard_concat(const void* gathered, int32_t world, int32_t cap, int32_t acap, const DSiteTableOut& G,
+                                int num_sms, cudaStream_t s);
+cudaError_t launch_shard_site_index(const DSites& S, const BatchStats& h, int32_t nb, int32_t* sidx, DSiteHdr* hdr,
+                                    cudaStream_t s);
+cudaError_t launch_shard_pack_rows(const DResults& D, int ns, const void* gathered_tables, int32_t world, int32_t rank,
+                                   int32_t tcap, int32_t tacap, const uint64_t* slots_used, uint64_t slots_cap, void* block,
+                                   int32_t rcap, int num_sms, cudaStream_t s);
+cudaError_t launch_shard_unpack_rows(const void* gathered_rows, int32_t world, int32_t rcap, int ns, const DResults& O,
+                                     int64_t out_rows, int num_sms, cudaStream_t s);
+
 // ---- launchers (each returns the cudaError_t of its launches) --------------------------------
 cudaError_t launch_batch_stats(const DReads& R, BatchStats* d_stats, cudaStream_t s);
 cudaError_t launch_site_setup(int32_t n, const int32_t* contig, const int32_t* start,

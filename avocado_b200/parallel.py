@@ -134,6 +134,124 @@ def _all_gather_rows(x, device=None, group=None):
     return [p[:s].cpu().numpy().view(x.dtype) for p, s in zip(parts, sizes)]
 
 
+class ShardedPipeline:
+    """Region-sharded discoverAndCall with everything on the device (the C ABI's avo_shard_discover /
+    avo_shard_call / avo_shard_finish around two NCCL all-gathers of fixed-size blocks): the owned slice of
+    every rank's site table, then the result rows of the owned sites.  The host waits once per step, in
+    avo_shard_finish.  `gather(out, inp)` is the collective: torch.distributed's all_gather_into_tensor over
+    NCCL by default; tests emulate several ranks on one GPU by passing their own."""
+
+    def __init__(self, ctx, rank: int, world: int, own_lo: int, own_hi: int, ploidy: int = 2, site_cap: int = 1 << 15,
+                 allele_cap: int = 1 << 17, global_cap: Optional[int] = None, gather=None, group=None, stream=None):
+        import torch
+        from . import _lib as L
+        self.ctx, self.L, self.torch = ctx, L, torch
+        self.dev = "cuda:%d" % ctx.device
+        self.plan = L.ShardPlanStruct()
+        self.plan.rank, self.plan.world, self.plan.own_lo, self.plan.own_hi = rank, world, own_lo, own_hi
+        self.plan.n_states = ploidy + 1
+        self.ploidy = ploidy
+        self.global_cap = global_cap
+        self.group = group
+        self.gather = gather or self._nccl_gather
+        self.nccl_bytes = 0
+        # the phases and the collectives are ordered on ONE stream of the pipeline's own (the context's
+        # default is a stream torch does not know; torch's default stream has no handle to pass)
+        self.stream = stream or torch.cuda.Stream(self.dev)
+        ctx.set_stream(self.stream.cuda_stream)
+        self._size(site_cap, allele_cap)
+
+    def _nccl_gather(self, out, inp):
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def _size(self, site_cap, allele_cap):
+        import ctypes as C
+        torch, L, p = self.torch, self.L, self.plan
+        p.site_cap, p.allele_cap, p.row_cap = int(site_cap), (int(allele_cap) + 15) // 16 * 16, int(site_cap)
+        lib = self.ctx.lib
+        self.tb = lib.avo_shard_table_block_bytes(C.byref(p))
+        self.rb = lib.avo_shard_rows_block_bytes(C.byref(p))
+        W = p.world
+        self.t_send = torch.empty(self.tb, dtype=torch.uint8, device=self.dev)
+        self.t_all = torch.empty(self.tb * W, dtype=torch.uint8, device=self.dev)
+        self.r_send = torch.empty(self.rb, dtype=torch.uint8, device=self.dev)
+        self.r_all = torch.empty(self.rb * W, dtype=torch.uint8, device=self.dev)
+        gcap = self.global_cap or p.site_cap * W
+        self.gcap, self.gacap = int(gcap), int(p.allele_cap * W * 2)
+        from .batch import _device_empty
+        mk = lambda n, dt: _device_empty(n, dt, self.dev)
+        self.sites = dict(start=mk(self.gcap, np.int32), ref_len=mk(self.gcap, np.int32), alt_len=mk(self.gcap, np.int32),
+                          allele_off=mk(self.gcap + 1, np.uint32), alleles4=mk(self.gacap // 2 + 16, np.uint8),
+                          count=mk(self.gcap, np.int32))
+        self.res, self.cols = self.ctx._alloc_results(self.gcap, p.n_states, self.dev)
+
+    # ---- the three phases (step() runs them around the two collectives; tests drive them by hand) ----
+    def phase_discover(self, batch: ReadBatch, phred: int = 0, min_obs: Optional[int] = None):
+        import ctypes as C
+        ctx, p = self.ctx, self.plan
+        self._params = ctx._params(ploidy=self.ploidy, phred=phred, min_obs=min_obs)
+        self._bs = batch.as_struct()
+        ctx._check(ctx.lib.avo_shard_discover(ctx.h, C.byref(self._bs), C.byref(self._params), C.byref(p),
+                                              self.t_send.data_ptr()))
+
+    def phase_call(self):
+        import ctypes as C
+        from ._lib import MEM_DEVICE, SitesOutStruct
+        from .batch import _ptr
+        ctx, p = self.ctx, self.plan
+        out = SitesOutStruct()
+        out.capacity, out.allele_capacity, out.mem = self.gcap, self.gacap, MEM_DEVICE
+        for k, a in self.sites.items():
+            setattr(out, k, _ptr(a))
+        self._out = out
+        self.res.n_sites = self.gcap
+        ctx._check(ctx.lib.avo_shard_call(ctx.h, None, C.byref(self._params), C.byref(p), self.t_all.data_ptr(),
+                                          C.byref(out), self.r_send.data_ptr()))
+
+    def phase_finish(self):
+        """-> (table, cols) or None when every rank has to run the step again (capacities grown)."""
+        import ctypes as C
+        from ._lib import AVO_E_CAPACITY, AVO_E_RETRY
+        ctx, p, out = self.ctx, self.plan, self._out
+        need = self.L.ShardPlanStruct()
+        rc = ctx.lib.avo_shard_finish(ctx.h, C.byref(p), self.t_all.data_ptr(), self.r_all.data_ptr(), C.byref(out),
+                                      C.byref(self.res), C.byref(need))
+        self.nccl_bytes = (self.tb + self.rb) * p.world              # bytes every rank receives per step
+        if rc == AVO_E_RETRY:
+            return None
+        if rc == AVO_E_CAPACITY:           # the same answer on every rank: all of them grow and run again
+            self.global_cap = max(self.gcap, int(out.n) + int(out.n) // 8 + 256)
+            self._size(max(p.site_cap, need.site_cap), max(p.allele_cap, need.allele_cap))
+            return None
+        ctx._check(rc)
+        n, nn = int(out.n), int(out.n_allele_nibbles)
+        s = self.sites
+        table = SiteTable(n, nn, s["start"][:n], s["ref_len"][:n], s["alt_len"][:n], s["allele_off"][:n + 1],
+                          s["alleles4"][:(nn + 1) // 2 or 1], None, s["count"][:n])
+        cols = {}
+        for name, dt, w in self.L.RESULT_COLUMNS:
+            width = p.n_states if w == "ns" else w
+            a = self.cols[name][:n * width]
+            cols[name] = a.reshape(n, width) if width != 1 else a
+        return table, cols
+
+    def step(self, batch: ReadBatch, phred: int = 0, min_obs: Optional[int] = None, max_tries: int = 6):
+        """One sharded discoverAndCall over this rank's reads (own interval + halo).  Returns, on every
+        rank, (global SiteTable, dict of result columns for all its rows) as device tensors."""
+        from ._lib import AVO_E_CAPACITY, AvocadoError
+        for _ in range(max_tries):
+            with self.torch.cuda.stream(self.stream):
+                self.phase_discover(batch, phred, min_obs)
+                self.gather(self.t_all, self.t_send)
+                self.phase_call()
+                self.gather(self.r_all, self.r_send)
+                got = self.phase_finish()
+            if got is not None:
+                return got
+        raise AvocadoError(AVO_E_CAPACITY, "sharded step kept asking for larger buffers")
+
+
 class GpuEngine:
     """The product engine: avo_discover / avo_call on this rank's GPU."""
 

@@ -50,7 +50,8 @@ typedef enum {
   AVO_E_EMPTY_SITES = -4,  /* call() with no variants: the reference throws (TreeRegionJoin.scala:77) */
   AVO_E_UNSORTED = -5,     /* reads not sorted by start / sites not sorted by (contig,start,end) */
   AVO_E_UNSUPPORTED = -6,  /* parameter outside the supported domain (e.g. ploidy > AVO_MAX_PLOIDY) */
-  AVO_E_NOMEM = -7
+  AVO_E_NOMEM = -7,
+  AVO_E_RETRY = -8         /* avo_shard_finish: a rank ran out of an internal capacity (now grown): run the step again */
 } avo_status;
 
 enum { AVO_MEM_HOST = 0, AVO_MEM_DEVICE = 1 };
@@ -314,6 +315,46 @@ int avo_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_sites* sites, 
 int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_cnv* cnv,
                           const avo_params* params, avo_sites_out* sites_out,
                           avo_site_results* results);
+
+/* ---- region-sharded discoverAndCall: one process per GPU -------------------------------
+ * Replaces, for several GPUs, what the reference does with `sortByKey().collect` + `sc.broadcast` of the
+ * variants (util/TreeRegionJoin.scala:43-50, 184-185) and with the shuffle behind the per-site sums
+ * (genotyping/BiallelicGenotyper.scala:475-500).  Rank g owns the sites that START in [own_lo, own_hi)
+ * and is handed every read that can overlap one of them or put a discovery candidate on one: the reads
+ * with own_lo - max_span <= start < own_hi + (longest site).  Nothing is reduced across ranks; the host
+ * framework runs two all-gathers of fixed-size DEVICE blocks between three calls that never wait for the
+ * device (only avo_shard_finish synchronises):
+ *
+ *   avo_shard_discover(...)            -> table_block            this rank's owned slice of its table
+ *   all-gather(table_block)            -> gathered_tables        (world blocks, rank order)
+ *   avo_shard_call(...)                -> rows_block             the global table is assembled on the device,
+ *                                                                the reads are called against it, owned rows packed
+ *   all-gather(rows_block)             -> gathered_rows
+ *   avo_shard_finish(...)              -> global table + every row on every rank; one synchronisation
+ *
+ * Block sizes come from the plan's capacities (avo_shard_*_block_bytes).  avo_shard_finish returns
+ * AVO_E_CAPACITY with the capacities that are needed (identical on every rank: they follow from the
+ * gathered headers), or AVO_E_RETRY when some rank ran out of an internal capacity (every rank sees it in
+ * the gathered headers): in both cases EVERY rank runs the three calls again.  Tables and rows are device
+ * memory.  All three calls use the context's stream; the collectives must be ordered on it. */
+typedef struct {
+  int32_t rank, world;
+  int32_t own_lo, own_hi;   /* sites with own_lo <= start < own_hi belong to this rank */
+  int64_t site_cap;         /* rows one rank's table block holds */
+  int64_t allele_cap;       /* allele bytes one rank's table block holds (a multiple of 16) */
+  int64_t row_cap;          /* rows one rank's result block holds */
+  int32_t n_states;         /* max ploidy + 1, as in avo_site_results */
+  int32_t reserved;
+} avo_shard_plan;
+int64_t avo_shard_table_block_bytes(const avo_shard_plan* plan);
+int64_t avo_shard_rows_block_bytes(const avo_shard_plan* plan);
+int avo_shard_discover(avo_ctx* ctx, const avo_read_batch* reads, const avo_params* params,
+                       const avo_shard_plan* plan, void* table_block);
+int avo_shard_call(avo_ctx* ctx, const avo_cnv* cnv, const avo_params* params, const avo_shard_plan* plan,
+                   const void* gathered_tables, avo_sites_out* global_sites, void* rows_block);
+int avo_shard_finish(avo_ctx* ctx, const avo_shard_plan* plan, const void* gathered_tables,
+                     const void* gathered_rows, avo_sites_out* global_sites, avo_site_results* global_results,
+                     avo_shard_plan* needed);
 
 /* ---- scoreAllSites (gVCF mode) ---------------------------------------------------------------- */
 /* Reference-model rows of BiallelicGenotyper.call(scoreAllSites = true) (BG:223-275, 299-306): one

@@ -42,6 +42,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include "../avocado_b200/csrc/avo_synth_core.h"   // the workload generator's source (bench / test input, not the path)
+
 namespace py = pybind11;
 
 namespace orc {
@@ -1540,48 +1542,31 @@ static std::shared_ptr<ReadSet> makeReads(
 // Packed columnar batch (include/avocado_b200.h) -> text AlignmentRecords, so that synthetic
 // batches (which are born packed) can be handed to the oracle.  CIGAR uses =/X/I/D/S/H, the MD
 // tag is rebuilt from the =/X/D runs.  skip-call reads get a null mapq (what the flag stands for).
-static std::shared_ptr<ReadSet> readsFromPacked(
-    const std::string& contigName,
-    py::array_t<int32_t, py::array::c_style | py::array::forcecast> start,
-    py::array_t<int32_t, py::array::c_style | py::array::forcecast> end,
-    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> mapq,
-    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> flags,
-    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> seqOff,
-    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> lSeq,
-    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> payload,
-    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> opOff,
-    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> nOps,
-    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> ops,
-    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> refbOff,
-    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> refb) {
+// reads [lo, hi) of a packed batch (include/avocado_b200.h layout) as text records
+static void readsFromPackedRaw(const std::string& contigName, size_t lo, size_t hi, const int32_t* st, const int32_t* en,
+                               const uint8_t* mq, const uint8_t* fl, const uint32_t* so, const uint32_t* ls,
+                               const uint8_t* pl, const uint32_t* oo, const uint32_t* no, const uint32_t* op,
+                               const uint32_t* fo, const uint8_t* fb, Read* out) {
   static const char* NIBS = "=ACMGRSVTWYHKDBN";
-  auto rs = std::make_shared<ReadSet>();
-  const size_t n = (size_t)start.size();
-  auto st = start.unchecked<1>(); auto en = end.unchecked<1>(); auto mq = mapq.unchecked<1>();
-  auto fl = flags.unchecked<1>(); auto so = seqOff.unchecked<1>(); auto ls = lSeq.unchecked<1>();
-  auto pl = payload.unchecked<1>(); auto oo = opOff.unchecked<1>();
-  auto no = nOps.unchecked<1>(); auto op = ops.unchecked<1>(); auto fo = refbOff.unchecked<1>();
-  auto fb = refb.unchecked<1>();
-  auto nib = [](const auto& a, uint64_t i) -> int { int b = a(i >> 1); return (i & 1) ? (b & 15) : (b >> 4); };
-  rs->reads.resize(n);
-  for (size_t i = 0; i < n; ++i) {
-    Read& r = rs->reads[i];
+  auto nib = [](const uint8_t* a, uint64_t i) -> int { int b = a[i >> 1]; return (i & 1) ? (b & 15) : (b >> 4); };
+  for (size_t i = lo; i < hi; ++i) {
+    Read& r = out[i];
     r.mapped = true; r.contigName = contigName; r.hasStart = true;
-    r.start = st(i); r.end = en(i);
-    r.negativeStrand = fl(i) & 1;
-    r.hasMapq = !(fl(i) & 2); r.mapq = mq(i);
+    r.start = st[i]; r.end = en[i];
+    r.negativeStrand = fl[i] & 1;
+    r.hasMapq = !(fl[i] & 2); r.mapq = mq[i];
     // payload: 16-byte blocks of 10 bases (bytes 0..4, 4 bit each) + their 10 qualities (bytes 5..14)
-    const uint64_t blk0 = so(i);
+    const uint64_t blk0 = so[i];
     auto baseAt = [&](uint64_t k) -> int {
       const uint64_t c = k / 10, w = k % 10;
-      const int v = pl((blk0 + c) * 16 + (w >> 1));
+      const int v = pl[(blk0 + c) * 16 + (w >> 1)];
       return (w & 1) ? (v & 15) : (v >> 4);
     };
-    for (uint64_t k = 0; k < ls(i); ++k) {
+    for (uint64_t k = 0; k < ls[i]; ++k) {
       r.seq.push_back(NIBS[baseAt(k)]);
-      r.qual.push_back((char)(pl((blk0 + k / 10) * 16 + 5 + k % 10) + 33));
+      r.qual.push_back((char)(pl[(blk0 + k / 10) * 16 + 5 + k % 10] + 33));
     }
-    uint64_t f = fo(i);   // byte index into refb
+    uint64_t f = fo[i];   // byte index into refb
     // read index the way DiscoverVariants counts it (DiscoverVariants.scala:139-172, 189-193): soft
     // clips count before the first aligned operator and are ignored after it
     uint64_t ridx = 0;
@@ -1589,17 +1574,17 @@ static std::shared_ptr<ReadSet> readsFromPacked(
     long run = 0;
     std::string md;
     bool any = false;
-    for (uint32_t k = oo(i); k < oo(i) + no(i); ++k) {
-      const uint32_t w = op(k), len = w >> 4, code = w & 15;
+    for (uint32_t k = oo[i]; k < oo[i] + no[i]; ++k) {
+      const uint32_t w = op[k], len = w >> 4, code = w & 15;
       any = true;
       r.cigar += std::to_string(len) + "=XIDSH"[code];
       if (code == 0) { run += len; ridx += len; aligned = true; }
       else if (code == 1) {
         for (uint32_t j = 0; j < len; ++j) {
-          const int pr = fb(f++);
+          const int pr = fb[f++];
           // the low nibble repeats the read base discovery takes as the alternate allele: a packer /
           // generator consistency check (a base past the end of the sequence is stored as N)
-          const int want = ridx + j < ls(i) ? baseAt(ridx + j) : 15;
+          const int want = ridx + j < ls[i] ? baseAt(ridx + j) : 15;
           if ((pr & 15) != want)
             throw std::runtime_error("packed batch: mismatch pair does not repeat the read base");
           md += std::to_string(run); md.push_back(NIBS[pr >> 4]); run = 0;
@@ -1616,7 +1601,145 @@ static std::shared_ptr<ReadSet> readsFromPacked(
     r.hasCigar = any; r.hasMd = any;
     r.md = md;
   }
+}
+
+static std::shared_ptr<ReadSet> readsFromPacked(
+    const std::string& contigName,
+    py::array_t<int32_t, py::array::c_style | py::array::forcecast> start,
+    py::array_t<int32_t, py::array::c_style | py::array::forcecast> end,
+    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> mapq,
+    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> flags,
+    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> seqOff,
+    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> lSeq,
+    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> payload,
+    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> opOff,
+    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> nOps,
+    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> ops,
+    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> refbOff,
+    py::array_t<uint8_t, py::array::c_style | py::array::forcecast> refb) {
+  auto rs = std::make_shared<ReadSet>();
+  const size_t n = (size_t)start.size();
+  rs->reads.resize(n);
+  readsFromPackedRaw(contigName, 0, n, start.data(), end.data(), mapq.data(), flags.data(), seqOff.data(), lSeq.data(),
+                     payload.data(), opOff.data(), nOps.data(), ops.data(), refbOff.data(), refb.data(), rs->reads.data());
   return rs;
+}
+
+// The synthetic workload of bench.py / the tests, generated HERE (same generator source as the product's
+// avo_synth_host / avo_synth_device: avocado_b200/csrc/avo_synth_core.h), so that bench.py's reference
+// arm and cpu_baseline leg build their input without loading libavocado_b200.so.  Reads [first, first + n)
+// of the workload `params` = {seed, contig_len, first_pos, n_reads_total, read_len, max_indel, snp_rate,
+// indel_rate, triallelic_frac, softclip_frac, sample} (missing keys: avo_synth_default_params' values).
+static avo_synth_params synthParams(const py::dict& d) {
+  avo_synth_params p;
+  p.seed = 0xA70CAD0ull; p.contig_len = 1000000; p.first_pos = 0; p.n_reads_total = 200000; p.read_len = 150;
+  p.max_indel = 20; p.snp_rate = 1.0e-3; p.indel_rate = 1.0e-4; p.triallelic_frac = 0.01; p.softclip_frac = 0.02;
+  p.sample = 0;
+  auto has = [&](const char* k) { return d.contains(k) && !d[k].is_none(); };
+  if (has("seed")) p.seed = d["seed"].cast<uint64_t>();
+  if (has("contig_len")) p.contig_len = d["contig_len"].cast<int32_t>();
+  if (has("first_pos")) p.first_pos = d["first_pos"].cast<int32_t>();
+  if (has("n_reads_total")) p.n_reads_total = d["n_reads_total"].cast<int64_t>();
+  if (has("read_len")) p.read_len = d["read_len"].cast<int32_t>();
+  if (has("max_indel")) p.max_indel = d["max_indel"].cast<int32_t>();
+  if (has("snp_rate")) p.snp_rate = d["snp_rate"].cast<double>();
+  if (has("indel_rate")) p.indel_rate = d["indel_rate"].cast<double>();
+  if (has("triallelic_frac")) p.triallelic_frac = d["triallelic_frac"].cast<double>();
+  if (has("softclip_frac")) p.softclip_frac = d["softclip_frac"].cast<double>();
+  if (has("sample")) p.sample = d["sample"].cast<uint64_t>();
+  return p;
+}
+
+struct SynthPacked {
+  std::vector<int32_t> start, end;
+  std::vector<uint8_t> mapq, flags, payload, refb;
+  std::vector<uint32_t> seq_off, l_seq, op_off, n_ops, ops, refb_off, qhead;
+};
+
+static void synthPacked(const avo_synth_params& p, int64_t first, int64_t n, int nThreads, SynthPacked& o) {
+  if (n < 0 || first < 0 || first + n > p.n_reads_total || p.read_len < 30 || p.read_len > 1000 || p.max_indel < 1 ||
+      p.max_indel > 20 || (int64_t)p.contig_len < (int64_t)p.read_len + 2 * p.max_indel + 4)
+    throw std::runtime_error("synth: bad parameters");
+  const uint32_t lpad = avo::blocks_of((uint32_t)p.read_len);
+  o.start.resize(n); o.end.resize(n); o.mapq.resize(n); o.flags.resize(n); o.seq_off.resize(n); o.l_seq.resize(n);
+  o.op_off.resize(n + 1); o.n_ops.resize(n); o.refb_off.resize(n + 1); o.qhead.resize(n);
+  const int T = std::max(1, std::min<int>(nThreads, (int)std::max<int64_t>(1, n / 4096)));
+  auto span = [&](int t, int64_t& lo, int64_t& hi) { lo = n * t / T; hi = n * (t + 1) / T; };
+  auto run = [&](auto&& fn) {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t) pool.emplace_back(fn, t);
+    fn(0);
+    for (auto& th : pool) th.join();
+  };
+  std::vector<uint32_t> cf(n);
+  run([&](int t) {
+    int64_t lo, hi; span(t, lo, hi);
+    for (int64_t j = lo; j < hi; ++j) {
+      avo::CountSink c;
+      int32_t s, e; uint8_t mq, fl;
+      avo::synth_read(p, first + j, c, &s, &e, &mq, &fl);
+      o.n_ops[j] = c.n_ops; cf[j] = c.n_refb;
+    }
+  });
+  uint64_t to = 0, tf = 0;
+  for (int64_t j = 0; j < n; ++j) { o.op_off[j] = (uint32_t)to; o.refb_off[j] = (uint32_t)tf; to += o.n_ops[j]; tf += cf[j]; }
+  o.op_off[n] = (uint32_t)to; o.refb_off[n] = (uint32_t)tf;
+  o.payload.assign((size_t)n * lpad * 16 + 16, 0); o.ops.assign(to + 4, 0); o.refb.assign(tf + 16, 0);
+  run([&](int t) {
+    int64_t lo, hi; span(t, lo, hi);
+    for (int64_t j = lo; j < hi; ++j) {
+      avo::WriteSink w;
+      w.payload = o.payload.data(); w.ops = o.ops.data(); w.refb = o.refb.data();
+      w.blk0 = (uint64_t)j * lpad; w.oi = o.op_off[j]; w.fi = o.refb_off[j];
+      int32_t s, e; uint8_t mq, fl;
+      avo::synth_read(p, first + j, w, &s, &e, &mq, &fl);
+      o.start[j] = s; o.end[j] = e; o.mapq[j] = mq; o.flags[j] = fl; o.seq_off[j] = (uint32_t)(j * lpad);
+      o.l_seq[j] = (uint32_t)p.read_len; o.qhead[j] = w.qhead;
+    }
+  });
+}
+
+static std::shared_ptr<ReadSet> synthReads(const py::dict& params, int64_t first, int64_t n, const std::string& contigName,
+                                           int nThreads) {
+  const avo_synth_params p = synthParams(params);
+  auto rs = std::make_shared<ReadSet>();
+  {
+    py::gil_scoped_release rel;
+    SynthPacked o;
+    synthPacked(p, first, n, nThreads, o);
+    rs->reads.resize((size_t)n);
+    const int T = std::max(1, std::min<int>(nThreads, (int)std::max<int64_t>(1, n / 4096)));
+    std::vector<std::thread> pool;
+    auto fn = [&](int t) {
+      readsFromPackedRaw(contigName, (size_t)(n * t / T), (size_t)(n * (t + 1) / T), o.start.data(), o.end.data(), o.mapq.data(),
+                         o.flags.data(), o.seq_off.data(), o.l_seq.data(), o.payload.data(), o.op_off.data(), o.n_ops.data(),
+                         o.ops.data(), o.refb_off.data(), o.refb.data(), rs->reads.data());
+    };
+    for (int t = 1; t < T; ++t) pool.emplace_back(fn, t);
+    fn(0);
+    for (auto& th : pool) th.join();
+  }
+  return rs;
+}
+
+// the packed columns themselves (tests: byte-identical to the product's avo_synth_host)
+static py::dict synthPackedPy(const py::dict& params, int64_t first, int64_t n, int nThreads) {
+  SynthPacked o;
+  synthPacked(synthParams(params), first, n, nThreads, o);
+  auto arr = [](auto& v, size_t cnt) {
+    using T = typename std::remove_reference<decltype(v)>::type::value_type;
+    py::array_t<T> a(cnt);
+    std::copy(v.begin(), v.begin() + cnt, a.mutable_data());
+    return a;
+  };
+  py::dict d;
+  const size_t nn = (size_t)n;
+  d["start"] = arr(o.start, nn); d["end"] = arr(o.end, nn); d["mapq"] = arr(o.mapq, nn); d["flags"] = arr(o.flags, nn);
+  d["seq_off"] = arr(o.seq_off, nn); d["l_seq"] = arr(o.l_seq, nn); d["op_off"] = arr(o.op_off, nn);
+  d["n_ops"] = arr(o.n_ops, nn); d["refb_off"] = arr(o.refb_off, nn); d["qhead"] = arr(o.qhead, nn);
+  d["payload"] = arr(o.payload, o.payload.size() - 16); d["ops"] = arr(o.ops, (size_t)o.op_off[nn]);
+  d["refb"] = arr(o.refb, (size_t)o.refb_off[nn]);
+  return d;
 }
 
 static Read readFromDict(const py::dict& d) {
@@ -1693,6 +1816,9 @@ PYBIND11_MODULE(avocado_oracle, m) {
   m.def("make_reads", &makeReads);
   m.def("reads_from_dicts", &readsFromDicts);
   m.def("reads_from_packed", &readsFromPacked);
+  m.def("synth_reads", &synthReads, py::arg("params"), py::arg("first"), py::arg("n"), py::arg("contig_name") = "ctg",
+        py::arg("n_threads") = 1);
+  m.def("synth_packed", &synthPackedPy, py::arg("params"), py::arg("first"), py::arg("n"), py::arg("n_threads") = 1);
   m.def("read_as_dict", [](std::shared_ptr<ReadSet> rs, size_t i) {
     const Read& r = rs->reads.at(i);
     py::dict d;

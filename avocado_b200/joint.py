@@ -38,12 +38,13 @@ def _joint_in(n_sites, n_samples, n_states, n_alt, n_ref, n_other, gl, present=N
 
 
 def joint_counts(ctx, n_sites, n_samples, n_states, n_alt, n_ref, n_other, gl, present=None,
-                 n_nocall=None):
-    """avo_joint_counts: (alt alleles, called alleles) per site over these samples."""
+                 n_nocall=None, out=None):
+    """avo_joint_counts: (alt alleles, called alleles) per site over these samples.  `out`: one int32
+    buffer of 2 x n_sites entries that receives both (a sharded cohort all-reduces it as ONE message)."""
     dev = _is_dev(n_alt)
-    mk = (lambda: _device_empty(n_sites, np.int32, "cuda:%d" % ctx.device)) if dev else \
-         (lambda: np.zeros(max(n_sites, 1), np.int32))
-    alt, called = mk(), mk()
+    if out is None:
+        out = _device_empty(2 * n_sites, np.int32, "cuda:%d" % ctx.device) if dev else np.zeros(max(2 * n_sites, 2), np.int32)
+    alt, called = out[:n_sites], out[n_sites:2 * n_sites]
     s = _joint_in(n_sites, n_samples, n_states, n_alt, n_ref, n_other, gl, present, n_nocall)
     ctx._check(ctx.lib.avo_joint_counts(ctx.h, C.byref(s), _ptr(alt), _ptr(called)))
     return alt[:n_sites], called[:n_sites]
@@ -150,14 +151,14 @@ def joint_call_sharded(ctx, cols, group=None) -> Dict[str, object]:
     tensors (NCCL) or numpy arrays (gloo); every rank must hold the same sites in the same order."""
     import torch
     import torch.distributed as dist
-    alt, called = joint_counts(ctx, **cols)
-    dev = _is_dev(alt)
-    t_alt = alt if dev else torch.from_numpy(np.ascontiguousarray(alt))
-    t_called = called if dev else torch.from_numpy(np.ascontiguousarray(called))
+    n = cols["n_sites"]
+    dev = _is_dev(cols["n_alt"])
+    both = _device_empty(2 * n, np.int32, "cuda:%d" % ctx.device) if dev else np.zeros(max(2 * n, 2), np.int32)
+    joint_counts(ctx, out=both, **cols)
+    t_both = both if dev else torch.from_numpy(both)
     if dist.is_available() and dist.is_initialized():
-        dist.all_reduce(t_alt, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(t_called, op=dist.ReduceOp.SUM, group=group)
-    totals = (t_alt, t_called) if dev else (t_alt.numpy(), t_called.numpy())
+        dist.all_reduce(t_both, op=dist.ReduceOp.SUM, group=group)     # both count vectors, one message
+    totals = (t_both[:n], t_both[n:2 * n]) if dev else (both[:n], both[n:2 * n])
     out = joint_call(ctx, totals=totals, **cols)
     p0 = out["post0_sum"] if dev else torch.from_numpy(out["post0_sum"])
     if dist.is_available() and dist.is_initialized():

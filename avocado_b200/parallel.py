@@ -214,7 +214,7 @@ class ShardedPipeline:
         import ctypes as C
         from ._lib import AVO_E_CAPACITY, AVO_E_RETRY
         ctx, p, out = self.ctx, self.plan, self._out
-        need = self.L.ShardPlanStruct()
+        need = self._need = self.L.ShardPlanStruct()
         rc = ctx.lib.avo_shard_finish(ctx.h, C.byref(p), self.t_all.data_ptr(), self.r_all.data_ptr(), C.byref(out),
                                       C.byref(self.res), C.byref(need))
         self.nccl_bytes = (self.tb + self.rb) * p.world              # bytes every rank receives per step
@@ -238,8 +238,13 @@ class ShardedPipeline:
 
     def step(self, batch: ReadBatch, phred: int = 0, min_obs: Optional[int] = None, max_tries: int = 6):
         """One sharded discoverAndCall over this rank's reads (own interval + halo).  Returns, on every
-        rank, (global SiteTable, dict of result columns for all its rows) as device tensors."""
+        rank, (global SiteTable, dict of result columns for all its rows) as device tensors -- views of the
+        pipeline's buffers, valid until the next step."""
         from ._lib import AVO_E_CAPACITY, AvocadoError
+        if getattr(self, "_shrink_to", None):        # (the previous step's result views end here)
+            self.global_cap = None
+            self._size(*self._shrink_to)
+            self._shrink_to = None
         for _ in range(max_tries):
             with self.torch.cuda.stream(self.stream):
                 self.phase_discover(batch, phred, min_obs)
@@ -248,6 +253,11 @@ class ShardedPipeline:
                 self.gather(self.r_all, self.r_send)
                 got = self.phase_finish()
             if got is not None:
+                # blocks much larger than what the ranks own waste NVLink bytes: every rank sees the same
+                # `needed` (it follows from the gathered headers) and shrinks the same way before its next step
+                need, p = self._need, self.plan
+                if p.site_cap > need.site_cap + need.site_cap // 4 or p.allele_cap > 2 * need.allele_cap:
+                    self._shrink_to = (int(need.site_cap), int(need.allele_cap))
                 return got
         raise AvocadoError(AVO_E_CAPACITY, "sharded step kept asking for larger buffers")
 

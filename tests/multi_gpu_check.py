@@ -3,7 +3,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29511 tests/multi_gpu_check.py
 
-Checks, on real GPUs, that (1) region-sharded discoverAndCall (avocado_b200.parallel) returns on
+Checks, on real GPUs, that (1) region-sharded discoverAndCall (avocado_b200.parallel.ShardedPipeline:
+avo_shard_discover / _call / _finish around two NCCL all-gathers, everything device-resident) returns on
 every rank exactly the rows a single GPU computes for the whole batch, and (2) sample-sharded joint
 calling (avocado_b200.joint.joint_call_sharded: all-reduce of allele counts and of posterior sums
 over NCCL) reproduces the single-GPU cohort result, and (3) so does the sample-sharded depth roll-up
@@ -23,30 +24,35 @@ def main():
     from avocado_b200 import batch as B
     from avocado_b200.genotyping import Context
     from avocado_b200.joint import joint_call, joint_call_sharded
-    from avocado_b200.parallel import GpuEngine, RegionShard, discover_and_call_sharded, plan_region_shards
+    from avocado_b200.parallel import ShardedPipeline, plan_region_shards
     rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = Context(local)
     dev = torch.device("cuda", local)
 
-    # ---- (1) region-sharded discoverAndCall --------------------------------------------------
-    p = B.synth_params(seed=33, n_reads_total=200000, contig_len=1000000, first_pos=10000)
+    # ---- (1) region-sharded discoverAndCall: the device-resident pipeline over NCCL ---------------------
+    p = B.synth_params(seed=33, n_reads_total=400000, contig_len=2000000, first_pos=10000)
     whole = B.synth_host(p)
     shards = plan_region_shards(whole.meta["start"], whole.meta["end"], world, max_site_len=64)
     sh = shards[rank]
-    mine = whole.slice(sh.read_lo, sh.read_hi)
-    table, cols = discover_and_call_sharded(GpuEngine(ctx), mine, sh, phred=25, min_obs=5, collective_device=dev)
-    one = RegionShard(0, -(1 << 40), 1 << 40, 0, whole.n_reads, 64)
-    import torch.distributed as d2
+    mine = whole.slice(sh.read_lo, sh.read_hi).to_device(dev)
+    pipe = ShardedPipeline(ctx, rank, world, max(sh.lo, -(1 << 31) + 1), min(sh.hi, (1 << 31) - 1),
+                           site_cap=256, allele_cap=256)        # too small on purpose: every rank grows together
+    for _ in range(3):                                          # grow, shrink to fit, steady state
+        table, cols = pipe.step(mine, phred=25, min_obs=5)
+    table = table.to_host()
+    cols = {k: v.cpu().numpy() for k, v in cols.items()}
     # the single-GPU answer, computed locally without collectives
-    t1 = ctx.discover_packed(whole, phred=25, min_obs=5)
-    c1 = ctx.call_packed(whole, t1)
-    assert table.n == t1.n and table.n > 500, (table.n, t1.n)
-    for k in ("start", "ref_len", "alt_len", "count"):
+    c1x = Context(local)
+    t1, c1 = c1x.discover_and_call_packed(whole, phred=25, min_obs=5)
+    c1x.close()
+    assert table.n == t1.n and table.n > 1000, (table.n, t1.n)
+    for k in ("start", "ref_len", "alt_len", "count", "allele_off"):
         assert np.array_equal(np.asarray(getattr(table, k)), np.asarray(getattr(t1, k))), k
     for k, v in c1.items():
         assert np.array_equal(cols[k], np.asarray(v), equal_nan=True), "column %s differs on rank %d" % (k, rank)
+    nccl_bytes = pipe.nccl_bytes
 
     # ---- (2) sample-sharded joint calling ------------------------------------------------------
     rng = np.random.default_rng(11)
@@ -84,7 +90,8 @@ def main():
         assert np.array_equal(got[k].cpu().numpy(), np.asarray(v)), "depth column %s differs on rank %d" % (k, rank)
     dist.barrier()
     if rank == 0:
-        print("multi_gpu_check ok: world=%d, %d sites region-sharded, %d x %d joint" % (world, table.n, S, N))
+        print("multi_gpu_check ok: world=%d, %d sites region-sharded (%d NCCL bytes received per rank per step), %d x %d joint"
+              % (world, table.n, nccl_bytes, S, N))
     dist.destroy_process_group()
 
 

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     declared = set()
     for h in ("avocado_b200.h", "avocado_b200_synth.h"):
         src = open(os.path.join(root, "include", h)).read()
-        declared |= set(re.findall(r"^\s*(?:int|void|const char\*)\s+(avo_\w+)\s*\(", src, re.M))
+        declared |= set(re.findall(r"^\s*(?:int|int64_t|void|const char\*)\s+(avo_\w+)\s*\(", src, re.M))
     assert declared, "no declarations found"
     assert declared == set(L.EXPORTED_SYMBOLS)
     for sym in declared:
@@ -260,6 +260,7 @@ def test_ctypes_mirrors_have_the_sizes_of_the_c_structs(tmp_path):
         "avo_filter_out": L.FilterOutStruct, "avo_sample_rows": L.SampleRowsStruct, "avo_square_out": L.SquareOutStruct,
         "avo_trio": L.TrioStruct, "avo_joint_in": L.JointInStruct, "avo_joint_out": L.JointOutStruct,
         "avo_synth_params": L.SynthParamsStruct, "avo_depths_in": L.DepthsInStruct, "avo_site_depths": L.SiteDepthsStruct,
+        "avo_shard_plan": L.ShardPlanStruct,
     }
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "avocado_b200.h"\n#include "avocado_b200_synth.h"\nint main(void) {\n' +

@@ -106,7 +106,12 @@ class TimingStruct(C.Structure):
 class TextReadsStruct(C.Structure):
     _fields_ = [("n", C.c_int64), ("start", P), ("end", P), ("mapq", P), ("rec_flags", P),
                 ("cigar", P), ("cigar_off", P), ("md", P), ("md_off", P), ("seq", P), ("seq_off", P),
-                ("qual", P), ("qual_off", P), ("keep", P)]
+                ("qual", P), ("qual_off", P), ("keep", P), ("prefilter", P)]
+
+
+class PrefilterStruct(C.Structure):
+    _fields_ = [("min_mapq", C.c_int32), ("keep_duplicates", C.c_int32), ("keep_non_primary", C.c_int32),
+                ("contig_kept", C.c_int32)]
 
 
 class TextOutStruct(C.Structure):

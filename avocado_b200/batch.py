@@ -388,7 +388,8 @@ def text_columns(records: Sequence[AlignmentRecord]):
     mapq = np.array([-1 if r.mapq is None else r.mapq for r in records], np.int32).reshape(n)
     flags = np.array([(1 if r.readMapped else 0) | (2 if r.readNegativeStrand else 0) |
                       (4 if r.cigar is not None else 0) | (8 if r.mismatchingPositions is not None else 0) |
-                      (16 if r.mapq is not None else 0) for r in records], np.uint8).reshape(n)
+                      (16 if r.mapq is not None else 0) | (32 if getattr(r, "primaryAlignment", True) else 0) |
+                      (64 if getattr(r, "duplicateRead", False) else 0) for r in records], np.uint8).reshape(n)
     cigar, cigar_off = _blob([r.cigar for r in records])
     md, md_off = _blob([r.mismatchingPositions for r in records])
     seq, seq_off = _blob([r.sequence for r in records])
@@ -412,7 +413,7 @@ def pack_reads(records: Sequence[AlignmentRecord], contig_id=0, keep=None, sort=
     return b
 
 
-def pack_text_columns(cols, contig_id=0, threads=1, keep=None, out=None) -> ReadBatch:
+def pack_text_columns(cols, contig_id=0, threads=1, keep=None, out=None, prefilter=None) -> ReadBatch:
     """avo_pack_reads_mt over text columns (the dict ``text_columns`` / ``text_columns_of`` return):
     PrefilterReads' ``keep`` mask + extractAlignmentOperators + payload packing, on ``threads`` host
     threads.  The reads must already be those of one contig, sorted by start.  ``out`` optionally
@@ -436,6 +437,8 @@ def pack_text_columns(cols, contig_id=0, threads=1, keep=None, out=None) -> Read
         t.keep = keep.ctypes.data
     else:
         t.keep = None
+    if prefilter is not None:       # an L.PrefilterStruct: PrefilterReads' read predicates, evaluated by the packer
+        t.prefilter = C.cast(C.pointer(prefilter), C.c_void_p)
     nr, nb, no, nf = (C.c_int64() for _ in range(4))
     rc = lib.avo_pack_bounds(C.byref(t), C.byref(nr), C.byref(nb), C.byref(no), C.byref(nf))
     if rc != 0:

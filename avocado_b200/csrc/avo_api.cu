@@ -13,11 +13,28 @@
 
 #include <thread>
 
+#include <nvtx3/nvToolsExt.h>     // header-only: ranges cost nothing unless a profiler is attached
+
 #include "avo_internal.h"
 
 using namespace avo;
 
 namespace {
+
+// NVTX ranges named after the reference's own timers (avocado-core/.../avocado/Timers.scala:25-69), so that
+// an nsys trace of a JVM shim around this library reads like the reference's instrumentation report.
+struct Range {
+  explicit Range(const char* name) { nvtxRangePushA(name); }
+  ~Range() { nvtxRangePop(); }
+};
+#define T_DISCOVER_AND_CALL "Discover variants and call genotypes"          /* Timers.DiscoverAndCall */
+#define T_CALL_GENOTYPES "Call genotypes"                                    /* Timers.CallGenotypes */
+#define T_DISCOVERING "Discovering variants in reads"                        /* Timers.DiscoveringVariants */
+#define T_BUILDING_TREES "Building interval tree"                            /* Timers.BuildingTrees: the sorted site table + its index */
+#define T_TREE_JOIN "Running broadcast join with interval tree"              /* Timers.TreeJoin */
+#define T_OBSERVE_READS "Observing variants in reads"                        /* Timers.ObserveReads */
+#define T_EMIT_GENOTYPES "Emit observations as genotype calls"               /* Timers.EmitGenotypes */
+#define T_EXTRACT_ALIGNMENT "Parsing alignment (CIGAR/MD tag)"               /* Timers.ExtractingAlignment */
 
 constexpr int32_t LNK_N = 1 << 16;
 
@@ -589,6 +606,7 @@ int gather_payload(avo_ctx* ctx, const DReads& R, const DSites& S, const void* d
 int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const DevSites& T,
                   const avo_cnv* cnv, const avo_params* p, bool fresh, avo_site_results* out,
                   avo_ref_model_out* ref_out = nullptr, DResults* res_out = nullptr, size_t* slots_cap = nullptr) {
+  Range r_call(T_CALL_GENOTYPES);
   if (!fresh && T.n == 0)
     return fail(ctx, AVO_E_EMPTY_SITES,
                 "empty variant set: the reference throws here (TreeRegionJoin.scala:77)");
@@ -732,10 +750,13 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
       }
     }
     CKS(get_buf(ctx, SL_C_BUCKETS, n_slots * 4, &d_buckets));
+    nvtxRangePushA(T_TREE_JOIN);
     CK(launch_call_join(R, S, X, hs.max_span, (uint32_t*)d_buckets, n_slots, d_jlist, small + SW_JOIN, ctx->num_sms, ctx->stream, &nl));
     const uint8_t* d_compact = nullptr;
     const uint32_t *d_pbase = nullptr, *d_blk0 = nullptr;
+    nvtxRangePop();
     if (ctx->gather_src && work) CKS(gather_payload(ctx, R, S, d_jlist, small + SW_JOIN, &d_compact, &d_pbase, &d_blk0, &nl));
+    Range r_obs(T_OBSERVE_READS " / " T_EMIT_GENOTYPES);
     CK(launch_call_observe(R, S, C, P, D, (const int32_t*)d_rbase, (const uint32_t*)d_blen, (const uint64_t*)d_boff,
                            (uint32_t*)d_buckets, n_slots, d_jlist, small + SW_JOIN, d_compact, d_pbase, d_blk0, ctx->num_sms,
                            ctx->stream, &nl));
@@ -919,6 +940,7 @@ int discover_enqueue(avo_ctx* ctx, const DReads& R, const BatchStats& hs, bool v
   D.sidx = (int32_t*)d_sidx;
   D.hdr = (DSiteHdr*)(small + SW_HDR);
 
+  Range r_disc(T_DISCOVERING);
   CK(launch_build_index(R, none, hs, (int32_t*)d_ridx, nullptr, nullptr, ctx->stream));
   ctx->timing.n_launches += 1;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -929,7 +951,10 @@ int discover_enqueue(avo_ctx* ctx, const DReads& R, const BatchStats& hs, bool v
   ctx->timing.n_tile_launches += nl;
   CK(launch_indel_group(R, Lst, d_table, d_tcount, tsize, p->min_obs_discover, U, small + SW_FLAGS, ctx->num_sms,
                         ctx->stream, &nl));
-  CK(launch_assemble_sites(R, Lst, U, hs, nb, D, ctx->stream, &nl));
+  {
+    Range r_tree(T_BUILDING_TREES);
+    CK(launch_assemble_sites(R, Lst, U, hs, nb, D, ctx->stream, &nl));
+  }
   ctx->timing.n_launches += nl;
 
   T->n = 0; T->n_nibbles = 0; T->contig = nullptr;
@@ -1221,6 +1246,7 @@ int avo_call_all_sites(avo_ctx* ctx, const avo_read_batch* reads, const avo_site
 int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_cnv* cnv,
                           const avo_params* params, avo_sites_out* sites_out,
                           avo_site_results* results) {
+  Range r_all(T_DISCOVER_AND_CALL);
   CKS(begin_call(ctx));
   CKS(validate_reads(ctx, reads));
   CKS(check_params(ctx, params));
@@ -1503,6 +1529,7 @@ int avo_shard_finish(avo_ctx* ctx, const avo_shard_plan* pl, const void* gathere
 
 // ---- PrefilterReads' mask + extractAlignmentOperators + payload packing, on the device -----------------
 int avo_pack_reads_device(avo_ctx* ctx, const avo_text_reads* in, int32_t in_mem, avo_packed_out* out) {
+  Range r_pack(T_EXTRACT_ALIGNMENT);
   CKS(begin_call(ctx));
   if (!in || !out || in->n < 0 || in->n >= (int64_t)INT32_MAX) return fail(ctx, AVO_E_INVALID, "bad text batch");
   if (in_mem != AVO_MEM_HOST && in_mem != AVO_MEM_DEVICE) return fail(ctx, AVO_E_INVALID, "bad in_mem");
@@ -1544,6 +1571,8 @@ int avo_pack_reads_device(avo_ctx* ctx, const avo_text_reads* in, int32_t in_mem
   if (in->qual_off == in->seq_off) T.qual_off = T.seq_off;
   else CKS(stage_in(ctx, SL_T_QUAL_OFF, in->qual_off, n + 1, in_mem, &T.qual_off));
   T.keep = nullptr;
+  T.prefilter = in->prefilter ? 1 : 0;
+  if (in->prefilter) T.pf = *in->prefilter; else memset(&T.pf, 0, sizeof T.pf);
   if (in->keep) CKS(stage_in(ctx, SL_T_KEEP, in->keep, n, in_mem, &T.keep));
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   void *d_counts, *d_offsets, *d_temp;
@@ -1606,23 +1635,31 @@ int avo_square_off(avo_ctx* ctx, const avo_sites* cohort, const avo_sample_rows*
     ctx->timing.h2d_bytes += (int64_t)bytes;
     return d;
   };
-  int32_t max_ref_len = 1;
+  // the look-back bounds: the longest variant and the longest reference-model block.  Host tables are
+  // scanned here; device tables by one small reduction each (discovery no longer caps allele lengths)
+  int32_t max_ref_len = 1, max_block_len = 1;
   if (mem == AVO_MEM_HOST) {
     for (size_t k = 0; k < nv; ++k) max_ref_len = std::max(max_ref_len, V->ref_len[k]);
-  } else {
-    max_ref_len = 1 << 16;    // device tables: bound of the allele length (uint16 in discovery keys)
-  }
-  int32_t max_block_len = 1;
-  if (sample->ref_model_len) {
-    max_block_len = sample->ref_model_max_len;
-    if (mem == AVO_MEM_HOST) {
+    if (sample->ref_model_len) {
+      max_block_len = sample->ref_model_max_len;
       for (size_t k = 0; k < nr; ++k) {
         if (sample->ref_model_len[k] < 1) return fail(ctx, AVO_E_INVALID, "ref_model_len[%zu] < 1", k);
         max_block_len = std::max(max_block_len, sample->ref_model_len[k]);
       }
-    } else if (max_block_len <= 0) {
-      max_block_len = 1 << 16;
     }
+  } else {
+    void* d_small;
+    CKS(get_buf(ctx, SL_SMALL, SW_COUNT_ * 4, &d_small));
+    int32_t* mx = (int32_t*)d_small + SW_TILE;
+    const int32_t one[2] = {1, 1};
+    CK(cudaMemcpyAsync(mx, one, sizeof one, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_max_i32(V->ref_len, (int64_t)nv, mx, ctx->stream));
+    const bool scan_blocks = sample->ref_model_len && sample->ref_model_max_len <= 0;
+    if (scan_blocks) CK(launch_max_i32(sample->ref_model_len, (int64_t)nr, mx + 1, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_small, mx, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    max_ref_len = std::max(1, ctx->h_small[0]);
+    if (sample->ref_model_len) max_block_len = scan_blocks ? std::max(1, ctx->h_small[1]) : sample->ref_model_max_len;
   }
   DSquareIn I{};
   I.n_sites = (int32_t)N; I.n_v = (int32_t)nv; I.n_r = (int32_t)nr; I.ns = ns; I.v_max_ref_len = max_ref_len;

@@ -248,9 +248,12 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
     // one match, or one mismatch run after the leading match, and are handled on the spot; the
     // others are queued and walked afterwards so that no lane idles while a neighbour works
     // through a long operator list.
+    // wlo fits 32 bits (win0 <= wlo < max_end) and a candidate lies within max_span + DISC_W of it, so
+    // one unsigned compare is the window test (a position below wlo wraps far past DISC_W)
+    const int32_t wlo32 = (int32_t)wlo;
     auto snp = [&](int32_t pos, uint32_t pair) {
-      const int64_t o = (int64_t)pos - wlo;
-      if (o < 0 || o >= DISC_W) return;
+      const uint32_t o = (uint32_t)pos - (uint32_t)wlo32;
+      if (o >= (uint32_t)DISC_W) return;
       const uint32_t refn = (pair >> 4) & 15u, altn = pair & 15u;
       // A C G T are the nibbles 1 2 4 8 (bits of 0x116); anything else takes the exact path
       if (!(((0x116u >> refn) & (0x116u >> altn)) & 1u)) { sm.exotic = 1; return; }
@@ -261,14 +264,17 @@ k_discover_tiles(DReads R, DIndex X, int32_t thr, int32_t min_count /* keep coun
     for (int32_t r = rLo + tid; r < rHi; r += DISC_THREADS) {
       const MetaA a = load_meta_a(R.meta, r);
       const MetaB m = load_meta_b(R.meta, r);
+      // the previous read's start: the neighbouring lane has it (the lanes still in the loop are 0..k)
+      int32_t prev_start = __shfl_up_sync(__activemask(), a.start, 1);
+      if (lane == 0) prev_start = r > 0 ? meta_start(R.meta, r - 1) : a.start;
       if (r >= rOwn) {
         if (R.coords) R.coords[r] = make_int2(a.start, a.end);   // dense (start, end) copy for the join
         if (verify) {     // sort order and the caller's bounds (avo_batch_stats)
-          if (r > 0 && meta_start(R.meta, r - 1) > a.start) atomicOr(flags, DISC_FLAG_UNSORTED);
-          if (a.end > max_end || (int64_t)a.end - a.start > max_span) atomicOr(flags, DISC_FLAG_BAD_STATS);
+          if (prev_start > a.start) atomicOr(flags, DISC_FLAG_UNSORTED);
+          if (a.end > max_end || a.end - a.start > max_span || a.end < a.start) atomicOr(flags, DISC_FLAG_BAD_STATS);
         }
       }
-      if ((int64_t)a.end <= wlo || m.n_ops == 0) continue;   // ends before the window / no operators
+      if (a.end <= wlo32 || m.n_ops == 0) continue;   // ends before the window / no operators
       const uint32_t w0 = __ldg(R.ops + a.op_off);
       const uint32_t w1 = (m.n_ops > 1) ? __ldg(R.ops + a.op_off + 1) : 0u;
       // the common shapes "=", "= X", "= X =" and "= X S"

@@ -193,6 +193,8 @@ struct DText {                   // avo_text_reads with device pointers
   const char* seq;   const int64_t* seq_off;
   const char* qual;  const int64_t* qual_off;
   const uint8_t* keep;           // may be NULL
+  int32_t prefilter;             // != 0: pf holds PrefilterReads' read predicates
+  avo_prefilter pf;
 };
 struct PackOffsets { uint64_t k, b, o, f; };   // packed record, payload block, operator, mismatch byte
 struct DPacked {
@@ -216,6 +218,7 @@ struct ColumnCopies {
   size_t bytes[32];
 };
 cudaError_t launch_copy_columns(const ColumnCopies& cc, cudaStream_t s);
+cudaError_t launch_max_i32(const int32_t* a, int64_t n, int32_t* d_out, cudaStream_t s);
 
 // ---- region-sharded discoverAndCall (avo_shard.cu) ---------------------------------------------------
 constexpr int AVO_MAX_SHARDS = 64;

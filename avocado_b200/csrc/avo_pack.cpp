@@ -212,8 +212,15 @@ bool extract_ops(const char* cig, size_t ncig, bool has_cigar, const char* md, s
 }
 
 bool kept(const avo_text_reads* in, int64_t i) {
-  if (!(in->rec_flags[i] & 1)) return false;             // unmapped reads never reach the path
+  const uint8_t rf = in->rec_flags[i];
+  if (!(rf & 1)) return false;                           // unmapped reads never reach the path
   if (in->start[i] < 0) return false;
+  if (const avo_prefilter* f = in->prefilter) {          // PrefilterReads.scala:142-209
+    if (!f->contig_kept) return false;
+    if (!(rf & 32) && !f->keep_non_primary) return false;                 // filterMapped
+    if ((rf & 16) && in->mapq[i] >= 0 && !(in->mapq[i] > f->min_mapq)) return false;   // filterMappingQuality
+    if ((rf & 64) && !f->keep_duplicates) return false;                   // filterUnique
+  }
   return in->keep ? in->keep[i] != 0 : true;
 }
 

@@ -204,8 +204,15 @@ __device__ Extracted extract_ops(const char* cig, int ncig, bool has_cigar, cons
 }
 
 __device__ __forceinline__ bool kept(const DText& T, int64_t i) {
-  if (!(T.rec_flags[i] & 1)) return false;
+  const uint8_t rf = T.rec_flags[i];
+  if (!(rf & 1)) return false;
   if (T.start[i] < 0) return false;
+  if (T.prefilter) {                                     // PrefilterReads.scala:142-209, as in avo_pack.cpp
+    if (!T.pf.contig_kept) return false;
+    if (!(rf & 32) && !T.pf.keep_non_primary) return false;
+    if ((rf & 16) && T.mapq[i] >= 0 && !(T.mapq[i] > T.pf.min_mapq)) return false;
+    if ((rf & 64) && !T.pf.keep_duplicates) return false;
+  }
   return T.keep ? T.keep[i] != 0 : true;
 }
 

@@ -311,6 +311,19 @@ cudaError_t launch_wire6_expand(const avo_read_wire6* wire, const uint8_t* oplen
   return cudaGetLastError();
 }
 
+// ---- max of an int32 column (device tables whose longest entry the host does not know) -------------------
+__global__ void k_max_i32(const int32_t* __restrict__ a, int64_t n, int32_t* __restrict__ out) {
+  int32_t m = INT32_MIN;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = max(m, a[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+  if ((threadIdx.x & 31) == 0 && m != INT32_MIN) atomicMax(out, m);
+}
+cudaError_t launch_max_i32(const int32_t* a, int64_t n, int32_t* d_out /* preset by the caller */, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_max_i32<<<(unsigned)std::min<int64_t>(1024, (n + 255) / 256), 256, 0, s>>>(a, n, d_out);
+  return cudaGetLastError();
+}
+
 // ---- device -> device export of result columns: one launch instead of one copy per column ------
 __global__ void k_copy_columns(ColumnCopies cc) {
   for (int c = blockIdx.y; c < cc.n; c += gridDim.y) {

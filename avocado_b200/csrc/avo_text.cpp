@@ -76,7 +76,7 @@ extern "C" int avo_synth_text(const avo_read_batch* b, int64_t first, int64_t n,
           ns + (int64_t)m.l_seq > out->seq_bytes)
         return AVO_E_CAPACITY;
       out->start[j] = m.start; out->end[j] = m.end; out->mapq[j] = m.mapq;
-      out->rec_flags[j] = (uint8_t)(1 | ((m.flags & AVO_READ_NEGATIVE_STRAND) ? 2 : 0) | (m.n_ops ? 4 | 8 : 0) | 16);
+      out->rec_flags[j] = (uint8_t)(1 | ((m.flags & AVO_READ_NEGATIVE_STRAND) ? 2 : 0) | (m.n_ops ? 4 | 8 : 0) | 16 | 32 /* primary */);
       out->cigar_off[j] = nc; out->md_off[j] = nm; out->seq_off[j] = ns;
       memcpy(out->cigar + nc, cigar.data(), cigar.size());
       memcpy(out->md + nm, md.data(), md.size());

@@ -111,10 +111,12 @@ class Context:
         return {k: getattr(t, k) for k, _ in L.TimingStruct._fields_}
 
     # ---- the packer on the device ---------------------------------------------------------------
-    def pack_text_device(self, cols, contig_id=0, keep=None, out=None, source_index=False) -> ReadBatch:
+    def pack_text_device(self, cols, contig_id=0, keep=None, out=None, source_index=False, prefilter=None) -> ReadBatch:
         """avo_pack_reads_device: text columns (``batch.text_columns`` layout; numpy arrays, ideally
         page-locked, or torch device tensors) -> a packed ReadBatch in device memory.  ``out``
-        optionally supplies reusable device buffers {meta, payload, ops, refb} of sufficient size."""
+        optionally supplies reusable device buffers {meta, payload, ops, refb} of sufficient size.
+        ``prefilter``: an ``L.PrefilterStruct`` (``prefilter.prefilter_struct``): PrefilterReads' read
+        predicates, evaluated by the packer kernels."""
         import torch
         on_dev = not isinstance(cols["start"], np.ndarray)
         n = int(cols["start"].shape[0])
@@ -144,6 +146,9 @@ class Context:
             t.keep = _ptr(keep)
         else:
             t.keep = None
+        if prefilter is not None:
+            hold.append(prefilter)
+            t.prefilter = C.cast(C.pointer(prefilter), C.c_void_p)
         # upper bounds from the blob sizes (what avo_pack_bounds sums read by read)
         cb, mb, sb = last("cigar_off"), last("md_off"), last("seq_off")
         cap = dict(meta=n, payload=sb // 10 + n, ops=cb // 2 + n + 2 * mb, refb=mb + n)

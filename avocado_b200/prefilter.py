@@ -1,6 +1,8 @@
 """PrefilterReads (CORE/util/PrefilterReads.scala:52-259): the read / contig predicates the CLI
-applies before genotyping (CLI/BiallelicGenotyper.scala:218-230).  Host logic, applied while the
-packer builds the columnar batch (`pack_reads(records, keep=prefilter_mask(...))`); SURVEY.md 8f N1.
+applies before genotyping (CLI/BiallelicGenotyper.scala:218-230); SURVEY.md 8f N1.  The read predicates
+run inside the packers (`prefilter_struct` -> avo_text_reads.prefilter: three flag bits and the mapq
+byte of columns the packer kernels load anyway); this module holds the contig-name predicates, the
+argument record, and the per-record Python form that the tests check the packers against.
 """
 from __future__ import annotations
 
@@ -75,8 +77,19 @@ def readFilterFn(args: PrefilterReadsArgs, contig_fn) -> Callable[[AlignmentReco
     return lambda r: filterUnique(r) and base(r)
 
 
+def prefilter_struct(args: PrefilterReadsArgs, contig_name: Optional[str]):
+    """The avo_prefilter the packers evaluate per read (host: avo_pack_reads*, device: k_pack_count /
+    k_pack_records).  The contig predicates are name tests, decided here once for the batch's contig."""
+    from . import _lib as L
+    f = L.PrefilterStruct()
+    f.min_mapq, f.keep_duplicates, f.keep_non_primary = args.minMappingQuality, int(args.keepDuplicates), int(args.keepNonPrimary)
+    f.contig_kept = int(contigFilterFn(args)(contig_name))
+    return f
+
+
 def prefilter_mask(reads: Sequence[AlignmentRecord], args: PrefilterReadsArgs) -> List[bool]:
-    """keep[i] for `pack_reads(records, keep=...)`."""
+    """keep[i] -- the same predicates read by read in Python: the checker of the packers' own evaluation
+    (tests), and a way to hand `pack_reads(records, keep=...)` an arbitrary selection."""
     fn = readFilterFn(args, contigFilterFn(args))
     return [bool(fn(r)) for r in reads]
 

@@ -560,10 +560,24 @@ typedef struct {
 int avo_joint_depths(avo_ctx* ctx, const avo_depths_in* in, avo_site_depths* out);
 
 /* ---- host-side packer (PrefilterReads + ObservationOperator.extractAlignmentOperators) ------ */
-/* Text columns of AlignmentRecords (blobs + [n+1] offsets; has_* bits in rec_flags:
- * bit0 readMapped, bit1 readNegativeStrand, bit2 cigar present, bit3 MD present, bit4 mapq present).
- * Packs the reads for which keep[i] != 0 (NULL = all mapped reads), in input order.  Output
- * arrays must be sized for the upper bounds returned by avo_pack_bounds. */
+/* PrefilterReads' read predicates (CORE/util/PrefilterReads.scala:142-209), evaluated by the packers --
+ * host (avo_pack_reads*) and device (avo_pack_reads_device, inside k_pack_count / k_pack_records) -- from
+ * the columns they load anyway: mapped AND (primary OR keep_non_primary) AND (mapq absent OR mapq >
+ * min_mapq) AND (NOT duplicate OR keep_duplicates) AND contig_kept.  The contig predicates (:118-134,
+ * 216-274) are tests of the contig NAME: the host evaluates them once per batch (one batch = one contig)
+ * and passes the answer. */
+typedef struct {
+  int32_t min_mapq;          /* PrefilterReadsArgs.minMappingQuality (CLI default 10; strict >) */
+  int32_t keep_duplicates;   /* keepDuplicates */
+  int32_t keep_non_primary;  /* keepNonPrimary */
+  int32_t contig_kept;       /* contigFilterFn(name of the batch's contig) */
+} avo_prefilter;
+
+/* Text columns of AlignmentRecords (blobs + [n+1] offsets; bits of rec_flags: bit0 readMapped, bit1
+ * readNegativeStrand, bit2 cigar present, bit3 MD present, bit4 mapq present, bit5 primaryAlignment,
+ * bit6 duplicateRead).  Packs, in input order, the mapped reads that pass `prefilter` (NULL = no
+ * predicate) and for which keep[i] != 0 (NULL = all).  Output arrays must be sized for the upper bounds
+ * returned by avo_pack_bounds. */
 typedef struct {
   int64_t n;
   const int64_t* start;
@@ -575,6 +589,7 @@ typedef struct {
   const char* seq;   const int64_t* seq_off;
   const char* qual;  const int64_t* qual_off;
   const uint8_t* keep;
+  const avo_prefilter* prefilter;   /* host pointer (also for avo_pack_reads_device); may be NULL */
 } avo_text_reads;
 
 typedef struct {

@@ -1700,7 +1700,7 @@ static void synthPacked(const avo_synth_params& p, int64_t first, int64_t n, int
 }
 
 static std::shared_ptr<ReadSet> synthReads(const py::dict& params, int64_t first, int64_t n, const std::string& contigName,
-                                           int nThreads) {
+                                           int nThreads, int minMapq) {
   const avo_synth_params p = synthParams(params);
   auto rs = std::make_shared<ReadSet>();
   {
@@ -1718,6 +1718,15 @@ static std::shared_ptr<ReadSet> synthReads(const py::dict& params, int64_t first
     for (int t = 1; t < T; ++t) pool.emplace_back(fn, t);
     fn(0);
     for (auto& th : pool) th.join();
+    // PrefilterReads.filterMappingQuality (CORE/util/PrefilterReads.scala:201-209): keep mapq > minMapq (the
+    // generator's reads are all mapped, primary and not duplicates)
+    if (minMapq >= 0) {
+      std::vector<Read> kept;
+      kept.reserve(rs->reads.size());
+      for (auto& r : rs->reads)
+        if (!r.hasMapq || r.mapq > minMapq) kept.push_back(std::move(r));
+      rs->reads.swap(kept);
+    }
   }
   return rs;
 }
@@ -1817,7 +1826,7 @@ PYBIND11_MODULE(avocado_oracle, m) {
   m.def("reads_from_dicts", &readsFromDicts);
   m.def("reads_from_packed", &readsFromPacked);
   m.def("synth_reads", &synthReads, py::arg("params"), py::arg("first"), py::arg("n"), py::arg("contig_name") = "ctg",
-        py::arg("n_threads") = 1);
+        py::arg("n_threads") = 1, py::arg("min_mapq") = -1);
   m.def("synth_packed", &synthPackedPy, py::arg("params"), py::arg("first"), py::arg("n"), py::arg("n_threads") = 1);
   m.def("read_as_dict", [](std::shared_ptr<ReadSet> rs, size_t i) {
     const Read& r = rs->reads.at(i);

@@ -104,3 +104,34 @@ def test_device_packed_batch_genotypes_like_the_oracle(oracle, ctx):
     assert len(keys) == len(want_v)
     st = compare_call(keys, cols, want)
     assert st["sites"] > 10
+
+
+def test_device_packer_evaluates_the_read_predicates(ctx):
+    """PrefilterReads' read predicates inside k_pack_count / k_pack_records: the device
+    packer given avo_prefilter keeps exactly the reads the per-record predicates keep
+    (PrefilterReads.scala:142-209) and packs them byte for byte like the host packer."""
+    import itertools
+    import random
+    from avocado_b200 import batch as B
+    from avocado_b200.prefilter import PrefilterReadsArgs, prefilter_mask, prefilter_struct
+    from avocado_b200.records import AlignmentRecord
+    rng = random.Random(4)
+    recs = []
+    for i in range(3000):
+        recs.append(AlignmentRecord(readMapped=rng.random() > 0.1, contigName="chr20", start=100 + i, end=110 + i, cigar="4M1X5M",
+                                    mismatchingPositions="4A5", sequence="ACGTCCGTAC", qual="IIIIIIIIII",
+                                    mapq=None if rng.random() < 0.1 else rng.choice([0, 5, 10, 11, 30, 60]),
+                                    readNegativeStrand=rng.random() < 0.5, readName="r%d" % i,
+                                    primaryAlignment=rng.random() > 0.2, duplicateRead=rng.random() < 0.2))
+    cols = B.text_columns(recs)
+    dcols = {k: (np.frombuffer(v + b"\0", np.uint8).copy() if isinstance(v, (bytes, bytearray)) else v) for k, v in cols.items()}
+    for dup, nonprim, minq, contig in itertools.product([False, True], [False, True], [0, 10], ["chr20", "GL000"]):
+        args = PrefilterReadsArgs(keepDuplicates=dup, keepNonPrimary=nonprim, minMappingQuality=minq)
+        f = prefilter_struct(args, contig)
+        want = [i for i, k in enumerate(prefilter_mask(recs, args)) if k and f.contig_kept]
+        host = B.pack_text_columns(cols, threads=2, prefilter=f)
+        dev = ctx.pack_text_device(dcols, prefilter=f, source_index=True)
+        assert dev.source_index.cpu().numpy().tolist() == want == host.source_index.tolist()
+        dh = dev.to_host()
+        assert np.array_equal(np.asarray(dh.meta).view(np.uint8)[:host.n_reads * 32], host.meta.view(np.uint8))
+        assert np.array_equal(np.asarray(dh.ops)[:host.n_ops], host.ops[:host.n_ops])

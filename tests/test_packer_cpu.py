@@ -273,3 +273,12 @@ def test_ctypes_mirrors_have_the_sizes_of_the_c_structs(tmp_path):
     for name, mirror in pairs.items():
         assert int(got[name]) == C.sizeof(mirror), name
     assert (int(got["avo_read_meta"]), int(got["avo_read_wire"]), int(got["avo_read_wire6"])) == (32, 16, 6)
+
+
+def test_jni_glue_compiles_against_the_headers():
+    """examples/jni/avocado_b200_jni.c (the binding INTEGRATION.md describes) against include/*.h and a
+    stand-in for the JDK's jni.h with the JDK's names and call shapes: the sketch cannot rot."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "tests", "mock_jni"),
+                           "-I", os.path.join(root, "include"), os.path.join(root, "examples", "jni", "avocado_b200_jni.c")])

@@ -58,3 +58,28 @@ def test_read_filter_generator_and_apply():                           # :160-236
         assert {i for i, k in enumerate(PF.prefilter_mask(READS, a)) if k} == want
         kept, contigs = PF.PrefilterReads(READS, CONTIGS, a)
         assert len(kept) == len(want) and len(contigs) == n_contigs
+
+
+def test_packer_evaluates_the_read_predicates():
+    """The host packer (avo_pack_reads_mt) given avo_prefilter keeps exactly the reads the per-record
+    predicates (PrefilterReads.scala:142-209) keep, for every argument combination."""
+    import itertools
+    import random
+    from avocado_b200 import batch as B
+    from avocado_b200.prefilter import PrefilterReadsArgs, prefilter_mask, prefilter_struct
+    from avocado_b200.records import AlignmentRecord
+    rng = random.Random(4)
+    recs = []
+    for i in range(600):
+        recs.append(AlignmentRecord(readMapped=rng.random() > 0.1, contigName="chr20", start=100 + i, end=110 + i, cigar="10M",
+                                    mismatchingPositions="10", sequence="ACGTACGTAC", qual="IIIIIIIIII",
+                                    mapq=None if rng.random() < 0.1 else rng.choice([0, 5, 10, 11, 30, 60]),
+                                    readNegativeStrand=rng.random() < 0.5, readName="r%d" % i,
+                                    primaryAlignment=rng.random() > 0.2, duplicateRead=rng.random() < 0.2))
+    cols = B.text_columns(recs)
+    for dup, nonprim, minq, contig in itertools.product([False, True], [False, True], [0, 10, 30], ["chr20", "chrM", "GL000"]):
+        args = PrefilterReadsArgs(keepDuplicates=dup, keepNonPrimary=nonprim, minMappingQuality=minq)
+        want = [i for i, k in enumerate(prefilter_mask([r if contig == "chr20" else __import__("dataclasses").replace(r, contigName=contig)
+                                                         for r in recs], args)) if k]
+        b = B.pack_text_columns(cols, threads=2, prefilter=prefilter_struct(args, contig))
+        assert b.source_index.tolist() == want, (dup, nonprim, minq, contig)

@@ -226,7 +226,7 @@ EXPORTED_SYMBOLS = [
     "avo_call_all_sites", "avo_filter_genotypes", "avo_square_off", "avo_trio_call", "avo_joint_counts", "avo_joint", "avo_joint_depths",
     "avo_pack_wire", "avo_pack_wire6", "avo_pack_bounds", "avo_pack_reads", "avo_pack_reads_mt", "avo_pack_reads_device", "avo_synth_default_params",
     "avo_synth_host", "avo_synth_device", "avo_synth_text",
-    "avo_shard_table_block_bytes", "avo_shard_rows_block_bytes", "avo_shard_discover", "avo_shard_call", "avo_shard_finish",
+    "avo_merge_meta", "avo_shard_table_block_bytes", "avo_shard_rows_block_bytes", "avo_shard_discover", "avo_shard_call", "avo_shard_finish",
 ]
 
 _lib = None
@@ -284,6 +284,7 @@ def load():
     lib.avo_synth_device.argtypes = [C.POINTER(SynthParamsStruct), C.c_int64, C.c_int64, P, P,
                                      C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                      C.POINTER(PackedOutStruct), P]
+    lib.avo_merge_meta.argtypes = [P, C.c_int32, P, P, P, P, P, P]
     lib.avo_shard_table_block_bytes.argtypes = [C.POINTER(ShardPlanStruct)]
     lib.avo_shard_table_block_bytes.restype = C.c_int64
     lib.avo_shard_rows_block_bytes.argtypes = [C.POINTER(ShardPlanStruct)]

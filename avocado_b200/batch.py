@@ -212,11 +212,23 @@ class ReadBatch:
         return out.with_stats() if self.stats is not None else out
 
 
-def merge_batches(batches: Sequence[ReadBatch]) -> ReadBatch:
+_MERGE_CTX = {}
+
+
+def _merge_ctx(device):
+    from .genotyping import Context
+    if device not in _MERGE_CTX:
+        _MERGE_CTX[device] = Context(device)
+    return _MERGE_CTX[device]
+
+
+def merge_batches(batches: Sequence[ReadBatch], ctx=None, stats=None) -> ReadBatch:
     """The union of several batches of ONE contig as a batch of its own, stably sorted by start
     (`reads.union(...)` of CLI/TrioGenotyper.scala:216: discovery over a trio counts the candidates
     of all three samples together).  Payload, operator and mismatch columns are concatenated, the
-    records are merged and their three offsets rebased.  Host (numpy) or device (torch) batches."""
+    records are merged and their three offsets rebased.  Host batches: numpy.  Device batches: one kernel
+    (avo_merge_meta, on `ctx`'s stream) merges the records; `stats` = (min_start, max_end, max_span) of the
+    union if the caller knows them (saves a reduction and its synchronisation)."""
     assert len(batches) > 0 and len({b.on_device for b in batches}) == 1
     assert len({b.contig_id for b in batches}) == 1
     dev = batches[0].on_device
@@ -227,17 +239,33 @@ def merge_batches(batches: Sequence[ReadBatch]) -> ReadBatch:
     rfb = np.cumsum([0] + [b.n_refb for b in batches])
     if dev:
         import torch
-        recs = []
-        for k, b in enumerate(batches):
-            m = b.meta[:b.n_reads * 32].view(torch.int32).view(-1, 8).clone()
-            m[:, 2] += int(blk[k]); m[:, 3] += int(ops[k]); m[:, 4] += int(rfb[k])    # wraps like uint32
-            recs.append(m)
-        m = torch.cat(recs)
-        order = torch.sort(m[:, 0], stable=True).indices
-        out.meta = m[order].contiguous().view(torch.uint8).view(-1)
-        out.payload = torch.cat([b.payload[:b.n_blocks * BLOCK_BYTES] for b in batches] + [batches[0].payload[:0].new_zeros(16)])
-        out.ops = torch.cat([b.ops[:b.n_ops] for b in batches] + [batches[0].ops[:0].new_zeros(4)])
-        out.refb = torch.cat([b.refb[:b.n_refb] for b in batches] + [batches[0].refb[:0].new_zeros(16)])
+        # columns that already lie back to back in one allocation (a shim that uploads the samples into one
+        # buffer; bench.py's trio mode) are used in place, otherwise concatenated
+        def joined(name, unit, pad):
+            parts = [getattr(b, name) for b in batches]
+            sizes = [b.n_blocks * BLOCK_BYTES if name == "payload" else (b.n_ops if name == "ops" else b.n_refb) for b in batches]
+            adj = all(parts[k].data_ptr() + sizes[k] * parts[k].element_size() == parts[k + 1].data_ptr()
+                      for k in range(len(parts) - 1))
+            if adj and getattr(batches[0], "_arena", None) is not None:
+                return batches[0]._arena[name]
+            return torch.cat([p[:n] for p, n in zip(parts, sizes)] + [parts[0][:0].new_zeros(pad)])
+        out.payload, out.ops, out.refb = joined("payload", 1, 16), joined("ops", 4, 4), joined("refb", 1, 16)
+        own_ctx = ctx is None
+        ctx = ctx or _merge_ctx(batches[0].meta.device.index or 0)
+        merged = torch.empty(max(out.n_reads, 1) * 32, dtype=torch.uint8, device=batches[0].meta.device)
+        K = len(batches)
+        ptrs = (C.c_void_p * K)(*[b.meta.data_ptr() for b in batches])
+        cnt = (C.c_int64 * K)(*[b.n_reads for b in batches])
+        u32 = lambda a: (C.c_uint32 * K)(*[int(x) & 0xFFFFFFFF for x in a[:K]])
+        ctx._check(ctx.lib.avo_merge_meta(ctx.h, K, ptrs, cnt, u32(blk), u32(ops), u32(rfb), merged.data_ptr()))
+        out.meta = merged
+        if own_ctx:                       # the helper context has a stream of its own: wait for the merge here
+            torch.cuda.synchronize(batches[0].meta.device)
+        if stats is None and all(b.stats is not None for b in batches):
+            stats = (min(b.stats[0] for b in batches), max(b.stats[1] for b in batches), max(b.stats[2] for b in batches))
+        if stats is not None:
+            out.stats = stats
+            return out
     else:
         recs = []
         for k, b in enumerate(batches):

@@ -1343,6 +1343,27 @@ int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_c
   return AVO_OK;
 }
 
+int avo_merge_meta(avo_ctx* ctx, int32_t n_parts, const avo_read_meta* const* part_meta, const int64_t* part_reads,
+                   const uint32_t* block_base, const uint32_t* op_base, const uint32_t* refb_base, avo_read_meta* out_meta) {
+  if (!ctx) return AVO_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (n_parts < 1 || n_parts > AVO_MAX_MERGE || !part_meta || !part_reads || !block_base || !op_base || !refb_base || !out_meta)
+    return fail(ctx, AVO_E_INVALID, "avo_merge_meta: 1..%d parts, no NULL arguments", AVO_MAX_MERGE);
+  MergeParts M{};
+  M.k = n_parts;
+  int64_t total = 0;
+  for (int k = 0; k < n_parts; ++k) {
+    if (part_reads[k] < 0 || (part_reads[k] > 0 && !part_meta[k])) return fail(ctx, AVO_E_INVALID, "avo_merge_meta: bad part %d", k);
+    M.meta[k] = part_meta[k]; M.n[k] = part_reads[k];
+    M.block_base[k] = block_base[k]; M.op_base[k] = op_base[k]; M.refb_base[k] = refb_base[k];
+    total += part_reads[k];
+  }
+  if (total >= (int64_t)INT32_MAX) return fail(ctx, AVO_E_INVALID, "the union must stay below 2^31 reads");
+  CK(launch_merge_meta(M, out_meta, ctx->stream));
+  ctx->timing.n_launches += 1;
+  return AVO_OK;
+}
+
 // ---- region-sharded discoverAndCall: three phases around the framework's two all-gathers ------------
 static int check_plan(avo_ctx* ctx, const avo_shard_plan* pl) {
   if (!pl) return fail(ctx, AVO_E_INVALID, "shard plan is NULL");

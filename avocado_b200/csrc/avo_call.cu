@@ -64,8 +64,8 @@ __global__ void k_site_buckets(DReads R, DSites S_in, DIndex X, int32_t max_span
   const DSites S = resolve_sites(S_in);
   const int32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_grid) return;
-  const int32_t j = S.c_lo + idx;
-  if (j >= S.c_hi) { len[j] = 0; return; }     // past the table (capacity rows, the scan's sentinel)
+  const int32_t j = S_in.c_lo + idx;           // the launch covers the host's range (a header table: its capacity)
+  if (j < S.c_lo || j >= S.c_hi) { len[j] = 0; return; }     // rows no read of the batch can touch; the scan's sentinel
   const int32_t a = first_read_at(R, X, (int64_t)__ldg(S.start + j) - max_span + 1);
   const int32_t b = max(a, first_read_at(R, X, (int64_t)__ldg(S.end + j)));
   rbase[j] = a;
@@ -351,8 +351,8 @@ __global__ void __launch_bounds__(128)
 k_call_reduce(DSites S_in, DCallParams P, DResults O, const uint64_t* __restrict__ boff,
               const uint32_t* __restrict__ blen, const uint32_t* __restrict__ buckets, uint64_t n_slots) {
   const DSites S = resolve_sites(S_in);
-  const int32_t j = S.c_lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= S.c_hi) return;
+  const int32_t j = S_in.c_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < S.c_lo || j >= S.c_hi) return;
   const uint32_t* __restrict__ bk = buckets + (size_t)__ldg(boff + j);
   const uint32_t n = __ldg(blen + j);
   if (__ldg(boff + j) + n > n_slots) return;   // guessed capacity too small: the host reruns the stage

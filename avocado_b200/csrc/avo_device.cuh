@@ -68,7 +68,11 @@ __device__ __forceinline__ int32_t meta_start(const avo_read_meta* __restrict__ 
 __device__ __forceinline__ DSites resolve_sites(DSites S) {
   if (S.hdr) {
     const int32_t n = min(S.hdr->n, S.cap);
-    S.n = n; S.c_lo = 0; S.c_hi = n; S.midpoint = S.hdr->midpoint;
+    S.n = n; S.midpoint = S.hdr->midpoint;
+    // the rows a read of THIS batch can touch: [s_begin, s_end) (a table discovered from the batch itself:
+    // all of it; the global table of a sharded run: the neighbourhood of the rank's interval)
+    S.c_lo = max(0, min(S.hdr->s_begin, n));
+    S.c_hi = max(S.c_lo, min(S.hdr->s_end, n));
   }
   return S;
 }

@@ -218,6 +218,14 @@ struct ColumnCopies {
   size_t bytes[32];
 };
 cudaError_t launch_copy_columns(const ColumnCopies& cc, cudaStream_t s);
+constexpr int AVO_MAX_MERGE = 8;
+struct MergeParts {
+  int k;
+  const avo_read_meta* meta[AVO_MAX_MERGE];
+  int64_t n[AVO_MAX_MERGE];
+  uint32_t block_base[AVO_MAX_MERGE], op_base[AVO_MAX_MERGE], refb_base[AVO_MAX_MERGE];
+};
+cudaError_t launch_merge_meta(const MergeParts& M, avo_read_meta* out, cudaStream_t s);
 cudaError_t launch_max_i32(const int32_t* a, int64_t n, int32_t* d_out, cudaStream_t s);
 
 // ---- region-sharded discoverAndCall (avo_shard.cu) ---------------------------------------------------

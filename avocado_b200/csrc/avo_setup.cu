@@ -311,6 +311,45 @@ cudaError_t launch_wire6_expand(const avo_read_wire6* wire, const uint8_t* oplen
   return cudaGetLastError();
 }
 
+// ---- union of K sorted batches' records (reads.union of CLI/TrioGenotyper.scala:216): every record finds
+// its place in the merged order by counting, in each other part, the records that come before it
+// (ties: the earlier part first, so the merge is stable), and is written there with its three offsets
+// rebased to the concatenated payload / operator / mismatch columns.
+__global__ void __launch_bounds__(256)
+k_merge_meta(MergeParts M, avo_read_meta* __restrict__ out) {
+  const int k = blockIdx.y;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M.n[k]) return;
+  const int4 a = __ldg(reinterpret_cast<const int4*>(M.meta[k] + i));
+  int4 b = __ldg(reinterpret_cast<const int4*>(M.meta[k] + i) + 1);
+  const int32_t start = a.x;
+  int64_t rank = i;
+  for (int q = 0; q < M.k; ++q) {
+    if (q == k) continue;
+    int64_t lo = 0, hi = M.n[q];
+    while (lo < hi) {                       // q < k: records with start <= mine; q > k: with start < mine
+      const int64_t mid = lo + ((hi - lo) >> 1);
+      const int32_t v = __ldg(&M.meta[q][mid].start);
+      if (q < k ? v <= start : v < start) lo = mid + 1; else hi = mid;
+    }
+    rank += lo;
+  }
+  int4 a2 = a;
+  a2.z = (int32_t)((uint32_t)a.z + M.block_base[k]);      // seq_off
+  a2.w = (int32_t)((uint32_t)a.w + M.op_base[k]);         // op_off
+  b.x = (int32_t)((uint32_t)b.x + M.refb_base[k]);        // refb_off
+  reinterpret_cast<int4*>(out + rank)[0] = a2;
+  reinterpret_cast<int4*>(out + rank)[1] = b;
+}
+
+cudaError_t launch_merge_meta(const MergeParts& M, avo_read_meta* out, cudaStream_t s) {
+  int64_t mx = 0;
+  for (int k = 0; k < M.k; ++k) mx = std::max(mx, M.n[k]);
+  if (mx == 0) return cudaSuccess;
+  k_merge_meta<<<dim3((unsigned)((mx + 255) / 256), (unsigned)M.k), 256, 0, s>>>(M, out);
+  return cudaGetLastError();
+}
+
 // ---- max of an int32 column (device tables whose longest entry the host does not know) -------------------
 __global__ void k_max_i32(const int32_t* __restrict__ a, int64_t n, int32_t* __restrict__ out) {
   int32_t m = INT32_MIN;

@@ -811,10 +811,24 @@ def run_trio(args):
     from avocado_b200.trio import trio_call_packed
     per = args.reads if args.reads != READS_C2 else 6_200_000          # 31 Mb x 30x = chr1 / 8 per sample
     contig = int(per * 150 / 30)
-    samples = []
+    parts = []
     for s in range(3):
         p = B.synth_params(seed=SEED + 5, contig_len=contig * world, n_reads_total=per * world, sample=s + 1)
-        samples.append(B.synth_device(p, first=rank * per, n=per, device="cuda:%d" % local))
+        parts.append(B.synth_device(p, first=rank * per, n=per, device="cuda:%d" % local))
+    # the three samples' columns back to back in one allocation (as a shim uploading into one buffer would
+    # leave them): the union batch then points at the same memory and only the records are merged
+    arena = {name: torch.cat([getattr(b, name)[:n] for b, n in zip(parts, sizes)] + [getattr(parts[0], name)[:0].new_zeros(16)])
+             for name, sizes in (("payload", [b.n_blocks * 16 for b in parts]), ("ops", [b.n_ops for b in parts]),
+                                 ("refb", [b.n_refb for b in parts]))}
+    samples, o = [], dict(payload=0, ops=0, refb=0)
+    for b in parts:
+        v = B.ReadBatch(b.n_reads, b.n_blocks, b.n_ops, b.n_refb, b.contig_id, meta=b.meta, stats=b.stats)
+        for name, n in (("payload", b.n_blocks * 16), ("ops", b.n_ops), ("refb", b.n_refb)):
+            setattr(v, name, arena[name][o[name]:o[name] + n])
+            o[name] += n
+        samples.append(v)
+    samples[0]._arena = arena
+    del parts
     torch.cuda.synchronize()
     cap = max(1 << 17, per // 64)
     stage = {}
@@ -822,7 +836,7 @@ def run_trio(args):
     def step():
         with torch.cuda.stream(stream):
             t0 = time.perf_counter()
-            union = B.merge_batches(samples)
+            union = B.merge_batches(samples, ctx=ctx)
             torch.cuda.synchronize(); t1 = time.perf_counter()
             table = ctx.discover_packed(union, phred=25, min_obs=5, capacity=cap, device_out=True)
             t2 = time.perf_counter()
@@ -845,8 +859,9 @@ def run_trio(args):
                         "union discovery -> 3 calls -> TrioCaller" % (contig / 1e6, per),
                         scaling="weak", reads_per_step=reads, sites_per_gpu=int(n_sites), trio_sites_kept_per_gpu=int(kept),
                         stages_ms=stage,
-                        note="merge = sorted union of the three device batches (torch sort + gathers; the reference's RDD union is free, "
-                             "a sorted batch is this design's requirement); stage times are host clocks around synchronised calls"))
+                        note="merge = sorted union of the three samples' RECORDS (avo_merge_meta, one kernel; bases, qualities and "
+                             "operators stay where they are: the samples lie back to back in one allocation); the reference's RDD union "
+                             "is free, a sorted batch is this design's requirement; stage times are host clocks around synchronised calls"))
     if dist:
         dist.destroy_process_group()
 

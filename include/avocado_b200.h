@@ -316,6 +316,16 @@ int avo_discover_and_call(avo_ctx* ctx, const avo_read_batch* reads, const avo_c
                           const avo_params* params, avo_sites_out* sites_out,
                           avo_site_results* results);
 
+/* ---- union of several samples' batches (CLI/TrioGenotyper.scala:216: `reads.union(...)` before discovery) ----
+ * Merges the RECORDS of n_parts sorted device batches of one contig into `out_meta` (device, sum of the
+ * parts' n_reads records), stably sorted by start, with seq_off / op_off / refb_off rebased by the given
+ * bases: where each part's payload blocks / operators / mismatch bytes begin in the concatenated columns
+ * the union batch will point at (the caller lays the parts' columns out back to back, or copies them).
+ * One launch; does not wait for the device. */
+int avo_merge_meta(avo_ctx* ctx, int32_t n_parts, const avo_read_meta* const* part_meta, const int64_t* part_reads,
+                   const uint32_t* block_base, const uint32_t* op_base, const uint32_t* refb_base,
+                   avo_read_meta* out_meta);
+
 /* ---- region-sharded discoverAndCall: one process per GPU -------------------------------
  * Replaces, for several GPUs, what the reference does with `sortByKey().collect` + `sc.broadcast` of the
  * variants (util/TreeRegionJoin.scala:43-50, 184-185) and with the shuffle behind the per-site sums

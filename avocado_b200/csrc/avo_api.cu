@@ -1067,8 +1067,17 @@ struct ShardState {
   size_t slots_cap = SIZE_MAX;
   int ns = 0;
   int phase = 0;
+  ShardHdr* d_hdrs = nullptr;      // the 2 x world block headers of a step, collected by the unpack kernel
+  ShardHdr* h_hdrs = nullptr;      // (pinned) so that they reach the host in ONE copy
 };
-void free_shard_state(avo_ctx* ctx) { delete ctx->shard; ctx->shard = nullptr; }
+void free_shard_state(avo_ctx* ctx) {
+  if (ctx->shard) {
+    if (ctx->shard->d_hdrs) cudaFree(ctx->shard->d_hdrs);
+    if (ctx->shard->h_hdrs) cudaFreeHost(ctx->shard->h_hdrs);
+  }
+  delete ctx->shard;
+  ctx->shard = nullptr;
+}
 
 // ---- public entry points -------------------------------------------------------------------------
 extern "C" {
@@ -1394,6 +1403,8 @@ int avo_shard_discover(avo_ctx* ctx, const avo_read_batch* reads, const avo_para
   if (!ctx->shard) return fail(ctx, AVO_E_NOMEM, "out of host memory");
   ShardState& st = *ctx->shard;
   st.phase = 0;
+  if (!st.d_hdrs) CK(cudaMalloc(&st.d_hdrs, 2 * AVO_MAX_SHARDS * sizeof(ShardHdr)));
+  if (!st.h_hdrs) CK(cudaHostAlloc(&st.h_hdrs, 2 * AVO_MAX_SHARDS * sizeof(ShardHdr), cudaHostAllocDefault));
   CKS(upload_reads(ctx, reads, params->host_payload != 1, &st.R, params));
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   const bool hinted = stats_from_hints(reads, &st.hs);
@@ -1488,15 +1499,12 @@ int avo_shard_finish(avo_ctx* ctx, const avo_shard_plan* pl, const void* gathere
   O.copy_number = gr->copy_number; O.n_alt = gr->n_alt; O.n_ref = gr->n_ref; O.n_other = gr->n_other; O.qual = gr->qual;
   O.gq = gr->gq; O.sb = gr->sb; O.fisher = gr->fisher; O.rms_mapq = gr->rms_mapq; O.gl = gr->gl; O.nonref_gl = gr->nonref_gl;
   const int64_t out_rows = gr->n_sites;
-  CK(launch_shard_unpack_rows(gathered_rows, pl->world, (int32_t)pl->row_cap, st.ns, O, out_rows, ctx->num_sms, ctx->stream));
+  CK(launch_shard_unpack_rows(gathered_rows, gathered_tables, (int32_t)pl->site_cap, (int32_t)pl->allele_cap, pl->world,
+                              (int32_t)pl->row_cap, st.ns, O, out_rows, st.d_hdrs, ctx->num_sms, ctx->stream));
   ctx->timing.n_launches += 1;
-  // headers of both gathers + this rank's own counters, one synchronisation
-  const size_t tb = shard_table_block_bytes(pl->site_cap, pl->allele_cap), rb = shard_rows_block_bytes(pl->row_cap, st.ns);
-  std::vector<ShardHdr> ht(pl->world), hr(pl->world);
-  for (int r = 0; r < pl->world; ++r) {
-    CK(cudaMemcpyAsync(&ht[r], (const char*)gathered_tables + (size_t)r * tb, sizeof(ShardHdr), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(&hr[r], (const char*)gathered_rows + (size_t)r * rb, sizeof(ShardHdr), cudaMemcpyDeviceToHost, ctx->stream));
-  }
+  // headers of both gathers (collected by the kernel: one copy) + this rank's own counters, one synchronisation
+  CK(cudaMemcpyAsync(st.h_hdrs, st.d_hdrs, 2 * (size_t)pl->world * sizeof(ShardHdr), cudaMemcpyDeviceToHost, ctx->stream));
+  const ShardHdr *ht = st.h_hdrs, *hr = st.h_hdrs + pl->world;
   CKS(discover_fetch_counts(ctx));
   CK(cudaEventRecord(ctx->ev[7], ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

@@ -102,15 +102,13 @@ __device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, co
   };
 
   const int ns = b - a;
-  uint32_t cats[MAX_LOCAL_SITES];
-  int32_t qs[MAX_LOCAL_SITES];
+  uint16_t cq[MAX_LOCAL_SITES];                           // category | (quality + 1) << 3 (quality -1 = none .. 255)
   const bool cached = ns <= MAX_LOCAL_SITES;
   if (cached) {
     for (int j = 0; j < ns; ++j) {
       const Cls c = classify_at(a + j);
       if (c.cat == CAT_EXC) return;                       // BG:385-391: the whole read is skipped
-      cats[j] = c.cat;
-      qs[j] = c.q;
+      cq[j] = (uint16_t)(c.cat | ((uint32_t)(c.q + 1) << 3));
     }
   } else {
     for (int j = 0; j < ns; ++j)
@@ -120,13 +118,13 @@ __device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, co
   const int mq = min(P.max_mapq, (int)rc.mapq);           // BG:452
   for (int32_t j = a; j < b; ++j) {
     Cls c;
-    if (cached) { c.cat = cats[j - a]; c.q = qs[j - a]; } else c = classify_at(j);
+    if (cached) { c.cat = cq[j - a] & 7u; c.q = (int32_t)(cq[j - a] >> 3) - 1; } else c = classify_at(j);
     if (c.cat == CAT_NONE) continue;
     const int32_t js = __ldg(S.start + j), je = __ldg(S.end + j);
     if (c.cat == CAT_NONREF) {                            // BG:359-373 other-alt pass
       for (int32_t k = a; k < b; ++k) {
         if (!(__ldg(S.start + k) < je && __ldg(S.end + k) > js)) continue;
-        const uint32_t kc = cached ? cats[k - a] : classify_at(k).cat;
+        const uint32_t kc = cached ? (cq[k - a] & 7u) : classify_at(k).cat;
         if (kc == CAT_ALT) { c.cat = CAT_OTHER; break; }
       }
     }

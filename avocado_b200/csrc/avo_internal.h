@@ -257,8 +257,9 @@ cudaError_t launch_shard_site_index(const DSites& S, const BatchStats& h, int32_
 cudaError_t launch_shard_pack_rows(const DResults& D, int ns, const void* gathered_tables, int32_t world, int32_t rank,
                                    int32_t tcap, int32_t tacap, const uint64_t* slots_used, uint64_t slots_cap, void* block,
                                    int32_t rcap, int num_sms, cudaStream_t s);
-cudaError_t launch_shard_unpack_rows(const void* gathered_rows, int32_t world, int32_t rcap, int ns, const DResults& O,
-                                     int64_t out_rows, int num_sms, cudaStream_t s);
+cudaError_t launch_shard_unpack_rows(const void* gathered_rows, const void* gathered_tables, int32_t tcap, int32_t tacap,
+                                     int32_t world, int32_t rcap, int ns, const DResults& O, int64_t out_rows, ShardHdr* hdrs_out,
+                                     int num_sms, cudaStream_t s);
 
 // ---- launchers (each returns the cudaError_t of its launches) --------------------------------
 cudaError_t launch_batch_stats(const DReads& R, BatchStats* d_stats, cudaStream_t s);

@@ -31,12 +31,88 @@ __device__ __forceinline__ int32_t ins_quality(const uint8_t* __restrict__ pl, u
   return sum / len;
 }
 
+// The same for every site that is not an insertion variant (SNVs, MNPs, deletions: BG:327-355 only looks at
+// the FIRST observation's allele and at counts), in two phases: the operator walk touches no payload and only
+// notes where the first observation lies; the payload is read once, after the walk, when the lanes of a
+// warp have left their differently long operator loops and issue that load together.
+__device__ inline Cls classify_by_head(const DReads& R, const ReadCtx& rc, int32_t vs, int32_t ref_len,
+                                       int32_t alt_len, uint32_t aoff, const uint8_t* __restrict__ alleles4) {
+  const int32_t ve = vs + ref_len;
+  const uint32_t altoff = aoff + (uint32_t)ref_len;
+  int32_t pos = rc.start;
+  uint32_t ridx = 0;
+  int n_obs = 0, n_nonempty = 0, n_del = 0, first_del_w = 0;
+  int head_kind = 0;             // 0 none, 1 aligned base, 2 insertion, 3 deletion
+  uint32_t head_at = 0;          // read index of the head's first base
+  int head_len = 0;
+  bool head_isref = false;
+  for (uint32_t k = 0; k < rc.no; ++k) {
+    const uint32_t op = __ldg(R.ops + rc.ob + k);
+    const int len = (int)(op >> 4);
+    const uint32_t code = op & 15u;
+    if (code == AVO_OP_SOFTCLIP) { ridx += len; continue; }             // Observer.scala:66-71
+    if (code == AVO_OP_HARDCLIP) continue;
+    if (code == AVO_OP_MATCH || code == AVO_OP_MISMATCH) {              // Observer.scala:72-92
+      const int32_t lo = max(pos, vs), hi = min(pos + len, ve);
+      if (lo < hi) {
+        if (n_obs == 0) { head_kind = 1; head_at = ridx + (uint32_t)(lo - pos); head_isref = (code == AVO_OP_MATCH); }
+        n_obs += hi - lo; n_nonempty += hi - lo;
+      }
+      pos += len; ridx += len;
+    } else if (code == AVO_OP_INS) {                                    // Observer.scala:93-118
+      if (pos - 1 < ve && pos > vs) {
+        if (n_obs == 0) { head_kind = 2; head_at = ridx; head_len = len; }
+        ++n_obs; ++n_nonempty;
+      }
+      ridx += len;
+    } else if (code == AVO_OP_DEL) {                                    // Observer.scala:119-138
+      if (pos < ve && pos + len > vs) {
+        if (n_obs == 0) head_kind = 3;
+        if (n_del == 0) first_del_w = len;
+        ++n_del; ++n_obs;
+      }
+      pos += len;
+    }
+    if (pos > ve) break;  // nothing later in the read can overlap the site
+  }
+  Cls out;
+  out.q = -1;
+  bool head_eq_alt = false;
+  if (head_kind == 1) {
+    uint32_t b, bq;
+    pl_base_qual(R.payload, rc.sb, head_at, b, bq);       // base and quality: one 16-byte load
+    out.q = (int32_t)bq;
+    head_eq_alt = (alt_len == 1 && b == nib_at(alleles4, altoff));
+  } else if (head_kind == 2) {
+    out.q = ins_quality(R.payload, rc.sb, head_at, head_len);
+    bool eq = (head_len == alt_len);
+    for (int i = 0; eq && i < head_len; ++i)
+      eq = pl_base(R.payload, rc.sb, head_at + i) == nib_at(alleles4, altoff + i);
+    head_eq_alt = eq;
+  } else if (head_kind == 3) {
+    head_eq_alt = (alt_len == 0);
+  }
+  if (n_obs == 0) { out.cat = CAT_NONE; return out; }                   // BG:297-298
+  if (n_nonempty == 1 && head_eq_alt) {                                 // BG:327-355
+    if (ref_len > 1 && alt_len == 1)                                    // isDeletion
+      out.cat = (n_del == 1 && n_obs == 2 && first_del_w == ref_len - alt_len) ? CAT_ALT : CAT_NONREF;
+    else
+      out.cat = head_isref ? CAT_REF : CAT_ALT;
+  } else if (!head_isref || n_obs != ref_len) {
+    out.cat = CAT_NONREF;
+  } else {
+    out.cat = CAT_REF;
+  }
+  return out;
+}
+
 // S4 + S5 of SURVEY.md for one (read, site): walk the read's operators, summarise the observations
 // that overlap [vs, vs + ref_len) in read order, then apply BG:297-355.
 __device__ inline Cls classify(const DReads& R, const ReadCtx& rc, int32_t vs, int32_t ref_len,
                         int32_t alt_len, uint32_t aoff, const uint8_t* __restrict__ alleles4) {
   const int32_t ve = vs + ref_len;
   const bool insVar = (ref_len == 1 && alt_len > 1);                    // BG:409-412
+  if (!insVar) return classify_by_head(R, rc, vs, ref_len, alt_len, aoff, alleles4);
   const uint32_t altoff = aoff + (uint32_t)ref_len;
   int32_t pos = rc.start;
   uint32_t ridx = 0;

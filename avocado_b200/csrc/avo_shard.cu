@@ -229,41 +229,57 @@ cudaError_t launch_shard_pack_rows(const DResults& D, int ns, const void* gather
   return cudaGetLastError();
 }
 
-// gathered rows blocks -> the global result columns (rows of rank r start where its table rows start)
+// gathered rows blocks -> the global result columns.  The rows of rank r start where its table rows start
+// (gathered table headers); a block whose header says 0 rows is skipped (a rank that is not the root of a
+// gather-to-root step holds only its own block).  blockIdx.y = rank; the block headers of both gathers are
+// collected into hdrs_out ([0, world) tables, [world, 2 world) rows) for the host's one copy.
 __global__ void __launch_bounds__(256)
-k_shard_unpack_rows(const unsigned char* __restrict__ gathered_rows, int32_t world, int32_t rcap, int ns, DResults O,
-                    int64_t out_rows) {
-  const size_t bb = shard_rows_bytes(rcap, ns);
+k_shard_unpack_rows(const unsigned char* __restrict__ gathered_rows, const unsigned char* __restrict__ gathered_tables,
+                    int32_t tcap, int32_t tacap, int32_t world, int32_t rcap, int ns, DResults O, int64_t out_rows,
+                    ShardHdr* __restrict__ hdrs_out) {
+  const size_t bb = shard_rows_bytes(rcap, ns), tbb = shard_table_bytes(tcap, tacap);
+  const int r = blockIdx.y;
+  const unsigned char* blk = gathered_rows + (size_t)r * bb;
+  if (blockIdx.x == 0 && threadIdx.x < 16) {
+    const int32_t* src = reinterpret_cast<const int32_t*>(threadIdx.x < 8 ? gathered_tables + (size_t)r * tbb : blk);
+    reinterpret_cast<int32_t*>(hdrs_out + (threadIdx.x < 8 ? r : world + r))[threadIdx.x & 7] = src[threadIdx.x & 7];
+  }
+  int64_t A = 0;
+  int32_t n_table = 0;
+  for (int q = 0; q <= r; ++q) {
+    A += n_table;
+    n_table = min(reinterpret_cast<const ShardHdr*>(gathered_tables + (size_t)q * tbb)->n_rows, tcap);
+  }
+  const int32_t n = min(min(reinterpret_cast<const ShardHdr*>(blk)->n_rows, rcap), n_table);
+  const int64_t rows = max((int64_t)0, min((int64_t)n, out_rows - A));
+  if (rows == 0) return;
   const void* dstp[AVO_RESULT_COLUMNS];
   int width[AVO_RESULT_COLUMNS];
   shard_row_columns(O, ns, dstp, width);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t A = 0;
-  for (int r = 0; r < world; ++r) {
-    const unsigned char* blk = gathered_rows + (size_t)r * bb;
-    const int32_t n = min(reinterpret_cast<const ShardHdr*>(blk)->n_rows, rcap);
-    const int64_t rows = max((int64_t)0, min((int64_t)n, out_rows - A));
-    size_t off = sizeof(ShardHdr);
-    for (int c = 0; c < AVO_RESULT_COLUMNS; ++c) {
-      const size_t bytes = (size_t)rows * width[c];
-      const unsigned char* s8 = blk + off;
-      unsigned char* d8 = (unsigned char*)dstp[c] + (size_t)A * width[c];
-      if (((((uintptr_t)s8) | (uintptr_t)d8) & 3u) == 0 && (width[c] & 3) == 0) {
-        const uint32_t* s4 = (const uint32_t*)s8;
-        uint32_t* d4 = (uint32_t*)d8;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)(bytes >> 2); i += stride) d4[i] = s4[i];
-      } else {
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)bytes; i += stride) d8[i] = s8[i];
-      }
-      off += ((size_t)rcap * width[c] + 15) & ~(size_t)15;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t off = sizeof(ShardHdr);
+#pragma unroll 1
+  for (int c = 0; c < AVO_RESULT_COLUMNS; ++c) {
+    const size_t bytes = (size_t)rows * width[c];
+    const unsigned char* s8 = blk + off;
+    unsigned char* d8 = (unsigned char*)dstp[c] + (size_t)A * width[c];
+    if (((((uintptr_t)s8) | (uintptr_t)d8) & 3u) == 0 && (width[c] & 3) == 0) {
+      const uint32_t* s4 = (const uint32_t*)s8;
+      uint32_t* d4 = (uint32_t*)d8;
+      for (int64_t i = t0; i < (int64_t)(bytes >> 2); i += stride) d4[i] = s4[i];
+    } else {
+      for (int64_t i = t0; i < (int64_t)bytes; i += stride) d8[i] = s8[i];
     }
-    A += n;
+    off += ((size_t)rcap * width[c] + 15) & ~(size_t)15;
   }
 }
 
-cudaError_t launch_shard_unpack_rows(const void* gathered_rows, int32_t world, int32_t rcap, int ns, const DResults& O,
-                                     int64_t out_rows, int num_sms, cudaStream_t s) {
-  k_shard_unpack_rows<<<2 * num_sms, 256, 0, s>>>((const unsigned char*)gathered_rows, world, rcap, ns, O, out_rows);
+cudaError_t launch_shard_unpack_rows(const void* gathered_rows, const void* gathered_tables, int32_t tcap, int32_t tacap,
+                                     int32_t world, int32_t rcap, int ns, const DResults& O, int64_t out_rows, ShardHdr* hdrs_out,
+                                     int num_sms, cudaStream_t s) {
+  const int bx = max(1, min(2 * num_sms / max(world, 1), (rcap + 255) / 256));
+  k_shard_unpack_rows<<<dim3(bx, world), 256, 0, s>>>((const unsigned char*)gathered_rows, (const unsigned char*)gathered_tables,
+                                                      tcap, tacap, world, rcap, ns, O, out_rows, hdrs_out);
   return cudaGetLastError();
 }
 

@@ -142,7 +142,8 @@ class ShardedPipeline:
     NCCL by default; tests emulate several ranks on one GPU by passing their own."""
 
     def __init__(self, ctx, rank: int, world: int, own_lo: int, own_hi: int, ploidy: int = 2, site_cap: int = 1 << 15,
-                 allele_cap: int = 1 << 17, global_cap: Optional[int] = None, gather=None, group=None, stream=None):
+                 allele_cap: int = 1 << 17, global_cap: Optional[int] = None, gather=None, group=None, stream=None,
+                 rows_to: str = "all"):
         import torch
         from . import _lib as L
         self.ctx, self.L, self.torch = ctx, L, torch
@@ -154,6 +155,11 @@ class ShardedPipeline:
         self.global_cap = global_cap
         self.group = group
         self.gather = gather or self._nccl_gather
+        # "all": every rank ends with every row (all-gather of the rows blocks).  "root": the rows are
+        # gathered to rank 0 only (the driver's `collect`); the other ranks all-gather just the 32-byte
+        # headers and end with the global table and their OWN rows.
+        assert rows_to in ("all", "root")
+        self.rows_to = rows_to if gather is None else "all"
         self.nccl_bytes = 0
         # the phases and the collectives are ordered on ONE stream of the pipeline's own (the context's
         # default is a stream torch does not know; torch's default stream has no handle to pass)
@@ -164,6 +170,32 @@ class ShardedPipeline:
     def _nccl_gather(self, out, inp):
         import torch.distributed as dist
         dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def _gather_rows(self):
+        """The second collective: the rows blocks to every rank, or to rank 0 (+ the headers to everyone)."""
+        if self.rows_to == "all":
+            self.gather(self.r_all, self.r_send)
+            return
+        import torch.distributed as dist
+        torch, p, W = self.torch, self.plan, self.plan.world
+        dist.all_gather_into_tensor(self.rh_all, self.r_send[:32], group=self.group)
+        blocks = self.r_all.view(W, self.rb)
+        if p.rank == 0:
+            dist.gather(self.r_send, gather_list=list(blocks.unbind(0)), dst=0, group=self.group)
+        else:
+            dist.gather(self.r_send, dst=0, group=self.group)
+            self._place_own_rows()
+
+    def _place_own_rows(self):
+        """A rank that is not the root of the rows gather: its own block in place; of the other ranks only
+        the header (self.rh_all), with a row count of 0 -- their flags still decide the retry."""
+        torch, p, W = self.torch, self.plan, self.plan.world
+        blocks = self.r_all.view(W, self.rb)
+        h = self.rh_all.view(W, 32).clone()
+        others = torch.arange(W, device=self.dev) != p.rank
+        h[:, :4] = torch.where(others[:, None], torch.zeros_like(h[:, :4]), h[:, :4])
+        blocks[:, :32].copy_(h)
+        blocks[p.rank].copy_(self.r_send)
 
     def _size(self, site_cap, allele_cap):
         import ctypes as C
@@ -177,6 +209,7 @@ class ShardedPipeline:
         self.t_all = torch.empty(self.tb * W, dtype=torch.uint8, device=self.dev)
         self.r_send = torch.empty(self.rb, dtype=torch.uint8, device=self.dev)
         self.r_all = torch.empty(self.rb * W, dtype=torch.uint8, device=self.dev)
+        self.rh_all = torch.empty(32 * W, dtype=torch.uint8, device=self.dev)
         gcap = self.global_cap or p.site_cap * W
         self.gcap, self.gacap = int(gcap), int(p.allele_cap * W * 2)
         from .batch import _device_empty
@@ -185,13 +218,17 @@ class ShardedPipeline:
                           allele_off=mk(self.gcap + 1, np.uint32), alleles4=mk(self.gacap // 2 + 16, np.uint8),
                           count=mk(self.gcap, np.int32))
         self.res, self.cols = self.ctx._alloc_results(self.gcap, p.n_states, self.dev)
+        self._views = None
 
     # ---- the three phases (step() runs them around the two collectives; tests drive them by hand) ----
     def phase_discover(self, batch: ReadBatch, phred: int = 0, min_obs: Optional[int] = None):
         import ctypes as C
         ctx, p = self.ctx, self.plan
-        self._params = ctx._params(ploidy=self.ploidy, phred=phred, min_obs=min_obs)
-        self._bs = batch.as_struct()
+        key = (phred, min_obs, batch.n_reads)
+        if getattr(self, "_bs_for", None) is not batch or self._bs_key != key:    # the same batch again: same structs
+            self._params = ctx._params(ploidy=self.ploidy, phred=phred, min_obs=min_obs)
+            self._bs = batch.as_struct()
+            self._bs_for, self._bs_key = batch, key
         ctx._check(ctx.lib.avo_shard_discover(ctx.h, C.byref(self._bs), C.byref(self._params), C.byref(p),
                                               self.t_send.data_ptr()))
 
@@ -217,7 +254,8 @@ class ShardedPipeline:
         need = self._need = self.L.ShardPlanStruct()
         rc = ctx.lib.avo_shard_finish(ctx.h, C.byref(p), self.t_all.data_ptr(), self.r_all.data_ptr(), C.byref(out),
                                       C.byref(self.res), C.byref(need))
-        self.nccl_bytes = (self.tb + self.rb) * p.world              # bytes every rank receives per step
+        # bytes this rank receives per step
+        self.nccl_bytes = self.tb * p.world + (self.rb * p.world if (self.rows_to == "all" or p.rank == 0) else 32 * p.world)
         if rc == AVO_E_RETRY:
             return None
         if rc == AVO_E_CAPACITY:           # the same answer on every rank: all of them grow and run again
@@ -226,6 +264,8 @@ class ShardedPipeline:
             return None
         ctx._check(rc)
         n, nn = int(out.n), int(out.n_allele_nibbles)
+        if self._views is not None and self._views[0] == (n, nn):     # same shapes as the previous step: same views
+            return self._views[1]
         s = self.sites
         table = SiteTable(n, nn, s["start"][:n], s["ref_len"][:n], s["alt_len"][:n], s["allele_off"][:n + 1],
                           s["alleles4"][:(nn + 1) // 2 or 1], None, s["count"][:n])
@@ -234,12 +274,14 @@ class ShardedPipeline:
             width = p.n_states if w == "ns" else w
             a = self.cols[name][:n * width]
             cols[name] = a.reshape(n, width) if width != 1 else a
+        self._views = ((n, nn), (table, cols))
         return table, cols
 
     def step(self, batch: ReadBatch, phred: int = 0, min_obs: Optional[int] = None, max_tries: int = 6):
         """One sharded discoverAndCall over this rank's reads (own interval + halo).  Returns, on every
         rank, (global SiteTable, dict of result columns for all its rows) as device tensors -- views of the
-        pipeline's buffers, valid until the next step."""
+        pipeline's buffers, valid until the next step.  With rows_to="root" only rank 0's columns hold
+        every row; on the other ranks the rows outside [own_lo, own_hi) are not filled."""
         from ._lib import AVO_E_CAPACITY, AvocadoError
         if getattr(self, "_shrink_to", None):        # (the previous step's result views end here)
             self.global_cap = None
@@ -250,7 +292,7 @@ class ShardedPipeline:
                 self.phase_discover(batch, phred, min_obs)
                 self.gather(self.t_all, self.t_send)
                 self.phase_call()
-                self.gather(self.r_all, self.r_send)
+                self._gather_rows()
                 got = self.phase_finish()
             if got is not None:
                 # blocks much larger than what the ranks own waste NVLink bytes: every rank sees the same
@@ -260,6 +302,23 @@ class ShardedPipeline:
                     self._shrink_to = (int(need.site_cap), int(need.allele_cap))
                 return got
         raise AvocadoError(AVO_E_CAPACITY, "sharded step kept asking for larger buffers")
+
+    def step_phases_ms(self, batch: ReadBatch, phred: int = 0, min_obs: Optional[int] = None):
+        """One steady-state step with CUDA events between its phases (a measurement aid; a step that has
+        to retry raises).  Returns the milliseconds of discover / table gather / call / rows gather / finish."""
+        ev = [self.torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        with self.torch.cuda.stream(self.stream):
+            ev[0].record()
+            self.phase_discover(batch, phred, min_obs); ev[1].record()
+            self.gather(self.t_all, self.t_send); ev[2].record()
+            self.phase_call(); ev[3].record()
+            self._gather_rows(); ev[4].record()
+            got = self.phase_finish(); ev[5].record()
+        self.stream.synchronize()
+        if got is None:
+            raise RuntimeError("step_phases_ms needs a pipeline in steady state")
+        names = ("discover", "gather_tables", "call", "gather_rows", "finish")
+        return {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)}
 
 
 class GpuEngine:

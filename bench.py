@@ -10,9 +10,10 @@ BASELINE.json configs[1] shape per GPU: single-sample 60x chr20 (64 Mb), 150 bp 
   value     reads/s with the packed batch already resident in HBM (device pointers through the C ABI).
             N = 1: avo_discover_and_call, one launch chain, no host round trip.  N > 1 (torchrun): the
             genome is N times larger, cut into N regions WITH read-overlap halos; every step runs the
-            region-sharded path (avo_shard_discover / _call / _finish around two NCCL all-gathers: the
-            owned slice of every rank's site table, then the owned result rows), so the collectives are
-            inside the timed region and every rank ends with the global table and all rows.
+            region-sharded path (avo_shard_discover / _call / _finish around two NCCL collectives: an
+            all-gather of the owned slice of every rank's site table, then a gather of the owned result
+            rows to rank 0 plus their 32-byte headers to every rank), so the collectives are inside the
+            timed region; every rank ends with the global table, rank 0 with all rows.
   e2e       the same metric from HOST buffers holding what the reference's job holds: AlignmentRecord
             TEXT columns (CIGAR, MD, sequence, qualities) in pinned memory -> H2D -> device packer
             (avo_pack_reads_device) -> avo_discover_and_call -> D2H of the site table and every result
@@ -204,8 +205,8 @@ def run_reference(args):
 
 def config_dict(args, per, contig, world):
     par = ("one GPU" if world == 1 else
-           "region-sharded x%d with read-overlap halos: NCCL all-gather of the owned site-table slices, then of the owned "
-           "result rows, both inside the timed step; every rank ends with the global table and all rows" % world)
+           "region-sharded x%d with read-overlap halos: NCCL all-gather of the owned site-table slices, then a gather of the "
+           "owned result rows to rank 0, both inside the timed step; every rank ends with the global table, rank 0 with all rows" % world)
     return {"workload": "single-sample germline discoverAndCall, synthetic 60x chr20-shaped (%.0f Mb, %d x 150 bp reads) per GPU"
                         % (contig / 1e6, per),
             "reads_per_gpu": per, "contig_mb_per_gpu": contig / 1e6, "read_len": 150, "ploidy": 2,
@@ -376,7 +377,7 @@ def main():
         span = int((dev.meta[:dev.n_reads * 32].view(torch.int32).view(-1, 8)[:, 1] - starts).max().item())
         assert rank == 0 or int(starts[0].item()) <= own_lo - span, "halo too short for the batch's longest read span"
         pipe = ShardedPipeline(ctx, rank, world, own_lo, own_hi, site_cap=max(1 << 12, per // 256), allele_cap=max(1 << 14, per // 64),
-                               stream=stream)
+                               stream=stream, rows_to="root")
 
     def step_device():
         if pipe is not None:
@@ -452,10 +453,13 @@ def main():
                 "other_kernel": {"call_kernels_ms": ms_call, "k_discover_tiles_ms": ms_disc}}
     sharding = None
     if pipe is not None:
+        for _ in range(2):                      # outside the timed region: where a step's time goes, per phase
+            phases = pipe.step_phases_ms(dev, phred=25, min_obs=5)
         sharding = {"halo_reads_before": halo_lo, "halo_reads_after": halo_hi, "nccl_bytes_received_per_rank_per_step": int(pipe.nccl_bytes),
                     "table_block_bytes": int(pipe.tb), "rows_block_bytes": int(pipe.rb), "collectives_per_step": 2,
-                    "note": "all_gather_into_tensor of one fixed-size block each (owned table slice; owned result rows); no other "
-                            "exchange, one host synchronisation per step"}
+                    "rows_to": pipe.rows_to, "phases_ms_rank0": {k: round(v, 4) for k, v in phases.items()},
+                    "note": "all_gather_into_tensor of the owned table slices; gather of the owned result rows to rank 0 and an all-gather "
+                            "of their 32-byte headers (the byte count is rank 0's); no other exchange, one host synchronisation per step"}
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------
     e2e = None

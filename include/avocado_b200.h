@@ -342,6 +342,10 @@ int avo_merge_meta(avo_ctx* ctx, int32_t n_parts, const avo_read_meta* const* pa
  *   all-gather(rows_block)             -> gathered_rows
  *   avo_shard_finish(...)              -> global table + every row on every rank; one synchronisation
  *
+ * A framework that wants the rows on ONE rank only gathers the rows blocks to that rank and all-gathers just
+ * their 32-byte headers (every rank needs the flags in them): the other ranks pass `gathered_rows` with
+ * their own block in place and, for the other ranks' blocks, the header with its first word (the row count)
+ * set to 0 -- avo_shard_finish then leaves those rows untouched.
  * Block sizes come from the plan's capacities (avo_shard_*_block_bytes).  avo_shard_finish returns
  * AVO_E_CAPACITY with the capacities that are needed (identical on every rank: they follow from the
  * gathered headers), or AVO_E_RETRY when some rank ran out of an internal capacity (every rank sees it in

@@ -53,6 +53,21 @@ def main():
     for k, v in c1.items():
         assert np.array_equal(cols[k], np.asarray(v), equal_nan=True), "column %s differs on rank %d" % (k, rank)
     nccl_bytes = pipe.nccl_bytes
+    # the same with the rows gathered to rank 0 only: the others keep the table and their own rows
+    pipe_r = ShardedPipeline(ctx, rank, world, max(sh.lo, -(1 << 31) + 1), min(sh.hi, (1 << 31) - 1),
+                             site_cap=256, allele_cap=256, rows_to="root")
+    for _ in range(3):
+        table_r, cols_r = pipe_r.step(mine, phred=25, min_obs=5)
+    table_r = table_r.to_host()
+    st = np.asarray(t1.start)
+    assert table_r.n == t1.n and np.array_equal(np.asarray(table_r.start), st)
+    own = np.ones(t1.n, bool) if rank == 0 else (st >= sh.lo) & (st < sh.hi)
+    for k, v in c1.items():
+        v = np.asarray(v)
+        per = v.size // t1.n
+        m = np.repeat(own, per) if per > 1 else own
+        assert np.array_equal(cols_r[k].cpu().numpy().ravel()[m], v.ravel()[m], equal_nan=True), "root-gather column %s differs on rank %d" % (k, rank)
+    assert rank == 0 or pipe_r.nccl_bytes < nccl_bytes
 
     # ---- (2) sample-sharded joint calling ------------------------------------------------------
     rng = np.random.default_rng(11)

@@ -9,7 +9,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def run_emulated(whole, world, phred, min_obs, site_cap, allele_cap, global_cap=None, max_site_len=64):
+def run_emulated(whole, world, phred, min_obs, site_cap, allele_cap, global_cap=None, max_site_len=64, rows_to="all"):
     import torch
     from avocado_b200.genotyping import Context
     from avocado_b200.parallel import ShardedPipeline, plan_region_shards
@@ -38,7 +38,12 @@ def run_emulated(whole, world, phred, min_obs, site_cap, allele_cap, global_cap=
                 allr = torch.cat([p.r_send for p in pipes])
                 got = []
                 for p in pipes:
-                    p.r_all.copy_(allr)
+                    if rows_to == "all" or p.plan.rank == 0:
+                        p.r_all.copy_(allr)
+                    else:                       # gather-to-root: the others see only the 32-byte headers
+                        p.r_all.fill_(0xEE)
+                        p.rh_all.copy_(torch.cat([q.r_send[:32] for q in pipes]))
+                        p._place_own_rows()
                     got.append(p.phase_finish())
             assert len({g is None for g in got}) == 1, "every rank takes the same decision"
             if got[0] is not None:
@@ -77,6 +82,32 @@ def test_emulated_ranks_reproduce_the_single_gpu_rows(world, site_cap, allele_ca
         assert np.array_equal(table.alleles4[:(table.n_allele_nibbles + 1) // 2], t1.alleles4[:(t1.n_allele_nibbles + 1) // 2])
         for k, v in c1.items():
             assert np.array_equal(cols[k], np.asarray(v), equal_nan=True), "column %s differs" % k
+
+
+def test_rows_gathered_to_the_root_only():
+    """rows_to="root": rank 0 ends with every row; the other ranks with the global table and their OWN rows
+    (the blocks of the others reach them as headers with a row count of 0)."""
+    from avocado_b200 import batch as B
+    from avocado_b200.genotyping import Context
+    p = B.synth_params(seed=34, n_reads_total=60000, contig_len=300000, first_pos=10000)
+    whole = B.synth_host(p)
+    ctx = Context(0)
+    try:
+        t1, c1 = ctx.discover_and_call_packed(whole, phred=25, min_obs=5)
+    finally:
+        ctx.close()
+    got, tries, shards = run_emulated(whole, 4, 25, 5, 64, 64, rows_to="root")
+    assert tries > 1
+    start = np.asarray(t1.start)
+    for sh, (table, cols) in zip(shards, got):
+        assert table.n == t1.n and np.array_equal(np.asarray(table.start), start)
+        own = np.ones(t1.n, bool) if sh.rank == 0 else (start >= sh.lo) & (start < sh.hi)
+        assert own.sum() > 20
+        for k, v in c1.items():
+            v = np.asarray(v)
+            per = v.size // t1.n
+            m = np.repeat(own, per) if per > 1 else own
+            assert np.array_equal(cols[k].ravel()[m], v.ravel()[m], equal_nan=True), "column %s differs on rank %d" % (k, sh.rank)
 
 
 def test_sharded_forest_quirk_across_the_boundary():

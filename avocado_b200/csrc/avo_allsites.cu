@@ -48,6 +48,7 @@ __device__ bool as_join(const DReads& R, const DSites& S, const DIndex& X, int32
   ReadCtx rc;
   rc.start = ma.start; rc.end = ma.end; rc.ob = ma.op_off; rc.no = mb.n_ops; rc.sb = ma.seq_off;
   rc.mapq = mb.mapq; rc.fwd = true;
+  rc.w0 = __ldg(R.ops + ma.op_off);
   for (int32_t j = a; j < b; ++j) {
     if (__ldg(S.ref_len + j) == 1 && __ldg(S.alt_len + j) > 1 && classify_site(R, rc, S, j).cat == CAT_EXC)
       return false;

@@ -729,8 +729,9 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
   if (work)
     CK(launch_call_buckets(R, S, X, hs, (int32_t*)d_rbase, (uint32_t*)d_blen, (uint64_t*)d_boff, d_temp, tb2,
                            ctx->stream, &nl));
-  void* d_jlist;
-  CKS(get_buf(ctx, SL_AS_JR, (size_t)(R.n + 1) * 12 /* + 1: the pair scan loads one element past the list */, &d_jlist));
+  void* d_jlist = nullptr;                 // the list of joined reads: only the host-gathered route builds one
+  if (ctx->gather_src)
+    CKS(get_buf(ctx, SL_AS_JR, (size_t)(R.n + 1) * 12 /* + 1: the pair scan loads one element past the list */, &d_jlist));
   // The number of bucket slots is known on the device.  Instead of waiting for it, the stage runs
   // with the previous call's count (+ 1/8) as capacity, the kernels never write past it, and the
   // count is checked with the results; a stage that ran out of slots is rerun with the exact count.
@@ -750,16 +751,24 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
       }
     }
     CKS(get_buf(ctx, SL_C_BUCKETS, n_slots * 4, &d_buckets));
-    nvtxRangePushA(T_TREE_JOIN);
-    CK(launch_call_join(R, S, X, hs.max_span, (uint32_t*)d_buckets, n_slots, d_jlist, small + SW_JOIN, ctx->num_sms, ctx->stream, &nl));
-    const uint8_t* d_compact = nullptr;
-    const uint32_t *d_pbase = nullptr, *d_blk0 = nullptr;
-    nvtxRangePop();
-    if (ctx->gather_src && work) CKS(gather_payload(ctx, R, S, d_jlist, small + SW_JOIN, &d_compact, &d_pbase, &d_blk0, &nl));
-    Range r_obs(T_OBSERVE_READS " / " T_EMIT_GENOTYPES);
-    CK(launch_call_observe(R, S, C, P, D, (const int32_t*)d_rbase, (const uint32_t*)d_blen, (const uint64_t*)d_boff,
-                           (uint32_t*)d_buckets, n_slots, d_jlist, small + SW_JOIN, d_compact, d_pbase, d_blk0, ctx->num_sms,
-                           ctx->stream, &nl));
+    if (ctx->gather_src) {
+      // host-gathered payload: the joined reads are listed first (the host copies the blocks they need)
+      nvtxRangePushA(T_TREE_JOIN);
+      CK(launch_call_join(R, S, X, hs.max_span, (uint32_t*)d_buckets, n_slots, d_jlist, small + SW_JOIN, ctx->num_sms, ctx->stream, &nl));
+      const uint8_t* d_compact = nullptr;
+      const uint32_t *d_pbase = nullptr, *d_blk0 = nullptr;
+      nvtxRangePop();
+      if (work) CKS(gather_payload(ctx, R, S, d_jlist, small + SW_JOIN, &d_compact, &d_pbase, &d_blk0, &nl));
+      Range r_obs(T_OBSERVE_READS " / " T_EMIT_GENOTYPES);
+      CK(launch_call_observe(R, S, C, P, D, (const int32_t*)d_rbase, (const uint32_t*)d_blen, (const uint64_t*)d_boff,
+                             (uint32_t*)d_buckets, n_slots, d_jlist, small + SW_JOIN, d_compact, d_pbase, d_blk0, ctx->num_sms,
+                             ctx->stream, &nl));
+    } else {
+      // device-resident payload: join and observation are one pass over the bucket slots
+      Range r_obs(T_TREE_JOIN " / " T_OBSERVE_READS " / " T_EMIT_GENOTYPES);
+      CK(launch_call_pairs_reduce(R, S, X, C, P, D, (const int32_t*)d_rbase, (const uint32_t*)d_blen, (const uint64_t*)d_boff,
+                                  (uint32_t*)d_buckets, n_slots, ctx->num_sms, ctx->stream, &nl));
+    }
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
     if (fresh) {                            // the caller checks *h_slots against *slots_cap after its sync
       if (slots_cap) *slots_cap = work ? n_slots : SIZE_MAX;

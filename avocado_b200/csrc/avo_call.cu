@@ -79,23 +79,26 @@ __global__ void k_site_buckets(DReads R, DSites S_in, DIndex X, int32_t max_span
 // place of the read's seq_off while that site is classified.  PAIRS is a template parameter so that
 // the device-resident route compiles to a kernel that never looks at pair_blk0.
 
-template <bool PAIRS>
-__device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
-                             int32_t r, int32_t a, int32_t b, const int32_t* __restrict__ rbase,
-                             const uint64_t* __restrict__ boff, uint32_t* __restrict__ buckets,
-                             uint64_t n_slots, const uint32_t* __restrict__ pair_blk0) {
-  const MetaA ma = load_meta_a(R.meta, r);
-  const MetaB mb = load_meta_b(R.meta, r);
+// read_records calls emit(j, record) for EVERY site j of [a, b), record 0 where the read contributes none.
+// The read's record travels in: `ma` (its first 16 bytes), `nmf` (the word holding n_ops | mapq << 16 | flags << 24)
+// and w0, its first operator (0 when it has none) -- loaded by the caller as early as it knows the read.
+template <bool PAIRS, typename EmitF>
+__device__ __forceinline__ void read_records(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
+                                             const MetaA& ma, uint32_t nmf, uint32_t w0, int32_t a, int32_t b,
+                                             const uint32_t* __restrict__ pair_blk0, EmitF&& emit) {
+  const uint32_t n_ops = nmf & 0xFFFFu, flags = nmf >> 24;
+  auto none = [&]() { for (int32_t j = a; j < b; ++j) emit(j, 0u); };
   // observeRead throws for such reads (BG:385-391: skipped); no operators -> no observations
-  if ((mb.flags & AVO_READ_SKIP_CALL) || mb.n_ops == 0) return;
+  if ((flags & AVO_READ_SKIP_CALL) || n_ops == 0) { none(); return; }
   ReadCtx rc;
   rc.start = ma.start;
   rc.end = ma.end;
   rc.ob = ma.op_off;
-  rc.no = mb.n_ops;
+  rc.no = n_ops;
+  rc.w0 = w0;
   rc.sb = ma.seq_off;
-  rc.mapq = mb.mapq;
-  rc.fwd = !(mb.flags & AVO_READ_NEGATIVE_STRAND);
+  rc.mapq = (nmf >> 16) & 0xFFu;
+  rc.fwd = !(flags & AVO_READ_NEGATIVE_STRAND);
   auto classify_at = [&](int32_t j) {
     if (PAIRS) rc.sb = pair_blk0[j - a];
     return classify_site(R, rc, S, j);
@@ -107,19 +110,19 @@ __device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, co
   if (cached) {
     for (int j = 0; j < ns; ++j) {
       const Cls c = classify_at(a + j);
-      if (c.cat == CAT_EXC) return;                       // BG:385-391: the whole read is skipped
+      if (c.cat == CAT_EXC) { none(); return; }           // BG:385-391: the whole read is skipped
       cq[j] = (uint16_t)(c.cat | ((uint32_t)(c.q + 1) << 3));
     }
   } else {
     for (int j = 0; j < ns; ++j)
-      if (classify_at(a + j).cat == CAT_EXC) return;
+      if (classify_at(a + j).cat == CAT_EXC) { none(); return; }
   }
 
   const int mq = min(P.max_mapq, (int)rc.mapq);           // BG:452
   for (int32_t j = a; j < b; ++j) {
     Cls c;
     if (cached) { c.cat = cq[j - a] & 7u; c.q = (int32_t)(cq[j - a] >> 3) - 1; } else c = classify_at(j);
-    if (c.cat == CAT_NONE) continue;
+    if (c.cat == CAT_NONE) { emit(j, 0u); continue; }
     const int32_t js = __ldg(S.start + j), je = __ldg(S.end + j);
     if (c.cat == CAT_NONREF) {                            // BG:359-373 other-alt pass
       for (int32_t k = a; k < b; ++k) {
@@ -129,12 +132,26 @@ __device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, co
       }
     }
     const int q = (c.q < 0) ? P.max_quality : min(P.max_quality, c.q);  // BG:451 least() skips null
-    if (q < 1 || mq < 1) continue;                        // no such row in the score table: dropped
+    if (q < 1 || mq < 1) { emit(j, 0u); continue; }       // no such row in the score table: dropped
     const int cn = copy_number_for(C, P.base_ploidy, rc.start, rc.end, js, js + __ldg(S.ref_len + j));
+    emit(j, make_record(c.cat, rc.fwd, q, mq, cn - P.min_ploidy));
+  }
+}
+
+template <bool PAIRS>
+__device__ void observe_read(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
+                             int32_t r, int32_t a, int32_t b, const int32_t* __restrict__ rbase,
+                             const uint64_t* __restrict__ boff, uint32_t* __restrict__ buckets,
+                             uint64_t n_slots, const uint32_t* __restrict__ pair_blk0) {
+  const MetaA ma = load_meta_a(R.meta, r);
+  const uint32_t nmf = meta_nmf(R.meta, r);
+  const uint32_t w0 = (nmf & 0xFFFFu) ? __ldg(R.ops + ma.op_off) : 0u;
+  read_records<PAIRS>(R, S, C, P, ma, nmf, w0, a, b, pair_blk0, [&](int32_t j, uint32_t rec) {
+    if (!rec) return;                                     // (the buckets were cleared)
     // n_slots may be a guess carried over from the previous call (the host checks it afterwards)
     const uint64_t at = __ldg(boff + j) + (uint32_t)(r - __ldg(rbase + j));
-    if (at < n_slots) buckets[at] = make_record(c.cat, rc.fwd, q, mq, cn - P.min_ploidy);
-  }
+    if (at < n_slots) buckets[at] = rec;
+  });
 }
 
 struct JoinedRead { int32_t r, a, b; };
@@ -145,6 +162,17 @@ struct JoinedRead { int32_t r, a, b; };
 // (one global atomic per flush; the list order is irrelevant: every record has its own slot).
 // No block barrier: a CTA-wide append would put two barriers and a global atomic on the critical
 // path of every 512 reads.
+// sites that start in the index bins [lo, hi] touches, or an earlier site reaching past lo: [hLo, hHi)
+// holds every site with start in [lo, hi]; false when no site can overlap [lo, hi)
+__device__ __forceinline__ bool site_hint(const DSites& S, const DIndex& X, int32_t lo, int64_t hi, int32_t& hLo,
+                                          int32_t& hHi) {
+  hLo = (lo <= X.win0) ? S.c_lo : __ldg(X.sidx + idx_bin_floor(X, lo));
+  const int64_t d = hi - X.win0;
+  const int64_t k = d < 0 ? 0 : d / IDX_G + 1;
+  hHi = (k >= X.nb) ? S.c_hi : __ldg(X.sidx + (int32_t)k);
+  return hLo < hHi || (hLo > S.c_lo && __ldg(S.pme + hLo - 1) > lo);
+}
+
 constexpr int JOIN_THREADS = 256;
 constexpr int JOIN_WARPS = JOIN_THREADS / 32;
 constexpr int JOIN_FLUSH = 96;
@@ -169,14 +197,7 @@ k_call_join(DReads R, DSites S_in, DIndex X, int32_t max_span, JoinedRead* __res
     cnt = 0;
     __syncwarp();
   };
-  // sites that start in the index bins [lo, hi] touches, or an earlier site reaching past lo
-  auto may_join = [&](int32_t lo, int64_t hi, int32_t& hLo, int32_t& hHi) -> bool {
-    hLo = (lo <= X.win0) ? S.c_lo : __ldg(X.sidx + idx_bin_floor(X, lo));
-    const int64_t d = hi - X.win0;
-    const int64_t k = d < 0 ? 0 : d / IDX_G + 1;
-    hHi = (k >= X.nb) ? S.c_hi : __ldg(X.sidx + (int32_t)k);
-    return hLo < hHi || (hLo > S.c_lo && __ldg(S.pme + hLo - 1) > lo);
-  };
+  auto may_join = [&](int32_t lo, int64_t hi, int32_t& hLo, int32_t& hHi) -> bool { return site_hint(S, X, lo, hi, hLo, hHi); };
   const int64_t n_blocks = (R.n + 31) / 32;               // blocks of 32 consecutive reads
   const int64_t n_super = (n_blocks + 31) / 32;           // 32 blocks per warp iteration
   const int64_t stride = (int64_t)gridDim.x * JOIN_WARPS;
@@ -246,6 +267,102 @@ k_call_observe(DReads R, DSites S_in, DCnv C, DCallParams P, const JoinedRead* _
     const JoinedRead j = list[i];
     observe_read<GATHERED>(R, S, C, P, j.r, j.a, j.b, rbase, boff, buckets, n_slots,
                            GATHERED ? blk0 + pbase[i] : nullptr);
+  }
+}
+
+// Join + observation in one pass over the bucket SLOTS (device-resident batches).  Slot s of site j's bucket
+// belongs to read r = rbase[j] + (s - boff[j]): the thread of that slot tests the pair, runs Forest.get for
+// the read and writes the slot -- the record, or 0 -- so the buckets need no clearing, no list of joined
+// reads is built, the 25.6 M reads that touch no site are never looked at, and the lanes of a warp hold
+// consecutive reads of ONE site (coalesced records, the same control flow).  A read whose Forest range
+// [a, b) has several sites is classified against all of them by each of its (at most PAIR_SITES) slot
+// threads (the other-alt pass and the skipped-read rule need the read's other sites); past PAIR_SITES
+// the thread of the read's first site writes all of the read's slots and the others stand back.
+constexpr int PAIR_SITES = 4;
+
+// Forest.get for a read KNOWN to overlap site j: the fast path of forest_get (avo_device.cuh) found by
+// walking from j -- the first site with start >= rs lies at or just before j, the last with start < re
+// just after it -- instead of two binary searches; the literal replay where the fast path does not apply.
+__device__ __forceinline__ void forest_get_near(const DSites& S, const DIndex& X, int32_t c, int32_t rs, int32_t re,
+                                                int32_t j, int32_t& a, int32_t& b) {
+  if (__ldg(S.start + j) >= rs) {
+    int32_t i0 = j;
+    while (i0 > S.c_lo && __ldg(S.start + i0 - 1) >= rs) --i0;
+    if (!(i0 > S.c_lo && __ldg(S.pme + i0 - 1) > rs)) {
+      a = i0;
+      b = j + 1;
+      while (b < S.c_hi && __ldg(S.start + b) < re) ++b;
+      return;
+    }
+  }
+  int32_t hLo, hHi;
+  a = b = 0;
+  if (site_hint(S, X, rs, (int64_t)re, hLo, hHi)) forest_get(S, c, rs, re, hLo, hHi, a, b);
+}
+
+__global__ void __launch_bounds__(OBS_THREADS, AVO_CALL_MINB)
+k_call_pairs(DReads R, DSites S_in, DIndex X, DCnv C, DCallParams P, const int32_t* __restrict__ rbase,
+             const uint64_t* __restrict__ boff, uint32_t* __restrict__ buckets, uint64_t n_slots) {
+  const DSites S = resolve_sites(S_in);
+  // nothing to join; or the table did not fit its arrays (its index points past them: the host reruns)
+  if (S.c_hi <= S.c_lo || (S.hdr && S.hdr->n > S.cap)) return;
+  const uint64_t total = min((uint64_t)__ldg(boff + S.c_hi), n_slots);
+  const uint64_t stride = (uint64_t)gridDim.x * OBS_THREADS;
+  const int lane = threadIdx.x & 31;
+  // a warp takes 32 consecutive slots per iteration (the loop bound is the same for all of its lanes)
+  for (uint64_t s0 = (uint64_t)blockIdx.x * OBS_THREADS + (threadIdx.x & ~31); s0 < total; s0 += stride) {
+    // the last site whose bucket starts at or before s0: a 32-way search by the whole warp (three rounds
+    // of one load each for 32 k sites, instead of fifteen dependent loads per lane)
+    int32_t lo = S.c_lo, hi = S.c_hi;
+    while (hi - lo > 1) {
+      const int32_t step = (hi - lo + 31) >> 5;
+      const int32_t p = lo + lane * step;
+      const bool le = p < hi && __ldg(boff + p) <= s0;
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, le);          // lanes 0 .. t (boff[lo] <= s0 always)
+      const int t = 31 - __clz((int)m);
+      lo += t * step;
+      hi = min(hi, lo + step);
+    }
+    const uint64_t s = s0 + lane;
+    if (s >= total) continue;
+    // the lane's own site: a few steps further (32 slots rarely span more than two or three buckets)
+    int32_t j = lo;
+    for (int k = 0; k < 4 && j + 1 < S.c_hi && __ldg(boff + j + 1) <= s; ++k) ++j;
+    if (j + 1 < S.c_hi && __ldg(boff + j + 1) <= s) {
+      int32_t l2 = j + 1, h2 = S.c_hi;                    // many short or empty buckets: finish by bisection
+      while (h2 - l2 > 1) {
+        const int32_t mid = l2 + ((h2 - l2) >> 1);
+        if (__ldg(boff + mid) <= s) l2 = mid; else h2 = mid;
+      }
+      j = l2;
+    }
+    const int32_t r = __ldg(rbase + j) + (int32_t)(s - __ldg(boff + j));
+    uint32_t rec = 0;
+    bool mine = true;                                     // this thread writes slot s
+    if (r >= R.n) { buckets[s] = 0; continue; }
+    // the read's record and first operator are requested now: nearly every slot's read overlaps its site, and
+    // the Forest range below is found while they travel
+    const MetaA ma = load_meta_a(R.meta, r);
+    const uint32_t nmf = meta_nmf(R.meta, r);
+    const int32_t j_end = __ldg(S.end + j), j_start = __ldg(S.start + j);
+    const uint32_t w0 = (nmf & 0xFFFFu) ? __ldg(R.ops + ma.op_off) : 0u;
+    if (ma.start < j_end && ma.end > j_start) {
+      int32_t a, b;
+      forest_get_near(S, X, R.contig, ma.start, ma.end, j, a, b);
+      if (a <= j && j < b) {
+        if (b - a <= PAIR_SITES) {
+          read_records<false>(R, S, C, P, ma, nmf, w0, a, b, nullptr, [&](int32_t k, uint32_t v) { if (k == j) rec = v; });
+        } else {
+          mine = false;
+          if (a == j)
+            read_records<false>(R, S, C, P, ma, nmf, w0, a, b, nullptr, [&](int32_t k, uint32_t v) {
+              const uint64_t at = __ldg(boff + k) + (uint32_t)(r - __ldg(rbase + k));
+              if (at < n_slots) buckets[at] = v;
+            });
+        }
+      }
+    }
+    if (mine) buckets[s] = rec;
   }
 }
 
@@ -450,6 +567,24 @@ cudaError_t launch_call_join(const DReads& R, const DSites& S, const DIndex& X, 
   const int grid = (int)max((int64_t)1, min(want, (int64_t)num_sms * max(1, bps)));
   k_call_join<<<grid, JOIN_THREADS, 0, s>>>(R, S, X, max_span, (JoinedRead*)joined_list, d_counter);
   if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+// device-resident batches: join + observation over the bucket slots, then the per-site reduction
+cudaError_t launch_call_pairs_reduce(const DReads& R, const DSites& S, const DIndex& X, const DCnv& C, const DCallParams& P,
+                                     const DResults& out, const int32_t* rbase, const uint32_t* blen, const uint64_t* boff,
+                                     uint32_t* buckets, size_t n_slots, int num_sms, cudaStream_t s, int* n_launches) {
+  if (R.n == 0 || S.c_hi <= S.c_lo) return cudaSuccess;
+  int blocks_per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_call_pairs, OBS_THREADS, 0);
+  if (e != cudaSuccess) return e;
+  k_call_pairs<<<num_sms * max(1, blocks_per_sm), OBS_THREADS, 0, s>>>(R, S, X, C, P, rbase, boff, buckets, (uint64_t)n_slots);
+  const int32_t n = S.c_hi - S.c_lo;
+  if (P.ns <= 3)
+    k_call_reduce<3><<<(n + 127) / 128, 128, 0, s>>>(S, P, out, boff, blen, buckets, (uint64_t)n_slots);
+  else
+    k_call_reduce<NSMAX><<<(n + 127) / 128, 128, 0, s>>>(S, P, out, boff, blen, buckets, (uint64_t)n_slots);
+  if (n_launches) *n_launches += 2;
   return cudaGetLastError();
 }
 

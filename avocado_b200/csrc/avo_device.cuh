@@ -58,6 +58,10 @@ __device__ __forceinline__ MetaB load_meta_b(const avo_read_meta* __restrict__ m
   b.qhead = (uint32_t)v.z; b.l_seq = (uint32_t)v.w;
   return b;
 }
+// n_ops | mapq << 16 | flags << 24: the one word of the record's second half the call stage needs
+__device__ __forceinline__ uint32_t meta_nmf(const avo_read_meta* __restrict__ m, int64_t r) {
+  return (uint32_t)__ldg(reinterpret_cast<const int32_t*>(m + r) + 5);
+}
 __device__ __forceinline__ int32_t meta_start(const avo_read_meta* __restrict__ m, int64_t r) {
   return __ldg(&m[r].start);
 }

@@ -295,6 +295,9 @@ cudaError_t launch_call_gather_plan(const DReads& R, const DSites& S, const void
 cudaError_t launch_call_blocklist(const DReads& R, const void* joined_list, int32_t n_joined, const uint32_t* pbase,
                                   const uint32_t* nblk, const uint32_t* slot, const uint32_t* clo, uint32_t* idx,
                                   uint32_t* blk0, cudaStream_t s, int* n_launches);
+cudaError_t launch_call_pairs_reduce(const DReads& R, const DSites& S, const DIndex& X, const DCnv& C, const DCallParams& P,
+                                     const DResults& out, const int32_t* rbase, const uint32_t* blen, const uint64_t* boff,
+                                     uint32_t* buckets, size_t n_slots, int num_sms, cudaStream_t s, int* n_launches);
 cudaError_t launch_call_observe(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
                                 const DResults& out, const int32_t* rbase, const uint32_t* blen,
                                 const uint64_t* boff, uint32_t* buckets, size_t n_slots /* capacity of buckets */,

@@ -17,6 +17,7 @@ struct ReadCtx {
   uint32_t sb;  // first payload block of the read
   uint32_t ob;  // first op
   uint32_t no;  // number of ops
+  uint32_t w0;  // the first op (loaded with the record, ahead of the walk)
   uint32_t mapq;
   bool fwd;
 };
@@ -46,33 +47,31 @@ __device__ inline Cls classify_by_head(const DReads& R, const ReadCtx& rc, int32
   uint32_t head_at = 0;          // read index of the head's first base
   int head_len = 0;
   bool head_isref = false;
+  // The loop body has no branch on the operator kind (the lanes of a warp hold different kinds at the same
+  // k): every kind's overlap test is evaluated and the state is updated through selects.
   for (uint32_t k = 0; k < rc.no; ++k) {
-    const uint32_t op = __ldg(R.ops + rc.ob + k);
+    const uint32_t op = (k == 0) ? rc.w0 : __ldg(R.ops + rc.ob + k);
     const int len = (int)(op >> 4);
     const uint32_t code = op & 15u;
-    if (code == AVO_OP_SOFTCLIP) { ridx += len; continue; }             // Observer.scala:66-71
-    if (code == AVO_OP_HARDCLIP) continue;
-    if (code == AVO_OP_MATCH || code == AVO_OP_MISMATCH) {              // Observer.scala:72-92
-      const int32_t lo = max(pos, vs), hi = min(pos + len, ve);
-      if (lo < hi) {
-        if (n_obs == 0) { head_kind = 1; head_at = ridx + (uint32_t)(lo - pos); head_isref = (code == AVO_OP_MATCH); }
-        n_obs += hi - lo; n_nonempty += hi - lo;
-      }
-      pos += len; ridx += len;
-    } else if (code == AVO_OP_INS) {                                    // Observer.scala:93-118
-      if (pos - 1 < ve && pos > vs) {
-        if (n_obs == 0) { head_kind = 2; head_at = ridx; head_len = len; }
-        ++n_obs; ++n_nonempty;
-      }
-      ridx += len;
-    } else if (code == AVO_OP_DEL) {                                    // Observer.scala:119-138
-      if (pos < ve && pos + len > vs) {
-        if (n_obs == 0) head_kind = 3;
-        if (n_del == 0) first_del_w = len;
-        ++n_del; ++n_obs;
-      }
-      pos += len;
+    const bool isMX = code <= AVO_OP_MISMATCH, isI = code == AVO_OP_INS, isD = code == AVO_OP_DEL;
+    const int32_t lo = max(pos, vs), hi = min(pos + len, ve);
+    const bool hitMX = isMX && lo < hi;                                 // Observer.scala:72-92
+    const bool hitI = isI && pos - 1 < ve && pos > vs;                  // Observer.scala:93-118
+    const bool hitD = isD && pos < ve && pos + len > vs;                // Observer.scala:119-138
+    const bool hit = hitMX || hitI || hitD;
+    if (hit && n_obs == 0) {
+      head_kind = hitMX ? 1 : hitI ? 2 : 3;
+      head_at = ridx + (hitMX ? (uint32_t)(lo - pos) : 0u);
+      head_len = len;
+      head_isref = code == AVO_OP_MATCH;
     }
+    const int cnt = hitMX ? hi - lo : (int)hit;
+    n_obs += cnt;
+    n_nonempty += hitD ? 0 : cnt;
+    first_del_w = (hitD && n_del == 0) ? len : first_del_w;
+    n_del += (int)hitD;
+    pos += (isMX || isD) ? len : 0;
+    ridx += (isMX || isI || code == AVO_OP_SOFTCLIP) ? (uint32_t)len : 0u;      // Observer.scala:66-71: clips
     if (pos > ve) break;  // nothing later in the read can overlap the site
   }
   Cls out;

@@ -227,6 +227,7 @@ EXPORTED_SYMBOLS = [
     "avo_pack_wire", "avo_pack_wire6", "avo_pack_bounds", "avo_pack_reads", "avo_pack_reads_mt", "avo_pack_reads_device", "avo_synth_default_params",
     "avo_synth_host", "avo_synth_device", "avo_synth_text",
     "avo_merge_meta", "avo_shard_table_block_bytes", "avo_shard_rows_block_bytes", "avo_shard_discover", "avo_shard_call", "avo_shard_finish",
+    "avo_shard_call_direct", "avo_peer_alloc", "avo_peer_open", "avo_peer_close", "avo_peer_free",
 ]
 
 _lib = None
@@ -292,6 +293,12 @@ def load():
     lib.avo_shard_discover.argtypes = [P, C.POINTER(ReadBatchStruct), C.POINTER(ParamsStruct), C.POINTER(ShardPlanStruct), P]
     lib.avo_shard_call.argtypes = [P, C.POINTER(CnvStruct), C.POINTER(ParamsStruct), C.POINTER(ShardPlanStruct), P,
                                    C.POINTER(SitesOutStruct), P]
+    lib.avo_shard_call_direct.argtypes = [P, C.POINTER(CnvStruct), C.POINTER(ParamsStruct), C.POINTER(ShardPlanStruct), P,
+                                          C.POINTER(SitesOutStruct), P, C.POINTER(SiteResultsStruct)]
+    lib.avo_peer_alloc.argtypes = [P, C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.avo_peer_open.argtypes = [P, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.avo_peer_close.argtypes = [P, C.c_void_p]
+    lib.avo_peer_free.argtypes = [P, C.c_void_p]
     lib.avo_shard_finish.argtypes = [P, C.POINTER(ShardPlanStruct), P, P, C.POINTER(SitesOutStruct),
                                      C.POINTER(SiteResultsStruct), C.POINTER(ShardPlanStruct)]
     _lib = lib

@@ -1436,6 +1436,12 @@ int avo_shard_discover(avo_ctx* ctx, const avo_read_batch* reads, const avo_para
 
 int avo_shard_call(avo_ctx* ctx, const avo_cnv* cnv, const avo_params* params, const avo_shard_plan* pl,
                    const void* gathered_tables, avo_sites_out* gs, void* rows_block) {
+  return avo_shard_call_direct(ctx, cnv, params, pl, gathered_tables, gs, rows_block, nullptr);
+}
+
+int avo_shard_call_direct(avo_ctx* ctx, const avo_cnv* cnv, const avo_params* params, const avo_shard_plan* pl,
+                          const void* gathered_tables, avo_sites_out* gs, void* rows_block,
+                          const avo_site_results* root_rows) {
   if (!ctx) return AVO_E_INVALID;
   CK(cudaSetDevice(ctx->device));
   CKS(check_params(ctx, params));
@@ -1459,7 +1465,12 @@ int avo_shard_call(avo_ctx* ctx, const avo_cnv* cnv, const avo_params* params, c
   CKS(get_buf(ctx, SL_G_PME, (size_t)G.cap * 4, &q)); G.pme = (int32_t*)q;
   CKS(get_buf(ctx, SL_G_SIDX, (size_t)(nb + 1) * 4, &q)); G.sidx = (int32_t*)q;
   G.hdr = (DSiteHdr*)(small + SW_HDR2);
-  CK(launch_shard_concat(gathered_tables, pl->world, (int32_t)pl->site_cap, (int32_t)pl->allele_cap, G, ctx->num_sms, ctx->stream));
+  if (root_rows) {
+    CKS(check_results(ctx, root_rows));
+    if (root_rows->mem != AVO_MEM_DEVICE) return fail(ctx, AVO_E_INVALID, "root_rows must be device arrays (local or peer-mapped)");
+  }
+  CK(launch_shard_concat(gathered_tables, pl->world, (int32_t)pl->site_cap, (int32_t)pl->allele_cap, G, root_rows ? pl->rank : -1,
+                         ctx->num_sms, ctx->stream));
   DevSites& T = st.T_glob;
   T = DevSites();
   T.start = G.start; T.ref_len = G.ref_len; T.alt_len = G.alt_len; T.allele_off = G.allele_off; T.alleles4 = G.alleles4;
@@ -1472,8 +1483,10 @@ int avo_shard_call(avo_ctx* ctx, const avo_cnv* cnv, const avo_params* params, c
   }
   ctx->timing.n_launches += 2;
   // the call stage against the global table; rows into the context's block (host-style destination)
+  // (direct rows: the reduction stores this rank's owned rows into root_rows, local or peer memory)
   avo_site_results fake{};
-  fake.mem = AVO_MEM_HOST; fake.n_states = pl->n_states; fake.n_sites = T.cap;
+  if (root_rows) fake = *root_rows;
+  else { fake.mem = AVO_MEM_HOST; fake.n_states = pl->n_states; fake.n_sites = T.cap; }
   uint64_t* h_slots = reinterpret_cast<uint64_t*>(ctx->h_small + 48);
   *h_slots = 0;
   CKS(call_internal(ctx, st.R, st.hs, T, cnv, params, true, &fake, nullptr, &st.D, &st.slots_cap));
@@ -1482,9 +1495,46 @@ int avo_shard_call(avo_ctx* ctx, const avo_cnv* cnv, const avo_params* params, c
   const uint64_t* d_slots = st.slots_cap != SIZE_MAX ? (const uint64_t*)d_boff + std::min<int64_t>(T.cap, fake.n_sites) : nullptr;
   CK(launch_shard_pack_rows(st.D, st.ns, gathered_tables, pl->world, pl->rank, (int32_t)pl->site_cap, (int32_t)pl->allele_cap,
                             d_slots, st.slots_cap == SIZE_MAX ? 0 : (uint64_t)st.slots_cap, rows_block, (int32_t)pl->row_cap,
-                            ctx->num_sms, ctx->stream));
+                            root_rows != nullptr, ctx->num_sms, ctx->stream));
   ctx->timing.n_launches += 1;
   st.phase = 2;
+  return AVO_OK;
+}
+
+int avo_peer_alloc(avo_ctx* ctx, int64_t bytes, void** ptr, unsigned char* handle) {
+  if (!ctx || !ptr || !handle || bytes <= 0) return ctx ? fail(ctx, AVO_E_INVALID, "bad argument") : AVO_E_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == AVO_PEER_HANDLE_BYTES, "CUDA IPC handle size");
+  CK(cudaSetDevice(ctx->device));
+  *ptr = nullptr;
+  CK(cudaMalloc(ptr, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) { cudaFree(*ptr); *ptr = nullptr; CK(e); }
+  memcpy(handle, &h, sizeof h);
+  return AVO_OK;
+}
+
+int avo_peer_open(avo_ctx* ctx, const unsigned char* handle, void** ptr) {
+  if (!ctx || !ptr || !handle) return ctx ? fail(ctx, AVO_E_INVALID, "bad argument") : AVO_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  *ptr = nullptr;
+  CK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return AVO_OK;
+}
+
+int avo_peer_close(avo_ctx* ctx, void* ptr) {
+  if (!ctx) return AVO_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (ptr) CK(cudaIpcCloseMemHandle(ptr));
+  return AVO_OK;
+}
+
+int avo_peer_free(avo_ctx* ctx, void* ptr) {
+  if (!ctx) return AVO_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (ptr) CK(cudaFree(ptr));
   return AVO_OK;
 }
 

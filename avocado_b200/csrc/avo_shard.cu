@@ -78,7 +78,8 @@ cudaError_t launch_shard_owned(const ShardTableIn& T, int32_t own_lo, int32_t ow
 
 // ---- the global table from the gathered blocks (rank order = position order) -----------------------
 __global__ void __launch_bounds__(256)
-k_shard_concat(const unsigned char* __restrict__ gathered, int32_t world, int32_t cap, int32_t acap, DSiteTableOut G) {
+k_shard_concat(const unsigned char* __restrict__ gathered, int32_t world, int32_t cap, int32_t acap, DSiteTableOut G,
+               int32_t own_rank /* >= 0: the per-site reduction writes only that rank's rows (direct rows) */) {
   const size_t bb = shard_table_bytes(cap, acap);
   // every thread adds up the (few) headers
   int32_t row0[AVO_MAX_SHARDS + 1], carry[AVO_MAX_SHARDS + 1];
@@ -127,14 +128,17 @@ k_shard_concat(const unsigned char* __restrict__ gathered, int32_t world, int32_
     int32_t mp = 1;                                              // TreeRegionJoin.scala:66-72
     while (!(2 * (int64_t)mp >= (int64_t)n)) mp *= 2;
     h.midpoint = mp;
-    h.reserved[0] = flags; h.reserved[1] = h.reserved[2] = 0;
+    h.reserved[0] = flags;
+    // [reserved[1], reserved[2] - 1): the rows the call stage's reduction may write; reserved[2] = 0: all
+    h.reserved[1] = own_rank >= 0 ? row0[own_rank] : 0;
+    h.reserved[2] = own_rank >= 0 ? row0[own_rank + 1] + 1 : 0;
     *G.hdr = h;
   }
 }
 
 cudaError_t launch_shard_concat(const void* gathered, int32_t world, int32_t cap, int32_t acap, const DSiteTableOut& G,
-                                int num_sms, cudaStream_t s) {
-  k_shard_concat<<<num_sms, 256, 0, s>>>((const unsigned char*)gathered, world, cap, acap, G);
+                                int32_t own_rank, int num_sms, cudaStream_t s) {
+  k_shard_concat<<<num_sms, 256, 0, s>>>((const unsigned char*)gathered, world, cap, acap, G, own_rank);
   return cudaGetLastError();
 }
 
@@ -186,7 +190,7 @@ size_t shard_table_block_bytes(int64_t cap, int64_t acap) { return shard_table_b
 __global__ void __launch_bounds__(256)
 k_shard_pack_rows(DResults D, int ns, const unsigned char* __restrict__ gathered_tables, int32_t world, int32_t rank,
                   int32_t tcap, int32_t tacap, const uint64_t* __restrict__ slots_used, uint64_t slots_cap,
-                  unsigned char* __restrict__ block, int32_t rcap) {
+                  unsigned char* __restrict__ block, int32_t rcap, int32_t header_only) {
   const size_t bb = shard_table_bytes(tcap, tacap);
   int32_t A = 0, n = 0;
   for (int r = 0; r <= rank; ++r) {
@@ -197,9 +201,11 @@ k_shard_pack_rows(DResults D, int ns, const unsigned char* __restrict__ gathered
   ShardHdr* H = reinterpret_cast<ShardHdr*>(block);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     H->n_rows = n; H->n_bytes = 0; H->max_end = 0;
-    H->flags = (n > rcap ? SHARD_BLOCK_FULL : 0) | ((slots_used && *slots_used > slots_cap) ? SHARD_RETRY : 0);
+    H->flags = (n > rcap ? SHARD_BLOCK_FULL : 0) | ((slots_used && *slots_used > slots_cap) ? SHARD_RETRY : 0) |
+               (header_only ? SHARD_ROWS_DIRECT : 0);
     H->reserved[0] = H->reserved[1] = H->reserved[2] = H->reserved[3] = 0;
   }
+  if (header_only) return;            // the rows went straight to their destination (avo_shard_call_direct)
   const void* src[AVO_RESULT_COLUMNS];
   int width[AVO_RESULT_COLUMNS];
   shard_row_columns(D, ns, src, width);
@@ -223,9 +229,10 @@ k_shard_pack_rows(DResults D, int ns, const unsigned char* __restrict__ gathered
 
 cudaError_t launch_shard_pack_rows(const DResults& D, int ns, const void* gathered_tables, int32_t world, int32_t rank,
                                    int32_t tcap, int32_t tacap, const uint64_t* slots_used, uint64_t slots_cap, void* block,
-                                   int32_t rcap, int num_sms, cudaStream_t s) {
-  k_shard_pack_rows<<<2 * num_sms, 256, 0, s>>>(D, ns, (const unsigned char*)gathered_tables, world, rank, tcap, tacap,
-                                               slots_used, slots_cap, (unsigned char*)block, rcap);
+                                   int32_t rcap, bool header_only, int num_sms, cudaStream_t s) {
+  k_shard_pack_rows<<<header_only ? 1 : 2 * num_sms, 256, 0, s>>>(D, ns, (const unsigned char*)gathered_tables, world, rank, tcap,
+                                                                 tacap, slots_used, slots_cap, (unsigned char*)block, rcap,
+                                                                 header_only ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -252,7 +259,7 @@ k_shard_unpack_rows(const unsigned char* __restrict__ gathered_rows, const unsig
   }
   const int32_t n = min(min(reinterpret_cast<const ShardHdr*>(blk)->n_rows, rcap), n_table);
   const int64_t rows = max((int64_t)0, min((int64_t)n, out_rows - A));
-  if (rows == 0) return;
+  if (rows == 0 || (reinterpret_cast<const ShardHdr*>(blk)->flags & SHARD_ROWS_DIRECT)) return;
   const void* dstp[AVO_RESULT_COLUMNS];
   int width[AVO_RESULT_COLUMNS];
   shard_row_columns(O, ns, dstp, width);

@@ -143,7 +143,7 @@ class ShardedPipeline:
 
     def __init__(self, ctx, rank: int, world: int, own_lo: int, own_hi: int, ploidy: int = 2, site_cap: int = 1 << 15,
                  allele_cap: int = 1 << 17, global_cap: Optional[int] = None, gather=None, group=None, stream=None,
-                 rows_to: str = "all"):
+                 rows_to: str = "all", direct_root=None):
         import torch
         from . import _lib as L
         self.ctx, self.L, self.torch = ctx, L, torch
@@ -158,8 +158,17 @@ class ShardedPipeline:
         # "all": every rank ends with every row (all-gather of the rows blocks).  "root": the rows are
         # gathered to rank 0 only (the driver's `collect`); the other ranks all-gather just the 32-byte
         # headers and end with the global table and their OWN rows.
-        assert rows_to in ("all", "root")
-        self.rows_to = rows_to if gather is None else "all"
+        # "direct": nothing is gathered but 32-byte headers -- every rank's per-site reduction stores its owned
+        # rows straight into rank 0's result columns over NVLink (avo_shard_call_direct; the columns live in a
+        # CUDA-IPC block the other ranks map).  Rank 0 ends with every row, the others with the table.
+        # `direct_root` (tests: several ranks emulated in ONE process): rank 0's pipeline, whose block the
+        # other ranks then address directly (rank 0 itself passes True).
+        assert rows_to in ("all", "root", "direct")
+        self.rows_to = rows_to if (gather is None or rows_to == "direct") else "all"
+        self._emul_root = direct_root if direct_root is not True else None
+        self._emulated = direct_root is not None
+        self._block = None            # rank 0: the peer-visible block; others: its mapping
+        self._block_for = None
         self.nccl_bytes = 0
         # the phases and the collectives are ordered on ONE stream of the pipeline's own (the context's
         # default is a stream torch does not know; torch's default stream has no handle to pass)
@@ -172,19 +181,102 @@ class ShardedPipeline:
         dist.all_gather_into_tensor(out, inp, group=self.group)
 
     def _gather_rows(self):
-        """The second collective: the rows blocks to every rank, or to rank 0 (+ the headers to everyone)."""
+        """The second collective: the rows blocks to every rank, or to rank 0 (+ the headers to everyone), or
+        the headers alone (direct rows)."""
         if self.rows_to == "all":
             self.gather(self.r_all, self.r_send)
             return
         import torch.distributed as dist
         torch, p, W = self.torch, self.plan, self.plan.world
         dist.all_gather_into_tensor(self.rh_all, self.r_send[:32], group=self.group)
+        if self.rows_to == "direct":
+            self._place_headers()
+            return
         blocks = self.r_all.view(W, self.rb)
         if p.rank == 0:
             dist.gather(self.r_send, gather_list=list(blocks.unbind(0)), dst=0, group=self.group)
         else:
             dist.gather(self.r_send, dst=0, group=self.group)
             self._place_own_rows()
+
+    def _place_headers(self):
+        """Direct rows: the gathered headers (self.rh_all) stand in for the rows blocks."""
+        W = self.plan.world
+        self.r_all.view(W, self.rb)[:, :32].copy_(self.rh_all.view(W, 32))
+
+    # ---- direct rows: rank 0's result columns in a block the other ranks can store into -------------------
+    def _results_layout(self):
+        offs, o = {}, 0
+        for name, dt, w in self.L.RESULT_COLUMNS:
+            width = self.plan.n_states if w == "ns" else w
+            offs[name] = o
+            o += (max(self.gcap * width, 1) * np.dtype(dt).itemsize + 255) // 256 * 256
+        return offs, o
+
+    def _results_at(self, base):
+        res = self.L.SiteResultsStruct()
+        res.n_sites, res.n_states, res.mem = self.gcap, self.plan.n_states, self.L.MEM_DEVICE
+        offs, _ = self._results_layout()
+        for name, off in offs.items():
+            setattr(res, name, base + off)
+        return res
+
+    def _direct_release(self):
+        import ctypes as C
+        if self._block is None:
+            return
+        ctx, lib = self.ctx, self.ctx.lib
+        if not self._emulated and self.plan.world > 1:
+            import torch.distributed as dist
+            self.stream.synchronize()
+            if self.plan.rank != 0:
+                ctx._check(lib.avo_peer_close(ctx.h, C.c_void_p(self._block)))
+            dist.barrier(group=self.group)           # every mapping is gone before the owner frees
+        if self.plan.rank == 0:
+            self.torch.cuda.synchronize()
+            ctx._check(lib.avo_peer_free(ctx.h, C.c_void_p(self._block)))
+        self._block = None
+
+    def _direct_setup(self):
+        import ctypes as C
+        ctx, lib, p, torch = self.ctx, self.ctx.lib, self.plan, self.torch
+        self._direct_release()
+        offs, total = self._results_layout()
+        handle = C.create_string_buffer(64)
+        ptr = C.c_void_p()
+        if p.rank == 0:
+            ctx._check(lib.avo_peer_alloc(ctx.h, total, C.byref(ptr), handle))
+            self._block = ptr.value
+        if not self._emulated and p.world > 1:
+            import torch.distributed as dist
+            obj = [handle.raw if p.rank == 0 else None]
+            dist.broadcast_object_list(obj, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                                       group=self.group)
+            if p.rank != 0:
+                ctx._check(lib.avo_peer_open(ctx.h, obj[0], C.byref(ptr)))
+                self._block = ptr.value
+        self.cols = {}
+        if p.rank == 0:
+            class _Raw:                                  # the block as a torch tensor (no copy)
+                pass
+            raw = _Raw()
+            raw.__cuda_array_interface__ = {"shape": (total,), "typestr": "|u1", "data": (self._block, False), "version": 2}
+            whole = torch.as_tensor(raw, device=self.dev)
+            for name, dt, w in self.L.RESULT_COLUMNS:
+                width = p.n_states if w == "ns" else w
+                nbytes = max(self.gcap * width, 1) * np.dtype(dt).itemsize
+                self.cols[name] = whole[offs[name]:offs[name] + nbytes].view(getattr(torch, dt))
+            self.res = self._results_at(self._block)
+            self._block_for = self._block
+        elif not self._emulated:
+            self.res = self._results_at(self._block)
+            self._block_for = self._block
+        else:
+            self.res, self._block_for = None, None       # bound to the root's block at call time
+
+    def close(self):
+        """Releases the peer-visible block of rows_to="direct" (collective: every rank calls it)."""
+        self._direct_release()
 
     def _place_own_rows(self):
         """A rank that is not the root of the rows gather: its own block in place; of the other ranks only
@@ -217,7 +309,10 @@ class ShardedPipeline:
         self.sites = dict(start=mk(self.gcap, np.int32), ref_len=mk(self.gcap, np.int32), alt_len=mk(self.gcap, np.int32),
                           allele_off=mk(self.gcap + 1, np.uint32), alleles4=mk(self.gacap // 2 + 16, np.uint8),
                           count=mk(self.gcap, np.int32))
-        self.res, self.cols = self.ctx._alloc_results(self.gcap, p.n_states, self.dev)
+        if self.rows_to == "direct":
+            self._direct_setup()
+        else:
+            self.res, self.cols = self.ctx._alloc_results(self.gcap, p.n_states, self.dev)
         self._views = None
 
     # ---- the three phases (step() runs them around the two collectives; tests drive them by hand) ----
@@ -242,6 +337,14 @@ class ShardedPipeline:
         for k, a in self.sites.items():
             setattr(out, k, _ptr(a))
         self._out = out
+        if self.rows_to == "direct":
+            if self._emul_root is not None and self._block_for != self._emul_root._block:
+                self._block_for = self._emul_root._block           # (tests) the root pipeline's block, same process
+                self.res = self._results_at(self._block_for)
+            self.res.n_sites = self.gcap
+            ctx._check(ctx.lib.avo_shard_call_direct(ctx.h, None, C.byref(self._params), C.byref(p), self.t_all.data_ptr(),
+                                                     C.byref(out), self.r_send.data_ptr(), C.byref(self.res)))
+            return
         self.res.n_sites = self.gcap
         ctx._check(ctx.lib.avo_shard_call(ctx.h, None, C.byref(self._params), C.byref(p), self.t_all.data_ptr(),
                                           C.byref(out), self.r_send.data_ptr()))
@@ -255,7 +358,8 @@ class ShardedPipeline:
         rc = ctx.lib.avo_shard_finish(ctx.h, C.byref(p), self.t_all.data_ptr(), self.r_all.data_ptr(), C.byref(out),
                                       C.byref(self.res), C.byref(need))
         # bytes this rank receives per step
-        self.nccl_bytes = self.tb * p.world + (self.rb * p.world if (self.rows_to == "all" or p.rank == 0) else 32 * p.world)
+        rows_in = self.rows_to == "all" or (self.rows_to == "root" and p.rank == 0)
+        self.nccl_bytes = self.tb * p.world + (self.rb * p.world if rows_in else 32 * p.world)
         if rc == AVO_E_RETRY:
             return None
         if rc == AVO_E_CAPACITY:           # the same answer on every rank: all of them grow and run again
@@ -271,6 +375,8 @@ class ShardedPipeline:
                           s["alleles4"][:(nn + 1) // 2 or 1], None, s["count"][:n])
         cols = {}
         for name, dt, w in self.L.RESULT_COLUMNS:
+            if name not in self.cols:              # direct rows: only rank 0 holds them
+                continue
             width = p.n_states if w == "ns" else w
             a = self.cols[name][:n * width]
             cols[name] = a.reshape(n, width) if width != 1 else a

@@ -10,10 +10,11 @@ BASELINE.json configs[1] shape per GPU: single-sample 60x chr20 (64 Mb), 150 bp 
   value     reads/s with the packed batch already resident in HBM (device pointers through the C ABI).
             N = 1: avo_discover_and_call, one launch chain, no host round trip.  N > 1 (torchrun): the
             genome is N times larger, cut into N regions WITH read-overlap halos; every step runs the
-            region-sharded path (avo_shard_discover / _call / _finish around two NCCL collectives: an
-            all-gather of the owned slice of every rank's site table, then a gather of the owned result
-            rows to rank 0 plus their 32-byte headers to every rank), so the collectives are inside the
-            timed region; every rank ends with the global table, rank 0 with all rows.
+            region-sharded path (avo_shard_discover / _call_direct / _finish): an NCCL all-gather of the
+            owned slice of every rank's site table; then every rank's per-site reduction stores the rows
+            of its owned sites straight into rank 0's result columns over NVLink peer memory, and only
+            32-byte headers are all-gathered.  Both exchanges are inside the timed region; every rank
+            ends with the global table, rank 0 with all rows.  (AVO_ROWS_TO=root|all: NCCL gathers.)
   e2e       the same metric from HOST buffers holding what the reference's job holds: AlignmentRecord
             TEXT columns (CIGAR, MD, sequence, qualities) in pinned memory -> H2D -> device packer
             (avo_pack_reads_device) -> avo_discover_and_call -> D2H of the site table and every result
@@ -205,8 +206,10 @@ def run_reference(args):
 
 def config_dict(args, per, contig, world):
     par = ("one GPU" if world == 1 else
-           "region-sharded x%d with read-overlap halos: NCCL all-gather of the owned site-table slices, then a gather of the "
-           "owned result rows to rank 0, both inside the timed step; every rank ends with the global table, rank 0 with all rows" % world)
+           "region-sharded x%d with read-overlap halos: NCCL all-gather of the owned site-table slices; the result rows of the "
+           "owned sites are stored by the kernel that computes them straight into rank 0's columns over NVLink peer memory "
+           "(CUDA IPC), and only their 32-byte headers are all-gathered; all inside the timed step; every rank ends with the "
+           "global table, rank 0 with all rows" % world)
     return {"workload": "single-sample germline discoverAndCall, synthetic 60x chr20-shaped (%.0f Mb, %d x 150 bp reads) per GPU"
                         % (contig / 1e6, per),
             "reads_per_gpu": per, "contig_mb_per_gpu": contig / 1e6, "read_len": 150, "ploidy": 2,
@@ -377,7 +380,7 @@ def main():
         span = int((dev.meta[:dev.n_reads * 32].view(torch.int32).view(-1, 8)[:, 1] - starts).max().item())
         assert rank == 0 or int(starts[0].item()) <= own_lo - span, "halo too short for the batch's longest read span"
         pipe = ShardedPipeline(ctx, rank, world, own_lo, own_hi, site_cap=max(1 << 12, per // 256), allele_cap=max(1 << 14, per // 64),
-                               stream=stream, rows_to="root")
+                               stream=stream, rows_to=os.environ.get("AVO_ROWS_TO", "direct"))
 
     def step_device():
         if pipe is not None:
@@ -408,8 +411,9 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     n_sites_dev = sites.n
-    emitted_dev = int(cols["emitted"].sum().item())
-    pairs_dev = int(cols["total_cov"].sum().item())     # (read, site) observations that were scored
+    # (region-sharded steps with direct rows: only rank 0 holds the result columns)
+    emitted_dev = int(cols["emitted"].sum().item()) if "emitted" in cols else -1
+    pairs_dev = int(cols["total_cov"].sum().item()) if "total_cov" in cols else -1     # (read, site) observations that were scored
     t_dev = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if use_dist:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
@@ -458,8 +462,9 @@ def main():
         sharding = {"halo_reads_before": halo_lo, "halo_reads_after": halo_hi, "nccl_bytes_received_per_rank_per_step": int(pipe.nccl_bytes),
                     "table_block_bytes": int(pipe.tb), "rows_block_bytes": int(pipe.rb), "collectives_per_step": 2,
                     "rows_to": pipe.rows_to, "phases_ms_rank0": {k: round(v, 4) for k, v in phases.items()},
-                    "note": "all_gather_into_tensor of the owned table slices; gather of the owned result rows to rank 0 and an all-gather "
-                            "of their 32-byte headers (the byte count is rank 0's); no other exchange, one host synchronisation per step"}
+                    "note": "all_gather_into_tensor of the owned table slices and of 32-byte headers; rows_to=direct: the result rows reach "
+                            "rank 0 as peer-memory stores of k_call_reduce (not counted in the NCCL bytes), root / all: NCCL gather / "
+                            "all-gather of the rows blocks; one host synchronisation per step"}
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------
     e2e = None

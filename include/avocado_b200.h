@@ -370,6 +370,30 @@ int avo_shard_finish(avo_ctx* ctx, const avo_shard_plan* plan, const void* gathe
                      const void* gathered_rows, avo_sites_out* global_sites, avo_site_results* global_results,
                      avo_shard_plan* needed);
 
+/* The same step with the rows written where they are wanted, over NVLink, by the kernel that computes
+ * them: `root_rows` are the global result columns of ONE rank (the root), as device pointers valid on
+ * THIS rank's GPU -- the root's own arrays on the root, a peer mapping of them elsewhere (avo_peer_open).
+ * The call stage's per-site reduction stores this rank's OWNED rows straight into them at their global
+ * row numbers (known on the device from the gathered table headers); no rows travel through rows_block,
+ * whose 32-byte header (flags) is all the framework still gathers -- to every rank -- before
+ * avo_shard_finish.  That collective, ordered after this call on every rank's stream, is also what tells
+ * the root that the peers' stores have landed.  The root must not hand the rows of a step to anyone who
+ * still reads them when it enters the next step's first all-gather. */
+int avo_shard_call_direct(avo_ctx* ctx, const avo_cnv* cnv, const avo_params* params, const avo_shard_plan* plan,
+                          const void* gathered_tables, avo_sites_out* global_sites, void* rows_block,
+                          const avo_site_results* root_rows);
+
+/* Device memory another process of the node can map (CUDA IPC; what the root's result columns live in
+ * for avo_shard_call_direct).  avo_peer_alloc returns the block and a 64-byte handle to send to the other
+ * processes (any channel); avo_peer_open maps the block of a handle on this context's GPU (peer access
+ * over NVLink is enabled on first use); avo_peer_close / avo_peer_free undo them -- every peer closes
+ * before the owner frees. */
+enum { AVO_PEER_HANDLE_BYTES = 64 };
+int avo_peer_alloc(avo_ctx* ctx, int64_t bytes, void** ptr, unsigned char* handle);
+int avo_peer_open(avo_ctx* ctx, const unsigned char* handle, void** ptr);
+int avo_peer_close(avo_ctx* ctx, void* ptr);
+int avo_peer_free(avo_ctx* ctx, void* ptr);
+
 /* ---- scoreAllSites (gVCF mode) ---------------------------------------------------------------- */
 /* Reference-model rows of BiallelicGenotyper.call(scoreAllSites = true) (BG:223-275, 299-306): one
  * row per reference position that an observation of a joined read reaches without overlapping

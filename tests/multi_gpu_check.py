@@ -68,6 +68,19 @@ def main():
         m = np.repeat(own, per) if per > 1 else own
         assert np.array_equal(cols_r[k].cpu().numpy().ravel()[m], v.ravel()[m], equal_nan=True), "root-gather column %s differs on rank %d" % (k, rank)
     assert rank == 0 or pipe_r.nccl_bytes < nccl_bytes
+    # and with no rows gathered at all: every rank stores its owned rows into rank 0's columns over NVLink
+    pipe_d = ShardedPipeline(ctx, rank, world, max(sh.lo, -(1 << 31) + 1), min(sh.hi, (1 << 31) - 1),
+                             site_cap=256, allele_cap=256, rows_to="direct")
+    for _ in range(4):
+        table_d, cols_d = pipe_d.step(mine, phred=25, min_obs=5)
+    assert table_d.n == t1.n and np.array_equal(table_d.to_host().start, st)
+    if rank == 0:
+        for k, v in c1.items():
+            assert np.array_equal(cols_d[k].cpu().numpy(), np.asarray(v), equal_nan=True), "direct rows: column %s differs" % k
+    else:
+        assert cols_d == {}
+    assert pipe_d.nccl_bytes <= pipe_r.nccl_bytes and (rank != 0 or pipe_d.nccl_bytes < pipe_r.nccl_bytes or world == 1)
+    pipe_d.close()
 
     # ---- (2) sample-sharded joint calling ------------------------------------------------------
     rng = np.random.default_rng(11)

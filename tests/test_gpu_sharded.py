@@ -22,7 +22,9 @@ def run_emulated(whole, world, phred, min_obs, site_cap, allele_cap, global_cap=
             lo = max(sh.lo, -(1 << 31) + 1)
             hi = min(sh.hi, (1 << 31) - 1)
             pipes.append(ShardedPipeline(ctxs[sh.rank], sh.rank, world, lo, hi, site_cap=site_cap, allele_cap=allele_cap,
-                                         global_cap=global_cap, gather=lambda out, inp: None, stream=stream))
+                                         global_cap=global_cap, gather=lambda out, inp: None, stream=stream,
+                                         rows_to="direct" if rows_to == "direct" else "all",
+                                         direct_root=(pipes[0] if pipes else True) if rows_to == "direct" else None))
             batches.append(whole.slice(sh.read_lo, sh.read_hi).to_device("cuda:0"))
         tries = 0
         while True:
@@ -38,7 +40,10 @@ def run_emulated(whole, world, phred, min_obs, site_cap, allele_cap, global_cap=
                 allr = torch.cat([p.r_send for p in pipes])
                 got = []
                 for p in pipes:
-                    if rows_to == "all" or p.plan.rank == 0:
+                    if rows_to == "direct":         # only the 32-byte headers are gathered; the rows are already in place
+                        p.rh_all.copy_(torch.cat([q.r_send[:32] for q in pipes]))
+                        p._place_headers()
+                    elif rows_to == "all" or p.plan.rank == 0:
                         p.r_all.copy_(allr)
                     else:                       # gather-to-root: the others see only the 32-byte headers
                         p.r_all.fill_(0xEE)
@@ -54,6 +59,9 @@ def run_emulated(whole, world, phred, min_obs, site_cap, allele_cap, global_cap=
             out.append((table.to_host(), {k: v.cpu().numpy() for k, v in cols.items()}))
         return out, tries, shards
     finally:
+        if rows_to == "direct":
+            for p in reversed(pipes):
+                p.close()
         for c in ctxs:
             c.close()
 
@@ -108,6 +116,30 @@ def test_rows_gathered_to_the_root_only():
             per = v.size // t1.n
             m = np.repeat(own, per) if per > 1 else own
             assert np.array_equal(cols[k].ravel()[m], v.ravel()[m], equal_nan=True), "column %s differs on rank %d" % (k, sh.rank)
+
+
+def test_rows_stored_directly_into_the_root_columns():
+    """rows_to="direct" (avo_shard_call_direct): every rank's reduction writes its owned rows into rank 0's
+    result columns; rank 0 ends with every row, bit for bit, with nothing gathered but headers."""
+    from avocado_b200 import batch as B
+    from avocado_b200.genotyping import Context
+    p = B.synth_params(seed=35, n_reads_total=60000, contig_len=300000, first_pos=10000)
+    whole = B.synth_host(p)
+    ctx = Context(0)
+    try:
+        t1, c1 = ctx.discover_and_call_packed(whole, phred=25, min_obs=5)
+    finally:
+        ctx.close()
+    for world, cap in ((4, 64), (3, 1 << 12)):
+        got, tries, shards = run_emulated(whole, world, 25, 5, cap, cap, rows_to="direct")
+        assert (tries > 1) == (cap == 64)
+        for rank, (table, cols) in enumerate(got):
+            assert table.n == t1.n and np.array_equal(np.asarray(table.start), np.asarray(t1.start))
+            if rank:
+                assert cols == {}
+                continue
+            for k, v in c1.items():
+                assert np.array_equal(cols[k], np.asarray(v), equal_nan=True), "column %s differs" % k
 
 
 def test_sharded_forest_quirk_across_the_boundary():

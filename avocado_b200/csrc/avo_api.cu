@@ -1469,8 +1469,7 @@ int avo_shard_call_direct(avo_ctx* ctx, const avo_cnv* cnv, const avo_params* pa
     CKS(check_results(ctx, root_rows));
     if (root_rows->mem != AVO_MEM_DEVICE) return fail(ctx, AVO_E_INVALID, "root_rows must be device arrays (local or peer-mapped)");
   }
-  CK(launch_shard_concat(gathered_tables, pl->world, (int32_t)pl->site_cap, (int32_t)pl->allele_cap, G, root_rows ? pl->rank : -1,
-                         ctx->num_sms, ctx->stream));
+  CK(launch_shard_concat(gathered_tables, pl->world, (int32_t)pl->site_cap, (int32_t)pl->allele_cap, G, ctx->num_sms, ctx->stream));
   DevSites& T = st.T_glob;
   T = DevSites();
   T.start = G.start; T.ref_len = G.ref_len; T.alt_len = G.alt_len; T.allele_off = G.allele_off; T.alleles4 = G.alleles4;
@@ -1483,19 +1482,28 @@ int avo_shard_call_direct(avo_ctx* ctx, const avo_cnv* cnv, const avo_params* pa
   }
   ctx->timing.n_launches += 2;
   // the call stage against the global table; rows into the context's block (host-style destination)
-  // (direct rows: the reduction stores this rank's owned rows into root_rows, local or peer memory)
   avo_site_results fake{};
-  if (root_rows) fake = *root_rows;
-  else { fake.mem = AVO_MEM_HOST; fake.n_states = pl->n_states; fake.n_sites = T.cap; }
+  fake.mem = AVO_MEM_HOST; fake.n_states = pl->n_states; fake.n_sites = T.cap;
   uint64_t* h_slots = reinterpret_cast<uint64_t*>(ctx->h_small + 48);
   *h_slots = 0;
   CKS(call_internal(ctx, st.R, st.hs, T, cnv, params, true, &fake, nullptr, &st.D, &st.slots_cap));
   st.ns = st.D.ns;
+  DResults to{};                 // direct rows: the owned rows go from the context's block into root_rows, local or peer memory
+  if (root_rows) {
+    if (root_rows->n_states != st.ns) return fail(ctx, AVO_E_INVALID, "root_rows->n_states must be %d", st.ns);
+    const avo_site_results* g = root_rows;
+    to.ns = st.ns;
+    to.emitted = g->emitted; to.allele_fwd = g->allele_fwd; to.other_fwd = g->other_fwd; to.allele_cov = g->allele_cov;
+    to.other_cov = g->other_cov; to.total_cov = g->total_cov; to.square_mapq = g->square_mapq; to.ref_ll = g->ref_ll;
+    to.allele_ll = g->allele_ll; to.other_ll = g->other_ll; to.nonref_ll = g->nonref_ll; to.first_is_ref = g->first_is_ref;
+    to.copy_number = g->copy_number; to.n_alt = g->n_alt; to.n_ref = g->n_ref; to.n_other = g->n_other; to.qual = g->qual;
+    to.gq = g->gq; to.sb = g->sb; to.fisher = g->fisher; to.rms_mapq = g->rms_mapq; to.gl = g->gl; to.nonref_gl = g->nonref_gl;
+  }
   void* d_boff = ctx->bufs[SL_C_BOFF].p;
   const uint64_t* d_slots = st.slots_cap != SIZE_MAX ? (const uint64_t*)d_boff + std::min<int64_t>(T.cap, fake.n_sites) : nullptr;
   CK(launch_shard_pack_rows(st.D, st.ns, gathered_tables, pl->world, pl->rank, (int32_t)pl->site_cap, (int32_t)pl->allele_cap,
                             d_slots, st.slots_cap == SIZE_MAX ? 0 : (uint64_t)st.slots_cap, rows_block, (int32_t)pl->row_cap,
-                            root_rows != nullptr, ctx->num_sms, ctx->stream));
+                            root_rows ? &to : nullptr, root_rows ? root_rows->n_sites : 0, ctx->num_sms, ctx->stream));
   ctx->timing.n_launches += 1;
   st.phase = 2;
   return AVO_OK;

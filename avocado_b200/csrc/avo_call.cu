@@ -468,10 +468,6 @@ k_call_reduce(DSites S_in, DCallParams P, DResults O, const uint64_t* __restrict
   const DSites S = resolve_sites(S_in);
   const int32_t j = S_in.c_lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (j < S.c_lo || j >= S.c_hi) return;
-  // region-sharded steps whose rows go straight to another rank's arrays (avo_shard_call_direct): only the
-  // rows this rank owns are its to write
-  const bool owned_only = S.hdr && S.hdr->reserved[2] != 0;
-  if (owned_only && (j < S.hdr->reserved[1] || j >= S.hdr->reserved[2] - 1)) return;
   const uint32_t* __restrict__ bk = buckets + (size_t)__ldg(boff + j);
   const uint32_t n = __ldg(blen + j);
   if (__ldg(boff + j) + n > n_slots) return;   // guessed capacity too small: the host reruns the stage
@@ -523,7 +519,6 @@ k_call_reduce(DSites S_in, DCallParams P, DResults O, const uint64_t* __restrict
   A.allele_fwd = c_afw; A.other_fwd = c_ofw; A.allele_cov = c_acov; A.other_cov = c_ocov; A.total_cov = c_tot;
   A.first_is_ref = first_is_ref; A.copy_number = first_cn; A.seen = seen;
   finalize_site<true>(P, O, j, A);        // a site nobody observed gets a row of zeros: no clearing pass
-  if (owned_only) __threadfence_system(); // the row may live in a peer's memory: on its way before the kernel ends
 }
 
 // ---- launchers --------------------------------------------------------------------------------------

@@ -251,12 +251,12 @@ cudaError_t launch_shard_owned(const ShardTableIn& T, int32_t own_lo, int32_t ow
                                const ShardLocalCaps& C, void* block, int32_t cap, int32_t acap, int num_sms, cudaStream_t s);
 struct DSiteTableOut;
 cudaError_t launch_shard_concat(const void* gathered, int32_t world, int32_t cap, int32_t acap, const DSiteTableOut& G,
-                                int32_t own_rank, int num_sms, cudaStream_t s);
+                                int num_sms, cudaStream_t s);
 cudaError_t launch_shard_site_index(const DSites& S, const BatchStats& h, int32_t nb, int32_t* sidx, DSiteHdr* hdr,
                                     cudaStream_t s);
 cudaError_t launch_shard_pack_rows(const DResults& D, int ns, const void* gathered_tables, int32_t world, int32_t rank,
                                    int32_t tcap, int32_t tacap, const uint64_t* slots_used, uint64_t slots_cap, void* block,
-                                   int32_t rcap, bool header_only, int num_sms, cudaStream_t s);
+                                   int32_t rcap, const DResults* direct_to, int64_t direct_rows, int num_sms, cudaStream_t s);
 cudaError_t launch_shard_unpack_rows(const void* gathered_rows, const void* gathered_tables, int32_t tcap, int32_t tacap,
                                      int32_t world, int32_t rcap, int ns, const DResults& O, int64_t out_rows, ShardHdr* hdrs_out,
                                      int num_sms, cudaStream_t s);

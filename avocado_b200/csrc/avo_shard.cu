@@ -78,8 +78,7 @@ cudaError_t launch_shard_owned(const ShardTableIn& T, int32_t own_lo, int32_t ow
 
 // ---- the global table from the gathered blocks (rank order = position order) -----------------------
 __global__ void __launch_bounds__(256)
-k_shard_concat(const unsigned char* __restrict__ gathered, int32_t world, int32_t cap, int32_t acap, DSiteTableOut G,
-               int32_t own_rank /* >= 0: the per-site reduction writes only that rank's rows (direct rows) */) {
+k_shard_concat(const unsigned char* __restrict__ gathered, int32_t world, int32_t cap, int32_t acap, DSiteTableOut G) {
   const size_t bb = shard_table_bytes(cap, acap);
   // every thread adds up the (few) headers
   int32_t row0[AVO_MAX_SHARDS + 1], carry[AVO_MAX_SHARDS + 1];
@@ -128,17 +127,14 @@ k_shard_concat(const unsigned char* __restrict__ gathered, int32_t world, int32_
     int32_t mp = 1;                                              // TreeRegionJoin.scala:66-72
     while (!(2 * (int64_t)mp >= (int64_t)n)) mp *= 2;
     h.midpoint = mp;
-    h.reserved[0] = flags;
-    // [reserved[1], reserved[2] - 1): the rows the call stage's reduction may write; reserved[2] = 0: all
-    h.reserved[1] = own_rank >= 0 ? row0[own_rank] : 0;
-    h.reserved[2] = own_rank >= 0 ? row0[own_rank + 1] + 1 : 0;
+    h.reserved[0] = flags; h.reserved[1] = h.reserved[2] = 0;
     *G.hdr = h;
   }
 }
 
 cudaError_t launch_shard_concat(const void* gathered, int32_t world, int32_t cap, int32_t acap, const DSiteTableOut& G,
-                                int32_t own_rank, int num_sms, cudaStream_t s) {
-  k_shard_concat<<<num_sms, 256, 0, s>>>((const unsigned char*)gathered, world, cap, acap, G, own_rank);
+                                int num_sms, cudaStream_t s) {
+  k_shard_concat<<<num_sms, 256, 0, s>>>((const unsigned char*)gathered, world, cap, acap, G);
   return cudaGetLastError();
 }
 
@@ -186,11 +182,35 @@ __host__ __device__ inline size_t shard_rows_bytes(int64_t cap, int ns) {
 size_t shard_rows_block_bytes(int64_t cap, int ns) { return shard_rows_bytes(cap, ns); }
 size_t shard_table_block_bytes(int64_t cap, int64_t acap) { return shard_table_bytes(cap, acap); }
 
-// rows [A, A + n) of this rank (A, n from the gathered table headers) -> rows block
+// bytes [0, n) from src to dst by the whole grid; 16-byte accesses where the two share their alignment (the
+// columns of a result set all start 256-byte aligned, so a row range has the same offset in both)
+__device__ __forceinline__ void grid_copy(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, size_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((((uintptr_t)dst ^ (uintptr_t)src) & 15u) == 0) {
+    const size_t head = min(n, (size_t)((16u - ((uintptr_t)dst & 15u)) & 15u));
+    for (int64_t i = t0; i < (int64_t)head; i += stride) dst[i] = src[i];
+    const size_t body = (n - head) >> 4;
+    const uint4* s16 = reinterpret_cast<const uint4*>(src + head);
+    uint4* d16 = reinterpret_cast<uint4*>(dst + head);
+    for (int64_t i = t0; i < (int64_t)body; i += stride) d16[i] = s16[i];
+    for (int64_t i = (int64_t)(head + (body << 4)) + t0; i < (int64_t)n; i += stride) dst[i] = src[i];
+  } else if (((((uintptr_t)dst) | (uintptr_t)src) & 3u) == 0 && (n & 3u) == 0) {
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
+    for (int64_t i = t0; i < (int64_t)(n >> 2); i += stride) d4[i] = s4[i];
+  } else {
+    for (int64_t i = t0; i < (int64_t)n; i += stride) dst[i] = src[i];
+  }
+}
+
+// rows [A, A + n) of this rank (A, n from the gathered table headers) -> rows block; or (DIRECT) straight
+// into the same rows of `dst`, the result columns of the rank that collects them -- its own arrays there,
+// a peer mapping elsewhere: contiguous 16-byte stores over NVLink, one range per column
+template <bool DIRECT>
 __global__ void __launch_bounds__(256)
 k_shard_pack_rows(DResults D, int ns, const unsigned char* __restrict__ gathered_tables, int32_t world, int32_t rank,
                   int32_t tcap, int32_t tacap, const uint64_t* __restrict__ slots_used, uint64_t slots_cap,
-                  unsigned char* __restrict__ block, int32_t rcap, int32_t header_only) {
+                  unsigned char* __restrict__ block, int32_t rcap, DResults dst, int64_t dst_rows) {
   const size_t bb = shard_table_bytes(tcap, tacap);
   int32_t A = 0, n = 0;
   for (int r = 0; r <= rank; ++r) {
@@ -202,37 +222,41 @@ k_shard_pack_rows(DResults D, int ns, const unsigned char* __restrict__ gathered
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     H->n_rows = n; H->n_bytes = 0; H->max_end = 0;
     H->flags = (n > rcap ? SHARD_BLOCK_FULL : 0) | ((slots_used && *slots_used > slots_cap) ? SHARD_RETRY : 0) |
-               (header_only ? SHARD_ROWS_DIRECT : 0);
+               (DIRECT ? SHARD_ROWS_DIRECT : 0);
     H->reserved[0] = H->reserved[1] = H->reserved[2] = H->reserved[3] = 0;
   }
-  if (header_only) return;            // the rows went straight to their destination (avo_shard_call_direct)
   const void* src[AVO_RESULT_COLUMNS];
   int width[AVO_RESULT_COLUMNS];
   shard_row_columns(D, ns, src, width);
+  if (DIRECT) {
+    const void* to[AVO_RESULT_COLUMNS];
+    shard_row_columns(dst, ns, to, width);
+    const int64_t rows = max((int64_t)0, min((int64_t)n, dst_rows - A));    // (a table past the arrays: the host reruns)
+#pragma unroll 1
+    for (int c = 0; c < AVO_RESULT_COLUMNS; ++c)
+      grid_copy((unsigned char*)to[c] + (size_t)A * width[c], (const unsigned char*)src[c] + (size_t)A * width[c],
+                (size_t)rows * width[c]);
+    __threadfence_system();             // on their way to the peer before the kernel ends
+    return;
+  }
   const int32_t rows = min(n, rcap);
   size_t off = sizeof(ShardHdr);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+#pragma unroll 1
   for (int c = 0; c < AVO_RESULT_COLUMNS; ++c) {
-    const size_t bytes = (size_t)rows * width[c];
-    const unsigned char* s8 = (const unsigned char*)src[c] + (size_t)A * width[c];
-    unsigned char* d8 = block + off;
-    if (((((uintptr_t)s8) | (uintptr_t)d8) & 3u) == 0 && (width[c] & 3) == 0) {
-      const uint32_t* s4 = (const uint32_t*)s8;
-      uint32_t* d4 = (uint32_t*)d8;
-      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)(bytes >> 2); i += stride) d4[i] = s4[i];
-    } else {
-      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)bytes; i += stride) d8[i] = s8[i];
-    }
+    grid_copy(block + off, (const unsigned char*)src[c] + (size_t)A * width[c], (size_t)rows * width[c]);
     off += ((size_t)rcap * width[c] + 15) & ~(size_t)15;
   }
 }
 
 cudaError_t launch_shard_pack_rows(const DResults& D, int ns, const void* gathered_tables, int32_t world, int32_t rank,
                                    int32_t tcap, int32_t tacap, const uint64_t* slots_used, uint64_t slots_cap, void* block,
-                                   int32_t rcap, bool header_only, int num_sms, cudaStream_t s) {
-  k_shard_pack_rows<<<header_only ? 1 : 2 * num_sms, 256, 0, s>>>(D, ns, (const unsigned char*)gathered_tables, world, rank, tcap,
-                                                                 tacap, slots_used, slots_cap, (unsigned char*)block, rcap,
-                                                                 header_only ? 1 : 0);
+                                   int32_t rcap, const DResults* direct_to, int64_t direct_rows, int num_sms, cudaStream_t s) {
+  if (direct_to)
+    k_shard_pack_rows<true><<<2 * num_sms, 256, 0, s>>>(D, ns, (const unsigned char*)gathered_tables, world, rank, tcap, tacap,
+                                                       slots_used, slots_cap, (unsigned char*)block, rcap, *direct_to, direct_rows);
+  else
+    k_shard_pack_rows<false><<<2 * num_sms, 256, 0, s>>>(D, ns, (const unsigned char*)gathered_tables, world, rank, tcap, tacap,
+                                                        slots_used, slots_cap, (unsigned char*)block, rcap, D, 0);
   return cudaGetLastError();
 }
 

@@ -158,8 +158,8 @@ class ShardedPipeline:
         # "all": every rank ends with every row (all-gather of the rows blocks).  "root": the rows are
         # gathered to rank 0 only (the driver's `collect`); the other ranks all-gather just the 32-byte
         # headers and end with the global table and their OWN rows.
-        # "direct": nothing is gathered but 32-byte headers -- every rank's per-site reduction stores its owned
-        # rows straight into rank 0's result columns over NVLink (avo_shard_call_direct; the columns live in a
+        # "direct": nothing is gathered but 32-byte headers -- every rank's last kernel stores its owned rows
+        # straight into rank 0's result columns over NVLink (avo_shard_call_direct; the columns live in a
         # CUDA-IPC block the other ranks map).  Rank 0 ends with every row, the others with the table.
         # `direct_root` (tests: several ranks emulated in ONE process): rank 0's pipeline, whose block the
         # other ranks then address directly (rank 0 itself passes True).

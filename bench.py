@@ -11,9 +11,9 @@ BASELINE.json configs[1] shape per GPU: single-sample 60x chr20 (64 Mb), 150 bp 
             N = 1: avo_discover_and_call, one launch chain, no host round trip.  N > 1 (torchrun): the
             genome is N times larger, cut into N regions WITH read-overlap halos; every step runs the
             region-sharded path (avo_shard_discover / _call_direct / _finish): an NCCL all-gather of the
-            owned slice of every rank's site table; then every rank's per-site reduction stores the rows
-            of its owned sites straight into rank 0's result columns over NVLink peer memory, and only
-            32-byte headers are all-gathered.  Both exchanges are inside the timed region; every rank
+            owned slice of every rank's site table; then every rank's last kernel stores the rows of its
+            owned sites straight into rank 0's result columns over NVLink peer memory, and only 32-byte
+            headers are all-gathered.  Both exchanges are inside the timed region; every rank
             ends with the global table, rank 0 with all rows.  (AVO_ROWS_TO=root|all: NCCL gathers.)
   e2e       the same metric from HOST buffers holding what the reference's job holds: AlignmentRecord
             TEXT columns (CIGAR, MD, sequence, qualities) in pinned memory -> H2D -> device packer
@@ -207,7 +207,7 @@ def run_reference(args):
 def config_dict(args, per, contig, world):
     par = ("one GPU" if world == 1 else
            "region-sharded x%d with read-overlap halos: NCCL all-gather of the owned site-table slices; the result rows of the "
-           "owned sites are stored by the kernel that computes them straight into rank 0's columns over NVLink peer memory "
+           "owned sites are stored by each rank's last kernel straight into rank 0's columns over NVLink peer memory "
            "(CUDA IPC), and only their 32-byte headers are all-gathered; all inside the timed step; every rank ends with the "
            "global table, rank 0 with all rows" % world)
     return {"workload": "single-sample germline discoverAndCall, synthetic 60x chr20-shaped (%.0f Mb, %d x 150 bp reads) per GPU"
@@ -463,7 +463,7 @@ def main():
                     "table_block_bytes": int(pipe.tb), "rows_block_bytes": int(pipe.rb), "collectives_per_step": 2,
                     "rows_to": pipe.rows_to, "phases_ms_rank0": {k: round(v, 4) for k, v in phases.items()},
                     "note": "all_gather_into_tensor of the owned table slices and of 32-byte headers; rows_to=direct: the result rows reach "
-                            "rank 0 as peer-memory stores of k_call_reduce (not counted in the NCCL bytes), root / all: NCCL gather / "
+                            "rank 0 as peer-memory stores of k_shard_pack_rows (not counted in the NCCL bytes), root / all: NCCL gather / "
                             "all-gather of the rows blocks; one host synchronisation per step"}
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------

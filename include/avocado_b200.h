@@ -373,8 +373,9 @@ int avo_shard_finish(avo_ctx* ctx, const avo_shard_plan* plan, const void* gathe
 /* The same step with the rows written where they are wanted, over NVLink, by the kernel that computes
  * them: `root_rows` are the global result columns of ONE rank (the root), as device pointers valid on
  * THIS rank's GPU -- the root's own arrays on the root, a peer mapping of them elsewhere (avo_peer_open).
- * The call stage's per-site reduction stores this rank's OWNED rows straight into them at their global
- * row numbers (known on the device from the gathered table headers); no rows travel through rows_block,
+ * The step's last kernel stores this rank's OWNED rows straight into them at their global row numbers
+ * (known on the device from the gathered table headers), one contiguous range of 16-byte stores per
+ * column; no rows travel through rows_block,
  * whose 32-byte header (flags) is all the framework still gathers -- to every rank -- before
  * avo_shard_finish.  That collective, ordered after this call on every rank's stream, is also what tells
  * the root that the peers' stores have landed.  The root must not hand the rows of a step to anyone who

@@ -232,11 +232,7 @@ int upload_reads(avo_ctx* ctx, const avo_read_batch* r, bool sparse, DReads* R, 
   R->qhead_short = 0;
   R->n_ops = r->n_ops;
   R->n_refb = r->n_refb;
-  {
-    void* c;
-    CKS(get_buf(ctx, SL_COORDS, n * sizeof(int2), &c));
-    R->coords = (int2*)c;
-  }
+  R->coords = nullptr;             // the dense (start, end) copy: only the host-gathered route's join reads it
   if (r->wire6_meta && r->mem == AVO_MEM_HOST) {
     // 6-byte records: starts, ends, lengths and offsets are rebuilt on the device; two head qualities
     const avo_read_wire6* dw;
@@ -289,6 +285,9 @@ int upload_reads(avo_ctx* ctx, const avo_read_batch* r, bool sparse, DReads* R, 
       ctx->timing.payload_in_place = 1;
       if (params && params->host_payload == 2) {     // the call stage gathers its blocks on the host
         ctx->gather_src = r->payload;
+        void* c;
+        CKS(get_buf(ctx, SL_COORDS, n * sizeof(int2), &c));
+        R->coords = (int2*)c;
         ctx->gather_threads = params->gather_threads > 0 ? std::min(params->gather_threads, 64) : 4;
         ctx->timing.payload_in_place = 2;
       }

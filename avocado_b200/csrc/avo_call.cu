@@ -54,7 +54,7 @@ __device__ __forceinline__ int32_t first_read_at(const DReads& R, const DIndex& 
   const int32_t k32 = (int32_t)min(key, (int64_t)INT32_MAX);
   while (lo < hi) {
     const int32_t mid = lo + ((hi - lo) >> 1);
-    if (__ldg(&R.coords[mid].x) < k32) lo = mid + 1; else hi = mid;
+    if (meta_start(R.meta, mid) < k32) lo = mid + 1; else hi = mid;
   }
   return lo;
 }

@@ -483,32 +483,45 @@ k_call_reduce(DSites S_in, DCallParams P, DResults O, const uint64_t* __restrict
   int32_t c_tot = 0, c_acov = 0, c_ocov = 0, c_afw = 0, c_ofw = 0;
   unsigned long long sq = 0;
   int seen = 0, first_is_ref = 0, first_cn = 0;
-  for (uint32_t i = 0; i < n; ++i) {
-    const uint32_t w = __ldg(bk + i);
-    if (!(w & 1u)) continue;
-    const uint32_t cat = (w >> 1) & 3u;
-    const uint32_t fwd = (w >> 3) & 1u;
-    const uint32_t mq = (w >> 11) & 127u;
-    // row = (copy-number index, mq', q') packed exactly as bits [21:4] of the record word
-    const double* __restrict__ row = P.lut + (size_t)((w >> 4) & 0x3FFFFu) * (uint32_t)ns;
-    double v[NS];
+  // Four slots per round: their words, then their table rows, are requested together (a thread's chain of
+  // slot -> row loads is the kernel's whole latency: 71 k threads are a third of a wave); the sums are still
+  // added one record at a time, in slot order.
+  constexpr int RU = 4;
+  for (uint32_t i0 = 0; i0 < n; i0 += RU) {
+    uint32_t ws[RU];
 #pragma unroll
-    for (int g = 0; g < NS; ++g) v[g] = (g < ns) ? __ldg(row + g) : 0.0;
+    for (int u = 0; u < RU; ++u) ws[u] = (i0 + u < n) ? __ldg(bk + i0 + u) : 0u;
+    double vs[RU][NS];
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (cat == (uint32_t)c) {
+    for (int u = 0; u < RU; ++u) {
+      // row = (copy-number index, mq', q') packed exactly as bits [21:4] of the record word
+      const double* __restrict__ row = P.lut + (size_t)((ws[u] >> 4) & 0x3FFFFu) * (uint32_t)ns;
 #pragma unroll
-        for (int g = 0; g < NS; ++g) acc[c][g] += v[g];
+      for (int g = 0; g < NS; ++g) vs[u][g] = ((ws[u] & 1u) && g < ns) ? __ldg(row + g) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const uint32_t w = ws[u];
+      if (!(w & 1u)) continue;
+      const uint32_t cat = (w >> 1) & 3u;
+      const uint32_t fwd = (w >> 3) & 1u;
+      const uint32_t mq = (w >> 11) & 127u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (cat == (uint32_t)c) {
+#pragma unroll
+          for (int g = 0; g < NS; ++g) acc[c][g] += vs[u][g];
+        }
+      ++c_tot;                                                   // ScoredObservation.scala:88
+      const uint32_t is_ref = cat == CAT_REF, is_al = (cat == CAT_ALT) | (cat == CAT_NONREF);
+      c_ocov += is_ref; c_ofw += is_ref & fwd;                   // :87, :80
+      c_acov += is_al; c_afw += is_al & fwd;                     // :86, :79
+      sq += (unsigned long long)(mq * mq);                       // :81
+      if (!seen) {                                               // first("isRef"), first("copyNumber")
+        seen = 1;
+        first_is_ref = (int)is_ref;
+        first_cn = (int)((w >> 18) & 15u) + P.min_ploidy;
       }
-    ++c_tot;                                                   // ScoredObservation.scala:88
-    const uint32_t is_ref = cat == CAT_REF, is_al = (cat == CAT_ALT) | (cat == CAT_NONREF);
-    c_ocov += is_ref; c_ofw += is_ref & fwd;                   // :87, :80
-    c_acov += is_al; c_afw += is_al & fwd;                     // :86, :79
-    sq += (unsigned long long)(mq * mq);                       // :81
-    if (!seen) {                                               // first("isRef"), first("copyNumber")
-      seen = 1;
-      first_is_ref = (int)is_ref;
-      first_cn = (int)((w >> 18) & 15u) + P.min_ploidy;
     }
   }
 #pragma unroll

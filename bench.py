@@ -434,7 +434,7 @@ def main():
     top, top_ms = ("call_kernels", ms_call) if ms_call >= ms_disc else ("k_discover_tiles", ms_disc)
     small_cols = sum(getattr(dev, c).numel() * getattr(dev, c).element_size() for c in ("meta", "ops", "refb"))
     n_local_sites = n_sites_dev // world
-    alg = small_cols + (n_local_sites * 16 + dev.n_reads * 8 if top == "k_discover_tiles"
+    alg = small_cols + (n_local_sites * 16 if top == "k_discover_tiles"
                         else pairs_dev // world * 64 + n_local_sites * SITE_ROW_BYTES)
     traffic = None
     try:
@@ -450,8 +450,8 @@ def main():
                 "algorithmic_bytes_per_launch": alg, "ms_per_launch": top_ms,
                 "basis": "measured DRAM bytes per launch (profiles/traffic.json, ncu) / CUDA-event time"
                          if traffic is not None else "algorithmic bytes / CUDA-event time",
-                "algorithmic_basis": "records + operators + mismatch bytes streamed once + 8 B coords per read + 16 B per site "
-                                     "(46 B/read; the payload is only touched at indels): DESIGN.md section 4",
+                "algorithmic_basis": "records + operators + mismatch bytes streamed once + 16 B per site "
+                                     "(about 44 B/read; the payload is only touched at indels): DESIGN.md section 4",
                 "whole_step": {"ms": step_ms, "note": "all kernels of the step; its DRAM bytes are in profiles/ (ncu launch list)"},
                 "note": "sparse kernels: latency / issue bound, not bandwidth bound (profiles/README.md)",
                 "other_kernel": {"call_kernels_ms": ms_call, "k_discover_tiles_ms": ms_disc}}

@@ -202,6 +202,55 @@ JNIEXPORT jint JNICALL Java_org_bdgenomics_avocado_nativelib_AvocadoB200_shardCa
                         (void*)(intptr_t)rowsBlockDevicePtr);
 }
 
+/* The same phase with the rows stored straight into the collecting executor's result columns over NVLink
+ * (`rootRows`: that executor's own holder there, a holder over the peerOpen mapping elsewhere). */
+JNIEXPORT jint JNICALL Java_org_bdgenomics_avocado_nativelib_AvocadoB200_shardCallDirect(
+    JNIEnv* e, jclass k, jlong ctx, jobject jc, jint ploidy, jint minPhred, jint minObs, jobject jp, jlong gatheredTables,
+    jobject js, jlong rowsBlockDevicePtr, jobject jrootRows) {
+  avo_cnv c = {0};
+  avo_shard_plan pl = {0};
+  avo_sites_out s = {0};
+  avo_site_results root = {0};
+  (void)k;
+  if (jc) cnv_in(e, jc, &c);
+  plan_in(e, jp, &pl);
+  sites_out(e, js, &s);
+  results(e, jrootRows, &root);
+  avo_params p = params(ploidy, 93, 93, minPhred, minObs);
+  return avo_shard_call_direct((avo_ctx*)(intptr_t)ctx, jc ? &c : NULL, &p, &pl, (const void*)(intptr_t)gatheredTables, &s,
+                               (void*)(intptr_t)rowsBlockDevicePtr, &root);
+}
+
+/* Device memory the other executors of the node can map (CUDA IPC): returns the device pointer (0 on failure)
+ * and fills the 64-byte handle the shim sends to its peers. */
+JNIEXPORT jlong JNICALL Java_org_bdgenomics_avocado_nativelib_AvocadoB200_peerAlloc(JNIEnv* e, jclass k, jlong ctx, jlong bytes,
+                                                                                   jbyteArray handle) {
+  void* ptr = NULL;
+  unsigned char h[AVO_PEER_HANDLE_BYTES];
+  (void)k;
+  if (avo_peer_alloc((avo_ctx*)(intptr_t)ctx, bytes, &ptr, h) != AVO_OK) return 0;
+  (*e)->SetByteArrayRegion(e, handle, 0, AVO_PEER_HANDLE_BYTES, (const jbyte*)h);
+  return (jlong)(intptr_t)ptr;
+}
+
+JNIEXPORT jlong JNICALL Java_org_bdgenomics_avocado_nativelib_AvocadoB200_peerOpen(JNIEnv* e, jclass k, jlong ctx, jbyteArray handle) {
+  void* ptr = NULL;
+  unsigned char h[AVO_PEER_HANDLE_BYTES];
+  (void)k;
+  (*e)->GetByteArrayRegion(e, handle, 0, AVO_PEER_HANDLE_BYTES, (jbyte*)h);
+  return avo_peer_open((avo_ctx*)(intptr_t)ctx, h, &ptr) == AVO_OK ? (jlong)(intptr_t)ptr : 0;
+}
+
+JNIEXPORT jint JNICALL Java_org_bdgenomics_avocado_nativelib_AvocadoB200_peerClose(JNIEnv* e, jclass k, jlong ctx, jlong ptr) {
+  (void)e; (void)k;
+  return avo_peer_close((avo_ctx*)(intptr_t)ctx, (void*)(intptr_t)ptr);
+}
+
+JNIEXPORT jint JNICALL Java_org_bdgenomics_avocado_nativelib_AvocadoB200_peerFree(JNIEnv* e, jclass k, jlong ctx, jlong ptr) {
+  (void)e; (void)k;
+  return avo_peer_free((avo_ctx*)(intptr_t)ctx, (void*)(intptr_t)ptr);
+}
+
 JNIEXPORT jint JNICALL Java_org_bdgenomics_avocado_nativelib_AvocadoB200_shardFinish(
     JNIEnv* e, jclass k, jlong ctx, jobject jp, jlong gatheredTables, jlong gatheredRows, jobject js, jobject jo, jobject jneeded) {
   avo_shard_plan pl = {0}, need = {0};

@@ -9,6 +9,10 @@ typedef int64_t jlong;
 typedef void* jobject;
 typedef jobject jclass;
 typedef jobject jstring;
+typedef jobject jarray;
+typedef jarray jbyteArray;
+typedef int8_t jbyte;
+typedef jint jsize;
 typedef struct _jfieldID* jfieldID;
 struct JNINativeInterface_;
 typedef const struct JNINativeInterface_* JNIEnv;
@@ -22,6 +26,8 @@ struct JNINativeInterface_ {
   void* (*GetDirectBufferAddress)(JNIEnv*, jobject);
   jlong (*GetDirectBufferCapacity)(JNIEnv*, jobject);
   jstring (*NewStringUTF)(JNIEnv*, const char*);
+  void (*GetByteArrayRegion)(JNIEnv*, jbyteArray, jsize, jsize, jbyte*);
+  void (*SetByteArrayRegion)(JNIEnv*, jbyteArray, jsize, jsize, const jbyte*);
 };
 #define JNIEXPORT
 #define JNICALL

@@ -106,7 +106,7 @@ class TimingStruct(C.Structure):
 class TextReadsStruct(C.Structure):
     _fields_ = [("n", C.c_int64), ("start", P), ("end", P), ("mapq", P), ("rec_flags", P),
                 ("cigar", P), ("cigar_off", P), ("md", P), ("md_off", P), ("seq", P), ("seq_off", P),
-                ("qual", P), ("qual_off", P), ("keep", P), ("prefilter", P)]
+                ("qual", P), ("qual_off", P), ("keep", P), ("prefilter", P), ("narrow", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PrefilterStruct(C.Structure):

@@ -426,6 +426,27 @@ def text_columns(records: Sequence[AlignmentRecord]):
                 md_off=md_off, seq=seq, seq_off=seq_off, qual=qual, qual_off=qual_off)
 
 
+def narrow_text_columns(cols):
+    """The same text columns with 32-bit numeric columns (avo_text_reads.narrow): start / end int32, the
+    offsets uint32, mapq uint8 (an absent mapq loses its flag bit instead of being -1).  23 bytes per read
+    less to move when the text is packed on the device."""
+    flags = np.array(cols["flags"], np.uint8, copy=True)
+    mapq = np.asarray(cols["mapq"])
+    flags[mapq < 0] &= np.uint8(0xFF ^ 16)
+    out = dict(cols)
+    out.update(narrow=True, flags=flags, start=np.asarray(cols["start"]).astype(np.int32),
+               end=np.asarray(cols["end"]).astype(np.int32), mapq=np.clip(mapq, 0, 255).astype(np.uint8))
+    shared = cols["qual_off"] is cols["seq_off"]
+    for k in ("cigar_off", "md_off", "seq_off", "qual_off"):
+        a = np.asarray(cols[k])
+        if a.size and int(a[-1]) >= 1 << 32:
+            raise ValueError("text blobs of 4 GB or more need the 64-bit columns")
+        out[k] = a.astype(np.uint32)
+    if shared:
+        out["qual_off"] = out["seq_off"]
+    return out
+
+
 def pack_reads(records: Sequence[AlignmentRecord], contig_id=0, keep=None, sort=True) -> ReadBatch:
     """Packs mapped reads of ONE contig, (stably) sorted by start, into a host ReadBatch.
     ``keep`` optionally selects reads (``prefilter.prefilter_mask`` gives the PrefilterReads predicate)."""
@@ -449,6 +470,7 @@ def pack_text_columns(cols, contig_id=0, threads=1, keep=None, out=None, prefilt
     lib = L.load()
     t = L.TextReadsStruct()
     t.n = len(cols["start"])
+    t.narrow = 1 if cols.get("narrow") else 0
     keepalive = []
     for name in ("start", "end", "mapq"):
         setattr(t, name, cols[name].ctypes.data)

@@ -1637,34 +1637,49 @@ int avo_pack_reads_device(avo_ctx* ctx, const avo_text_reads* in, int32_t in_mem
   if ((uintptr_t)out->meta & 15u || (uintptr_t)out->payload & 15u)
     return fail(ctx, AVO_E_INVALID, "out->meta and out->payload must be 16-byte aligned");
   if (n == 0) { out->n_reads = out->n_blocks = out->n_ops = out->n_refb = 0; return AVO_OK; }
-  // blob sizes = the last offsets
+  // blob sizes = the last offsets (64-bit columns, or 32-bit ones: avo_text_reads.narrow)
+  const bool narrow = in->narrow != 0;
   int64_t tot[4];
+  uint32_t tot32[4] = {0, 0, 0, 0};
   const int64_t* offs[4] = {in->cigar_off, in->md_off, in->seq_off, in->qual_off};
   for (int k = 0; k < 4; ++k) {
-    if (in_mem == AVO_MEM_HOST) tot[k] = offs[k][n];
+    if (in_mem == AVO_MEM_HOST) tot[k] = narrow ? (int64_t)reinterpret_cast<const uint32_t*>(offs[k])[n] : offs[k][n];
+    else if (narrow) CK(cudaMemcpyAsync(&tot32[k], reinterpret_cast<const uint32_t*>(offs[k]) + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
     else CK(cudaMemcpyAsync(&tot[k], offs[k] + n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   }
-  if (in_mem == AVO_MEM_DEVICE) CK(cudaStreamSynchronize(ctx->stream));
+  if (in_mem == AVO_MEM_DEVICE) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (narrow) for (int k = 0; k < 4; ++k) tot[k] = tot32[k];
+  }
   for (int k = 0; k < 4; ++k)
     if (tot[k] < 0) return fail(ctx, AVO_E_INVALID, "negative blob size");
   if ((tot[0] && !in->cigar) || (tot[1] && !in->md) || (tot[2] && !in->seq) || (tot[3] && !in->qual))
     return fail(ctx, AVO_E_INVALID, "text batch has NULL blobs");
   DText T;
   T.n = in->n;
+  T.narrow = narrow ? 1 : 0;
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  CKS(stage_in(ctx, SL_T_START, in->start, n, in_mem, &T.start));
-  CKS(stage_in(ctx, SL_T_END, in->end, n, in_mem, &T.end));
-  CKS(stage_in(ctx, SL_T_MAPQ, in->mapq, n, in_mem, &T.mapq));
+  // numeric columns travel as bytes of their own width
+  auto stage_num = [&](int slot, const void* src, size_t count, size_t wide, size_t slim, const void** dst) -> int {
+    const uint8_t* d = nullptr;
+    const int rc = stage_in(ctx, slot, reinterpret_cast<const uint8_t*>(src), count * (narrow ? slim : wide), in_mem, &d);
+    *dst = d;
+    return rc;
+  };
+  const void* q = nullptr;
+  CKS(stage_num(SL_T_START, in->start, n, 8, 4, &q)); T.start = (const int64_t*)q;
+  CKS(stage_num(SL_T_END, in->end, n, 8, 4, &q)); T.end = (const int64_t*)q;
+  CKS(stage_num(SL_T_MAPQ, in->mapq, n, 4, 1, &q)); T.mapq = (const int32_t*)q;
   CKS(stage_in(ctx, SL_T_FLAGS, in->rec_flags, n, in_mem, &T.rec_flags));
   CKS(stage_in(ctx, SL_T_CIGAR, in->cigar, (size_t)tot[0], in_mem, &T.cigar));
-  CKS(stage_in(ctx, SL_T_CIGAR_OFF, in->cigar_off, n + 1, in_mem, &T.cigar_off));
+  CKS(stage_num(SL_T_CIGAR_OFF, in->cigar_off, n + 1, 8, 4, &q)); T.cigar_off = (const int64_t*)q;
   CKS(stage_in(ctx, SL_T_MD, in->md, (size_t)tot[1], in_mem, &T.md));
-  CKS(stage_in(ctx, SL_T_MD_OFF, in->md_off, n + 1, in_mem, &T.md_off));
+  CKS(stage_num(SL_T_MD_OFF, in->md_off, n + 1, 8, 4, &q)); T.md_off = (const int64_t*)q;
   CKS(stage_in(ctx, SL_T_SEQ, in->seq, (size_t)tot[2], in_mem, &T.seq));
-  CKS(stage_in(ctx, SL_T_SEQ_OFF, in->seq_off, n + 1, in_mem, &T.seq_off));
+  CKS(stage_num(SL_T_SEQ_OFF, in->seq_off, n + 1, 8, 4, &q)); T.seq_off = (const int64_t*)q;
   if (in->qual == in->seq) T.qual = T.seq; else CKS(stage_in(ctx, SL_T_QUAL, in->qual, (size_t)tot[3], in_mem, &T.qual));
   if (in->qual_off == in->seq_off) T.qual_off = T.seq_off;
-  else CKS(stage_in(ctx, SL_T_QUAL_OFF, in->qual_off, n + 1, in_mem, &T.qual_off));
+  else { CKS(stage_num(SL_T_QUAL_OFF, in->qual_off, n + 1, 8, 4, &q)); T.qual_off = (const int64_t*)q; }
   T.keep = nullptr;
   T.prefilter = in->prefilter ? 1 : 0;
   if (in->prefilter) T.pf = *in->prefilter; else memset(&T.pf, 0, sizeof T.pf);

@@ -195,7 +195,12 @@ struct DText {                   // avo_text_reads with device pointers
   const uint8_t* keep;           // may be NULL
   int32_t prefilter;             // != 0: pf holds PrefilterReads' read predicates
   avo_prefilter pf;
+  int32_t narrow;                // != 0: start / end are int32, the offsets uint32, mapq uint8 (avo_text_reads.narrow)
 };
+// column accessors of both packers (T: DText or avo_text_reads)
+#define AVO_T_I64(T, col, i) ((T).narrow ? (int64_t)reinterpret_cast<const int32_t*>((T).col)[i] : (T).col[i])
+#define AVO_T_OFF(T, col, i) ((T).narrow ? (int64_t)reinterpret_cast<const uint32_t*>((T).col)[i] : (T).col[i])
+#define AVO_T_MAPQ(T, i) ((T).narrow ? (int32_t)reinterpret_cast<const uint8_t*>((T).mapq)[i] : (T).mapq[i])
 struct PackOffsets { uint64_t k, b, o, f; };   // packed record, payload block, operator, mismatch byte
 struct DPacked {
   avo_read_meta* meta;

@@ -19,6 +19,17 @@
 
 #include "../../include/avocado_b200.h"
 
+// numeric text columns in either width (avo_text_reads.narrow)
+static inline int64_t t_i64(const avo_text_reads* in, const int64_t* col, int64_t i) {
+  return in->narrow ? (int64_t)reinterpret_cast<const int32_t*>(col)[i] : col[i];
+}
+static inline int64_t t_off(const avo_text_reads* in, const int64_t* col, int64_t i) {
+  return in->narrow ? (int64_t)reinterpret_cast<const uint32_t*>(col)[i] : col[i];
+}
+static inline int32_t t_mapq(const avo_text_reads* in, int64_t i) {
+  return in->narrow ? (int32_t)reinterpret_cast<const uint8_t*>(in->mapq)[i] : in->mapq[i];
+}
+
 namespace {
 
 // BAM 4-bit base codes "=ACMGRSVTWYHKDBN"
@@ -214,11 +225,11 @@ bool extract_ops(const char* cig, size_t ncig, bool has_cigar, const char* md, s
 bool kept(const avo_text_reads* in, int64_t i) {
   const uint8_t rf = in->rec_flags[i];
   if (!(rf & 1)) return false;                           // unmapped reads never reach the path
-  if (in->start[i] < 0) return false;
+  if (t_i64(in, in->start, i) < 0) return false;
   if (const avo_prefilter* f = in->prefilter) {          // PrefilterReads.scala:142-209
     if (!f->contig_kept) return false;
     if (!(rf & 32) && !f->keep_non_primary) return false;                 // filterMapped
-    if ((rf & 16) && in->mapq[i] >= 0 && !(in->mapq[i] > f->min_mapq)) return false;   // filterMappingQuality
+    if ((rf & 16) && t_mapq(in, i) >= 0 && !(t_mapq(in, i) > f->min_mapq)) return false;   // filterMappingQuality
     if ((rf & 64) && !f->keep_duplicates) return false;                   // filterUnique
   }
   return in->keep ? in->keep[i] != 0 : true;
@@ -246,16 +257,16 @@ void pack_chunk(const avo_text_reads* in, avo_packed_out* out, Chunk& ch) {
   for (int64_t i = ch.i0; i < ch.i1; ++i) {
     if (!kept(in, i)) continue;
     const uint8_t rf = in->rec_flags[i];
-    const char* seq = in->seq + in->seq_off[i];
-    const int64_t lseq = in->seq_off[i + 1] - in->seq_off[i];
-    const char* qual = in->qual + in->qual_off[i];
-    const int64_t lqual = in->qual_off[i + 1] - in->qual_off[i];
+    const char* seq = in->seq + t_off(in, in->seq_off, i);
+    const int64_t lseq = t_off(in, in->seq_off, i + 1) - t_off(in, in->seq_off, i);
+    const char* qual = in->qual + t_off(in, in->qual_off, i);
+    const int64_t lqual = t_off(in, in->qual_off, i + 1) - t_off(in, in->qual_off, i);
     uint32_t need = 0;
-    bool ok = extract_ops(in->cigar + in->cigar_off[i], (size_t)(in->cigar_off[i + 1] - in->cigar_off[i]),
-                          rf & 4, in->md + in->md_off[i], (size_t)(in->md_off[i + 1] - in->md_off[i]),
+    bool ok = extract_ops(in->cigar + t_off(in, in->cigar_off, i), (size_t)(t_off(in, in->cigar_off, i + 1) - t_off(in, in->cigar_off, i)),
+                          rf & 4, in->md + t_off(in, in->md_off, i), (size_t)(t_off(in, in->md_off, i + 1) - t_off(in, in->md_off, i)),
                           rf & 8, seq, lseq, sc, &need);
     uint8_t flags = (rf & 2) ? AVO_READ_NEGATIVE_STRAND : 0;
-    const bool has_mapq = (rf & 16) && in->mapq[i] >= 0;
+    const bool has_mapq = (rf & 16) && t_mapq(in, i) >= 0;
     // observeRead indexes sequence and qualities up to the CIGAR's read length
     if (!has_mapq || (int64_t)need > lseq || (int64_t)need > lqual) flags |= AVO_READ_SKIP_CALL;
     // discovery additionally indexes qual(i) from 0 and sequence up to the same length: a read
@@ -269,9 +280,9 @@ void pack_chunk(const avo_text_reads* in, avo_packed_out* out, Chunk& ch) {
       return;
     }
     avo_read_meta& m = out->meta[r];
-    m.start = (int32_t)in->start[i];
-    m.end = (int32_t)in->end[i];
-    const int mq = has_mapq ? in->mapq[i] : 0;
+    m.start = (int32_t)t_i64(in, in->start, i);
+    m.end = (int32_t)t_i64(in, in->end, i);
+    const int mq = has_mapq ? t_mapq(in, i) : 0;
     m.mapq = (uint8_t)(mq > 255 ? 255 : mq);
     m.flags = flags;
     m.seq_off = (uint32_t)nb;
@@ -409,10 +420,10 @@ int avo_pack_bounds(const avo_text_reads* in, int64_t* n_reads, int64_t* n_block
   for (int64_t i = 0; i < in->n; ++i) {
     if (!kept(in, i)) continue;
     ++r;
-    b += ((in->seq_off[i + 1] - in->seq_off[i]) + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES;   // payload blocks
+    b += ((t_off(in, in->seq_off, i + 1) - t_off(in, in->seq_off, i)) + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES;   // payload blocks
     // every op needs at least one CIGAR character pair or one MD character
-    const int64_t c = in->cigar_off[i + 1] - in->cigar_off[i];
-    const int64_t m = in->md_off[i + 1] - in->md_off[i];
+    const int64_t c = t_off(in, in->cigar_off, i + 1) - t_off(in, in->cigar_off, i);
+    const int64_t m = t_off(in, in->md_off, i + 1) - t_off(in, in->md_off, i);
     o += c / 2 + 1 + 2 * m;
     f += m + 1;
   }
@@ -432,7 +443,7 @@ int avo_pack_reads_mt(const avo_text_reads* in, avo_packed_out* out, int n_threa
     for (int64_t i = ch.i0; i < ch.i1; ++i) {
       if (!kept(in, i)) continue;
       ++ch.n_kept;
-      ch.n_blk += (uint64_t)((in->seq_off[i + 1] - in->seq_off[i]) + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES;
+      ch.n_blk += (uint64_t)((t_off(in, in->seq_off, i + 1) - t_off(in, in->seq_off, i)) + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES;
     }
   });
   int64_t r = 0;

@@ -206,11 +206,11 @@ __device__ Extracted extract_ops(const char* cig, int ncig, bool has_cigar, cons
 __device__ __forceinline__ bool kept(const DText& T, int64_t i) {
   const uint8_t rf = T.rec_flags[i];
   if (!(rf & 1)) return false;
-  if (T.start[i] < 0) return false;
+  if (AVO_T_I64(T, start, i) < 0) return false;
   if (T.prefilter) {                                     // PrefilterReads.scala:142-209, as in avo_pack.cpp
     if (!T.pf.contig_kept) return false;
     if (!(rf & 32) && !T.pf.keep_non_primary) return false;
-    if ((rf & 16) && T.mapq[i] >= 0 && !(T.mapq[i] > T.pf.min_mapq)) return false;
+    if ((rf & 16) && AVO_T_MAPQ(T, i) >= 0 && !(AVO_T_MAPQ(T, i) > T.pf.min_mapq)) return false;
     if ((rf & 64) && !T.pf.keep_duplicates) return false;
   }
   return T.keep ? T.keep[i] != 0 : true;
@@ -226,11 +226,12 @@ struct ReadText {
 
 __device__ __forceinline__ ReadText read_text(const DText& T, int64_t i) {
   ReadText t;
-  const int64_t c0 = T.cigar_off[i], m0 = T.md_off[i], s0 = T.seq_off[i], q0 = T.qual_off[i];
-  t.cig = T.cigar + c0; t.ncig = (int)(T.cigar_off[i + 1] - c0);
-  t.md = T.md + m0; t.nmd = (int)(T.md_off[i + 1] - m0);
-  t.seq = T.seq + s0; t.lseq = T.seq_off[i + 1] - s0;
-  t.qual = T.qual + q0; t.lqual = T.qual_off[i + 1] - q0;
+  const int64_t c0 = AVO_T_OFF(T, cigar_off, i), m0 = AVO_T_OFF(T, md_off, i), s0 = AVO_T_OFF(T, seq_off, i),
+                q0 = AVO_T_OFF(T, qual_off, i);
+  t.cig = T.cigar + c0; t.ncig = (int)(AVO_T_OFF(T, cigar_off, i + 1) - c0);
+  t.md = T.md + m0; t.nmd = (int)(AVO_T_OFF(T, md_off, i + 1) - m0);
+  t.seq = T.seq + s0; t.lseq = AVO_T_OFF(T, seq_off, i + 1) - s0;
+  t.qual = T.qual + q0; t.lqual = AVO_T_OFF(T, qual_off, i + 1) - q0;
   t.rf = T.rec_flags[i];
   return t;
 }
@@ -271,8 +272,8 @@ __global__ void __launch_bounds__(128) k_pack_records(DText T, const PackOffsets
   Extracted x{0, 0, 0, false};
   if (keep_ops) x = extract_read<true>(t, out.ops + o.o, out.refb + o.f, &skip);
   else x = extract_read<false>(t, nullptr, nullptr, &skip);
-  const bool has_mapq = (t.rf & 16) && T.mapq[i] >= 0;
-  const int mq = has_mapq ? T.mapq[i] : 0;
+  const bool has_mapq = (t.rf & 16) && AVO_T_MAPQ(T, i) >= 0;
+  const int mq = has_mapq ? AVO_T_MAPQ(T, i) : 0;
   uint32_t qhead = 0;
   for (int k = 0; k < 4 && k < t.lseq; ++k) {
     int q = (k < t.lqual) ? (int)(unsigned char)t.qual[k] - 33 : 0;
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(128) k_pack_records(DText T, const PackOffsets
   const uint8_t flags = (uint8_t)(((t.rf & 2) ? AVO_READ_NEGATIVE_STRAND : 0) | skip | (has_mapq ? 0 : AVO_READ_SKIP_CALL));
   // the record as two 16-byte stores: (start, end, seq_off, op_off | refb_off, n_ops/mapq/flags, qhead, l_seq)
   uint4* rec = reinterpret_cast<uint4*>(out.meta + o.k);
-  rec[0] = make_uint4((uint32_t)(int32_t)T.start[i], (uint32_t)(int32_t)T.end[i], (uint32_t)o.b, (uint32_t)o.o);
+  rec[0] = make_uint4((uint32_t)(int32_t)AVO_T_I64(T, start, i), (uint32_t)(int32_t)AVO_T_I64(T, end, i), (uint32_t)o.b, (uint32_t)o.o);
   rec[1] = make_uint4((uint32_t)o.f, (x.n_ops & 0xFFFFu) | ((uint32_t)(mq > 255 ? 255 : mq) << 16) | ((uint32_t)flags << 24),
                       qhead, (uint32_t)t.lseq);
   if (out.source_index) out.source_index[o.k] = i;
@@ -294,8 +295,8 @@ __global__ void __launch_bounds__(256) k_pack_payload(DText T, const PackOffsets
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   const int sub = threadIdx.x & 15;
   if (i >= T.n || !kept(T, i)) return;
-  const int64_t s0 = T.seq_off[i], q0 = T.qual_off[i];
-  const int64_t lseq = T.seq_off[i + 1] - s0, lqual = T.qual_off[i + 1] - q0;
+  const int64_t s0 = AVO_T_OFF(T, seq_off, i), q0 = AVO_T_OFF(T, qual_off, i);
+  const int64_t lseq = AVO_T_OFF(T, seq_off, i + 1) - s0, lqual = AVO_T_OFF(T, qual_off, i + 1) - q0;
   const unsigned char* seq = reinterpret_cast<const unsigned char*>(T.seq) + s0;
   const unsigned char* qual = reinterpret_cast<const unsigned char*>(T.qual) + q0;
   const int64_t lpad = (lseq + AVO_BLOCK_BASES - 1) / AVO_BLOCK_BASES;

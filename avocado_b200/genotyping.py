@@ -135,6 +135,7 @@ class Context:
             a = cols[name]
             return int(a[n]) if n or len(a) else 0
 
+        t.narrow = 1 if cols.get("narrow") else 0       # batch.narrow_text_columns: 32-bit numeric columns
         t.start, t.end, t.mapq = col("start", np.int64), col("end", np.int64), col("mapq", np.int32)
         t.rec_flags = col("flags", np.uint8)
         for name in ("cigar", "md", "seq", "qual"):

@@ -563,13 +563,13 @@ def run_e2e(args, np, torch, B, Context, own, per, local, world, rank, cpus_per_
 
     def text_of(i):
         sl = hb.slice(shards[i].read_lo, shards[i].read_hi)
-        c = B.text_columns_of(sl)
+        c = B.narrow_text_columns(B.text_columns_of(sl))     # 32-bit positions and offsets, 8-bit mapq (avo_text_reads.narrow)
         qo = c.pop("qual_off")
-        c = {k: pin(v) for k, v in c.items()}
+        c = {k: (pin(v) if isinstance(v, np.ndarray) else v) for k, v in c.items()}
         c["qual_off"] = c["seq_off"] if qo is not None else None
         return c
     tcols = list(pool.map(text_of, range(n_text_bins)))
-    text_bytes = sum(v.nbytes for c in tcols for k, v in c.items() if k != "qual_off")
+    text_bytes = sum(v.nbytes for c in tcols for k, v in c.items() if k != "qual_off" and isinstance(v, np.ndarray))
     n_text = sum(len(c["start"]) for c in tcols)
     reuse = [dict() for _ in range(T)]
     for c in ctxs:

@@ -89,6 +89,12 @@ def test_synthetic_text_packs_to_the_generated_batch(ctx):
     _same(ctx.pack_text_device(cols), host)
     dcols = {k: torch.from_numpy(v).cuda() for k, v in cols.items()}
     _same(ctx.pack_text_device(dcols), host)
+    # 32-bit positions / offsets and 8-bit mapq (avo_text_reads.narrow), host and device resident
+    slim = B.narrow_text_columns(cols)
+    _same(ctx.pack_text_device(slim), host)
+    dslim = {k: (torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v).cuda() if isinstance(v, np.ndarray) else v)
+             for k, v in slim.items()}
+    _same(ctx.pack_text_device(dslim), host)
 
 
 def test_device_packed_batch_genotypes_like_the_oracle(oracle, ctx):

@@ -126,6 +126,28 @@ def test_text_round_trip_reproduces_the_packed_batch(threads):
     cols = B.text_columns_of(b)
     assert cols["cigar_off"][-1] > 4 * n and cols["md_off"][-1] > 3 * n
     _same_batch(b, B.pack_text_columns(cols, threads=threads))
+    # the same text with 32-bit positions / offsets and 8-bit mapq (avo_text_reads.narrow)
+    slim = B.narrow_text_columns(cols)
+    assert slim["start"].dtype == np.int32 and slim["seq_off"].dtype == np.uint32 and slim["mapq"].dtype == np.uint8
+    _same_batch(b, B.pack_text_columns(slim, threads=threads))
+
+
+def test_narrow_text_columns_keep_an_absent_mapq_absent():
+    """mapq = None travels as a cleared flag bit in the narrow form; both forms pack to the same records
+    (PrefilterReads keeps reads without a mapq, PrefilterReads.scala:201-209)."""
+    from avocado_b200 import batch as B
+    from avocado_b200.prefilter import PrefilterReadsArgs, prefilter_struct
+    from avocado_b200.records import AlignmentRecord
+    recs = [AlignmentRecord(readMapped=True, contigName="1", start=10 * i, end=10 * i + 20, sequence="ACGT" * 5, qual="I" * 20,
+                            cigar="20M", mismatchingPositions="20", mapq=(None if i % 3 == 0 else 5 + 10 * (i % 5)),
+                            readName="r%d" % i) for i in range(40)]
+    cols = B.text_columns(recs)
+    pf = prefilter_struct(PrefilterReadsArgs(minMappingQuality=10), "1")
+    wide = B.pack_text_columns(cols, prefilter=pf)
+    slim = B.pack_text_columns(B.narrow_text_columns(cols), prefilter=pf)
+    assert 0 < wide.n_reads < 40
+    _same_batch(wide, slim)
+    assert np.array_equal(wide.source_index, slim.source_index)
 
 
 def test_threaded_packer_matches_serial_on_the_reference_fixtures():

@@ -136,9 +136,10 @@ def _all_gather_rows(x, device=None, group=None):
 
 class ShardedPipeline:
     """Region-sharded discoverAndCall with everything on the device (the C ABI's avo_shard_discover /
-    avo_shard_call / avo_shard_finish around two NCCL all-gathers of fixed-size blocks): the owned slice of
-    every rank's site table, then the result rows of the owned sites.  The host waits once per step, in
-    avo_shard_finish.  `gather(out, inp)` is the collective: torch.distributed's all_gather_into_tensor over
+    avo_shard_call[_direct] / avo_shard_finish): an NCCL all-gather of fixed-size blocks holding the owned
+    slice of every rank's site table, then the result rows of the owned sites -- as a second all-gather
+    (rows_to="all"), a gather to rank 0 ("root"), or stored by every rank's last kernel straight into rank
+    0's columns over NVLink peer memory ("direct").  The host waits once per step, in avo_shard_finish.  `gather(out, inp)` is the collective: torch.distributed's all_gather_into_tensor over
     NCCL by default; tests emulate several ranks on one GPU by passing their own."""
 
     def __init__(self, ctx, rank: int, world: int, own_lo: int, own_hi: int, ploidy: int = 2, site_cap: int = 1 << 15,

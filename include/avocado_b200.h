@@ -345,7 +345,8 @@ int avo_merge_meta(avo_ctx* ctx, int32_t n_parts, const avo_read_meta* const* pa
  * A framework that wants the rows on ONE rank only gathers the rows blocks to that rank and all-gathers just
  * their 32-byte headers (every rank needs the flags in them): the other ranks pass `gathered_rows` with
  * their own block in place and, for the other ranks' blocks, the header with its first word (the row count)
- * set to 0 -- avo_shard_finish then leaves those rows untouched.
+ * set to 0 -- avo_shard_finish then leaves those rows untouched.  Fastest is no rows gather at all:
+ * avo_shard_call_direct (below) stores the rows into the collecting rank's arrays over NVLink.
  * Block sizes come from the plan's capacities (avo_shard_*_block_bytes).  avo_shard_finish returns
  * AVO_E_CAPACITY with the capacities that are needed (identical on every rank: they follow from the
  * gathered headers), or AVO_E_RETRY when some rank ran out of an internal capacity (every rank sees it in

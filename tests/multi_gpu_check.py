@@ -4,7 +4,8 @@
         --master-port 29511 tests/multi_gpu_check.py
 
 Checks, on real GPUs, that (1) region-sharded discoverAndCall (avocado_b200.parallel.ShardedPipeline:
-avo_shard_discover / _call / _finish around two NCCL all-gathers, everything device-resident) returns on
+avo_shard_discover / _call / _finish around two NCCL all-gathers, everything device-resident; then with the
+rows gathered to rank 0 only, then stored into rank 0's columns over CUDA-IPC peer memory) returns on
 every rank exactly the rows a single GPU computes for the whole batch, and (2) sample-sharded joint
 calling (avocado_b200.joint.joint_call_sharded: all-reduce of allele counts and of posterior sums
 over NCCL) reproduces the single-GPU cohort result, and (3) so does the sample-sharded depth roll-up

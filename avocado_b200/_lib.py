@@ -41,7 +41,15 @@ class ReadBatchStruct(C.Structure):
                 ("stats_max_span", C.c_int32), ("stats_valid", C.c_int32),
                 ("meta", P), ("payload", P), ("ops", P), ("refb", P), ("wire_meta", P), ("wire_ops", P),
                 ("wire6_meta", P), ("wire6_oplen", P), ("wire6_opcode", P), ("wire6_exc", P), ("n_wire6_exc", C.c_int64), ("wire6_base", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("events", P)]
+
+
+class ReadEventsStruct(C.Structure):
+    """avo_read_events: discovery's candidate events of a batch (avo_derive_events)."""
+    _fields_ = [("n_snv", C.c_int64), ("n_indel", C.c_int64), ("snv_pos", P), ("snv_pq", P), ("snv_first", P),
+                ("indel_read", P), ("indel_op", P),
+                ("stats_min_start", C.c_int32), ("stats_max_end", C.c_int32), ("stats_max_span", C.c_int32),
+                ("stats_valid", C.c_int32)]
 
 
 class SitesStruct(C.Structure):
@@ -99,7 +107,7 @@ class TimingStruct(C.Structure):
                 ("ms_observe", C.c_float), ("ms_d2h", C.c_float), ("ms_discover_tiles", C.c_float),
                 ("ms_call_tiles", C.c_float), ("n_launches", C.c_int32),
                 ("n_tile_launches", C.c_int32), ("h2d_bytes", C.c_int64),
-                ("d2h_bytes", C.c_int64), ("payload_in_place", C.c_int32), ("reserved", C.c_int32),
+                ("d2h_bytes", C.c_int64), ("payload_in_place", C.c_int32), ("ms_call_pairs", C.c_float),
                 ("gathered_blocks", C.c_int64)]
 
 
@@ -227,7 +235,7 @@ EXPORTED_SYMBOLS = [
     "avo_pack_wire", "avo_pack_wire6", "avo_pack_bounds", "avo_pack_reads", "avo_pack_reads_mt", "avo_pack_reads_device", "avo_synth_default_params",
     "avo_synth_host", "avo_synth_device", "avo_synth_text",
     "avo_merge_meta", "avo_shard_table_block_bytes", "avo_shard_rows_block_bytes", "avo_shard_discover", "avo_shard_call", "avo_shard_finish",
-    "avo_shard_call_direct", "avo_peer_alloc", "avo_peer_open", "avo_peer_close", "avo_peer_free",
+    "avo_shard_call_direct", "avo_peer_alloc", "avo_peer_open", "avo_peer_close", "avo_peer_free", "avo_derive_events",
 ]
 
 _lib = None
@@ -299,6 +307,7 @@ def load():
     lib.avo_peer_open.argtypes = [P, C.c_char_p, C.POINTER(C.c_void_p)]
     lib.avo_peer_close.argtypes = [P, C.c_void_p]
     lib.avo_peer_free.argtypes = [P, C.c_void_p]
+    lib.avo_derive_events.argtypes = [P, C.POINTER(ReadBatchStruct), C.POINTER(ReadEventsStruct)]
     lib.avo_shard_finish.argtypes = [P, C.POINTER(ShardPlanStruct), P, P, C.POINTER(SitesOutStruct),
                                      C.POINTER(SiteResultsStruct), C.POINTER(ShardPlanStruct)]
     _lib = lib

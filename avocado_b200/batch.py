@@ -76,6 +76,9 @@ class ReadBatch:
     wire6_opcode: Optional[np.ndarray] = None  # ... and a code nibble each
     wire6_exc: Optional[np.ndarray] = None
     wire6_base: int = 0
+    # discovery's candidate events (Context.derive_events): dict(snv_pos, snv_pq, snv_first, indel_read, indel_op,
+    # n_snv, n_indel, stats) in the batch's memory; a device batch that has them is discovered by counting them
+    events: Optional[dict] = None
 
     def with_wire6(self, alloc=None, max_exceptions=None):
         """Adds the 6-byte wire columns (host batches): start differences, sizes implied by the
@@ -159,7 +162,20 @@ class ReadBatch:
             s.wire6_oplen, s.wire6_opcode = _ptr(self.wire6_oplen), _ptr(self.wire6_opcode)
             s.wire6_exc = _ptr(self.wire6_exc) if len(self.wire6_exc) else None
             s.n_wire6_exc, s.wire6_base = len(self.wire6_exc), self.wire6_base
+        if self.events is not None:
+            e = self._events_struct = self.events_struct()       # (kept alive with the batch)
+            s.events = C.cast(C.pointer(e), C.c_void_p)
         return s
+
+    def events_struct(self):
+        ev = self.events
+        e = L.ReadEventsStruct()
+        e.n_snv, e.n_indel = ev["n_snv"], ev["n_indel"]
+        for k in ("snv_pos", "snv_pq", "snv_first", "indel_read", "indel_op"):
+            setattr(e, k, _ptr(ev[k]))
+        e.stats_min_start, e.stats_max_end, e.stats_max_span = ev["stats"]
+        e.stats_valid = 1
+        return e
 
     def nbytes(self):
         """Bytes of the packed batch = the algorithmic bytes of one full scan."""
@@ -168,6 +184,13 @@ class ReadBatch:
             a = getattr(self, name)
             tot += a.nbytes if isinstance(a, np.ndarray) else a.numel() * a.element_size()
         return tot
+
+    def events_nbytes(self):
+        """Bytes of the candidate events a device batch carries (0 without)."""
+        if self.events is None:
+            return 0
+        return sum((a.nbytes if isinstance(a, np.ndarray) else a.numel() * a.element_size())
+                   for a in self.events.values() if hasattr(a, "shape"))
 
     def to_device(self, device="cuda:0", pinned=False):
         import torch
@@ -180,6 +203,9 @@ class ReadBatch:
                 t = t.pin_memory()
             setattr(out, name, t.to(device, non_blocking=pinned, **kw))
         out.stats = self.stats
+        if self.events is not None:
+            out.events = {k: (torch.from_numpy(_torch_view(v)).to(device) if isinstance(v, np.ndarray) else v)
+                          for k, v in self.events.items()}
         return out
 
     def to_host(self):
@@ -300,7 +326,7 @@ def _from_torch(t, dtype) -> np.ndarray:
 
 def _device_empty(n, dtype, device):
     import torch
-    tdt = {np.int32: torch.int32, np.uint32: torch.int32, np.uint8: torch.uint8,
+    tdt = {np.int32: torch.int32, np.uint32: torch.int32, np.uint8: torch.uint8, np.uint16: torch.int16,
            np.float64: torch.float64, np.float32: torch.float32, np.int64: torch.int64}[dtype]
     return torch.empty(max(int(n), 1), dtype=tdt, device=device)
 

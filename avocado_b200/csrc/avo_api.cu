@@ -52,7 +52,7 @@ enum Slot {
   SL_AS_RES, SL_AS_START,
   SL_F_IN, SL_F_OUT,
   SL_T_START, SL_T_END, SL_T_MAPQ, SL_T_FLAGS, SL_T_CIGAR, SL_T_CIGAR_OFF, SL_T_MD, SL_T_MD_OFF, SL_T_SEQ,
-  SL_T_SEQ_OFF, SL_T_QUAL, SL_T_QUAL_OFF, SL_T_KEEP, SL_T_COUNTS, SL_T_OFFSETS,
+  SL_T_SEQ_OFF, SL_T_QUAL, SL_T_QUAL_OFF, SL_T_KEEP, SL_T_COUNTS, SL_T_OFFSETS, SL_EV_CSNV, SL_EV_CIND, SL_EV_IFIRST,
   SL_J_PRESENT, SL_J_NALT, SL_J_NREF, SL_J_NOTHER, SL_J_NOCALL, SL_J_GL, SL_J_ALT, SL_J_CALLED, SL_J_OUT,
   SL_JD_DP, SL_JD_REFDP, SL_JD_SB, SL_JD_OUT,
   SL_TABLE, SL_TCOUNT, SL_KEYS_A, SL_KEYS_B, SL_VALS_A, SL_VALS_B, SL_FOOT, SL_AOFF,
@@ -79,11 +79,13 @@ struct avo_ctx {
   // score table cache key
   int lut_minp = -1, lut_maxp = -1, lut_maxq = -1, lut_maxmq = -1;
   avo_timing timing{};
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[10] = {};         // [8], [9]: around k_call_pairs
+  bool pairs_timed = false;
   int64_t indel_guess = 0;         // indel candidates seen by the previous discovery (sizes the table)
   int64_t site_guess = 0;          // survivors / allele nibbles of the previous discovery (+ margin): the
   int64_t nib_guess = 0;           // capacities the next one runs with (checked when its counts arrive)
   int disc_blocks_per_sm = 0;      // resident CTAs of k_discover_tiles per SM (occupancy query, once)
+  int ev_blocks_per_sm = 0;        // ... of k_discover_events
   ShardState* shard = nullptr;     // between avo_shard_discover / _call / _finish
   BatchStats* h_stats = nullptr;   // pinned
   int32_t* h_small = nullptr;      // pinned scratch (16 ints)
@@ -233,6 +235,17 @@ int upload_reads(avo_ctx* ctx, const avo_read_batch* r, bool sparse, DReads* R, 
   R->n_ops = r->n_ops;
   R->n_refb = r->n_refb;
   R->coords = nullptr;             // the dense (start, end) copy: only the host-gathered route's join reads it
+  R->n_snv = R->n_indel = 0;
+  R->snv_pos = nullptr; R->snv_pq = nullptr; R->snv_first = nullptr; R->indel_read = nullptr; R->indel_op = nullptr;
+  if (r->events && r->mem == AVO_MEM_DEVICE && r->n_reads > 0) {     // candidate events: discovery counts them
+    const avo_read_events* e = r->events;
+    if (e->n_snv < 0 || e->n_indel < 0 || !e->snv_first || (e->n_snv > 0 && (!e->snv_pos || !e->snv_pq)) ||
+        (e->n_indel > 0 && (!e->indel_read || !e->indel_op)) || !e->stats.valid)
+      return fail(ctx, AVO_E_INVALID, "reads->events is incomplete (fill it with avo_derive_events)");
+    R->n_snv = e->n_snv; R->n_indel = e->n_indel;
+    R->snv_pos = e->snv_pos; R->snv_pq = e->snv_pq; R->snv_first = e->snv_first;
+    R->indel_read = e->indel_read; R->indel_op = e->indel_op;
+  }
   if (r->wire6_meta && r->mem == AVO_MEM_HOST) {
     // 6-byte records: starts, ends, lengths and offsets are rebuilt on the device; two head qualities
     const avo_read_wire6* dw;
@@ -325,6 +338,12 @@ float ev_ms(avo_ctx* ctx, int a, int b) {
 
 // The caller's bounds (avo_batch_stats), to be verified on the device by the discovery kernel.
 bool stats_from_hints(const avo_read_batch* r, BatchStats* h) {
+  if (r->events && r->mem == AVO_MEM_DEVICE && r->events->stats.valid && r->n_reads > 0) {
+    // measured by avo_derive_events together with the sort order: exact
+    h->min_start = r->events->stats.min_start; h->max_end = r->events->stats.max_end; h->max_span = r->events->stats.max_span;
+    h->unsorted = 0;
+    return true;
+  }
   if (!r->stats.valid || r->n_reads == 0) return false;
   if (r->stats.max_end < r->stats.min_start || r->stats.max_span < 0) return false;
   h->min_start = r->stats.min_start; h->max_end = r->stats.max_end; h->max_span = r->stats.max_span;
@@ -750,6 +769,7 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
       }
     }
     CKS(get_buf(ctx, SL_C_BUCKETS, n_slots * 4, &d_buckets));
+    ctx->pairs_timed = false;
     if (ctx->gather_src) {
       // host-gathered payload: the joined reads are listed first (the host copies the blocks they need)
       nvtxRangePushA(T_TREE_JOIN);
@@ -766,7 +786,8 @@ int call_internal(avo_ctx* ctx, const DReads& R, const BatchStats& hs, const Dev
       // device-resident payload: join and observation are one pass over the bucket slots
       Range r_obs(T_TREE_JOIN " / " T_OBSERVE_READS " / " T_EMIT_GENOTYPES);
       CK(launch_call_pairs_reduce(R, S, X, C, P, D, (const int32_t*)d_rbase, (const uint32_t*)d_blen, (const uint64_t*)d_boff,
-                                  (uint32_t*)d_buckets, n_slots, ctx->num_sms, ctx->stream, &nl));
+                                  (uint32_t*)d_buckets, n_slots, ctx->num_sms, ctx->stream, &nl, ctx->ev[8], ctx->ev[9]));
+      ctx->pairs_timed = work;
     }
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
     if (fresh) {                            // the caller checks *h_slots against *slots_cap after its sync
@@ -953,8 +974,12 @@ int discover_enqueue(avo_ctx* ctx, const DReads& R, const BatchStats& hs, bool v
   ctx->timing.n_launches += 1;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   int nl = 0;
-  CK(launch_discover_tiles(R, p->min_phred_discover, p->min_obs_discover, X, hs, verify ? 1 : 0, U, Lst,
-                           small + SW_TILE, small + SW_FLAGS, ctx->num_sms, &ctx->disc_blocks_per_sm, ctx->stream, &nl));
+  if (R.snv_first)
+    CK(launch_discover_events(R, p->min_phred_discover, p->min_obs_discover, X, hs, U, Lst, small + SW_TILE, small + SW_FLAGS,
+                              ctx->num_sms, &ctx->ev_blocks_per_sm, ctx->stream, &nl));
+  else
+    CK(launch_discover_tiles(R, p->min_phred_discover, p->min_obs_discover, X, hs, verify ? 1 : 0, U, Lst,
+                             small + SW_TILE, small + SW_FLAGS, ctx->num_sms, &ctx->disc_blocks_per_sm, ctx->stream, &nl));
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timing.n_tile_launches += nl;
   CK(launch_indel_group(R, Lst, d_table, d_tcount, tsize, p->min_obs_discover, U, small + SW_FLAGS, ctx->num_sms,
@@ -1059,6 +1084,7 @@ int finish_call(avo_ctx* ctx, bool did_discover, bool did_call) {
   if (did_call) t.ms_observe = did_discover ? ev_ms(ctx, 6, 5) : ev_ms(ctx, 1, 5);
   if (did_discover) t.ms_discover_tiles = ev_ms(ctx, 2, 3);
   if (did_call) t.ms_call_tiles = ev_ms(ctx, 4, 5);
+  if (did_call && ctx->pairs_timed) t.ms_call_pairs = ev_ms(ctx, 8, 9);
   t.ms_d2h = did_call ? ev_ms(ctx, 5, 7) : ev_ms(ctx, 6, 7);
   return AVO_OK;
 }
@@ -1508,6 +1534,104 @@ int avo_shard_call_direct(avo_ctx* ctx, const avo_cnv* cnv, const avo_params* pa
   return AVO_OK;
 }
 
+// host form of walk_events (avo_discover.cu): the same events in the same order
+static int derive_events_host(avo_ctx* ctx, const avo_read_batch* r, avo_read_events* ev) {
+  if (r->wire_meta || r->wire6_meta) return fail(ctx, AVO_E_INVALID, "avo_derive_events needs the full records of a host batch");
+  const int64_t n = r->n_reads, scap = ev->n_snv, icap = ev->n_indel;
+  int64_t ns = 0, ni = 0;
+  int32_t mn = INT32_MAX, mxe = INT32_MIN, mxs = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const avo_read_meta& m = r->meta[i];
+    if ((i & 31) == 0) ev->snv_first[i >> 5] = (uint32_t)ns;
+    if (i > 0 && r->meta[i - 1].start > m.start) return fail(ctx, AVO_E_UNSORTED, "reads are not sorted by start");
+    mn = std::min(mn, m.start); mxe = std::max(mxe, m.end); mxs = std::max(mxs, m.end - m.start);
+    int32_t pos = m.start;
+    uint32_t rb = m.refb_off;
+    bool ff = true;
+    for (uint32_t k = 0; k < m.n_ops; ++k) {
+      const uint32_t op = r->ops[m.op_off + k], len = op >> 4, code = op & 15u;
+      const bool isX = code == AVO_OP_MISMATCH, isD = code == AVO_OP_DEL, aligned = code <= AVO_OP_MISMATCH;
+      if (isX)
+        for (uint32_t j = 0; j < len; ++j) {
+          const uint32_t q = (j < 4u) ? ((m.qhead >> (8 * j)) & 255u)
+                                      : r->payload[((size_t)(m.seq_off + j / AVO_BLOCK_BASES) << 4) + 5 + j % AVO_BLOCK_BASES];
+          if (ns < scap) { ev->snv_pos[ns] = pos + (int32_t)j; ev->snv_pq[ns] = (uint16_t)(((uint32_t)r->refb[rb + j] << 8) | q); }
+          ++ns;
+        }
+      if ((code == AVO_OP_INS || isD) && !ff) {
+        if (ni < icap) { ev->indel_read[ni] = (int32_t)i; ev->indel_op[ni] = k; }
+        ++ni;
+      }
+      pos += (aligned || isD) ? (int32_t)len : 0;
+      rb += isX ? len : isD ? ((len + 1) >> 1) : 0u;
+      ff = ff && !aligned;
+    }
+  }
+  ev->snv_first[(n + 31) >> 5] = (uint32_t)ns;
+  ev->n_snv = ns; ev->n_indel = ni;
+  if (ns > scap || ni > icap) return fail(ctx, AVO_E_CAPACITY, "events need %lld + %lld entries", (long long)ns, (long long)ni);
+  ev->stats.min_start = n ? mn : 0; ev->stats.max_end = n ? mxe : 0; ev->stats.max_span = mxs; ev->stats.valid = 1;
+  return AVO_OK;
+}
+
+int avo_derive_events(avo_ctx* ctx, const avo_read_batch* reads, avo_read_events* ev) {
+  // host batches need no device: ctx may be NULL for them (a host-side packer's last step)
+  if (!ctx && !(reads && reads->mem == AVO_MEM_HOST)) return AVO_E_INVALID;
+  if (ctx) CKS(begin_call(ctx));
+  CKS(validate_reads(ctx, reads));
+  if (!ev || !ev->snv_first || ev->n_snv < 0 || ev->n_indel < 0 || (ev->n_snv > 0 && (!ev->snv_pos || !ev->snv_pq)) ||
+      (ev->n_indel > 0 && (!ev->indel_read || !ev->indel_op)))
+    return fail(ctx, AVO_E_INVALID, "events needs its arrays and their capacities");
+  ev->stats.valid = 0;
+  const int64_t n = reads->n_reads;
+  if (reads->mem == AVO_MEM_HOST && n > 0) return derive_events_host(ctx, reads, ev);
+  if (n == 0) {
+    if (reads->mem == AVO_MEM_DEVICE) CK(cudaMemsetAsync(ev->snv_first, 0, sizeof(uint32_t), ctx->stream));
+    else ev->snv_first[0] = 0;
+    ev->n_snv = ev->n_indel = 0;
+    ev->stats.min_start = ev->stats.max_end = ev->stats.max_span = 0; ev->stats.valid = 1;
+    if (reads->mem == AVO_MEM_DEVICE) CK(cudaStreamSynchronize(ctx->stream));
+    return AVO_OK;
+  }
+  CK(cudaSetDevice(ctx->device));
+  DReads R{};
+  R.n = n; R.contig = reads->contig_id; R.meta = reads->meta; R.payload = reads->payload; R.ops = reads->ops; R.refb = reads->refb;
+  R.n_ops = reads->n_ops; R.n_refb = reads->n_refb;
+  const int64_t nw = (n + 31) >> 5;
+  void *c_snv, *c_ind, *i_first, *d_stats, *d_temp;
+  CKS(get_buf(ctx, SL_EV_CSNV, (size_t)(nw + 1) * 4, &c_snv));
+  CKS(get_buf(ctx, SL_EV_CIND, (size_t)(nw + 1) * 4, &c_ind));
+  CKS(get_buf(ctx, SL_EV_IFIRST, (size_t)(nw + 1) * 4, &i_first));
+  CKS(get_buf(ctx, SL_STATS, sizeof(BatchStats), &d_stats));
+  const size_t tb = events_scan_temp_bytes(nw + 1);
+  CKS(get_buf(ctx, SL_TEMP, tb, &d_temp));
+  const BatchStats init{INT32_MAX, INT32_MIN, 0, 0};
+  CK(cudaMemcpyAsync(d_stats, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync((uint32_t*)c_snv + nw, 0, 4, ctx->stream));
+  CK(cudaMemsetAsync((uint32_t*)c_ind + nw, 0, 4, ctx->stream));
+  CK(launch_events_count(R, (uint32_t*)c_snv, (uint32_t*)c_ind, (BatchStats*)d_stats, ctx->stream));
+  CK(launch_events_scan((const uint32_t*)c_snv, ev->snv_first, nw + 1, d_temp, tb, ctx->stream));
+  CK(launch_events_scan((const uint32_t*)c_ind, (uint32_t*)i_first, nw + 1, d_temp, tb, ctx->stream));
+  uint32_t tot[2];
+  CK(cudaMemcpyAsync(&tot[0], ev->snv_first + nw, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&tot[1], (uint32_t*)i_first + nw, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_stats, d_stats, sizeof(BatchStats), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing.n_launches += 3;
+  if (ctx->h_stats->unsorted) return fail(ctx, AVO_E_UNSORTED, "reads are not sorted by start");
+  const int64_t scap = ev->n_snv, icap = ev->n_indel;
+  ev->n_snv = tot[0]; ev->n_indel = tot[1];
+  if ((int64_t)tot[0] > scap || (int64_t)tot[1] > icap)
+    return fail(ctx, AVO_E_CAPACITY, "events need %u + %u entries", tot[0], tot[1]);
+  CK(launch_events_write(R, ev->snv_first, (const uint32_t*)i_first, scap, icap, ev->snv_pos, ev->snv_pq, ev->indel_read,
+                         ev->indel_op, ctx->stream));
+  ctx->timing.n_launches += 1;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ev->stats.min_start = ctx->h_stats->min_start; ev->stats.max_end = ctx->h_stats->max_end;
+  ev->stats.max_span = ctx->h_stats->max_span; ev->stats.valid = 1;
+  return AVO_OK;
+}
+
 int avo_peer_alloc(avo_ctx* ctx, int64_t bytes, void** ptr, unsigned char* handle) {
   if (!ctx || !ptr || !handle || bytes <= 0) return ctx ? fail(ctx, AVO_E_INVALID, "bad argument") : AVO_E_INVALID;
   static_assert(sizeof(cudaIpcMemHandle_t) == AVO_PEER_HANDLE_BYTES, "CUDA IPC handle size");
@@ -1601,6 +1725,7 @@ int avo_shard_finish(avo_ctx* ctx, const avo_shard_plan* pl, const void* gathere
   ctx->timing.ms_discover = ev_ms(ctx, 1, 6);
   ctx->timing.ms_discover_tiles = ev_ms(ctx, 2, 3);
   ctx->timing.ms_call_tiles = ev_ms(ctx, 4, 5);
+  if (ctx->pairs_timed) ctx->timing.ms_call_pairs = ev_ms(ctx, 8, 9);
   if (flags & SHARD_UNSORTED) return fail(ctx, AVO_E_UNSORTED, "reads are not sorted by start (on some rank)");
   if (flags & SHARD_BAD_STATS) return fail(ctx, AVO_E_INVALID, "reads->stats does not bound the batch (on some rank)");
   if (needed) {

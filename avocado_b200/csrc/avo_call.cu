@@ -586,12 +586,15 @@ cudaError_t launch_call_join(const DReads& R, const DSites& S, const DIndex& X, 
 // device-resident batches: join + observation over the bucket slots, then the per-site reduction
 cudaError_t launch_call_pairs_reduce(const DReads& R, const DSites& S, const DIndex& X, const DCnv& C, const DCallParams& P,
                                      const DResults& out, const int32_t* rbase, const uint32_t* blen, const uint64_t* boff,
-                                     uint32_t* buckets, size_t n_slots, int num_sms, cudaStream_t s, int* n_launches) {
+                                     uint32_t* buckets, size_t n_slots, int num_sms, cudaStream_t s, int* n_launches,
+                                     cudaEvent_t before_pairs, cudaEvent_t after_pairs) {
   if (R.n == 0 || S.c_hi <= S.c_lo) return cudaSuccess;
   int blocks_per_sm = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_call_pairs, OBS_THREADS, 0);
   if (e != cudaSuccess) return e;
+  if (before_pairs && (e = cudaEventRecord(before_pairs, s)) != cudaSuccess) return e;
   k_call_pairs<<<num_sms * max(1, blocks_per_sm), OBS_THREADS, 0, s>>>(R, S, X, C, P, rbase, boff, buckets, (uint64_t)n_slots);
+  if (after_pairs && (e = cudaEventRecord(after_pairs, s)) != cudaSuccess) return e;
   const int32_t n = S.c_hi - S.c_lo;
   if (P.ns <= 3)
     k_call_reduce<3><<<(n + 127) / 128, 128, 0, s>>>(S, P, out, boff, blen, buckets, (uint64_t)n_slots);

@@ -11,6 +11,7 @@
 // exactly by a verified hash table (k_indel_count).  Survivors are sorted and materialised by
 // assemble_sites().
 #include <cub/block/block_scan.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "avo_device.cuh"
 
@@ -458,6 +459,386 @@ cudaError_t launch_discover_tiles(const DReads& R, int32_t thr, int32_t min_obs,
                                                  hstats.max_end, verify, out, indels, d_tile_counter,
                                                  d_flags);
   if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+// ---- candidate events: derived once per batch (avo_derive_events), counted per call ---------------------
+// The per-read part of DiscoverVariants.variantsInRead with nothing filtered: every mismatching base with the
+// quality the reference tests (qual(i), i counted inside the run: walk_mismatch), every I / D operator after
+// the first aligned one.
+template <typename SnvF, typename IndelF>
+__device__ __forceinline__ void walk_events(const DReads& R, const MetaA& a, const MetaB& m, SnvF&& snv, IndelF&& indel) {
+  int32_t pos = a.start;
+  uint32_t rb = m.refb_off;
+  bool ff = true;
+  for (uint32_t k = 0; k < m.n_ops; ++k) {
+    const uint32_t op = __ldg(R.ops + a.op_off + k);
+    const uint32_t len = op >> 4, code = op & 15u;
+    const bool isX = code == AVO_OP_MISMATCH, isD = code == AVO_OP_DEL, aligned = code <= AVO_OP_MISMATCH;
+    if (isX)
+      for (uint32_t i = 0; i < len; ++i) {
+        const uint32_t q = (i < 4u) ? ((m.qhead >> (8 * i)) & 255u) : pl_qual(R.payload, a.seq_off, i);
+        snv(pos + (int32_t)i, (uint32_t)__ldg(R.refb + rb + i), q);
+      }
+    if ((code == AVO_OP_INS || isD) && !ff) indel(k);                     // :215-242
+    pos += (aligned || isD) ? (int32_t)len : 0;
+    rb += isX ? len : isD ? ((len + 1) >> 1) : 0u;
+    ff = ff && !aligned;
+  }
+}
+
+// one thread per read, a warp = 32 consecutive reads = one entry of the per-32-reads counts
+__global__ void __launch_bounds__(256)
+k_events_count(DReads R, uint32_t* __restrict__ c_snv, uint32_t* __restrict__ c_ind, BatchStats* __restrict__ st) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t ns = 0, ni = 0;
+  int32_t mn = INT32_MAX, mxe = INT32_MIN, mxs = 0, uns = 0;
+  if (r < R.n) {
+    const MetaA a = load_meta_a(R.meta, r);
+    const MetaB m = load_meta_b(R.meta, r);
+    mn = a.start; mxe = a.end; mxs = a.end - a.start;
+    if (r > 0 && meta_start(R.meta, r - 1) > a.start) uns = 1;
+    walk_events(R, a, m, [&](int32_t, uint32_t, uint32_t) { ++ns; }, [&](uint32_t) { ++ni; });
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ns += __shfl_xor_sync(0xFFFFFFFFu, ns, o);
+    ni += __shfl_xor_sync(0xFFFFFFFFu, ni, o);
+    mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+    mxe = max(mxe, __shfl_xor_sync(0xFFFFFFFFu, mxe, o));
+    mxs = max(mxs, __shfl_xor_sync(0xFFFFFFFFu, mxs, o));
+    uns |= __shfl_xor_sync(0xFFFFFFFFu, uns, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (r & ~(int64_t)31) < R.n) {
+    c_snv[r >> 5] = ns;
+    c_ind[r >> 5] = ni;
+    atomicMin(&st->min_start, mn);
+    atomicMax(&st->max_end, mxe);
+    atomicMax(&st->max_span, mxs);
+    if (uns) atomicOr(&st->unsorted, 1);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_events_write(DReads R, const uint32_t* __restrict__ snv_first, const uint32_t* __restrict__ ind_first, int64_t snv_cap,
+               int64_t ind_cap, int32_t* __restrict__ snv_pos, uint16_t* __restrict__ snv_pq,
+               int32_t* __restrict__ indel_read, uint32_t* __restrict__ indel_op) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  if ((r & ~(int64_t)31) >= R.n) return;                       // (whole warps only)
+  MetaA a{};
+  MetaB m{};
+  uint32_t ns = 0, ni = 0;
+  if (r < R.n) {
+    a = load_meta_a(R.meta, r);
+    m = load_meta_b(R.meta, r);
+    walk_events(R, a, m, [&](int32_t, uint32_t, uint32_t) { ++ns; }, [&](uint32_t) { ++ni; });
+  }
+  uint32_t ps = ns, pi = ni;                                   // inclusive scans over the warp
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t ys = __shfl_up_sync(0xFFFFFFFFu, ps, d), yi = __shfl_up_sync(0xFFFFFFFFu, pi, d);
+    if (lane >= d) { ps += ys; pi += yi; }
+  }
+  if (r >= R.n) return;
+  int64_t es = (int64_t)__ldg(snv_first + (r >> 5)) + (ps - ns), ei = (int64_t)__ldg(ind_first + (r >> 5)) + (pi - ni);
+  walk_events(R, a, m,
+              [&](int32_t pos, uint32_t pair, uint32_t q) {
+                if (es < snv_cap) { snv_pos[es] = pos; snv_pq[es] = (uint16_t)((pair << 8) | q); }
+                ++es;
+              },
+              [&](uint32_t k) {
+                if (ei < ind_cap) { indel_read[ei] = (int32_t)r; indel_op[ei] = k; }
+                ++ei;
+              });
+}
+
+cudaError_t launch_events_count(const DReads& R, uint32_t* c_snv, uint32_t* c_ind, BatchStats* d_stats, cudaStream_t s) {
+  if (R.n == 0) return cudaSuccess;
+  k_events_count<<<(unsigned)((R.n + 255) / 256), 256, 0, s>>>(R, c_snv, c_ind, d_stats);
+  return cudaGetLastError();
+}
+
+size_t events_scan_temp_bytes(int64_t n) {
+  size_t a = 0;
+  cub::DeviceScan::ExclusiveSum((void*)nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+  return a + 256;
+}
+cudaError_t launch_events_scan(const uint32_t* counts, uint32_t* first, int64_t n, void* d_temp, size_t temp_bytes, cudaStream_t s) {
+  return cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, counts, first, (int)n, s);
+}
+
+cudaError_t launch_events_write(const DReads& R, const uint32_t* snv_first, const uint32_t* ind_first, int64_t snv_cap,
+                                int64_t ind_cap, int32_t* snv_pos, uint16_t* snv_pq, int32_t* indel_read, uint32_t* indel_op,
+                                cudaStream_t s) {
+  if (R.n == 0) return cudaSuccess;
+  k_events_write<<<(unsigned)((R.n + 255) / 256), 256, 0, s>>>(R, snv_first, ind_first, snv_cap, ind_cap, snv_pos, snv_pq,
+                                                             indel_read, indel_op);
+  return cudaGetLastError();
+}
+
+// Discovery over a batch that carries its events.  Tiles of EV_W positions (larger than k_discover_tiles': a
+// tile's work is only its events, a few hundred per 2048 positions, so the per-tile costs -- barriers, the
+// bounds look-ups, clearing the counters -- are what has to be amortised); the candidates of a tile are the
+// events of the reads that can reach it -- [snv_first[rLo / 32], snv_first[ceil(rHi / 32)]): a superset whose
+// surplus (events of up to 31 reads on either side) lies outside the window and is dropped by the window test
+// -- streamed with coalesced 4 + 2 byte loads.  The same 16-bit counters per (position, alternate base) as
+// k_discover_tiles; the event that lifts a counter over minObservations notes (position, base) in a list, so
+// emission looks at the survivors instead of scanning the window (the scan remains for lists that overflow:
+// minObservations unset makes every candidate a survivor).
+#ifndef AVO_EV_W
+#define AVO_EV_W 2048
+#endif
+#ifndef AVO_EV_THREADS
+#define AVO_EV_THREADS 128
+#endif
+constexpr int EV_W = AVO_EV_W;
+constexpr int EV_THREADS = AVO_EV_THREADS;
+constexpr int EV_WARPS = EV_THREADS / 32;
+constexpr int EV_HOT = 1024;
+constexpr int EV_UNROLL = 4;          // events requested per thread before the first is counted
+static_assert(EV_W % DISC_W == 0 && EV_W % (4 * EV_THREADS) == 0, "event tiles are whole discovery tiles");
+struct __align__(16) EvSmem {
+  uint32_t cnt[2][EV_W];
+  uint32_t refm[EV_W / 8];
+  uint32_t hist[DISC_HB][256];
+  typename cub::BlockScan<int, EV_THREADS>::TempStorage scan;
+  int64_t bounds[4];                    // (first, last) event of the current / next tile
+  int32_t hot[EV_HOT];                  // (window offset << 2) | alternate base index
+  int32_t n_hot;
+  int32_t exotic;
+  int32_t hotpos[DISC_HB];
+};
+
+__global__ void __launch_bounds__(EV_THREADS)
+k_discover_events(DReads R, DIndex X, int32_t thr, int32_t min_count, int32_t n_tiles, int32_t max_span, DDiscoverOut out) {
+  extern __shared__ __align__(16) unsigned char disc_smem_raw[];
+  EvSmem& sm = *reinterpret_cast<EvSmem*>(disc_smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int BPT = EV_W / IDX_G;
+  constexpr int PER_T = EV_W / EV_THREADS;
+  const int64_t n_w = (R.n + 31) >> 5;
+
+  auto clear_counters = [&]() {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < PER_T / 4; ++j) {
+      reinterpret_cast<uint4*>(sm.cnt[0])[tid + j * EV_THREADS] = z;
+      reinterpret_cast<uint4*>(sm.cnt[1])[tid + j * EV_THREADS] = z;
+    }
+    for (int i = tid; i < EV_W / 8; i += EV_THREADS) sm.refm[i] = 0;
+  };
+  // lanes 0 and 1 fetch the NEXT tile's bounds (read index -> event index: two dependent look-ups) while the
+  // current tile is counted; tiles are taken in strides of the grid (their work is uniform)
+  auto fetch_bounds = [&](int32_t t, int slot) {
+    if (tid >= 2) return;
+    int64_t v = 0;
+    if (t < n_tiles) {
+      const int64_t w = (int64_t)X.win0 + (int64_t)t * EV_W;
+      if (tid == 0) {
+        const int32_t rLo = __ldg(X.ridx + idx_bin_floor(X, w - max_span));
+        v = __ldg(R.snv_first + (rLo >> 5));
+      } else {
+        const int32_t rHi = __ldg(X.ridx + (int32_t)min((int64_t)(t + 1) * BPT, (int64_t)X.nb));
+        v = min((int64_t)__ldg(R.snv_first + min(((int64_t)rHi + 31) >> 5, n_w)), R.n_snv);
+      }
+    }
+    sm.bounds[slot * 2 + tid] = v;
+  };
+  clear_counters();
+  fetch_bounds(blockIdx.x, 0);
+  if (tid == 0) { sm.exotic = 0; sm.n_hot = 0; }
+  int it = 0;
+  for (int32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    __syncthreads();                      // counters cleared, flags reset, this tile's bounds in place
+    const int64_t eLo = sm.bounds[(it & 1) * 2], eHi = sm.bounds[(it & 1) * 2 + 1];
+    fetch_bounds(tile + (int32_t)gridDim.x, (it + 1) & 1);
+    if (eLo >= eHi) continue;
+    const int64_t wlo = (int64_t)X.win0 + (int64_t)tile * EV_W;
+    const int32_t wlo32 = (int32_t)wlo;
+    const bool counted = (eHi - eLo) < 32768 && min_count < 32767;      // 16-bit fields cannot overflow
+    if (counted) {
+      for (int64_t e0 = eLo + tid; e0 < eHi; e0 += EV_UNROLL * EV_THREADS) {
+       uint32_t pqs[EV_UNROLL], pos_s[EV_UNROLL];
+#pragma unroll
+       for (int u = 0; u < EV_UNROLL; ++u) {
+         const int64_t e = e0 + (int64_t)u * EV_THREADS;
+         const bool in = e < eHi;
+         pqs[u] = in ? (uint32_t)__ldg(R.snv_pq + e) : 0u;
+         pos_s[u] = in ? (uint32_t)__ldg(R.snv_pos + e) : (uint32_t)wlo32 - 1u;      // (outside every window)
+       }
+#pragma unroll
+       for (int u = 0; u < EV_UNROLL; ++u) {
+        const uint32_t pq = pqs[u];
+        const uint32_t o = pos_s[u] - (uint32_t)wlo32;
+        if (o >= (uint32_t)EV_W) continue;
+        if ((int32_t)(pq & 255u) < thr) continue;
+        const uint32_t refn = (pq >> 12) & 15u, altn = (pq >> 8) & 15u;
+        // A C G T are the nibbles 1 2 4 8 (bits of 0x116); anything else takes the exact path
+        if (!(((0x116u >> refn) & (0x116u >> altn)) & 1u)) { sm.exotic = 1; continue; }
+        const int ai = (int)((altn >> 1) - (altn >> 3));                // 1 2 4 8 -> 0 1 2 3
+        const int sh = (ai & 1) * 16;
+        const uint32_t old = atomicAdd(&sm.cnt[ai >> 1][o], 1u << sh);
+        atomicOr(&sm.refm[o >> 3], refn << ((o & 7) * 4));
+        if ((int32_t)((old >> sh) & 0xFFFFu) == min_count) {             // this event makes it a survivor
+          const int k = atomicAdd(&sm.n_hot, 1);
+          if (k < EV_HOT) sm.hot[k] = (int32_t)((o << 2) | (uint32_t)ai);
+        }
+       }
+      }
+    }
+    __syncthreads();
+    bool slow = !counted || sm.exotic != 0;
+    const int n_hot = sm.n_hot;
+    if (!slow && n_hot <= EV_HOT) {
+      // ---- emission from the survivor list (a position whose reads disagree about its reference base: exact path)
+      bool bad = false;
+      for (int k = tid; k < n_hot; k += EV_THREADS) {
+        const uint32_t o = (uint32_t)sm.hot[k] >> 2;
+        bad = bad || __popc((sm.refm[o >> 3] >> ((o & 7) * 4)) & 15u) != 1;
+      }
+      slow = __syncthreads_or(bad);
+      if (!slow) {
+        for (int k = tid; k < n_hot; k += EV_THREADS) {
+          const uint32_t o = (uint32_t)sm.hot[k] >> 2;
+          const int ai = sm.hot[k] & 3;
+          const uint32_t refn = (sm.refm[o >> 3] >> ((o & 7) * 4)) & 15u;
+          const int32_t c = (int32_t)((sm.cnt[ai >> 1][o] >> ((ai & 1) * 16)) & 0xFFFFu);
+          disc_emit_snv(out, (int32_t)(wlo + o), (refn << 4) | (1u << ai), c);
+        }
+        __syncthreads();
+        clear_counters();
+        if (tid == 0) { sm.exotic = 0; sm.n_hot = 0; }
+        continue;
+      }
+    } else if (!slow) {
+      // ---- more survivors than the list holds: scan the window (four positions per word operation)
+      const uint32_t bias = (uint32_t)(0x7FFF - min_count) * 0x00010001u;
+      bool bad = false;
+      for (int j = 0; j < PER_T / 4; ++j) {
+        const int o4 = tid + j * EV_THREADS;
+        const uint4 vAC = reinterpret_cast<const uint4*>(sm.cnt[0])[o4];
+        const uint4 vGT = reinterpret_cast<const uint4*>(sm.cnt[1])[o4];
+        const uint32_t wa[4] = {vAC.x, vAC.y, vAC.z, vAC.w};
+        const uint32_t wg[4] = {vGT.x, vGT.y, vGT.z, vGT.w};
+        for (int e = 0; e < 4; ++e)
+          if (((wa[e] + bias) | (wg[e] + bias)) & 0x80008000u) {
+            const int o = 4 * o4 + e;
+            bad = bad || __popc((sm.refm[o >> 3] >> ((o & 7) * 4)) & 15u) != 1;
+          }
+      }
+      slow = __syncthreads_or(bad);
+      if (!slow) {
+        for (int j = 0; j < PER_T / 4; ++j) {
+          const int o4 = tid + j * EV_THREADS;
+          for (int e = 0; e < 4; ++e) {
+            const int o = 4 * o4 + e;
+            const uint32_t wAC = sm.cnt[0][o], wGT = sm.cnt[1][o];
+            if (!(((wAC + bias) | (wGT + bias)) & 0x80008000u)) continue;
+            const uint32_t refn = (sm.refm[o >> 3] >> ((o & 7) * 4)) & 15u;
+            const int32_t c[4] = {(int32_t)(wAC & 0xFFFFu), (int32_t)(wAC >> 16), (int32_t)(wGT & 0xFFFFu),
+                                  (int32_t)(wGT >> 16)};
+            for (int ai = 0; ai < 4; ++ai)
+              if (c[ai] > min_count) disc_emit_snv(out, (int32_t)(wlo + o), (refn << 4) | (1u << ai), c[ai]);
+          }
+        }
+        __syncthreads();
+        clear_counters();
+        if (tid == 0) { sm.exotic = 0; sm.n_hot = 0; }
+        continue;
+      }
+    }
+
+    // ---- slow path (non-ACGT candidate bases, inconsistent reference bases, or extreme depth): exact.
+    // Per-position candidate totals, then (ref, alt) histograms of the positions whose total exceeds the
+    // threshold, DISC_HB positions at a time -- over the same event range.
+    auto each = [&](auto&& f) {
+      for (int64_t e = eLo + tid; e < eHi; e += EV_THREADS) {
+        const uint32_t pq = __ldg(R.snv_pq + e);
+        if ((int32_t)(pq & 255u) < thr) continue;
+        const uint32_t o = (uint32_t)__ldg(R.snv_pos + e) - (uint32_t)wlo32;
+        if (o < (uint32_t)EV_W) f(o, pq >> 8);
+      }
+    };
+    __syncthreads();
+    clear_counters();
+    __syncthreads();
+    each([&](uint32_t o, uint32_t) { atomicAdd(&sm.cnt[0][o], 1u); });
+    __syncthreads();
+    int nh = 0;
+    uint32_t hot_mask = 0;
+    static_assert(PER_T <= 32, "one bit per owned position");
+    for (int i = 0; i < PER_T; ++i) {
+      const bool is_hot = (int32_t)sm.cnt[0][tid * PER_T + i] > min_count;
+      hot_mask |= (uint32_t)is_hot << i;
+      nh += is_hot;
+    }
+    int hoff, htotal;
+    cub::BlockScan<int, EV_THREADS>(sm.scan).ExclusiveSum(nh, hoff, htotal);
+    for (int i = 0; i < PER_T; ++i) {
+      const bool is_hot = (hot_mask >> i) & 1u;
+      sm.cnt[0][tid * PER_T + i] = is_hot ? (uint32_t)hoff : NOT_HOT;
+      hoff += is_hot;
+    }
+    __syncthreads();
+    for (int hb = 0; hb < htotal; hb += DISC_HB) {
+      for (int i = tid; i < DISC_HB * 256; i += EV_THREADS) (&sm.hist[0][0])[i] = 0;
+      __syncthreads();
+      each([&](uint32_t o, uint32_t pair) {
+        const uint32_t h = sm.cnt[0][o];
+        if (h == NOT_HOT || (int)h < hb || (int)h >= hb + DISC_HB) return;
+        atomicAdd(&sm.hist[h - hb][pair & 255u], 1u);
+      });
+      __syncthreads();
+      for (int i = tid; i < EV_W; i += EV_THREADS) {
+        const uint32_t h = sm.cnt[0][i];
+        if (h != NOT_HOT && (int)h >= hb && (int)h < hb + DISC_HB) sm.hotpos[h - hb] = i;
+      }
+      __syncthreads();
+      for (int s = warp; s < min(DISC_HB, htotal - hb); s += EV_WARPS) {
+        const int i = sm.hotpos[s];
+        for (int k = lane; k < 256; k += 32) {
+          const int32_t c = (int32_t)sm.hist[s][k];
+          if (c > min_count) disc_emit_snv(out, (int32_t)(wlo + i), (uint32_t)k, c);
+        }
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    clear_counters();
+    if (tid == 0) { sm.exotic = 0; sm.n_hot = 0; }
+  }
+}
+
+// every I / D event once: quality test and candidate (disc_handle_indel replays the read up to the operator)
+__global__ void __launch_bounds__(256)
+k_indel_events(DReads R, DIndelList L, int32_t thr) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= R.n_indel) return;
+  const int32_t r = __ldg(R.indel_read + e);
+  if (r < 0 || r >= R.n) return;
+  disc_handle_indel(R, L, r, __ldg(R.indel_op + e), thr);
+}
+
+cudaError_t launch_discover_events(const DReads& R, int32_t thr, int32_t min_obs, const DIndex& X, const BatchStats& hstats,
+                                   const DDiscoverOut& out, const DIndelList& indels, int32_t* d_tile_counter, int32_t* d_flags,
+                                   int num_sms, int* blocks_per_sm_cache, cudaStream_t s, int* n_launches) {
+  (void)d_flags;
+  cudaError_t e = cudaMemsetAsync(d_tile_counter, 0, sizeof(int32_t), s);
+  if (e != cudaSuccess) return e;
+  if (R.n == 0) return cudaSuccess;
+  const int32_t n_tiles = (discover_tiles(hstats) + EV_W / DISC_W - 1) / (EV_W / DISC_W);
+  if (*blocks_per_sm_cache == 0) {
+    e = cudaFuncSetAttribute(k_discover_events, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EvSmem));
+    if (e != cudaSuccess) return e;
+    int b = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_discover_events, EV_THREADS, sizeof(EvSmem));
+    if (e != cudaSuccess) return e;
+    *blocks_per_sm_cache = max(1, b);
+  }
+  const int grid = (int)min((int64_t)n_tiles, (int64_t)num_sms * max(1, *blocks_per_sm_cache));
+  const int32_t min_count = min_obs < 0 ? 0 : min_obs;
+  k_discover_events<<<grid, EV_THREADS, sizeof(EvSmem), s>>>(R, X, thr, min_count, n_tiles, hstats.max_span, out);
+  if (R.n_indel > 0) k_indel_events<<<(unsigned)((R.n_indel + 255) / 256), 256, 0, s>>>(R, indels, thr);
+  if (n_launches) *n_launches += R.n_indel > 0 ? 2 : 1;
   return cudaGetLastError();
 }
 

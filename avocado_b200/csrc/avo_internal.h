@@ -21,6 +21,13 @@ struct DReads {
   const uint8_t* refb;
   int32_t qhead_short;         // 1: only the first two bytes of meta.qhead are valid (6-byte wire form)
   int64_t n_ops, n_refb;       // entries of ops / bytes of refb (bounds of the staged copies)
+  // candidate events (avo_read_events), when the batch carries them: discovery counts these instead of walking
+  int64_t n_snv, n_indel;
+  const int32_t* snv_pos;
+  const uint16_t* snv_pq;
+  const uint32_t* snv_first;
+  const int32_t* indel_read;
+  const uint32_t* indel_op;
 };
 static_assert(sizeof(avo_read_meta) == 32, "avo_read_meta must be one 32-byte sector");
 
@@ -302,7 +309,8 @@ cudaError_t launch_call_blocklist(const DReads& R, const void* joined_list, int3
                                   uint32_t* blk0, cudaStream_t s, int* n_launches);
 cudaError_t launch_call_pairs_reduce(const DReads& R, const DSites& S, const DIndex& X, const DCnv& C, const DCallParams& P,
                                      const DResults& out, const int32_t* rbase, const uint32_t* blen, const uint64_t* boff,
-                                     uint32_t* buckets, size_t n_slots, int num_sms, cudaStream_t s, int* n_launches);
+                                     uint32_t* buckets, size_t n_slots, int num_sms, cudaStream_t s, int* n_launches,
+                                     cudaEvent_t before_pairs = nullptr, cudaEvent_t after_pairs = nullptr);
 cudaError_t launch_call_observe(const DReads& R, const DSites& S, const DCnv& C, const DCallParams& P,
                                 const DResults& out, const int32_t* rbase, const uint32_t* blen,
                                 const uint64_t* boff, uint32_t* buckets, size_t n_slots /* capacity of buckets */,
@@ -370,6 +378,16 @@ struct DIndelList {
 // d_flags: DISC_FLAG_* bits set by the kernels
 enum : int32_t { DISC_FLAG_UNSORTED = 1, DISC_FLAG_BAD_STATS = 2, DISC_FLAG_TABLE_FULL = 4 };
 // verify != 0: every record is checked against hstats and the sort order while it is walked
+// candidate events: count per 32 reads (+ exact bounds, sort order), then write in read order
+cudaError_t launch_events_count(const DReads& R, uint32_t* c_snv, uint32_t* c_ind, BatchStats* d_stats, cudaStream_t s);
+size_t events_scan_temp_bytes(int64_t n);
+cudaError_t launch_events_scan(const uint32_t* counts, uint32_t* first, int64_t n, void* d_temp, size_t temp_bytes, cudaStream_t s);
+cudaError_t launch_events_write(const DReads& R, const uint32_t* snv_first, const uint32_t* ind_first, int64_t snv_cap,
+                                int64_t ind_cap, int32_t* snv_pos, uint16_t* snv_pq, int32_t* indel_read, uint32_t* indel_op,
+                                cudaStream_t s);
+cudaError_t launch_discover_events(const DReads& R, int32_t thr, int32_t min_obs, const DIndex& X, const BatchStats& hstats,
+                                   const DDiscoverOut& out, const DIndelList& indels, int32_t* d_tile_counter, int32_t* d_flags,
+                                   int num_sms, int* blocks_per_sm_cache, cudaStream_t s, int* n_launches);
 cudaError_t launch_discover_tiles(const DReads& R, int32_t thr, int32_t min_obs /* <0: distinct */,
                                   const DIndex& X, const BatchStats& hstats, int verify,
                                   const DDiscoverOut& out, const DIndelList& indels,

@@ -110,6 +110,11 @@ class Context:
         self.lib.avo_get_timing(self.h, C.byref(t))
         return {k: getattr(t, k) for k, _ in L.TimingStruct._fields_}
 
+    # ---- discovery's candidate events ----------------------------------------------------------------
+    def derive_events(self, batch: ReadBatch) -> ReadBatch:
+        """avo_derive_events on this context's GPU (device batches) or on the host (host batches)."""
+        return derive_events(batch, self)
+
     # ---- the packer on the device ---------------------------------------------------------------
     def pack_text_device(self, cols, contig_id=0, keep=None, out=None, source_index=False, prefilter=None) -> ReadBatch:
         """avo_pack_reads_device: text columns (``batch.text_columns`` layout; numpy arrays, ideally
@@ -366,6 +371,47 @@ class Context:
                                   sites.allele_off.copy(), sites.alleles4.copy(), None, sites.count.copy())
             return sites, cols
         raise L.AvocadoError(L.AVO_E_CAPACITY, "discover_and_call output kept growing")
+
+
+def derive_events(batch: ReadBatch, ctx: "Optional[Context]" = None) -> ReadBatch:
+    """avo_derive_events: attaches the candidate events (every mismatching base, every I / D operator after
+    the first aligned one, in read order) to ``batch`` -- in its own memory -- and returns it.  A DEVICE
+    batch that carries them is discovered by counting them (k_discover_events) instead of walking its reads;
+    packers call this once per batch.  Host batches need no context.  Raises AVO_E_UNSORTED for an unsorted
+    batch."""
+    lib = L.load()
+    if batch.on_device and ctx is None:
+        raise ValueError("a device batch needs the Context of its GPU")
+    n_w = (batch.n_reads + 31) // 32
+    dev = ("cuda:%d" % ctx.device) if batch.on_device else None
+    mk = (lambda n, dt: _device_empty(max(n, 1), dt, dev)) if dev else (lambda n, dt: np.zeros(max(n, 1), dt))
+    caps = (batch.n_refb, batch.n_ops)
+    for _ in range(2):
+        arrs = dict(snv_pos=mk(caps[0], np.int32), snv_pq=mk(caps[0], np.uint16), snv_first=mk(n_w + 1, np.uint32),
+                    indel_read=mk(caps[1], np.int32), indel_op=mk(caps[1], np.uint32))
+        e = L.ReadEventsStruct()
+        e.n_snv, e.n_indel = caps
+        for k, a in arrs.items():
+            setattr(e, k, _ptr(a))
+        saved, batch.events = batch.events, None
+        try:
+            bs = batch.as_struct()
+        finally:
+            batch.events = saved
+        rc = lib.avo_derive_events(ctx.h if (ctx is not None and batch.on_device) else None, C.byref(bs), C.byref(e))
+        if rc == L.AVO_E_CAPACITY:
+            caps = (int(e.n_snv), int(e.n_indel))
+            continue
+        if rc != 0:
+            msg = (lib.avo_last_error(ctx.h) or b"").decode() if (ctx is not None and batch.on_device) else "avo_derive_events failed"
+            raise L.AvocadoError(rc, msg)
+        ns, ni = int(e.n_snv), int(e.n_indel)
+        batch.events = dict(snv_pos=arrs["snv_pos"][:max(ns, 1)], snv_pq=arrs["snv_pq"][:max(ns, 1)],
+                            snv_first=arrs["snv_first"], indel_read=arrs["indel_read"][:max(ni, 1)],
+                            indel_op=arrs["indel_op"][:max(ni, 1)], n_snv=ns, n_indel=ni,
+                            stats=(e.stats_min_start, e.stats_max_end, e.stats_max_span))
+        return batch
+    raise L.AvocadoError(L.AVO_E_CAPACITY, "avo_derive_events kept asking for more room")
 
 
 _default_ctx: Dict[int, Context] = {}

@@ -50,6 +50,7 @@ READS_C2 = 25_600_000
 CONTIG_C2 = 64_000_000
 SITE_ROW_BYTES = 208   # SURVEY.md 8(d) B_site at P = 2
 SEED = 0xA70CAD0 + 1
+EVENTS = os.environ.get("AVO_EVENTS", "1") != "0"   # packed batches carry their candidate events (avo_derive_events)
 MIN_MAPQ = 10          # PrefilterReadsArgs.minMappingQuality, the CLI default (applied by the e2e legs that start from text)
 
 
@@ -214,6 +215,9 @@ def config_dict(args, per, contig, world):
                         % (contig / 1e6, per),
             "reads_per_gpu": per, "contig_mb_per_gpu": contig / 1e6, "read_len": 150, "ploidy": 2,
             "min_phred_discover": 25, "min_obs_discover": 5, "parallelism": par,
+            "batch": ("packed batch with its candidate events (avo_derive_events, the packer's last step: 6 B per mismatching base, "
+                      "8 B per I / D operator); discovery counts them (k_discover_events)" if EVENTS
+                      else "packed batch without candidate events: discovery walks the reads (k_discover_tiles)"),
             "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (per * 270 / 1e9)}
 
 
@@ -368,6 +372,8 @@ def main():
     dev = B.synth_device(p, first=first, n=per + halo_lo + halo_hi, device="cuda:%d" % local)
     torch.cuda.synchronize()
     ctx = Context(local)
+    if EVENTS:       # the packer's last step (avo_derive_events): the batch carries discovery's candidate events
+        ctx.derive_events(dev)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
 
@@ -431,11 +437,20 @@ def main():
     ms_disc = statistics.mean(t["ms_discover_tiles"] for t in tim)
     batch_bytes = dev.nbytes()
     peak, peak_src = measured_peak()
-    top, top_ms = ("call_kernels", ms_call) if ms_call >= ms_disc else ("k_discover_tiles", ms_disc)
+    ms_pairs = statistics.mean(t["ms_call_pairs"] for t in tim)
+    disc_name = "k_discover_events" if dev.events is not None else "k_discover_tiles"
+    # the dominant single kernel: the discovery kernel or k_call_pairs (join + observation), each timed by its own events
+    top, top_ms = ("k_call_pairs", ms_pairs) if ms_pairs >= ms_disc else (disc_name, ms_disc)
     small_cols = sum(getattr(dev, c).numel() * getattr(dev, c).element_size() for c in ("meta", "ops", "refb"))
     n_local_sites = n_sites_dev // world
-    alg = small_cols + (n_local_sites * 16 if top == "k_discover_tiles"
-                        else pairs_dev // world * 64 + n_local_sites * SITE_ROW_BYTES)
+    if top == "k_discover_tiles":
+        alg, alg_basis = small_cols + n_local_sites * 16, ("records + operators + mismatch bytes streamed once + 16 B per site "
+                                                           "(about 44 B/read; the payload is only touched at indels): DESIGN.md section 4")
+    elif top == "k_discover_events":
+        alg, alg_basis = dev.events_nbytes() + n_local_sites * 16, "the candidate events streamed once (6 B per mismatching base) + 16 B per site"
+    else:
+        alg, alg_basis = max(pairs_dev, 0) * 80, ("per scored (read, site) pair: the 32-byte record, ~12 B of operators, one 32-byte "
+                                                  "sector holding the payload block, the 4-byte slot (rank 0's pairs)")
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
@@ -450,11 +465,10 @@ def main():
                 "algorithmic_bytes_per_launch": alg, "ms_per_launch": top_ms,
                 "basis": "measured DRAM bytes per launch (profiles/traffic.json, ncu) / CUDA-event time"
                          if traffic is not None else "algorithmic bytes / CUDA-event time",
-                "algorithmic_basis": "records + operators + mismatch bytes streamed once + 16 B per site "
-                                     "(about 44 B/read; the payload is only touched at indels): DESIGN.md section 4",
+                "algorithmic_basis": alg_basis,
                 "whole_step": {"ms": step_ms, "note": "all kernels of the step; its DRAM bytes are in profiles/ (ncu launch list)"},
                 "note": "sparse kernels: latency / issue bound, not bandwidth bound (profiles/README.md)",
-                "other_kernel": {"call_kernels_ms": ms_call, "k_discover_tiles_ms": ms_disc}}
+                "other_kernel": {"call_kernels_ms": ms_call, "k_call_pairs_ms": ms_pairs, disc_name + "_ms": ms_disc}}
     sharding = None
     if pipe is not None:
         for _ in range(2):                      # outside the timed region: where a step's time goes, per phase
@@ -584,6 +598,8 @@ def run_e2e(args, np, torch, B, Context, own, per, local, world, rank, cpus_per_
             for i in range(t, n_text_bins, T):
                 pb = ctxs[t].pack_text_device(tcols[i], out=reuse[t], prefilter=pf)
                 tp = ctxs[t].timing()
+                if EVENTS:
+                    ctxs[t].derive_events(pb)
                 s_i, c_i = ctxs[t].discover_and_call_packed(pb, ploidy=2, phred=25, min_obs=5, capacity=site_cap, copy=False)
                 st = np.asarray(s_i.start[:s_i.n], np.int64)
                 out[-1].append((pb.n_reads, int(((st >= shards[i].lo) & (st < shards[i].hi)).sum()), tp, ctxs[t].timing()))
@@ -725,6 +741,8 @@ def run_wgs(args):
     for b in range(n_batches):
         p = B.synth_params(seed=SEED + 17 * b, contig_len=contig, n_reads_total=per, sample=0)
         batches.append(B.synth_device(p, device="cuda:%d" % local))
+        if EVENTS:
+            ctx.derive_events(batches[-1])
     torch.cuda.synchronize()
     site_cap = max(1 << 18, per // 128)
 

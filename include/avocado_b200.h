@@ -157,6 +157,27 @@ typedef struct {
   uint32_t reserved;
 } avo_wire_exception;
 
+/* Discovery's per-read candidate events, a by-product of packing (DiscoverVariants.variantsInRead,
+ * DiscoverVariants.scala:112-252, is a walk over the operators extractAlignmentOperators produced): every
+ * mismatching base as (reference position, (reference base << 4 | read base) << 8 | the quality the
+ * reference tests, qual(i) with i counted inside the mismatch run) and every I / D operator after the read's
+ * first aligned base as (read, operator index), in read order.  avo_derive_events fills them from a packed
+ * batch (device batches: three kernels; host batches: a loop); a DEVICE batch that carries them
+ * (avo_read_batch.events) is discovered by counting events -- a coalesced stream of 6 bytes per mismatching
+ * base -- instead of walking 25 M reads (k_discover_events instead of k_discover_tiles).  `snv_first[w]` is
+ * the first SNV event of read 32 w (the index the tiles use).  The deriving pass also measures the exact
+ * bounds and checks the sort order (AVO_E_UNSORTED), so a batch with events needs no stats hints. */
+typedef struct {
+  int64_t n_snv;          /* in (avo_derive_events): capacity of snv_pos / snv_pq (n_refb always suffices); out: events */
+  int64_t n_indel;        /* in: capacity of indel_read / indel_op (n_ops always suffices); out: events */
+  int32_t* snv_pos;
+  uint16_t* snv_pq;
+  uint32_t* snv_first;    /* [(n_reads + 31) / 32 + 1] */
+  int32_t* indel_read;
+  uint32_t* indel_op;
+  avo_batch_stats stats;  /* out: exact bounds of the batch (valid = 1) */
+} avo_read_events;
+
 /* One batch = reads of ONE contig, sorted by start (ties in any order; the order of the batch is
  * the canonical summation order). */
 typedef struct {
@@ -185,7 +206,13 @@ typedef struct {
   int64_t n_wire6_exc;
   int32_t wire6_base;                   /* start of the first read minus its stored difference */
   int32_t reserved;
+  const avo_read_events* events;        /* optional (AVO_MEM_DEVICE batches; ignored otherwise): avo_derive_events */
 } avo_read_batch;
+
+/* Fills `events` (arrays in the batch's memory: device arrays for a device batch, host arrays for a host
+ * batch in the full form -- `ctx` may then be NULL) from the packed columns.  Waits for the device (the
+ * counts come back). */
+int avo_derive_events(avo_ctx* ctx, const avo_read_batch* reads, avo_read_events* events);
 
 /* Variant sites, sorted by (contig, start, start + ref_len); unique.  Replaces the Variant
  * fields read by DiscoveredVariant.apply (DiscoveredVariant.scala:32-37); end == start + ref_len. */
@@ -294,7 +321,7 @@ typedef struct {
   int64_t d2h_bytes;
   int32_t payload_in_place; /* 1: the payload was read from pinned host memory, not copied; 2: and the call
                                stage's blocks were gathered on the host */
-  int32_t reserved;
+  float ms_call_pairs;      /* of ms_call_tiles: k_call_pairs alone (join + observation; 0 on the host-gathered route) */
   int64_t gathered_blocks;  /* host_payload == 2: 16-byte blocks gathered on the host */
 } avo_timing;
 int avo_get_timing(const avo_ctx* ctx, avo_timing* out);

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(L.EXPORTED_SYMBOLS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert C.sizeof(L.ReadBatchStruct) == 4 * 8 + 2 * 4 + 4 * 4 + 6 * 8 + 5 * 8 + 2 * 4
+    assert C.sizeof(L.ReadBatchStruct) == 4 * 8 + 2 * 4 + 4 * 4 + 6 * 8 + 5 * 8 + 2 * 4 + 8
 
 
 @pytest.mark.parametrize("name", FIXTURES)
@@ -148,6 +148,48 @@ def test_narrow_text_columns_keep_an_absent_mapq_absent():
     assert 0 < wide.n_reads < 40
     _same_batch(wide, slim)
     assert np.array_equal(wide.source_index, slim.source_index)
+
+
+def test_host_events_are_the_walk_of_the_operators():
+    """avo_derive_events on a host batch (no device needed) against the per-read walk of DiscoverVariants.scala:112-252
+    written out in Python: every mismatching base with the quality qual(i) the reference tests, every I / D operator
+    after the first aligned one, in read order; snv_first indexes every 32nd read; exact bounds."""
+    from avocado_b200 import batch as B
+    from avocado_b200.genotyping import derive_events
+    p = B.synth_params(seed=5, n_reads_total=6000, contig_len=30000, first_pos=100, indel_rate=2e-3, softclip_frac=0.1)
+    b = derive_events(B.synth_host(p))
+    ev, m = b.events, b.meta
+    pos_l, pq_l, ind, first = [], [], [], []
+    for r in range(b.n_reads):
+        if r % 32 == 0:
+            first.append(len(pos_l))
+        pos, rb, ff, qh = int(m["start"][r]), int(m["refb_off"][r]), True, int(m["qhead"][r])
+        for k in range(int(m["n_ops"][r])):
+            op = int(b.ops[int(m["op_off"][r]) + k])
+            ln, code = op >> 4, op & 15
+            if code == 1:
+                for i in range(ln):
+                    q = (qh >> (8 * i)) & 255 if i < 4 else int(b.payload[(int(m["seq_off"][r]) + i // 10) * 16 + 5 + i % 10])
+                    pos_l.append(pos + i)
+                    pq_l.append((int(b.refb[rb + i]) << 8) | q)
+            if code in (2, 3) and not ff:
+                ind.append((r, k))
+            if code in (0, 1, 3):
+                pos += ln
+            rb += ln if code == 1 else (ln + 1) // 2 if code == 3 else 0
+            if code <= 1:
+                ff = False
+    first.append(len(pos_l))
+    assert (ev["n_snv"], ev["n_indel"]) == (len(pos_l), len(ind)) and len(ind) > 100 and len(pos_l) > 1000
+    assert np.array_equal(ev["snv_pos"][:len(pos_l)], np.array(pos_l, np.int32))
+    assert np.array_equal(ev["snv_pq"][:len(pq_l)], np.array(pq_l, np.uint16))
+    assert np.array_equal(ev["snv_first"], np.array(first, np.uint32))
+    assert [(int(x), int(y)) for x, y in zip(ev["indel_read"][:len(ind)], ev["indel_op"][:len(ind)])] == ind
+    st, en = m["start"].astype(np.int64), m["end"].astype(np.int64)
+    assert tuple(ev["stats"]) == (int(st.min()), int(en.max()), int((en - st).max()))
+    b.meta["start"][100] -= 1000
+    with pytest.raises(Exception):
+        derive_events(b)
 
 
 def test_threaded_packer_matches_serial_on_the_reference_fixtures():
@@ -282,7 +324,7 @@ def test_ctypes_mirrors_have_the_sizes_of_the_c_structs(tmp_path):
         "avo_filter_out": L.FilterOutStruct, "avo_sample_rows": L.SampleRowsStruct, "avo_square_out": L.SquareOutStruct,
         "avo_trio": L.TrioStruct, "avo_joint_in": L.JointInStruct, "avo_joint_out": L.JointOutStruct,
         "avo_synth_params": L.SynthParamsStruct, "avo_depths_in": L.DepthsInStruct, "avo_site_depths": L.SiteDepthsStruct,
-        "avo_shard_plan": L.ShardPlanStruct,
+        "avo_shard_plan": L.ShardPlanStruct, "avo_read_events": L.ReadEventsStruct,
     }
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "avocado_b200.h"\n#include "avocado_b200_synth.h"\nint main(void) {\n' +

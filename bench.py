@@ -335,6 +335,30 @@ class ReadBatchPinned:
         return batch.with_wire6(alloc) or batch.with_wire(alloc)
 
 
+NEAR_CPUS = None
+
+
+def bind_near_gpu(torch, local):
+    """One process per GPU: run on the cores next to that GPU (NVML's CPU affinity), so that the page-locked buffers
+    this rank allocates -- first touch -- live in the memory its GPU reads over the shortest path.  What
+    `numactl --cpunodebind` / an executor's core binding does in a deployment; best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%08x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def main():
     claim_stdout()
     args = parse_args()
@@ -354,6 +378,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     use_dist = world > 1
+    global NEAR_CPUS
+    NEAR_CPUS = bind_near_gpu(torch, local) if (use_dist and os.environ.get("AVO_BIND", "1") != "0") else None
     if use_dist:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -667,6 +693,7 @@ def run_e2e(args, np, torch, B, Context, own, per, local, world, rank, cpus_per_
     e2e = {"value": n_text * world / (ms_t / 1e3), "unit": "reads/s", "ms_per_step": ms_t,
            "h2d_bytes_per_step": int(sum(x[2]["h2d_bytes"] + x[3]["h2d_bytes"] for x in last)) * world,
            "d2h_bytes_per_step": int(sum(x[3]["d2h_bytes"] for x in last)) * world,
+           "cpus_bound_to": ("%d cores next to the GPU (NVML affinity)" % len(NEAR_CPUS)) if NEAR_CPUS else "all",
            "input": "AlignmentRecord text columns (CIGAR, MD, sequence, phred+33 qualities) in pinned host memory",
            "reads_per_step_per_gpu": n_text, "reads_kept_by_prefilter": kept_reads, "sites_called_per_gpu": owned_sites,
            "region_bins": n_text_bins, "of_bins": K, "host_threads": T,

@@ -34,7 +34,21 @@ static void set_lng(JNIEnv* e, jobject holder, const char* field, jlong v) {
  * on the host.  The two wire forms are alternatives: the 6-byte records go with THEIR operator columns
  * (wire6 + wire6Oplen + wire6Opcode [+ wire6Exc]), the 16-byte records with the 16-bit operators
  * (wireMeta + wireOps); validate_reads refuses a mix. */
-static void read_batch(JNIEnv* e, jobject jr, avo_read_batch* r) {
+/* ReadEvents holder <-> avo_read_events (the arrays live where the batch lives; nSnv / nIndel: capacities in, counts out) */
+static void events_in(JNIEnv* e, jobject je, avo_read_events* v) {
+  v->n_snv = lng(e, je, "nSnv"); v->n_indel = lng(e, je, "nIndel");
+  v->snv_pos = (int32_t*)buf(e, je, "snvPos"); v->snv_pq = (uint16_t*)buf(e, je, "snvPq");
+  v->snv_first = (uint32_t*)buf(e, je, "snvFirst");
+  v->indel_read = (int32_t*)buf(e, je, "indelRead"); v->indel_op = (uint32_t*)buf(e, je, "indelOp");
+  v->stats.min_start = num(e, je, "minStart"); v->stats.max_end = num(e, je, "maxEnd"); v->stats.max_span = num(e, je, "maxSpan");
+  v->stats.valid = num(e, je, "statsValid");
+}
+
+/* `ev`: storage for the batch's candidate events when its holder carries a ReadEvents (PackedBatch.events) */
+static void read_batch(JNIEnv* e, jobject jr, avo_read_batch* r, avo_read_events* ev) {
+  jobject je = (*e)->GetObjectField(e, jr, (*e)->GetFieldID(e, (*e)->GetObjectClass(e, jr), "events",
+                                                             "Lorg/bdgenomics/avocado/nativelib/ReadEvents;"));
+  if (je && ev) { events_in(e, je, ev); r->events = ev; }
   r->n_reads = lng(e, jr, "nReads"); r->n_blocks = lng(e, jr, "nBlocks");
   r->n_ops = lng(e, jr, "nOps"); r->n_refb = lng(e, jr, "nRefb");
   r->contig_id = num(e, jr, "contigId");
@@ -122,9 +136,10 @@ JNIEXPORT jstring JNICALL Java_org_bdgenomics_avocado_nativelib_AvocadoB200_last
 JNIEXPORT jint JNICALL Java_org_bdgenomics_avocado_nativelib_AvocadoB200_discover(
     JNIEnv* e, jclass k, jlong ctx, jobject jr, jint minPhred, jint minObs, jobject js) {
   avo_read_batch r = {0};
+  avo_read_events ev = {0};
   avo_sites_out s = {0};
   (void)k;
-  read_batch(e, jr, &r);
+  read_batch(e, jr, &r, &ev);
   sites_out(e, js, &s);
   avo_params p = params(2, 93, 93, minPhred, minObs);
   const int rc = avo_discover((avo_ctx*)(intptr_t)ctx, &r, &p, &s);
@@ -136,11 +151,12 @@ JNIEXPORT jint JNICALL Java_org_bdgenomics_avocado_nativelib_AvocadoB200_discove
 JNIEXPORT jint JNICALL Java_org_bdgenomics_avocado_nativelib_AvocadoB200_call(
     JNIEnv* e, jclass k, jlong ctx, jobject jr, jobject js, jobject jc, jint ploidy, jint maxQ, jint maxMapQ, jobject jo) {
   avo_read_batch r = {0};
+  avo_read_events ev = {0};
   avo_sites s = {0};
   avo_cnv c = {0};
   avo_site_results o = {0};
   (void)k;
-  read_batch(e, jr, &r);
+  read_batch(e, jr, &r, &ev);
   sites_in(e, js, &s);
   if (jc) cnv_in(e, jc, &c);
   results(e, jo, &o);
@@ -153,11 +169,12 @@ JNIEXPORT jint JNICALL Java_org_bdgenomics_avocado_nativelib_AvocadoB200_discove
     JNIEnv* e, jclass k, jlong ctx, jobject jr, jobject jc, jint ploidy, jint maxQ, jint maxMapQ, jint minPhred, jint minObs,
     jobject js, jobject jo) {
   avo_read_batch r = {0};
+  avo_read_events ev = {0};
   avo_cnv c = {0};
   avo_sites_out s = {0};
   avo_site_results o = {0};
   (void)k;
-  read_batch(e, jr, &r);
+  read_batch(e, jr, &r, &ev);
   if (jc) cnv_in(e, jc, &c);
   sites_out(e, js, &s);
   results(e, jo, &o);
@@ -165,6 +182,26 @@ JNIEXPORT jint JNICALL Java_org_bdgenomics_avocado_nativelib_AvocadoB200_discove
   const int rc = avo_discover_and_call((avo_ctx*)(intptr_t)ctx, &r, jc ? &c : NULL, &p, &s, &o);
   set_lng(e, js, "n", s.n); set_lng(e, js, "nAlleleNibbles", s.n_allele_nibbles);
   set_lng(e, jo, "nSites", o.n_sites);
+  return rc;
+}
+
+/* avo_derive_events: a packer's last step for a batch that will be genotyped more than once */
+JNIEXPORT jint JNICALL Java_org_bdgenomics_avocado_nativelib_AvocadoB200_deriveEvents(JNIEnv* e, jclass k, jlong ctx, jobject jr,
+                                                                                     jobject jevents) {
+  avo_read_batch r = {0};
+  avo_read_events out = {0};
+  (void)k;
+  read_batch(e, jr, &r, NULL);
+  events_in(e, jevents, &out);
+  const int rc = avo_derive_events((avo_ctx*)(intptr_t)ctx, &r, &out);
+  set_lng(e, jevents, "nSnv", out.n_snv); set_lng(e, jevents, "nIndel", out.n_indel);
+  if (rc == AVO_OK) {
+    jclass c = (*e)->GetObjectClass(e, jevents);
+    (*e)->SetIntField(e, jevents, (*e)->GetFieldID(e, c, "minStart", "I"), out.stats.min_start);
+    (*e)->SetIntField(e, jevents, (*e)->GetFieldID(e, c, "maxEnd", "I"), out.stats.max_end);
+    (*e)->SetIntField(e, jevents, (*e)->GetFieldID(e, c, "maxSpan", "I"), out.stats.max_span);
+    (*e)->SetIntField(e, jevents, (*e)->GetFieldID(e, c, "statsValid", "I"), 1);
+  }
   return rc;
 }
 
@@ -179,9 +216,10 @@ static void plan_in(JNIEnv* e, jobject jp, avo_shard_plan* p) {
 JNIEXPORT jint JNICALL Java_org_bdgenomics_avocado_nativelib_AvocadoB200_shardDiscover(
     JNIEnv* e, jclass k, jlong ctx, jobject jr, jint ploidy, jint minPhred, jint minObs, jobject jp, jlong tableBlockDevicePtr) {
   avo_read_batch r = {0};
+  avo_read_events ev = {0};
   avo_shard_plan pl = {0};
   (void)k;
-  read_batch(e, jr, &r);
+  read_batch(e, jr, &r, &ev);
   plan_in(e, jp, &pl);
   avo_params p = params(ploidy, 93, 93, minPhred, minObs);
   return avo_shard_discover((avo_ctx*)(intptr_t)ctx, &r, &p, &pl, (void*)(intptr_t)tableBlockDevicePtr);

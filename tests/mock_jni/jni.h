@@ -23,6 +23,7 @@ struct JNINativeInterface_ {
   jint (*GetIntField)(JNIEnv*, jobject, jfieldID);
   jlong (*GetLongField)(JNIEnv*, jobject, jfieldID);
   void (*SetLongField)(JNIEnv*, jobject, jfieldID, jlong);
+  void (*SetIntField)(JNIEnv*, jobject, jfieldID, jint);
   void* (*GetDirectBufferAddress)(JNIEnv*, jobject);
   jlong (*GetDirectBufferCapacity)(JNIEnv*, jobject);
   jstring (*NewStringUTF)(JNIEnv*, const char*);

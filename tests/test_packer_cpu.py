@@ -150,6 +150,54 @@ def test_narrow_text_columns_keep_an_absent_mapq_absent():
     assert np.array_equal(wide.source_index, slim.source_index)
 
 
+def _walk_events(b):
+    """DiscoverVariants.scala:112-252 per read, in Python, over a packed host batch -> (positions, pq words, indel events, first)."""
+    m = b.meta
+    pos_l, pq_l, ind, first = [], [], [], []
+    for r in range(b.n_reads):
+        if r % 32 == 0:
+            first.append(len(pos_l))
+        pos, rb, ff, qh = int(m["start"][r]), int(m["refb_off"][r]), True, int(m["qhead"][r])
+        for k in range(int(m["n_ops"][r])):
+            op = int(b.ops[int(m["op_off"][r]) + k])
+            ln, code = op >> 4, op & 15
+            if code == 1:
+                for i in range(ln):
+                    q = (qh >> (8 * i)) & 255 if i < 4 else int(b.payload[(int(m["seq_off"][r]) + i // 10) * 16 + 5 + i % 10])
+                    pos_l.append(pos + i)
+                    pq_l.append((int(b.refb[rb + i]) << 8) | q)
+            if code in (2, 3) and not ff:
+                ind.append((r, k))
+            if code in (0, 1, 3):
+                pos += ln
+            rb += ln if code == 1 else (ln + 1) // 2 if code == 3 else 0
+            if code <= 1:
+                ff = False
+    first.append(len(pos_l))
+    return pos_l, pq_l, ind, first
+
+
+def test_host_events_of_messy_reads_and_of_an_empty_batch():
+    """Fuzzed operator mixes (mismatch runs longer than the four head qualities, insertions before the first aligned base,
+    reads without operators) and the empty batch."""
+    from avocado_b200 import batch as B
+    from avocado_b200.genotyping import derive_events
+    from helpers import fuzz_records
+    recs = [r for r in fuzz_records(77, 3000) if r.readMapped]
+    b = derive_events(B.pack_reads(recs, sort=True))
+    pos_l, pq_l, ind, first = _walk_events(b)
+    ev = b.events
+    assert (ev["n_snv"], ev["n_indel"]) == (len(pos_l), len(ind)) and len(pos_l) > 500 and len(ind) > 50
+    assert np.array_equal(ev["snv_pos"][:len(pos_l)], np.array(pos_l, np.int32))
+    assert np.array_equal(ev["snv_pq"][:len(pq_l)], np.array(pq_l, np.uint16))
+    assert np.array_equal(ev["snv_first"], np.array(first, np.uint32))
+    assert [(int(x), int(y)) for x, y in zip(ev["indel_read"][:len(ind)], ev["indel_op"][:len(ind)])] == ind
+    ops = [int(b.ops[int(b.meta["op_off"][r]) + k]) for r in range(b.n_reads) for k in range(int(b.meta["n_ops"][r]))]
+    assert max(o >> 4 for o in ops if o & 15 == 1) > 4 and (b.meta["n_ops"] == 0).any()
+    empty = derive_events(B.pack_reads([]))
+    assert (empty.events["n_snv"], empty.events["n_indel"]) == (0, 0) and int(empty.events["snv_first"][0]) == 0
+
+
 def test_host_events_are_the_walk_of_the_operators():
     """avo_derive_events on a host batch (no device needed) against the per-read walk of DiscoverVariants.scala:112-252
     written out in Python: every mismatching base with the quality qual(i) the reference tests, every I / D operator

@@ -22,3 +22,26 @@ def test_oracle_generator_reproduces_the_product_generator(oracle):
         assert oracle.read_as_dict(rs, i) == oracle.read_as_dict(rs2, i)
     # the text reads discover the same sites with any thread count
     assert oracle.discover(rs, 25, 5, 1) == oracle.discover(rs2, 25, 5, 3)
+
+
+def test_reference_arm_of_the_bench_runs_without_the_product_library():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm): one JSON line with the
+    contract's keys, produced by a process that never maps libavocado_b200.so or imports torch."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', "
+            "'--cpu-sample', '20000']; runpy.run_path(%r, run_name='__main__'); "
+            "maps = open('/proc/self/maps').read(); "
+            "sys.stderr.write('LOADED_PRODUCT=%%d TORCH=%%d\\n' %% ('libavocado_b200' in maps, 'torch' in sys.modules))"
+            % os.path.join(root, "bench.py"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "reads/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
+    assert "LOADED_PRODUCT=0 TORCH=0" in r.stderr, r.stderr[-500:]

@@ -163,8 +163,12 @@ class ReadBatch:
             s.wire6_exc = _ptr(self.wire6_exc) if len(self.wire6_exc) else None
             s.n_wire6_exc, s.wire6_base = len(self.wire6_exc), self.wire6_base
         if self.events is not None:
-            e = self._events_struct = self.events_struct()       # (kept alive with the batch)
-            s.events = C.cast(C.pointer(e), C.c_void_p)
+            # one struct per events dict, kept alive with the batch: a caller may cache the batch struct
+            # (ShardedPipeline does) while other calls build theirs
+            held = self.__dict__.get("_events_struct")
+            if held is None or held[0] is not self.events:
+                held = self._events_struct = (self.events, self.events_struct())
+            s.events = C.cast(C.pointer(held[1]), C.c_void_p)
         return s
 
     def events_struct(self):

@@ -538,6 +538,16 @@ def main():
                 "whole_step": {"ms": step_ms, "note": "all kernels of the step; its DRAM bytes are in profiles/ (ncu launch list)"},
                 "note": "sparse kernels: latency / issue bound, not bandwidth bound (profiles/README.md)",
                 "other_kernel": {"call_kernels_ms": ms_call, "k_call_pairs_ms": ms_pairs, disc_name + "_ms": ms_disc}}
+    try:        # the other large kernel, for the reader who wants both fractions on one line
+        other = "k_call_pairs" if top != "k_call_pairs" else disc_name
+        other_ms = ms_pairs if other == "k_call_pairs" else ms_disc
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tj2 = json.load(fh)[other]
+        tr2 = tj2["dram_bytes"] * (dev.n_reads / tj2["reads"])
+        roofline["second_kernel"] = {"kernel": other, "ms_per_launch": other_ms, "traffic": int(tr2),
+                                     "achieved": tr2 / (other_ms / 1e3) / 1e9, "frac": tr2 / (other_ms / 1e3) / 1e9 / peak}
+    except Exception:
+        pass
     sharding = None
     if pipe is not None:
         for _ in range(2):                      # outside the timed region: where a step's time goes, per phase
